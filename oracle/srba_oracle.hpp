@@ -1489,8 +1489,12 @@ struct Engine {
 						const pose_t *pose_base_wrt_remote = observer_is_near_to ? (pose_base_wrt_from ? pose_base_wrt_from : &default_identity_pose)
 						                                                         : (pose_base_wrt_to ? pose_base_wrt_to : &default_identity_pose);
 						const pose_t pose_local_wrt_remote = ((*pose_base_wrt_remote) + (pose_new_kf_wrt_old_kf)) + (-(*pose_observer_wrt_local));
+#ifdef ORC_EXPERIMENT_FIX_LC_INIT
+						if (observer_is_near_to) nei_edge.inv_pose = -pose_local_wrt_remote; else nei_edge.inv_pose = pose_local_wrt_remote;
+#else
 						if (edge_dir_to_newkf) nei_edge.inv_pose = -pose_local_wrt_remote;
 						else nei_edge.inv_pose = pose_local_wrt_remote;
+#endif
 					}
 				}
 			}

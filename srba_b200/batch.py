@@ -1,0 +1,70 @@
+"""Staged batch API (include/srba_b200.h): pack -> one H2D copy -> persistent LM kernel -> one D2H copy."""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as K
+from ._capi import lib
+from .engine import ResultBuffers
+
+
+class Batch:
+    def __init__(self, flats, trace_cap=0, want_dense=False):
+        self.L = lib()
+        self.flats = list(flats)
+        n = len(self.flats)
+        arr = (C.POINTER(K.Problem) * n)(*[f.problem for f in self.flats])
+        tc = -max(trace_cap, 1) if want_dense else trace_cap
+        self.trace_cap, self.want_dense = trace_cap, want_dense
+        self.h = self.L.srba_b200_batch_create(n, arr, tc)
+        if not self.h:
+            raise K.SrbaError(-1, self.L.srba_b200_last_error().decode())
+        self.n = n
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.srba_b200_batch_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != K.SRBA_OK:
+            raise K.SrbaError(rc, self.L.srba_b200_last_error().decode())
+
+    def upload(self, stream=0):
+        self._chk(self.L.srba_b200_batch_upload(self.h, C.c_void_p(stream)))
+
+    def run(self, stream=0):
+        self._chk(self.L.srba_b200_batch_run(self.h, C.c_void_p(stream)))
+
+    def download(self, stream=0):
+        self._chk(self.L.srba_b200_batch_download(self.h, C.c_void_p(stream)))
+
+    def unpack(self, i):
+        res = ResultBuffers(self.flats[i].p, self.trace_cap, self.want_dense)
+        self._chk(self.L.srba_b200_batch_unpack(self.h, i, C.byref(res.r)))
+        return res
+
+    def stats(self, i):
+        r = K.Result()
+        self.L.srba_b200_batch_unpack(self.h, i, C.byref(r))
+        return r.stats.as_dict()
+
+    @property
+    def h2d_bytes(self):
+        return self.L.srba_b200_batch_h2d_bytes(self.h)
+
+    @property
+    def d2h_bytes(self):
+        return self.L.srba_b200_batch_d2h_bytes(self.h)
+
+    @property
+    def kernel_launches(self):
+        return self.L.srba_b200_batch_kernel_launches(self.h)
+
+    def algorithmic_bytes(self):
+        out = np.zeros(5)
+        self.L.srba_b200_batch_algorithmic_bytes(self.h, out.ctypes.data_as(C.POINTER(C.c_double)))
+        return dict(B_chain=out[0], B_assem=out[1], B_schur=out[2], B_chol=out[3], F_chol=out[4])

@@ -1,0 +1,1101 @@
+// B200-native (sm_100a) Levenberg–Marquardt local-area optimiser: one persistent CTA ("team") per flattened
+// optimize_edges() problem, the WHOLE LM loop of MRPT/srba's impl/optimize_edges.h:245-751 on the device:
+//   numeric spanning tree (impl/spantree_update_numeric.h:19-81) -> Jacobians (impl/jacobians.h:207-354,363-494,
+//   644-744,888-1013; models/sensors.h) -> block-sparse Hessian H_Ap/H_f/H_Apf (impl/sparse_hessian_update_numeric.h:
+//   22-60) -> gradient (impl/compute_minus_gradient.h:20-91) -> Schur complement (impl/schur.h:180-311) -> dense
+//   Cholesky + back-substitution (impl/lev-marq_solvers.h:474-568) -> manifold update / accept / reject / relinearise
+//   (impl/optimize_edges.h:454-696).
+// Inputs are read once from the packed image in HBM, every intermediate lives in a per-problem workspace that stays
+// L1/L2-resident for the kernel's lifetime, results are written once.  All arithmetic is FP64 (the reference's).
+// Hessian blocks are GATHERED: each (block,element) is owned by one thread that walks the block's term list in
+// ascending observation order == the reference's summation order, so results are deterministic and differ from the
+// CPU path only by FMA contraction.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "dev_types.h"
+
+#define LM_THREADS 256
+#define MAXO 4
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ pose algebra
+__device__ __forceinline__ double wrapTo2Pi(double a) {  // mrpt::math::wrapTo2Pi
+	const bool was_neg = a < 0;
+	a = fmod(a, 2.0 * M_PI);
+	if (was_neg) a += 2.0 * M_PI;
+	return a;
+}
+__device__ __forceinline__ double wrapToPi(double a) { return wrapTo2Pi(a + M_PI) - M_PI; }
+
+template <int P>
+struct PoseOps;
+
+template <>
+struct PoseOps<3> {  // CPose2D: x,y,phi
+	static constexpr int S = 3;
+	__device__ static void identity(double *p) { p[0] = 0; p[1] = 0; p[2] = 0; }
+	__device__ static void compose(double *o, const double *a, const double *b) {
+		double s, c;
+		sincos(a[2], &s, &c);
+		const double nx = a[0] + b[0] * c - b[1] * s;
+		const double ny = a[1] + b[0] * s + b[1] * c;
+		const double nphi = wrapToPi(a[2] + b[2]);
+		o[0] = nx; o[1] = ny; o[2] = nphi;
+	}
+	__device__ static void inverse(double *o, const double *a) {
+		double s, c;
+		sincos(a[2], &s, &c);
+		const double x = a[0], y = a[1];
+		o[0] = -x * c - y * s;
+		o[1] = x * s - y * c;
+		o[2] = -a[2];
+	}
+	__device__ static void pseudo_exp(double *o, const double *v) { o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; }
+};
+
+template <>
+struct PoseOps<6> {  // CPose3D: R row-major (9) + t (3)
+	static constexpr int S = 12;
+	__device__ static void identity(double *p) {
+		p[0] = 1; p[1] = 0; p[2] = 0; p[3] = 0; p[4] = 1; p[5] = 0; p[6] = 0; p[7] = 0; p[8] = 1; p[9] = 0; p[10] = 0; p[11] = 0;
+	}
+	__device__ static void compose(double *o, const double *a, const double *b) {
+		double t[12];
+#pragma unroll
+		for (int r = 0; r < 3; r++) t[9 + r] = a[9 + r] + a[3 * r + 0] * b[9] + a[3 * r + 1] * b[10] + a[3 * r + 2] * b[11];
+#pragma unroll
+		for (int r = 0; r < 3; r++)
+#pragma unroll
+			for (int c = 0; c < 3; c++) t[3 * r + c] = a[3 * r + 0] * b[c] + a[3 * r + 1] * b[3 + c] + a[3 * r + 2] * b[6 + c];
+#pragma unroll
+		for (int i = 0; i < 12; i++) o[i] = t[i];
+	}
+	__device__ static void inverse(double *o, const double *a) {
+		double t[12];
+#pragma unroll
+		for (int r = 0; r < 3; r++)
+#pragma unroll
+			for (int c = 0; c < 3; c++) t[3 * r + c] = a[3 * c + r];
+#pragma unroll
+		for (int r = 0; r < 3; r++) t[9 + r] = -(t[3 * r + 0] * a[9] + t[3 * r + 1] * a[10] + t[3 * r + 2] * a[11]);
+#pragma unroll
+		for (int i = 0; i < 12; i++) o[i] = t[i];
+	}
+	// CPose3D::exp(v, pseudo_exponential=true): t copied, R = Rodrigues(w) with MRPT's small-angle series.
+	__device__ static void pseudo_exp(double *o, const double *v) {
+		o[9] = v[0]; o[10] = v[1]; o[11] = v[2];
+		const double w0 = v[3], w1 = v[4], w2 = v[5];
+		const double theta_sq = w0 * w0 + w1 * w1 + w2 * w2;
+		const double theta = sqrt(theta_sq);
+		double A, B;
+		if (theta_sq < 1e-8) { A = 1.0 - theta_sq / 6.0; B = 0.5; }
+		else if (theta_sq < 1e-6) { B = 0.5 - 0.25 * (1.0 / 6.0) * theta_sq; A = 1.0 - theta_sq * (1.0 / 6.0) * (1.0 - (1.0 / 20.0) * theta_sq); }
+		else { const double inv_theta = 1.0 / theta; A = sin(theta) * inv_theta; B = (1 - cos(theta)) * (inv_theta * inv_theta); }
+		const double wx2 = w0 * w0, wy2 = w1 * w1, wz2 = w2 * w2;
+		o[0] = 1.0 - B * (wy2 + wz2);
+		o[4] = 1.0 - B * (wx2 + wz2);
+		o[8] = 1.0 - B * (wx2 + wy2);
+		{ const double a = A * w2, b = B * (w0 * w1); o[1] = b - a; o[3] = b + a; }
+		{ const double a = A * w1, b = B * (w0 * w2); o[2] = b + a; o[6] = b - a; }
+		{ const double a = A * w0, b = B * (w1 * w2); o[5] = b - a; o[7] = b + a; }
+	}
+};
+
+__device__ __forceinline__ void compose_point3(const double *P, const double *l, double *g) {
+	const double x = P[0] * l[0] + P[1] * l[1] + P[2] * l[2] + P[9];
+	const double y = P[3] * l[0] + P[4] * l[1] + P[5] * l[2] + P[10];
+	const double z = P[6] * l[0] + P[7] * l[1] + P[8] * l[2] + P[11];
+	g[0] = x; g[1] = y; g[2] = z;
+}
+__device__ __forceinline__ void inverse_compose_point3(const double *P, const double *g, double *l) {
+	const double dx = g[0] - P[9], dy = g[1] - P[10], dz = g[2] - P[11];
+	const double x = P[0] * dx + P[3] * dy + P[6] * dz;
+	const double y = P[1] * dx + P[4] * dy + P[7] * dz;
+	const double z = P[2] * dx + P[5] * dy + P[8] * dz;
+	l[0] = x; l[1] = y; l[2] = z;
+}
+// C(n x m) = A(n x k) * B(k x m), row-major, left-to-right accumulation like the CPU restatement
+template <int N, int K, int M>
+__device__ __forceinline__ void matmul(double *C, const double *A, const double *B) {
+#pragma unroll
+	for (int r = 0; r < N; r++)
+#pragma unroll
+		for (int c = 0; c < M; c++) {
+			double s = 0;
+#pragma unroll
+			for (int t = 0; t < K; t++) s += A[r * K + t] * B[t * M + c];
+			C[r * M + c] = s;
+		}
+}
+
+template <int OBSK> struct ObsDims;
+template <> struct ObsDims<SRBA_OBS_RELPOSES2D> { static constexpr int O = 3; };
+template <> struct ObsDims<SRBA_OBS_CARTESIAN3D> { static constexpr int O = 3; };
+template <> struct ObsDims<SRBA_OBS_MONO> { static constexpr int O = 2; };
+template <> struct ObsDims<SRBA_OBS_STEREO> { static constexpr int O = 4; };
+
+// ------------------------------------------------------------------------------------------------ views
+struct View {
+	const DevProblem *h;
+	// inputs
+	const double *edge_pose, *lm_pos, *obs_z;
+	const int32_t *unk_edge, *unk_lm, *pair_path_ptr, *path_edge, *obs_slot, *obs_lm, *obs_mult;
+	const uint8_t *path_dir, *blkA_normal_dir;
+	const int32_t *colA_ptr, *blkA_obs, *blkA_col, *blkA_slotA, *blkA_slotD, *colF_ptr, *blkF_obs, *blkF_col, *blkF_slot;
+	const int32_t *row_ptr, *row_blk;
+	const int32_t *HAp_row, *HAp_col, *HAp_term_ptr, *HAp_term_a, *HAp_term_b;
+	const int32_t *HApf_row, *HApf_col, *HApf_term_ptr, *HApf_term_a, *HApf_term_f, *rowApf_ptr, *colApf_ptr, *colApf_idx;
+	const int32_t *S_row, *S_col, *S_HAp, *S_term_ptr, *S_term_rowblk, *S_term_colblk;
+	// workspace
+	double *edge_cur, *edge_bak, *lm_cur, *lm_bak, *slot, *slot_bak, *JA, *JF, *resid[2], *HAp, *HApf, *Hf, *Hf_inv, *W, *grad, *delta, *dense;
+	uint8_t *valid, *blk_ok, *lm_inv, *slot_listed, *pair_refresh;
+	// results
+	srba_stats_t *stats;
+	double *r_edge_pose, *r_lm_pos, *r_slot_pose, *r_Hf_diag, *r_dense, *r_trace, *r_trace_delta;
+	uint8_t *r_obs_valid, *r_lm_inv;
+};
+
+__device__ void make_view(View &v, const DevProblem *h, const char *img, char *ws, char *res) {
+	v.h = h;
+#define IMG(T, name) v.name = reinterpret_cast<const T *>(img + h->img_##name)
+	IMG(double, edge_pose); IMG(int32_t, unk_edge); IMG(double, lm_pos); IMG(int32_t, unk_lm);
+	IMG(int32_t, pair_path_ptr); IMG(int32_t, path_edge); IMG(uint8_t, path_dir);
+	IMG(double, obs_z); IMG(int32_t, obs_slot); IMG(int32_t, obs_lm); IMG(int32_t, obs_mult);
+	IMG(int32_t, colA_ptr); IMG(int32_t, blkA_obs); IMG(int32_t, blkA_col); IMG(int32_t, blkA_slotA); IMG(int32_t, blkA_slotD); IMG(uint8_t, blkA_normal_dir);
+	IMG(int32_t, colF_ptr); IMG(int32_t, blkF_obs); IMG(int32_t, blkF_col); IMG(int32_t, blkF_slot);
+	IMG(int32_t, row_ptr); IMG(int32_t, row_blk);
+	IMG(int32_t, HAp_row); IMG(int32_t, HAp_col); IMG(int32_t, HAp_term_ptr); IMG(int32_t, HAp_term_a); IMG(int32_t, HAp_term_b);
+	IMG(int32_t, HApf_row); IMG(int32_t, HApf_col); IMG(int32_t, HApf_term_ptr); IMG(int32_t, HApf_term_a); IMG(int32_t, HApf_term_f);
+	IMG(int32_t, rowApf_ptr); IMG(int32_t, colApf_ptr); IMG(int32_t, colApf_idx);
+	IMG(int32_t, S_row); IMG(int32_t, S_col); IMG(int32_t, S_HAp); IMG(int32_t, S_term_ptr); IMG(int32_t, S_term_rowblk); IMG(int32_t, S_term_colblk);
+#undef IMG
+#define WS(T, name) v.name = reinterpret_cast<T *>(ws + h->ws_##name)
+	WS(double, edge_cur); WS(double, edge_bak); WS(double, lm_cur); WS(double, lm_bak); WS(double, slot); WS(double, slot_bak);
+	WS(double, JA); WS(double, JF);
+	v.resid[0] = reinterpret_cast<double *>(ws + h->ws_resid0);
+	v.resid[1] = reinterpret_cast<double *>(ws + h->ws_resid1);
+	WS(double, HAp); WS(double, HApf); WS(double, Hf); WS(double, Hf_inv); WS(double, W); WS(double, grad); WS(double, delta); WS(double, dense);
+	WS(uint8_t, valid); WS(uint8_t, blk_ok); WS(uint8_t, lm_inv); WS(uint8_t, slot_listed); WS(uint8_t, pair_refresh);
+#undef WS
+	v.stats = reinterpret_cast<srba_stats_t *>(res + h->res_stats);
+	v.r_edge_pose = reinterpret_cast<double *>(res + h->res_edge_pose);
+	v.r_lm_pos = reinterpret_cast<double *>(res + h->res_lm_pos);
+	v.r_slot_pose = reinterpret_cast<double *>(res + h->res_slot_pose);
+	v.r_Hf_diag = reinterpret_cast<double *>(res + h->res_Hf_diag);
+	v.r_dense = reinterpret_cast<double *>(res + h->res_dense);
+	v.r_trace = reinterpret_cast<double *>(res + h->res_trace);
+	v.r_trace_delta = reinterpret_cast<double *>(res + h->res_trace_delta);
+	v.r_obs_valid = reinterpret_cast<uint8_t *>(res + h->res_obs_valid);
+	v.r_lm_inv = reinterpret_cast<uint8_t *>(res + h->res_lm_inv);
+}
+
+// ------------------------------------------------------------------------------------------------ team (one CTA)
+struct Shared {
+	double red[LM_THREADS / 32];
+	double bcast;
+	// LM state (impl/optimize_edges.h:361-363,452-459)
+	double lambda, nu, err, rmse, rho, new_err;
+	int iter, stop, trials, accepted, relin, cholfail, cur, chol_ok, status;
+	double sensor_inv[12];  // (-sensor_pose) hoisted: pose_robot2sensor (srba_options_sensor_pose.h:108-113)
+};
+
+__device__ __forceinline__ double team_sum(double v, Shared &sh) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+	__syncthreads();
+	if ((threadIdx.x & 31) == 0) sh.red[threadIdx.x >> 5] = v;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		double s = 0;
+		for (int i = 0; i < LM_THREADS / 32; i++) s += sh.red[i];
+		sh.bcast = s;
+	}
+	__syncthreads();
+	return sh.bcast;
+}
+__device__ __forceinline__ double team_max(double v, Shared &sh) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+	__syncthreads();
+	if ((threadIdx.x & 31) == 0) sh.red[threadIdx.x >> 5] = v;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		double s = sh.red[0];
+		for (int i = 1; i < LM_THREADS / 32; i++) s = fmax(s, sh.red[i]);
+		sh.bcast = s;
+	}
+	__syncthreads();
+	return sh.bcast;
+}
+
+// ------------------------------------------------------------------------------------------------ stages
+// K1: numeric spanning tree.  update_numeric_only_all_from_node (impl/spantree_update_numeric.h:19-81)
+template <int P>
+__device__ void stage_chain(const View &v, bool only_refresh) {
+	constexpr int S = PoseOps<P>::S;
+	const int n = v.h->n_pairs;
+	for (int t = threadIdx.x; t < n; t += LM_THREADS) {
+		if (only_refresh && !v.pair_refresh[t]) continue;
+		double accum[S], tmp[S];
+		PoseOps<P>::identity(accum);
+		for (int k = v.pair_path_ptr[t]; k < v.pair_path_ptr[t + 1]; k++) {
+			const double *ep = v.edge_cur + (size_t)v.path_edge[k] * S;
+			if (v.path_dir[k]) PoseOps<P>::compose(accum, accum, ep);
+			else { PoseOps<P>::inverse(tmp, ep); PoseOps<P>::compose(accum, accum, tmp); }
+		}
+		double *o = v.slot + (size_t)(2 * t) * S;
+#pragma unroll
+		for (int i = 0; i < S; i++) o[i] = accum[i];
+		PoseOps<P>::inverse(tmp, accum);
+#pragma unroll
+		for (int i = 0; i < S; i++) o[S + i] = tmp[i];
+	}
+}
+
+// sensor_model<>::eval_jacob_dh_dx on the sensor-frame point (models/sensors.h:85-110,230-280,383-393,804-814)
+template <int OBSK>
+__device__ __forceinline__ bool eval_dh_dx(const DevProblem *h, double *dh_dx, const double *x) {
+	constexpr int O = ObsDims<OBSK>::O;
+	if (OBSK == SRBA_OBS_RELPOSES2D || OBSK == SRBA_OBS_CARTESIAN3D) {
+#pragma unroll
+		for (int i = 0; i < O * 3; i++) dh_dx[i] = 0;
+		dh_dx[0] = 1; dh_dx[4] = 1; dh_dx[8] = 1;
+		return true;
+	}
+	if (x[2] <= 0) return false;
+	{
+		const double pz_inv = 1.0 / x[2], pz_inv2 = pz_inv * pz_inv;
+		const double fx = h->model.cam_left[0], fy = h->model.cam_left[1];
+		dh_dx[0] = fx * pz_inv; dh_dx[1] = 0; dh_dx[2] = -fx * x[0] * pz_inv2;
+		dh_dx[3] = 0; dh_dx[4] = fy * pz_inv; dh_dx[5] = -fy * x[1] * pz_inv2;
+	}
+	if (OBSK == SRBA_OBS_STEREO) {
+		double r[3];
+		compose_point3(h->model.right_cam_R2L, x, r);
+		const double pz_inv = 1.0 / r[2], pz_inv2 = pz_inv * pz_inv;
+		const double fx = h->model.cam_right[0], fy = h->model.cam_right[1];
+		dh_dx[6] = fx * pz_inv; dh_dx[7] = 0; dh_dx[8] = -fx * r[0] * pz_inv2;
+		dh_dx[9] = 0; dh_dx[10] = fy * pz_inv; dh_dx[11] = -fy * r[1] * pz_inv2;
+	}
+	return true;
+}
+// jacob_dh_dx_rotate (srba_options_sensor_pose.h:124-129): dh_dx := dh_dx * R_s^T
+template <int O>
+__device__ __forceinline__ void dh_dx_rotate(const DevProblem *h, double *dh_dx) {
+	if (h->model.sensor_pose_kind != SRBA_SENSORPOSE_SE3) return;
+	const double *R = h->model.sensor_pose;
+	double t[O * 3];
+#pragma unroll
+	for (int r = 0; r < O; r++)
+#pragma unroll
+		for (int c = 0; c < 3; c++) t[3 * r + c] = dh_dx[3 * r + 0] * R[3 * c + 0] + dh_dx[3 * r + 1] * R[3 * c + 1] + dh_dx[3 * r + 2] * R[3 * c + 2];
+#pragma unroll
+	for (int i = 0; i < O * 3; i++) dh_dx[i] = t[i];
+}
+
+// One dh_dAp block: compute_jacobian_dh_dp (impl/jacobians.h:207-354) + compute_jacobian_dAepsDx_deps
+// (SE3 x point :363-494, SE2 x relpose :644-744).  Returns false when the sensor model rejects the point.
+template <int P, int OBSK>
+__device__ bool jacob_dh_dAp(const View &v, int b, double *J) {
+	constexpr int S = PoseOps<P>::S;
+	constexpr int O = ObsDims<OBSK>::O;
+	const int obs = v.blkA_obs[b];
+	const int sA = v.blkA_slotA[b];
+	const double *D = v.slot + (size_t)v.blkA_slotD[b] * S;
+	const double *A = sA >= 0 ? v.slot + (size_t)sA * S : nullptr;
+	const bool inverse_dir = !v.blkA_normal_dir[b];
+	const double *pdd1 = v.edge_cur + (size_t)v.unk_edge[v.blkA_col[b]] * S;  // k2k_edges[k2k_edge_id].inv_pose
+	if (P == 3) {
+		double dh_dx[9];
+		eval_dh_dx<OBSK>(v.h, dh_dx, nullptr);
+		double Xd, Yd, PHIa, bwo[3];
+		if (!inverse_dir) {
+			Xd = D[0]; Yd = D[1]; PHIa = 0;
+			if (A) { PHIa = A[2]; PoseOps<3>::compose(bwo, A, D); }
+			else { bwo[0] = D[0]; bwo[1] = D[1]; bwo[2] = D[2]; }
+		} else {
+			double Dp[3], pinv[3], Ap[3];
+			PoseOps<3>::compose(Dp, pdd1, D);
+			PoseOps<3>::inverse(pinv, pdd1);
+			if (A) PoseOps<3>::compose(Ap, A, pinv);
+			else { Ap[0] = pinv[0]; Ap[1] = pinv[1]; Ap[2] = pinv[2]; }
+			Xd = Dp[0]; Yd = Dp[1]; PHIa = Ap[2];
+			PoseOps<3>::compose(bwo, Ap, Dp);
+		}
+		double s_ad, c_ad, s_a, c_a;
+		sincos(bwo[2], &s_ad, &c_ad);
+		sincos(PHIa, &s_a, &c_a);
+		const double J0[9] = {c_ad, s_ad, 0, -s_ad, c_ad, 0, 0, 0, 1};
+		const double J1[9] = {1, 0, -Xd * s_a - Yd * c_a, 0, 1, Xd * c_a - Yd * s_a, 0, 0, 1};
+		const double J2[9] = {c_a, -s_a, 0, s_a, c_a, 0, 0, 0, 1};
+		double T0[9], T1[9];
+		matmul<3, 3, 3>(T0, dh_dx, J0);
+		matmul<3, 3, 3>(T1, T0, J1);
+		matmul<3, 3, 3>(J, T1, J2);
+		if (inverse_dir) {
+#pragma unroll
+			for (int i = 0; i < 9; i++) J[i] = -J[i];
+		}
+		return true;
+	} else {
+		const double *xji_i = v.lm_cur + (size_t)v.obs_lm[obs] * 3;
+		double piwl[12];
+		if (A) PoseOps<6>::compose(piwl, A, D);
+		else {
+#pragma unroll
+			for (int i = 0; i < 12; i++) piwl[i] = D[i];
+		}
+		double xji_l[3];
+		compose_point3(piwl, xji_i, xji_l);
+		if (v.h->model.sensor_pose_kind == SRBA_SENSORPOSE_SE3) inverse_compose_point3(v.h->model.sensor_pose, xji_l, xji_l);
+		double dh_dx[O * 3];
+		if (!eval_dh_dx<OBSK>(v.h, dh_dx, xji_l)) return false;
+		dh_dx_rotate<O>(v.h, dh_dx);
+		double H_ROTA[O * 3], Dq[12];
+		if (!inverse_dir) {
+#pragma unroll
+			for (int i = 0; i < 12; i++) Dq[i] = D[i];
+			if (A) matmul<O, 3, 3>(H_ROTA, dh_dx, A);
+			else {
+#pragma unroll
+				for (int i = 0; i < O * 3; i++) H_ROTA[i] = dh_dx[i];
+			}
+		} else {
+			PoseOps<6>::compose(Dq, pdd1, D);
+			double Rt[9];
+#pragma unroll
+			for (int r = 0; r < 3; r++)
+#pragma unroll
+				for (int c = 0; c < 3; c++) Rt[3 * r + c] = pdd1[3 * c + r];
+			if (A) { double T[O * 3]; matmul<O, 3, 3>(T, dh_dx, A); matmul<O, 3, 3>(H_ROTA, T, Rt); }
+			else matmul<O, 3, 3>(H_ROTA, dh_dx, Rt);
+		}
+		double vv[3];
+#pragma unroll
+		for (int r = 0; r < 3; r++) vv[r] = -Dq[9 + r] - xji_i[0] * Dq[3 * r + 0] - xji_i[1] * Dq[3 * r + 1] - xji_i[2] * Dq[3 * r + 2];
+		const double aux[9] = {0, -vv[2], vv[1], vv[2], 0, -vv[0], -vv[1], vv[0], 0};
+		double second[O * 3];
+		matmul<O, 3, 3>(second, H_ROTA, aux);
+#pragma unroll
+		for (int r = 0; r < O; r++)
+#pragma unroll
+			for (int c = 0; c < 3; c++) {
+				J[r * 6 + c] = inverse_dir ? -H_ROTA[3 * r + c] : H_ROTA[3 * r + c];
+				J[r * 6 + 3 + c] = inverse_dir ? -second[3 * r + c] : second[3 * r + c];
+			}
+		return true;
+	}
+}
+
+// One dh_df block: compute_jacobian_dh_df (impl/jacobians.h:888-1013).  Only for point landmarks (SE3 models here).
+template <int OBSK>
+__device__ bool jacob_dh_df(const View &v, int b, double *J) {
+	constexpr int O = ObsDims<OBSK>::O;
+	const int obs = v.blkF_obs[b];
+	const int s = v.blkF_slot[b];
+	const double *Pp = s >= 0 ? v.slot + (size_t)s * 12 : nullptr;
+	const double *xji_i = v.lm_cur + (size_t)v.obs_lm[obs] * 3;
+	double xji_l[3] = {xji_i[0], xji_i[1], xji_i[2]};
+	if (Pp) compose_point3(Pp, xji_i, xji_l);
+	if (v.h->model.sensor_pose_kind == SRBA_SENSORPOSE_SE3) inverse_compose_point3(v.h->model.sensor_pose, xji_l, xji_l);
+	double dh_dx[O * 3];
+	if (!eval_dh_dx<OBSK>(v.h, dh_dx, xji_l)) return false;
+	dh_dx_rotate<O>(v.h, dh_dx);
+	if (Pp) matmul<O, 3, 3>(J, dh_dx, Pp);
+	else {
+#pragma unroll
+		for (int i = 0; i < O * 3; i++) J[i] = dh_dx[i];
+	}
+	return true;
+}
+
+// K2a: recompute_all_Jacobians (impl/jacobians.h:1083-1117) with the validity protocol of SURVEY.md §9-5:
+// the first block of a row (in the reference's column-major walk) whose sensor model fails zeroes itself and clears the
+// row's validity byte; blocks walked before it keep their fresh value, blocks walked after it keep their PREVIOUS value.
+// `first` additionally records which numeric-ST entries the walk registers in list_of_required_num_poses (:226-230,:902-903).
+template <int P, int OBSK>
+__device__ void stage_jacobians(const View &v, bool first) {
+	constexpr int O = ObsDims<OBSK>::O;
+	const int nA = v.h->n_blkA, nF = (OBSK == SRBA_OBS_RELPOSES2D) ? 0 : v.h->n_blkF;
+	const bool can_fail = (OBSK == SRBA_OBS_MONO || OBSK == SRBA_OBS_STEREO);
+	for (int i = threadIdx.x; i < v.h->n_obs; i += LM_THREADS) v.valid[i] = 1;
+	__syncthreads();
+	// pass 1: evaluate every block into its slot of JA/JF scratch (fresh), remember ok flags
+	for (int b = threadIdx.x; b < nA + nF; b += LM_THREADS) {
+		if (b < nA) {
+			double J[O * P];
+			const bool ok = jacob_dh_dAp<P, OBSK>(v, b, J);
+			v.blk_ok[b] = ok;
+			if (!can_fail) {
+				double *dst = v.JA + (size_t)b * O * P;
+#pragma unroll
+				for (int i = 0; i < O * P; i++) dst[i] = J[i];
+			}
+		} else if (P == 6) {
+			const int f = b - nA;
+			double J[O * 3];
+			const bool ok = jacob_dh_df<OBSK>(v, f, J);
+			v.blk_ok[b] = ok;
+			if (!can_fail) {
+				double *dst = v.JF + (size_t)f * O * 3;
+#pragma unroll
+				for (int i = 0; i < O * 3; i++) dst[i] = J[i];
+			}
+		}
+	}
+	if (can_fail) {
+		__syncthreads();
+		// pass 2: commit according to the walk order of each row
+		for (int b = threadIdx.x; b < nA + nF; b += LM_THREADS) {
+			const int obs = b < nA ? v.blkA_obs[b] : v.blkF_obs[b - nA];
+			int first_bad = -1, my_pos = -1;
+			for (int k = v.row_ptr[obs]; k < v.row_ptr[obs + 1]; k++) {
+				const int rb = v.row_blk[k];
+				if (rb == b) my_pos = k;
+				if (first_bad < 0 && !v.blk_ok[rb]) first_bad = k;
+			}
+			const bool visited_valid = (first_bad < 0 || my_pos <= first_bad);
+			if (b < nA) {
+				double *dst = v.JA + (size_t)b * O * P;
+				if (first_bad < 0 || my_pos < first_bad) {
+					double J[O * P];
+					jacob_dh_dAp<P, OBSK>(v, b, J);
+#pragma unroll
+					for (int i = 0; i < O * P; i++) dst[i] = J[i];
+				} else if (my_pos == first_bad) {
+#pragma unroll
+					for (int i = 0; i < O * P; i++) dst[i] = 0;
+					v.valid[obs] = 0;
+				}
+			} else if (P == 6) {
+				const int f = b - nA;
+				double *dst = v.JF + (size_t)f * O * 3;
+				if (first_bad < 0 || my_pos < first_bad) {
+					double J[O * 3];
+					jacob_dh_df<OBSK>(v, f, J);
+#pragma unroll
+					for (int i = 0; i < O * 3; i++) dst[i] = J[i];
+				} else if (my_pos == first_bad) {
+#pragma unroll
+					for (int i = 0; i < O * 3; i++) dst[i] = 0;
+					v.valid[obs] = 0;
+				}
+			}
+			if (first && visited_valid) {
+				if (b < nA) { if (v.blkA_slotA[b] >= 0) v.slot_listed[v.blkA_slotA[b]] = 1; v.slot_listed[v.blkA_slotD[b]] = 1; }
+				else if (v.blkF_slot[b - nA] >= 0) v.slot_listed[v.blkF_slot[b - nA]] = 1;
+			}
+		}
+	} else if (first) {
+		for (int b = threadIdx.x; b < nA + nF; b += LM_THREADS) {
+			if (b < nA) { if (v.blkA_slotA[b] >= 0) v.slot_listed[v.blkA_slotA[b]] = 1; v.slot_listed[v.blkA_slotD[b]] = 1; }
+			else if (v.blkF_slot[b - nA] >= 0) v.slot_listed[v.blkF_slot[b - nA]] = 1;
+		}
+	}
+}
+
+// accum_JtJ element (a,b) of J1^t Lambda J2 (srba_options_noise.h:45-50,103-109)
+template <int O>
+__device__ __forceinline__ double jtj_elem(const DevProblem *h, const double *J1, int m1, int a, const double *J2, int m2, int b) {
+	double s = 0;
+	if (h->model.noise_kind == SRBA_NOISE_IDENTITY) {
+#pragma unroll
+		for (int k = 0; k < O; k++) s += J1[k * m1 + a] * J2[k * m2 + b];
+	} else {
+#pragma unroll
+		for (int k = 0; k < O; k++) {
+			double t = 0;
+#pragma unroll
+			for (int l = 0; l < O; l++) t += J1[l * m1 + a] * h->model.noise_lambda[l * O + k];
+			s += t * J2[k * m2 + b];
+		}
+	}
+	return s;
+}
+
+// K2b: sparse_hessian_update_numeric x3 (impl/sparse_hessian_update_numeric.h:22-60): one thread per block element,
+// terms in ascending observation order, invalid rows skipped, identity noise scaled by 1/sigma afterwards.
+template <int P, int OBSK>
+__device__ void stage_hessian(const View &v) {
+	constexpr int O = ObsDims<OBSK>::O;
+	const DevProblem *h = v.h;
+	const double scale = (h->model.noise_kind == SRBA_NOISE_IDENTITY) ? 1.0 / h->model.noise_std : 1.0;
+	const bool do_scale = (h->model.noise_kind == SRBA_NOISE_IDENTITY);
+	const int nAp = h->n_HAp * P * P, nApf = h->n_HApf * P * 3, nf = h->n_unk_lms * 9;
+	for (int it = threadIdx.x; it < nAp + nApf + nf; it += LM_THREADS) {
+		if (it < nAp) {
+			const int blk = it / (P * P), e = it % (P * P), a = e / P, b = e % P;
+			double s = 0;
+			for (int t = v.HAp_term_ptr[blk]; t < v.HAp_term_ptr[blk + 1]; t++) {
+				const int ba = v.HAp_term_a[t], bb = v.HAp_term_b[t];
+				if (!v.valid[v.blkA_obs[ba]]) continue;
+				s += jtj_elem<O>(h, v.JA + (size_t)ba * O * P, P, a, v.JA + (size_t)bb * O * P, P, b);
+			}
+			v.HAp[it] = do_scale ? s * scale : s;
+		} else if (it < nAp + nApf) {
+			const int j = it - nAp;
+			const int blk = j / (P * 3), e = j % (P * 3), a = e / 3, b = e % 3;
+			double s = 0;
+			for (int t = v.HApf_term_ptr[blk]; t < v.HApf_term_ptr[blk + 1]; t++) {
+				const int ba = v.HApf_term_a[t], bf = v.HApf_term_f[t];
+				if (!v.valid[v.blkA_obs[ba]]) continue;
+				s += jtj_elem<O>(h, v.JA + (size_t)ba * O * P, P, a, v.JF + (size_t)bf * O * 3, 3, b);
+			}
+			v.HApf[j] = do_scale ? s * scale : s;
+		} else {
+			const int j = it - nAp - nApf;
+			const int k = j / 9, e = j % 9, a = e / 3, b = e % 3;
+			double s = 0;
+			for (int bf = v.colF_ptr[k]; bf < v.colF_ptr[k + 1]; bf++) {
+				if (!v.valid[v.blkF_obs[bf]]) continue;
+				s += jtj_elem<O>(h, v.JF + (size_t)bf * O * 3, 3, a, v.JF + (size_t)bf * O * 3, 3, b);
+			}
+			v.Hf[j] = do_scale ? s * scale : s;
+		}
+	}
+}
+
+// reprojection_residuals (impl/reprojection_residuals.h:16-81) + sensor_model<>::observe_error; returns the team-wide
+// total squared error INCLUDING the duplicated rows of optimize_edges.h:177-193 (obs_mult).
+template <int P, int OBSK>
+__device__ double stage_residuals(const View &v, double *resid, Shared &sh) {
+	constexpr int S = PoseOps<P>::S;
+	constexpr int O = ObsDims<OBSK>::O;
+	const DevProblem *h = v.h;
+	double local = 0;
+	for (int i = threadIdx.x; i < h->n_obs; i += LM_THREADS) {
+		const int s = v.obs_slot[i];
+		const double *z = v.obs_z + (size_t)i * O;
+		double r[O];
+		if (P == 3) {
+			double Pp[3] = {0, 0, 0};
+			if (s >= 0) { Pp[0] = v.slot[(size_t)s * S]; Pp[1] = v.slot[(size_t)s * S + 1]; Pp[2] = v.slot[(size_t)s * S + 2]; }
+			double sn, cs;
+			sincos(Pp[2], &sn, &cs);
+			r[0] = (z[0] - Pp[0]) * cs + (z[1] - Pp[1]) * sn;
+			r[1] = -(z[0] - Pp[0]) * sn + (z[1] - Pp[1]) * cs;
+			r[2] = wrapToPi(z[2] - Pp[2]);
+		} else {
+			double Pp[12];
+			if (s >= 0) {
+#pragma unroll
+				for (int k = 0; k < 12; k++) Pp[k] = v.slot[(size_t)s * 12 + k];
+			} else PoseOps<6>::identity(Pp);
+			if (h->model.sensor_pose_kind == SRBA_SENSORPOSE_SE3) PoseOps<6>::compose(Pp, sh.sensor_inv, Pp);
+			double x[3];
+			compose_point3(Pp, v.lm_cur + (size_t)v.obs_lm[i] * 3, x);
+			double pred[O];
+			if (OBSK == SRBA_OBS_CARTESIAN3D) { pred[0] = x[0]; pred[1] = x[1]; pred[2] = x[2]; }
+			else {
+				pred[0] = h->model.cam_left[2] + h->model.cam_left[0] * x[0] / x[2];
+				pred[1] = h->model.cam_left[3] + h->model.cam_left[1] * x[1] / x[2];
+				if (OBSK == SRBA_OBS_STEREO) {
+					double rr[3];
+					compose_point3(h->model.right_cam_R2L, x, rr);
+					pred[2] = h->model.cam_right[2] + h->model.cam_right[0] * rr[0] / rr[2];
+					pred[O - 1] = h->model.cam_right[3] + h->model.cam_right[1] * rr[1] / rr[2];
+				}
+			}
+#pragma unroll
+			for (int k = 0; k < O; k++) r[k] = z[k] - pred[k];
+		}
+		double sum_2 = 0;
+#pragma unroll
+		for (int k = 0; k < O; k++) sum_2 += r[k] * r[k];
+		double contrib = sum_2;
+		if (h->model.use_robust_kernel) {
+			const double nrm = fmax(1e-11, sqrt(sum_2));
+			const double kp = h->model.kernel_param;
+			const double hub = fabs(2 * (kp * kp) * (sqrt(1 + (nrm / kp) * (nrm / kp)) - 1));  // huber_kernel RbaEngine.h:810-813
+			const double w = sqrt(hub) / nrm;
+#pragma unroll
+			for (int k = 0; k < O; k++) r[k] *= w;
+			contrib = (w * w) * sum_2;
+		}
+#pragma unroll
+		for (int k = 0; k < O; k++) resid[(size_t)i * O + k] = r[k];
+		local += contrib * (double)v.obs_mult[i];
+	}
+	return team_sum(local, sh);
+}
+
+// compute_minus_gradient (impl/compute_minus_gradient.h:20-91): one thread per scalar unknown, blocks in ascending obs.
+template <int P, int OBSK>
+__device__ void stage_gradient(const View &v, const double *resid) {
+	constexpr int O = ObsDims<OBSK>::O;
+	const DevProblem *h = v.h;
+	const bool ident = (h->model.noise_kind == SRBA_NOISE_IDENTITY);
+	const double scale = ident ? 1.0 / h->model.noise_std : 1.0;
+	const int nAp = h->n_unk_edges * P;
+	for (int it = threadIdx.x; it < h->n_scalars; it += LM_THREADS) {
+		double g = 0;
+		if (it < nAp) {
+			const int col = it / P, a = it % P;
+			for (int b = v.colA_ptr[col]; b < v.colA_ptr[col + 1]; b++) {
+				const double *J = v.JA + (size_t)b * O * P;
+				const double *r = resid + (size_t)v.blkA_obs[b] * O;
+				double s = 0;
+				if (ident) {
+#pragma unroll
+					for (int k = 0; k < O; k++) s += J[k * P + a] * r[k];
+				} else {
+#pragma unroll
+					for (int k = 0; k < O; k++) {
+						double t = 0;
+#pragma unroll
+						for (int l = 0; l < O; l++) t += J[l * P + a] * h->model.noise_lambda[l * O + k];
+						s += t * r[k];
+					}
+				}
+				g += s;
+			}
+		} else {
+			const int j = it - nAp, col = j / 3, a = j % 3;
+			for (int b = v.colF_ptr[col]; b < v.colF_ptr[col + 1]; b++) {
+				const double *J = v.JF + (size_t)b * O * 3;
+				const double *r = resid + (size_t)v.blkF_obs[b] * O;
+				double s = 0;
+				if (ident) {
+#pragma unroll
+					for (int k = 0; k < O; k++) s += J[k * 3 + a] * r[k];
+				} else {
+#pragma unroll
+					for (int k = 0; k < O; k++) {
+						double t = 0;
+#pragma unroll
+						for (int l = 0; l < O; l++) t += J[l * 3 + a] * h->model.noise_lambda[l * O + k];
+						s += t * r[k];
+					}
+				}
+				g += s;
+			}
+		}
+		v.grad[it] = ident ? g * scale : g;
+	}
+}
+
+// Eigen::FullPivLU<3x3>: isInvertible() + inverse()  (impl/schur.h:193-208)
+__device__ bool fullpiv_lu_inverse3(const double *Ain, double *inv) {
+	double lu[9];
+#pragma unroll
+	for (int i = 0; i < 9; i++) lu[i] = Ain[i];
+	int rowsT[3] = {0, 1, 2}, colsT[3] = {0, 1, 2};
+	int nonzero_pivots = 3;
+	double maxpivot = 0;
+	for (int k = 0; k < 3; k++) {
+		int rbig = k, cbig = k;
+		double big = 0;
+		for (int r = k; r < 3; r++)
+			for (int c = k; c < 3; c++)
+				if (fabs(lu[3 * r + c]) > big) { big = fabs(lu[3 * r + c]); rbig = r; cbig = c; }
+		if (big == 0) { nonzero_pivots = k; for (int i = k; i < 3; i++) { rowsT[i] = i; colsT[i] = i; } break; }
+		if (big > maxpivot) maxpivot = big;
+		rowsT[k] = rbig; colsT[k] = cbig;
+		if (k != rbig) for (int c = 0; c < 3; c++) { const double t = lu[3 * k + c]; lu[3 * k + c] = lu[3 * rbig + c]; lu[3 * rbig + c] = t; }
+		if (k != cbig) for (int r = 0; r < 3; r++) { const double t = lu[3 * r + k]; lu[3 * r + k] = lu[3 * r + cbig]; lu[3 * r + cbig] = t; }
+		if (k < 2) {
+			for (int r = k + 1; r < 3; r++) lu[3 * r + k] /= lu[3 * k + k];
+			for (int r = k + 1; r < 3; r++)
+				for (int c = k + 1; c < 3; c++) lu[3 * r + c] -= lu[3 * r + k] * lu[3 * k + c];
+		}
+	}
+	const double thr = fabs(maxpivot) * (2.220446049250313e-16 * 3);
+	int rank = 0;
+	for (int i = 0; i < nonzero_pivots; i++) rank += (fabs(lu[3 * i + i]) > thr) ? 1 : 0;
+	if (rank != 3) return false;
+	int p[3] = {0, 1, 2}, q[3] = {0, 1, 2};
+	for (int k = 0; k < 3; k++) { const int t = p[k]; p[k] = p[rowsT[k]]; p[rowsT[k]] = t; }
+	for (int k = 0; k < 3; k++) { const int t = q[k]; q[k] = q[colsT[k]]; q[colsT[k]] = t; }
+	for (int col = 0; col < 3; col++) {
+		double b[3];
+		for (int i = 0; i < 3; i++) b[i] = (p[i] == col) ? 1.0 : 0.0;
+		for (int i = 0; i < 3; i++)
+			for (int j = 0; j < i; j++) b[i] -= lu[3 * i + j] * b[j];
+		for (int i = 2; i >= 0; i--) {
+			for (int j = i + 1; j < 3; j++) b[i] -= lu[3 * i + j] * b[j];
+			b[i] /= lu[3 * i + i];
+		}
+		for (int i = 0; i < 3; i++) inv[3 * q[i] + col] = b[i];
+	}
+	return true;
+}
+
+// K3: SchurComplement::numeric_build_reduced_system(lambda) (impl/schur.h:180-268) fused with the dense fill of
+// solver_engine<true,true>::solve (impl/lev-marq_solvers.h:492-519).  The reduced gradient head is written IN PLACE
+// (quirk SURVEY.md §9-1) and also copied into the augmented column of the dense system.
+template <int P>
+__device__ void stage_schur_and_fill(const View &v, double lambda) {
+	const DevProblem *h = v.h;
+	const int nf = h->n_unk_lms, n = h->n_dense, ld = h->ld_dense;
+	// (1) inv(Hf_kk + lambda I)
+	for (int k = threadIdx.x; k < nf; k += LM_THREADS) {
+		double M[9], inv[9];
+#pragma unroll
+		for (int i = 0; i < 9; i++) M[i] = v.Hf[(size_t)k * 9 + i];
+		M[0] += lambda; M[4] += lambda; M[8] += lambda;
+		const bool ok = fullpiv_lu_inverse3(M, inv);
+		v.lm_inv[k] = ok;
+		if (ok) {
+#pragma unroll
+			for (int i = 0; i < 9; i++) v.Hf_inv[(size_t)k * 9 + i] = inv[i];
+		}
+	}
+	// zero the dense system (denseH.setZero, lev-marq_solvers.h:492)
+	for (size_t i = threadIdx.x; i < (size_t)n * ld; i += LM_THREADS) v.dense[i] = 0;
+	__syncthreads();
+	// (2) W_ik = HApf_ik * inv_k
+	for (int it = threadIdx.x; it < h->n_HApf * P * 3; it += LM_THREADS) {
+		const int blk = it / (P * 3), e = it % (P * 3), a = e / 3, b = e % 3;
+		const int k = v.HApf_col[blk];
+		if (!v.lm_inv[k]) continue;
+		const double *Hb = v.HApf + (size_t)blk * P * 3;
+		const double *inv = v.Hf_inv + (size_t)k * 9;
+		v.W[it] = Hb[a * 3 + 0] * inv[0 * 3 + b] + Hb[a * 3 + 1] * inv[1 * 3 + b] + Hb[a * 3 + 2] * inv[2 * 3 + b];
+	}
+	__syncthreads();
+	// (3) S blocks -> dense upper triangle (+lambda on the diagonal); (4) reduced gradient
+	const int nS = h->n_S * P * P;
+	for (int it = threadIdx.x; it < nS + n; it += LM_THREADS) {
+		if (it < nS) {
+			const int blk = it / (P * P), e = it % (P * P), a = e / P, b = e % P;
+			const int row = v.S_row[blk], col = v.S_col[blk];
+			const int hb = v.S_HAp[blk];
+			double s = hb >= 0 ? v.HAp[(size_t)hb * P * P + e] : 0.0;
+			for (int t = v.S_term_ptr[blk]; t < v.S_term_ptr[blk + 1]; t++) {
+				const int rb = v.S_term_rowblk[t], cb = v.S_term_colblk[t];
+				if (!v.lm_inv[v.HApf_col[rb]]) continue;
+				const double *Wr = v.W + (size_t)rb * P * 3;
+				const double *Hc = v.HApf + (size_t)cb * P * 3;
+				s -= Wr[a * 3 + 0] * Hc[b * 3 + 0] + Wr[a * 3 + 1] * Hc[b * 3 + 1] + Wr[a * 3 + 2] * Hc[b * 3 + 2];
+			}
+			if (row == col && a == b) s += lambda;
+			v.dense[(size_t)(P * row + a) * ld + P * col + b] = s;
+		} else {
+			const int i = it - nS;  // scalar of the pose part
+			const int ucol = i / P, a = i % P;
+			double g = v.grad[i];
+			for (int blk = v.rowApf_ptr[ucol]; blk < v.rowApf_ptr[ucol + 1]; blk++) {
+				const int k = v.HApf_col[blk];
+				if (!v.lm_inv[k]) continue;
+				const double *Wr = v.W + (size_t)blk * P * 3;
+				const double *gf = v.grad + n + (size_t)k * 3;
+				g -= Wr[a * 3 + 0] * gf[0] + Wr[a * 3 + 1] * gf[1] + Wr[a * 3 + 2] * gf[2];
+			}
+			v.grad[i] = g;
+			v.dense[(size_t)i * ld + n] = g;  // augmented column: forward substitution comes for free
+		}
+	}
+}
+
+// K4: dense Cholesky A = U^T U on the upper triangle + forward substitution (augmented column) + back substitution
+// (Eigen::LLT<Upper>, impl/lev-marq_solvers.h:527-549).  Right-looking; returns false on a non-positive pivot.
+__device__ bool stage_cholesky_solve(const View &v, Shared &sh) {
+	const int n = v.h->n_dense, ld = v.h->ld_dense;
+	double *A = v.dense;
+	if (threadIdx.x == 0) sh.chol_ok = 1;
+	__syncthreads();
+	for (int k = 0; k < n; k++) {
+		double *rowk = A + (size_t)k * ld;
+		const double d = rowk[k];
+		if (!(d > 0)) {  // Eigen: if (x<=0) return k  (NaN continues in Eigen; treated as failure here is unreachable for finite input)
+			if (d <= 0) { if (threadIdx.x == 0) sh.chol_ok = 0; __syncthreads(); return false; }
+		}
+		const double sd = sqrt(d);
+		__syncthreads();  // everybody has read the pivot
+		for (int j = k + threadIdx.x; j <= n; j += LM_THREADS) rowk[j] = (j == k) ? sd : rowk[j] / sd;
+		__syncthreads();
+		// trailing update: rows i in (k, n), columns j in [i, n]
+		const int m = n - k - 1;
+		if (m > 0) {
+			// flatten the (i,j>=i) trapezoid row by row; a warp handles a row segment for coalescing
+			const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = LM_THREADS / 32;
+			for (int i = k + 1 + warp; i < n; i += nw) {
+				const double uki = rowk[i];
+				double *rowi = A + (size_t)i * ld;
+				for (int j = i + lane; j <= n; j += 32) rowi[j] -= uki * rowk[j];
+			}
+		}
+		__syncthreads();
+	}
+	// back substitution U x = y, y = augmented column; column-oriented
+	double *x = v.delta;
+	for (int i = threadIdx.x; i < n; i += LM_THREADS) x[i] = A[(size_t)i * ld + n];
+	__syncthreads();
+	for (int j = n - 1; j >= 0; j--) {
+		if (threadIdx.x == 0) x[j] = x[j] / A[(size_t)j * ld + j];
+		__syncthreads();
+		const double xj = x[j];
+		for (int i = threadIdx.x; i < j; i += LM_THREADS) x[i] -= A[(size_t)i * ld + j] * xj;
+		__syncthreads();
+	}
+	return true;
+}
+
+// K5a: SchurComplement::numeric_solve_for_features (impl/schur.h:271-311): mutates the gradient tail in place.
+template <int P>
+__device__ void stage_features(const View &v) {
+	const DevProblem *h = v.h;
+	const int n = h->n_dense;
+	for (int k = threadIdx.x; k < h->n_unk_lms; k += LM_THREADS) {
+		double *d = v.delta + n + (size_t)k * 3;
+		if (!v.lm_inv[k]) { d[0] = 0; d[1] = 0; d[2] = 0; continue; }  // delta_eps.tail().setZero()
+		double *gf = v.grad + n + (size_t)k * 3;
+		double g0 = gf[0], g1 = gf[1], g2 = gf[2];
+		for (int q = v.colApf_ptr[k]; q < v.colApf_ptr[k + 1]; q++) {
+			const int blk = v.colApf_idx[q];
+			const double *Hb = v.HApf + (size_t)blk * P * 3;
+			const double *dp = v.delta + (size_t)v.HApf_row[blk] * P;
+			double s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+			for (int a = 0; a < P; a++) { s0 += Hb[a * 3 + 0] * dp[a]; s1 += Hb[a * 3 + 1] * dp[a]; s2 += Hb[a * 3 + 2] * dp[a]; }
+			g0 -= s0; g1 -= s1; g2 -= s2;
+		}
+		gf[0] = g0; gf[1] = g1; gf[2] = g2;
+		const double *inv = v.Hf_inv + (size_t)k * 9;
+		d[0] = inv[0] * g0 + inv[1] * g1 + inv[2] * g2;
+		d[1] = inv[3] * g0 + inv[4] * g1 + inv[5] * g2;
+		d[2] = inv[6] * g0 + inv[7] * g1 + inv[8] * g2;
+	}
+}
+
+// K5b: back-up + manifold update (impl/optimize_edges.h:491-557)
+template <int P>
+__device__ void stage_update(const View &v) {
+	constexpr int S = PoseOps<P>::S;
+	const DevProblem *h = v.h;
+	for (int i = threadIdx.x; i < h->n_unk_edges; i += LM_THREADS) {
+		double *ep = v.edge_cur + (size_t)v.unk_edge[i] * S;
+		double oldp[S], incr[S], np[S];
+#pragma unroll
+		for (int k = 0; k < S; k++) { oldp[k] = ep[k]; v.edge_bak[(size_t)i * S + k] = oldp[k]; }
+		PoseOps<P>::pseudo_exp(incr, v.delta + (size_t)i * P);
+		PoseOps<P>::compose(np, incr, oldp);
+#pragma unroll
+		for (int k = 0; k < S; k++) ep[k] = np[k];
+	}
+	for (int i = threadIdx.x; i < h->n_unk_lms; i += LM_THREADS) {
+		double *lp = v.lm_cur + (size_t)v.unk_lm[i] * 3;
+		const double *d = v.delta + h->n_dense + (size_t)i * 3;
+#pragma unroll
+		for (int k = 0; k < 3; k++) { v.lm_bak[(size_t)i * 3 + k] = lp[k]; lp[k] += d[k]; }
+	}
+	for (size_t i = threadIdx.x; i < (size_t)2 * h->n_pairs * S; i += LM_THREADS) v.slot_bak[i] = v.slot[i];
+}
+// rejected step (impl/optimize_edges.h:660-680): only the LISTED directed entries of the numeric ST are restored.
+template <int P>
+__device__ void stage_restore(const View &v) {
+	constexpr int S = PoseOps<P>::S;
+	const DevProblem *h = v.h;
+	for (int i = threadIdx.x; i < h->n_unk_edges * S; i += LM_THREADS) v.edge_cur[(size_t)v.unk_edge[i / S] * S + (i % S)] = v.edge_bak[i];
+	for (int i = threadIdx.x; i < h->n_unk_lms * 3; i += LM_THREADS) v.lm_cur[(size_t)v.unk_lm[i / 3] * 3 + (i % 3)] = v.lm_bak[i];
+	for (size_t i = threadIdx.x; i < (size_t)2 * h->n_pairs * S; i += LM_THREADS)
+		if (v.slot_listed[i / S]) v.slot[i] = v.slot_bak[i];
+}
+
+// ------------------------------------------------------------------------------------------------ the LM program
+template <int P, int OBSK>
+__device__ void lm_program(const DevProblem *h, const char *img, char *ws, char *res, Shared &sh) {
+	constexpr int S = PoseOps<P>::S;
+	View v;
+	make_view(v, h, img, ws, res);
+	const int n = h->n_dense, nsc = h->n_scalars;
+	const int nObsRows = h->n_total_obs_rows;
+
+	// ---- load inputs into the workspace (edges and landmarks are the only mutable inputs)
+	for (size_t i = threadIdx.x; i < (size_t)h->n_edges * S; i += LM_THREADS) v.edge_cur[i] = v.edge_pose[i];
+	for (size_t i = threadIdx.x; i < (size_t)h->n_lms * 3; i += LM_THREADS) v.lm_cur[i] = v.lm_pos[i];
+	for (int i = threadIdx.x; i < 2 * h->n_pairs; i += LM_THREADS) v.slot_listed[i] = 0;
+	if (threadIdx.x == 0) {
+		if (h->model.sensor_pose_kind == SRBA_SENSORPOSE_SE3) PoseOps<6>::inverse(sh.sensor_inv, h->model.sensor_pose);
+		sh.status = SRBA_OK;
+	}
+	__syncthreads();
+	// E. update_numeric(set,false)  (optimize_edges.h:256)
+	stage_chain<P>(v, false);
+	__syncthreads();
+	// F/G. validity reset + recompute_all_Jacobians (:269-276)
+	stage_jacobians<P, OBSK>(v, true);
+	__syncthreads();
+	for (int t = threadIdx.x; t < h->n_pairs; t += LM_THREADS) v.pair_refresh[t] = v.slot_listed[2 * t] | v.slot_listed[2 * t + 1];
+	// J. Hessian (:329-331)
+	stage_hessian<P, OBSK>(v);
+	__syncthreads();
+	// L. lambda0 = tau * max diag (:365-390)
+	double dmax = 0;
+	for (int b = threadIdx.x; b < h->n_HAp; b += LM_THREADS)
+		if (v.HAp_row[b] == v.HAp_col[b]) {
+			double m = v.HAp[(size_t)b * P * P];
+			for (int k = 1; k < P; k++) m = fmax(m, v.HAp[(size_t)b * P * P + k * P + k]);
+			dmax = fmax(dmax, m);
+		}
+	for (int k = threadIdx.x; k < h->n_unk_lms; k += LM_THREADS)
+		dmax = fmax(dmax, fmax(v.Hf[(size_t)k * 9], fmax(v.Hf[(size_t)k * 9 + 4], v.Hf[(size_t)k * 9 + 8])));
+	dmax = team_max(dmax, sh);
+	// M. residuals (:395-404)
+	const double err0 = stage_residuals<P, OBSK>(v, v.resid[0], sh);
+	// N. gradient (:422-426)
+	stage_gradient<P, OBSK>(v, v.resid[0]);
+	if (threadIdx.x == 0) {
+		sh.nu = 2;
+		sh.lambda = 1e-3 * dmax;
+		sh.err = err0;
+		sh.rmse = sqrt(err0 / nObsRows);
+		sh.iter = 0; sh.stop = 0; sh.trials = 0; sh.accepted = 0; sh.relin = 0; sh.cholfail = 0; sh.cur = 0;
+		v.stats->total_sqr_error_init = err0;
+	}
+	__syncthreads();
+
+	const double MAX_LAMBDA = h->model.max_lambda;
+	const double max_gradient_to_stop = 1e-15;
+	// P. LM iterations (:454-696).  Every thread follows the same control flow through the shared state.
+	for (;;) {
+		if (!(sh.iter < h->model.max_iters && !sh.stop)) break;
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			sh.rho = 0;
+			if (sh.lambda >= MAX_LAMBDA) sh.stop = 1;
+			if (sh.rmse < h->model.max_error_per_obs_to_stop) sh.stop = 1;
+		}
+		__syncthreads();
+		while (sh.rho <= 0 && !sh.stop) {
+			const double lambda = sh.lambda;
+			const int trial = sh.trials;
+			__syncthreads();
+			stage_schur_and_fill<P>(v, lambda);
+			__syncthreads();
+			if (h->want_dense)  // extra_results.hessian = denseH of the last solve (lev-marq_solvers.h:582-586)
+				for (size_t i = threadIdx.x; i < (size_t)n * n; i += LM_THREADS) v.r_dense[i] = v.dense[(i / n) * h->ld_dense + (i % n)];
+			const bool ok = stage_cholesky_solve(v, sh);
+			if (!ok) {  // not positive definite (:476-485)
+				if (threadIdx.x == 0) {
+					if (trial < h->trace_cap) {
+						double *tr = v.r_trace + (size_t)trial * 6;
+						tr[0] = lambda; tr[1] = 0; tr[2] = 0; tr[3] = 0; tr[4] = 0; tr[5] = 0;
+					}
+					sh.trials++; sh.cholfail++;
+					sh.lambda *= sh.nu;
+					sh.nu *= 2.;
+					sh.stop = (sh.lambda > MAX_LAMBDA);
+				}
+				if (trial < h->trace_cap)
+					for (int i = threadIdx.x; i < nsc; i += LM_THREADS) v.r_trace_delta[(size_t)trial * nsc + i] = 0;
+				__syncthreads();
+				continue;
+			}
+			stage_features<P>(v);
+			__syncthreads();
+			stage_update<P>(v);
+			__syncthreads();
+			stage_chain<P>(v, true);  // update_numeric(set, true) (:565)
+			__syncthreads();
+			double *new_resid = v.resid[sh.cur ^ 1];
+			const double new_err = stage_residuals<P, OBSK>(v, new_resid, sh);
+			// rho (:585)
+			double dl = 0;
+			for (int i = threadIdx.x; i < nsc; i += LM_THREADS) dl += v.delta[i] * (lambda * v.delta[i] + v.grad[i]);
+			const double denom = team_sum(dl, sh);
+			const double err = sh.err;
+			const double rho = (err - new_err) / denom;
+			const double error_reduction_ratio = err > 0 ? (err - new_err) / err : 0;
+			const bool accept = rho > 0;
+			const bool do_relinearize = accept && (error_reduction_ratio < 0 || error_reduction_ratio > h->model.min_error_reduction_ratio_to_relinearize);
+			if (trial < h->trace_cap) {
+				if (threadIdx.x == 0) {
+					double *tr = v.r_trace + (size_t)trial * 6;
+					tr[0] = lambda; tr[1] = 1; tr[2] = rho; tr[3] = new_err; tr[4] = accept ? 1 : 0; tr[5] = do_relinearize ? 1 : 0;
+				}
+				for (int i = threadIdx.x; i < nsc; i += LM_THREADS) v.r_trace_delta[(size_t)trial * nsc + i] = v.delta[i];
+			}
+			__syncthreads();
+			if (accept) {
+				if (do_relinearize) {  // :606-629
+					stage_jacobians<P, OBSK>(v, false);
+					__syncthreads();
+					stage_hessian<P, OBSK>(v);
+					__syncthreads();
+				}
+				stage_gradient<P, OBSK>(v, new_resid);  // :633
+				__syncthreads();
+				double gm = 0;
+				for (int i = threadIdx.x; i < nsc; i += LM_THREADS) gm = fmax(gm, fabs(v.grad[i]));
+				gm = team_max(gm, sh);
+				if (threadIdx.x == 0) {
+					sh.cur ^= 1;
+					sh.err = new_err;
+					sh.rmse = sqrt(new_err / nObsRows);
+					sh.trials++; sh.accepted++; sh.relin += do_relinearize ? 1 : 0;
+					if (gm <= max_gradient_to_stop) sh.stop = 1;
+					if (sh.rmse < h->model.max_error_per_obs_to_stop) sh.stop = 1;
+					if (rho > h->model.max_rho) sh.stop = 1;
+					sh.lambda *= 1.0 / 3.0;
+					sh.nu = 2.0;
+					sh.rho = rho;
+				}
+			} else {
+				stage_restore<P>(v);
+				if (threadIdx.x == 0) {
+					sh.trials++;
+					sh.lambda *= sh.nu;
+					sh.nu *= 2.0;
+					sh.stop = (sh.lambda > MAX_LAMBDA);
+					sh.rho = rho;  // <=0 or NaN: NaN also leaves the while in the reference ("rho<=0" false)
+				}
+			}
+			__syncthreads();
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) sh.iter++;
+		__syncthreads();
+	}
+	__syncthreads();
+	// Q/S. outputs
+	for (size_t i = threadIdx.x; i < (size_t)h->n_unk_edges * S; i += LM_THREADS) v.r_edge_pose[i] = v.edge_cur[(size_t)v.unk_edge[i / S] * S + (i % S)];
+	for (int i = threadIdx.x; i < h->n_unk_lms * 3; i += LM_THREADS) v.r_lm_pos[i] = v.lm_cur[(size_t)v.unk_lm[i / 3] * 3 + (i % 3)];
+	for (size_t i = threadIdx.x; i < (size_t)2 * h->n_pairs * S; i += LM_THREADS) v.r_slot_pose[i] = v.slot[i];
+	for (int i = threadIdx.x; i < h->n_obs; i += LM_THREADS) v.r_obs_valid[i] = v.valid[i];
+	for (int i = threadIdx.x; i < h->n_unk_lms; i += LM_THREADS) v.r_lm_inv[i] = sh.trials > 0 ? v.lm_inv[i] : 0;
+	for (int i = threadIdx.x; i < h->n_unk_lms * 9; i += LM_THREADS) v.r_Hf_diag[i] = v.Hf[i];
+	if (threadIdx.x == 0) {
+		srba_stats_t *st = v.stats;
+		st->num_iters = sh.iter;
+		st->num_trials = sh.trials;
+		st->num_accepted = sh.accepted;
+		st->num_relinearized = sh.relin;
+		st->num_chol_failures = sh.cholfail;
+		st->num_jacobians = h->n_blkA + ((OBSK == SRBA_OBS_RELPOSES2D) ? 0 : h->n_blkF);
+		st->hessian_valid = sh.trials > 0;
+		st->status = sh.status;
+		st->total_sqr_error_final = sh.err;
+		st->obs_rmse = sh.rmse;
+		st->lambda_final = sh.lambda;
+	}
+}
+
+__global__ void __launch_bounds__(LM_THREADS) srba_lm_batch_kernel(const char *img, const uint64_t *img_off, char *ws, const uint64_t *ws_off,
+                                                                    char *res, const uint64_t *res_off, const int32_t *order, int n_problems) {
+	__shared__ Shared sh;
+	for (int q = blockIdx.x; q < n_problems; q += gridDim.x) {
+		const int pi = order[q];
+		const char *pimg = img + img_off[pi];
+		const DevProblem *h = reinterpret_cast<const DevProblem *>(pimg);
+		char *pws = ws + ws_off[pi];
+		char *pres = res + res_off[pi];
+		const int pk = h->model.pose_kind, ok = h->model.obs_kind;
+		if (pk == SRBA_POSE_SE2 && ok == SRBA_OBS_RELPOSES2D) lm_program<3, SRBA_OBS_RELPOSES2D>(h, pimg, pws, pres, sh);
+		else if (pk == SRBA_POSE_SE3 && ok == SRBA_OBS_CARTESIAN3D) lm_program<6, SRBA_OBS_CARTESIAN3D>(h, pimg, pws, pres, sh);
+		else if (pk == SRBA_POSE_SE3 && ok == SRBA_OBS_MONO) lm_program<6, SRBA_OBS_MONO>(h, pimg, pws, pres, sh);
+		else if (pk == SRBA_POSE_SE3 && ok == SRBA_OBS_STEREO) lm_program<6, SRBA_OBS_STEREO>(h, pimg, pws, pres, sh);
+		__syncthreads();
+	}
+}
+
+}  // namespace
+
+extern "C" int srba_launch_lm_batch(const char *img, const uint64_t *img_off, char *ws, const uint64_t *ws_off, char *res, const uint64_t *res_off,
+                                    const int32_t *order, int n_problems, int grid, void *stream) {
+	srba_lm_batch_kernel<<<grid, LM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(img, img_off, ws, ws_off, res, res_off, order, n_problems);
+	return (int)cudaGetLastError();
+}

@@ -1,0 +1,170 @@
+"""CPU-only checks of the product's host engine (srba_b200/csrc/host_engine.hpp) against the oracle: graph
+construction, edge-creation policy, spanning trees, bootstrap values, unknown selection and the FLATTENED problem
+(index arrays must be bit-exact).  No GPU work: the product engine runs with
+run_local_optimization=False and the oracle's numeric state is injected after each keyframe."""
+import math
+
+import numpy as np
+import pytest
+
+import srba_b200 as sb
+from fixtures import FX, se2_noise_lambda
+from oracle import pyoracle as po
+from srba_b200 import datasets as D
+
+S2 = dict(pose_kind=0, obs_kind=0, noise_kind=1, max_tree_depth=3, max_optimize_depth=3, submap_size=10, min_obs_to_loop_closure=1,
+          max_error_per_obs_to_stop=1e-8)
+
+
+def make_pair(kw):
+    return po.OracleEngine(po.default_params(**kw)), sb.RbaEngine(sb.default_engine_params(**kw))
+
+
+def flat_pose_chain(flat):
+    """numpy re-evaluation of the flattened numeric spanning tree (SE2 only): slot poses from edge poses + paths."""
+    p = flat.p
+    edge = flat.array("edge_pose", p.n_edges * 3, np.float64).reshape(-1, 3)
+    ptr, pe, pd = flat.array("pair_path_ptr", p.n_pairs + 1, np.int32), flat.array("path_edge", p.n_path, np.int32), flat.array("path_dir", p.n_path, np.uint8)
+    slots = np.zeros((2 * p.n_pairs, 3))
+    for t in range(p.n_pairs):
+        acc = np.zeros(3)
+        for k in range(ptr[t], ptr[t + 1]):
+            acc = D.se2_compose(acc, edge[pe[k]] if pd[k] else D.se2_inverse(edge[pe[k]]))
+        slots[2 * t], slots[2 * t + 1] = acc, D.se2_inverse(acc)
+    return slots
+
+
+def flat_total_error(flat, slots):
+    p = flat.p
+    z = flat.array("obs_z", p.n_obs * 3, np.float64).reshape(-1, 3)
+    os_, mult = flat.array("obs_slot", p.n_obs, np.int32), flat.array("obs_mult", p.n_obs, np.int32)
+    tot = 0.0
+    for i in range(p.n_obs):
+        P = slots[os_[i]] if os_[i] >= 0 else np.zeros(3)
+        c, s = math.cos(P[2]), math.sin(P[2])
+        r = np.array([(z[i, 0] - P[0]) * c + (z[i, 1] - P[1]) * s, -(z[i, 0] - P[0]) * s + (z[i, 1] - P[1]) * c, D.wrap(z[i, 2] - P[2])])
+        tot += mult[i] * float(r @ r)
+    return tot
+
+
+def compare_graph(eo, ep, kf):
+    to, no, do = eo.next_edge(kf)
+    tp, np_, dp = ep.next_edge(kf)
+    assert to.tolist() == tp.tolist() and no.tolist() == np_.tolist() and do.tolist() == dp.tolist()
+    for t in to:
+        a, b = max(kf, int(t)), min(kf, int(t))
+        assert eo.all_edges_path(a, b).tolist() == ep.all_edges_path(a, b).tolist()
+
+
+def run_lockstep(kw, frames, check_every=1):
+    eo, ep = make_pair(kw)
+    eo.trace_enable(True)
+    depth = kw["max_optimize_depth"]
+    for k, f in enumerate(frames):
+        ro = D.feed(eo, f, run_local_optimization=False)
+        rp = D.feed(ep, f, run_local_optimization=False)
+        assert ro["kf_id"] == rp["kf_id"] == k
+        assert ro["created_edges"] == rp["created_edges"]
+        for c in ro["created_edges"]:  # bootstrap values of the new edges
+            fo, to_, po_ = eo.get_edge(c["id"])
+            fp, tp_, pp_ = ep.get_edge(c["id"])
+            assert (fo, to_) == (fp, tp_)
+            np.testing.assert_allclose(po_, pp_, rtol=0, atol=1e-12)
+        if k % check_every == 0:
+            compare_graph(eo, ep, k)
+        # stage 1 (define_new_keyframe.h:59-91) then the local area, on the oracle; flatten on the product BEFORE each
+        calls = [("edges", [c["id"]]) for c in ro["created_edges"] if not c["has_approx_init_val"]] + [("area", None)]
+        for kind, ids in calls:
+            if kind == "edges":
+                flat = ep.flatten(ids)
+            else:
+                sel_k2k, sel_lm = ep.select_local_area(k, depth)
+                flat = ep.flatten(sel_k2k, sel_lm) if (len(sel_k2k) or len(sel_lm)) else None
+            eo.trace_clear()
+            info = eo.optimize_edges(ids) if kind == "edges" else eo.optimize_local_area(k, depth)
+            tr = eo.traces()
+            if flat is None:
+                assert len(tr) == 0 or info["num_total_scalar_optimized"] == 0
+                continue
+            assert len(tr) == 1
+            t = tr[0]
+            fid = flat.ids()
+            assert fid["k2k_ids"].tolist() == t["k2k_ids"].tolist()       # unknown edges, BFS visit order
+            assert fid["lm_ids"].tolist() == t["lm_ids"].tolist()         # unknown landmarks, threshold-crossing order
+            # observation rows incl. the duplicates of optimize_edges.h:177-193
+            mult = flat.array("obs_mult", flat.p.n_obs, np.int32)
+            assert flat.p.n_total_obs_rows == len(t["obs_idx"]) == info["num_observations"] == int(mult.sum())
+            uniq, cnt = np.unique(t["obs_idx"], return_counts=True)
+            mine = dict(zip(fid["obs_global"].tolist(), mult.tolist()))
+            assert mine == dict(zip(uniq.tolist(), cnt.tolist()))
+            first_touch = list(dict.fromkeys(t["obs_idx"].tolist()))
+            assert fid["obs_global"].tolist() == first_touch              # residual order = first-touch order
+            assert flat.p.n_blkA + (0 if kw["obs_kind"] == 0 else flat.p.n_blkF) == info["num_jacobians"]
+            if kw["pose_kind"] == 0:
+                # numeric spanning tree + residuals of the flattened problem reproduce the oracle's initial error
+                # (the oracle evaluated it on the same pre-optimisation state)
+                slots = flat_pose_chain(flat)
+                tot = flat_total_error(flat, slots)
+                assert abs(tot - info["total_sqr_error_init"]) <= 1e-9 * max(1.0, info["total_sqr_error_init"])
+                npairs = sum(len(eo.next_edge(int(fr))[0][eo.next_edge(int(fr))[0] < fr]) for fr in np.unique(fid["pairs"][:, 0]))
+                assert info["num_span_tree_numeric_updates"] >= flat.p.n_pairs > 0 and npairs >= 0
+        # inject the oracle's numeric state into the product engine
+        _, poses = eo.edges()
+        for i in range(eo.num_edges):
+            ep.set_edge_pose(i, poses[i])
+        ids_, _, pos = eo.unknown_lms()
+        for i, q in zip(ids_, pos):
+            ep.set_lm_pos(int(i), q)
+        for src in range(eo.num_keyframes):
+            tt, pp, _ = eo.num(src)
+            for dst, q in zip(tt, pp):
+                ep.set_num(src, int(dst), q)
+    return eo, ep
+
+
+def test_lockstep_se2_graph_slam_tour():
+    ds = D.graphslam_se2_tour(260, seed=3)
+    kw = dict(S2, noise_lambda=D.se2_noise_lambda(ds["sigma_xy"], ds["sigma_yaw"]))
+    run_lockstep(kw, ds["frames"])
+
+
+def test_lockstep_se2_reference_fixtures():
+    for key, cols in (("submaps_edge_init_values", (2, 3, 4)), ("tutorial_relgraphslam_se2", (2, 3, 5))):
+        rows = FX[key]["dataset"] if key == "submaps_edge_init_values" else FX[key]["dataset"]["rows"]
+        nkf = int(max(r[0] for r in rows)) + 1
+        frames = []
+        for kf in range(nkf):
+            ids, obs, fixed = [kf], [[0, 0, 0]], [1]
+            for r in rows:
+                if int(r[0]) == kf:
+                    ids.append(int(r[1])); obs.append([r[cols[0]], r[cols[1]], r[cols[2]]]); fixed.append(0)
+            frames.append(dict(feat_id=np.array(ids, np.uint64), obs=np.array(obs, float), is_fixed=np.array(fixed, np.uint8),
+                               is_unknown_with_init_val=np.zeros(len(ids), np.uint8), feat_rel_pos=np.zeros((len(ids), 3))))
+        kw = dict(S2, submap_size=5, noise_lambda=se2_noise_lambda(0.001, math.radians(0.05)))
+        run_lockstep(kw, frames)
+
+
+@pytest.mark.parametrize("obs_kind,name", [(1, "cartesian3d"), (3, "stereo"), (2, "mono")])
+def test_lockstep_se3_landmark_slam(obs_kind, name):
+    ds = D.landmark_slam_se3(n_kfs=60, n_lms=400, seed=2, obs_kind=name, lm_init_sigma=0.05 if name == "mono" else None)
+    kw = dict(pose_kind=1, obs_kind=obs_kind, noise_kind=0, noise_std=0.5 if obs_kind != 1 else 1e-3, max_tree_depth=3, max_optimize_depth=3,
+              submap_size=10, min_obs_to_loop_closure=4)
+    if obs_kind != 1:
+        kw.update(sensor_pose_kind=1, sensor_pose=ds["sensor_pose_xyzypr"], cam_left=ds["cam"], cam_right=ds["cam"],
+                  right_cam_pose=[ds["baseline"], 0, 0, 1, 0, 0, 0])
+    run_lockstep(kw, ds["frames"], check_every=5)
+
+
+def test_symbols_and_no_device_error():
+    """The C-ABI library loads, exports every declared symbol, and fails loudly (no CPU fallback) without a GPU."""
+    from srba_b200 import _capi as K
+    L = K.lib()
+    for s in K.EXPORTED_SYMBOLS:
+        assert hasattr(L, s), s
+    if L.srba_b200_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    ds = D.graphslam_se2_tour(12, seed=1)
+    ep = sb.RbaEngine(sb.default_engine_params(**dict(S2, noise_lambda=D.se2_noise_lambda(1e-3, 1e-3))))
+    D.feed(ep, ds["frames"][0])
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        D.feed(ep, ds["frames"][1])
