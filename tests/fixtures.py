@@ -58,3 +58,18 @@ def se2_noise_lambda(sxy, syaw):
     nl = np.zeros(16)
     nl[:9] = np.diag([1 / sxy ** 2, 1 / sxy ** 2, 1 / syaw ** 2]).ravel()
     return nl
+
+
+def inject_state(eo, ep):
+    """Copies the oracle's numeric state (edge poses, unknown landmark positions, numeric spanning tree) into the
+    product engine so that the next optimize call of both starts from bit-identical inputs."""
+    _, poses = eo.edges()
+    for i in range(eo.num_edges):
+        ep.set_edge_pose(i, poses[i])
+    ids_, _, pos = eo.unknown_lms()
+    for i, q in zip(ids_, pos):
+        ep.set_lm_pos(int(i), q)
+    for src in range(eo.num_keyframes):
+        tt, pp, _ = eo.num(src)
+        for dst, q in zip(tt, pp):
+            ep.set_num(src, int(dst), q)

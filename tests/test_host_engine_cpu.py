@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import srba_b200 as sb
-from fixtures import FX, se2_noise_lambda
+from fixtures import FX, inject_state, se2_noise_lambda
 from oracle import pyoracle as po
 from srba_b200 import datasets as D
 
@@ -108,17 +108,7 @@ def run_lockstep(kw, frames, check_every=1):
                 assert abs(tot - info["total_sqr_error_init"]) <= 1e-9 * max(1.0, info["total_sqr_error_init"])
                 npairs = sum(len(eo.next_edge(int(fr))[0][eo.next_edge(int(fr))[0] < fr]) for fr in np.unique(fid["pairs"][:, 0]))
                 assert info["num_span_tree_numeric_updates"] >= flat.p.n_pairs > 0 and npairs >= 0
-        # inject the oracle's numeric state into the product engine
-        _, poses = eo.edges()
-        for i in range(eo.num_edges):
-            ep.set_edge_pose(i, poses[i])
-        ids_, _, pos = eo.unknown_lms()
-        for i, q in zip(ids_, pos):
-            ep.set_lm_pos(int(i), q)
-        for src in range(eo.num_keyframes):
-            tt, pp, _ = eo.num(src)
-            for dst, q in zip(tt, pp):
-                ep.set_num(src, int(dst), q)
+        inject_state(eo, ep)  # the oracle's numeric state becomes the product engine's
     return eo, ep
 
 
