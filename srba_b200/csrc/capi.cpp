@@ -194,8 +194,37 @@ double problem_cost(const DevProblem &h) {
 }
 }  // namespace
 
+// Grow-only buffer pool reused by the synchronous entry points (srba_b200_optimize / _optimize_batch): the library
+// keeps no problem state between calls, only this reusable workspace (SURVEY.md §8b "optional reusable device workspace").
+struct Pool {
+	char *h_img = nullptr, *h_res = nullptr, *d_img = nullptr, *d_ws = nullptr, *d_res = nullptr;
+	uint64_t h_img_cap = 0, h_res_cap = 0, d_img_cap = 0, d_ws_cap = 0, d_res_cap = 0;
+	cudaStream_t stream = nullptr;
+};
+static thread_local Pool g_pool;
+
+static bool pool_reserve_host(char **p, uint64_t *cap, uint64_t need) {
+	if (*cap >= need) return true;
+	if (*p) cudaFreeHost(*p);
+	*p = nullptr; *cap = 0;
+	const uint64_t want = need + need / 4 + 4096;
+	if (cudaMallocHost(p, want) != cudaSuccess) return false;
+	*cap = want;
+	return true;
+}
+static bool pool_reserve_dev(char **p, uint64_t *cap, uint64_t need) {
+	if (*cap >= need) return true;
+	if (*p) cudaFree(*p);
+	*p = nullptr; *cap = 0;
+	const uint64_t want = need + need / 4 + 4096;
+	if (cudaMalloc(p, want) != cudaSuccess) return false;
+	*cap = want;
+	return true;
+}
+
 struct srba_batch {
 	int n = 0;
+	bool pooled = false;
 	std::vector<DevProblem> hdr;
 	std::vector<uint64_t> img_off, ws_off, res_off;
 	std::vector<int32_t> order;
@@ -220,6 +249,7 @@ int srba_b200_device_count(void) {
 
 void srba_b200_batch_destroy(srba_batch_t *b) {
 	if (!b) return;
+	if (b->pooled) { delete b; return; }
 	if (b->h_img) cudaFreeHost(b->h_img);
 	if (b->h_res) cudaFreeHost(b->h_res);
 	if (b->d_img) cudaFree(b->d_img);
@@ -228,7 +258,9 @@ void srba_b200_batch_destroy(srba_batch_t *b) {
 	delete b;
 }
 
-srba_batch_t *srba_b200_batch_create(int32_t n, const srba_problem_t *const *in, int32_t trace_cap) {
+static srba_batch_t *batch_create_impl(int32_t n, const srba_problem_t *const *in, int32_t trace_cap, Pool *pool);
+srba_batch_t *srba_b200_batch_create(int32_t n, const srba_problem_t *const *in, int32_t trace_cap) { return batch_create_impl(n, in, trace_cap, nullptr); }
+static srba_batch_t *batch_create_impl(int32_t n, const srba_problem_t *const *in, int32_t trace_cap, Pool *pool) {
 	if (n <= 0 || !in) { fail(SRBA_ERR_BAD_ARGUMENT, "empty batch"); return nullptr; }
 	if (srba_b200_device_count() <= 0) { fail(SRBA_ERR_NO_DEVICE, "no CUDA device: the srba_b200 hot path has no CPU fallback"); return nullptr; }
 	for (int i = 0; i < n; i++)
@@ -260,14 +292,23 @@ srba_batch_t *srba_b200_batch_create(int32_t n, const srba_problem_t *const *in,
 	cudaDeviceProp prop;
 	int dev = 0;
 	if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess) b->sm_count = prop.multiProcessorCount;
-	if (cudaMallocHost(&b->h_img, b->img_bytes) != cudaSuccess || cudaMallocHost(&b->h_res, b->res_bytes) != cudaSuccess ||
-	    cudaMalloc(&b->d_img, b->img_bytes) != cudaSuccess || cudaMalloc(&b->d_ws, b->ws_bytes) != cudaSuccess ||
-	    cudaMalloc(&b->d_res, b->res_bytes) != cudaSuccess) {
+	bool ok;
+	if (pool) {
+		b->pooled = true;
+		ok = pool_reserve_host(&pool->h_img, &pool->h_img_cap, b->img_bytes) && pool_reserve_host(&pool->h_res, &pool->h_res_cap, b->res_bytes) &&
+		     pool_reserve_dev(&pool->d_img, &pool->d_img_cap, b->img_bytes) && pool_reserve_dev(&pool->d_ws, &pool->d_ws_cap, b->ws_bytes) &&
+		     pool_reserve_dev(&pool->d_res, &pool->d_res_cap, b->res_bytes);
+		b->h_img = pool->h_img; b->h_res = pool->h_res; b->d_img = pool->d_img; b->d_ws = pool->d_ws; b->d_res = pool->d_res;
+	} else {
+		ok = cudaMallocHost(&b->h_img, b->img_bytes) == cudaSuccess && cudaMallocHost(&b->h_res, b->res_bytes) == cudaSuccess &&
+		     cudaMalloc(&b->d_img, b->img_bytes) == cudaSuccess && cudaMalloc(&b->d_ws, b->ws_bytes) == cudaSuccess &&
+		     cudaMalloc(&b->d_res, b->res_bytes) == cudaSuccess;
+	}
+	if (!ok) {
 		fail(SRBA_ERR_CUDA, std::string("allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
 		srba_b200_batch_destroy(b);
 		return nullptr;
 	}
-	std::memset(b->h_img, 0, b->img_bytes);
 	std::memcpy(b->h_img + b->tab_img_off, b->img_off.data(), (size_t)n * 8);
 	std::memcpy(b->h_img + b->tab_ws_off, b->ws_off.data(), (size_t)n * 8);
 	std::memcpy(b->h_img + b->tab_res_off, b->res_off.data(), (size_t)n * 8);
@@ -360,11 +401,11 @@ int srba_b200_optimize_batch(int32_t n, const srba_problem_t *const *in, srba_re
 		if (out[i]->dense_hessian) want_dense = 1;
 	}
 	if (want_dense && tcap == 0) tcap = 1;
-	srba_batch_t *b = srba_b200_batch_create(n, in, want_dense ? -tcap : tcap);
+	srba_batch_t *b = batch_create_impl(n, in, want_dense ? -tcap : tcap, &g_pool);
 	if (!b) return g_code != SRBA_OK ? g_code : SRBA_ERR_INTERNAL;
-	cudaStream_t st = nullptr;
 	int rc = SRBA_OK;
-	if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) rc = fail(SRBA_ERR_CUDA, "cudaStreamCreate failed");
+	if (!g_pool.stream && cudaStreamCreateWithFlags(&g_pool.stream, cudaStreamNonBlocking) != cudaSuccess) rc = fail(SRBA_ERR_CUDA, "cudaStreamCreate failed");
+	cudaStream_t st = g_pool.stream;
 	if (rc == SRBA_OK) rc = srba_b200_batch_upload(b, st);
 	if (rc == SRBA_OK) rc = srba_b200_batch_run(b, st);
 	if (rc == SRBA_OK) rc = srba_b200_batch_download(b, st);
@@ -373,7 +414,6 @@ int srba_b200_optimize_batch(int32_t n, const srba_problem_t *const *in, srba_re
 			const int r = srba_b200_batch_unpack(b, i, out[i]);
 			if (r != SRBA_OK && rc == SRBA_OK) rc = r;
 		}
-	if (st) cudaStreamDestroy(st);
 	srba_b200_batch_destroy(b);
 	return rc;
 }
