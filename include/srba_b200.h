@@ -158,6 +158,9 @@ void srba_b200_batch_destroy(srba_batch_t *b);
 int64_t srba_b200_batch_h2d_bytes(const srba_batch_t *b);
 int64_t srba_b200_batch_d2h_bytes(const srba_batch_t *b);
 int64_t srba_b200_batch_kernel_launches(const srba_batch_t *b); /* launches issued by the last batch_run */
+/* SM clock cycles problem i spent in each stage of the LM program (measured by the kernel itself with clock64):
+ * init, schur+fill, cholesky, backsub, features, update, chain, residuals, rho, jacobians, hessian, gradient, control, output */
+int srba_b200_batch_stage_cycles(srba_batch_t *b, int32_t i, uint64_t out[16]);
 /* Algorithmic bytes of one accepted+relinearised LM iteration of the whole batch (SURVEY.md §8d formulas), per stage:
  * out[0]=B_chain out[1]=B_assem out[2]=B_schur out[3]=B_chol out[4]=F_chol(flop) */
 void srba_b200_batch_algorithmic_bytes(const srba_batch_t *b, double out[5]);

@@ -52,6 +52,14 @@ class Batch:
         self.L.srba_b200_batch_unpack(self.h, i, C.byref(r))
         return r.stats.as_dict()
 
+    STAGES = ("init", "schur_fill", "cholesky", "backsub", "features", "update", "chain", "residuals", "rho", "jacobians", "hessian",
+              "gradient", "control", "output")
+
+    def stage_cycles(self, i):
+        out = np.zeros(16, np.uint64)
+        self._chk(self.L.srba_b200_batch_stage_cycles(self.h, i, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return dict(zip(self.STAGES, out[:len(self.STAGES)].tolist()))
+
     @property
     def h2d_bytes(self):
         return self.L.srba_b200_batch_h2d_bytes(self.h)

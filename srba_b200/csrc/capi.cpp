@@ -12,8 +12,8 @@
 
 #include "dev_types.h"
 
-extern "C" int srba_launch_lm_batch(const char *img, const uint64_t *img_off, char *ws, const uint64_t *ws_off, char *res, const uint64_t *res_off,
-                                    const int32_t *order, int n_problems, int grid, void *stream);
+extern "C" int srba_launch_lm_batch(int model, const char *img, const uint64_t *img_off, char *ws, const uint64_t *ws_off, char *res,
+                                    const uint64_t *res_off, const int32_t *order, int n_problems, int grid, int panel_cap, void *stream);
 
 namespace {
 thread_local std::string g_err;
@@ -184,6 +184,7 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 	h.res_dense = R.add(want_dense ? (size_t)h.n_dense * h.n_dense * 8 : 0);
 	h.res_trace = R.add((size_t)trace_cap * 6 * 8);
 	h.res_trace_delta = R.add((size_t)trace_cap * h.n_scalars * 8);
+	h.res_stage_cycles = R.add(16 * 8);
 	h.res_bytes = R.total();
 	if (base) std::memcpy(base, &h, sizeof(h));
 }
@@ -227,7 +228,9 @@ struct srba_batch {
 	bool pooled = false;
 	std::vector<DevProblem> hdr;
 	std::vector<uint64_t> img_off, ws_off, res_off;
-	std::vector<int32_t> order;
+	std::vector<int32_t> order;      // grouped by model, cost-descending inside each group
+	int group_begin[5] = {0, 0, 0, 0, 0};
+	int group_max_n[4] = {0, 0, 0, 0};
 	uint64_t tab_img_off = 0, tab_ws_off = 0, tab_res_off = 0, tab_order = 0;
 	uint64_t img_bytes = 0, ws_bytes = 0, res_bytes = 0;
 	char *h_img = nullptr, *h_res = nullptr;
@@ -288,7 +291,20 @@ static srba_batch_t *batch_create_impl(int32_t n, const srba_problem_t *const *i
 	}
 	b->img_bytes = I.total(); b->ws_bytes = std::max<uint64_t>(ws, 16); b->res_bytes = std::max<uint64_t>(rs, 16);
 	std::iota(b->order.begin(), b->order.end(), 0);
-	std::stable_sort(b->order.begin(), b->order.end(), [&](int a, int c) { return problem_cost(b->hdr[a]) > problem_cost(b->hdr[c]); });
+	auto model_of = [&](int i) {
+		const srba_model_t &m = b->hdr[i].model;
+		return m.pose_kind == SRBA_POSE_SE2 ? 0 : (m.obs_kind == SRBA_OBS_CARTESIAN3D ? 1 : (m.obs_kind == SRBA_OBS_MONO ? 2 : 3));
+	};
+	std::stable_sort(b->order.begin(), b->order.end(), [&](int a, int c) {
+		const int ma = model_of(a), mc = model_of(c);
+		if (ma != mc) return ma < mc;
+		return problem_cost(b->hdr[a]) > problem_cost(b->hdr[c]);
+	});
+	{
+		int cnt[4] = {0, 0, 0, 0};
+		for (int i = 0; i < n; i++) { const int g = model_of(i); cnt[g]++; b->group_max_n[g] = std::max(b->group_max_n[g], b->hdr[i].n_dense); }
+		for (int g = 0; g < 4; g++) b->group_begin[g + 1] = b->group_begin[g] + cnt[g];
+	}
 	cudaDeviceProp prop;
 	int dev = 0;
 	if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess) b->sm_count = prop.multiProcessorCount;
@@ -330,13 +346,20 @@ int srba_b200_batch_upload(srba_batch_t *b, void *stream) {
 int srba_b200_batch_run(srba_batch_t *b, void *stream) {
 	if (!b) return fail(SRBA_ERR_BAD_ARGUMENT, "null batch");
 	if (!b->uploaded) return fail(SRBA_ERR_BAD_ARGUMENT, "batch_run before batch_upload");
-	const int grid = std::min(b->n, b->sm_count * 2);
-	const int rc = srba_launch_lm_batch(b->d_img, reinterpret_cast<const uint64_t *>(b->d_img + b->tab_img_off), b->d_ws,
-	                                    reinterpret_cast<const uint64_t *>(b->d_img + b->tab_ws_off), b->d_res,
-	                                    reinterpret_cast<const uint64_t *>(b->d_img + b->tab_res_off),
-	                                    reinterpret_cast<const int32_t *>(b->d_img + b->tab_order), b->n, grid, stream);
-	if (rc != 0) return fail(SRBA_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
-	b->launches = 1;
+	b->launches = 0;
+	for (int g = 0; g < 4; g++) {
+		const int cnt = b->group_begin[g + 1] - b->group_begin[g];
+		if (!cnt) continue;
+		// one CTA per problem, dispatched in cost-descending order (largest first); staged Cholesky panel sized for the
+		// largest problem of the group, capped so that 2 CTAs/SM stay resident
+		const int panel_cap = std::min(std::max((b->group_max_n[g] + 1 + 3) / 4 * 4, 24), 1024);
+		const int rc = srba_launch_lm_batch(g, b->d_img, reinterpret_cast<const uint64_t *>(b->d_img + b->tab_img_off), b->d_ws,
+		                                    reinterpret_cast<const uint64_t *>(b->d_img + b->tab_ws_off), b->d_res,
+		                                    reinterpret_cast<const uint64_t *>(b->d_img + b->tab_res_off),
+		                                    reinterpret_cast<const int32_t *>(b->d_img + b->tab_order) + b->group_begin[g], cnt, cnt, panel_cap, stream);
+		if (rc != 0) return fail(SRBA_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
+		b->launches++;
+	}
 	return SRBA_OK;
 }
 
@@ -369,6 +392,11 @@ int srba_b200_batch_unpack(srba_batch_t *b, int32_t i, srba_result_t *out) {
 	return out->stats.status;
 }
 
+int srba_b200_batch_stage_cycles(srba_batch_t *b, int32_t i, uint64_t out[16]) {
+	if (!b || i < 0 || i >= b->n || !b->downloaded) return fail(SRBA_ERR_BAD_ARGUMENT, "bad stage_cycles arguments");
+	std::memcpy(out, b->h_res + b->res_off[i] + b->hdr[i].res_stage_cycles, 16 * 8);
+	return SRBA_OK;
+}
 int64_t srba_b200_batch_h2d_bytes(const srba_batch_t *b) { return b ? (int64_t)b->img_bytes : 0; }
 int64_t srba_b200_batch_d2h_bytes(const srba_batch_t *b) { return b ? (int64_t)b->res_bytes : 0; }
 int64_t srba_b200_batch_kernel_launches(const srba_batch_t *b) { return b ? b->launches : 0; }

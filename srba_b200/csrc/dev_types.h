@@ -42,6 +42,6 @@ struct DevProblem {
 	uint64_t ws_bytes;
 
 	// ---- result blob
-	uint64_t res_stats, res_edge_pose, res_lm_pos, res_slot_pose, res_obs_valid, res_lm_inv, res_Hf_diag, res_dense, res_trace, res_trace_delta;
+	uint64_t res_stats, res_edge_pose, res_lm_pos, res_slot_pose, res_obs_valid, res_lm_inv, res_Hf_diag, res_dense, res_trace, res_trace_delta, res_stage_cycles;
 	uint64_t res_bytes;
 };

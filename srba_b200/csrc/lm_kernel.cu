@@ -193,8 +193,14 @@ __device__ void make_view(View &v, const DevProblem *h, const char *img, char *w
 }
 
 // ------------------------------------------------------------------------------------------------ team (one CTA)
+enum { ST_INIT = 0, ST_SCHUR, ST_CHOL, ST_BACKSUB, ST_FEATURES, ST_UPDATE, ST_CHAIN, ST_RESID, ST_RHO, ST_JACOB, ST_HESS, ST_GRAD, ST_CTRL, ST_OUT, ST_COUNT };
+
 struct Shared {
 	double red[LM_THREADS / 32];
+	unsigned long long stage_cycles[ST_COUNT];
+	unsigned long long t_last;
+	double U11[64];         // diagonal block of the blocked Cholesky
+	double xblk[8];
 	double bcast;
 	// LM state (impl/optimize_edges.h:361-363,452-459)
 	double lambda, nu, err, rmse, rho, new_err;
@@ -790,48 +796,309 @@ __device__ void stage_schur_and_fill(const View &v, double lambda) {
 	}
 }
 
-// K4: dense Cholesky A = U^T U on the upper triangle + forward substitution (augmented column) + back substitution
-// (Eigen::LLT<Upper>, impl/lev-marq_solvers.h:527-549).  Right-looking; returns false on a non-positive pivot.
-__device__ bool stage_cholesky_solve(const View &v, Shared &sh) {
+// K4: dense Cholesky A = U^T U on the upper triangle + forward substitution (augmented column n) + back substitution
+// (Eigen::LLT<Upper>, impl/lev-marq_solvers.h:527-549).  Blocked right-looking, NB = 8:
+//   (a) warp 0 factors the 8x8 diagonal block (already updated by earlier block columns) and keeps U11 in shared memory,
+//   (b) every thread solves one column of the 8-row panel  U[kb:kb+8, j] = U11^-T A[kb:kb+8, j]  (coalesced row reads),
+//       the panel is staged in shared memory,
+//   (c) the trailing trapezoid gets the rank-8 update from the staged panel with 4x4 register tiles (one global RMW per
+//       element per block column instead of one per column).
+// 3 barriers per block column instead of 3 per column.  Returns false on a non-positive pivot (Eigen: "if (x<=0) return k").
+#define CH_NB 8
+__device__ bool stage_cholesky(const View &v, Shared &sh, double *panel, int panel_cap) {
 	const int n = v.h->n_dense, ld = v.h->ld_dense;
 	double *A = v.dense;
+	const int ncols = n + 1;  // including the augmented column
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = LM_THREADS / 32;
 	if (threadIdx.x == 0) sh.chol_ok = 1;
 	__syncthreads();
-	for (int k = 0; k < n; k++) {
-		double *rowk = A + (size_t)k * ld;
-		const double d = rowk[k];
-		if (!(d > 0)) {  // Eigen: if (x<=0) return k  (NaN continues in Eigen; treated as failure here is unreachable for finite input)
-			if (d <= 0) { if (threadIdx.x == 0) sh.chol_ok = 0; __syncthreads(); return false; }
+	for (int kb = 0; kb < n; kb += CH_NB) {
+		const int w = min(CH_NB, n - kb);
+		// (a) diagonal block
+		if (warp == 0) {
+			for (int e = lane; e < 64; e += 32) {
+				const int r = e >> 3, c = e & 7;
+				sh.U11[e] = (r < w && c < w && c >= r) ? A[(size_t)(kb + r) * ld + kb + c] : 0.0;
+			}
+			__syncwarp();
+			for (int r = 0; r < w; r++) {
+				const double d = sh.U11[r * 8 + r];
+				if (d <= 0) { if (lane == 0) sh.chol_ok = 0; break; }
+				const double sd = sqrt(d);
+				__syncwarp();
+				if (lane < 8 && lane >= r && lane < w) sh.U11[r * 8 + lane] = (lane == r) ? sd : sh.U11[r * 8 + lane] / sd;
+				__syncwarp();
+				for (int e = lane; e < 64; e += 32) {
+					const int i = e >> 3, c = e & 7;
+					if (i > r && i < w && c >= i && c < w) sh.U11[e] -= sh.U11[r * 8 + i] * sh.U11[r * 8 + c];
+				}
+				__syncwarp();
+			}
+			if (sh.chol_ok)
+				for (int e = lane; e < 64; e += 32) {
+					const int r = e >> 3, c = e & 7;
+					if (r < w && c < w && c >= r) A[(size_t)(kb + r) * ld + kb + c] = sh.U11[e];
+				}
 		}
-		const double sd = sqrt(d);
-		__syncthreads();  // everybody has read the pivot
-		for (int j = k + threadIdx.x; j <= n; j += LM_THREADS) rowk[j] = (j == k) ? sd : rowk[j] / sd;
 		__syncthreads();
-		// trailing update: rows i in (k, n), columns j in [i, n]
-		const int m = n - k - 1;
-		if (m > 0) {
-			// flatten the (i,j>=i) trapezoid row by row; a warp handles a row segment for coalescing
-			const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = LM_THREADS / 32;
-			for (int i = k + 1 + warp; i < n; i += nw) {
-				const double uki = rowk[i];
-				double *rowi = A + (size_t)i * ld;
-				for (int j = i + lane; j <= n; j += 32) rowi[j] -= uki * rowk[j];
+		if (!sh.chol_ok) return false;
+		const int j0 = kb + w;           // first trailing column
+		const int m = ncols - j0;        // trailing columns incl. the augmented one
+		if (m <= 0) break;
+		const bool staged = (m <= panel_cap);
+		// (b) panel solve: thread per column
+		for (int jj = threadIdx.x; jj < m; jj += LM_THREADS) {
+			double x[CH_NB];
+#pragma unroll
+			for (int r = 0; r < CH_NB; r++) {
+				if (r < w) {
+					double s = A[(size_t)(kb + r) * ld + j0 + jj];
+#pragma unroll
+					for (int q = 0; q < CH_NB; q++)
+						if (q < r) s -= sh.U11[q * 8 + r] * x[q];
+					x[r] = s / sh.U11[r * 8 + r];
+					A[(size_t)(kb + r) * ld + j0 + jj] = x[r];
+					if (staged) panel[r * panel_cap + jj] = x[r];
+				} else if (staged) panel[r * panel_cap + jj] = 0.0;
+			}
+		}
+		__syncthreads();
+		// (c) trailing update on rows i in [j0, n), columns j in [i, n]  (local indices i' = i - j0, j' = j - j0)
+		const int mr = n - j0;  // trailing rows
+		if (mr > 0) {
+			const int MT = (m + 3) >> 2, MR = (mr + 3) >> 2;
+			for (int ti = warp; ti < MR; ti += nw) {
+				for (int tj = ti + lane; tj < MT; tj += 32) {
+					double acc[4][4];
+#pragma unroll
+					for (int a = 0; a < 4; a++)
+#pragma unroll
+						for (int b = 0; b < 4; b++) acc[a][b] = 0;
+#pragma unroll
+					for (int r = 0; r < CH_NB; r++) {
+						double pi[4], pj[4];
+#pragma unroll
+						for (int a = 0; a < 4; a++) {
+							const int ii = 4 * ti + a, jj = 4 * tj + a;
+							if (staged) {
+								pi[a] = ii < m ? panel[r * panel_cap + ii] : 0.0;
+								pj[a] = jj < m ? panel[r * panel_cap + jj] : 0.0;
+							} else {
+								pi[a] = (r < w && ii < m) ? A[(size_t)(kb + r) * ld + j0 + ii] : 0.0;
+								pj[a] = (r < w && jj < m) ? A[(size_t)(kb + r) * ld + j0 + jj] : 0.0;
+							}
+						}
+#pragma unroll
+						for (int a = 0; a < 4; a++)
+#pragma unroll
+							for (int b = 0; b < 4; b++) acc[a][b] += pi[a] * pj[b];
+					}
+#pragma unroll
+					for (int a = 0; a < 4; a++) {
+						const int ii = 4 * ti + a;
+						if (ii >= mr) continue;
+						double *row = A + (size_t)(j0 + ii) * ld + j0;
+#pragma unroll
+						for (int b = 0; b < 4; b++) {
+							const int jj = 4 * tj + b;
+							if (jj >= ii && jj < m) row[jj] -= acc[a][b];
+						}
+					}
+				}
 			}
 		}
 		__syncthreads();
 	}
-	// back substitution U x = y, y = augmented column; column-oriented
+	return true;
+}
+
+// K4 (small/medium systems): REGISTER-RESIDENT dense Cholesky + forward + back substitution.
+// The upper triangle (plus the augmented right-hand-side column) is cut into 4x4 tiles; every thread owns up to TPT
+// tiles and keeps them in registers for the whole factorisation, so the only shared-memory traffic per tile row is the
+// 4-row panel (read 8 values per 64 FMAs) and there are 2 barriers per FOUR pivots:
+//   D: the owner of diagonal tile (tk,tk) factors it alone (4 pivots, rsqrt) and publishes U11 + 1/diag,
+//   P: owners of (tk,tj>tk) solve U11^T X = T in registers and publish X as the panel,
+//   U: owners of (ti>tk,tj) apply the rank-4 update from the panel.
+// Back substitution runs bottom-up on the same register tiles (y and x live in shared memory).
+// Returns false on a non-positive pivot (Eigen::LLT: "if (x<=0) return k", impl/lev-marq_solvers.h:527-534).
+template <int TPT>
+__device__ bool stage_cholesky_solve_reg(const View &v, Shared &sh, double *sm) {
+	const int n = v.h->n_dense, ld = v.h->ld_dense;
+	const double *A = v.dense;
+	const int TR = (n + 3) >> 2, TC = TR + 1;  // tile column TR holds the augmented column (local column 0)
+	double *sU = sm;                 // 16: U11 of the current tile row
+	double *sRinv = sm + 16;         // 4
+	double *sPanel = sm + 32;        // 4 x (4*TC)
+	double *sY = sPanel + 16 * TC;   // 4*TR
+	double *sX = sY + 4 * TR;        // 4*TR
+	const int PW = 4 * TC;
+	double t[TPT][4][4];
+	int ti_[TPT], tj_[TPT];
+#pragma unroll
+	for (int s = 0; s < TPT; s++) {
+		int q = threadIdx.x + s * LM_THREADS, ti = 0;
+		while (ti < TR && q >= TC - ti) { q -= TC - ti; ti++; }
+		if (ti >= TR) { ti_[s] = -1; tj_[s] = -1; continue; }
+		ti_[s] = ti; tj_[s] = ti + q;
+		const int tj = ti + q;
+#pragma unroll
+		for (int a = 0; a < 4; a++)
+#pragma unroll
+			for (int b = 0; b < 4; b++) {
+				const int i = 4 * ti + a;
+				double val = 0.0;
+				if (tj == TR) { if (b == 0 && i < n) val = A[(size_t)i * ld + n]; }
+				else {
+					const int j = 4 * tj + b;
+					if (i < n && j < n) { if (j >= i) val = A[(size_t)i * ld + j]; }
+					else if (i == j) val = 1.0;  // identity padding of the last partial tile
+				}
+				t[s][a][b] = val;
+			}
+	}
+	if (threadIdx.x == 0) sh.chol_ok = 1;
+	__syncthreads();
+	for (int tk = 0; tk < TR; tk++) {
+		// D: diagonal tile
+#pragma unroll
+		for (int s = 0; s < TPT; s++)
+			if (ti_[s] == tk && tj_[s] == tk) {
+				double rinv[4];
+				bool ok = true;
+#pragma unroll
+				for (int r = 0; r < 4; r++) {
+					const double d = t[s][r][r];
+					if (d <= 0) ok = false;
+					rinv[r] = rsqrt(d);
+					t[s][r][r] = d * rinv[r];
+#pragma unroll
+					for (int c = r + 1; c < 4; c++) t[s][r][c] *= rinv[r];
+#pragma unroll
+					for (int i = r + 1; i < 4; i++)
+#pragma unroll
+						for (int c = i; c < 4; c++) t[s][i][c] -= t[s][r][i] * t[s][r][c];
+				}
+				if (!ok) sh.chol_ok = 0;
+#pragma unroll
+				for (int r = 0; r < 4; r++) {
+					sRinv[r] = rinv[r];
+#pragma unroll
+					for (int c = 0; c < 4; c++) sU[r * 4 + c] = (c >= r) ? t[s][r][c] : 0.0;
+				}
+				t[s][1][0] = rinv[0]; t[s][2][0] = rinv[1]; t[s][2][1] = rinv[2]; t[s][3][0] = rinv[3];  // kept for the back substitution
+			}
+		__syncthreads();
+		if (!sh.chol_ok) return false;
+		// P: panel solve  U11^T X = T
+#pragma unroll
+		for (int s = 0; s < TPT; s++)
+			if (ti_[s] == tk && tj_[s] > tk) {
+				const double u01 = sU[1], u02 = sU[2], u03 = sU[3], u12 = sU[6], u13 = sU[7], u23 = sU[11];
+				const double r0 = sRinv[0], r1 = sRinv[1], r2 = sRinv[2], r3 = sRinv[3];
+#pragma unroll
+				for (int b = 0; b < 4; b++) {
+					const double x0 = t[s][0][b] * r0;
+					const double x1 = (t[s][1][b] - u01 * x0) * r1;
+					const double x2 = (t[s][2][b] - u02 * x0 - u12 * x1) * r2;
+					const double x3 = (t[s][3][b] - u03 * x0 - u13 * x1 - u23 * x2) * r3;
+					t[s][0][b] = x0; t[s][1][b] = x1; t[s][2][b] = x2; t[s][3][b] = x3;
+					const int c = 4 * tj_[s] + b;
+					sPanel[c] = x0; sPanel[PW + c] = x1; sPanel[2 * PW + c] = x2; sPanel[3 * PW + c] = x3;
+				}
+			}
+		__syncthreads();
+		// U: rank-4 update of the tiles below
+#pragma unroll
+		for (int s = 0; s < TPT; s++)
+			if (ti_[s] > tk) {
+#pragma unroll
+				for (int r = 0; r < 4; r++) {
+					double pi[4], pj[4];
+#pragma unroll
+					for (int a = 0; a < 4; a++) { pi[a] = sPanel[r * PW + 4 * ti_[s] + a]; pj[a] = sPanel[r * PW + 4 * tj_[s] + a]; }
+#pragma unroll
+					for (int a = 0; a < 4; a++)
+#pragma unroll
+						for (int b = 0; b < 4; b++) t[s][a][b] -= pi[a] * pj[b];
+				}
+			}
+		// (no barrier: the next D touches only registers/sU, and sPanel is rewritten after the next barrier)
+	}
+	// forward-substituted right-hand side lives in column 0 of the tiles of column TR
+#pragma unroll
+	for (int s = 0; s < TPT; s++)
+		if (tj_[s] == TR) {
+#pragma unroll
+			for (int a = 0; a < 4; a++) sY[4 * ti_[s] + a] = t[s][a][0];
+		}
+	__syncthreads();
+	// back substitution, bottom-up
+	for (int tk = TR - 1; tk >= 0; tk--) {
+#pragma unroll
+		for (int s = 0; s < TPT; s++)
+			if (ti_[s] == tk && tj_[s] == tk) {
+				const double x3 = sY[4 * tk + 3] * t[s][3][0];
+				const double x2 = (sY[4 * tk + 2] - t[s][2][3] * x3) * t[s][2][1];
+				const double x1 = (sY[4 * tk + 1] - t[s][1][2] * x2 - t[s][1][3] * x3) * t[s][2][0];
+				const double x0 = (sY[4 * tk + 0] - t[s][0][1] * x1 - t[s][0][2] * x2 - t[s][0][3] * x3) * t[s][1][0];
+				sX[4 * tk + 0] = x0; sX[4 * tk + 1] = x1; sX[4 * tk + 2] = x2; sX[4 * tk + 3] = x3;
+			}
+		__syncthreads();
+#pragma unroll
+		for (int s = 0; s < TPT; s++)
+			if (tj_[s] == tk && ti_[s] >= 0 && ti_[s] < tk) {
+				const double x0 = sX[4 * tk], x1 = sX[4 * tk + 1], x2 = sX[4 * tk + 2], x3 = sX[4 * tk + 3];
+#pragma unroll
+				for (int a = 0; a < 4; a++) sY[4 * ti_[s] + a] -= t[s][a][0] * x0 + t[s][a][1] * x1 + t[s][a][2] * x2 + t[s][a][3] * x3;
+			}
+		__syncthreads();
+	}
+	for (int i = threadIdx.x; i < n; i += LM_THREADS) v.delta[i] = sX[i];
+	__syncthreads();
+	return true;
+}
+__device__ __forceinline__ int chol_reg_tiles(int n) { const int TR = (n + 3) >> 2; return TR * (TR + 1) / 2 + TR; }
+__device__ __forceinline__ int chol_reg_smem_doubles(int n) { const int TR = (n + 3) >> 2; return 32 + 16 * (TR + 1) + 8 * TR; }
+
+// Back substitution U x = y (y = augmented column), blocked by 8 from the bottom: warp 0 solves the diagonal block,
+// then every thread updates one earlier row with the 8 new unknowns.
+__device__ void stage_backsub(const View &v, Shared &sh) {
+	const int n = v.h->n_dense, ld = v.h->ld_dense;
+	const double *A = v.dense;
 	double *x = v.delta;
 	for (int i = threadIdx.x; i < n; i += LM_THREADS) x[i] = A[(size_t)i * ld + n];
 	__syncthreads();
-	for (int j = n - 1; j >= 0; j--) {
-		if (threadIdx.x == 0) x[j] = x[j] / A[(size_t)j * ld + j];
+	const int nb = (n + CH_NB - 1) / CH_NB;
+	for (int b = nb - 1; b >= 0; b--) {
+		const int kb = b * CH_NB, w = min(CH_NB, n - kb);
+		if (threadIdx.x < 32) {
+			for (int e = threadIdx.x; e < 64; e += 32) {
+				const int r = e >> 3, c = e & 7;
+				sh.U11[e] = (r < w && c < w && c >= r) ? A[(size_t)(kb + r) * ld + kb + c] : 0.0;
+			}
+			if (threadIdx.x < 8) sh.xblk[threadIdx.x] = threadIdx.x < w ? x[kb + threadIdx.x] : 0.0;
+			__syncwarp();
+			if (threadIdx.x == 0) {
+				for (int r = w - 1; r >= 0; r--) {
+					double s = sh.xblk[r];
+					for (int c = r + 1; c < w; c++) s -= sh.U11[r * 8 + c] * sh.xblk[c];
+					sh.xblk[r] = s / sh.U11[r * 8 + r];
+				}
+			}
+			__syncwarp();
+			if (threadIdx.x < w) x[kb + threadIdx.x] = sh.xblk[threadIdx.x];
+		}
 		__syncthreads();
-		const double xj = x[j];
-		for (int i = threadIdx.x; i < j; i += LM_THREADS) x[i] -= A[(size_t)i * ld + j] * xj;
+		for (int i = threadIdx.x; i < kb; i += LM_THREADS) {
+			const double *row = A + (size_t)i * ld + kb;
+			double s = 0;
+#pragma unroll
+			for (int c = 0; c < CH_NB; c++)
+				if (c < w) s += row[c] * sh.xblk[c];
+			x[i] -= s;
+		}
 		__syncthreads();
 	}
-	return true;
 }
 
 // K5a: SchurComplement::numeric_solve_for_features (impl/schur.h:271-311): mutates the gradient tail in place.
@@ -896,11 +1163,24 @@ __device__ void stage_restore(const View &v) {
 }
 
 // ------------------------------------------------------------------------------------------------ the LM program
-template <int P, int OBSK>
-__device__ void lm_program(const DevProblem *h, const char *img, char *ws, char *res, Shared &sh) {
+#define STAGE(id)                                            \
+	do {                                                     \
+		if (threadIdx.x == 0) {                              \
+			const unsigned long long t_ = clock64();         \
+			sh.stage_cycles[id] += t_ - sh.t_last;           \
+			sh.t_last = t_;                                  \
+		}                                                    \
+	} while (0)
+
+template <int P, int OBSK, int MAXTPT>
+__device__ void lm_program(const DevProblem *h, const char *img, char *ws, char *res, Shared &sh, double *panel, int panel_cap) {
 	constexpr int S = PoseOps<P>::S;
 	View v;
 	make_view(v, h, img, ws, res);
+	if (threadIdx.x == 0) {
+		for (int i = 0; i < ST_COUNT; i++) sh.stage_cycles[i] = 0;
+		sh.t_last = clock64();
+	}
 	const int n = h->n_dense, nsc = h->n_scalars;
 	const int nObsRows = h->n_total_obs_rows;
 
@@ -947,6 +1227,7 @@ __device__ void lm_program(const DevProblem *h, const char *img, char *ws, char 
 		v.stats->total_sqr_error_init = err0;
 	}
 	__syncthreads();
+	STAGE(ST_INIT);
 
 	const double MAX_LAMBDA = h->model.max_lambda;
 	const double max_gradient_to_stop = 1e-15;
@@ -966,9 +1247,22 @@ __device__ void lm_program(const DevProblem *h, const char *img, char *ws, char 
 			__syncthreads();
 			stage_schur_and_fill<P>(v, lambda);
 			__syncthreads();
-			if (h->want_dense)  // extra_results.hessian = denseH of the last solve (lev-marq_solvers.h:582-586)
+			if (h->want_dense) {  // extra_results.hessian = denseH of the last solve (lev-marq_solvers.h:582-586)
 				for (size_t i = threadIdx.x; i < (size_t)n * n; i += LM_THREADS) v.r_dense[i] = v.dense[(i / n) * h->ld_dense + (i % n)];
-			const bool ok = stage_cholesky_solve(v, sh);
+				__syncthreads();
+			}
+			STAGE(ST_SCHUR);
+			// dense solve: register-resident tiles when the system fits the CTA's register file, blocked global/shared otherwise
+			bool ok, solved = false;
+			{
+				const int tiles = chol_reg_tiles(n);
+				const bool fits = chol_reg_smem_doubles(n) <= CH_NB * panel_cap;
+				if (fits && tiles <= LM_THREADS) { ok = stage_cholesky_solve_reg<1>(v, sh, panel); solved = true; }
+				else if (MAXTPT >= 2 && fits && tiles <= 2 * LM_THREADS) { ok = stage_cholesky_solve_reg<(MAXTPT >= 2 ? 2 : 1)>(v, sh, panel); solved = true; }
+				else if (MAXTPT >= 4 && fits && tiles <= 4 * LM_THREADS) { ok = stage_cholesky_solve_reg<(MAXTPT >= 4 ? 4 : 1)>(v, sh, panel); solved = true; }
+				else ok = stage_cholesky(v, sh, panel, panel_cap);
+			}
+			STAGE(ST_CHOL);
 			if (!ok) {  // not positive definite (:476-485)
 				if (threadIdx.x == 0) {
 					if (trial < h->trace_cap) {
@@ -983,16 +1277,25 @@ __device__ void lm_program(const DevProblem *h, const char *img, char *ws, char 
 				if (trial < h->trace_cap)
 					for (int i = threadIdx.x; i < nsc; i += LM_THREADS) v.r_trace_delta[(size_t)trial * nsc + i] = 0;
 				__syncthreads();
+				STAGE(ST_CTRL);
 				continue;
 			}
-			stage_features<P>(v);
-			__syncthreads();
+			if (!solved) stage_backsub(v, sh);
+			STAGE(ST_BACKSUB);
+			if (h->n_unk_lms > 0) {
+				stage_features<P>(v);
+				__syncthreads();
+			}
+			STAGE(ST_FEATURES);
 			stage_update<P>(v);
 			__syncthreads();
+			STAGE(ST_UPDATE);
 			stage_chain<P>(v, true);  // update_numeric(set, true) (:565)
 			__syncthreads();
+			STAGE(ST_CHAIN);
 			double *new_resid = v.resid[sh.cur ^ 1];
 			const double new_err = stage_residuals<P, OBSK>(v, new_resid, sh);
+			STAGE(ST_RESID);
 			// rho (:585)
 			double dl = 0;
 			for (int i = threadIdx.x; i < nsc; i += LM_THREADS) dl += v.delta[i] * (lambda * v.delta[i] + v.grad[i]);
@@ -1010,15 +1313,19 @@ __device__ void lm_program(const DevProblem *h, const char *img, char *ws, char 
 				for (int i = threadIdx.x; i < nsc; i += LM_THREADS) v.r_trace_delta[(size_t)trial * nsc + i] = v.delta[i];
 			}
 			__syncthreads();
+			STAGE(ST_RHO);
 			if (accept) {
 				if (do_relinearize) {  // :606-629
 					stage_jacobians<P, OBSK>(v, false);
 					__syncthreads();
+					STAGE(ST_JACOB);
 					stage_hessian<P, OBSK>(v);
 					__syncthreads();
+					STAGE(ST_HESS);
 				}
 				stage_gradient<P, OBSK>(v, new_resid);  // :633
 				__syncthreads();
+				STAGE(ST_GRAD);
 				double gm = 0;
 				for (int i = threadIdx.x; i < nsc; i += LM_THREADS) gm = fmax(gm, fabs(v.grad[i]));
 				gm = team_max(gm, sh);
@@ -1045,6 +1352,7 @@ __device__ void lm_program(const DevProblem *h, const char *img, char *ws, char 
 				}
 			}
 			__syncthreads();
+			STAGE(ST_CTRL);
 		}
 		__syncthreads();
 		if (threadIdx.x == 0) sh.iter++;
@@ -1071,31 +1379,49 @@ __device__ void lm_program(const DevProblem *h, const char *img, char *ws, char 
 		st->total_sqr_error_final = sh.err;
 		st->obs_rmse = sh.rmse;
 		st->lambda_final = sh.lambda;
+		unsigned long long *sc = reinterpret_cast<unsigned long long *>(res + h->res_stage_cycles);
+		const unsigned long long t_ = clock64();
+		sh.stage_cycles[ST_OUT] += t_ - sh.t_last;
+		for (int i = 0; i < ST_COUNT; i++) sc[i] = sh.stage_cycles[i];
 	}
 }
 
-__global__ void __launch_bounds__(LM_THREADS) srba_lm_batch_kernel(const char *img, const uint64_t *img_off, char *ws, const uint64_t *ws_off,
-                                                                    char *res, const uint64_t *res_off, const int32_t *order, int n_problems) {
+// One kernel per model combination so that each gets its own register budget (the SE(2) graph-SLAM program needs
+// far fewer registers than the SE(3) camera models and can keep 2 CTAs per SM resident).
+template <int P, int OBSK, int MINB, int MAXTPT>
+__global__ void __launch_bounds__(LM_THREADS, MINB) srba_lm_batch_kernel(const char *img, const uint64_t *img_off, char *ws, const uint64_t *ws_off, char *res,
+                                                                          const uint64_t *res_off, const int32_t *order, int n_problems, int panel_cap) {
 	__shared__ Shared sh;
+	extern __shared__ double panel[];
 	for (int q = blockIdx.x; q < n_problems; q += gridDim.x) {
 		const int pi = order[q];
 		const char *pimg = img + img_off[pi];
 		const DevProblem *h = reinterpret_cast<const DevProblem *>(pimg);
-		char *pws = ws + ws_off[pi];
-		char *pres = res + res_off[pi];
-		const int pk = h->model.pose_kind, ok = h->model.obs_kind;
-		if (pk == SRBA_POSE_SE2 && ok == SRBA_OBS_RELPOSES2D) lm_program<3, SRBA_OBS_RELPOSES2D>(h, pimg, pws, pres, sh);
-		else if (pk == SRBA_POSE_SE3 && ok == SRBA_OBS_CARTESIAN3D) lm_program<6, SRBA_OBS_CARTESIAN3D>(h, pimg, pws, pres, sh);
-		else if (pk == SRBA_POSE_SE3 && ok == SRBA_OBS_MONO) lm_program<6, SRBA_OBS_MONO>(h, pimg, pws, pres, sh);
-		else if (pk == SRBA_POSE_SE3 && ok == SRBA_OBS_STEREO) lm_program<6, SRBA_OBS_STEREO>(h, pimg, pws, pres, sh);
+		lm_program<P, OBSK, MAXTPT>(h, pimg, ws + ws_off[pi], res + res_off[pi], sh, panel, panel_cap);
 		__syncthreads();
 	}
 }
 
 }  // namespace
 
-extern "C" int srba_launch_lm_batch(const char *img, const uint64_t *img_off, char *ws, const uint64_t *ws_off, char *res, const uint64_t *res_off,
-                                    const int32_t *order, int n_problems, int grid, void *stream) {
-	srba_lm_batch_kernel<<<grid, LM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(img, img_off, ws, ws_off, res, res_off, order, n_problems);
+// model: 0 = SE2+RelativePoses2D, 1 = SE3+Cartesian3D, 2 = SE3+Mono, 3 = SE3+Stereo.  `order` lists the problems of that model.
+extern "C" int srba_launch_lm_batch(int model, const char *img, const uint64_t *img_off, char *ws, const uint64_t *ws_off, char *res,
+                                    const uint64_t *res_off, const int32_t *order, int n_problems, int grid, int panel_cap, void *stream) {
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	const size_t smem = (size_t)CH_NB * panel_cap * sizeof(double);
+#define LAUNCH(P, OBSK, MINB, MAXTPT)                                                                                                     \
+	do {                                                                                                                                  \
+		auto kern = srba_lm_batch_kernel<P, OBSK, MINB, MAXTPT>;                                                                                  \
+		if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                         \
+		kern<<<grid, LM_THREADS, smem, st>>>(img, img_off, ws, ws_off, res, res_off, order, n_problems, panel_cap);                       \
+	} while (0)
+	switch (model) {
+		case 0: LAUNCH(3, SRBA_OBS_RELPOSES2D, 2, 2); break;
+		case 1: LAUNCH(6, SRBA_OBS_CARTESIAN3D, 1, 4); break;
+		case 2: LAUNCH(6, SRBA_OBS_MONO, 1, 4); break;
+		case 3: LAUNCH(6, SRBA_OBS_STEREO, 1, 4); break;
+		default: return (int)cudaErrorInvalidValue;
+	}
+#undef LAUNCH
 	return (int)cudaGetLastError();
 }
