@@ -159,11 +159,18 @@ int64_t srba_b200_batch_h2d_bytes(const srba_batch_t *b);
 int64_t srba_b200_batch_d2h_bytes(const srba_batch_t *b);
 int64_t srba_b200_batch_kernel_launches(const srba_batch_t *b); /* launches issued by the last batch_run */
 /* SM clock cycles problem i spent in each stage of the LM program (measured by the kernel itself with clock64):
- * init, schur+fill, cholesky, backsub, features, update, chain, residuals, rho, jacobians, hessian, gradient, control, output */
-int srba_b200_batch_stage_cycles(srba_batch_t *b, int32_t i, uint64_t out[16]);
+ * out[0..13] = init, schur+fill, cholesky, backsub, features, update, chain, residuals, rho, jacobians, hessian, gradient,
+ * control, output; out[16..20] = sub-timers of the register-resident solver: tile gather + first pivot block, factorisation
+ * loop, back-substitution loop, busy time of the critical-path threads inside the factorisation loop, call prologue */
+int srba_b200_batch_stage_cycles(srba_batch_t *b, int32_t i, uint64_t out[24]);
 /* Algorithmic bytes of one accepted+relinearised LM iteration of the whole batch (SURVEY.md §8d formulas), per stage:
  * out[0]=B_chain out[1]=B_assem out[2]=B_schur out[3]=B_chol out[4]=F_chol(flop) */
 void srba_b200_batch_algorithmic_bytes(const srba_batch_t *b, double out[5]);
+
+/* Host-only: how the packer would lay problem `in` out.  out[0..7] = image bytes, global workspace bytes, result bytes,
+ * shared-memory bytes planned (Cholesky scratch + on-chip arena), dense solver (0 register-resident tiles, 1 blocked),
+ * image arrays on chip, workspace arrays on chip, shared-memory budget of the model's kernel.  No device needed. */
+int srba_b200_problem_plan(const srba_problem_t *in, int64_t out[8]);
 
 const char *srba_b200_last_error(void);
 int srba_b200_device_count(void);

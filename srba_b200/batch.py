@@ -55,10 +55,14 @@ class Batch:
     STAGES = ("init", "schur_fill", "cholesky", "backsub", "features", "update", "chain", "residuals", "rho", "jacobians", "hessian",
               "gradient", "control", "output")
 
+    SOLVER_SUBSTAGES = ("chol.gather", "chol.factor_loop", "chol.backsub_loop", "chol.w0_W", "chol.w0_bar1", "chol.w0_U", "chol.w0_bar2", "chol.iwarp_UI")
+
     def stage_cycles(self, i):
-        out = np.zeros(16, np.uint64)
+        out = np.zeros(24, np.uint64)
         self._chk(self.L.srba_b200_batch_stage_cycles(self.h, i, out.ctypes.data_as(C.POINTER(C.c_uint64))))
-        return dict(zip(self.STAGES, out[:len(self.STAGES)].tolist()))
+        d = dict(zip(self.STAGES, out[:len(self.STAGES)].tolist()))
+        d.update(zip(self.SOLVER_SUBSTAGES, out[16:16 + len(self.SOLVER_SUBSTAGES)].tolist()))
+        return d
 
     @property
     def h2d_bytes(self):

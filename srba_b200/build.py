@@ -25,7 +25,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + [os.path.join(CSRC, f) for f in SOURCES]
+    extra = ["-DSRBA_SOLVER_TIMERS"] if os.environ.get("SRBA_SOLVER_TIMERS") else []   # per-phase clocks inside the solver (tools/stage_breakdown.py)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + [os.path.join(CSRC, f) for f in SOURCES]
     subprocess.check_call(cmd, cwd=CSRC)
     return SO
 

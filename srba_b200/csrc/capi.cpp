@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <numeric>
@@ -13,7 +15,7 @@
 #include "dev_types.h"
 
 extern "C" int srba_launch_lm_batch(int model, const char *img, const uint64_t *img_off, char *ws, const uint64_t *ws_off, char *res,
-                                    const uint64_t *res_off, const int32_t *order, int n_problems, int grid, int panel_cap, void *stream);
+                                    const uint64_t *res_off, const int32_t *order, int n_problems, int grid, int smem_bytes, void *stream);
 
 namespace {
 thread_local std::string g_err;
@@ -71,8 +73,191 @@ void put(char *base, uint64_t off, const T *src, size_t n) {
 	if (n) std::memcpy(base + off, src, n * sizeof(T));
 }
 
+inline const void *src_of_edge_pose(const srba_problem_t &p) { return p.edge_pose; }
+inline const void *src_of_unk_edge(const srba_problem_t &p) { return p.unk_edge; }
+inline const void *src_of_lm_pos(const srba_problem_t &p) { return p.lm_pos; }
+inline const void *src_of_unk_lm(const srba_problem_t &p) { return p.unk_lm; }
+inline const void *src_of_pair_path_ptr(const srba_problem_t &p) { return p.pair_path_ptr; }
+inline const void *src_of_path_edge(const srba_problem_t &p) { return p.path_edge; }
+inline const void *src_of_path_dir(const srba_problem_t &p) { return p.path_dir; }
+inline const void *src_of_obs_z(const srba_problem_t &p) { return p.obs_z; }
+inline const void *src_of_obs_slot(const srba_problem_t &p) { return p.obs_slot; }
+inline const void *src_of_obs_lm(const srba_problem_t &p) { return p.obs_lm; }
+inline const void *src_of_obs_mult(const srba_problem_t &p) { return p.obs_mult; }
+inline const void *src_of_colA_ptr(const srba_problem_t &p) { return p.colA_ptr; }
+inline const void *src_of_blkA_obs(const srba_problem_t &p) { return p.blkA_obs; }
+inline const void *src_of_blkA_slotA(const srba_problem_t &p) { return p.blkA_slotA; }
+inline const void *src_of_blkA_slotD(const srba_problem_t &p) { return p.blkA_slotD; }
+inline const void *src_of_blkA_normal_dir(const srba_problem_t &p) { return p.blkA_normal_dir; }
+inline const void *src_of_colF_ptr(const srba_problem_t &p) { return p.colF_ptr; }
+inline const void *src_of_blkF_obs(const srba_problem_t &p) { return p.blkF_obs; }
+inline const void *src_of_blkF_slot(const srba_problem_t &p) { return p.blkF_slot; }
+inline const void *src_of_row_ptr(const srba_problem_t &p) { return p.row_ptr; }
+inline const void *src_of_row_blk(const srba_problem_t &p) { return p.row_blk; }
+inline const void *src_of_HAp_row(const srba_problem_t &p) { return p.HAp_row; }
+inline const void *src_of_HAp_col(const srba_problem_t &p) { return p.HAp_col; }
+inline const void *src_of_HAp_term_ptr(const srba_problem_t &p) { return p.HAp_term_ptr; }
+inline const void *src_of_HAp_term_a(const srba_problem_t &p) { return p.HAp_term_a; }
+inline const void *src_of_HAp_term_b(const srba_problem_t &p) { return p.HAp_term_b; }
+inline const void *src_of_HApf_row(const srba_problem_t &p) { return p.HApf_row; }
+inline const void *src_of_HApf_col(const srba_problem_t &p) { return p.HApf_col; }
+inline const void *src_of_HApf_term_ptr(const srba_problem_t &p) { return p.HApf_term_ptr; }
+inline const void *src_of_HApf_term_a(const srba_problem_t &p) { return p.HApf_term_a; }
+inline const void *src_of_HApf_term_f(const srba_problem_t &p) { return p.HApf_term_f; }
+inline const void *src_of_rowApf_ptr(const srba_problem_t &p) { return p.rowApf_ptr; }
+inline const void *src_of_colApf_ptr(const srba_problem_t &p) { return p.colApf_ptr; }
+inline const void *src_of_colApf_idx(const srba_problem_t &p) { return p.colApf_idx; }
+inline const void *src_of_S_row(const srba_problem_t &p) { return p.S_row; }
+inline const void *src_of_S_col(const srba_problem_t &p) { return p.S_col; }
+inline const void *src_of_S_HAp(const srba_problem_t &p) { return p.S_HAp; }
+inline const void *src_of_S_term_ptr(const srba_problem_t &p) { return p.S_term_ptr; }
+inline const void *src_of_S_term_rowblk(const srba_problem_t &p) { return p.S_term_rowblk; }
+inline const void *src_of_S_term_colblk(const srba_problem_t &p) { return p.S_term_colblk; }
+inline const void *src_of_blkA_col(const srba_problem_t &) { return nullptr; }
+inline const void *src_of_blkF_col(const srba_problem_t &) { return nullptr; }
+inline const void *src_of_ldl_row(const srba_problem_t &) { return nullptr; }
+inline const void *src_of_ldl_tile_ij(const srba_problem_t &) { return nullptr; }
+inline const void *src_of_ldl_src(const srba_problem_t &) { return nullptr; }
+inline const void *src_of_ldl_upd(const srba_problem_t &) { return nullptr; }
+inline const void *src_of_ldl_col_ptr(const srba_problem_t &) { return nullptr; }
+inline const void *src_of_ldl_col_tile(const srba_problem_t &) { return nullptr; }
+// pointer to the caller's array behind image slot `id` (NULL for the derived ones)
+const void *src_ptr(const srba_problem_t &p, int id) {
+	switch (id) {
+#define X(T, name) case SRBA_I_##name: return src_of_##name(p);
+		SRBA_IMG_ARRAYS(X)
+#undef X
+	}
+	return nullptr;
+}
+
+// Symbolic factorisation of the reduced system at 3x3-tile granularity (SE(2) block = 1 tile, SE(3) block = 2x2 tiles):
+// filled upper pattern of U (no reordering: the reference's unknown order) + the right-hand side as tile column NTR, the
+// tile numbering and the per-row update schedule consumed by stage_ldl_solve_smem (lm_kernel.cu).
+struct TileSymbolic {
+	int ntr = 0;
+	std::vector<int32_t> rs;        // NTR+1: first tile of each row (row-major numbering, diagonal first, RHS last)
+	std::vector<int32_t> row;       // 4 per row (+ sentinel): {first tile, end tile | has_superdiag<<30, first update, end update}
+	std::vector<int32_t> tile_ij;   // ntiles: (ti<<16)|tj
+	std::vector<int32_t> src;       // ntiles: offset of the tile's (0,0) in the reduced blocks, -1 fill-in, -2-row right-hand side
+	std::vector<int32_t> upd_ptr;   // NTR+1
+	std::vector<int32_t> upd;       // 2 per update: {dst tile | tile(k,i)<<16, tile(k,j)}; the update of the next pivot block is implicit
+	std::vector<int32_t> col_ptr;   // NTR+1
+	std::vector<int32_t> col_tile;  // off-diagonal tiles (i<j) of every column j < NTR
+	bool ok = false;                // false: too large for the on-chip solver (schedule not built)
+	void clear() { rs.clear(); row.clear(); src.clear(); tile_ij.clear(); upd_ptr.clear(); upd.clear(); col_ptr.clear(); col_tile.clear(); ok = false; }
+};
+void symbolic_tiles(const srba_problem_t &p, int P, long max_tiles, TileSymbolic &sy) {
+	const int q = P / 3, ntr = q * p.n_unk_edges, ntc = ntr + 1;
+	sy.clear();
+	sy.ntr = ntr;
+	if (ntr <= 0 || ntr >= 32768) return;
+	const int W = (ntc + 63) / 64;
+	std::vector<uint64_t> rows((size_t)ntr * W, 0);
+	auto setbit = [&](int r, int c) { rows[(size_t)r * W + (c >> 6)] |= 1ull << (c & 63); };
+	for (int r = 0; r < ntr; r++) { setbit(r, r); setbit(r, ntr); }
+	for (int b = 0; b < p.n_S; b++) {
+		const int br = p.S_row[b], bc = p.S_col[b];
+		for (int a = 0; a < q; a++)
+			for (int c = 0; c < q; c++) {
+				const int ti = q * br + a, tj = q * bc + c;
+				if (ti <= tj) setbit(ti, tj);
+			}
+	}
+	long total = 0;
+	for (int k = 0; k < ntr; k++) {
+		const uint64_t *rk = &rows[(size_t)k * W];
+		// every row i > k present in row k inherits row k's columns >= i
+		for (int w = k >> 6; w < W; w++) {
+			uint64_t m = rk[w];
+			if (w == (k >> 6)) m &= ~((2ull << (k & 63)) - 1);  // bits > k
+			while (m) {
+				const int i = w * 64 + __builtin_ctzll(m);
+				m &= m - 1;
+				if (i >= ntr) continue;  // right-hand-side column
+				uint64_t *ri = &rows[(size_t)i * W];
+				for (int w2 = i >> 6; w2 < W; w2++) {
+					uint64_t add = rk[w2];
+					if (w2 == (i >> 6)) add &= ~((1ull << (i & 63)) - 1);  // bits >= i
+					ri[w2] |= add;
+				}
+			}
+		}
+		for (int w = 0; w < W; w++) total += __builtin_popcountll(rk[w]);
+		if (total > max_tiles) return;  // does not fit on chip
+	}
+	// numbering
+	sy.rs.assign(ntr + 1, 0);
+	sy.tile_ij.reserve(total);
+	for (int r = 0; r < ntr; r++) {
+		sy.rs[r] = (int32_t)sy.tile_ij.size();
+		const uint64_t *rr = &rows[(size_t)r * W];
+		for (int w = r >> 6; w < W; w++) {
+			uint64_t m = rr[w];
+			if (w == (r >> 6)) m &= ~((1ull << (r & 63)) - 1);
+			while (m) { const int c = w * 64 + __builtin_ctzll(m); m &= m - 1; sy.tile_ij.push_back((r << 16) | c); }
+		}
+	}
+	sy.rs[ntr] = (int32_t)sy.tile_ij.size();
+	auto find_tile = [&](int i, int j) {  // id of tile (i,j): row i's tiles are contiguous, ascending column
+		const int32_t key = (i << 16) | j;
+		const auto it = std::lower_bound(sy.tile_ij.begin() + sy.rs[i], sy.tile_ij.begin() + sy.rs[i + 1], key);
+		return (int32_t)(it - sy.tile_ij.begin());
+	};
+	// update schedule + column lists
+	sy.upd_ptr.assign(ntr + 1, 0);
+	std::vector<int32_t> col_cnt(ntr + 1, 0);
+	for (int k = 0; k < ntr; k++) {
+		sy.upd_ptr[k] = (int32_t)(sy.upd.size() / 2);
+		for (int a = sy.rs[k] + 1; a < sy.rs[k + 1]; a++) {
+			const int i = sy.tile_ij[a] & 0xffff;
+			if (i >= ntr) break;  // the right-hand side is never a row
+			col_cnt[i]++;
+			for (int b = a; b < sy.rs[k + 1]; b++) {
+				const int j = sy.tile_ij[b] & 0xffff;
+				if (i == k + 1 && j == k + 1) continue;  // next pivot block: updated by the inverting lanes themselves
+				sy.upd.push_back(find_tile(i, j) | (a << 16));  // dst | tile(k,i) << 16
+				sy.upd.push_back(b);                             // tile(k,j)
+			}
+		}
+	}
+	sy.upd_ptr[ntr] = (int32_t)(sy.upd.size() / 2);
+	sy.col_ptr.assign(ntr + 1, 0);
+	for (int j = 0; j < ntr; j++) sy.col_ptr[j + 1] = sy.col_ptr[j] + col_cnt[j];
+	sy.col_tile.assign(sy.col_ptr[ntr], 0);
+	std::vector<int32_t> fillp(sy.col_ptr.begin(), sy.col_ptr.end() - 1);
+	for (int k = 0; k < ntr; k++)
+		for (int a = sy.rs[k] + 1; a < sy.rs[k + 1]; a++) {
+			const int i = sy.tile_ij[a] & 0xffff;
+			if (i < ntr) sy.col_tile[fillp[i]++] = a;
+		}
+	// per-row records and tile sources
+	sy.row.assign(4 * (size_t)(ntr + 1), 0);
+	for (int k = 0; k <= ntr; k++) {
+		int32_t *r = &sy.row[4 * (size_t)k];
+		if (k == ntr) { r[0] = r[1] = sy.rs[ntr]; r[2] = r[3] = sy.upd_ptr[ntr]; break; }
+		const bool has_sd = sy.rs[k] + 1 < sy.rs[k + 1] && (sy.tile_ij[sy.rs[k] + 1] & 0xffff) == k + 1 && k + 1 < ntr;
+		r[0] = sy.rs[k]; r[1] = sy.rs[k + 1] | (has_sd ? 1 << 30 : 0); r[2] = sy.upd_ptr[k]; r[3] = sy.upd_ptr[k + 1];
+	}
+	std::vector<int32_t> blk((size_t)p.n_unk_edges * p.n_unk_edges, -1);  // (block row, block col) -> reduced block
+	for (int b = 0; b < p.n_S; b++) blk[(size_t)p.S_row[b] * p.n_unk_edges + p.S_col[b]] = b;
+	sy.src.resize(sy.tile_ij.size());
+	for (size_t t = 0; t < sy.tile_ij.size(); t++) {
+		const int ti = sy.tile_ij[t] >> 16, tj = sy.tile_ij[t] & 0xffff;
+		if (tj == ntr) { sy.src[t] = -2 - ti; continue; }
+		const int br = ti / q, bc = tj / q;
+		const int32_t b = blk[(size_t)br * p.n_unk_edges + bc];
+		sy.src[t] = b < 0 ? -1 : b * P * P + (ti - br * q) * 3 * P + (tj - bc * q) * 3;
+	}
+	sy.ok = sy.tile_ij.size() < 65535;
+}
+
+int model_index(const srba_model_t &m) {
+	return m.pose_kind == SRBA_POSE_SE2 ? 0 : (m.obs_kind == SRBA_OBS_CARTESIAN3D ? 1 : (m.obs_kind == SRBA_OBS_MONO ? 2 : 3));
+}
+
 // Fills the header's layout fields; when `base` != NULL also copies the arrays.
-void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_cap, int want_dense) {
+void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_cap, int want_dense, TileSymbolic &sy) {
 	std::memset(&h, 0, sizeof(h));
 	h.model = p.model;
 	h.n_edges = p.n_edges; h.n_unk_edges = p.n_unk_edges; h.n_lms = p.n_lms; h.n_unk_lms = p.n_unk_lms; h.n_pairs = p.n_pairs;
@@ -86,92 +271,130 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 	h.ld_dense = (h.n_dense + 1 + 1) / 2 * 2;
 	h.trace_cap = trace_cap;
 	h.want_dense = want_dense;
+	// ---- dense solver: register-resident block-sparse tiles when the filled pattern fits the model kernel's register file
+	const int model = model_index(p.model);
+	const SrbaKernelCfg cfg = srba_kernel_cfg(model);
+	if (!base) {  // layout pass: symbolic factorisation (reused by the copy pass)
+		const long max_tiles = std::min(32767L, ((long)cfg.smem_bytes / 2 / 8 - 37 - h.n_dense) / 12);  // tile ids are packed in 15/16 bits
+		if (max_tiles > 0) symbolic_tiles(p, P, max_tiles, sy);
+		else sy.clear();
+	}
+	const int reg_scratch = sy.ok ? srba_chol_reg_scratch_doubles(model, h.n_dense, (int)sy.tile_ij.size()) : -1;
+	uint64_t scratch_bytes;
+	if (reg_scratch >= 0) {
+		h.chol_mode = SRBA_CHOL_REG;
+		h.ldl_n_tiles = (int)sy.tile_ij.size();
+		scratch_bytes = (uint64_t)reg_scratch * 8;
+	} else {
+		h.chol_mode = SRBA_CHOL_BLOCKED;
+		h.panel_cap = std::min(std::max((h.n_dense + 1 + 3) / 4 * 4, 24), 1024);
+		scratch_bytes = (uint64_t)8 * h.panel_cap * 8;
+	}
+	// ---- input image
+	uint64_t img_count[SRBA_I_COUNT];
+	{
+		uint64_t *c = img_count;
+		c[SRBA_I_edge_pose] = (uint64_t)p.n_edges * S; c[SRBA_I_unk_edge] = p.n_unk_edges; c[SRBA_I_lm_pos] = (uint64_t)p.n_lms * 3; c[SRBA_I_unk_lm] = p.n_unk_lms;
+		c[SRBA_I_pair_path_ptr] = p.n_pairs + 1; c[SRBA_I_path_edge] = p.n_path; c[SRBA_I_path_dir] = p.n_path;
+		c[SRBA_I_obs_z] = (uint64_t)p.n_obs * o; c[SRBA_I_obs_slot] = p.n_obs; c[SRBA_I_obs_lm] = p.n_obs; c[SRBA_I_obs_mult] = p.n_obs;
+		c[SRBA_I_colA_ptr] = p.n_unk_edges + 1; c[SRBA_I_blkA_obs] = p.n_blkA; c[SRBA_I_blkA_slotA] = p.n_blkA; c[SRBA_I_blkA_slotD] = p.n_blkA; c[SRBA_I_blkA_normal_dir] = p.n_blkA;
+		c[SRBA_I_colF_ptr] = p.n_unk_lms + 1; c[SRBA_I_blkF_obs] = p.n_blkF; c[SRBA_I_blkF_slot] = p.n_blkF;
+		c[SRBA_I_row_ptr] = p.n_obs + 1; c[SRBA_I_row_blk] = p.n_blkA + p.n_blkF;
+		c[SRBA_I_HAp_row] = p.n_HAp; c[SRBA_I_HAp_col] = p.n_HAp; c[SRBA_I_HAp_term_ptr] = p.n_HAp + 1; c[SRBA_I_HAp_term_a] = p.n_HAp_terms; c[SRBA_I_HAp_term_b] = p.n_HAp_terms;
+		c[SRBA_I_HApf_row] = p.n_HApf; c[SRBA_I_HApf_col] = p.n_HApf; c[SRBA_I_HApf_term_ptr] = p.n_HApf + 1; c[SRBA_I_HApf_term_a] = p.n_HApf_terms; c[SRBA_I_HApf_term_f] = p.n_HApf_terms;
+		c[SRBA_I_rowApf_ptr] = p.n_unk_edges + 1; c[SRBA_I_colApf_ptr] = p.n_unk_lms + 1; c[SRBA_I_colApf_idx] = p.n_HApf;
+		c[SRBA_I_S_row] = p.n_S; c[SRBA_I_S_col] = p.n_S; c[SRBA_I_S_HAp] = p.n_S; c[SRBA_I_S_term_ptr] = p.n_S + 1; c[SRBA_I_S_term_rowblk] = p.n_S_terms; c[SRBA_I_S_term_colblk] = p.n_S_terms;
+		c[SRBA_I_blkA_col] = p.n_blkA; c[SRBA_I_blkF_col] = p.n_blkF;
+		const bool reg = h.chol_mode == SRBA_CHOL_REG;
+		c[SRBA_I_ldl_row] = reg ? sy.row.size() : 0; c[SRBA_I_ldl_tile_ij] = reg ? sy.tile_ij.size() : 0;
+		c[SRBA_I_ldl_src] = reg ? sy.src.size() : 0; c[SRBA_I_ldl_upd] = reg ? sy.upd.size() : 0;
+		c[SRBA_I_ldl_col_ptr] = reg ? sy.col_ptr.size() : 0; c[SRBA_I_ldl_col_tile] = reg ? sy.col_tile.size() : 0;
+	}
 	Layout L;
 	L.add(sizeof(DevProblem));
-#define PUT(T, name, count)                               \
-	h.img_##name = L.add((uint64_t)(count) * sizeof(T));  \
-	if (base) put<T>(base, h.img_##name, p.name, (size_t)(count));
-	PUT(double, edge_pose, (size_t)p.n_edges * S)
-	PUT(int32_t, unk_edge, p.n_unk_edges)
-	PUT(double, lm_pos, (size_t)p.n_lms * 3)
-	PUT(int32_t, unk_lm, p.n_unk_lms)
-	PUT(int32_t, pair_path_ptr, p.n_pairs + 1)
-	PUT(int32_t, path_edge, p.n_path)
-	PUT(uint8_t, path_dir, p.n_path)
-	PUT(double, obs_z, (size_t)p.n_obs * o)
-	PUT(int32_t, obs_slot, p.n_obs)
-	PUT(int32_t, obs_lm, p.n_obs)
-	PUT(int32_t, obs_mult, p.n_obs)
-	PUT(int32_t, colA_ptr, p.n_unk_edges + 1)
-	PUT(int32_t, blkA_obs, p.n_blkA)
-	PUT(int32_t, blkA_slotA, p.n_blkA)
-	PUT(int32_t, blkA_slotD, p.n_blkA)
-	PUT(uint8_t, blkA_normal_dir, p.n_blkA)
-	PUT(int32_t, colF_ptr, p.n_unk_lms + 1)
-	PUT(int32_t, blkF_obs, p.n_blkF)
-	PUT(int32_t, blkF_slot, p.n_blkF)
-	PUT(int32_t, row_ptr, p.n_obs + 1)
-	PUT(int32_t, row_blk, p.n_blkA + p.n_blkF)
-	PUT(int32_t, HAp_row, p.n_HAp)
-	PUT(int32_t, HAp_col, p.n_HAp)
-	PUT(int32_t, HAp_term_ptr, p.n_HAp + 1)
-	PUT(int32_t, HAp_term_a, p.n_HAp_terms)
-	PUT(int32_t, HAp_term_b, p.n_HAp_terms)
-	PUT(int32_t, HApf_row, p.n_HApf)
-	PUT(int32_t, HApf_col, p.n_HApf)
-	PUT(int32_t, HApf_term_ptr, p.n_HApf + 1)
-	PUT(int32_t, HApf_term_a, p.n_HApf_terms)
-	PUT(int32_t, HApf_term_f, p.n_HApf_terms)
-	PUT(int32_t, rowApf_ptr, p.n_unk_edges + 1)
-	PUT(int32_t, colApf_ptr, p.n_unk_lms + 1)
-	PUT(int32_t, colApf_idx, p.n_HApf)
-	PUT(int32_t, S_row, p.n_S)
-	PUT(int32_t, S_col, p.n_S)
-	PUT(int32_t, S_HAp, p.n_S)
-	PUT(int32_t, S_term_ptr, p.n_S + 1)
-	PUT(int32_t, S_term_rowblk, p.n_S_terms)
-	PUT(int32_t, S_term_colblk, p.n_S_terms)
-#undef PUT
-	// derived: column of every block
-	h.img_blkA_col = L.add((uint64_t)p.n_blkA * 4);
-	h.img_blkF_col = L.add((uint64_t)p.n_blkF * 4);
+#define X(T, name)                                                        \
+	h.img_len[SRBA_I_##name] = (uint32_t)(img_count[SRBA_I_##name] * sizeof(T)); \
+	h.img_off[SRBA_I_##name] = L.add(img_count[SRBA_I_##name] * sizeof(T));      \
+	h.img_sm[SRBA_I_##name] = SRBA_NOT_IN_SMEM;
+	SRBA_IMG_ARRAYS(X)
+#undef X
+	h.img_bytes = L.total();
 	if (base) {
-		int32_t *ca = reinterpret_cast<int32_t *>(base + h.img_blkA_col);
+#define X(T, name) \
+	if (src_ptr(p, SRBA_I_##name)) put<T>(base, h.img_off[SRBA_I_##name], reinterpret_cast<const T *>(src_ptr(p, SRBA_I_##name)), (size_t)img_count[SRBA_I_##name]);
+		SRBA_IMG_ARRAYS(X)
+#undef X
+		// derived: column of every block
+		int32_t *ca = reinterpret_cast<int32_t *>(base + h.img_off[SRBA_I_blkA_col]);
 		for (int c = 0; c < p.n_unk_edges; c++)
 			for (int b = p.colA_ptr[c]; b < p.colA_ptr[c + 1]; b++) ca[b] = c;
-		int32_t *cf = reinterpret_cast<int32_t *>(base + h.img_blkF_col);
+		int32_t *cf = reinterpret_cast<int32_t *>(base + h.img_off[SRBA_I_blkF_col]);
 		for (int c = 0; c < p.n_unk_lms; c++)
 			for (int b = p.colF_ptr[c]; b < p.colF_ptr[c + 1]; b++) cf[b] = c;
+		if (h.chol_mode == SRBA_CHOL_REG) {
+			put<int32_t>(base, h.img_off[SRBA_I_ldl_row], sy.row.data(), sy.row.size());
+			put<int32_t>(base, h.img_off[SRBA_I_ldl_tile_ij], sy.tile_ij.data(), sy.tile_ij.size());
+			put<int32_t>(base, h.img_off[SRBA_I_ldl_src], sy.src.data(), sy.src.size());
+			put<int32_t>(base, h.img_off[SRBA_I_ldl_upd], sy.upd.data(), sy.upd.size());
+			put<int32_t>(base, h.img_off[SRBA_I_ldl_col_ptr], sy.col_ptr.data(), sy.col_ptr.size());
+			put<int32_t>(base, h.img_off[SRBA_I_ldl_col_tile], sy.col_tile.data(), sy.col_tile.size());
+		}
 	}
-	h.img_bytes = L.total();
 
+	// ---- reduced system == H_Ap when there is no Schur term (relative graph-SLAM): no copy, no Sblk
+	h.s_alias_hap = (p.n_S_terms == 0 && p.n_S == p.n_HAp) ? 1 : 0;
+	if (h.s_alias_hap)
+		for (int b = 0; b < p.n_S; b++)
+			if (p.S_HAp[b] != b) { h.s_alias_hap = 0; break; }
+
+	// ---- workspace
+	uint64_t ws_bytes[SRBA_W_COUNT];
+	{
+		uint64_t *w = ws_bytes;
+		w[SRBA_W_edge_cur] = (uint64_t)p.n_edges * S * 8; w[SRBA_W_edge_bak] = (uint64_t)p.n_unk_edges * S * 8;
+		w[SRBA_W_lm_cur] = (uint64_t)p.n_lms * 3 * 8; w[SRBA_W_lm_bak] = (uint64_t)p.n_unk_lms * 3 * 8;
+		w[SRBA_W_slot] = (uint64_t)2 * p.n_pairs * S * 8; w[SRBA_W_slot_bak] = w[SRBA_W_slot];
+		w[SRBA_W_JA] = (uint64_t)p.n_blkA * o * P * 8; w[SRBA_W_JF] = (uint64_t)p.n_blkF * o * 3 * 8;
+		w[SRBA_W_resid0] = (uint64_t)p.n_obs * o * 8; w[SRBA_W_resid1] = w[SRBA_W_resid0];
+		w[SRBA_W_HAp] = (uint64_t)p.n_HAp * P * P * 8; w[SRBA_W_HApf] = (uint64_t)p.n_HApf * P * 3 * 8;
+		w[SRBA_W_Hf] = (uint64_t)p.n_unk_lms * 9 * 8; w[SRBA_W_Hf_inv] = w[SRBA_W_Hf]; w[SRBA_W_W] = w[SRBA_W_HApf];
+		w[SRBA_W_Sblk] = h.s_alias_hap ? 0 : (uint64_t)p.n_S * P * P * 8;
+		w[SRBA_W_grad] = (uint64_t)h.n_scalars * 8; w[SRBA_W_delta] = w[SRBA_W_grad];
+		w[SRBA_W_dense] = (h.chol_mode == SRBA_CHOL_BLOCKED || want_dense) ? (uint64_t)h.n_dense * h.ld_dense * 8 : 0;
+		w[SRBA_W_valid] = p.n_obs; w[SRBA_W_blk_ok] = p.n_blkA + p.n_blkF; w[SRBA_W_lm_inv] = p.n_unk_lms;
+		w[SRBA_W_slot_listed] = 2 * p.n_pairs; w[SRBA_W_pair_refresh] = p.n_pairs;
+	}
 	Layout W;
-#define WS(name, bytes) h.ws_##name = W.add((uint64_t)(bytes));
-	WS(edge_cur, (size_t)p.n_edges * S * 8)
-	WS(edge_bak, (size_t)p.n_unk_edges * S * 8)
-	WS(lm_cur, (size_t)p.n_lms * 3 * 8)
-	WS(lm_bak, (size_t)p.n_unk_lms * 3 * 8)
-	WS(slot, (size_t)2 * p.n_pairs * S * 8)
-	WS(slot_bak, (size_t)2 * p.n_pairs * S * 8)
-	WS(JA, (size_t)p.n_blkA * o * P * 8)
-	WS(JF, (size_t)p.n_blkF * o * 3 * 8)
-	WS(resid0, (size_t)p.n_obs * o * 8)
-	WS(resid1, (size_t)p.n_obs * o * 8)
-	WS(HAp, (size_t)p.n_HAp * P * P * 8)
-	WS(HApf, (size_t)p.n_HApf * P * 3 * 8)
-	WS(Hf, (size_t)p.n_unk_lms * 9 * 8)
-	WS(Hf_inv, (size_t)p.n_unk_lms * 9 * 8)
-	WS(W, (size_t)p.n_HApf * P * 3 * 8)
-	WS(grad, (size_t)h.n_scalars * 8)
-	WS(delta, (size_t)h.n_scalars * 8)
-	WS(dense, (size_t)h.n_dense * h.ld_dense * 8)
-	WS(valid, p.n_obs)
-	WS(blk_ok, p.n_blkA + p.n_blkF)
-	WS(lm_inv, p.n_unk_lms)
-	WS(slot_listed, 2 * p.n_pairs)
-	WS(pair_refresh, p.n_pairs)
-#undef WS
+	for (int a = 0; a < SRBA_W_COUNT; a++) { h.ws_off[a] = W.add(ws_bytes[a]); h.ws_sm[a] = SRBA_NOT_IN_SMEM; }
 	h.ws_bytes = W.total();
+
+	// ---- on-chip placement: scratch first, then arrays in priority order (most latency-critical per byte first) while they fit
+	{
+		Layout A;
+		h.sm_scratch = (uint32_t)A.add(scratch_bytes);
+		const uint64_t budget = (uint64_t)cfg.smem_bytes;
+		struct Cand { int is_img, id; };
+		static const Cand order[] = {
+			{0, SRBA_W_edge_cur}, {0, SRBA_W_edge_bak}, {0, SRBA_W_grad}, {0, SRBA_W_delta}, {0, SRBA_W_lm_cur}, {0, SRBA_W_lm_bak},
+			{0, SRBA_W_valid}, {0, SRBA_W_lm_inv}, {0, SRBA_W_pair_refresh}, {0, SRBA_W_slot_listed},
+			{0, SRBA_W_resid0}, {0, SRBA_W_resid1}, {0, SRBA_W_slot}, {0, SRBA_W_HAp}, {0, SRBA_W_Hf}, {0, SRBA_W_Hf_inv},
+			{1, SRBA_I_ldl_row}, {1, SRBA_I_ldl_col_ptr}, {1, SRBA_I_ldl_tile_ij}, {1, SRBA_I_ldl_upd}, {1, SRBA_I_ldl_col_tile}, {1, SRBA_I_ldl_src}, {1, SRBA_I_unk_edge}, {1, SRBA_I_unk_lm}, {1, SRBA_I_obs_slot}, {1, SRBA_I_obs_z}, {1, SRBA_I_obs_mult}, {1, SRBA_I_obs_lm},
+			{1, SRBA_I_pair_path_ptr}, {1, SRBA_I_path_edge}, {1, SRBA_I_path_dir},
+			{0, SRBA_W_Sblk}, {0, SRBA_W_HApf}, {0, SRBA_W_W}, {0, SRBA_W_JA}, {0, SRBA_W_JF}, {0, SRBA_W_slot_bak}, {0, SRBA_W_blk_ok},
+			{1, SRBA_I_colA_ptr}, {1, SRBA_I_blkA_obs}, {1, SRBA_I_blkA_col}, {1, SRBA_I_blkA_slotA}, {1, SRBA_I_blkA_slotD}, {1, SRBA_I_blkA_normal_dir},
+			{1, SRBA_I_HAp_term_ptr}, {1, SRBA_I_HAp_term_a}, {1, SRBA_I_HAp_term_b}, {1, SRBA_I_HAp_row}, {1, SRBA_I_HAp_col},
+			{1, SRBA_I_S_row}, {1, SRBA_I_S_col},
+		};
+		for (const Cand &c : order) {
+			const uint64_t bytes = c.is_img ? h.img_len[c.id] : ws_bytes[c.id];
+			if (!bytes) continue;
+			const uint64_t start = (A.cur + 15) / 16 * 16;
+			if (start + (bytes + 15) / 16 * 16 > budget) continue;
+			const uint32_t off = (uint32_t)A.add((bytes + 15) / 16 * 16);
+			if (c.is_img) h.img_sm[c.id] = off; else h.ws_sm[c.id] = off;
+		}
+		h.sm_bytes = (uint32_t)A.total();
+	}
 
 	Layout R;
 	h.res_stats = R.add(sizeof(srba_stats_t));
@@ -184,7 +407,7 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 	h.res_dense = R.add(want_dense ? (size_t)h.n_dense * h.n_dense * 8 : 0);
 	h.res_trace = R.add((size_t)trace_cap * 6 * 8);
 	h.res_trace_delta = R.add((size_t)trace_cap * h.n_scalars * 8);
-	h.res_stage_cycles = R.add(16 * 8);
+	h.res_stage_cycles = R.add(24 * 8);
 	h.res_bytes = R.total();
 	if (base) std::memcpy(base, &h, sizeof(h));
 }
@@ -227,16 +450,17 @@ struct srba_batch {
 	int n = 0;
 	bool pooled = false;
 	std::vector<DevProblem> hdr;
+	std::vector<TileSymbolic> sym;
 	std::vector<uint64_t> img_off, ws_off, res_off;
 	std::vector<int32_t> order;      // grouped by model, cost-descending inside each group
 	int group_begin[5] = {0, 0, 0, 0, 0};
 	int group_max_n[4] = {0, 0, 0, 0};
+	int group_smem[4] = {0, 0, 0, 0};  // largest planned shared-memory arena of each model group
 	uint64_t tab_img_off = 0, tab_ws_off = 0, tab_res_off = 0, tab_order = 0;
 	uint64_t img_bytes = 0, ws_bytes = 0, res_bytes = 0;
 	char *h_img = nullptr, *h_res = nullptr;
 	char *d_img = nullptr, *d_ws = nullptr, *d_res = nullptr;
 	int64_t launches = 0;
-	int sm_count = 148;
 	bool uploaded = false, downloaded = false;
 };
 
@@ -274,6 +498,7 @@ static srba_batch_t *batch_create_impl(int32_t n, const srba_problem_t *const *i
 	srba_batch_t *b = new srba_batch();
 	b->n = n;
 	b->hdr.resize(n);
+	b->sym.resize(n);
 	b->img_off.resize(n); b->ws_off.resize(n); b->res_off.resize(n); b->order.resize(n);
 	const int want_dense = trace_cap < 0 ? 1 : 0;  // negative trace_cap: |trace_cap| trials of trace AND the dense Hessian
 	const int tcap = trace_cap < 0 ? -trace_cap : trace_cap;
@@ -284,17 +509,14 @@ static srba_batch_t *batch_create_impl(int32_t n, const srba_problem_t *const *i
 	b->tab_order = I.add((uint64_t)n * 4);
 	uint64_t ws = 0, rs = 0;
 	for (int i = 0; i < n; i++) {
-		pack_problem(*in[i], b->hdr[i], nullptr, tcap, want_dense);
+		pack_problem(*in[i], b->hdr[i], nullptr, tcap, want_dense, b->sym[i]);
 		b->img_off[i] = I.add(b->hdr[i].img_bytes);
 		b->ws_off[i] = ws; ws += b->hdr[i].ws_bytes;
 		b->res_off[i] = rs; rs += b->hdr[i].res_bytes;
 	}
 	b->img_bytes = I.total(); b->ws_bytes = std::max<uint64_t>(ws, 16); b->res_bytes = std::max<uint64_t>(rs, 16);
 	std::iota(b->order.begin(), b->order.end(), 0);
-	auto model_of = [&](int i) {
-		const srba_model_t &m = b->hdr[i].model;
-		return m.pose_kind == SRBA_POSE_SE2 ? 0 : (m.obs_kind == SRBA_OBS_CARTESIAN3D ? 1 : (m.obs_kind == SRBA_OBS_MONO ? 2 : 3));
-	};
+	auto model_of = [&](int i) { return model_index(b->hdr[i].model); };
 	std::stable_sort(b->order.begin(), b->order.end(), [&](int a, int c) {
 		const int ma = model_of(a), mc = model_of(c);
 		if (ma != mc) return ma < mc;
@@ -302,12 +524,9 @@ static srba_batch_t *batch_create_impl(int32_t n, const srba_problem_t *const *i
 	});
 	{
 		int cnt[4] = {0, 0, 0, 0};
-		for (int i = 0; i < n; i++) { const int g = model_of(i); cnt[g]++; b->group_max_n[g] = std::max(b->group_max_n[g], b->hdr[i].n_dense); }
+		for (int i = 0; i < n; i++) { const int g = model_of(i); cnt[g]++; b->group_max_n[g] = std::max(b->group_max_n[g], b->hdr[i].n_dense); b->group_smem[g] = std::max(b->group_smem[g], (int)b->hdr[i].sm_bytes); }
 		for (int g = 0; g < 4; g++) b->group_begin[g + 1] = b->group_begin[g] + cnt[g];
 	}
-	cudaDeviceProp prop;
-	int dev = 0;
-	if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess) b->sm_count = prop.multiProcessorCount;
 	bool ok;
 	if (pool) {
 		b->pooled = true;
@@ -331,7 +550,7 @@ static srba_batch_t *batch_create_impl(int32_t n, const srba_problem_t *const *i
 	std::memcpy(b->h_img + b->tab_order, b->order.data(), (size_t)n * 4);
 	for (int i = 0; i < n; i++) {
 		b->hdr[i].cost_rank = 0;
-		pack_problem(*in[i], b->hdr[i], b->h_img + b->img_off[i], tcap, want_dense);
+		pack_problem(*in[i], b->hdr[i], b->h_img + b->img_off[i], tcap, want_dense, b->sym[i]);
 	}
 	return b;
 }
@@ -350,13 +569,11 @@ int srba_b200_batch_run(srba_batch_t *b, void *stream) {
 	for (int g = 0; g < 4; g++) {
 		const int cnt = b->group_begin[g + 1] - b->group_begin[g];
 		if (!cnt) continue;
-		// one CTA per problem, dispatched in cost-descending order (largest first); staged Cholesky panel sized for the
-		// largest problem of the group, capped so that 2 CTAs/SM stay resident
-		const int panel_cap = std::min(std::max((b->group_max_n[g] + 1 + 3) / 4 * 4, 24), 1024);
+		// one CTA per problem, dispatched in cost-descending order (largest first)
 		const int rc = srba_launch_lm_batch(g, b->d_img, reinterpret_cast<const uint64_t *>(b->d_img + b->tab_img_off), b->d_ws,
 		                                    reinterpret_cast<const uint64_t *>(b->d_img + b->tab_ws_off), b->d_res,
 		                                    reinterpret_cast<const uint64_t *>(b->d_img + b->tab_res_off),
-		                                    reinterpret_cast<const int32_t *>(b->d_img + b->tab_order) + b->group_begin[g], cnt, cnt, panel_cap, stream);
+		                                    reinterpret_cast<const int32_t *>(b->d_img + b->tab_order) + b->group_begin[g], cnt, cnt, b->group_smem[g], stream);
 		if (rc != 0) return fail(SRBA_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
 		b->launches++;
 	}
@@ -392,9 +609,9 @@ int srba_b200_batch_unpack(srba_batch_t *b, int32_t i, srba_result_t *out) {
 	return out->stats.status;
 }
 
-int srba_b200_batch_stage_cycles(srba_batch_t *b, int32_t i, uint64_t out[16]) {
+int srba_b200_batch_stage_cycles(srba_batch_t *b, int32_t i, uint64_t out[24]) {
 	if (!b || i < 0 || i >= b->n || !b->downloaded) return fail(SRBA_ERR_BAD_ARGUMENT, "bad stage_cycles arguments");
-	std::memcpy(out, b->h_res + b->res_off[i] + b->hdr[i].res_stage_cycles, 16 * 8);
+	std::memcpy(out, b->h_res + b->res_off[i] + b->hdr[i].res_stage_cycles, 24 * 8);
 	return SRBA_OK;
 }
 int64_t srba_b200_batch_h2d_bytes(const srba_batch_t *b) { return b ? (int64_t)b->img_bytes : 0; }
@@ -420,6 +637,21 @@ void srba_b200_batch_algorithmic_bytes(const srba_batch_t *b, double out[5]) {
 	}
 }
 
+int srba_b200_problem_plan(const srba_problem_t *in, int64_t out[8]) {
+	if (!in || !out) return fail(SRBA_ERR_BAD_ARGUMENT, "null argument");
+	const int rc = validate(*in);
+	if (rc != SRBA_OK) return rc;
+	DevProblem h;
+	TileSymbolic sy;
+	pack_problem(*in, h, nullptr, 0, 0, sy);
+	int n_img = 0, n_ws = 0;
+	for (int a = 0; a < SRBA_I_COUNT; a++) n_img += (h.img_sm[a] != SRBA_NOT_IN_SMEM && h.img_len[a]) ? 1 : 0;
+	for (int a = 0; a < SRBA_W_COUNT; a++) n_ws += h.ws_sm[a] != SRBA_NOT_IN_SMEM ? 1 : 0;
+	out[0] = (int64_t)h.img_bytes; out[1] = (int64_t)h.ws_bytes; out[2] = (int64_t)h.res_bytes; out[3] = h.sm_bytes;
+	out[4] = h.chol_mode; out[5] = n_img; out[6] = n_ws; out[7] = srba_kernel_cfg(model_index(in->model)).smem_bytes;
+	return SRBA_OK;
+}
+
 int srba_b200_optimize_batch(int32_t n, const srba_problem_t *const *in, srba_result_t *const *out) {
 	if (!out) return fail(SRBA_ERR_BAD_ARGUMENT, "null out");
 	int tcap = 0, want_dense = 0;
@@ -429,20 +661,31 @@ int srba_b200_optimize_batch(int32_t n, const srba_problem_t *const *in, srba_re
 		if (out[i]->dense_hessian) want_dense = 1;
 	}
 	if (want_dense && tcap == 0) tcap = 1;
+	static const bool timing = std::getenv("SRBA_B200_TIMING") != nullptr;  // host-side phase timings on stderr
+	auto now = [] { return std::chrono::steady_clock::now(); };
+	auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point c) { return std::chrono::duration<double, std::milli>(c - a).count(); };
+	const auto t0 = now();
 	srba_batch_t *b = batch_create_impl(n, in, want_dense ? -tcap : tcap, &g_pool);
 	if (!b) return g_code != SRBA_OK ? g_code : SRBA_ERR_INTERNAL;
+	const auto t1 = now();
 	int rc = SRBA_OK;
 	if (!g_pool.stream && cudaStreamCreateWithFlags(&g_pool.stream, cudaStreamNonBlocking) != cudaSuccess) rc = fail(SRBA_ERR_CUDA, "cudaStreamCreate failed");
 	cudaStream_t st = g_pool.stream;
 	if (rc == SRBA_OK) rc = srba_b200_batch_upload(b, st);
 	if (rc == SRBA_OK) rc = srba_b200_batch_run(b, st);
+	const auto t2 = now();
 	if (rc == SRBA_OK) rc = srba_b200_batch_download(b, st);
+	const auto t3 = now();
 	if (rc == SRBA_OK)
 		for (int i = 0; i < n; i++) {
 			const int r = srba_b200_batch_unpack(b, i, out[i]);
 			if (r != SRBA_OK && rc == SRBA_OK) rc = r;
 		}
 	srba_b200_batch_destroy(b);
+	if (timing) {
+		const auto t4 = now();
+		std::fprintf(stderr, "[srba_b200] optimize_batch n=%d: pack %.3f ms, enqueue %.3f ms, wait+d2h %.3f ms, unpack %.3f ms\n", n, ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4));
+	}
 	return rc;
 }
 

@@ -1,12 +1,61 @@
 // Packed device image of one flattened optimize_edges() problem (host/device shared POD).
 // The host packer (capi.cpp) lays every array of srba_problem_t (include/srba_b200.h) out in ONE contiguous,
 // 16-byte-aligned blob per problem, all problems of a batch back to back, so a batch is one H2D copy.
-// Offsets are in BYTES: img_* relative to the problem's blob in the input image, ws_* relative to the problem's
+// Offsets are in BYTES: img_off[] relative to the problem's blob in the input image, ws_off[] relative to the problem's
 // workspace, res_* relative to the problem's result blob.
+//
+// On-chip residency: the LM kernel (lm_kernel.cu) owns a shared-memory ARENA per CTA.  The packer decides, per problem
+// and in priority order, which mutable workspace arrays (and which hot read-only index arrays of the image) live in that
+// arena for the whole LM loop (sm offset != SRBA_NOT_IN_SMEM) and which stay in the L2-resident global workspace.
 #pragma once
 #include <stdint.h>
 
 #include "../../include/srba_b200.h"
+
+#define SRBA_NOT_IN_SMEM 0xFFFFFFFFu
+
+// (type, name) of every array of the input image, in srba_problem_t order + derived ones: block -> column, and the
+// symbolic factorisation of the reduced system at 3x3-tile granularity (tiles numbered row-major, diagonal first, the
+// right-hand side as tile column NTR):  ldl_row[4*(NTR+1)] per row {first tile, end tile | has_superdiag<<30, first
+// update, end update} (+ sentinel);  ldl_tile_ij (ti<<16|tj);  ldl_src: where the tile comes from (offset into the reduced
+// blocks, -1 fill-in, -2-row right-hand side);  ldl_upd: per eliminated row the updates {dst tile | tile(k,i)<<16,
+// tile(k,j)} (the one that hits the next pivot block is implicit);  ldl_col_ptr / ldl_col_tile: off-diagonal tiles per column.
+#define SRBA_IMG_ARRAYS(X)                                                                                              \
+	X(double, edge_pose) X(int32_t, unk_edge) X(double, lm_pos) X(int32_t, unk_lm)                                       \
+	X(int32_t, pair_path_ptr) X(int32_t, path_edge) X(uint8_t, path_dir)                                                 \
+	X(double, obs_z) X(int32_t, obs_slot) X(int32_t, obs_lm) X(int32_t, obs_mult)                                        \
+	X(int32_t, colA_ptr) X(int32_t, blkA_obs) X(int32_t, blkA_slotA) X(int32_t, blkA_slotD) X(uint8_t, blkA_normal_dir)  \
+	X(int32_t, colF_ptr) X(int32_t, blkF_obs) X(int32_t, blkF_slot)                                                      \
+	X(int32_t, row_ptr) X(int32_t, row_blk)                                                                              \
+	X(int32_t, HAp_row) X(int32_t, HAp_col) X(int32_t, HAp_term_ptr) X(int32_t, HAp_term_a) X(int32_t, HAp_term_b)       \
+	X(int32_t, HApf_row) X(int32_t, HApf_col) X(int32_t, HApf_term_ptr) X(int32_t, HApf_term_a) X(int32_t, HApf_term_f)  \
+	X(int32_t, rowApf_ptr) X(int32_t, colApf_ptr) X(int32_t, colApf_idx)                                                 \
+	X(int32_t, S_row) X(int32_t, S_col) X(int32_t, S_HAp) X(int32_t, S_term_ptr) X(int32_t, S_term_rowblk) X(int32_t, S_term_colblk) \
+	X(int32_t, blkA_col) X(int32_t, blkF_col) X(int32_t, ldl_row) X(int32_t, ldl_tile_ij) X(int32_t, ldl_src) X(int32_t, ldl_upd) X(int32_t, ldl_col_ptr) X(int32_t, ldl_col_tile)
+
+// (type, name) of every workspace array.
+#define SRBA_WS_ARRAYS(X)                                                                                               \
+	X(double, edge_cur) X(double, edge_bak) X(double, lm_cur) X(double, lm_bak) X(double, slot) X(double, slot_bak)      \
+	X(double, JA) X(double, JF) X(double, resid0) X(double, resid1)                                                      \
+	X(double, HAp) X(double, HApf) X(double, Hf) X(double, Hf_inv) X(double, W) X(double, Sblk)                          \
+	X(double, grad) X(double, delta) X(double, dense)                                                                    \
+	X(uint8_t, valid) X(uint8_t, blk_ok) X(uint8_t, lm_inv) X(uint8_t, slot_listed) X(uint8_t, pair_refresh)
+
+enum {
+#define X(T, name) SRBA_I_##name,
+	SRBA_IMG_ARRAYS(X)
+#undef X
+	SRBA_I_COUNT
+};
+enum {
+#define X(T, name) SRBA_W_##name,
+	SRBA_WS_ARRAYS(X)
+#undef X
+	SRBA_W_COUNT
+};
+
+// How the dense reduced system is solved for this problem (decided by the packer from the kernel's tile capacity).
+enum { SRBA_CHOL_REG = 0 /* on-chip block-sparse LDL^t */, SRBA_CHOL_BLOCKED = 1 /* dense blocked Cholesky in the L2-resident workspace */ };
 
 struct DevProblem {
 	srba_model_t model;
@@ -19,29 +68,40 @@ struct DevProblem {
 	int32_t trace_cap;
 	int32_t cost_rank;   // position in the batch's cost-descending order (scheduling only)
 	int32_t want_dense;  // copy the dense reduced Hessian of the last solve into the result blob
+	int32_t chol_mode;   // SRBA_CHOL_*
+	int32_t panel_cap;   // SRBA_CHOL_BLOCKED: columns of the staged 8-row panel that fit the scratch
+	int32_t ldl_n_tiles; // SRBA_CHOL_REG: 3x3 tiles of the filled pattern incl. the right-hand-side column
+	int32_t s_alias_hap; // 1: no Schur terms and S block b == H_Ap block b -> the reduced blocks ARE the H_Ap blocks
+	uint32_t sm_scratch; // byte offset of the Cholesky scratch inside the CTA's dynamic shared memory
+	uint32_t sm_bytes;   // dynamic shared memory this problem uses (scratch + arena)
 
-	// ---- input image
-	uint64_t img_edge_pose, img_unk_edge, img_lm_pos, img_unk_lm;
-	uint64_t img_pair_path_ptr, img_path_edge, img_path_dir;
-	uint64_t img_obs_z, img_obs_slot, img_obs_lm, img_obs_mult;
-	uint64_t img_colA_ptr, img_blkA_obs, img_blkA_col, img_blkA_slotA, img_blkA_slotD, img_blkA_normal_dir;
-	uint64_t img_colF_ptr, img_blkF_obs, img_blkF_col, img_blkF_slot;
-	uint64_t img_row_ptr, img_row_blk;
-	uint64_t img_HAp_row, img_HAp_col, img_HAp_term_ptr, img_HAp_term_a, img_HAp_term_b;
-	uint64_t img_HApf_row, img_HApf_col, img_HApf_term_ptr, img_HApf_term_a, img_HApf_term_f;
-	uint64_t img_rowApf_ptr, img_colApf_ptr, img_colApf_idx;
-	uint64_t img_S_row, img_S_col, img_S_HAp, img_S_term_ptr, img_S_term_rowblk, img_S_term_colblk;
+	uint64_t img_off[SRBA_I_COUNT];
+	uint32_t img_len[SRBA_I_COUNT];  // bytes
+	uint32_t img_sm[SRBA_I_COUNT];   // offset of the on-chip copy or SRBA_NOT_IN_SMEM
 	uint64_t img_bytes;
 
-	// ---- workspace (doubles unless noted)
-	uint64_t ws_edge_cur, ws_edge_bak, ws_lm_cur, ws_lm_bak, ws_slot, ws_slot_bak;
-	uint64_t ws_JA, ws_JF, ws_resid0, ws_resid1;
-	uint64_t ws_HAp, ws_HApf, ws_Hf, ws_Hf_inv, ws_W;
-	uint64_t ws_grad, ws_delta, ws_dense;
-	uint64_t ws_valid, ws_blk_ok, ws_lm_inv, ws_slot_listed, ws_pair_refresh;  // bytes
+	uint64_t ws_off[SRBA_W_COUNT];
+	uint32_t ws_sm[SRBA_W_COUNT];    // offset in the arena or SRBA_NOT_IN_SMEM (then ws_off is used)
 	uint64_t ws_bytes;
 
 	// ---- result blob
 	uint64_t res_stats, res_edge_pose, res_lm_pos, res_slot_pose, res_obs_valid, res_lm_inv, res_Hf_diag, res_dense, res_trace, res_trace_delta, res_stage_cycles;
 	uint64_t res_bytes;
 };
+
+// Per-model kernel configuration shared by the packer and the launcher.
+struct SrbaKernelCfg {
+	int threads;      // CTA size
+	int tpt;          // register tiles per thread of the dense solver
+	int smem_bytes;   // dynamic shared memory per CTA (Cholesky scratch + arena)
+};
+#ifdef __cplusplus
+extern "C" {
+#endif
+// model: 0 = SE2+RelativePoses2D, 1 = SE3+Cartesian3D, 2 = SE3+Mono, 3 = SE3+Stereo
+SrbaKernelCfg srba_kernel_cfg(int model);
+// doubles of shared-memory scratch the register-resident solver needs; <0 when the filled pattern does not fit the tiles
+int srba_chol_reg_scratch_doubles(int model, int n_dense, int n_tiles);
+#ifdef __cplusplus
+}
+#endif

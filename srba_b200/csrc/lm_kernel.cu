@@ -12,21 +12,37 @@
 // CPU path only by FMA contraction.
 #include <cuda_runtime.h>
 #include <math.h>
+
+#include <algorithm>
 #include <stdint.h>
 
 #include "dev_types.h"
 
-#define LM_THREADS 256
+// CTA size is a launch parameter (per-model, srba_kernel_cfg): every stage strides by the run-time block size.
+#define LM_THREADS ((int)blockDim.x)
+#define LM_MAX_WARPS 32
 #define MAXO 4
 
 namespace {
 
 // ------------------------------------------------------------------------------------------------ pose algebra
+// The LM program is latency-bound on a handful of warps, and ncu shows the instruction cache as a first-order limiter
+// (icc hit rate 65 %, "no instruction" the second largest stall): the transcendental helpers are therefore kept OUT of
+// line so that the kernel holds one copy of each instead of one per call site.
+__device__ __noinline__ void sincos_ni(double a, double *s, double *c) { sincos(a, s, c); }
+__device__ __noinline__ double fmod_2pi_ni(double a) { return fmod(a, 2.0 * M_PI); }
 __device__ __forceinline__ double wrapTo2Pi(double a) {  // mrpt::math::wrapTo2Pi
+	// fmod(a, 2pi) costs ~330 cycles on B200 (tools/microbench); for |a| < 4pi -- every angle this path produces -- the
+	// same value comes from at most one subtraction, which is EXACT (Sterbenz), so the result is bit-identical to fmod's.
+	const double T = 2.0 * M_PI;
 	const bool was_neg = a < 0;
-	a = fmod(a, 2.0 * M_PI);
-	if (was_neg) a += 2.0 * M_PI;
-	return a;
+	const double m = fabs(a);
+	double r;
+	if (m < T) r = a;
+	else if (m < 2.0 * T) r = was_neg ? a + T : a - T;
+	else r = fmod_2pi_ni(a);
+	if (was_neg) r += T;
+	return r;
 }
 __device__ __forceinline__ double wrapToPi(double a) { return wrapTo2Pi(a + M_PI) - M_PI; }
 
@@ -39,7 +55,7 @@ struct PoseOps<3> {  // CPose2D: x,y,phi
 	__device__ static void identity(double *p) { p[0] = 0; p[1] = 0; p[2] = 0; }
 	__device__ static void compose(double *o, const double *a, const double *b) {
 		double s, c;
-		sincos(a[2], &s, &c);
+		sincos_ni(a[2], &s, &c);
 		const double nx = a[0] + b[0] * c - b[1] * s;
 		const double ny = a[1] + b[0] * s + b[1] * c;
 		const double nphi = wrapToPi(a[2] + b[2]);
@@ -47,7 +63,7 @@ struct PoseOps<3> {  // CPose2D: x,y,phi
 	}
 	__device__ static void inverse(double *o, const double *a) {
 		double s, c;
-		sincos(a[2], &s, &c);
+		sincos_ni(a[2], &s, &c);
 		const double x = a[0], y = a[1];
 		o[0] = -x * c - y * s;
 		o[1] = x * s - y * c;
@@ -138,48 +154,37 @@ template <> struct ObsDims<SRBA_OBS_MONO> { static constexpr int O = 2; };
 template <> struct ObsDims<SRBA_OBS_STEREO> { static constexpr int O = 4; };
 
 // ------------------------------------------------------------------------------------------------ views
+// Every array is reached through a generic pointer that targets either the CTA's shared-memory arena (when the packer
+// placed it there, dev_types.h) or the problem's blob in global memory.
 struct View {
 	const DevProblem *h;
 	// inputs
-	const double *edge_pose, *lm_pos, *obs_z;
-	const int32_t *unk_edge, *unk_lm, *pair_path_ptr, *path_edge, *obs_slot, *obs_lm, *obs_mult;
-	const uint8_t *path_dir, *blkA_normal_dir;
-	const int32_t *colA_ptr, *blkA_obs, *blkA_col, *blkA_slotA, *blkA_slotD, *colF_ptr, *blkF_obs, *blkF_col, *blkF_slot;
-	const int32_t *row_ptr, *row_blk;
-	const int32_t *HAp_row, *HAp_col, *HAp_term_ptr, *HAp_term_a, *HAp_term_b;
-	const int32_t *HApf_row, *HApf_col, *HApf_term_ptr, *HApf_term_a, *HApf_term_f, *rowApf_ptr, *colApf_ptr, *colApf_idx;
-	const int32_t *S_row, *S_col, *S_HAp, *S_term_ptr, *S_term_rowblk, *S_term_colblk;
+#define X(T, name) const T *name;
+	SRBA_IMG_ARRAYS(X)
+#undef X
 	// workspace
-	double *edge_cur, *edge_bak, *lm_cur, *lm_bak, *slot, *slot_bak, *JA, *JF, *resid[2], *HAp, *HApf, *Hf, *Hf_inv, *W, *grad, *delta, *dense;
-	uint8_t *valid, *blk_ok, *lm_inv, *slot_listed, *pair_refresh;
+#define X(T, name) T *name;
+	SRBA_WS_ARRAYS(X)
+#undef X
+	double *resid[2];
+	const double *S;  // reduced-system blocks: Sblk, or HAp itself when there is no Schur term (h->s_alias_hap)
 	// results
 	srba_stats_t *stats;
 	double *r_edge_pose, *r_lm_pos, *r_slot_pose, *r_Hf_diag, *r_dense, *r_trace, *r_trace_delta;
 	uint8_t *r_obs_valid, *r_lm_inv;
 };
 
-__device__ void make_view(View &v, const DevProblem *h, const char *img, char *ws, char *res) {
+__device__ void make_view(View &v, const DevProblem *h, const char *img, char *ws, char *res, char *arena) {
 	v.h = h;
-#define IMG(T, name) v.name = reinterpret_cast<const T *>(img + h->img_##name)
-	IMG(double, edge_pose); IMG(int32_t, unk_edge); IMG(double, lm_pos); IMG(int32_t, unk_lm);
-	IMG(int32_t, pair_path_ptr); IMG(int32_t, path_edge); IMG(uint8_t, path_dir);
-	IMG(double, obs_z); IMG(int32_t, obs_slot); IMG(int32_t, obs_lm); IMG(int32_t, obs_mult);
-	IMG(int32_t, colA_ptr); IMG(int32_t, blkA_obs); IMG(int32_t, blkA_col); IMG(int32_t, blkA_slotA); IMG(int32_t, blkA_slotD); IMG(uint8_t, blkA_normal_dir);
-	IMG(int32_t, colF_ptr); IMG(int32_t, blkF_obs); IMG(int32_t, blkF_col); IMG(int32_t, blkF_slot);
-	IMG(int32_t, row_ptr); IMG(int32_t, row_blk);
-	IMG(int32_t, HAp_row); IMG(int32_t, HAp_col); IMG(int32_t, HAp_term_ptr); IMG(int32_t, HAp_term_a); IMG(int32_t, HAp_term_b);
-	IMG(int32_t, HApf_row); IMG(int32_t, HApf_col); IMG(int32_t, HApf_term_ptr); IMG(int32_t, HApf_term_a); IMG(int32_t, HApf_term_f);
-	IMG(int32_t, rowApf_ptr); IMG(int32_t, colApf_ptr); IMG(int32_t, colApf_idx);
-	IMG(int32_t, S_row); IMG(int32_t, S_col); IMG(int32_t, S_HAp); IMG(int32_t, S_term_ptr); IMG(int32_t, S_term_rowblk); IMG(int32_t, S_term_colblk);
-#undef IMG
-#define WS(T, name) v.name = reinterpret_cast<T *>(ws + h->ws_##name)
-	WS(double, edge_cur); WS(double, edge_bak); WS(double, lm_cur); WS(double, lm_bak); WS(double, slot); WS(double, slot_bak);
-	WS(double, JA); WS(double, JF);
-	v.resid[0] = reinterpret_cast<double *>(ws + h->ws_resid0);
-	v.resid[1] = reinterpret_cast<double *>(ws + h->ws_resid1);
-	WS(double, HAp); WS(double, HApf); WS(double, Hf); WS(double, Hf_inv); WS(double, W); WS(double, grad); WS(double, delta); WS(double, dense);
-	WS(uint8_t, valid); WS(uint8_t, blk_ok); WS(uint8_t, lm_inv); WS(uint8_t, slot_listed); WS(uint8_t, pair_refresh);
-#undef WS
+#define X(T, name) v.name = reinterpret_cast<const T *>(h->img_sm[SRBA_I_##name] != SRBA_NOT_IN_SMEM ? arena + h->img_sm[SRBA_I_##name] : img + h->img_off[SRBA_I_##name]);
+	SRBA_IMG_ARRAYS(X)
+#undef X
+#define X(T, name) v.name = reinterpret_cast<T *>(h->ws_sm[SRBA_W_##name] != SRBA_NOT_IN_SMEM ? arena + h->ws_sm[SRBA_W_##name] : ws + h->ws_off[SRBA_W_##name]);
+	SRBA_WS_ARRAYS(X)
+#undef X
+	v.resid[0] = v.resid0;
+	v.resid[1] = v.resid1;
+	v.S = h->s_alias_hap ? v.HAp : v.Sblk;
 	v.stats = reinterpret_cast<srba_stats_t *>(res + h->res_stats);
 	v.r_edge_pose = reinterpret_cast<double *>(res + h->res_edge_pose);
 	v.r_lm_pos = reinterpret_cast<double *>(res + h->res_lm_pos);
@@ -196,8 +201,11 @@ __device__ void make_view(View &v, const DevProblem *h, const char *img, char *w
 enum { ST_INIT = 0, ST_SCHUR, ST_CHOL, ST_BACKSUB, ST_FEATURES, ST_UPDATE, ST_CHAIN, ST_RESID, ST_RHO, ST_JACOB, ST_HESS, ST_GRAD, ST_CTRL, ST_OUT, ST_COUNT };
 
 struct Shared {
-	double red[LM_THREADS / 32];
+	DevProblem hdr;         // on-chip copy of the problem header (model parameters, counts, placement tables)
+	View view;              // resolved array pointers (arena or global), one copy per CTA
+	double red[LM_MAX_WARPS];
 	unsigned long long stage_cycles[ST_COUNT];
+	unsigned long long dbg[8];  // solver sub-timers: gather, factor loop, back-substitution loop, critical-thread busy time
 	unsigned long long t_last;
 	double U11[64];         // diagonal block of the blocked Cholesky
 	double xblk[8];
@@ -240,7 +248,8 @@ __device__ __forceinline__ double team_max(double v, Shared &sh) {
 // ------------------------------------------------------------------------------------------------ stages
 // K1: numeric spanning tree.  update_numeric_only_all_from_node (impl/spantree_update_numeric.h:19-81)
 template <int P>
-__device__ void stage_chain(const View &v, bool only_refresh) {
+__device__ __noinline__ void stage_chain(const View &vs, bool only_refresh) {
+	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	constexpr int S = PoseOps<P>::S;
 	const int n = v.h->n_pairs;
 	for (int t = threadIdx.x; t < n; t += LM_THREADS) {
@@ -332,8 +341,8 @@ __device__ bool jacob_dh_dAp(const View &v, int b, double *J) {
 			PoseOps<3>::compose(bwo, Ap, Dp);
 		}
 		double s_ad, c_ad, s_a, c_a;
-		sincos(bwo[2], &s_ad, &c_ad);
-		sincos(PHIa, &s_a, &c_a);
+		sincos_ni(bwo[2], &s_ad, &c_ad);
+		sincos_ni(PHIa, &s_a, &c_a);
 		const double J0[9] = {c_ad, s_ad, 0, -s_ad, c_ad, 0, 0, 0, 1};
 		const double J1[9] = {1, 0, -Xd * s_a - Yd * c_a, 0, 1, Xd * c_a - Yd * s_a, 0, 0, 1};
 		const double J2[9] = {c_a, -s_a, 0, s_a, c_a, 0, 0, 0, 1};
@@ -423,7 +432,8 @@ __device__ bool jacob_dh_df(const View &v, int b, double *J) {
 // row's validity byte; blocks walked before it keep their fresh value, blocks walked after it keep their PREVIOUS value.
 // `first` additionally records which numeric-ST entries the walk registers in list_of_required_num_poses (:226-230,:902-903).
 template <int P, int OBSK>
-__device__ void stage_jacobians(const View &v, bool first) {
+__device__ __noinline__ void stage_jacobians(const View &vs, bool first) {
+	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	constexpr int O = ObsDims<OBSK>::O;
 	const int nA = v.h->n_blkA, nF = (OBSK == SRBA_OBS_RELPOSES2D) ? 0 : v.h->n_blkF;
 	const bool can_fail = (OBSK == SRBA_OBS_MONO || OBSK == SRBA_OBS_STEREO);
@@ -525,7 +535,8 @@ __device__ __forceinline__ double jtj_elem(const DevProblem *h, const double *J1
 // K2b: sparse_hessian_update_numeric x3 (impl/sparse_hessian_update_numeric.h:22-60): one thread per block element,
 // terms in ascending observation order, invalid rows skipped, identity noise scaled by 1/sigma afterwards.
 template <int P, int OBSK>
-__device__ void stage_hessian(const View &v) {
+__device__ __noinline__ void stage_hessian(const View &vs) {
+	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	constexpr int O = ObsDims<OBSK>::O;
 	const DevProblem *h = v.h;
 	const double scale = (h->model.noise_kind == SRBA_NOISE_IDENTITY) ? 1.0 / h->model.noise_std : 1.0;
@@ -567,7 +578,8 @@ __device__ void stage_hessian(const View &v) {
 // reprojection_residuals (impl/reprojection_residuals.h:16-81) + sensor_model<>::observe_error; returns the team-wide
 // total squared error INCLUDING the duplicated rows of optimize_edges.h:177-193 (obs_mult).
 template <int P, int OBSK>
-__device__ double stage_residuals(const View &v, double *resid, Shared &sh) {
+__device__ __noinline__ double stage_residuals(const View &vs, double *resid, Shared &sh) {
+	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	constexpr int S = PoseOps<P>::S;
 	constexpr int O = ObsDims<OBSK>::O;
 	const DevProblem *h = v.h;
@@ -580,7 +592,7 @@ __device__ double stage_residuals(const View &v, double *resid, Shared &sh) {
 			double Pp[3] = {0, 0, 0};
 			if (s >= 0) { Pp[0] = v.slot[(size_t)s * S]; Pp[1] = v.slot[(size_t)s * S + 1]; Pp[2] = v.slot[(size_t)s * S + 2]; }
 			double sn, cs;
-			sincos(Pp[2], &sn, &cs);
+			sincos_ni(Pp[2], &sn, &cs);
 			r[0] = (z[0] - Pp[0]) * cs + (z[1] - Pp[1]) * sn;
 			r[1] = -(z[0] - Pp[0]) * sn + (z[1] - Pp[1]) * cs;
 			r[2] = wrapToPi(z[2] - Pp[2]);
@@ -630,7 +642,8 @@ __device__ double stage_residuals(const View &v, double *resid, Shared &sh) {
 
 // compute_minus_gradient (impl/compute_minus_gradient.h:20-91): one thread per scalar unknown, blocks in ascending obs.
 template <int P, int OBSK>
-__device__ void stage_gradient(const View &v, const double *resid) {
+__device__ __noinline__ void stage_gradient(const View &vs, const double *resid) {
+	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	constexpr int O = ObsDims<OBSK>::O;
 	const DevProblem *h = v.h;
 	const bool ident = (h->model.noise_kind == SRBA_NOISE_IDENTITY);
@@ -729,13 +742,16 @@ __device__ bool fullpiv_lu_inverse3(const double *Ain, double *inv) {
 	return true;
 }
 
-// K3: SchurComplement::numeric_build_reduced_system(lambda) (impl/schur.h:180-268) fused with the dense fill of
-// solver_engine<true,true>::solve (impl/lev-marq_solvers.h:492-519).  The reduced gradient head is written IN PLACE
-// (quirk SURVEY.md §9-1) and also copied into the augmented column of the dense system.
+// K3: SchurComplement::numeric_build_reduced_system(lambda) (impl/schur.h:180-268).  Writes the reduced blocks
+// S_ji = HAp_ji - sum_k W_jk HApf_ik^T into Sblk (lambda is added when the dense system is filled, as the reference does,
+// lev-marq_solvers.h:506-509) and reduces the gradient head IN PLACE (quirk SURVEY.md §9-1).  Without landmark unknowns
+// (relative graph-SLAM) the reduced system IS H_Ap and this stage is empty.
 template <int P>
-__device__ void stage_schur_and_fill(const View &v, double lambda) {
+__device__ __noinline__ void stage_schur(const View &vs, double lambda) {
+	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	const DevProblem *h = v.h;
-	const int nf = h->n_unk_lms, n = h->n_dense, ld = h->ld_dense;
+	const int nf = h->n_unk_lms, n = h->n_dense;
+	if (nf == 0 && h->s_alias_hap) return;
 	// (1) inv(Hf_kk + lambda I)
 	for (int k = threadIdx.x; k < nf; k += LM_THREADS) {
 		double M[9], inv[9];
@@ -749,8 +765,6 @@ __device__ void stage_schur_and_fill(const View &v, double lambda) {
 			for (int i = 0; i < 9; i++) v.Hf_inv[(size_t)k * 9 + i] = inv[i];
 		}
 	}
-	// zero the dense system (denseH.setZero, lev-marq_solvers.h:492)
-	for (size_t i = threadIdx.x; i < (size_t)n * ld; i += LM_THREADS) v.dense[i] = 0;
 	__syncthreads();
 	// (2) W_ik = HApf_ik * inv_k
 	for (int it = threadIdx.x; it < h->n_HApf * P * 3; it += LM_THREADS) {
@@ -762,12 +776,11 @@ __device__ void stage_schur_and_fill(const View &v, double lambda) {
 		v.W[it] = Hb[a * 3 + 0] * inv[0 * 3 + b] + Hb[a * 3 + 1] * inv[1 * 3 + b] + Hb[a * 3 + 2] * inv[2 * 3 + b];
 	}
 	__syncthreads();
-	// (3) S blocks -> dense upper triangle (+lambda on the diagonal); (4) reduced gradient
-	const int nS = h->n_S * P * P;
+	// (3) reduced blocks; (4) reduced gradient
+	const int nS = h->s_alias_hap ? 0 : h->n_S * P * P;
 	for (int it = threadIdx.x; it < nS + n; it += LM_THREADS) {
 		if (it < nS) {
 			const int blk = it / (P * P), e = it % (P * P), a = e / P, b = e % P;
-			const int row = v.S_row[blk], col = v.S_col[blk];
 			const int hb = v.S_HAp[blk];
 			double s = hb >= 0 ? v.HAp[(size_t)hb * P * P + e] : 0.0;
 			for (int t = v.S_term_ptr[blk]; t < v.S_term_ptr[blk + 1]; t++) {
@@ -777,8 +790,7 @@ __device__ void stage_schur_and_fill(const View &v, double lambda) {
 				const double *Hc = v.HApf + (size_t)cb * P * 3;
 				s -= Wr[a * 3 + 0] * Hc[b * 3 + 0] + Wr[a * 3 + 1] * Hc[b * 3 + 1] + Wr[a * 3 + 2] * Hc[b * 3 + 2];
 			}
-			if (row == col && a == b) s += lambda;
-			v.dense[(size_t)(P * row + a) * ld + P * col + b] = s;
+			v.Sblk[it] = s;
 		} else {
 			const int i = it - nS;  // scalar of the pose part
 			const int ucol = i / P, a = i % P;
@@ -791,7 +803,31 @@ __device__ void stage_schur_and_fill(const View &v, double lambda) {
 				g -= Wr[a * 3 + 0] * gf[0] + Wr[a * 3 + 1] * gf[1] + Wr[a * 3 + 2] * gf[2];
 			}
 			v.grad[i] = g;
-			v.dense[(size_t)i * ld + n] = g;  // augmented column: forward substitution comes for free
+		}
+	}
+}
+
+// Dense fill of solver_engine<true,true>::solve (impl/lev-marq_solvers.h:492-519) for the blocked solver and for
+// extra_results.hessian: denseH := 0, upper blocks of the reduced system, +lambda on the diagonal, and the reduced
+// gradient as an augmented column (forward substitution then comes for free).
+template <int P>
+__device__ __noinline__ void stage_dense_fill(const View &vs, double lambda) {
+	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
+	const DevProblem *h = v.h;
+	const int n = h->n_dense, ld = h->ld_dense;
+	for (size_t i = threadIdx.x; i < (size_t)n * ld; i += LM_THREADS) v.dense[i] = 0;
+	__syncthreads();
+	const int nS = h->n_S * P * P;
+	for (int it = threadIdx.x; it < nS + n; it += LM_THREADS) {
+		if (it < nS) {
+			const int blk = it / (P * P), e = it % (P * P), a = e / P, b = e % P;
+			const int row = v.S_row[blk], col = v.S_col[blk];
+			double s = v.S[it];
+			if (row == col && a == b) s += lambda;
+			v.dense[(size_t)(P * row + a) * ld + P * col + b] = s;
+		} else {
+			const int i = it - nS;
+			v.dense[(size_t)i * ld + n] = v.grad[i];
 		}
 	}
 }
@@ -805,7 +841,8 @@ __device__ void stage_schur_and_fill(const View &v, double lambda) {
 //       element per block column instead of one per column).
 // 3 barriers per block column instead of 3 per column.  Returns false on a non-positive pivot (Eigen: "if (x<=0) return k").
 #define CH_NB 8
-__device__ bool stage_cholesky(const View &v, Shared &sh, double *panel, int panel_cap) {
+__device__ __noinline__ bool stage_cholesky(const View &vs, Shared &sh, double *panel, int panel_cap) {
+	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	const int n = v.h->n_dense, ld = v.h->ld_dense;
 	double *A = v.dense;
 	const int ncols = n + 1;  // including the augmented column
@@ -912,157 +949,185 @@ __device__ bool stage_cholesky(const View &v, Shared &sh, double *panel, int pan
 	return true;
 }
 
-// K4 (small/medium systems): REGISTER-RESIDENT dense Cholesky + forward + back substitution.
-// The upper triangle (plus the augmented right-hand-side column) is cut into 4x4 tiles; every thread owns up to TPT
-// tiles and keeps them in registers for the whole factorisation, so the only shared-memory traffic per tile row is the
-// 4-row panel (read 8 values per 64 FMAs) and there are 2 barriers per FOUR pivots:
-//   D: the owner of diagonal tile (tk,tk) factors it alone (4 pivots, rsqrt) and publishes U11 + 1/diag,
-//   P: owners of (tk,tj>tk) solve U11^T X = T in registers and publish X as the panel,
-//   U: owners of (ti>tk,tj) apply the rank-4 update from the panel.
-// Back substitution runs bottom-up on the same register tiles (y and x live in shared memory).
-// Returns false on a non-positive pivot (Eigen::LLT: "if (x<=0) return k", impl/lev-marq_solvers.h:527-534).
-template <int TPT>
-__device__ bool stage_cholesky_solve_reg(const View &v, Shared &sh, double *sm) {
-	const int n = v.h->n_dense, ld = v.h->ld_dense;
-	const double *A = v.dense;
-	const int TR = (n + 3) >> 2, TC = TR + 1;  // tile column TR holds the augmented column (local column 0)
-	double *sU = sm;                 // 16: U11 of the current tile row
-	double *sRinv = sm + 16;         // 4
-	double *sPanel = sm + 32;        // 4 x (4*TC)
-	double *sY = sPanel + 16 * TC;   // 4*TR
-	double *sX = sY + 4 * TR;        // 4*TR
-	const int PW = 4 * TC;
-	double t[TPT][4][4];
-	int ti_[TPT], tj_[TPT];
-#pragma unroll
-	for (int s = 0; s < TPT; s++) {
-		int q = threadIdx.x + s * LM_THREADS, ti = 0;
-		while (ti < TR && q >= TC - ti) { q -= TC - ti; ti++; }
-		if (ti >= TR) { ti_[s] = -1; tj_[s] = -1; continue; }
-		ti_[s] = ti; tj_[s] = ti + q;
-		const int tj = ti + q;
-#pragma unroll
-		for (int a = 0; a < 4; a++)
-#pragma unroll
-			for (int b = 0; b < 4; b++) {
-				const int i = 4 * ti + a;
-				double val = 0.0;
-				if (tj == TR) { if (b == 0 && i < n) val = A[(size_t)i * ld + n]; }
-				else {
-					const int j = 4 * tj + b;
-					if (i < n && j < n) { if (j >= i) val = A[(size_t)i * ld + j]; }
-					else if (i == j) val = 1.0;  // identity padding of the last partial tile
-				}
-				t[s][a][b] = val;
-			}
+// K4 (small/medium systems): ON-CHIP BLOCK-SPARSE  L D L^T  solve of the reduced system, one scalar element per lane.
+// Solves the system that Eigen::LLT<Upper> + solve see after the dense fill (impl/lev-marq_solvers.h:492-549), fed
+// DIRECTLY from the reduced blocks: the dense matrix is never materialised, and structural zeros are never touched
+// (a relative graph-SLAM area is block-banded: ~5 % of the dense flops and no fill-in in the reference's own ordering).
+// The factorisation is the block form of the same elimination (3x3 pivot blocks inverted explicitly by cofactors, no
+// square roots): a pivot block is rejected exactly when one of its leading minors is <= 0, i.e. when LLT would meet a
+// non-positive scalar pivot.
+//
+// Why this shape (measured on B200, tools/microbench + in-kernel phase clocks): the elimination is a chain of dependent
+// 3x3 products, one link per block row, and a lone warp retires ~1 instruction per 5-6 cycles -- so the cost of a block
+// row is the number of instructions (and barriers) on its critical path, not its flops.  One ELEMENT per lane makes every
+// 3x3 product 3 DFMA per lane, and the row is organised so that ONE barrier separates consecutive rows:
+//   U  every pair (i,j) of tiles of row k:  T(i,j) -= T(k,i)^t inv(D_k) T(k,j)   -- 9 lanes per update, host-made list;
+//      the lanes form inv(D_k) T(k,j) themselves (9 extra DFMA) instead of waiting for a separate "W" step,
+//   P  meanwhile 9 lanes of the last warp apply row k to the NEXT pivot block and invert it straight away,
+//   W  meanwhile the tiles of row k-1 (no longer read by anybody) are overwritten by W = inv(D_{k-1}) T for the backward
+//      pass (inverse pivot blocks are triple-buffered so that U, P and W never meet).
+// The filled upper pattern, the tile numbering (row-major, diagonal first, right-hand side as tile column NTR) and the
+// per-row update lists come from the packer's symbolic factorisation (capi.cpp: symbolic_tiles).  Tiles live in shared
+// memory, column-major 3x3 padded to 3x4 so that a column is one 16-byte + one 8-byte load.
+// The backward pass  x_j = z_j - sum W(j,.) x  runs column by column (one barrier each), again one element per lane.
+// Returns false when a pivot block is not positive definite (Eigen::LLT "if (x<=0) return k", lev-marq_solvers.h:527-534).
+template <int P>
+__device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, double *scr, double lambda) {
+	static_assert(P % 3 == 0, "tiles are 3x3");
+#ifdef SRBA_SOLVER_TIMERS
+	const long long c_entry = clock64();
+#endif
+	const View v = vs;
+	const int n = v.h->n_dense, ntiles = v.h->ldl_n_tiles;
+	const int NTR = n / 3;
+	double *tile = scr;                        // ntiles x 12
+	double *sInv = tile + 12 * (size_t)ntiles; // 3 x 12 : inverse pivot blocks of rows k-1, k, k+1 (slot = row % 3)
+	double *sAcc = sInv + 36;                  // 3*NTR : backward-pass accumulators
+	const int4 *rowinfo = reinterpret_cast<const int4 *>(v.ldl_row);  // {first tile, end tile | has_superdiag << 30, first update, end update}
+	const int32_t *tij = v.ldl_tile_ij, *upd = v.ldl_upd, *cptr = v.ldl_col_ptr, *ctile = v.ldl_col_tile, *src = v.ldl_src;
+	const int tid = threadIdx.x, NT = LM_THREADS;
+	const int lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+	const int iwarp = nwarps - 1;              // the warp that carries the pivot chain (its lanes 0..8)
+	// coordinates of this lane inside a 9-lane tile group: element (wa,wb) at column-major padded offset eo
+	const int wg = lane / 9, we = lane - wg * 9, wb = we / 3, wa = we - wb * 3, eo = wb * 4 + wa;
+	// cyclic cofactor of a symmetric 3x3: C(a,b) = d(a1,b1) d(a2,b2) - d(a1,b2) d(a2,b1)
+	const int a1 = wa == 2 ? 0 : wa + 1, a2 = wa == 0 ? 2 : wa - 1, b1 = wb == 2 ? 0 : wb + 1, b2 = wb == 0 ? 2 : wb - 1;
+	const int o11 = b1 * 4 + a1, o22 = b2 * 4 + a2, o12 = b2 * 4 + a1, o21 = b1 * 4 + a2;
+	// gather: tile element <- reduced block element (+lambda on the diagonal); tile column NTR = reduced gradient
+#pragma unroll 1
+	for (int q = tid; q < ntiles * 9; q += NT) {
+		const int tl = q / 9, e = q - tl * 9, b = e / 3, a = e - b * 3;
+		const int so = src[tl];  // >= 0: offset of the tile's (0,0) in S; -1: fill-in; <= -2: right-hand side of row -so-2
+		double val = 0.0;
+		if (so >= 0) {
+			val = v.S[so + a * P + b];
+			if (a == b && (tij[tl] >> 16) == (tij[tl] & 0xffff)) val += lambda;
+		} else if (so <= -2 && b == 0) val = v.grad[3 * (-so - 2) + a];
+		tile[tl * 12 + b * 4 + a] = val;
 	}
-	if (threadIdx.x == 0) sh.chol_ok = 1;
+#pragma unroll 1
+	for (int i = tid; i < n; i += NT) sAcc[i] = 0.0;
+	if (tid == 0) sh.chol_ok = 1;
+	int4 ri = rowinfo[0];
 	__syncthreads();
-	for (int tk = 0; tk < TR; tk++) {
-		// D: diagonal tile
-#pragma unroll
-		for (int s = 0; s < TPT; s++)
-			if (ti_[s] == tk && tj_[s] == tk) {
-				double rinv[4];
-				bool ok = true;
-#pragma unroll
-				for (int r = 0; r < 4; r++) {
-					const double d = t[s][r][r];
-					if (d <= 0) ok = false;
-					rinv[r] = rsqrt(d);
-					t[s][r][r] = d * rinv[r];
-#pragma unroll
-					for (int c = r + 1; c < 4; c++) t[s][r][c] *= rinv[r];
-#pragma unroll
-					for (int i = r + 1; i < 4; i++)
-#pragma unroll
-						for (int c = i; c < 4; c++) t[s][i][c] -= t[s][r][i] * t[s][r][c];
-				}
-				if (!ok) sh.chol_ok = 0;
-#pragma unroll
-				for (int r = 0; r < 4; r++) {
-					sRinv[r] = rinv[r];
-#pragma unroll
-					for (int c = 0; c < 4; c++) sU[r * 4 + c] = (c >= r) ? t[s][r][c] : 0.0;
-				}
-				t[s][1][0] = rinv[0]; t[s][2][0] = rinv[1]; t[s][2][1] = rinv[2]; t[s][3][0] = rinv[3];  // kept for the back substitution
-			}
-		__syncthreads();
+	// pivot-block inversion by 9 lanes: own cofactor, determinant, one reciprocal
+	auto invert_pivot = [&](const double *D, double *inv) {
+		const double d00 = D[0], d01 = D[4], d02 = D[8], d11 = D[5], d12 = D[9], d22 = D[10];
+		const double c = D[o11] * D[o22] - D[o12] * D[o21];
+		const double det = d00 * (d11 * d22 - d12 * d12) + d01 * (d02 * d12 - d01 * d22) + d02 * (d01 * d12 - d02 * d11);
+		inv[eo] = c / det;
+		// leading minors == LLT's scalar pivots up to positive factors
+		if (d00 <= 0 || d00 * d11 - d01 * d01 <= 0 || det <= 0) sh.chol_ok = 0;
+	};
+	if (warp == iwarp && lane < 9) invert_pivot(tile + ri.x * 12, sInv);
+	__syncthreads();
+#ifdef SRBA_SOLVER_TIMERS
+	const long long c_loop = clock64();
+#endif
+	int prev_r0 = 0, prev_r1 = 0;  // tiles of row k-1 still to be turned into W
+#pragma unroll 1
+	for (int k = 0; k <= NTR; k++) {
 		if (!sh.chol_ok) return false;
-		// P: panel solve  U11^T X = T
-#pragma unroll
-		for (int s = 0; s < TPT; s++)
-			if (ti_[s] == tk && tj_[s] > tk) {
-				const double u01 = sU[1], u02 = sU[2], u03 = sU[3], u12 = sU[6], u13 = sU[7], u23 = sU[11];
-				const double r0 = sRinv[0], r1 = sRinv[1], r2 = sRinv[2], r3 = sRinv[3];
-#pragma unroll
-				for (int b = 0; b < 4; b++) {
-					const double x0 = t[s][0][b] * r0;
-					const double x1 = (t[s][1][b] - u01 * x0) * r1;
-					const double x2 = (t[s][2][b] - u02 * x0 - u12 * x1) * r2;
-					const double x3 = (t[s][3][b] - u03 * x0 - u13 * x1 - u23 * x2) * r3;
-					t[s][0][b] = x0; t[s][1][b] = x1; t[s][2][b] = x2; t[s][3][b] = x3;
-					const int c = 4 * tj_[s] + b;
-					sPanel[c] = x0; sPanel[PW + c] = x1; sPanel[2 * PW + c] = x2; sPanel[3 * PW + c] = x3;
-				}
-			}
-		__syncthreads();
-		// U: rank-4 update of the tiles below
-#pragma unroll
-		for (int s = 0; s < TPT; s++)
-			if (ti_[s] > tk) {
-#pragma unroll
-				for (int r = 0; r < 4; r++) {
-					double pi[4], pj[4];
-#pragma unroll
-					for (int a = 0; a < 4; a++) { pi[a] = sPanel[r * PW + 4 * ti_[s] + a]; pj[a] = sPanel[r * PW + 4 * tj_[s] + a]; }
-#pragma unroll
-					for (int a = 0; a < 4; a++)
-#pragma unroll
-						for (int b = 0; b < 4; b++) t[s][a][b] -= pi[a] * pj[b];
-				}
-			}
-		// (no barrier: the next D touches only registers/sU, and sPanel is rewritten after the next barrier)
-	}
-	// forward-substituted right-hand side lives in column 0 of the tiles of column TR
-#pragma unroll
-	for (int s = 0; s < TPT; s++)
-		if (tj_[s] == TR) {
-#pragma unroll
-			for (int a = 0; a < 4; a++) sY[4 * ti_[s] + a] = t[s][a][0];
+		const int r0 = ri.x, r1 = ri.y & 0x3fffffff, has_sd = ri.y >> 30, u0 = ri.z, nitems = (ri.w - ri.z) * 9;
+		const int4 rn = rowinfo[k < NTR ? k + 1 : NTR];  // row NTR is a sentinel without tiles or updates
+		const double *Ik = sInv + (k % 3) * 12;
+		// ---- U: T(i,j) -= T(k,i)^t inv(D_k) T(k,j) for the pairs of row-k tiles (x: dst | tile(k,i) << 16, y: tile(k,j))
+#pragma unroll 1
+		for (int q = tid; q < nitems; q += NT) {
+			const int ui = q / 9, e = q - ui * 9, b = e / 3, a = e - b * 3;
+			const int2 u = *reinterpret_cast<const int2 *>(upd + 2 * (u0 + ui));
+			const double *Ti = tile + (u.x >> 16) * 12 + a * 4;
+			const double *Tj = tile + u.y * 12 + b * 4;
+			const double2 p01 = *reinterpret_cast<const double2 *>(Ti), t01 = *reinterpret_cast<const double2 *>(Tj);
+			const double p2 = Ti[2], t2 = Tj[2];
+			const double2 i0 = *reinterpret_cast<const double2 *>(Ik), i1 = *reinterpret_cast<const double2 *>(Ik + 4);
+			const double i02 = Ik[2], i12 = Ik[6], i22 = Ik[10];
+			const double w0 = i0.x * t01.x + i0.y * t01.y + i02 * t2;
+			const double w1 = i0.y * t01.x + i1.y * t01.y + i12 * t2;
+			const double w2 = i02 * t01.x + i12 * t01.y + i22 * t2;
+			double *dst = tile + (u.x & 0xffff) * 12 + b * 4 + a;
+			*dst = *dst - p01.x * w0 - p01.y * w1 - p2 * w2;
 		}
-	__syncthreads();
-	// back substitution, bottom-up
-	for (int tk = TR - 1; tk >= 0; tk--) {
-#pragma unroll
-		for (int s = 0; s < TPT; s++)
-			if (ti_[s] == tk && tj_[s] == tk) {
-				const double x3 = sY[4 * tk + 3] * t[s][3][0];
-				const double x2 = (sY[4 * tk + 2] - t[s][2][3] * x3) * t[s][2][1];
-				const double x1 = (sY[4 * tk + 1] - t[s][1][2] * x2 - t[s][1][3] * x3) * t[s][2][0];
-				const double x0 = (sY[4 * tk + 0] - t[s][0][1] * x1 - t[s][0][2] * x2 - t[s][0][3] * x3) * t[s][1][0];
-				sX[4 * tk + 0] = x0; sX[4 * tk + 1] = x1; sX[4 * tk + 2] = x2; sX[4 * tk + 3] = x3;
+		// ---- P: the next pivot block gets its row-k update from the super-diagonal tile and is inverted right away
+		if (warp == iwarp) {
+			if (k + 1 < NTR) {
+				double *Dn = tile + rn.x * 12;
+				if (lane < 9 && has_sd) {
+					const double *Ts = tile + (r0 + 1) * 12;
+					const double2 p01 = *reinterpret_cast<const double2 *>(Ts + wa * 4), t01 = *reinterpret_cast<const double2 *>(Ts + wb * 4);
+					const double p2 = Ts[wa * 4 + 2], t2 = Ts[wb * 4 + 2];
+					const double2 i0 = *reinterpret_cast<const double2 *>(Ik), i1 = *reinterpret_cast<const double2 *>(Ik + 4);
+					const double i02 = Ik[2], i12 = Ik[6], i22 = Ik[10];
+					const double w0 = i0.x * t01.x + i0.y * t01.y + i02 * t2;
+					const double w1 = i0.y * t01.x + i1.y * t01.y + i12 * t2;
+					const double w2 = i02 * t01.x + i12 * t01.y + i22 * t2;
+					Dn[eo] = Dn[eo] - p01.x * w0 - p01.y * w1 - p2 * w2;
+				}
+				__syncwarp();
+				if (lane < 9) invert_pivot(Dn, sInv + ((k + 1) % 3) * 12);
 			}
-		__syncthreads();
-#pragma unroll
-		for (int s = 0; s < TPT; s++)
-			if (tj_[s] == tk && ti_[s] >= 0 && ti_[s] < tk) {
-				const double x0 = sX[4 * tk], x1 = sX[4 * tk + 1], x2 = sX[4 * tk + 2], x3 = sX[4 * tk + 3];
-#pragma unroll
-				for (int a = 0; a < 4; a++) sY[4 * ti_[s] + a] -= t[s][a][0] * x0 + t[s][a][1] * x1 + t[s][a][2] * x2 + t[s][a][3] * x3;
+		} else if (k > 0) {
+			// ---- W: the tiles of row k-1 become W = inv(D_{k-1}) T in place (3 tiles per warp and round, top warps first)
+			const double *Ip = sInv + ((k - 1) % 3) * 12;
+#pragma unroll 1
+			for (int base = prev_r0 + 1 + 3 * (iwarp - 1 - warp); base < prev_r1; base += 3 * (nwarps - 1)) {
+				const int tl = base + wg;
+				const bool act = lane < 27 && tl < prev_r1;
+				double w = 0.0;
+				if (act) {
+					const double *Tc = tile + tl * 12 + wb * 4;
+					const double2 t01 = *reinterpret_cast<const double2 *>(Tc);
+					const double2 i01 = *reinterpret_cast<const double2 *>(Ip + wa * 4);
+					w = i01.x * t01.x + i01.y * t01.y + Ip[wa * 4 + 2] * Tc[2];
+				}
+				__syncwarp();
+				if (act) tile[tl * 12 + eo] = w;
 			}
+		}
+		prev_r0 = r0; prev_r1 = r1;
+		ri = rn;
 		__syncthreads();
 	}
-	for (int i = threadIdx.x; i < n; i += LM_THREADS) v.delta[i] = sX[i];
+	if (!sh.chol_ok) return false;
+#ifdef SRBA_SOLVER_TIMERS
+	const long long c_back = clock64();
+#endif
+	// backward pass: column j folds x_j = z_j - acc_j into the rows above it; z_j = column 0 of the last tile of row j
+#pragma unroll 1
+	for (int j = NTR - 1; j >= 1; j--) {
+		const int c0 = cptr[j], nitems = (cptr[j + 1] - c0) * 3;
+		if (nitems == 0) continue;
+#pragma unroll 1
+		for (int q = tid; q < nitems; q += NT) {
+			const int ci = q / 3, a = q - ci * 3;
+			const int tl = ctile[c0 + ci];
+			const int i = tij[tl] >> 16;
+			const double *z = tile + (rowinfo[j + 1].x - 1) * 12;
+			const double x0 = z[0] - sAcc[3 * j], x1 = z[1] - sAcc[3 * j + 1], x2 = z[2] - sAcc[3 * j + 2];
+			const double *Wt = tile + tl * 12 + a;
+			sAcc[3 * i + a] += Wt[0] * x0 + Wt[4] * x1 + Wt[8] * x2;
+		}
+		__syncthreads();
+	}
+#pragma unroll 1
+	for (int i = tid; i < n; i += NT) {
+		const int r = i / 3;
+		v.delta[i] = tile[(rowinfo[r + 1].x - 1) * 12 + (i - 3 * r)] - sAcc[i];
+	}
 	__syncthreads();
+#ifdef SRBA_SOLVER_TIMERS
+	if (tid == 0) {
+		const long long c_end = clock64();
+		sh.dbg[0] += c_loop - c_entry; sh.dbg[1] += c_back - c_loop; sh.dbg[2] += c_end - c_back;
+	}
+#endif
 	return true;
 }
-__device__ __forceinline__ int chol_reg_tiles(int n) { const int TR = (n + 3) >> 2; return TR * (TR + 1) / 2 + TR; }
-__device__ __forceinline__ int chol_reg_smem_doubles(int n) { const int TR = (n + 3) >> 2; return 32 + 16 * (TR + 1) + 8 * TR; }
 
 // Back substitution U x = y (y = augmented column), blocked by 8 from the bottom: warp 0 solves the diagonal block,
 // then every thread updates one earlier row with the 8 new unknowns.
-__device__ void stage_backsub(const View &v, Shared &sh) {
+__device__ __noinline__ void stage_backsub(const View &vs, Shared &sh) {
+	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	const int n = v.h->n_dense, ld = v.h->ld_dense;
 	const double *A = v.dense;
 	double *x = v.delta;
@@ -1103,7 +1168,8 @@ __device__ void stage_backsub(const View &v, Shared &sh) {
 
 // K5a: SchurComplement::numeric_solve_for_features (impl/schur.h:271-311): mutates the gradient tail in place.
 template <int P>
-__device__ void stage_features(const View &v) {
+__device__ __noinline__ void stage_features(const View &vs) {
+	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	const DevProblem *h = v.h;
 	const int n = h->n_dense;
 	for (int k = threadIdx.x; k < h->n_unk_lms; k += LM_THREADS) {
@@ -1130,7 +1196,8 @@ __device__ void stage_features(const View &v) {
 
 // K5b: back-up + manifold update (impl/optimize_edges.h:491-557)
 template <int P>
-__device__ void stage_update(const View &v) {
+__device__ __noinline__ void stage_update(const View &vs) {
+	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	constexpr int S = PoseOps<P>::S;
 	const DevProblem *h = v.h;
 	for (int i = threadIdx.x; i < h->n_unk_edges; i += LM_THREADS) {
@@ -1153,7 +1220,8 @@ __device__ void stage_update(const View &v) {
 }
 // rejected step (impl/optimize_edges.h:660-680): only the LISTED directed entries of the numeric ST are restored.
 template <int P>
-__device__ void stage_restore(const View &v) {
+__device__ __noinline__ void stage_restore(const View &vs) {
+	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	constexpr int S = PoseOps<P>::S;
 	const DevProblem *h = v.h;
 	for (int i = threadIdx.x; i < h->n_unk_edges * S; i += LM_THREADS) v.edge_cur[(size_t)v.unk_edge[i / S] * S + (i % S)] = v.edge_bak[i];
@@ -1172,21 +1240,43 @@ __device__ void stage_restore(const View &v) {
 		}                                                    \
 	} while (0)
 
-template <int P, int OBSK, int MAXTPT>
-__device__ void lm_program(const DevProblem *h, const char *img, char *ws, char *res, Shared &sh, double *panel, int panel_cap) {
+template <int P, int OBSK, int TPT>
+__device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char *res, Shared &sh, char *dyn) {
 	constexpr int S = PoseOps<P>::S;
-	View v;
-	make_view(v, h, img, ws, res);
 	if (threadIdx.x == 0) {
 		for (int i = 0; i < ST_COUNT; i++) sh.stage_cycles[i] = 0;
+		for (int i = 0; i < 8; i++) sh.dbg[i] = 0;
 		sh.t_last = clock64();
+	}
+	// ---- problem header on chip, then the hot read-only index arrays the packer placed in the arena
+	{
+		const uint32_t *src = reinterpret_cast<const uint32_t *>(gh);
+		uint32_t *dst = reinterpret_cast<uint32_t *>(&sh.hdr);
+		for (int i = threadIdx.x; i < (int)(sizeof(DevProblem) / 4); i += LM_THREADS) dst[i] = src[i];
+	}
+	__syncthreads();
+	const DevProblem *h = &sh.hdr;
+	if (threadIdx.x == 0) make_view(sh.view, h, img, ws, res, dyn);
+	__syncthreads();
+	const View &v = sh.view;
+	double *scratch = reinterpret_cast<double *>(dyn + h->sm_scratch);
+	for (int a = 0; a < SRBA_I_COUNT; a++) {
+		if (h->img_sm[a] == SRBA_NOT_IN_SMEM) continue;
+		const uint4 *src = reinterpret_cast<const uint4 *>(img + h->img_off[a]);
+		uint4 *dst = reinterpret_cast<uint4 *>(dyn + h->img_sm[a]);
+		const int n16 = (int)((h->img_len[a] + 15) >> 4);
+		for (int i = threadIdx.x; i < n16; i += LM_THREADS) dst[i] = src[i];
 	}
 	const int n = h->n_dense, nsc = h->n_scalars;
 	const int nObsRows = h->n_total_obs_rows;
 
 	// ---- load inputs into the workspace (edges and landmarks are the only mutable inputs)
-	for (size_t i = threadIdx.x; i < (size_t)h->n_edges * S; i += LM_THREADS) v.edge_cur[i] = v.edge_pose[i];
-	for (size_t i = threadIdx.x; i < (size_t)h->n_lms * 3; i += LM_THREADS) v.lm_cur[i] = v.lm_pos[i];
+	{
+		const double *ge = reinterpret_cast<const double *>(img + h->img_off[SRBA_I_edge_pose]);
+		const double *gl = reinterpret_cast<const double *>(img + h->img_off[SRBA_I_lm_pos]);
+		for (size_t i = threadIdx.x; i < (size_t)h->n_edges * S; i += LM_THREADS) v.edge_cur[i] = ge[i];
+		for (size_t i = threadIdx.x; i < (size_t)h->n_lms * 3; i += LM_THREADS) v.lm_cur[i] = gl[i];
+	}
 	for (int i = threadIdx.x; i < 2 * h->n_pairs; i += LM_THREADS) v.slot_listed[i] = 0;
 	if (threadIdx.x == 0) {
 		if (h->model.sensor_pose_kind == SRBA_SENSORPOSE_SE3) PoseOps<6>::inverse(sh.sensor_inv, h->model.sensor_pose);
@@ -1245,23 +1335,22 @@ __device__ void lm_program(const DevProblem *h, const char *img, char *ws, char 
 			const double lambda = sh.lambda;
 			const int trial = sh.trials;
 			__syncthreads();
-			stage_schur_and_fill<P>(v, lambda);
+			stage_schur<P>(v, lambda);
 			__syncthreads();
-			if (h->want_dense) {  // extra_results.hessian = denseH of the last solve (lev-marq_solvers.h:582-586)
-				for (size_t i = threadIdx.x; i < (size_t)n * n; i += LM_THREADS) v.r_dense[i] = v.dense[(i / n) * h->ld_dense + (i % n)];
+			const bool reg = (h->chol_mode == SRBA_CHOL_REG);
+			if (!reg || h->want_dense) {
+				stage_dense_fill<P>(v, lambda);
 				__syncthreads();
+				if (h->want_dense) {  // extra_results.hessian = denseH of the last solve (lev-marq_solvers.h:582-586)
+					for (size_t i = threadIdx.x; i < (size_t)n * n; i += LM_THREADS) v.r_dense[i] = v.dense[(i / n) * h->ld_dense + (i % n)];
+					__syncthreads();
+				}
 			}
 			STAGE(ST_SCHUR);
-			// dense solve: register-resident tiles when the system fits the CTA's register file, blocked global/shared otherwise
-			bool ok, solved = false;
-			{
-				const int tiles = chol_reg_tiles(n);
-				const bool fits = chol_reg_smem_doubles(n) <= CH_NB * panel_cap;
-				if (fits && tiles <= LM_THREADS) { ok = stage_cholesky_solve_reg<1>(v, sh, panel); solved = true; }
-				else if (MAXTPT >= 2 && fits && tiles <= 2 * LM_THREADS) { ok = stage_cholesky_solve_reg<(MAXTPT >= 2 ? 2 : 1)>(v, sh, panel); solved = true; }
-				else if (MAXTPT >= 4 && fits && tiles <= 4 * LM_THREADS) { ok = stage_cholesky_solve_reg<(MAXTPT >= 4 ? 4 : 1)>(v, sh, panel); solved = true; }
-				else ok = stage_cholesky(v, sh, panel, panel_cap);
-			}
+			// dense solve: register-resident pipelined tiles when the system fits the CTA's register file, blocked global/shared otherwise
+			bool ok;
+			if (reg) ok = stage_ldl_solve_smem<P>(v, sh, scratch, lambda);
+			else ok = stage_cholesky(v, sh, scratch, h->panel_cap);
 			STAGE(ST_CHOL);
 			if (!ok) {  // not positive definite (:476-485)
 				if (threadIdx.x == 0) {
@@ -1280,7 +1369,7 @@ __device__ void lm_program(const DevProblem *h, const char *img, char *ws, char 
 				STAGE(ST_CTRL);
 				continue;
 			}
-			if (!solved) stage_backsub(v, sh);
+			if (!reg) stage_backsub(v, sh);
 			STAGE(ST_BACKSUB);
 			if (h->n_unk_lms > 0) {
 				stage_features<P>(v);
@@ -1383,43 +1472,71 @@ __device__ void lm_program(const DevProblem *h, const char *img, char *ws, char 
 		const unsigned long long t_ = clock64();
 		sh.stage_cycles[ST_OUT] += t_ - sh.t_last;
 		for (int i = 0; i < ST_COUNT; i++) sc[i] = sh.stage_cycles[i];
+		for (int i = 0; i < 8; i++) sc[16 + i] = sh.dbg[i];
 	}
 }
 
 // One kernel per model combination so that each gets its own register budget (the SE(2) graph-SLAM program needs
-// far fewer registers than the SE(3) camera models and can keep 2 CTAs per SM resident).
-template <int P, int OBSK, int MINB, int MAXTPT>
-__global__ void __launch_bounds__(LM_THREADS, MINB) srba_lm_batch_kernel(const char *img, const uint64_t *img_off, char *ws, const uint64_t *ws_off, char *res,
-                                                                          const uint64_t *res_off, const int32_t *order, int n_problems, int panel_cap) {
+// far fewer registers than the SE(3) camera models and keeps 2 CTAs per SM resident).
+template <int P, int OBSK, int NT, int MINB, int TPT>
+__global__ void __launch_bounds__(NT, MINB) srba_lm_batch_kernel(const char *img, const uint64_t *img_off, char *ws, const uint64_t *ws_off, char *res,
+                                                                          const uint64_t *res_off, const int32_t *order, int n_problems) {
 	__shared__ Shared sh;
-	extern __shared__ double panel[];
+	extern __shared__ __align__(16) char dyn_smem[];
 	for (int q = blockIdx.x; q < n_problems; q += gridDim.x) {
 		const int pi = order[q];
 		const char *pimg = img + img_off[pi];
 		const DevProblem *h = reinterpret_cast<const DevProblem *>(pimg);
-		lm_program<P, OBSK, MAXTPT>(h, pimg, ws + ws_off[pi], res + res_off[pi], sh, panel, panel_cap);
+		lm_program<P, OBSK, TPT>(h, pimg, ws + ws_off[pi], res + res_off[pi], sh, dyn_smem);
 		__syncthreads();
 	}
 }
 
 }  // namespace
 
+// Per-model kernel configuration: CTA size, register tiles per thread, dynamic shared memory per CTA.
+//   SE2+RelativePoses2D: 128 regs -> 2 CTAs/SM, 2 x (108 KB dynamic + ~3 KB static + 1 KB reserved) of the SM's 228 KB;  SE3 models: 255 regs -> 1 CTA/SM, 220 KB.
+#define SE2_NT 192
+#define SE3_NT 256
+#define SE2_TPT 2
+#define SE3_TPT 4
+extern "C" SrbaKernelCfg srba_kernel_cfg(int model) {
+	SrbaKernelCfg c;
+	c.threads = model == 0 ? SE2_NT : SE3_NT;
+	c.tpt = model == 0 ? SE2_TPT : SE3_TPT;
+	c.smem_bytes = model == 0 ? 108 * 1024 : 220 * 1024;
+	return c;
+}
+// Doubles of shared-memory scratch of the on-chip solver for `n_tiles` 3x3 tiles, or -1 when they exceed the budget
+// reserved for the solver (half of the CTA's dynamic shared memory; larger systems use the blocked solver).
+extern "C" int srba_chol_reg_scratch_doubles(int model, int n_dense, int n_tiles) {
+	const SrbaKernelCfg c = srba_kernel_cfg(model);
+	const int NTR = n_dense / 3;
+	const long need = 12L * n_tiles + 36 + 3L * NTR + 1;
+	if (n_tiles >= 65535 || need * 8 > c.smem_bytes / 2) return -1;
+	return (int)need;
+}
+
 // model: 0 = SE2+RelativePoses2D, 1 = SE3+Cartesian3D, 2 = SE3+Mono, 3 = SE3+Stereo.  `order` lists the problems of that model.
 extern "C" int srba_launch_lm_batch(int model, const char *img, const uint64_t *img_off, char *ws, const uint64_t *ws_off, char *res,
-                                    const uint64_t *res_off, const int32_t *order, int n_problems, int grid, int panel_cap, void *stream) {
+                                    const uint64_t *res_off, const int32_t *order, int n_problems, int grid, int smem_bytes, void *stream) {
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
-	const size_t smem = (size_t)CH_NB * panel_cap * sizeof(double);
-#define LAUNCH(P, OBSK, MINB, MAXTPT)                                                                                                     \
+	// dynamic shared memory = the largest arena any problem of this group was planned with (<= the model's budget);
+	// what the batch does not need stays available to L1
+	const size_t smem = (size_t)std::min(std::max(smem_bytes, 1024), srba_kernel_cfg(model).smem_bytes);
+#define LAUNCH(P, OBSK, NT, MINB, TPT)                                                                                                    \
 	do {                                                                                                                                  \
-		auto kern = srba_lm_batch_kernel<P, OBSK, MINB, MAXTPT>;                                                                                  \
-		if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                         \
-		kern<<<grid, LM_THREADS, smem, st>>>(img, img_off, ws, ws_off, res, res_off, order, n_problems, panel_cap);                       \
+		auto kern = srba_lm_batch_kernel<P, OBSK, NT, MINB, TPT>;                                                                         \
+		cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                               \
+		kern<<<grid, NT, smem, st>>>(img, img_off, ws, ws_off, res, res_off, order, n_problems);                                          \
 	} while (0)
 	switch (model) {
-		case 0: LAUNCH(3, SRBA_OBS_RELPOSES2D, 2, 2); break;
-		case 1: LAUNCH(6, SRBA_OBS_CARTESIAN3D, 1, 4); break;
-		case 2: LAUNCH(6, SRBA_OBS_MONO, 1, 4); break;
-		case 3: LAUNCH(6, SRBA_OBS_STEREO, 1, 4); break;
+		case 0: LAUNCH(3, SRBA_OBS_RELPOSES2D, SE2_NT, 2, SE2_TPT); break;
+#ifndef SRBA_ONLY_SE2  /* compile-time experiments on the graph-SLAM kernel only */
+		case 1: LAUNCH(6, SRBA_OBS_CARTESIAN3D, SE3_NT, 1, SE3_TPT); break;
+		case 2: LAUNCH(6, SRBA_OBS_MONO, SE3_NT, 1, SE3_TPT); break;
+		case 3: LAUNCH(6, SRBA_OBS_STEREO, SE3_NT, 1, SE3_TPT); break;
+#endif
 		default: return (int)cudaErrorInvalidValue;
 	}
 #undef LAUNCH

@@ -22,10 +22,10 @@ rows = []
 for i in range(b.n):
     sc = b.stage_cycles(i)
     st = b.stats(i)
-    rows.append((sum(sc.values()), flats[i].p.n_unk_edges, st["num_trials"], sc))
+    rows.append((sum(v for k, v in sc.items() if not k.startswith("chol.")), flats[i].p.n_unk_edges, st["num_trials"], sc))
     for k, v in sc.items():
         tot[k] = tot.get(k, 0) + v
-T = sum(tot.values())
+T = sum(v for k, v in tot.items() if not k.startswith("chol."))
 print("all problems: total %.1f Mcycles; share per stage:" % (T / 1e6))
 for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
     print("  %-10s %5.1f%%" % (k, 100.0 * v / T))
