@@ -4,8 +4,15 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdlib>
+#include <functional>
+#include <mutex>
+#include <thread>
+
+#include <pthread.h>
 #include <cstdio>
 #include <cstring>
 #include <numeric>
@@ -119,8 +126,6 @@ inline const void *src_of_ldl_row(const srba_problem_t &) { return nullptr; }
 inline const void *src_of_ldl_tile_ij(const srba_problem_t &) { return nullptr; }
 inline const void *src_of_ldl_src(const srba_problem_t &) { return nullptr; }
 inline const void *src_of_ldl_upd(const srba_problem_t &) { return nullptr; }
-inline const void *src_of_ldl_col_ptr(const srba_problem_t &) { return nullptr; }
-inline const void *src_of_ldl_col_tile(const srba_problem_t &) { return nullptr; }
 // pointer to the caller's array behind image slot `id` (NULL for the derived ones)
 const void *src_ptr(const srba_problem_t &p, int id) {
 	switch (id) {
@@ -142,10 +147,8 @@ struct TileSymbolic {
 	std::vector<int32_t> src;       // ntiles: offset of the tile's (0,0) in the reduced blocks, -1 fill-in, -2-row right-hand side
 	std::vector<int32_t> upd_ptr;   // NTR+1
 	std::vector<int32_t> upd;       // 2 per update: {dst tile | tile(k,i)<<16, tile(k,j)}; the update of the next pivot block is implicit
-	std::vector<int32_t> col_ptr;   // NTR+1
-	std::vector<int32_t> col_tile;  // off-diagonal tiles (i<j) of every column j < NTR
 	bool ok = false;                // false: too large for the on-chip solver (schedule not built)
-	void clear() { rs.clear(); row.clear(); src.clear(); tile_ij.clear(); upd_ptr.clear(); upd.clear(); col_ptr.clear(); col_tile.clear(); ok = false; }
+	void clear() { rs.clear(); row.clear(); src.clear(); tile_ij.clear(); upd_ptr.clear(); upd.clear(); ok = false; }
 };
 void symbolic_tiles(const srba_problem_t &p, int P, long max_tiles, TileSymbolic &sy) {
 	const int q = P / 3, ntr = q * p.n_unk_edges, ntc = ntr + 1;
@@ -204,15 +207,13 @@ void symbolic_tiles(const srba_problem_t &p, int P, long max_tiles, TileSymbolic
 		const auto it = std::lower_bound(sy.tile_ij.begin() + sy.rs[i], sy.tile_ij.begin() + sy.rs[i + 1], key);
 		return (int32_t)(it - sy.tile_ij.begin());
 	};
-	// update schedule + column lists
+	// update schedule
 	sy.upd_ptr.assign(ntr + 1, 0);
-	std::vector<int32_t> col_cnt(ntr + 1, 0);
 	for (int k = 0; k < ntr; k++) {
 		sy.upd_ptr[k] = (int32_t)(sy.upd.size() / 2);
 		for (int a = sy.rs[k] + 1; a < sy.rs[k + 1]; a++) {
 			const int i = sy.tile_ij[a] & 0xffff;
 			if (i >= ntr) break;  // the right-hand side is never a row
-			col_cnt[i]++;
 			for (int b = a; b < sy.rs[k + 1]; b++) {
 				const int j = sy.tile_ij[b] & 0xffff;
 				if (i == k + 1 && j == k + 1) continue;  // next pivot block: updated by the inverting lanes themselves
@@ -222,15 +223,6 @@ void symbolic_tiles(const srba_problem_t &p, int P, long max_tiles, TileSymbolic
 		}
 	}
 	sy.upd_ptr[ntr] = (int32_t)(sy.upd.size() / 2);
-	sy.col_ptr.assign(ntr + 1, 0);
-	for (int j = 0; j < ntr; j++) sy.col_ptr[j + 1] = sy.col_ptr[j] + col_cnt[j];
-	sy.col_tile.assign(sy.col_ptr[ntr], 0);
-	std::vector<int32_t> fillp(sy.col_ptr.begin(), sy.col_ptr.end() - 1);
-	for (int k = 0; k < ntr; k++)
-		for (int a = sy.rs[k] + 1; a < sy.rs[k + 1]; a++) {
-			const int i = sy.tile_ij[a] & 0xffff;
-			if (i < ntr) sy.col_tile[fillp[i]++] = a;
-		}
 	// per-row records and tile sources
 	sy.row.assign(4 * (size_t)(ntr + 1), 0);
 	for (int k = 0; k <= ntr; k++) {
@@ -308,7 +300,6 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 		const bool reg = h.chol_mode == SRBA_CHOL_REG;
 		c[SRBA_I_ldl_row] = reg ? sy.row.size() : 0; c[SRBA_I_ldl_tile_ij] = reg ? sy.tile_ij.size() : 0;
 		c[SRBA_I_ldl_src] = reg ? sy.src.size() : 0; c[SRBA_I_ldl_upd] = reg ? sy.upd.size() : 0;
-		c[SRBA_I_ldl_col_ptr] = reg ? sy.col_ptr.size() : 0; c[SRBA_I_ldl_col_tile] = reg ? sy.col_tile.size() : 0;
 	}
 	Layout L;
 	L.add(sizeof(DevProblem));
@@ -336,8 +327,6 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 			put<int32_t>(base, h.img_off[SRBA_I_ldl_tile_ij], sy.tile_ij.data(), sy.tile_ij.size());
 			put<int32_t>(base, h.img_off[SRBA_I_ldl_src], sy.src.data(), sy.src.size());
 			put<int32_t>(base, h.img_off[SRBA_I_ldl_upd], sy.upd.data(), sy.upd.size());
-			put<int32_t>(base, h.img_off[SRBA_I_ldl_col_ptr], sy.col_ptr.data(), sy.col_ptr.size());
-			put<int32_t>(base, h.img_off[SRBA_I_ldl_col_tile], sy.col_tile.data(), sy.col_tile.size());
 		}
 	}
 
@@ -362,7 +351,7 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 		w[SRBA_W_grad] = (uint64_t)h.n_scalars * 8; w[SRBA_W_delta] = w[SRBA_W_grad];
 		w[SRBA_W_dense] = (h.chol_mode == SRBA_CHOL_BLOCKED || want_dense) ? (uint64_t)h.n_dense * h.ld_dense * 8 : 0;
 		w[SRBA_W_valid] = p.n_obs; w[SRBA_W_blk_ok] = p.n_blkA + p.n_blkF; w[SRBA_W_lm_inv] = p.n_unk_lms;
-		w[SRBA_W_slot_listed] = 2 * p.n_pairs; w[SRBA_W_pair_refresh] = p.n_pairs;
+		w[SRBA_W_slot_listed] = 2 * p.n_pairs; w[SRBA_W_pair_refresh] = p.n_pairs; w[SRBA_W_listed_idx] = (uint64_t)2 * p.n_pairs * 4;
 	}
 	Layout W;
 	for (int a = 0; a < SRBA_W_COUNT; a++) { h.ws_off[a] = W.add(ws_bytes[a]); h.ws_sm[a] = SRBA_NOT_IN_SMEM; }
@@ -376,9 +365,9 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 		struct Cand { int is_img, id; };
 		static const Cand order[] = {
 			{0, SRBA_W_edge_cur}, {0, SRBA_W_edge_bak}, {0, SRBA_W_grad}, {0, SRBA_W_delta}, {0, SRBA_W_lm_cur}, {0, SRBA_W_lm_bak},
-			{0, SRBA_W_valid}, {0, SRBA_W_lm_inv}, {0, SRBA_W_pair_refresh}, {0, SRBA_W_slot_listed},
+			{0, SRBA_W_valid}, {0, SRBA_W_lm_inv}, {0, SRBA_W_pair_refresh}, {0, SRBA_W_slot_listed}, {0, SRBA_W_listed_idx},
 			{0, SRBA_W_resid0}, {0, SRBA_W_resid1}, {0, SRBA_W_slot}, {0, SRBA_W_HAp}, {0, SRBA_W_Hf}, {0, SRBA_W_Hf_inv},
-			{1, SRBA_I_ldl_row}, {1, SRBA_I_ldl_col_ptr}, {1, SRBA_I_ldl_tile_ij}, {1, SRBA_I_ldl_upd}, {1, SRBA_I_ldl_col_tile}, {1, SRBA_I_ldl_src}, {1, SRBA_I_unk_edge}, {1, SRBA_I_unk_lm}, {1, SRBA_I_obs_slot}, {1, SRBA_I_obs_z}, {1, SRBA_I_obs_mult}, {1, SRBA_I_obs_lm},
+			{1, SRBA_I_ldl_row}, {1, SRBA_I_ldl_tile_ij}, {1, SRBA_I_ldl_upd}, {1, SRBA_I_ldl_src}, {1, SRBA_I_unk_edge}, {1, SRBA_I_unk_lm}, {1, SRBA_I_obs_slot}, {1, SRBA_I_obs_z}, {1, SRBA_I_obs_mult}, {1, SRBA_I_obs_lm},
 			{1, SRBA_I_pair_path_ptr}, {1, SRBA_I_path_edge}, {1, SRBA_I_path_dir},
 			{0, SRBA_W_Sblk}, {0, SRBA_W_HApf}, {0, SRBA_W_W}, {0, SRBA_W_JA}, {0, SRBA_W_JF}, {0, SRBA_W_slot_bak}, {0, SRBA_W_blk_ok},
 			{1, SRBA_I_colA_ptr}, {1, SRBA_I_blkA_obs}, {1, SRBA_I_blkA_col}, {1, SRBA_I_blkA_slotA}, {1, SRBA_I_blkA_slotD}, {1, SRBA_I_blkA_normal_dir},
@@ -410,6 +399,78 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 	h.res_stage_cycles = R.add(24 * 8);
 	h.res_bytes = R.total();
 	if (base) std::memcpy(base, &h, sizeof(h));
+}
+
+// Small persistent worker pool for the host side of a batch call (packing / unpacking 256 problems is as long as the
+// kernel itself when done on one core).  parallel_for(n, f) runs f(0..n-1) on the caller + workers (dynamic chunks).
+// SRBA_B200_THREADS overrides the thread count (default: hardware threads, at most 16).
+std::atomic<bool> g_forked{false};  // worker threads do not survive fork(): a forked child packs serially
+class WorkerPool {
+	std::vector<std::thread> th_;
+	std::mutex m_;
+	std::condition_variable cv_, done_;
+	const std::function<void(int)> *fn_ = nullptr;
+	int n_ = 0, active_ = 0;
+	std::atomic<int> next_{0};
+	uint64_t gen_ = 0;
+	bool stop_ = false;
+	void work() {
+		for (;;) {
+			const int i = next_.fetch_add(1, std::memory_order_relaxed);
+			if (i >= n_) break;
+			(*fn_)(i);
+		}
+	}
+	void loop() {
+		uint64_t seen = 0;
+		for (;;) {
+			{
+				std::unique_lock<std::mutex> lk(m_);
+				cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
+				if (stop_) return;
+				seen = gen_;
+			}
+			work();
+			{
+				std::lock_guard<std::mutex> lk(m_);
+				if (--active_ == 0) done_.notify_one();
+			}
+		}
+	}
+
+public:
+	WorkerPool() {
+		int k = (int)std::thread::hardware_concurrency();
+		if (const char *e = std::getenv("SRBA_B200_THREADS")) k = std::atoi(e);
+		k = std::max(1, std::min(k, 16));
+		for (int i = 1; i < k; i++) th_.emplace_back([this] { loop(); });
+		pthread_atfork(nullptr, nullptr, [] { g_forked.store(true); });
+	}
+	~WorkerPool() {
+		if (g_forked.load()) { for (auto &t : th_) t.detach(); return; }
+		{
+			std::lock_guard<std::mutex> lk(m_);
+			stop_ = true;
+		}
+		cv_.notify_all();
+		for (auto &t : th_) t.join();
+	}
+	int threads() const { return (int)th_.size() + 1; }
+	void parallel_for(int n, const std::function<void(int)> &f) {
+		if (n < 16 || th_.empty() || g_forked.load()) { for (int i = 0; i < n; i++) f(i); return; }
+		{
+			std::lock_guard<std::mutex> lk(m_);
+			fn_ = &f; n_ = n; next_.store(0); active_ = (int)th_.size(); gen_++;
+		}
+		cv_.notify_all();
+		work();
+		std::unique_lock<std::mutex> lk(m_);
+		done_.wait(lk, [&] { return active_ == 0; });
+	}
+};
+WorkerPool &workers() {
+	static WorkerPool p;
+	return p;
 }
 
 double problem_cost(const DevProblem &h) {
@@ -508,8 +569,8 @@ static srba_batch_t *batch_create_impl(int32_t n, const srba_problem_t *const *i
 	b->tab_res_off = I.add((uint64_t)n * 8);
 	b->tab_order = I.add((uint64_t)n * 4);
 	uint64_t ws = 0, rs = 0;
+	workers().parallel_for(n, [&](int i) { pack_problem(*in[i], b->hdr[i], nullptr, tcap, want_dense, b->sym[i]); });  // layout + symbolic
 	for (int i = 0; i < n; i++) {
-		pack_problem(*in[i], b->hdr[i], nullptr, tcap, want_dense, b->sym[i]);
 		b->img_off[i] = I.add(b->hdr[i].img_bytes);
 		b->ws_off[i] = ws; ws += b->hdr[i].ws_bytes;
 		b->res_off[i] = rs; rs += b->hdr[i].res_bytes;
@@ -548,10 +609,7 @@ static srba_batch_t *batch_create_impl(int32_t n, const srba_problem_t *const *i
 	std::memcpy(b->h_img + b->tab_ws_off, b->ws_off.data(), (size_t)n * 8);
 	std::memcpy(b->h_img + b->tab_res_off, b->res_off.data(), (size_t)n * 8);
 	std::memcpy(b->h_img + b->tab_order, b->order.data(), (size_t)n * 4);
-	for (int i = 0; i < n; i++) {
-		b->hdr[i].cost_rank = 0;
-		pack_problem(*in[i], b->hdr[i], b->h_img + b->img_off[i], tcap, want_dense, b->sym[i]);
-	}
+	workers().parallel_for(n, [&](int i) { pack_problem(*in[i], b->hdr[i], b->h_img + b->img_off[i], tcap, want_dense, b->sym[i]); });  // copy
 	return b;
 }
 
@@ -676,11 +734,14 @@ int srba_b200_optimize_batch(int32_t n, const srba_problem_t *const *in, srba_re
 	const auto t2 = now();
 	if (rc == SRBA_OK) rc = srba_b200_batch_download(b, st);
 	const auto t3 = now();
-	if (rc == SRBA_OK)
-		for (int i = 0; i < n; i++) {
+	if (rc == SRBA_OK) {
+		std::atomic<int> first_bad{SRBA_OK};
+		workers().parallel_for(n, [&](int i) {
 			const int r = srba_b200_batch_unpack(b, i, out[i]);
-			if (r != SRBA_OK && rc == SRBA_OK) rc = r;
-		}
+			if (r != SRBA_OK) { int expect = SRBA_OK; first_bad.compare_exchange_strong(expect, r); }
+		});
+		rc = first_bad.load();
+	}
 	srba_b200_batch_destroy(b);
 	if (timing) {
 		const auto t4 = now();

@@ -19,7 +19,7 @@
 // right-hand side as tile column NTR):  ldl_row[4*(NTR+1)] per row {first tile, end tile | has_superdiag<<30, first
 // update, end update} (+ sentinel);  ldl_tile_ij (ti<<16|tj);  ldl_src: where the tile comes from (offset into the reduced
 // blocks, -1 fill-in, -2-row right-hand side);  ldl_upd: per eliminated row the updates {dst tile | tile(k,i)<<16,
-// tile(k,j)} (the one that hits the next pivot block is implicit);  ldl_col_ptr / ldl_col_tile: off-diagonal tiles per column.
+// tile(k,j)} (the one that hits the next pivot block is implicit).
 #define SRBA_IMG_ARRAYS(X)                                                                                              \
 	X(double, edge_pose) X(int32_t, unk_edge) X(double, lm_pos) X(int32_t, unk_lm)                                       \
 	X(int32_t, pair_path_ptr) X(int32_t, path_edge) X(uint8_t, path_dir)                                                 \
@@ -31,7 +31,7 @@
 	X(int32_t, HApf_row) X(int32_t, HApf_col) X(int32_t, HApf_term_ptr) X(int32_t, HApf_term_a) X(int32_t, HApf_term_f)  \
 	X(int32_t, rowApf_ptr) X(int32_t, colApf_ptr) X(int32_t, colApf_idx)                                                 \
 	X(int32_t, S_row) X(int32_t, S_col) X(int32_t, S_HAp) X(int32_t, S_term_ptr) X(int32_t, S_term_rowblk) X(int32_t, S_term_colblk) \
-	X(int32_t, blkA_col) X(int32_t, blkF_col) X(int32_t, ldl_row) X(int32_t, ldl_tile_ij) X(int32_t, ldl_src) X(int32_t, ldl_upd) X(int32_t, ldl_col_ptr) X(int32_t, ldl_col_tile)
+	X(int32_t, blkA_col) X(int32_t, blkF_col) X(int32_t, ldl_row) X(int32_t, ldl_tile_ij) X(int32_t, ldl_src) X(int32_t, ldl_upd)
 
 // (type, name) of every workspace array.
 #define SRBA_WS_ARRAYS(X)                                                                                               \
@@ -39,6 +39,7 @@
 	X(double, JA) X(double, JF) X(double, resid0) X(double, resid1)                                                      \
 	X(double, HAp) X(double, HApf) X(double, Hf) X(double, Hf_inv) X(double, W) X(double, Sblk)                          \
 	X(double, grad) X(double, delta) X(double, dense)                                                                    \
+	X(int32_t, listed_idx)                                                                                               \
 	X(uint8_t, valid) X(uint8_t, blk_ok) X(uint8_t, lm_inv) X(uint8_t, slot_listed) X(uint8_t, pair_refresh)
 
 enum {

@@ -55,7 +55,7 @@ struct PoseOps<3> {  // CPose2D: x,y,phi
 	__device__ static void identity(double *p) { p[0] = 0; p[1] = 0; p[2] = 0; }
 	__device__ static void compose(double *o, const double *a, const double *b) {
 		double s, c;
-		sincos_ni(a[2], &s, &c);
+		sincos(a[2], &s, &c);
 		const double nx = a[0] + b[0] * c - b[1] * s;
 		const double ny = a[1] + b[0] * s + b[1] * c;
 		const double nphi = wrapToPi(a[2] + b[2]);
@@ -63,7 +63,7 @@ struct PoseOps<3> {  // CPose2D: x,y,phi
 	}
 	__device__ static void inverse(double *o, const double *a) {
 		double s, c;
-		sincos_ni(a[2], &s, &c);
+		sincos(a[2], &s, &c);
 		const double x = a[0], y = a[1];
 		o[0] = -x * c - y * s;
 		o[1] = x * s - y * c;
@@ -212,7 +212,7 @@ struct Shared {
 	double bcast;
 	// LM state (impl/optimize_edges.h:361-363,452-459)
 	double lambda, nu, err, rmse, rho, new_err;
-	int iter, stop, trials, accepted, relin, cholfail, cur, chol_ok, status;
+	int iter, stop, trials, accepted, relin, cholfail, cur, chol_ok, status, n_listed;
 	double sensor_inv[12];  // (-sensor_pose) hoisted: pose_robot2sensor (srba_options_sensor_pose.h:108-113)
 };
 
@@ -984,7 +984,7 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 	double *sInv = tile + 12 * (size_t)ntiles; // 3 x 12 : inverse pivot blocks of rows k-1, k, k+1 (slot = row % 3)
 	double *sAcc = sInv + 36;                  // 3*NTR : backward-pass accumulators
 	const int4 *rowinfo = reinterpret_cast<const int4 *>(v.ldl_row);  // {first tile, end tile | has_superdiag << 30, first update, end update}
-	const int32_t *tij = v.ldl_tile_ij, *upd = v.ldl_upd, *cptr = v.ldl_col_ptr, *ctile = v.ldl_col_tile, *src = v.ldl_src;
+	const int32_t *tij = v.ldl_tile_ij, *upd = v.ldl_upd, *src = v.ldl_src;
 	const int tid = threadIdx.x, NT = LM_THREADS;
 	const int lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
 	const int iwarp = nwarps - 1;              // the warp that carries the pivot chain (its lanes 0..8)
@@ -994,7 +994,7 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 	const int a1 = wa == 2 ? 0 : wa + 1, a2 = wa == 0 ? 2 : wa - 1, b1 = wb == 2 ? 0 : wb + 1, b2 = wb == 0 ? 2 : wb - 1;
 	const int o11 = b1 * 4 + a1, o22 = b2 * 4 + a2, o12 = b2 * 4 + a1, o21 = b1 * 4 + a2;
 	// gather: tile element <- reduced block element (+lambda on the diagonal); tile column NTR = reduced gradient
-#pragma unroll 1
+#pragma unroll 4
 	for (int q = tid; q < ntiles * 9; q += NT) {
 		const int tl = q / 9, e = q - tl * 9, b = e / 3, a = e - b * 3;
 		const int so = src[tl];  // >= 0: offset of the tile's (0,0) in S; -1: fill-in; <= -2: right-hand side of row -so-2
@@ -1005,8 +1005,6 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 		} else if (so <= -2 && b == 0) val = v.grad[3 * (-so - 2) + a];
 		tile[tl * 12 + b * 4 + a] = val;
 	}
-#pragma unroll 1
-	for (int i = tid; i < n; i += NT) sAcc[i] = 0.0;
 	if (tid == 0) sh.chol_ok = 1;
 	int4 ri = rowinfo[0];
 	__syncthreads();
@@ -1092,28 +1090,80 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 #ifdef SRBA_SOLVER_TIMERS
 	const long long c_back = clock64();
 #endif
-	// backward pass: column j folds x_j = z_j - acc_j into the rows above it; z_j = column 0 of the last tile of row j
+	// backward pass  x_k = z_k - sum_j W(k,j) x_j  (z_k = column 0 of the last tile of row k): a recurrence over the rows,
+	// carried by ONE warp with warp-level synchronisation only (a CTA barrier per row costs ~400 cycles here).
+	if (warp == 0) {
+		double *sX = sAcc;
+		if (NTR <= 32) {
+			// register wavefront: lane k owns row k.  Step j: the owner of x_j broadcasts it by shuffle, every lane whose row
+			// holds a tile in column j folds it into its accumulator (its W tile was fetched while waiting).
+			const int k = lane;
+			int r0 = 0, m = 0;
+			double z0 = 0, z1 = 0, z2 = 0;
+			if (k < NTR) {
+				const int4 rk = rowinfo[k];
+				const int r1 = rk.y & 0x3fffffff;
+				r0 = rk.x; m = r1 - r0 - 2;  // off-diagonal tiles without the right-hand side
+				const double *z = tile + (r1 - 1) * 12;
+				z0 = z[0]; z1 = z[1]; z2 = z[2];
+			}
+			int nxt_col = -1;
+			double w[9];
+#pragma unroll
+			for (int e = 0; e < 9; e++) w[e] = 0.0;
+			auto fetch = [&]() {  // the lane's next tile, walking its row from the last column down
+				if (m > 0) {
+					const int tl = r0 + m;
+					nxt_col = tij[tl] & 0xffff;
+					const double *Wt = tile + tl * 12;
+#pragma unroll
+					for (int b = 0; b < 3; b++)
+#pragma unroll
+						for (int a = 0; a < 3; a++) w[b * 3 + a] = Wt[b * 4 + a];
+					m--;
+				} else nxt_col = -1;
+			};
+			fetch();
 #pragma unroll 1
-	for (int j = NTR - 1; j >= 1; j--) {
-		const int c0 = cptr[j], nitems = (cptr[j + 1] - c0) * 3;
-		if (nitems == 0) continue;
+			for (int j = NTR - 1; j >= 0; j--) {
+				const double x0 = __shfl_sync(0xffffffffu, z0, j), x1 = __shfl_sync(0xffffffffu, z1, j), x2 = __shfl_sync(0xffffffffu, z2, j);
+				if (nxt_col == j) {
+					z0 -= w[0] * x0 + w[3] * x1 + w[6] * x2;
+					z1 -= w[1] * x0 + w[4] * x1 + w[7] * x2;
+					z2 -= w[2] * x0 + w[5] * x1 + w[8] * x2;
+					fetch();
+				}
+			}
+			if (k < NTR) { sX[3 * k] = z0; sX[3 * k + 1] = z1; sX[3 * k + 2] = z2; }
+		} else {
+			// general size: lane (a, t) multiplies row a of the t-th tile of the row, a 3-step butterfly sums over the tiles
+			const int a = lane >> 3, t8 = lane & 7;
 #pragma unroll 1
-		for (int q = tid; q < nitems; q += NT) {
-			const int ci = q / 3, a = q - ci * 3;
-			const int tl = ctile[c0 + ci];
-			const int i = tij[tl] >> 16;
-			const double *z = tile + (rowinfo[j + 1].x - 1) * 12;
-			const double x0 = z[0] - sAcc[3 * j], x1 = z[1] - sAcc[3 * j + 1], x2 = z[2] - sAcc[3 * j + 2];
-			const double *Wt = tile + tl * 12 + a;
-			sAcc[3 * i + a] += Wt[0] * x0 + Wt[4] * x1 + Wt[8] * x2;
+			for (int k = NTR - 1; k >= 0; k--) {
+				const int4 rk = rowinfo[k];
+				const int r0 = rk.x, r1 = rk.y & 0x3fffffff, m = r1 - r0 - 2;
+				double p = 0.0;
+#pragma unroll 1
+				for (int base = 0; base < m; base += 8) {
+					const int t = base + t8;
+					if (a < 3 && t < m) {
+						const int tl = r0 + 1 + t;
+						const double *x = sX + 3 * (tij[tl] & 0xffff);
+						const double *Wt = tile + tl * 12 + a;
+						p += Wt[0] * x[0] + Wt[4] * x[1] + Wt[8] * x[2];
+					}
+				}
+				p += __shfl_xor_sync(0xffffffffu, p, 4);
+				p += __shfl_xor_sync(0xffffffffu, p, 2);
+				p += __shfl_xor_sync(0xffffffffu, p, 1);
+				if (a < 3 && t8 == 0) sX[3 * k + a] = tile[(r1 - 1) * 12 + a] - p;
+				__syncwarp();
+			}
 		}
-		__syncthreads();
 	}
+	__syncthreads();
 #pragma unroll 1
-	for (int i = tid; i < n; i += NT) {
-		const int r = i / 3;
-		v.delta[i] = tile[(rowinfo[r + 1].x - 1) * 12 + (i - 3 * r)] - sAcc[i];
-	}
+	for (int i = tid; i < n; i += NT) v.delta[i] = sAcc[i];
 	__syncthreads();
 #ifdef SRBA_SOLVER_TIMERS
 	if (tid == 0) {
@@ -1196,7 +1246,7 @@ __device__ __noinline__ void stage_features(const View &vs) {
 
 // K5b: back-up + manifold update (impl/optimize_edges.h:491-557)
 template <int P>
-__device__ __noinline__ void stage_update(const View &vs) {
+__device__ __noinline__ void stage_update(const View &vs, int n_listed) {
 	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	constexpr int S = PoseOps<P>::S;
 	const DevProblem *h = v.h;
@@ -1216,21 +1266,24 @@ __device__ __noinline__ void stage_update(const View &vs) {
 #pragma unroll
 		for (int k = 0; k < 3; k++) { v.lm_bak[(size_t)i * 3 + k] = lp[k]; lp[k] += d[k]; }
 	}
-	for (size_t i = threadIdx.x; i < (size_t)2 * h->n_pairs * S; i += LM_THREADS) v.slot_bak[i] = v.slot[i];
+	// only the LISTED directed entries are ever restored (optimize_edges.h:664-670): back up just those, compactly
+	for (int q = threadIdx.x; q < n_listed * S; q += LM_THREADS) v.slot_bak[q] = v.slot[(size_t)v.listed_idx[q / S] * S + (q % S)];
 }
 // rejected step (impl/optimize_edges.h:660-680): only the LISTED directed entries of the numeric ST are restored.
 template <int P>
-__device__ __noinline__ void stage_restore(const View &vs) {
+__device__ __noinline__ void stage_restore(const View &vs, int n_listed) {
 	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	constexpr int S = PoseOps<P>::S;
 	const DevProblem *h = v.h;
 	for (int i = threadIdx.x; i < h->n_unk_edges * S; i += LM_THREADS) v.edge_cur[(size_t)v.unk_edge[i / S] * S + (i % S)] = v.edge_bak[i];
 	for (int i = threadIdx.x; i < h->n_unk_lms * 3; i += LM_THREADS) v.lm_cur[(size_t)v.unk_lm[i / 3] * 3 + (i % 3)] = v.lm_bak[i];
-	for (size_t i = threadIdx.x; i < (size_t)2 * h->n_pairs * S; i += LM_THREADS)
-		if (v.slot_listed[i / S]) v.slot[i] = v.slot_bak[i];
+	for (int q = threadIdx.x; q < n_listed * S; q += LM_THREADS) v.slot[(size_t)v.listed_idx[q / S] * S + (q % S)] = v.slot_bak[q];
 }
 
 // ------------------------------------------------------------------------------------------------ the LM program
+// Per-stage cycle counters (tools/stage_breakdown.py) are compiled in only with -DSRBA_SOLVER_TIMERS: each probe costs
+// the lone active warp ~250 cycles.
+#ifdef SRBA_SOLVER_TIMERS
 #define STAGE(id)                                            \
 	do {                                                     \
 		if (threadIdx.x == 0) {                              \
@@ -1239,6 +1292,9 @@ __device__ __noinline__ void stage_restore(const View &vs) {
 			sh.t_last = t_;                                  \
 		}                                                    \
 	} while (0)
+#else
+#define STAGE(id) do { } while (0)
+#endif
 
 template <int P, int OBSK, int TPT>
 __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char *res, Shared &sh, char *dyn) {
@@ -1290,6 +1346,17 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 	stage_jacobians<P, OBSK>(v, true);
 	__syncthreads();
 	for (int t = threadIdx.x; t < h->n_pairs; t += LM_THREADS) v.pair_refresh[t] = v.slot_listed[2 * t] | v.slot_listed[2 * t + 1];
+	if (threadIdx.x < 32) {  // compact list of the listed directed entries (ascending), built once by one warp
+		int cnt = 0;
+		for (int base = 0; base < 2 * h->n_pairs; base += 32) {
+			const int sidx = base + threadIdx.x;
+			const bool on = sidx < 2 * h->n_pairs && v.slot_listed[sidx];
+			const unsigned m = __ballot_sync(0xffffffffu, on);
+			if (on) v.listed_idx[cnt + __popc(m & ((1u << threadIdx.x) - 1))] = sidx;
+			cnt += __popc(m);
+		}
+		if (threadIdx.x == 0) sh.n_listed = cnt;
+	}
 	// J. Hessian (:329-331)
 	stage_hessian<P, OBSK>(v);
 	__syncthreads();
@@ -1335,8 +1402,10 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 			const double lambda = sh.lambda;
 			const int trial = sh.trials;
 			__syncthreads();
-			stage_schur<P>(v, lambda);
-			__syncthreads();
+			if (!(h->n_unk_lms == 0 && h->s_alias_hap)) {  // relative graph-SLAM: the reduced system IS H_Ap
+				stage_schur<P>(v, lambda);
+				__syncthreads();
+			}
 			const bool reg = (h->chol_mode == SRBA_CHOL_REG);
 			if (!reg || h->want_dense) {
 				stage_dense_fill<P>(v, lambda);
@@ -1376,7 +1445,7 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 				__syncthreads();
 			}
 			STAGE(ST_FEATURES);
-			stage_update<P>(v);
+			stage_update<P>(v, sh.n_listed);
 			__syncthreads();
 			STAGE(ST_UPDATE);
 			stage_chain<P>(v, true);  // update_numeric(set, true) (:565)
@@ -1431,7 +1500,7 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 					sh.rho = rho;
 				}
 			} else {
-				stage_restore<P>(v);
+				stage_restore<P>(v, sh.n_listed);
 				if (threadIdx.x == 0) {
 					sh.trials++;
 					sh.lambda *= sh.nu;
