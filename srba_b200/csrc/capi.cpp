@@ -144,7 +144,7 @@ struct TileSymbolic {
 	std::vector<int32_t> rs;        // NTR+1: first tile of each row (row-major numbering, diagonal first, RHS last)
 	std::vector<int32_t> row;       // 4 per row (+ sentinel): {first tile, end tile | has_superdiag<<30, first update, end update}
 	std::vector<int32_t> tile_ij;   // ntiles: (ti<<16)|tj
-	std::vector<int32_t> src;       // ntiles: offset of the tile's (0,0) in the reduced blocks, -1 fill-in, -2-row right-hand side
+	std::vector<int32_t> src;       // ntiles: offset of the tile's (0,0) in the reduced blocks (bit 30: diagonal tile), -1 fill-in, -2-row right-hand side
 	std::vector<int32_t> upd_ptr;   // NTR+1
 	std::vector<int32_t> upd;       // 2 per update: {dst tile | tile(k,i)<<16, tile(k,j)}; the update of the next pivot block is implicit
 	bool ok = false;                // false: too large for the on-chip solver (schedule not built)
@@ -239,7 +239,7 @@ void symbolic_tiles(const srba_problem_t &p, int P, long max_tiles, TileSymbolic
 		if (tj == ntr) { sy.src[t] = -2 - ti; continue; }
 		const int br = ti / q, bc = tj / q;
 		const int32_t b = blk[(size_t)br * p.n_unk_edges + bc];
-		sy.src[t] = b < 0 ? -1 : b * P * P + (ti - br * q) * 3 * P + (tj - bc * q) * 3;
+		sy.src[t] = b < 0 ? -1 : (b * P * P + (ti - br * q) * 3 * P + (tj - bc * q) * 3) | (ti == tj ? 1 << 30 : 0);
 	}
 	sy.ok = sy.tile_ij.size() < 65535;
 }
@@ -351,7 +351,7 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 		w[SRBA_W_grad] = (uint64_t)h.n_scalars * 8; w[SRBA_W_delta] = w[SRBA_W_grad];
 		w[SRBA_W_dense] = (h.chol_mode == SRBA_CHOL_BLOCKED || want_dense) ? (uint64_t)h.n_dense * h.ld_dense * 8 : 0;
 		w[SRBA_W_valid] = p.n_obs; w[SRBA_W_blk_ok] = p.n_blkA + p.n_blkF; w[SRBA_W_lm_inv] = p.n_unk_lms;
-		w[SRBA_W_slot_listed] = 2 * p.n_pairs; w[SRBA_W_pair_refresh] = p.n_pairs; w[SRBA_W_listed_idx] = (uint64_t)2 * p.n_pairs * 4;
+		w[SRBA_W_slot_listed] = 2 * p.n_pairs; w[SRBA_W_pair_refresh] = p.n_pairs; w[SRBA_W_listed_idx] = (uint64_t)2 * p.n_pairs * 4; w[SRBA_W_refresh_idx] = (uint64_t)p.n_pairs * 4;
 	}
 	Layout W;
 	for (int a = 0; a < SRBA_W_COUNT; a++) { h.ws_off[a] = W.add(ws_bytes[a]); h.ws_sm[a] = SRBA_NOT_IN_SMEM; }
@@ -365,7 +365,7 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 		struct Cand { int is_img, id; };
 		static const Cand order[] = {
 			{0, SRBA_W_edge_cur}, {0, SRBA_W_edge_bak}, {0, SRBA_W_grad}, {0, SRBA_W_delta}, {0, SRBA_W_lm_cur}, {0, SRBA_W_lm_bak},
-			{0, SRBA_W_valid}, {0, SRBA_W_lm_inv}, {0, SRBA_W_pair_refresh}, {0, SRBA_W_slot_listed}, {0, SRBA_W_listed_idx},
+			{0, SRBA_W_valid}, {0, SRBA_W_lm_inv}, {0, SRBA_W_pair_refresh}, {0, SRBA_W_slot_listed}, {0, SRBA_W_listed_idx}, {0, SRBA_W_refresh_idx},
 			{0, SRBA_W_resid0}, {0, SRBA_W_resid1}, {0, SRBA_W_slot}, {0, SRBA_W_HAp}, {0, SRBA_W_Hf}, {0, SRBA_W_Hf_inv},
 			{1, SRBA_I_ldl_row}, {1, SRBA_I_ldl_tile_ij}, {1, SRBA_I_ldl_upd}, {1, SRBA_I_ldl_src}, {1, SRBA_I_unk_edge}, {1, SRBA_I_unk_lm}, {1, SRBA_I_obs_slot}, {1, SRBA_I_obs_z}, {1, SRBA_I_obs_mult}, {1, SRBA_I_obs_lm},
 			{1, SRBA_I_pair_path_ptr}, {1, SRBA_I_path_edge}, {1, SRBA_I_path_dir},

@@ -39,7 +39,7 @@
 	X(double, JA) X(double, JF) X(double, resid0) X(double, resid1)                                                      \
 	X(double, HAp) X(double, HApf) X(double, Hf) X(double, Hf_inv) X(double, W) X(double, Sblk)                          \
 	X(double, grad) X(double, delta) X(double, dense)                                                                    \
-	X(int32_t, listed_idx)                                                                                               \
+	X(int32_t, listed_idx) X(int32_t, refresh_idx)                                                                                             \
 	X(uint8_t, valid) X(uint8_t, blk_ok) X(uint8_t, lm_inv) X(uint8_t, slot_listed) X(uint8_t, pair_refresh)
 
 enum {

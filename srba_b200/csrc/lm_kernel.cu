@@ -61,6 +61,8 @@ struct PoseOps<3> {  // CPose2D: x,y,phi
 		const double nphi = wrapToPi(a[2] + b[2]);
 		o[0] = nx; o[1] = ny; o[2] = nphi;
 	}
+	// compose(identity, b) without the sincos(0): 0 + b.x*1 - b.y*0 is exactly b.x; the angle still goes through the wrap
+	__device__ static void compose_from_identity(double *o, const double *b) { o[0] = b[0]; o[1] = b[1]; o[2] = wrapToPi(0.0 + b[2]); }
 	__device__ static void inverse(double *o, const double *a) {
 		double s, c;
 		sincos(a[2], &s, &c);
@@ -88,6 +90,11 @@ struct PoseOps<6> {  // CPose3D: R row-major (9) + t (3)
 			for (int c = 0; c < 3; c++) t[3 * r + c] = a[3 * r + 0] * b[c] + a[3 * r + 1] * b[3 + c] + a[3 * r + 2] * b[6 + c];
 #pragma unroll
 		for (int i = 0; i < 12; i++) o[i] = t[i];
+	}
+	__device__ static void compose_from_identity(double *o, const double *b) {
+		double id[12];
+		identity(id);
+		compose(o, id, b);  // I*R and 0 + I*t reproduce the reference's products exactly; no shortcut needed for parity
 	}
 	__device__ static void inverse(double *o, const double *a) {
 		double t[12];
@@ -203,7 +210,7 @@ enum { ST_INIT = 0, ST_SCHUR, ST_CHOL, ST_BACKSUB, ST_FEATURES, ST_UPDATE, ST_CH
 struct Shared {
 	DevProblem hdr;         // on-chip copy of the problem header (model parameters, counts, placement tables)
 	View view;              // resolved array pointers (arena or global), one copy per CTA
-	double red[LM_MAX_WARPS];
+	double red[3][2 * LM_MAX_WARPS];
 	unsigned long long stage_cycles[ST_COUNT];
 	unsigned long long dbg[8];  // solver sub-timers: gather, factor loop, back-substitution loop, critical-thread busy time
 	unsigned long long t_last;
@@ -212,54 +219,61 @@ struct Shared {
 	double bcast;
 	// LM state (impl/optimize_edges.h:361-363,452-459)
 	double lambda, nu, err, rmse, rho, new_err;
-	int iter, stop, trials, accepted, relin, cholfail, cur, chol_ok, status, n_listed;
+	int iter, stop, trials, accepted, relin, cholfail, cur, chol_ok, status, n_listed, n_refresh, need_outer, go;
 	double sensor_inv[12];  // (-sensor_pose) hoisted: pose_robot2sensor (srba_options_sensor_pose.h:108-113)
 };
 
-__device__ __forceinline__ double team_sum(double v, Shared &sh) {
+// Team-wide reductions with ONE barrier: warp partials go to one of three scratch rows (a row is reused only after at
+// least one other barrier), then every thread combines them in the same fixed order -- identical result on all threads.
+__device__ __forceinline__ double team_sum(double v, Shared &sh, int buf) {
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+	if ((threadIdx.x & 31) == 0) sh.red[buf][threadIdx.x >> 5] = v;
 	__syncthreads();
-	if ((threadIdx.x & 31) == 0) sh.red[threadIdx.x >> 5] = v;
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		double s = 0;
-		for (int i = 0; i < LM_THREADS / 32; i++) s += sh.red[i];
-		sh.bcast = s;
-	}
-	__syncthreads();
-	return sh.bcast;
+	double s = 0;
+	for (int i = 0; i < LM_THREADS / 32; i++) s += sh.red[buf][i];
+	return s;
 }
-__device__ __forceinline__ double team_max(double v, Shared &sh) {
+// two sums at once (second value in the upper half of the row)
+__device__ __forceinline__ double team_sum2(double v, double w, double &wsum, Shared &sh, int buf) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) { v += __shfl_down_sync(0xffffffffu, v, o); w += __shfl_down_sync(0xffffffffu, w, o); }
+	if ((threadIdx.x & 31) == 0) { sh.red[buf][threadIdx.x >> 5] = v; sh.red[buf][LM_MAX_WARPS + (threadIdx.x >> 5)] = w; }
+	__syncthreads();
+	double s = 0, t = 0;
+	for (int i = 0; i < LM_THREADS / 32; i++) { s += sh.red[buf][i]; t += sh.red[buf][LM_MAX_WARPS + i]; }
+	wsum = t;
+	return s;
+}
+__device__ __forceinline__ double team_max(double v, Shared &sh, int buf) {
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+	if ((threadIdx.x & 31) == 0) sh.red[buf][threadIdx.x >> 5] = v;
 	__syncthreads();
-	if ((threadIdx.x & 31) == 0) sh.red[threadIdx.x >> 5] = v;
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		double s = sh.red[0];
-		for (int i = 1; i < LM_THREADS / 32; i++) s = fmax(s, sh.red[i]);
-		sh.bcast = s;
-	}
-	__syncthreads();
-	return sh.bcast;
+	double s = sh.red[buf][0];
+	for (int i = 1; i < LM_THREADS / 32; i++) s = fmax(s, sh.red[buf][i]);
+	return s;
 }
 
 // ------------------------------------------------------------------------------------------------ stages
 // K1: numeric spanning tree.  update_numeric_only_all_from_node (impl/spantree_update_numeric.h:19-81)
 template <int P>
-__device__ __noinline__ void stage_chain(const View &vs, bool only_refresh) {
+__device__ __noinline__ void stage_chain(const View &vs, int n_refresh) {
 	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	constexpr int S = PoseOps<P>::S;
-	const int n = v.h->n_pairs;
-	for (int t = threadIdx.x; t < n; t += LM_THREADS) {
-		if (only_refresh && !v.pair_refresh[t]) continue;
+	// n_refresh < 0: every pair (update_numeric(set,false)); otherwise the compact list of pairs holding a listed pose
+	const int n = n_refresh < 0 ? v.h->n_pairs : n_refresh;
+	for (int q = threadIdx.x; q < n; q += LM_THREADS) {
+		const int t = n_refresh < 0 ? q : v.refresh_idx[q];
 		double accum[S], tmp[S];
-		PoseOps<P>::identity(accum);
-		for (int k = v.pair_path_ptr[t]; k < v.pair_path_ptr[t + 1]; k++) {
+		const int k0 = v.pair_path_ptr[t], k1 = v.pair_path_ptr[t + 1];
+		if (k0 == k1) PoseOps<P>::identity(accum);
+		for (int k = k0; k < k1; k++) {
 			const double *ep = v.edge_cur + (size_t)v.path_edge[k] * S;
-			if (v.path_dir[k]) PoseOps<P>::compose(accum, accum, ep);
-			else { PoseOps<P>::inverse(tmp, ep); PoseOps<P>::compose(accum, accum, tmp); }
+			const double *rhs = ep;
+			if (!v.path_dir[k]) { PoseOps<P>::inverse(tmp, ep); rhs = tmp; }
+			if (k == k0) PoseOps<P>::compose_from_identity(accum, rhs);
+			else PoseOps<P>::compose(accum, accum, rhs);
 		}
 		double *o = v.slot + (size_t)(2 * t) * S;
 #pragma unroll
@@ -578,7 +592,7 @@ __device__ __noinline__ void stage_hessian(const View &vs) {
 // reprojection_residuals (impl/reprojection_residuals.h:16-81) + sensor_model<>::observe_error; returns the team-wide
 // total squared error INCLUDING the duplicated rows of optimize_edges.h:177-193 (obs_mult).
 template <int P, int OBSK>
-__device__ __noinline__ double stage_residuals(const View &vs, double *resid, Shared &sh) {
+__device__ __noinline__ double stage_residuals(const View &vs, double *resid, Shared &sh, double extra, double *extra_sum) {
 	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	constexpr int S = PoseOps<P>::S;
 	constexpr int O = ObsDims<OBSK>::O;
@@ -637,18 +651,23 @@ __device__ __noinline__ double stage_residuals(const View &vs, double *resid, Sh
 		for (int k = 0; k < O; k++) resid[(size_t)i * O + k] = r[k];
 		local += contrib * (double)v.obs_mult[i];
 	}
-	return team_sum(local, sh);
+	// `extra` rides along in the same reduction (the denominator of rho, optimize_edges.h:585)
+	double es = 0;
+	const double tot = team_sum2(local, extra, es, sh, 0);
+	*extra_sum = es;
+	return tot;
 }
 
 // compute_minus_gradient (impl/compute_minus_gradient.h:20-91): one thread per scalar unknown, blocks in ascending obs.
 template <int P, int OBSK>
-__device__ __noinline__ void stage_gradient(const View &vs, const double *resid) {
+__device__ __noinline__ double stage_gradient(const View &vs, const double *resid) {
 	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	constexpr int O = ObsDims<OBSK>::O;
 	const DevProblem *h = v.h;
 	const bool ident = (h->model.noise_kind == SRBA_NOISE_IDENTITY);
 	const double scale = ident ? 1.0 / h->model.noise_std : 1.0;
 	const int nAp = h->n_unk_edges * P;
+	double gmax = 0;
 	for (int it = threadIdx.x; it < h->n_scalars; it += LM_THREADS) {
 		double g = 0;
 		if (it < nAp) {
@@ -692,8 +711,11 @@ __device__ __noinline__ void stage_gradient(const View &vs, const double *resid)
 				g += s;
 			}
 		}
-		v.grad[it] = ident ? g * scale : g;
+		const double gv = ident ? g * scale : g;
+		v.grad[it] = gv;
+		gmax = fmax(gmax, fabs(gv));
 	}
+	return gmax;  // this thread's share of max |g| (optimize_edges.h:636-640)
 }
 
 // Eigen::FullPivLU<3x3>: isInvertible() + inverse()  (impl/schur.h:193-208)
@@ -993,31 +1015,39 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 	// cyclic cofactor of a symmetric 3x3: C(a,b) = d(a1,b1) d(a2,b2) - d(a1,b2) d(a2,b1)
 	const int a1 = wa == 2 ? 0 : wa + 1, a2 = wa == 0 ? 2 : wa - 1, b1 = wb == 2 ? 0 : wb + 1, b2 = wb == 0 ? 2 : wb - 1;
 	const int o11 = b1 * 4 + a1, o22 = b2 * 4 + a2, o12 = b2 * 4 + a1, o21 = b1 * 4 + a2;
-	// gather: tile element <- reduced block element (+lambda on the diagonal); tile column NTR = reduced gradient
-#pragma unroll 4
-	for (int q = tid; q < ntiles * 9; q += NT) {
-		const int tl = q / 9, e = q - tl * 9, b = e / 3, a = e - b * 3;
-		const int so = src[tl];  // >= 0: offset of the tile's (0,0) in S; -1: fill-in; <= -2: right-hand side of row -so-2
-		double val = 0.0;
-		if (so >= 0) {
-			val = v.S[so + a * P + b];
-			if (a == b && (tij[tl] >> 16) == (tij[tl] & 0xffff)) val += lambda;
-		} else if (so <= -2 && b == 0) val = v.grad[3 * (-so - 2) + a];
-		tile[tl * 12 + b * 4 + a] = val;
-	}
-	if (tid == 0) sh.chol_ok = 1;
-	int4 ri = rowinfo[0];
-	__syncthreads();
+	int4 ri = rowinfo[0], rn = rowinfo[NTR > 1 ? 1 : NTR];
 	// pivot-block inversion by 9 lanes: own cofactor, determinant, one reciprocal
 	auto invert_pivot = [&](const double *D, double *inv) {
 		const double d00 = D[0], d01 = D[4], d02 = D[8], d11 = D[5], d12 = D[9], d22 = D[10];
 		const double c = D[o11] * D[o22] - D[o12] * D[o21];
 		const double det = d00 * (d11 * d22 - d12 * d12) + d01 * (d02 * d12 - d01 * d22) + d02 * (d01 * d12 - d02 * d11);
 		inv[eo] = c / det;
-		// leading minors == LLT's scalar pivots up to positive factors
+		// leading minors == LLT's scalar pivots up to positive factors; garbage after a failure is harmless and is
+		// discarded by the single check after the loop
 		if (d00 <= 0 || d00 * d11 - d01 * d01 <= 0 || det <= 0) sh.chol_ok = 0;
 	};
-	if (warp == iwarp && lane < 9) invert_pivot(tile + ri.x * 12, sInv);
+	// the first pivot block does not wait for the gather: its 9 lanes fetch their own elements and invert it while the
+	// other warps gather the remaining tiles
+	if (warp == iwarp) {
+		if (lane == 0) sh.chol_ok = 1;
+		if (lane < 9) tile[eo] = v.S[(src[0] & 0x3fffffff) + wa * P + wb] + (wa == wb ? lambda : 0.0);
+		__syncwarp();
+		if (lane < 9) invert_pivot(tile, sInv);
+	}
+	// gather: tile element <- reduced block element (+lambda on the diagonal); tile column NTR = reduced gradient.
+	// 9 lanes per tile (3 tiles per warp and round); ldl_src: >= 0 offset of the tile's (0,0) in S (bit 30: diagonal tile),
+	// -1 fill-in, <= -2 right-hand side of row -src-2
+	if (lane < 27) {
+		const double dl = wa == wb ? lambda : 0.0;
+#pragma unroll 4
+		for (int tl = 1 + 3 * warp + wg; tl < ntiles; tl += 3 * nwarps) {
+			const int so = src[tl];
+			double val = 0.0;
+			if (so >= 0) val = v.S[(so & 0x3fffffff) + wa * P + wb] + ((so >> 30) ? dl : 0.0);
+			else if (so <= -2 && wb == 0) val = v.grad[3 * (-so - 2) + wa];
+			tile[tl * 12 + eo] = val;
+		}
+	}
 	__syncthreads();
 #ifdef SRBA_SOLVER_TIMERS
 	const long long c_loop = clock64();
@@ -1025,9 +1055,8 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 	int prev_r0 = 0, prev_r1 = 0;  // tiles of row k-1 still to be turned into W
 #pragma unroll 1
 	for (int k = 0; k <= NTR; k++) {
-		if (!sh.chol_ok) return false;
 		const int r0 = ri.x, r1 = ri.y & 0x3fffffff, has_sd = ri.y >> 30, u0 = ri.z, nitems = (ri.w - ri.z) * 9;
-		const int4 rn = rowinfo[k < NTR ? k + 1 : NTR];  // row NTR is a sentinel without tiles or updates
+		const int4 rnn = rowinfo[k + 2 < NTR ? k + 2 : NTR];  // two rows ahead: off the critical path; row NTR is a sentinel
 		const double *Ik = sInv + (k % 3) * 12;
 		// ---- U: T(i,j) -= T(k,i)^t inv(D_k) T(k,j) for the pairs of row-k tiles (x: dst | tile(k,i) << 16, y: tile(k,j))
 #pragma unroll 1
@@ -1083,7 +1112,7 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 			}
 		}
 		prev_r0 = r0; prev_r1 = r1;
-		ri = rn;
+		ri = rn; rn = rnn;
 		__syncthreads();
 	}
 	if (!sh.chol_ok) return false;
@@ -1340,7 +1369,7 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 	}
 	__syncthreads();
 	// E. update_numeric(set,false)  (optimize_edges.h:256)
-	stage_chain<P>(v, false);
+	stage_chain<P>(v, -1);
 	__syncthreads();
 	// F/G. validity reset + recompute_all_Jacobians (:269-276)
 	stage_jacobians<P, OBSK>(v, true);
@@ -1356,6 +1385,17 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 			cnt += __popc(m);
 		}
 		if (threadIdx.x == 0) sh.n_listed = cnt;
+	} else if (threadIdx.x < 64) {  // compact list of the pairs holding a listed pose, by the second warp
+		const int l = threadIdx.x - 32;
+		int cnt = 0;
+		for (int base = 0; base < h->n_pairs; base += 32) {
+			const int t = base + l;
+			const bool on = t < h->n_pairs && (v.slot_listed[2 * t] | v.slot_listed[2 * t + 1]);
+			const unsigned m = __ballot_sync(0xffffffffu, on);
+			if (on) v.refresh_idx[cnt + __popc(m & ((1u << l) - 1))] = t;
+			cnt += __popc(m);
+		}
+		if (l == 0) sh.n_refresh = cnt;
 	}
 	// J. Hessian (:329-331)
 	stage_hessian<P, OBSK>(v);
@@ -1370,9 +1410,10 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 		}
 	for (int k = threadIdx.x; k < h->n_unk_lms; k += LM_THREADS)
 		dmax = fmax(dmax, fmax(v.Hf[(size_t)k * 9], fmax(v.Hf[(size_t)k * 9 + 4], v.Hf[(size_t)k * 9 + 8])));
-	dmax = team_max(dmax, sh);
+	dmax = team_max(dmax, sh, 1);
 	// M. residuals (:395-404)
-	const double err0 = stage_residuals<P, OBSK>(v, v.resid[0], sh);
+	double unused_sum;
+	const double err0 = stage_residuals<P, OBSK>(v, v.resid[0], sh, 0.0, &unused_sum);
 	// N. gradient (:422-426)
 	stage_gradient<P, OBSK>(v, v.resid[0]);
 	if (threadIdx.x == 0) {
@@ -1381,27 +1422,37 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 		sh.err = err0;
 		sh.rmse = sqrt(err0 / nObsRows);
 		sh.iter = 0; sh.stop = 0; sh.trials = 0; sh.accepted = 0; sh.relin = 0; sh.cholfail = 0; sh.cur = 0;
+		sh.need_outer = 1; sh.rho = 0;
 		v.stats->total_sqr_error_init = err0;
 	}
+	const double MAX_LAMBDA = h->model.max_lambda;
+	const double max_gradient_to_stop = 1e-15;
+	// P. LM iterations (:454-696).  The reference's two nested loops
+	//     while (iter < max_iters && !stop) { rho = 0; stop tests; while (rho <= 0 && !stop) { TRIAL } iter++; }
+	// are flattened: after every trial thread 0 walks the scalar control flow up to the next trial (or the exit) and
+	// publishes the decision in sh.go, so a trial costs one control barrier instead of one per loop level.
+	auto advance = [&]() {
+		for (;;) {
+			if (sh.need_outer) {
+				if (!(sh.iter < h->model.max_iters && !sh.stop)) { sh.go = 0; return; }
+				sh.rho = 0;
+				if (sh.lambda >= MAX_LAMBDA) sh.stop = 1;
+				if (sh.rmse < h->model.max_error_per_obs_to_stop) sh.stop = 1;
+				sh.need_outer = 0;
+			}
+			if (sh.rho <= 0 && !sh.stop) { sh.go = 1; return; }
+			sh.iter++;
+			sh.need_outer = 1;
+		}
+	};
+	if (threadIdx.x == 0) advance();
 	__syncthreads();
 	STAGE(ST_INIT);
 
-	const double MAX_LAMBDA = h->model.max_lambda;
-	const double max_gradient_to_stop = 1e-15;
-	// P. LM iterations (:454-696).  Every thread follows the same control flow through the shared state.
-	for (;;) {
-		if (!(sh.iter < h->model.max_iters && !sh.stop)) break;
-		__syncthreads();
-		if (threadIdx.x == 0) {
-			sh.rho = 0;
-			if (sh.lambda >= MAX_LAMBDA) sh.stop = 1;
-			if (sh.rmse < h->model.max_error_per_obs_to_stop) sh.stop = 1;
-		}
-		__syncthreads();
-		while (sh.rho <= 0 && !sh.stop) {
+	{
+		while (sh.go) {
 			const double lambda = sh.lambda;
 			const int trial = sh.trials;
-			__syncthreads();
 			if (!(h->n_unk_lms == 0 && h->s_alias_hap)) {  // relative graph-SLAM: the reduced system IS H_Ap
 				stage_schur<P>(v, lambda);
 				__syncthreads();
@@ -1431,6 +1482,7 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 					sh.lambda *= sh.nu;
 					sh.nu *= 2.;
 					sh.stop = (sh.lambda > MAX_LAMBDA);
+					advance();
 				}
 				if (trial < h->trace_cap)
 					for (int i = threadIdx.x; i < nsc; i += LM_THREADS) v.r_trace_delta[(size_t)trial * nsc + i] = 0;
@@ -1448,16 +1500,16 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 			stage_update<P>(v, sh.n_listed);
 			__syncthreads();
 			STAGE(ST_UPDATE);
-			stage_chain<P>(v, true);  // update_numeric(set, true) (:565)
+			stage_chain<P>(v, sh.n_refresh);  // update_numeric(set, true) (:565)
 			__syncthreads();
 			STAGE(ST_CHAIN);
 			double *new_resid = v.resid[sh.cur ^ 1];
-			const double new_err = stage_residuals<P, OBSK>(v, new_resid, sh);
-			STAGE(ST_RESID);
-			// rho (:585)
+			// rho (:585): its denominator rides along in the residual reduction
 			double dl = 0;
 			for (int i = threadIdx.x; i < nsc; i += LM_THREADS) dl += v.delta[i] * (lambda * v.delta[i] + v.grad[i]);
-			const double denom = team_sum(dl, sh);
+			double denom;
+			const double new_err = stage_residuals<P, OBSK>(v, new_resid, sh, dl, &denom);
+			STAGE(ST_RESID);
 			const double err = sh.err;
 			const double rho = (err - new_err) / denom;
 			const double error_reduction_ratio = err > 0 ? (err - new_err) / err : 0;
@@ -1470,7 +1522,6 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 				}
 				for (int i = threadIdx.x; i < nsc; i += LM_THREADS) v.r_trace_delta[(size_t)trial * nsc + i] = v.delta[i];
 			}
-			__syncthreads();
 			STAGE(ST_RHO);
 			if (accept) {
 				if (do_relinearize) {  // :606-629
@@ -1481,12 +1532,9 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 					__syncthreads();
 					STAGE(ST_HESS);
 				}
-				stage_gradient<P, OBSK>(v, new_resid);  // :633
-				__syncthreads();
+				double gm = stage_gradient<P, OBSK>(v, new_resid);  // :633
+				gm = team_max(gm, sh, 1);
 				STAGE(ST_GRAD);
-				double gm = 0;
-				for (int i = threadIdx.x; i < nsc; i += LM_THREADS) gm = fmax(gm, fabs(v.grad[i]));
-				gm = team_max(gm, sh);
 				if (threadIdx.x == 0) {
 					sh.cur ^= 1;
 					sh.err = new_err;
@@ -1498,6 +1546,7 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 					sh.lambda *= 1.0 / 3.0;
 					sh.nu = 2.0;
 					sh.rho = rho;
+					advance();
 				}
 			} else {
 				stage_restore<P>(v, sh.n_listed);
@@ -1507,14 +1556,12 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 					sh.nu *= 2.0;
 					sh.stop = (sh.lambda > MAX_LAMBDA);
 					sh.rho = rho;  // <=0 or NaN: NaN also leaves the while in the reference ("rho<=0" false)
+					advance();
 				}
 			}
 			__syncthreads();
 			STAGE(ST_CTRL);
 		}
-		__syncthreads();
-		if (threadIdx.x == 0) sh.iter++;
-		__syncthreads();
 	}
 	__syncthreads();
 	// Q/S. outputs
