@@ -486,7 +486,8 @@ struct Pool {
 	uint64_t h_img_cap = 0, h_res_cap = 0, d_img_cap = 0, d_ws_cap = 0, d_res_cap = 0;
 	cudaStream_t stream = nullptr;
 };
-static thread_local Pool g_pool;
+#define SRBA_MAX_CHUNKS 4
+static thread_local Pool g_pool[SRBA_MAX_CHUNKS];  // one buffer set per pipelined chunk of a batch call
 
 static bool pool_reserve_host(char **p, uint64_t *cap, uint64_t need) {
 	if (*cap >= need) return true;
@@ -723,30 +724,52 @@ int srba_b200_optimize_batch(int32_t n, const srba_problem_t *const *in, srba_re
 	auto now = [] { return std::chrono::steady_clock::now(); };
 	auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point c) { return std::chrono::duration<double, std::milli>(c - a).count(); };
 	const auto t0 = now();
-	srba_batch_t *b = batch_create_impl(n, in, want_dense ? -tcap : tcap, &g_pool);
-	if (!b) return g_code != SRBA_OK ? g_code : SRBA_ERR_INTERNAL;
-	const auto t1 = now();
+	// A large batch is cut into up to SRBA_MAX_CHUNKS chunks, each with its own stream and buffers: while chunk c is copied
+	// and solved, chunk c+1 is being packed on the host cores, and results come back chunk by chunk.  All chunks fit the
+	// GPU together (2 CTAs/SM), so the kernels overlap; only the first pack and the last copy-back stay exposed.
+	const int K = n >= 64 ? SRBA_MAX_CHUNKS : 1;
+	srba_batch_t *bt[SRBA_MAX_CHUNKS] = {nullptr, nullptr, nullptr, nullptr};
+	int begin[SRBA_MAX_CHUNKS + 1];
+	for (int c = 0; c <= K; c++) begin[c] = (int)((int64_t)n * c / K);
 	int rc = SRBA_OK;
-	if (!g_pool.stream && cudaStreamCreateWithFlags(&g_pool.stream, cudaStreamNonBlocking) != cudaSuccess) rc = fail(SRBA_ERR_CUDA, "cudaStreamCreate failed");
-	cudaStream_t st = g_pool.stream;
-	if (rc == SRBA_OK) rc = srba_b200_batch_upload(b, st);
-	if (rc == SRBA_OK) rc = srba_b200_batch_run(b, st);
+	double t_pack = 0;
+	for (int c = 0; c < K && rc == SRBA_OK; c++) {
+		Pool &pool = g_pool[c];
+		const auto tp = now();
+		bt[c] = batch_create_impl(begin[c + 1] - begin[c], in + begin[c], want_dense ? -tcap : tcap, &pool);
+		t_pack += ms(tp, now());
+		if (!bt[c]) { rc = g_code != SRBA_OK ? g_code : SRBA_ERR_INTERNAL; break; }
+		if (!pool.stream && cudaStreamCreateWithFlags(&pool.stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(SRBA_ERR_CUDA, "cudaStreamCreate failed"); break; }
+		rc = srba_b200_batch_upload(bt[c], pool.stream);
+		if (rc == SRBA_OK) rc = srba_b200_batch_run(bt[c], pool.stream);
+		if (rc == SRBA_OK && cudaMemcpyAsync(bt[c]->h_res, bt[c]->d_res, bt[c]->res_bytes, cudaMemcpyDeviceToHost, pool.stream) != cudaSuccess)
+			rc = fail(SRBA_ERR_CUDA, "cudaMemcpyAsync (results) failed");
+	}
 	const auto t2 = now();
-	if (rc == SRBA_OK) rc = srba_b200_batch_download(b, st);
-	const auto t3 = now();
-	if (rc == SRBA_OK) {
-		std::atomic<int> first_bad{SRBA_OK};
-		workers().parallel_for(n, [&](int i) {
-			const int r = srba_b200_batch_unpack(b, i, out[i]);
-			if (r != SRBA_OK) { int expect = SRBA_OK; first_bad.compare_exchange_strong(expect, r); }
-		});
-		rc = first_bad.load();
+	double t_wait = 0, t_unpack = 0;
+	for (int c = 0; c < K; c++) {
+		if (!bt[c]) continue;
+		const auto tw = now();
+		if (cudaStreamSynchronize(g_pool[c].stream) != cudaSuccess && rc == SRBA_OK) rc = fail(SRBA_ERR_CUDA, std::string("kernel execution: ") + cudaGetErrorString(cudaGetLastError()));
+		const auto tu = now();
+		t_wait += ms(tw, tu);
+		if (rc == SRBA_OK) {
+			bt[c]->downloaded = true;
+			std::atomic<int> first_bad{SRBA_OK};
+			srba_batch_t *b = bt[c];
+			srba_result_t *const *o = out + begin[c];
+			workers().parallel_for(b->n, [&](int i) {
+				const int r = srba_b200_batch_unpack(b, i, o[i]);
+				if (r != SRBA_OK) { int expect = SRBA_OK; first_bad.compare_exchange_strong(expect, r); }
+			});
+			if (first_bad.load() != SRBA_OK) rc = first_bad.load();
+		}
+		t_unpack += ms(tu, now());
+		srba_b200_batch_destroy(bt[c]);
 	}
-	srba_b200_batch_destroy(b);
-	if (timing) {
-		const auto t4 = now();
-		std::fprintf(stderr, "[srba_b200] optimize_batch n=%d: pack %.3f ms, enqueue %.3f ms, wait+d2h %.3f ms, unpack %.3f ms\n", n, ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4));
-	}
+	if (timing)
+		std::fprintf(stderr, "[srba_b200] optimize_batch n=%d in %d chunk(s): total %.3f ms (pack %.3f ms, enqueue window %.3f ms, waits %.3f ms, unpack %.3f ms)\n", n, K,
+		             ms(t0, now()), t_pack, ms(t0, t2), t_wait, t_unpack);
 	return rc;
 }
 
