@@ -172,6 +172,14 @@ void srba_b200_batch_algorithmic_bytes(const srba_batch_t *b, double out[5]);
  * image arrays on chip, workspace arrays on chip, shared-memory budget of the model's kernel.  No device needed. */
 int srba_b200_problem_plan(const srba_problem_t *in, int64_t out[8]);
 
+/* Host-only (tests): the symbolic factorisation the packer ships with a problem for the on-chip block-sparse L D L^t
+ * solver -- 3x3 tiles numbered row-major (diagonal first, right-hand side as tile column NTR).  counts[4] = {NTR, tiles,
+ * updates, fits}; row[4*(NTR+1)] = {first tile, end tile | has_superdiag<<30, first update, end update} per row;
+ * tile_ij[tiles] = ti<<16|tj; src[tiles] = offset into the reduced blocks (bit 30: diagonal), -1 fill-in, -2-row right-hand
+ * side; upd[2*updates] = {dst tile | tile(k,i)<<16, tile(k,j)}.  Call with NULL arrays to get the counts first. */
+int srba_b200_debug_ldl_schedule(const srba_problem_t *in, int32_t counts[4], int32_t *row, int32_t *tile_ij, int32_t *src, int32_t *upd,
+                                 int32_t cap_tiles, int32_t cap_upd);
+
 const char *srba_b200_last_error(void);
 int srba_b200_device_count(void);
 const char *srba_b200_version(void);

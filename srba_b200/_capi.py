@@ -84,7 +84,7 @@ class NewEdge(C.Structure):
 EXPORTED_SYMBOLS = [
     "srba_b200_optimize", "srba_b200_optimize_batch", "srba_b200_batch_create", "srba_b200_batch_upload", "srba_b200_batch_run",
     "srba_b200_batch_download", "srba_b200_batch_unpack", "srba_b200_batch_destroy", "srba_b200_batch_h2d_bytes", "srba_b200_batch_d2h_bytes",
-    "srba_b200_batch_kernel_launches", "srba_b200_batch_stage_cycles", "srba_b200_problem_plan", "srba_b200_batch_algorithmic_bytes", "srba_b200_last_error", "srba_b200_device_count", "srba_b200_version",
+    "srba_b200_batch_kernel_launches", "srba_b200_batch_stage_cycles", "srba_b200_problem_plan", "srba_b200_debug_ldl_schedule", "srba_b200_batch_algorithmic_bytes", "srba_b200_last_error", "srba_b200_device_count", "srba_b200_version",
     "srba_engine_default_params", "srba_engine_create", "srba_engine_destroy", "srba_engine_set_params", "srba_engine_define_new_keyframe",
     "srba_engine_optimize_local_area", "srba_engine_optimize_edges", "srba_engine_select_local_area", "srba_engine_flatten",
     "srba_engine_flatten_local_area", "srba_flat_problem", "srba_flat_apply", "srba_flat_ids", "srba_flat_destroy",
@@ -128,6 +128,9 @@ def lib():
     L.srba_b200_batch_algorithmic_bytes.argtypes = [vp, pdbl]
     L.srba_b200_batch_stage_cycles.restype = C.c_int
     L.srba_b200_batch_stage_cycles.argtypes = [vp, i32, pu64]
+    pi32 = C.POINTER(C.c_int32)
+    L.srba_b200_debug_ldl_schedule.restype = C.c_int
+    L.srba_b200_debug_ldl_schedule.argtypes = [pp, pi32, pi32, pi32, pi32, pi32, i32, i32]
     L.srba_b200_problem_plan.restype = C.c_int
     L.srba_b200_problem_plan.argtypes = [pp, C.POINTER(C.c_int64)]
     L.srba_b200_last_error.restype = C.c_char_p

@@ -271,7 +271,8 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 		if (max_tiles > 0) symbolic_tiles(p, P, max_tiles, sy);
 		else sy.clear();
 	}
-	const int reg_scratch = sy.ok ? srba_chol_reg_scratch_doubles(model, h.n_dense, (int)sy.tile_ij.size()) : -1;
+	static const bool force_blocked = [] { const char *e = std::getenv("SRBA_B200_SOLVER"); return e && std::string(e) == "blocked"; }();  // tests
+	const int reg_scratch = (sy.ok && !force_blocked) ? srba_chol_reg_scratch_doubles(model, h.n_dense, (int)sy.tile_ij.size()) : -1;
 	uint64_t scratch_bytes;
 	if (reg_scratch >= 0) {
 		h.chol_mode = SRBA_CHOL_REG;
@@ -694,6 +695,26 @@ void srba_b200_batch_algorithmic_bytes(const srba_batch_t *b, double out[5]) {
 		out[3] += n * n * 8;
 		out[4] += n * n * n / 3.0 + 2 * n * n;
 	}
+}
+
+int srba_b200_debug_ldl_schedule(const srba_problem_t *in, int32_t counts[4], int32_t *row, int32_t *tile_ij, int32_t *src, int32_t *upd, int32_t cap_tiles,
+                                 int32_t cap_upd) {
+	if (!in || !counts) return fail(SRBA_ERR_BAD_ARGUMENT, "null argument");
+	const int rc = validate(*in);
+	if (rc != SRBA_OK) return rc;
+	const int P = in->model.pose_kind == SRBA_POSE_SE2 ? 3 : 6;
+	TileSymbolic sy;
+	symbolic_tiles(*in, P, 32767, sy);
+	counts[0] = sy.ntr; counts[1] = (int32_t)sy.tile_ij.size(); counts[2] = (int32_t)(sy.upd.size() / 2); counts[3] = sy.ok ? 1 : 0;
+	if (!sy.ok) return SRBA_OK;
+	if (row && tile_ij && src && upd) {
+		if (cap_tiles < counts[1] || cap_upd < counts[2]) return fail(SRBA_ERR_BAD_ARGUMENT, "schedule buffers too small");
+		std::memcpy(row, sy.row.data(), sy.row.size() * 4);
+		std::memcpy(tile_ij, sy.tile_ij.data(), sy.tile_ij.size() * 4);
+		std::memcpy(src, sy.src.data(), sy.src.size() * 4);
+		std::memcpy(upd, sy.upd.data(), sy.upd.size() * 4);
+	}
+	return SRBA_OK;
 }
 
 int srba_b200_problem_plan(const srba_problem_t *in, int64_t out[8]) {

@@ -211,6 +211,50 @@ def test_batch_matches_single_and_is_repeatable():
     assert b.kernel_launches >= 1 and b.h2d_bytes > 0 and b.d2h_bytes > 0
 
 
+def test_blocked_fallback_matches_onchip_solver():
+    """The dense blocked Cholesky (systems whose tiles do not fit on chip) and the on-chip block-sparse L D L^t solver
+    factor the same reduced system: first increment within 1e-9 relative, final edges within 1e-6."""
+    import json
+    import os
+    import subprocess
+    import sys
+    script = os.path.join(os.path.dirname(__file__), "_solve_flats.py")
+    runs = []
+    for mode in ("", "blocked"):
+        env = dict(os.environ, SRBA_B200_SOLVER=mode)
+        out = subprocess.run([sys.executable, script], env=env, capture_output=True, text=True, check=True).stdout.strip().splitlines()[-1]
+        runs.append(json.loads(out))
+    assert len(runs[0]) == len(runs[1]) >= 6
+    for a, b in zip(*runs):
+        assert a["n_unk"] == b["n_unk"] and a["trials"] > 0 and b["trials"] > 0
+        assert rel_err(a["first_delta"], b["first_delta"]) <= 1e-9
+        assert rel_err(a["edge"], b["edge"]) <= 1e-6
+
+
+def test_pipelined_batch_call_matches_single_calls():
+    """srba_b200_optimize_batch cuts a large batch into chunks on separate streams: results must be bit-identical to
+    one-problem calls, in the caller's order."""
+    import ctypes as C
+    from srba_b200 import _capi as K
+    ds = D.graphslam_se2_tour(130, seed=6)
+    kw = dict(S2, noise_lambda=D.se2_noise_lambda(ds["sigma_xy"], ds["sigma_yaw"]))
+    ep = sb.RbaEngine(sb.default_engine_params(**kw))
+    ep.record_problems(True)
+    for f in ds["frames"]:
+        D.feed(ep, f)
+    flats = [f for f in ep.take_recorded() if f.p.n_unk_edges >= 2][-70:]
+    assert len(flats) >= 64   # enough to trigger the chunked path
+    singles = [sb.optimize(f) for f in flats]
+    n = len(flats)
+    parr = (C.POINTER(K.Problem) * n)(*[f.problem for f in flats])
+    bufs = [sb.ResultBuffers(f.p) for f in flats]
+    rarr = (C.POINTER(K.Result) * n)(*[C.pointer(b.r) for b in bufs])
+    assert K.lib().srba_b200_optimize_batch(n, parr, rarr) == 0
+    for s, b in zip(singles, bufs):
+        assert b.r.stats.as_dict() == s.stats
+        assert np.array_equal(b.edge_pose, s.edge_pose) and np.array_equal(b.slot_pose, s.slot_pose)
+
+
 def test_error_codes():
     from srba_b200 import _capi as K
     ds = D.graphslam_se2_tour(30, seed=1)

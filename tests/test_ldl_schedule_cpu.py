@@ -1,0 +1,141 @@
+"""CPU-only check of the packer's symbolic factorisation (srba_b200/csrc/capi.cpp: symbolic_tiles), i.e. the schedule the
+on-chip block-sparse L D L^t solver of lm_kernel.cu executes instead of the reference's dense fill + Eigen::LLT
+(impl/lev-marq_solvers.h:492-549).  The schedule is emulated step by step in numpy on a random SPD system with the
+problem's own block pattern and compared with a dense solve: this pins the fill-in, the tile numbering, the update lists,
+the implicit pivot update and the source mapping without a GPU."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import srba_b200 as sb
+from srba_b200 import _capi as K
+from srba_b200 import datasets as D
+
+
+def schedule(flat):
+    L = K.lib()
+    counts = (C.c_int32 * 4)()
+    assert L.srba_b200_debug_ldl_schedule(flat.problem, counts, None, None, None, None, 0, 0) == 0
+    ntr, ntiles, nupd, ok = list(counts)
+    assert ok == 1
+    row = np.zeros(4 * (ntr + 1), np.int32); tij = np.zeros(ntiles, np.int32); src = np.zeros(ntiles, np.int32); upd = np.zeros(2 * nupd, np.int32)
+    p32 = C.POINTER(C.c_int32)
+    assert L.srba_b200_debug_ldl_schedule(flat.problem, counts, row.ctypes.data_as(p32), tij.ctypes.data_as(p32), src.ctypes.data_as(p32),
+                                          upd.ctypes.data_as(p32), ntiles, nupd) == 0
+    return ntr, row.reshape(-1, 4), tij, src, upd.reshape(-1, 2)
+
+
+def emulate(flat, P, rng):
+    """Random SPD blocks with the problem's reduced-system pattern -> solve through the schedule and densely."""
+    p = flat.p
+    n_p, n = p.n_unk_edges, P * p.n_unk_edges
+    S_row, S_col = flat.array("S_row", p.n_S, np.int32), flat.array("S_col", p.n_S, np.int32)
+    blocks = rng.normal(size=(p.n_S, P, P))
+    A = np.zeros((n, n))
+    for b in range(p.n_S):
+        r, c = S_row[b], S_col[b]
+        if r == c:
+            blocks[b] = blocks[b] @ blocks[b].T + 4.0 * P * np.eye(P)   # diagonally dominant: the whole matrix is SPD
+        A[P * r:P * r + P, P * c:P * c + P] = blocks[b]
+        A[P * c:P * c + P, P * r:P * r + P] = blocks[b].T
+    for b in range(p.n_S):
+        if S_row[b] == S_col[b]:
+            A[P * S_row[b]:P * S_row[b] + P, P * S_row[b]:P * S_row[b] + P] += 0.3 * n_p * np.eye(P)
+            blocks[b] += 0.3 * n_p * np.eye(P)
+    g = rng.normal(size=n)
+    lam = 0.37
+    Sflat = blocks.reshape(-1)
+    ntr, row, tij, src, upd = schedule(flat)
+    assert ntr == n // 3
+    tiles = np.zeros((len(tij), 3, 3))
+    for t in range(len(tij)):
+        ti, tj = tij[t] >> 16, tij[t] & 0xffff
+        assert ti <= tj <= ntr
+        if src[t] >= 0:
+            off = src[t] & 0x3fffffff
+            for a in range(3):
+                tiles[t, a] = Sflat[off + a * P: off + a * P + 3]
+            assert bool(src[t] >> 30) == (ti == tj)
+            if ti == tj:
+                tiles[t] += lam * np.eye(3)
+        elif src[t] <= -2:
+            assert tj == ntr and -src[t] - 2 == ti
+            tiles[t, :, 0] = g[3 * ti:3 * ti + 3]
+    # rows are contiguous, diagonal first, right-hand side last
+    for k in range(ntr):
+        r0, r1 = row[k, 0], row[k, 1] & 0x3fffffff
+        cols = [tij[t] & 0xffff for t in range(r0, r1)]
+        assert cols[0] == k and cols[-1] == ntr and cols == sorted(cols) and all(tij[t] >> 16 == k for t in range(r0, r1))
+    inv = [None] * ntr
+    inv[0] = np.linalg.inv(tiles[row[0, 0]])
+    for k in range(ntr):
+        r0, r1, has_sd = row[k, 0], row[k, 1] & 0x3fffffff, row[k, 1] >> 30
+        for u in range(row[k, 2], row[k, 3]):
+            dst, ti_, tj_ = upd[u, 0] & 0xffff, upd[u, 0] >> 16, upd[u, 1]
+            assert r0 < ti_ < r1 and r0 < tj_ < r1 and (tij[dst] >> 16) == (tij[ti_] & 0xffff) and (tij[dst] & 0xffff) == (tij[tj_] & 0xffff)
+            tiles[dst] -= tiles[ti_].T @ inv[k] @ tiles[tj_]
+        if k + 1 < ntr:
+            dn = row[k + 1, 0]
+            if has_sd:
+                assert (tij[r0 + 1] & 0xffff) == k + 1
+                tiles[dn] -= tiles[r0 + 1].T @ inv[k] @ tiles[r0 + 1]
+            else:
+                assert r0 + 1 >= r1 or (tij[r0 + 1] & 0xffff) != k + 1
+            inv[k + 1] = np.linalg.inv(tiles[dn])
+    for k in range(ntr):   # W = inv(D) T in place
+        for t in range(row[k, 0] + 1, row[k, 1] & 0x3fffffff):
+            tiles[t] = inv[k] @ tiles[t]
+    x = np.zeros((ntr, 3))
+    for k in range(ntr - 1, -1, -1):
+        r0, r1 = row[k, 0], row[k, 1] & 0x3fffffff
+        acc = tiles[r1 - 1][:, 0].copy()
+        for t in range(r0 + 1, r1 - 1):
+            acc -= tiles[t] @ x[tij[t] & 0xffff]
+        x[k] = acc
+    ref = np.linalg.solve(A + lam * np.eye(n), g)
+    return x.reshape(-1), ref, len(tij), p.n_S
+
+
+def flats_se2():
+    ds = D.graphslam_se2_tour(90, seed=3)
+    kw = dict(pose_kind=0, obs_kind=0, noise_kind=1, noise_lambda=D.se2_noise_lambda(ds["sigma_xy"], ds["sigma_yaw"]), max_tree_depth=3,
+              max_optimize_depth=3, submap_size=10, min_obs_to_loop_closure=1)
+    e = sb.RbaEngine(sb.default_engine_params(**kw))
+    out = []
+    for k, f in enumerate(ds["frames"]):
+        D.feed(e, f, run_local_optimization=False)
+        if k in (5, 33, 60, 89):
+            out.append(e.flatten_local_area(k, 3))
+    return out
+
+
+def flats_se3():
+    ds = D.landmark_slam_se3(n_kfs=25, n_lms=150, seed=5, obs_kind="cartesian3d")
+    kw = dict(pose_kind=1, obs_kind=1, noise_kind=0, noise_std=1e-3, max_tree_depth=3, max_optimize_depth=3, submap_size=5, min_obs_to_loop_closure=4)
+    e = sb.RbaEngine(sb.default_engine_params(**kw))
+    out = []
+    for k, f in enumerate(ds["frames"]):
+        D.feed(e, f, run_local_optimization=False)
+        if k in (8, 24):
+            out.append(e.flatten_local_area(k, 3))
+    return out
+
+
+@pytest.mark.parametrize("kind", ["se2", "se3"])
+def test_schedule_solves_the_reduced_system(kind):
+    rng = np.random.default_rng(11)
+    flats, P = (flats_se2(), 3) if kind == "se2" else (flats_se3(), 6)
+    assert flats
+    for fl in flats:
+        x, ref, ntiles, n_S = emulate(fl, P, rng)
+        assert np.abs(x - ref).max() <= 1e-10 * max(1.0, np.abs(ref).max())
+
+
+def test_plan_fits_the_shared_memory_budget():
+    L = K.lib()
+    for fl in flats_se2():
+        out = (C.c_int64 * 8)()
+        assert L.srba_b200_problem_plan(fl.problem, out) == 0
+        img, ws, res, sm, chol, n_img, n_ws, budget = list(out)
+        assert 0 < sm <= budget and chol == 0 and n_ws >= 10 and img > 0 and res > 0
