@@ -118,11 +118,11 @@ class ClockSampler:
         return out
 
 
-def build_problems(seed, areas, n_kfs):
+def build_problems(seed, areas, n_kfs, noise_seed=None):
     """Sequential product-engine run over the tour; returns the flattened local-area problem of the last `areas` keyframes."""
     import srba_b200 as sb
     from srba_b200 import datasets as D
-    ds = D.graphslam_se2_tour(n_kfs, seed=seed)
+    ds = D.graphslam_se2_tour(n_kfs, seed=seed, noise_seed=noise_seed)
     eng = sb.RbaEngine(sb.default_engine_params(**engine_kwargs(ds)))
     flats = []
     first = n_kfs - areas
@@ -199,6 +199,7 @@ def main():
     ap.add_argument("--kfs", type=int, default=700, help="keyframes of the tour the areas are snapshotted from")
     ap.add_argument("--ref-kfs", type=int, default=0, help="tour length of the CPU legs (default: same as --kfs, i.e. the very same problems)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tour-seed", type=int, default=1, help="seed of the tour geometry (1 = the workload every number in profiles/ is quoted on)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -221,7 +222,9 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    ds, eng, flats = build_problems(seed=1 + rank, areas=args.areas, n_kfs=args.kfs)
+    # weak scaling: every rank gets the SAME tour (seed 1: same shape of every local area, i.e. the same work per GPU) with
+    # its own observation-noise realisation; rank 0 is bit-identical to the single-GPU run
+    ds, eng, flats = build_problems(seed=args.tour_seed, areas=args.areas, n_kfs=args.kfs, noise_seed=None if rank == 0 else 1000 + rank)
     batch = sb.Batch(flats)
     stream = torch.cuda.current_stream()
     sp = stream.cuda_stream
@@ -304,6 +307,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.areas), "areas_per_gpu": args.areas, "tour_keyframes": args.kfs, "lm_trials_per_step_per_gpu": trials_per_step,
+                       "ranks": "same tour (seed 1) on every rank, independent observation noise per rank",
                        "l2": "flushed between timed iterations (256 MiB fill)", "timing": "CUDA events around each launch on the launching stream"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(batch.h2d_bytes), "d2h_bytes_per_step": int(batch.d2h_bytes)},
             "gpu_launches": int(batch.kernel_launches) * args.steps,

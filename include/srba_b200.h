@@ -175,10 +175,12 @@ int srba_b200_problem_plan(const srba_problem_t *in, int64_t out[8]);
 /* Host-only (tests): the symbolic factorisation the packer ships with a problem for the on-chip block-sparse L D L^t
  * solver -- 3x3 tiles numbered row-major (diagonal first, right-hand side as tile column NTR).  counts[4] = {NTR, tiles,
  * updates, fits}; row[4*(NTR+1)] = {first tile, end tile | has_superdiag<<30, first update, end update} per row;
- * tile_ij[tiles] = ti<<16|tj; src[tiles] = offset into the reduced blocks (bit 30: diagonal), -1 fill-in, -2-row right-hand
- * side; upd[2*updates] = {dst tile | tile(k,i)<<16, tile(k,j)}.  Call with NULL arrays to get the counts first. */
+ * tile_ij[tiles] = ti<<16|tj; src[tiles] = offset into the reduced blocks (bit 30: diagonal, bit 29: transposed), -1
+ * fill-in, -2-row right-hand side; upd[2*updates] = {dst tile | tile(k,i)<<16, tile(k,j)}; orow[NTR] = tile row in
+ * elimination order -> tile row in the caller's unknown order (identity unless the reference's order would overflow
+ * `max_tiles_on_chip`, then greedy minimum degree).  Call with NULL arrays to get the counts first. */
 int srba_b200_debug_ldl_schedule(const srba_problem_t *in, int32_t counts[4], int32_t *row, int32_t *tile_ij, int32_t *src, int32_t *upd,
-                                 int32_t cap_tiles, int32_t cap_upd);
+                                 int32_t *orow, int32_t cap_tiles, int32_t cap_upd, int32_t max_tiles_on_chip);
 
 const char *srba_b200_last_error(void);
 int srba_b200_device_count(void);

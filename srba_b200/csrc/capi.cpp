@@ -125,6 +125,7 @@ inline const void *src_of_blkF_col(const srba_problem_t &) { return nullptr; }
 inline const void *src_of_ldl_row(const srba_problem_t &) { return nullptr; }
 inline const void *src_of_ldl_tile_ij(const srba_problem_t &) { return nullptr; }
 inline const void *src_of_ldl_src(const srba_problem_t &) { return nullptr; }
+inline const void *src_of_ldl_orow(const srba_problem_t &) { return nullptr; }
 inline const void *src_of_ldl_upd(const srba_problem_t &) { return nullptr; }
 // pointer to the caller's array behind image slot `id` (NULL for the derived ones)
 const void *src_ptr(const srba_problem_t &p, int id) {
@@ -144,27 +145,100 @@ struct TileSymbolic {
 	std::vector<int32_t> rs;        // NTR+1: first tile of each row (row-major numbering, diagonal first, RHS last)
 	std::vector<int32_t> row;       // 4 per row (+ sentinel): {first tile, end tile | has_superdiag<<30, first update, end update}
 	std::vector<int32_t> tile_ij;   // ntiles: (ti<<16)|tj
-	std::vector<int32_t> src;       // ntiles: offset of the tile's (0,0) in the reduced blocks (bit 30: diagonal tile), -1 fill-in, -2-row right-hand side
+	std::vector<int32_t> src;       // ntiles: offset of the tile's (0,0) in the reduced blocks (bit 30: diagonal tile, bit 29: transposed), -1 fill-in, -2-row right-hand side
+	std::vector<int32_t> orow;      // NTR: tile row in elimination order -> tile row in the reference's unknown order
+	bool on_chip = false;           // the tiles fit the shared-memory budget (else they live in the L2-resident workspace)
 	std::vector<int32_t> upd_ptr;   // NTR+1
 	std::vector<int32_t> upd;       // 2 per update: {dst tile | tile(k,i)<<16, tile(k,j)}; the update of the next pivot block is implicit
 	bool ok = false;                // false: too large for the on-chip solver (schedule not built)
-	void clear() { rs.clear(); row.clear(); src.clear(); tile_ij.clear(); upd_ptr.clear(); upd.clear(); ok = false; }
+	void clear() { rs.clear(); row.clear(); src.clear(); orow.clear(); on_chip = false; tile_ij.clear(); upd_ptr.clear(); upd.clear(); ok = false; }
 };
-void symbolic_tiles(const srba_problem_t &p, int P, long max_tiles, TileSymbolic &sy) {
-	const int q = P / 3, ntr = q * p.n_unk_edges, ntc = ntr + 1;
+// Elimination order of the unknown edges (block level).  The reference's own order is kept whenever its fill fits on chip
+// (a relative graph-SLAM chain is block-banded in that order: no fill at all); areas with loop closures fill the whole band
+// between the two ends of every loop, so they are eliminated in greedy MINIMUM-DEGREE order instead.  Only the increment
+// must match the reference (any elimination order of an SPD system gives the same solution up to rounding, and meets a
+// non-positive pivot iff the matrix is not positive definite).
+// Returns the number of 3x3 tiles of the filled pattern (right-hand side column included) for `order`.
+long elimination_fill(const std::vector<uint64_t> &adj0, int np, int Wb, int q, const std::vector<int> *order, std::vector<int> *md_order) {
+	std::vector<uint64_t> adj(adj0);
+	std::vector<uint64_t> alive(Wb, 0);
+	for (int i = 0; i < np; i++) alive[i >> 6] |= 1ull << (i & 63);
+	long tiles = (long)q * np;  // right-hand side
+	for (int step = 0; step < np; step++) {
+		int pick = -1;
+		if (order) pick = (*order)[step];
+		else {
+			int best = 1 << 30;
+			for (int i = 0; i < np; i++) {
+				if (!(alive[i >> 6] >> (i & 63) & 1)) continue;
+				int d = 0;
+				for (int w = 0; w < Wb; w++) d += __builtin_popcountll(adj[(size_t)i * Wb + w] & alive[w]);
+				if (d < best) { best = d; pick = i; }
+			}
+			md_order->push_back(pick);
+		}
+		alive[pick >> 6] &= ~(1ull << (pick & 63));
+		std::vector<uint64_t> nb(Wb);
+		int deg = 0;
+		for (int w = 0; w < Wb; w++) { nb[w] = adj[(size_t)pick * Wb + w] & alive[w]; deg += __builtin_popcountll(nb[w]); }
+		tiles += (long)q * (q + 1) / 2 + (long)q * q * deg;
+		for (int w = 0; w < Wb; w++) {
+			uint64_t m = nb[w];
+			while (m) {
+				const int j = w * 64 + __builtin_ctzll(m);
+				m &= m - 1;
+				for (int w2 = 0; w2 < Wb; w2++) adj[(size_t)j * Wb + w2] |= nb[w2];
+				adj[(size_t)j * Wb + (j >> 6)] &= ~(1ull << (j & 63));
+			}
+		}
+	}
+	return tiles;
+}
+
+void symbolic_tiles(const srba_problem_t &p, int P, long max_tiles_on_chip, TileSymbolic &sy) {
+	const int q = P / 3, np = p.n_unk_edges, ntr = q * np, ntc = ntr + 1;
 	sy.clear();
 	sy.ntr = ntr;
-	if (ntr <= 0 || ntr >= 32768) return;
+	if (ntr <= 0 || ntr > 2048) return;
+	// ---- elimination order
+	const int Wb = (np + 63) / 64;
+	std::vector<uint64_t> adj((size_t)np * Wb, 0);
+	for (int b = 0; b < p.n_S; b++) {
+		const int r = p.S_row[b], c = p.S_col[b];
+		if (r == c) continue;
+		adj[(size_t)r * Wb + (c >> 6)] |= 1ull << (c & 63);
+		adj[(size_t)c * Wb + (r >> 6)] |= 1ull << (r & 63);
+	}
+	std::vector<int> perm(np);  // position in the elimination order -> unknown edge
+	std::iota(perm.begin(), perm.end(), 0);
+	long tiles = elimination_fill(adj, np, Wb, q, &perm, nullptr);
+	if (tiles > max_tiles_on_chip) {
+		std::vector<int> md;
+		const long tiles_md = elimination_fill(adj, np, Wb, q, nullptr, &md);
+		if (tiles_md < tiles) { perm = md; tiles = tiles_md; }
+	}
+	if (tiles > 32767) return;  // tile ids are packed in 15/16 bits; such systems use the blocked dense solver
+	sy.on_chip = tiles <= max_tiles_on_chip;
+	std::vector<int> inv(np);
+	for (int i = 0; i < np; i++) inv[perm[i]] = i;
+	sy.orow.resize(ntr);
+	for (int t = 0; t < ntr; t++) sy.orow[t] = q * perm[t / q] + t % q;
+	// ---- initial tile pattern in elimination order + where every tile comes from
 	const int W = (ntc + 63) / 64;
 	std::vector<uint64_t> rows((size_t)ntr * W, 0);
+	std::vector<int32_t> srcmap((size_t)ntr * ntc, -1);
 	auto setbit = [&](int r, int c) { rows[(size_t)r * W + (c >> 6)] |= 1ull << (c & 63); };
-	for (int r = 0; r < ntr; r++) { setbit(r, r); setbit(r, ntr); }
+	for (int r = 0; r < ntr; r++) { setbit(r, r); setbit(r, ntr); srcmap[(size_t)r * ntc + ntr] = -2 - sy.orow[r]; }
 	for (int b = 0; b < p.n_S; b++) {
-		const int br = p.S_row[b], bc = p.S_col[b];
+		const int pr = inv[p.S_row[b]], pc = inv[p.S_col[b]];
 		for (int a = 0; a < q; a++)
 			for (int c = 0; c < q; c++) {
-				const int ti = q * br + a, tj = q * bc + c;
-				if (ti <= tj) setbit(ti, tj);
+				const int32_t off = b * P * P + a * 3 * P + c * 3;  // sub-block (a,c) of the stored block (row <= col in the reference's order)
+				int ti = q * pr + a, tj = q * pc + c, flags = 0;
+				if (pr == pc) { if (a > c) continue; if (a == c) flags = 1 << 30; }
+				else if (pr > pc) { std::swap(ti, tj); flags = 1 << 29; }  // the tile is the TRANSPOSE of the stored sub-block
+				setbit(ti, tj);
+				srcmap[(size_t)ti * ntc + tj] = off | flags;
 			}
 	}
 	long total = 0;
@@ -187,7 +261,6 @@ void symbolic_tiles(const srba_problem_t &p, int P, long max_tiles, TileSymbolic
 			}
 		}
 		for (int w = 0; w < W; w++) total += __builtin_popcountll(rk[w]);
-		if (total > max_tiles) return;  // does not fit on chip
 	}
 	// numbering
 	sy.rs.assign(ntr + 1, 0);
@@ -231,17 +304,9 @@ void symbolic_tiles(const srba_problem_t &p, int P, long max_tiles, TileSymbolic
 		const bool has_sd = sy.rs[k] + 1 < sy.rs[k + 1] && (sy.tile_ij[sy.rs[k] + 1] & 0xffff) == k + 1 && k + 1 < ntr;
 		r[0] = sy.rs[k]; r[1] = sy.rs[k + 1] | (has_sd ? 1 << 30 : 0); r[2] = sy.upd_ptr[k]; r[3] = sy.upd_ptr[k + 1];
 	}
-	std::vector<int32_t> blk((size_t)p.n_unk_edges * p.n_unk_edges, -1);  // (block row, block col) -> reduced block
-	for (int b = 0; b < p.n_S; b++) blk[(size_t)p.S_row[b] * p.n_unk_edges + p.S_col[b]] = b;
 	sy.src.resize(sy.tile_ij.size());
-	for (size_t t = 0; t < sy.tile_ij.size(); t++) {
-		const int ti = sy.tile_ij[t] >> 16, tj = sy.tile_ij[t] & 0xffff;
-		if (tj == ntr) { sy.src[t] = -2 - ti; continue; }
-		const int br = ti / q, bc = tj / q;
-		const int32_t b = blk[(size_t)br * p.n_unk_edges + bc];
-		sy.src[t] = b < 0 ? -1 : (b * P * P + (ti - br * q) * 3 * P + (tj - bc * q) * 3) | (ti == tj ? 1 << 30 : 0);
-	}
-	sy.ok = sy.tile_ij.size() < 65535;
+	for (size_t t = 0; t < sy.tile_ij.size(); t++) sy.src[t] = srcmap[(size_t)(sy.tile_ij[t] >> 16) * ntc + (sy.tile_ij[t] & 0xffff)];
+	sy.ok = sy.tile_ij.size() <= 32767;
 }
 
 int model_index(const srba_model_t &m) {
@@ -267,16 +332,18 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 	const int model = model_index(p.model);
 	const SrbaKernelCfg cfg = srba_kernel_cfg(model);
 	if (!base) {  // layout pass: symbolic factorisation (reused by the copy pass)
-		const long max_tiles = std::min(32767L, ((long)cfg.smem_bytes / 2 / 8 - 37 - h.n_dense) / 12);  // tile ids are packed in 15/16 bits
+		// tiles may take up to 3/4 of the CTA's shared memory (other arrays then spill to the L2-resident workspace)
+		const long max_tiles = std::min(32767L, ((long)cfg.smem_bytes * 3 / 4 / 8 - 37 - h.n_dense) / 12);
 		if (max_tiles > 0) symbolic_tiles(p, P, max_tiles, sy);
 		else sy.clear();
 	}
 	static const bool force_blocked = [] { const char *e = std::getenv("SRBA_B200_SOLVER"); return e && std::string(e) == "blocked"; }();  // tests
-	const int reg_scratch = (sy.ok && !force_blocked) ? srba_chol_reg_scratch_doubles(model, h.n_dense, (int)sy.tile_ij.size()) : -1;
+	const int reg_scratch = (sy.ok && !force_blocked) ? srba_chol_reg_scratch_doubles(model, h.n_dense, sy.on_chip ? (int)sy.tile_ij.size() : 0) : -1;
 	uint64_t scratch_bytes;
 	if (reg_scratch >= 0) {
 		h.chol_mode = SRBA_CHOL_REG;
 		h.ldl_n_tiles = (int)sy.tile_ij.size();
+		h.ldl_tiles_in_ws = sy.on_chip ? 0 : 1;
 		scratch_bytes = (uint64_t)reg_scratch * 8;
 	} else {
 		h.chol_mode = SRBA_CHOL_BLOCKED;
@@ -300,7 +367,7 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 		c[SRBA_I_blkA_col] = p.n_blkA; c[SRBA_I_blkF_col] = p.n_blkF;
 		const bool reg = h.chol_mode == SRBA_CHOL_REG;
 		c[SRBA_I_ldl_row] = reg ? sy.row.size() : 0; c[SRBA_I_ldl_tile_ij] = reg ? sy.tile_ij.size() : 0;
-		c[SRBA_I_ldl_src] = reg ? sy.src.size() : 0; c[SRBA_I_ldl_upd] = reg ? sy.upd.size() : 0;
+		c[SRBA_I_ldl_src] = reg ? sy.src.size() : 0; c[SRBA_I_ldl_upd] = reg ? sy.upd.size() : 0; c[SRBA_I_ldl_orow] = reg ? sy.orow.size() : 0;
 	}
 	Layout L;
 	L.add(sizeof(DevProblem));
@@ -327,6 +394,7 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 			put<int32_t>(base, h.img_off[SRBA_I_ldl_row], sy.row.data(), sy.row.size());
 			put<int32_t>(base, h.img_off[SRBA_I_ldl_tile_ij], sy.tile_ij.data(), sy.tile_ij.size());
 			put<int32_t>(base, h.img_off[SRBA_I_ldl_src], sy.src.data(), sy.src.size());
+			put<int32_t>(base, h.img_off[SRBA_I_ldl_orow], sy.orow.data(), sy.orow.size());
 			put<int32_t>(base, h.img_off[SRBA_I_ldl_upd], sy.upd.data(), sy.upd.size());
 		}
 	}
@@ -351,6 +419,7 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 		w[SRBA_W_Sblk] = h.s_alias_hap ? 0 : (uint64_t)p.n_S * P * P * 8;
 		w[SRBA_W_grad] = (uint64_t)h.n_scalars * 8; w[SRBA_W_delta] = w[SRBA_W_grad];
 		w[SRBA_W_dense] = (h.chol_mode == SRBA_CHOL_BLOCKED || want_dense) ? (uint64_t)h.n_dense * h.ld_dense * 8 : 0;
+		w[SRBA_W_ldl_tiles] = (h.chol_mode == SRBA_CHOL_REG && h.ldl_tiles_in_ws) ? (uint64_t)h.ldl_n_tiles * 12 * 8 : 0;
 		w[SRBA_W_valid] = p.n_obs; w[SRBA_W_blk_ok] = p.n_blkA + p.n_blkF; w[SRBA_W_lm_inv] = p.n_unk_lms;
 		w[SRBA_W_slot_listed] = 2 * p.n_pairs; w[SRBA_W_pair_refresh] = p.n_pairs; w[SRBA_W_listed_idx] = (uint64_t)2 * p.n_pairs * 4; w[SRBA_W_refresh_idx] = (uint64_t)p.n_pairs * 4;
 	}
@@ -368,7 +437,7 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 			{0, SRBA_W_edge_cur}, {0, SRBA_W_edge_bak}, {0, SRBA_W_grad}, {0, SRBA_W_delta}, {0, SRBA_W_lm_cur}, {0, SRBA_W_lm_bak},
 			{0, SRBA_W_valid}, {0, SRBA_W_lm_inv}, {0, SRBA_W_pair_refresh}, {0, SRBA_W_slot_listed}, {0, SRBA_W_listed_idx}, {0, SRBA_W_refresh_idx},
 			{0, SRBA_W_resid0}, {0, SRBA_W_resid1}, {0, SRBA_W_slot}, {0, SRBA_W_HAp}, {0, SRBA_W_Hf}, {0, SRBA_W_Hf_inv},
-			{1, SRBA_I_ldl_row}, {1, SRBA_I_ldl_tile_ij}, {1, SRBA_I_ldl_upd}, {1, SRBA_I_ldl_src}, {1, SRBA_I_unk_edge}, {1, SRBA_I_unk_lm}, {1, SRBA_I_obs_slot}, {1, SRBA_I_obs_z}, {1, SRBA_I_obs_mult}, {1, SRBA_I_obs_lm},
+			{1, SRBA_I_ldl_row}, {1, SRBA_I_ldl_tile_ij}, {1, SRBA_I_ldl_upd}, {1, SRBA_I_ldl_src}, {1, SRBA_I_ldl_orow}, {1, SRBA_I_unk_edge}, {1, SRBA_I_unk_lm}, {1, SRBA_I_obs_slot}, {1, SRBA_I_obs_z}, {1, SRBA_I_obs_mult}, {1, SRBA_I_obs_lm},
 			{1, SRBA_I_pair_path_ptr}, {1, SRBA_I_path_edge}, {1, SRBA_I_path_dir},
 			{0, SRBA_W_Sblk}, {0, SRBA_W_HApf}, {0, SRBA_W_W}, {0, SRBA_W_JA}, {0, SRBA_W_JF}, {0, SRBA_W_slot_bak}, {0, SRBA_W_blk_ok},
 			{1, SRBA_I_colA_ptr}, {1, SRBA_I_blkA_obs}, {1, SRBA_I_blkA_col}, {1, SRBA_I_blkA_slotA}, {1, SRBA_I_blkA_slotD}, {1, SRBA_I_blkA_normal_dir},
@@ -697,14 +766,14 @@ void srba_b200_batch_algorithmic_bytes(const srba_batch_t *b, double out[5]) {
 	}
 }
 
-int srba_b200_debug_ldl_schedule(const srba_problem_t *in, int32_t counts[4], int32_t *row, int32_t *tile_ij, int32_t *src, int32_t *upd, int32_t cap_tiles,
-                                 int32_t cap_upd) {
+int srba_b200_debug_ldl_schedule(const srba_problem_t *in, int32_t counts[4], int32_t *row, int32_t *tile_ij, int32_t *src, int32_t *upd, int32_t *orow,
+                                 int32_t cap_tiles, int32_t cap_upd, int32_t max_tiles_on_chip) {
 	if (!in || !counts) return fail(SRBA_ERR_BAD_ARGUMENT, "null argument");
 	const int rc = validate(*in);
 	if (rc != SRBA_OK) return rc;
 	const int P = in->model.pose_kind == SRBA_POSE_SE2 ? 3 : 6;
 	TileSymbolic sy;
-	symbolic_tiles(*in, P, 32767, sy);
+	symbolic_tiles(*in, P, max_tiles_on_chip, sy);
 	counts[0] = sy.ntr; counts[1] = (int32_t)sy.tile_ij.size(); counts[2] = (int32_t)(sy.upd.size() / 2); counts[3] = sy.ok ? 1 : 0;
 	if (!sy.ok) return SRBA_OK;
 	if (row && tile_ij && src && upd) {
@@ -713,6 +782,7 @@ int srba_b200_debug_ldl_schedule(const srba_problem_t *in, int32_t counts[4], in
 		std::memcpy(tile_ij, sy.tile_ij.data(), sy.tile_ij.size() * 4);
 		std::memcpy(src, sy.src.data(), sy.src.size() * 4);
 		std::memcpy(upd, sy.upd.data(), sy.upd.size() * 4);
+		if (orow) std::memcpy(orow, sy.orow.data(), sy.orow.size() * 4);
 	}
 	return SRBA_OK;
 }

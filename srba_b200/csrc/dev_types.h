@@ -19,7 +19,8 @@
 // right-hand side as tile column NTR):  ldl_row[4*(NTR+1)] per row {first tile, end tile | has_superdiag<<30, first
 // update, end update} (+ sentinel);  ldl_tile_ij (ti<<16|tj);  ldl_src: where the tile comes from (offset into the reduced
 // blocks, -1 fill-in, -2-row right-hand side);  ldl_upd: per eliminated row the updates {dst tile | tile(k,i)<<16,
-// tile(k,j)} (the one that hits the next pivot block is implicit).
+// tile(k,j)} (the one that hits the next pivot block is implicit);  ldl_orow: tile row in elimination order -> tile row in the
+// reference's unknown order (the packer re-orders areas with loop closures by minimum degree).
 #define SRBA_IMG_ARRAYS(X)                                                                                              \
 	X(double, edge_pose) X(int32_t, unk_edge) X(double, lm_pos) X(int32_t, unk_lm)                                       \
 	X(int32_t, pair_path_ptr) X(int32_t, path_edge) X(uint8_t, path_dir)                                                 \
@@ -31,7 +32,7 @@
 	X(int32_t, HApf_row) X(int32_t, HApf_col) X(int32_t, HApf_term_ptr) X(int32_t, HApf_term_a) X(int32_t, HApf_term_f)  \
 	X(int32_t, rowApf_ptr) X(int32_t, colApf_ptr) X(int32_t, colApf_idx)                                                 \
 	X(int32_t, S_row) X(int32_t, S_col) X(int32_t, S_HAp) X(int32_t, S_term_ptr) X(int32_t, S_term_rowblk) X(int32_t, S_term_colblk) \
-	X(int32_t, blkA_col) X(int32_t, blkF_col) X(int32_t, ldl_row) X(int32_t, ldl_tile_ij) X(int32_t, ldl_src) X(int32_t, ldl_upd)
+	X(int32_t, blkA_col) X(int32_t, blkF_col) X(int32_t, ldl_row) X(int32_t, ldl_tile_ij) X(int32_t, ldl_src) X(int32_t, ldl_upd) X(int32_t, ldl_orow)
 
 // (type, name) of every workspace array.
 #define SRBA_WS_ARRAYS(X)                                                                                               \
@@ -39,7 +40,7 @@
 	X(double, JA) X(double, JF) X(double, resid0) X(double, resid1)                                                      \
 	X(double, HAp) X(double, HApf) X(double, Hf) X(double, Hf_inv) X(double, W) X(double, Sblk)                          \
 	X(double, grad) X(double, delta) X(double, dense)                                                                    \
-	X(int32_t, listed_idx) X(int32_t, refresh_idx)                                                                                             \
+	X(int32_t, listed_idx) X(int32_t, refresh_idx) X(double, ldl_tiles)                                                                                             \
 	X(uint8_t, valid) X(uint8_t, blk_ok) X(uint8_t, lm_inv) X(uint8_t, slot_listed) X(uint8_t, pair_refresh)
 
 enum {
@@ -72,6 +73,7 @@ struct DevProblem {
 	int32_t chol_mode;   // SRBA_CHOL_*
 	int32_t panel_cap;   // SRBA_CHOL_BLOCKED: columns of the staged 8-row panel that fit the scratch
 	int32_t ldl_n_tiles; // SRBA_CHOL_REG: 3x3 tiles of the filled pattern incl. the right-hand-side column
+	int32_t ldl_tiles_in_ws; // 1: the tiles do not fit on chip and live in the workspace array ldl_tiles (L2-resident)
 	int32_t s_alias_hap; // 1: no Schur terms and S block b == H_Ap block b -> the reduced blocks ARE the H_Ap blocks
 	uint32_t sm_scratch; // byte offset of the Cholesky scratch inside the CTA's dynamic shared memory
 	uint32_t sm_bytes;   // dynamic shared memory this problem uses (scratch + arena)
@@ -102,7 +104,7 @@ extern "C" {
 // model: 0 = SE2+RelativePoses2D, 1 = SE3+Cartesian3D, 2 = SE3+Mono, 3 = SE3+Stereo
 SrbaKernelCfg srba_kernel_cfg(int model);
 // doubles of shared-memory scratch the register-resident solver needs; <0 when the filled pattern does not fit the tiles
-int srba_chol_reg_scratch_doubles(int model, int n_dense, int n_tiles);
+int srba_chol_reg_scratch_doubles(int model, int n_dense, int n_tiles_on_chip);
 #ifdef __cplusplus
 }
 #endif

@@ -1002,11 +1002,12 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 	const View v = vs;
 	const int n = v.h->n_dense, ntiles = v.h->ldl_n_tiles;
 	const int NTR = n / 3;
-	double *tile = scr;                        // ntiles x 12
-	double *sInv = tile + 12 * (size_t)ntiles; // 3 x 12 : inverse pivot blocks of rows k-1, k, k+1 (slot = row % 3)
+	const bool tiles_in_ws = v.h->ldl_tiles_in_ws != 0;
+	double *tile = tiles_in_ws ? v.ldl_tiles : scr;                    // ntiles x 12 (on chip unless the pattern is too large)
+	double *sInv = tiles_in_ws ? scr : scr + 12 * (size_t)ntiles;      // 3 x 12 : inverse pivot blocks of rows k-1, k, k+1 (slot = row % 3)
 	double *sAcc = sInv + 36;                  // 3*NTR : backward-pass accumulators
 	const int4 *rowinfo = reinterpret_cast<const int4 *>(v.ldl_row);  // {first tile, end tile | has_superdiag << 30, first update, end update}
-	const int32_t *tij = v.ldl_tile_ij, *upd = v.ldl_upd, *src = v.ldl_src;
+	const int32_t *tij = v.ldl_tile_ij, *upd = v.ldl_upd, *src = v.ldl_src, *orow = v.ldl_orow;
 	const int tid = threadIdx.x, NT = LM_THREADS;
 	const int lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
 	const int iwarp = nwarps - 1;              // the warp that carries the pivot chain (its lanes 0..8)
@@ -1030,7 +1031,7 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 	// other warps gather the remaining tiles
 	if (warp == iwarp) {
 		if (lane == 0) sh.chol_ok = 1;
-		if (lane < 9) tile[eo] = v.S[(src[0] & 0x3fffffff) + wa * P + wb] + (wa == wb ? lambda : 0.0);
+		if (lane < 9) tile[eo] = v.S[(src[0] & 0x1fffffff) + wa * P + wb] + (wa == wb ? lambda : 0.0);
 		__syncwarp();
 		if (lane < 9) invert_pivot(tile, sInv);
 	}
@@ -1043,7 +1044,7 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 		for (int tl = 1 + 3 * warp + wg; tl < ntiles; tl += 3 * nwarps) {
 			const int so = src[tl];
 			double val = 0.0;
-			if (so >= 0) val = v.S[(so & 0x3fffffff) + wa * P + wb] + ((so >> 30) ? dl : 0.0);
+			if (so >= 0) val = v.S[(so & 0x1fffffff) + ((so >> 29) & 1 ? wb * P + wa : wa * P + wb)] + ((so >> 30) ? dl : 0.0);
 			else if (so <= -2 && wb == 0) val = v.grad[3 * (-so - 2) + wa];
 			tile[tl * 12 + eo] = val;
 		}
@@ -1192,7 +1193,7 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 	}
 	__syncthreads();
 #pragma unroll 1
-	for (int i = tid; i < n; i += NT) v.delta[i] = sAcc[i];
+	for (int i = tid; i < n; i += NT) { const int r = i / 3; v.delta[3 * orow[r] + (i - 3 * r)] = sAcc[i]; }  // back to the reference's unknown order
 	__syncthreads();
 #ifdef SRBA_SOLVER_TIMERS
 	if (tid == 0) {
@@ -1623,13 +1624,13 @@ extern "C" SrbaKernelCfg srba_kernel_cfg(int model) {
 	c.smem_bytes = model == 0 ? 108 * 1024 : 220 * 1024;
 	return c;
 }
-// Doubles of shared-memory scratch of the on-chip solver for `n_tiles` 3x3 tiles, or -1 when they exceed the budget
-// reserved for the solver (half of the CTA's dynamic shared memory; larger systems use the blocked solver).
-extern "C" int srba_chol_reg_scratch_doubles(int model, int n_dense, int n_tiles) {
+// Doubles of shared-memory scratch of the block-sparse solver with `n_tiles_on_chip` 3x3 tiles kept in shared memory (0:
+// the tiles live in the L2-resident workspace), or -1 when even that does not fit.
+extern "C" int srba_chol_reg_scratch_doubles(int model, int n_dense, int n_tiles_on_chip) {
 	const SrbaKernelCfg c = srba_kernel_cfg(model);
 	const int NTR = n_dense / 3;
-	const long need = 12L * n_tiles + 36 + 3L * NTR + 1;
-	if (n_tiles >= 65535 || need * 8 > c.smem_bytes / 2) return -1;
+	const long need = 12L * n_tiles_on_chip + 36 + 3L * NTR + 1;
+	if (need * 8 > (long)c.smem_bytes * 7 / 8) return -1;
 	return (int)need;
 }
 

@@ -25,13 +25,16 @@ def wrap(a):
 
 
 def graphslam_se2_tour(n_kfs=3000, seed=1, cell=100.0, ncells=3, step=2.0, max_turn_deg=30.0, sensor_range=9.0, sigma_xy=0.001,
-                       sigma_yaw_deg=0.2, add_noise=True):
+                       sigma_yaw_deg=0.2, add_noise=True, noise_seed=None):
     """G1: relative SE(2) graph-SLAM on a corridor tour of a `ncells` x `ncells` grid of `cell`-metre blocks
     (mirrors datasets/world-2d-30k-landmarks.wrl:8-53 and world-2d-30k-rel-graph-slam.cfg:26-27,44-45): 2 m / <=30 deg
     steps, each keyframe observes every earlier keyframe within `sensor_range` as a relative pose
     (CDatasetParser_RelGraphSLAM2D.h:30-43), Gaussian noise as `srba-slam --noise 0.001 --noise-ang 0.2 --add-noise`.
     Each keyframe's list starts with its own fixed fake landmark (srba-run-generic-impl.h:370-377)."""
     rng = np.random.default_rng(seed)
+    # noise_seed: draw the observation noise from its own stream, so that several runs share the tour (hence the shape of
+    # every local area) and differ only in the noise realisation; None keeps the single stream of the original generator
+    nrng = rng if noise_seed is None else np.random.default_rng(noise_seed)
     nodes = [(i * cell, j * cell) for i in range(ncells + 1) for j in range(ncells + 1)]
 
     def neighbours(n):
@@ -76,7 +79,7 @@ def graphslam_se2_tour(n_kfs=3000, seed=1, cell=100.0, ncells=3, step=2.0, max_t
             if math.hypot(gt[j, 0] - gt[k, 0], gt[j, 1] - gt[k, 1]) < sensor_range:
                 rel = se2_compose(inv_k, gt[j])
                 if add_noise:
-                    rel = rel + np.array([rng.normal(0, sigma_xy), rng.normal(0, sigma_xy), rng.normal(0, sig_yaw)])
+                    rel = rel + np.array([nrng.normal(0, sigma_xy), nrng.normal(0, sigma_xy), nrng.normal(0, sig_yaw)])
                 ids.append(j)
                 obs.append([rel[0], rel[1], rel[2]])
                 fixed.append(0)

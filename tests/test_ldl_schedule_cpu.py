@@ -13,20 +13,21 @@ from srba_b200 import _capi as K
 from srba_b200 import datasets as D
 
 
-def schedule(flat):
+def schedule(flat, max_on_chip=32767):
     L = K.lib()
     counts = (C.c_int32 * 4)()
-    assert L.srba_b200_debug_ldl_schedule(flat.problem, counts, None, None, None, None, 0, 0) == 0
+    assert L.srba_b200_debug_ldl_schedule(flat.problem, counts, None, None, None, None, None, 0, 0, max_on_chip) == 0
     ntr, ntiles, nupd, ok = list(counts)
     assert ok == 1
     row = np.zeros(4 * (ntr + 1), np.int32); tij = np.zeros(ntiles, np.int32); src = np.zeros(ntiles, np.int32); upd = np.zeros(2 * nupd, np.int32)
+    orow = np.zeros(ntr, np.int32)
     p32 = C.POINTER(C.c_int32)
     assert L.srba_b200_debug_ldl_schedule(flat.problem, counts, row.ctypes.data_as(p32), tij.ctypes.data_as(p32), src.ctypes.data_as(p32),
-                                          upd.ctypes.data_as(p32), ntiles, nupd) == 0
-    return ntr, row.reshape(-1, 4), tij, src, upd.reshape(-1, 2)
+                                          upd.ctypes.data_as(p32), orow.ctypes.data_as(p32), ntiles, nupd, max_on_chip) == 0
+    return ntr, row.reshape(-1, 4), tij, src, upd.reshape(-1, 2), orow
 
 
-def emulate(flat, P, rng):
+def emulate(flat, P, rng, max_on_chip=32767):
     """Random SPD blocks with the problem's reduced-system pattern -> solve through the schedule and densely."""
     p = flat.p
     n_p, n = p.n_unk_edges, P * p.n_unk_edges
@@ -46,22 +47,25 @@ def emulate(flat, P, rng):
     g = rng.normal(size=n)
     lam = 0.37
     Sflat = blocks.reshape(-1)
-    ntr, row, tij, src, upd = schedule(flat)
+    ntr, row, tij, src, upd, orow = schedule(flat, max_on_chip)
+    assert sorted(orow.tolist()) == list(range(ntr))
     assert ntr == n // 3
     tiles = np.zeros((len(tij), 3, 3))
     for t in range(len(tij)):
         ti, tj = tij[t] >> 16, tij[t] & 0xffff
         assert ti <= tj <= ntr
         if src[t] >= 0:
-            off = src[t] & 0x3fffffff
+            off = src[t] & 0x1fffffff
             for a in range(3):
                 tiles[t, a] = Sflat[off + a * P: off + a * P + 3]
+            if (src[t] >> 29) & 1:
+                tiles[t] = tiles[t].T.copy()
             assert bool(src[t] >> 30) == (ti == tj)
             if ti == tj:
                 tiles[t] += lam * np.eye(3)
         elif src[t] <= -2:
-            assert tj == ntr and -src[t] - 2 == ti
-            tiles[t, :, 0] = g[3 * ti:3 * ti + 3]
+            assert tj == ntr and -src[t] - 2 == orow[ti]
+            tiles[t, :, 0] = g[3 * orow[ti]:3 * orow[ti] + 3]
     # rows are contiguous, diagonal first, right-hand side last
     for k in range(ntr):
         r0, r1 = row[k, 0], row[k, 1] & 0x3fffffff
@@ -94,7 +98,10 @@ def emulate(flat, P, rng):
             acc -= tiles[t] @ x[tij[t] & 0xffff]
         x[k] = acc
     ref = np.linalg.solve(A + lam * np.eye(n), g)
-    return x.reshape(-1), ref, len(tij), p.n_S
+    xo = np.zeros(n)
+    for t in range(ntr):
+        xo[3 * orow[t]:3 * orow[t] + 3] = x[t]   # back to the caller's unknown order
+    return xo, ref, len(tij), p.n_S, orow
 
 
 def flats_se2():
@@ -128,8 +135,12 @@ def test_schedule_solves_the_reduced_system(kind):
     flats, P = (flats_se2(), 3) if kind == "se2" else (flats_se3(), 6)
     assert flats
     for fl in flats:
-        x, ref, ntiles, n_S = emulate(fl, P, rng)
+        x, ref, ntiles, n_S, orow = emulate(fl, P, rng)
         assert np.abs(x - ref).max() <= 1e-10 * max(1.0, np.abs(ref).max())
+        assert orow.tolist() == list(range(len(orow)))       # the reference's own order is kept when its fill fits on chip
+        # a tiny on-chip budget forces the minimum-degree re-ordering: same solution, tiles from transposed blocks included
+        x2, ref2, ntiles2, _, orow2 = emulate(fl, P, rng, max_on_chip=8)
+        assert np.abs(x2 - ref2).max() <= 1e-10 * max(1.0, np.abs(ref2).max())
 
 
 def test_plan_fits_the_shared_memory_budget():

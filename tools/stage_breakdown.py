@@ -1,4 +1,6 @@
-"""Prints where the LM kernel spends its cycles (per stage, measured by the kernel with clock64) for the bench batch."""
+"""Prints where the LM kernel spends its cycles (per stage, measured by the kernel with clock64) for the bench batch.
+Needs a library built with the probes:  SRBA_SOLVER_TIMERS=1 python -m srba_b200.build --force
+Usage: python tools/stage_breakdown.py [areas] [tour_keyframes] [tour_seed]"""
 import sys
 
 import numpy as np
@@ -9,7 +11,8 @@ import srba_b200 as sb
 
 areas = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 kfs = int(sys.argv[2]) if len(sys.argv) > 2 else 700
-ds, eng, flats = bench.build_problems(1, areas, kfs)
+seed = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+ds, eng, flats = bench.build_problems(seed, areas, kfs)
 b = sb.Batch(flats)
 b.upload(); b.run(); b.download()
 import torch
