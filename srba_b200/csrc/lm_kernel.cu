@@ -993,6 +993,66 @@ __device__ __noinline__ bool stage_cholesky(const View &vs, Shared &sh, double *
 // memory, column-major 3x3 padded to 3x4 so that a column is one 16-byte + one 8-byte load.
 // The backward pass  x_j = z_j - sum W(j,.) x  runs column by column (one barrier each), again one element per lane.
 // Returns false when a pivot block is not positive definite (Eigen::LLT "if (x<=0) return k", lev-marq_solvers.h:527-534).
+// Backward pass of the block-sparse solver as a REGISTER WAVEFRONT carried by one warp: lane l owns rows l, l+32, ...
+// (R rows per lane).  Step j: the owner of x_j broadcasts it by shuffle, every lane whose rows hold a tile in column j
+// folds it into that row's accumulator (the W tile was fetched while waiting).  No barrier, no shared-memory round trip.
+template <int R>
+__device__ __forceinline__ void ldl_backward_wavefront(const double *tile, const int4 *rowinfo, const int32_t *tij, double *sX, int NTR, int lane) {
+	int r0[R], m[R], nxt_col[R];
+	double z[R][3], w[R][9];
+#pragma unroll
+	for (int s2 = 0; s2 < R; s2++) {
+		const int k = lane + 32 * s2;
+		r0[s2] = 0; m[s2] = 0; nxt_col[s2] = -1;
+		z[s2][0] = z[s2][1] = z[s2][2] = 0.0;
+#pragma unroll
+		for (int e = 0; e < 9; e++) w[s2][e] = 0.0;
+		if (k < NTR) {
+			const int4 rk = rowinfo[k];
+			const int r1 = rk.y & 0x3fffffff;
+			r0[s2] = rk.x; m[s2] = r1 - rk.x - 2;  // off-diagonal tiles without the right-hand side
+			const double *zz = tile + (r1 - 1) * 12;
+			z[s2][0] = zz[0]; z[s2][1] = zz[1]; z[s2][2] = zz[2];
+		}
+	}
+	auto fetch = [&](int s2) {  // the row's next tile, walking it from the last column down
+		if (m[s2] > 0) {
+			const int tl = r0[s2] + m[s2];
+			nxt_col[s2] = tij[tl] & 0xffff;
+			const double *Wt = tile + tl * 12;
+#pragma unroll
+			for (int b = 0; b < 3; b++)
+#pragma unroll
+				for (int a = 0; a < 3; a++) w[s2][b * 3 + a] = Wt[b * 4 + a];
+			m[s2]--;
+		} else nxt_col[s2] = -1;
+	};
+#pragma unroll
+	for (int s2 = 0; s2 < R; s2++) fetch(s2);
+#pragma unroll 1
+	for (int j = NTR - 1; j >= 0; j--) {
+		const int js = j >> 5, jl = j & 31;
+		double y0 = z[0][0], y1 = z[0][1], y2 = z[0][2];
+#pragma unroll
+		for (int s2 = 1; s2 < R; s2++)
+			if (js == s2) { y0 = z[s2][0]; y1 = z[s2][1]; y2 = z[s2][2]; }
+		const double x0 = __shfl_sync(0xffffffffu, y0, jl), x1 = __shfl_sync(0xffffffffu, y1, jl), x2 = __shfl_sync(0xffffffffu, y2, jl);
+#pragma unroll
+		for (int s2 = 0; s2 < R; s2++)
+			if (nxt_col[s2] == j) {
+				z[s2][0] -= w[s2][0] * x0 + w[s2][3] * x1 + w[s2][6] * x2;
+				z[s2][1] -= w[s2][1] * x0 + w[s2][4] * x1 + w[s2][7] * x2;
+				z[s2][2] -= w[s2][2] * x0 + w[s2][5] * x1 + w[s2][8] * x2;
+				fetch(s2);
+			}
+	}
+#pragma unroll
+	for (int s2 = 0; s2 < R; s2++) {
+		const int k = lane + 32 * s2;
+		if (k < NTR) { sX[3 * k] = z[s2][0]; sX[3 * k + 1] = z[s2][1]; sX[3 * k + 2] = z[s2][2]; }
+	}
+}
+
 template <int P>
 __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, double *scr, double lambda) {
 	static_assert(P % 3 == 0, "tiles are 3x3");
@@ -1054,28 +1114,40 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 	const long long c_loop = clock64();
 #endif
 	int prev_r0 = 0, prev_r1 = 0;  // tiles of row k-1 still to be turned into W
+	int2 u_first = make_int2(0, 0);
+	if (tid < (ri.w - ri.z) * 9) u_first = *reinterpret_cast<const int2 *>(upd + 2 * (ri.z + tid / 9));
 #pragma unroll 1
 	for (int k = 0; k <= NTR; k++) {
 		const int r0 = ri.x, r1 = ri.y & 0x3fffffff, has_sd = ri.y >> 30, u0 = ri.z, nitems = (ri.w - ri.z) * 9;
 		const int4 rnn = rowinfo[k + 2 < NTR ? k + 2 : NTR];  // two rows ahead: off the critical path; row NTR is a sentinel
 		const double *Ik = sInv + (k % 3) * 12;
-		// ---- U: T(i,j) -= T(k,i)^t inv(D_k) T(k,j) for the pairs of row-k tiles (x: dst | tile(k,i) << 16, y: tile(k,j))
+		// ---- U: T(i,j) -= T(k,i)^t inv(D_k) T(k,j) for the pairs of row-k tiles (x: dst | tile(k,i) << 16, y: tile(k,j)).
+		// The update descriptors are fetched one item ahead (the first one of a row before the previous row's barrier):
+		// for large areas the list lives in L2 and its latency would otherwise sit on every iteration.
+		{
+			int2 u = u_first;
 #pragma unroll 1
-		for (int q = tid; q < nitems; q += NT) {
-			const int ui = q / 9, e = q - ui * 9, b = e / 3, a = e - b * 3;
-			const int2 u = *reinterpret_cast<const int2 *>(upd + 2 * (u0 + ui));
-			const double *Ti = tile + (u.x >> 16) * 12 + a * 4;
-			const double *Tj = tile + u.y * 12 + b * 4;
-			const double2 p01 = *reinterpret_cast<const double2 *>(Ti), t01 = *reinterpret_cast<const double2 *>(Tj);
-			const double p2 = Ti[2], t2 = Tj[2];
-			const double2 i0 = *reinterpret_cast<const double2 *>(Ik), i1 = *reinterpret_cast<const double2 *>(Ik + 4);
-			const double i02 = Ik[2], i12 = Ik[6], i22 = Ik[10];
-			const double w0 = i0.x * t01.x + i0.y * t01.y + i02 * t2;
-			const double w1 = i0.y * t01.x + i1.y * t01.y + i12 * t2;
-			const double w2 = i02 * t01.x + i12 * t01.y + i22 * t2;
-			double *dst = tile + (u.x & 0xffff) * 12 + b * 4 + a;
-			*dst = *dst - p01.x * w0 - p01.y * w1 - p2 * w2;
+			for (int q = tid; q < nitems; q += NT) {
+				const int ui = q / 9, e = q - ui * 9, b = e / 3, a = e - b * 3;
+				int2 un = u;
+				if (q + NT < nitems) un = *reinterpret_cast<const int2 *>(upd + 2 * (u0 + (q + NT) / 9));
+				const double *Ti = tile + (u.x >> 16) * 12 + a * 4;
+				const double *Tj = tile + u.y * 12 + b * 4;
+				const double2 p01 = *reinterpret_cast<const double2 *>(Ti), t01 = *reinterpret_cast<const double2 *>(Tj);
+				const double p2 = Ti[2], t2 = Tj[2];
+				const double2 i0 = *reinterpret_cast<const double2 *>(Ik), i1 = *reinterpret_cast<const double2 *>(Ik + 4);
+				const double i02 = Ik[2], i12 = Ik[6], i22 = Ik[10];
+				const double w0 = i0.x * t01.x + i0.y * t01.y + i02 * t2;
+				const double w1 = i0.y * t01.x + i1.y * t01.y + i12 * t2;
+				const double w2 = i02 * t01.x + i12 * t01.y + i22 * t2;
+				double *dst = tile + (u.x & 0xffff) * 12 + b * 4 + a;
+				*dst = *dst - p01.x * w0 - p01.y * w1 - p2 * w2;
+				u = un;
+			}
 		}
+		// first update descriptor of the NEXT row, in the shadow of this row's barrier
+		u_first = make_int2(0, 0);
+		if (tid < (rn.w - rn.z) * 9) u_first = *reinterpret_cast<const int2 *>(upd + 2 * (rn.z + tid / 9));
 		// ---- P: the next pivot block gets its row-k update from the super-diagonal tile and is inverted right away
 		if (warp == iwarp) {
 			if (k + 1 < NTR) {
@@ -1124,48 +1196,10 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 	// carried by ONE warp with warp-level synchronisation only (a CTA barrier per row costs ~400 cycles here).
 	if (warp == 0) {
 		double *sX = sAcc;
-		if (NTR <= 32) {
-			// register wavefront: lane k owns row k.  Step j: the owner of x_j broadcasts it by shuffle, every lane whose row
-			// holds a tile in column j folds it into its accumulator (its W tile was fetched while waiting).
-			const int k = lane;
-			int r0 = 0, m = 0;
-			double z0 = 0, z1 = 0, z2 = 0;
-			if (k < NTR) {
-				const int4 rk = rowinfo[k];
-				const int r1 = rk.y & 0x3fffffff;
-				r0 = rk.x; m = r1 - r0 - 2;  // off-diagonal tiles without the right-hand side
-				const double *z = tile + (r1 - 1) * 12;
-				z0 = z[0]; z1 = z[1]; z2 = z[2];
-			}
-			int nxt_col = -1;
-			double w[9];
-#pragma unroll
-			for (int e = 0; e < 9; e++) w[e] = 0.0;
-			auto fetch = [&]() {  // the lane's next tile, walking its row from the last column down
-				if (m > 0) {
-					const int tl = r0 + m;
-					nxt_col = tij[tl] & 0xffff;
-					const double *Wt = tile + tl * 12;
-#pragma unroll
-					for (int b = 0; b < 3; b++)
-#pragma unroll
-						for (int a = 0; a < 3; a++) w[b * 3 + a] = Wt[b * 4 + a];
-					m--;
-				} else nxt_col = -1;
-			};
-			fetch();
-#pragma unroll 1
-			for (int j = NTR - 1; j >= 0; j--) {
-				const double x0 = __shfl_sync(0xffffffffu, z0, j), x1 = __shfl_sync(0xffffffffu, z1, j), x2 = __shfl_sync(0xffffffffu, z2, j);
-				if (nxt_col == j) {
-					z0 -= w[0] * x0 + w[3] * x1 + w[6] * x2;
-					z1 -= w[1] * x0 + w[4] * x1 + w[7] * x2;
-					z2 -= w[2] * x0 + w[5] * x1 + w[8] * x2;
-					fetch();
-				}
-			}
-			if (k < NTR) { sX[3 * k] = z0; sX[3 * k + 1] = z1; sX[3 * k + 2] = z2; }
-		} else {
+		if (NTR <= 32) ldl_backward_wavefront<1>(tile, rowinfo, tij, sX, NTR, lane);
+		else if (NTR <= 64) ldl_backward_wavefront<2>(tile, rowinfo, tij, sX, NTR, lane);
+		else if (NTR <= 128) ldl_backward_wavefront<4>(tile, rowinfo, tij, sX, NTR, lane);
+		else {
 			// general size: lane (a, t) multiplies row a of the t-th tile of the row, a 3-step butterfly sums over the tiles
 			const int a = lane >> 3, t8 = lane & 7;
 #pragma unroll 1

@@ -267,3 +267,14 @@ def test_error_codes():
     with pytest.raises(K.SrbaError) as ei:
         sb.optimize(flat)
     assert ei.value.code == K.ERR_RANK_DEFICIENT
+
+
+def test_se2_loop_closure_areas_parity():
+    """A tour that revisits its own path: local areas reach ~90 unknown edges with loop closures, the reference's unknown
+    order would fill the whole band, so the packer eliminates in minimum-degree order (and keeps the tiles in the L2
+    workspace when they exceed the on-chip budget).  Same bars as the chain-like tour: indices bit-exact, increments 1e-6."""
+    ds = D.graphslam_se2_tour(640, seed=2)
+    kw = dict(S2, noise_lambda=D.se2_noise_lambda(ds["sigma_xy"], ds["sigma_yaw"]))
+    eo, ep, worst, ns = run_parallel(kw, ds["frames"], check_state_every=40)
+    print("loop-closure tour: worst relative increment error %.3e over %d decision-comparable trials" % (worst, ns))
+    assert ns > 500
