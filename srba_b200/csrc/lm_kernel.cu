@@ -560,29 +560,34 @@ __device__ __noinline__ void stage_hessian(const View &vs) {
 		if (it < nAp) {
 			const int blk = it / (P * P), e = it % (P * P), a = e / P, b = e % P;
 			double s = 0;
+			// terms are added in list order (== the reference's); an invalid row contributes an exact +0.0, so the loads of
+			// several terms can be in flight at once (for large areas J lives in L2)
+#pragma unroll 4
 			for (int t = v.HAp_term_ptr[blk]; t < v.HAp_term_ptr[blk + 1]; t++) {
 				const int ba = v.HAp_term_a[t], bb = v.HAp_term_b[t];
-				if (!v.valid[v.blkA_obs[ba]]) continue;
-				s += jtj_elem<O>(h, v.JA + (size_t)ba * O * P, P, a, v.JA + (size_t)bb * O * P, P, b);
+				const double term = jtj_elem<O>(h, v.JA + (size_t)ba * O * P, P, a, v.JA + (size_t)bb * O * P, P, b);
+				s += v.valid[v.blkA_obs[ba]] ? term : 0.0;
 			}
 			v.HAp[it] = do_scale ? s * scale : s;
 		} else if (it < nAp + nApf) {
 			const int j = it - nAp;
 			const int blk = j / (P * 3), e = j % (P * 3), a = e / 3, b = e % 3;
 			double s = 0;
+#pragma unroll 4
 			for (int t = v.HApf_term_ptr[blk]; t < v.HApf_term_ptr[blk + 1]; t++) {
 				const int ba = v.HApf_term_a[t], bf = v.HApf_term_f[t];
-				if (!v.valid[v.blkA_obs[ba]]) continue;
-				s += jtj_elem<O>(h, v.JA + (size_t)ba * O * P, P, a, v.JF + (size_t)bf * O * 3, 3, b);
+				const double term = jtj_elem<O>(h, v.JA + (size_t)ba * O * P, P, a, v.JF + (size_t)bf * O * 3, 3, b);
+				s += v.valid[v.blkA_obs[ba]] ? term : 0.0;
 			}
 			v.HApf[j] = do_scale ? s * scale : s;
 		} else {
 			const int j = it - nAp - nApf;
 			const int k = j / 9, e = j % 9, a = e / 3, b = e % 3;
 			double s = 0;
+#pragma unroll 4
 			for (int bf = v.colF_ptr[k]; bf < v.colF_ptr[k + 1]; bf++) {
-				if (!v.valid[v.blkF_obs[bf]]) continue;
-				s += jtj_elem<O>(h, v.JF + (size_t)bf * O * 3, 3, a, v.JF + (size_t)bf * O * 3, 3, b);
+				const double term = jtj_elem<O>(h, v.JF + (size_t)bf * O * 3, 3, a, v.JF + (size_t)bf * O * 3, 3, b);
+				s += v.valid[v.blkF_obs[bf]] ? term : 0.0;
 			}
 			v.Hf[j] = do_scale ? s * scale : s;
 		}
@@ -805,12 +810,13 @@ __device__ __noinline__ void stage_schur(const View &vs, double lambda) {
 			const int blk = it / (P * P), e = it % (P * P), a = e / P, b = e % P;
 			const int hb = v.S_HAp[blk];
 			double s = hb >= 0 ? v.HAp[(size_t)hb * P * P + e] : 0.0;
+#pragma unroll 4
 			for (int t = v.S_term_ptr[blk]; t < v.S_term_ptr[blk + 1]; t++) {
 				const int rb = v.S_term_rowblk[t], cb = v.S_term_colblk[t];
-				if (!v.lm_inv[v.HApf_col[rb]]) continue;
 				const double *Wr = v.W + (size_t)rb * P * 3;
 				const double *Hc = v.HApf + (size_t)cb * P * 3;
-				s -= Wr[a * 3 + 0] * Hc[b * 3 + 0] + Wr[a * 3 + 1] * Hc[b * 3 + 1] + Wr[a * 3 + 2] * Hc[b * 3 + 2];
+				const double term = Wr[a * 3 + 0] * Hc[b * 3 + 0] + Wr[a * 3 + 1] * Hc[b * 3 + 1] + Wr[a * 3 + 2] * Hc[b * 3 + 2];
+				s -= v.lm_inv[v.HApf_col[rb]] ? term : 0.0;  // non-invertible landmarks are skipped (schur.h:228): exact -0.0
 			}
 			v.Sblk[it] = s;
 		} else {
@@ -1122,15 +1128,13 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 		const int4 rnn = rowinfo[k + 2 < NTR ? k + 2 : NTR];  // two rows ahead: off the critical path; row NTR is a sentinel
 		const double *Ik = sInv + (k % 3) * 12;
 		// ---- U: T(i,j) -= T(k,i)^t inv(D_k) T(k,j) for the pairs of row-k tiles (x: dst | tile(k,i) << 16, y: tile(k,j)).
-		// The update descriptors are fetched one item ahead (the first one of a row before the previous row's barrier):
-		// for large areas the list lives in L2 and its latency would otherwise sit on every iteration.
+		// The first update descriptor of a row is fetched before the previous row's barrier, and two items are in flight per
+		// thread: for large areas the lists and tiles live in L2 and their latency would otherwise sit on every iteration.
 		{
-			int2 u = u_first;
-#pragma unroll 1
+#pragma unroll 2
 			for (int q = tid; q < nitems; q += NT) {
 				const int ui = q / 9, e = q - ui * 9, b = e / 3, a = e - b * 3;
-				int2 un = u;
-				if (q + NT < nitems) un = *reinterpret_cast<const int2 *>(upd + 2 * (u0 + (q + NT) / 9));
+				const int2 u = q == tid ? u_first : *reinterpret_cast<const int2 *>(upd + 2 * (u0 + ui));
 				const double *Ti = tile + (u.x >> 16) * 12 + a * 4;
 				const double *Tj = tile + u.y * 12 + b * 4;
 				const double2 p01 = *reinterpret_cast<const double2 *>(Ti), t01 = *reinterpret_cast<const double2 *>(Tj);
@@ -1142,7 +1146,6 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 				const double w2 = i02 * t01.x + i12 * t01.y + i22 * t2;
 				double *dst = tile + (u.x & 0xffff) * 12 + b * 4 + a;
 				*dst = *dst - p01.x * w0 - p01.y * w1 - p2 * w2;
-				u = un;
 			}
 		}
 		// first update descriptor of the NEXT row, in the shadow of this row's barrier
@@ -1200,15 +1203,33 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 		else if (NTR <= 64) ldl_backward_wavefront<2>(tile, rowinfo, tij, sX, NTR, lane);
 		else if (NTR <= 128) ldl_backward_wavefront<4>(tile, rowinfo, tij, sX, NTR, lane);
 		else {
-			// general size: lane (a, t) multiplies row a of the t-th tile of the row, a 3-step butterfly sums over the tiles
+			// general size: lane (a, t) multiplies row a of the t-th tile of the row, a 3-step butterfly sums over the tiles;
+			// the next row's record, tile columns and W entries do not depend on x and are fetched one row ahead
 			const int a = lane >> 3, t8 = lane & 7;
+			int4 rk = rowinfo[NTR - 1];
+			auto prefetch = [&](const int4 &r, int &col, double &w0, double &w1, double &w2) {
+				const int r0 = r.x, m = (r.y & 0x3fffffff) - r0 - 2;
+				col = -1; w0 = w1 = w2 = 0.0;
+				if (a < 3 && t8 < m) {
+					const int tl = r0 + 1 + t8;
+					col = tij[tl] & 0xffff;
+					const double *Wt = tile + tl * 12 + a;
+					w0 = Wt[0]; w1 = Wt[4]; w2 = Wt[8];
+				}
+			};
+			int col; double w0, w1, w2;
+			prefetch(rk, col, w0, w1, w2);
 #pragma unroll 1
 			for (int k = NTR - 1; k >= 0; k--) {
-				const int4 rk = rowinfo[k];
 				const int r0 = rk.x, r1 = rk.y & 0x3fffffff, m = r1 - r0 - 2;
+				const double zk = a < 3 ? tile[(r1 - 1) * 12 + a] : 0.0;
+				const int4 rnx = rowinfo[k > 0 ? k - 1 : 0];
+				int ncol; double n0, n1, n2;
+				prefetch(rnx, ncol, n0, n1, n2);
 				double p = 0.0;
+				if (col >= 0) { const double *x = sX + 3 * col; p = w0 * x[0] + w1 * x[1] + w2 * x[2]; }
 #pragma unroll 1
-				for (int base = 0; base < m; base += 8) {
+				for (int base = 8; base < m; base += 8) {  // rows with more than 8 off-diagonal tiles
 					const int t = base + t8;
 					if (a < 3 && t < m) {
 						const int tl = r0 + 1 + t;
@@ -1220,8 +1241,9 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 				p += __shfl_xor_sync(0xffffffffu, p, 4);
 				p += __shfl_xor_sync(0xffffffffu, p, 2);
 				p += __shfl_xor_sync(0xffffffffu, p, 1);
-				if (a < 3 && t8 == 0) sX[3 * k + a] = tile[(r1 - 1) * 12 + a] - p;
+				if (a < 3 && t8 == 0) sX[3 * k + a] = zk - p;
 				__syncwarp();
+				rk = rnx; col = ncol; w0 = n0; w1 = n1; w2 = n2;
 			}
 		}
 	}
@@ -1648,7 +1670,7 @@ __global__ void __launch_bounds__(NT, MINB) srba_lm_batch_kernel(const char *img
 // Per-model kernel configuration: CTA size, register tiles per thread, dynamic shared memory per CTA.
 //   SE2+RelativePoses2D: 128 regs -> 2 CTAs/SM, 2 x (108 KB dynamic + ~3 KB static + 1 KB reserved) of the SM's 228 KB;  SE3 models: 255 regs -> 1 CTA/SM, 220 KB.
 #define SE2_NT 192
-#define SE3_NT 256
+#define SE3_NT 1024
 #define SE2_TPT 2
 #define SE3_TPT 4
 extern "C" SrbaKernelCfg srba_kernel_cfg(int model) {
