@@ -55,6 +55,17 @@ trials = sum(s["num_trials"] for s in st)
 ms = ev[0].elapsed_time(ev[1])
 print("batch of %d %s areas (depth %d): %.3f ms, %d LM trials -> %.0f LM it/s; trials/area mean %.1f max %d; final rmse median %.3g" %
       (b.n, name, depth, ms, trials, trials / (ms * 1e-3), trials / b.n, max(s["num_trials"] for s in st), np.median([s["obs_rmse"] for s in st])))
+if "--cpu" in sys.argv:   # the oracle (CPU restatement of the reference) on the same keyframes, 1 thread, 'opt' span only
+    from oracle import pyoracle as po
+    eo = po.OracleEngine(po.default_params(**kw))
+    sec, tr = 0.0, 0
+    for k, f in enumerate(ds["frames"]):
+        s0, t0_ = eo.opt_timer()
+        D.feed(eo, f)
+        s1, t1_ = eo.opt_timer()
+        if k >= n_kfs - areas:
+            sec += s1 - s0; tr += t1_ - t0_
+    print("oracle (1 CPU thread) on the same %d keyframes: %d LM trials in %.2f s -> %.0f LM it/s" % (areas, tr, sec, tr / max(sec, 1e-9)))
 if "--stages" in sys.argv:
     rows = sorted(((sum(v for k2, v in b.stage_cycles(i).items() if not k2.startswith("chol.")), i) for i in range(b.n)), reverse=True)
     for tot, i in rows[:2]:
