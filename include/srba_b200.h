@@ -173,14 +173,18 @@ void srba_b200_batch_algorithmic_bytes(const srba_batch_t *b, double out[5]);
 int srba_b200_problem_plan(const srba_problem_t *in, int64_t out[8]);
 
 /* Host-only (tests): the symbolic factorisation the packer ships with a problem for the on-chip block-sparse L D L^t
- * solver -- 3x3 tiles numbered row-major (diagonal first, right-hand side as tile column NTR).  counts[4] = {NTR, tiles,
- * updates, fits}; row[4*(NTR+1)] = {first tile, end tile | has_superdiag<<30, first update, end update} per row;
+ * solver -- 3x3 tiles numbered row-major (diagonal first, right-hand side as tile column NTR).  counts[6] = {NTR, tiles,
+ * updates, ok, phases, tiles fit on chip}; row[4*(NTR+1)] = {first tile, end tile, first update, end update} per row;
+ * phase[16*(phases+1)] = {first row, rows (1 or 2 independent rows eliminated together), first update, end of the first
+ * row's updates, end update, pivots of the next phase, their tiles (2), the tiles through which this phase updates them
+ * (2; bit 30: from the second row; -1 = none), first tile, first tile of the second row, end tile, 0, 0, 0};
  * tile_ij[tiles] = ti<<16|tj; src[tiles] = offset into the reduced blocks (bit 30: diagonal, bit 29: transposed), -1
  * fill-in, -2-row right-hand side; upd[2*updates] = {dst tile | tile(k,i)<<16, tile(k,j)}; orow[NTR] = tile row in
  * elimination order -> tile row in the caller's unknown order (identity unless the reference's order would overflow
- * `max_tiles_on_chip`, then greedy minimum degree).  Call with NULL arrays to get the counts first. */
-int srba_b200_debug_ldl_schedule(const srba_problem_t *in, int32_t counts[4], int32_t *row, int32_t *tile_ij, int32_t *src, int32_t *upd,
-                                 int32_t *orow, int32_t cap_tiles, int32_t cap_upd, int32_t max_tiles_on_chip);
+ * `max_tiles_on_chip`, then greedy minimum degree; chain-like SE(2) areas are eliminated from both ends: 0, n-1, 1, ...).
+ * Call with NULL arrays to get the counts first. */
+int srba_b200_debug_ldl_schedule(const srba_problem_t *in, int32_t counts[6], int32_t *row, int32_t *tile_ij, int32_t *src, int32_t *upd,
+                                 int32_t *orow, int32_t *phase, int32_t cap_tiles, int32_t cap_upd, int32_t max_tiles_on_chip);
 
 const char *srba_b200_last_error(void);
 int srba_b200_device_count(void);

@@ -130,7 +130,7 @@ def lib():
     L.srba_b200_batch_stage_cycles.argtypes = [vp, i32, pu64]
     pi32 = C.POINTER(C.c_int32)
     L.srba_b200_debug_ldl_schedule.restype = C.c_int
-    L.srba_b200_debug_ldl_schedule.argtypes = [pp, pi32, pi32, pi32, pi32, pi32, pi32, i32, i32, i32]
+    L.srba_b200_debug_ldl_schedule.argtypes = [pp, pi32, pi32, pi32, pi32, pi32, pi32, pi32, i32, i32, i32]
     L.srba_b200_problem_plan.restype = C.c_int
     L.srba_b200_problem_plan.argtypes = [pp, C.POINTER(C.c_int64)]
     L.srba_b200_last_error.restype = C.c_char_p

@@ -126,6 +126,7 @@ inline const void *src_of_ldl_row(const srba_problem_t &) { return nullptr; }
 inline const void *src_of_ldl_tile_ij(const srba_problem_t &) { return nullptr; }
 inline const void *src_of_ldl_src(const srba_problem_t &) { return nullptr; }
 inline const void *src_of_ldl_orow(const srba_problem_t &) { return nullptr; }
+inline const void *src_of_ldl_phase(const srba_problem_t &) { return nullptr; }
 inline const void *src_of_ldl_upd(const srba_problem_t &) { return nullptr; }
 // pointer to the caller's array behind image slot `id` (NULL for the derived ones)
 const void *src_ptr(const srba_problem_t &p, int id) {
@@ -146,12 +147,14 @@ struct TileSymbolic {
 	std::vector<int32_t> row;       // 4 per row (+ sentinel): {first tile, end tile | has_superdiag<<30, first update, end update}
 	std::vector<int32_t> tile_ij;   // ntiles: (ti<<16)|tj
 	std::vector<int32_t> src;       // ntiles: offset of the tile's (0,0) in the reduced blocks (bit 30: diagonal tile, bit 29: transposed), -1 fill-in, -2-row right-hand side
+	std::vector<int32_t> phase;     // 16 per phase (+ sentinel), see symbolic_tiles
+	int n_phases = 0;
 	std::vector<int32_t> orow;      // NTR: tile row in elimination order -> tile row in the reference's unknown order
 	bool on_chip = false;           // the tiles fit the shared-memory budget (else they live in the L2-resident workspace)
 	std::vector<int32_t> upd_ptr;   // NTR+1
 	std::vector<int32_t> upd;       // 2 per update: {dst tile | tile(k,i)<<16, tile(k,j)}; the update of the next pivot block is implicit
 	bool ok = false;                // false: too large for the on-chip solver (schedule not built)
-	void clear() { rs.clear(); row.clear(); src.clear(); orow.clear(); on_chip = false; tile_ij.clear(); upd_ptr.clear(); upd.clear(); ok = false; }
+	void clear() { rs.clear(); row.clear(); phase.clear(); n_phases = 0; src.clear(); orow.clear(); on_chip = false; tile_ij.clear(); upd_ptr.clear(); upd.clear(); ok = false; }
 };
 // Elimination order of the unknown edges (block level).  The reference's own order is kept whenever its fill fits on chip
 // (a relative graph-SLAM chain is block-banded in that order: no fill at all); areas with loop closures fill the whole band
@@ -195,7 +198,7 @@ long elimination_fill(const std::vector<uint64_t> &adj0, int np, int Wb, int q, 
 	return tiles;
 }
 
-void symbolic_tiles(const srba_problem_t &p, int P, long max_tiles_on_chip, TileSymbolic &sy) {
+void symbolic_tiles(const srba_problem_t &p, int P, long max_tiles_on_chip, TileSymbolic &sy, bool two_front = true) {
 	const int q = P / 3, np = p.n_unk_edges, ntr = q * np, ntc = ntr + 1;
 	sy.clear();
 	sy.ntr = ntr;
@@ -212,6 +215,14 @@ void symbolic_tiles(const srba_problem_t &p, int P, long max_tiles_on_chip, Tile
 	std::vector<int> perm(np);  // position in the elimination order -> unknown edge
 	std::iota(perm.begin(), perm.end(), 0);
 	long tiles = elimination_fill(adj, np, Wb, q, &perm, nullptr);
+	if (q == 1 && np >= 8 && tiles <= max_tiles_on_chip && two_front) {
+		// chain-like area (block-banded in the reference's order): eliminate from BOTH ends at once -- order 0, n-1, 1, n-2, ...
+		// The two fronts are independent until they meet, so the solver retires two block rows per barrier.
+		std::vector<int> tw(np);
+		for (int i = 0; i < np; i++) tw[i] = (i & 1) ? np - 1 - i / 2 : i / 2;
+		const long tiles_tw = elimination_fill(adj, np, Wb, q, &tw, nullptr);
+		if (tiles_tw <= max_tiles_on_chip && tiles_tw <= tiles + tiles / 4) { perm = tw; tiles = tiles_tw; }
+	}
 	if (tiles > max_tiles_on_chip) {
 		std::vector<int> md;
 		const long tiles_md = elimination_fill(adj, np, Wb, q, nullptr, &md);
@@ -280,7 +291,31 @@ void symbolic_tiles(const srba_problem_t &p, int P, long max_tiles_on_chip, Tile
 		const auto it = std::lower_bound(sy.tile_ij.begin() + sy.rs[i], sy.tile_ij.begin() + sy.rs[i + 1], key);
 		return (int32_t)(it - sy.tile_ij.begin());
 	};
-	// update schedule
+	// phases: consecutive rows p, p+1 are eliminated together when they are independent -- no tile (p,p+1) and no common
+	// column (then their update targets are disjoint and each pivot of the next phase is touched by at most one of them)
+	auto has = [&](int r, int c) { return (rows[(size_t)r * W + (c >> 6)] >> (c & 63)) & 1; };
+	std::vector<int> phase_row;  // first row of each phase (+ sentinel)
+	for (int pz = 0; pz < ntr;) {
+		phase_row.push_back(pz);
+		bool pair = pz + 1 < ntr && !has(pz, pz + 1);
+		if (pair) {
+			const uint64_t *ra = &rows[(size_t)pz * W], *rb = &rows[(size_t)(pz + 1) * W];
+			for (int w = 0; w < W && pair; w++) {
+				uint64_t m = ra[w] & rb[w];
+				if (w == (ntr >> 6)) m &= ~(1ull << (ntr & 63));         // the right-hand-side column is shared by construction
+				if (w == ((pz + 1) >> 6)) m &= ~(1ull << ((pz + 1) & 63));  // row p+1's own diagonal is not a column of row p
+				if (m) pair = false;
+			}
+		}
+		pz += pair ? 2 : 1;
+	}
+	const int nph = (int)phase_row.size();
+	phase_row.push_back(ntr);
+	std::vector<int> phase_of(ntr + 1, nph);
+	for (int m = 0; m < nph; m++)
+		for (int r = phase_row[m]; r < phase_row[m + 1]; r++) phase_of[r] = m;
+	// update schedule: row k's pairs of tiles; the updates of the NEXT phase's pivot blocks are implicit (done by the lanes
+	// that invert those pivots)
 	sy.upd_ptr.assign(ntr + 1, 0);
 	for (int k = 0; k < ntr; k++) {
 		sy.upd_ptr[k] = (int32_t)(sy.upd.size() / 2);
@@ -289,21 +324,40 @@ void symbolic_tiles(const srba_problem_t &p, int P, long max_tiles_on_chip, Tile
 			if (i >= ntr) break;  // the right-hand side is never a row
 			for (int b = a; b < sy.rs[k + 1]; b++) {
 				const int j = sy.tile_ij[b] & 0xffff;
-				if (i == k + 1 && j == k + 1) continue;  // next pivot block: updated by the inverting lanes themselves
+				if (i == j && phase_of[i] == phase_of[k] + 1) continue;  // next pivot block
 				sy.upd.push_back(find_tile(i, j) | (a << 16));  // dst | tile(k,i) << 16
 				sy.upd.push_back(b);                             // tile(k,j)
 			}
 		}
 	}
 	sy.upd_ptr[ntr] = (int32_t)(sy.upd.size() / 2);
-	// per-row records and tile sources
+	// per-row records
 	sy.row.assign(4 * (size_t)(ntr + 1), 0);
 	for (int k = 0; k <= ntr; k++) {
 		int32_t *r = &sy.row[4 * (size_t)k];
 		if (k == ntr) { r[0] = r[1] = sy.rs[ntr]; r[2] = r[3] = sy.upd_ptr[ntr]; break; }
-		const bool has_sd = sy.rs[k] + 1 < sy.rs[k + 1] && (sy.tile_ij[sy.rs[k] + 1] & 0xffff) == k + 1 && k + 1 < ntr;
-		r[0] = sy.rs[k]; r[1] = sy.rs[k + 1] | (has_sd ? 1 << 30 : 0); r[2] = sy.upd_ptr[k]; r[3] = sy.upd_ptr[k + 1];
+		r[0] = sy.rs[k]; r[1] = sy.rs[k + 1]; r[2] = sy.upd_ptr[k]; r[3] = sy.upd_ptr[k + 1];
 	}
+	// per-phase records (16 ints, + sentinel): {first row, rows, first update, end of the first row's updates | end update,
+	// pivots in the next phase, pivot tile 0, pivot tile 1 | link 0, link 1, first tile, first tile of the second row |
+	// end tile, 0, 0, 0}; link g = the tile (r, q_g) through which a row r of this phase updates pivot q_g of the next one
+	// (bit 30: r is the phase's second row), or -1
+	sy.phase.assign(16 * (size_t)(nph + 1), 0);
+	for (int m = 0; m <= nph; m++) {
+		int32_t *r = &sy.phase[16 * (size_t)m];
+		const int row0 = phase_row[std::min(m, nph)], nrows = m < nph ? phase_row[m + 1] - row0 : 0;
+		r[0] = row0; r[1] = nrows; r[2] = sy.upd_ptr[row0]; r[3] = sy.upd_ptr[std::min(row0 + 1, ntr)]; r[4] = sy.upd_ptr[std::min(row0 + nrows, ntr)];
+		const int nnext = m + 1 < nph ? phase_row[m + 2] - phase_row[m + 1] : 0;
+		r[5] = nnext; r[6] = r[7] = 0; r[8] = r[9] = -1;
+		for (int g = 0; g < nnext; g++) {
+			const int qrow = phase_row[m + 1] + g;
+			r[6 + g] = sy.rs[qrow];
+			for (int rr = row0; rr < row0 + nrows; rr++)
+				if (has(rr, qrow)) r[8 + g] = find_tile(rr, qrow) | (rr > row0 ? 1 << 30 : 0);
+		}
+		r[10] = sy.rs[row0]; r[11] = sy.rs[std::min(row0 + 1, ntr)]; r[12] = sy.rs[std::min(row0 + nrows, ntr)];
+	}
+	sy.n_phases = nph;
 	sy.src.resize(sy.tile_ij.size());
 	for (size_t t = 0; t < sy.tile_ij.size(); t++) sy.src[t] = srcmap[(size_t)(sy.tile_ij[t] >> 16) * ntc + (sy.tile_ij[t] & 0xffff)];
 	sy.ok = sy.tile_ij.size() <= 32767;
@@ -333,7 +387,7 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 	const SrbaKernelCfg cfg = srba_kernel_cfg(model);
 	if (!base) {  // layout pass: symbolic factorisation (reused by the copy pass)
 		// tiles may take up to 3/4 of the CTA's shared memory (other arrays then spill to the L2-resident workspace)
-		const long max_tiles = std::min(32767L, ((long)cfg.smem_bytes * 3 / 4 / 8 - 37 - h.n_dense) / 12);
+		const long max_tiles = std::min(32767L, ((long)cfg.smem_bytes * 3 / 4 / 8 - 73 - h.n_dense) / 12);
 		if (max_tiles > 0) symbolic_tiles(p, P, max_tiles, sy);
 		else sy.clear();
 	}
@@ -344,6 +398,7 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 		h.chol_mode = SRBA_CHOL_REG;
 		h.ldl_n_tiles = (int)sy.tile_ij.size();
 		h.ldl_tiles_in_ws = sy.on_chip ? 0 : 1;
+		h.ldl_n_phases = sy.n_phases;
 		scratch_bytes = (uint64_t)reg_scratch * 8;
 	} else {
 		h.chol_mode = SRBA_CHOL_BLOCKED;
@@ -367,7 +422,7 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 		c[SRBA_I_blkA_col] = p.n_blkA; c[SRBA_I_blkF_col] = p.n_blkF;
 		const bool reg = h.chol_mode == SRBA_CHOL_REG;
 		c[SRBA_I_ldl_row] = reg ? sy.row.size() : 0; c[SRBA_I_ldl_tile_ij] = reg ? sy.tile_ij.size() : 0;
-		c[SRBA_I_ldl_src] = reg ? sy.src.size() : 0; c[SRBA_I_ldl_upd] = reg ? sy.upd.size() : 0; c[SRBA_I_ldl_orow] = reg ? sy.orow.size() : 0;
+		c[SRBA_I_ldl_src] = reg ? sy.src.size() : 0; c[SRBA_I_ldl_upd] = reg ? sy.upd.size() : 0; c[SRBA_I_ldl_orow] = reg ? sy.orow.size() : 0; c[SRBA_I_ldl_phase] = reg ? sy.phase.size() : 0;
 	}
 	Layout L;
 	L.add(sizeof(DevProblem));
@@ -395,6 +450,7 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 			put<int32_t>(base, h.img_off[SRBA_I_ldl_tile_ij], sy.tile_ij.data(), sy.tile_ij.size());
 			put<int32_t>(base, h.img_off[SRBA_I_ldl_src], sy.src.data(), sy.src.size());
 			put<int32_t>(base, h.img_off[SRBA_I_ldl_orow], sy.orow.data(), sy.orow.size());
+			put<int32_t>(base, h.img_off[SRBA_I_ldl_phase], sy.phase.data(), sy.phase.size());
 			put<int32_t>(base, h.img_off[SRBA_I_ldl_upd], sy.upd.data(), sy.upd.size());
 		}
 	}
@@ -437,7 +493,7 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 			{0, SRBA_W_edge_cur}, {0, SRBA_W_edge_bak}, {0, SRBA_W_grad}, {0, SRBA_W_delta}, {0, SRBA_W_lm_cur}, {0, SRBA_W_lm_bak},
 			{0, SRBA_W_valid}, {0, SRBA_W_lm_inv}, {0, SRBA_W_pair_refresh}, {0, SRBA_W_slot_listed}, {0, SRBA_W_listed_idx}, {0, SRBA_W_refresh_idx},
 			{0, SRBA_W_resid0}, {0, SRBA_W_resid1}, {0, SRBA_W_slot}, {0, SRBA_W_HAp}, {0, SRBA_W_Hf}, {0, SRBA_W_Hf_inv},
-			{1, SRBA_I_ldl_row}, {1, SRBA_I_ldl_tile_ij}, {1, SRBA_I_ldl_upd}, {1, SRBA_I_ldl_src}, {1, SRBA_I_ldl_orow}, {1, SRBA_I_unk_edge}, {1, SRBA_I_unk_lm}, {1, SRBA_I_obs_slot}, {1, SRBA_I_obs_z}, {1, SRBA_I_obs_mult}, {1, SRBA_I_obs_lm},
+			{1, SRBA_I_ldl_phase}, {1, SRBA_I_ldl_row}, {1, SRBA_I_ldl_tile_ij}, {1, SRBA_I_ldl_upd}, {1, SRBA_I_ldl_src}, {1, SRBA_I_ldl_orow}, {1, SRBA_I_unk_edge}, {1, SRBA_I_unk_lm}, {1, SRBA_I_obs_slot}, {1, SRBA_I_obs_z}, {1, SRBA_I_obs_mult}, {1, SRBA_I_obs_lm},
 			{1, SRBA_I_pair_path_ptr}, {1, SRBA_I_path_edge}, {1, SRBA_I_path_dir},
 			{0, SRBA_W_Sblk}, {0, SRBA_W_HApf}, {0, SRBA_W_W}, {0, SRBA_W_JA}, {0, SRBA_W_JF}, {0, SRBA_W_slot_bak}, {0, SRBA_W_blk_ok},
 			{1, SRBA_I_colA_ptr}, {1, SRBA_I_blkA_obs}, {1, SRBA_I_blkA_col}, {1, SRBA_I_blkA_slotA}, {1, SRBA_I_blkA_slotD}, {1, SRBA_I_blkA_normal_dir},
@@ -766,8 +822,8 @@ void srba_b200_batch_algorithmic_bytes(const srba_batch_t *b, double out[5]) {
 	}
 }
 
-int srba_b200_debug_ldl_schedule(const srba_problem_t *in, int32_t counts[4], int32_t *row, int32_t *tile_ij, int32_t *src, int32_t *upd, int32_t *orow,
-                                 int32_t cap_tiles, int32_t cap_upd, int32_t max_tiles_on_chip) {
+int srba_b200_debug_ldl_schedule(const srba_problem_t *in, int32_t counts[6], int32_t *row, int32_t *tile_ij, int32_t *src, int32_t *upd, int32_t *orow,
+                                 int32_t *phase, int32_t cap_tiles, int32_t cap_upd, int32_t max_tiles_on_chip) {
 	if (!in || !counts) return fail(SRBA_ERR_BAD_ARGUMENT, "null argument");
 	const int rc = validate(*in);
 	if (rc != SRBA_OK) return rc;
@@ -775,6 +831,7 @@ int srba_b200_debug_ldl_schedule(const srba_problem_t *in, int32_t counts[4], in
 	TileSymbolic sy;
 	symbolic_tiles(*in, P, max_tiles_on_chip, sy);
 	counts[0] = sy.ntr; counts[1] = (int32_t)sy.tile_ij.size(); counts[2] = (int32_t)(sy.upd.size() / 2); counts[3] = sy.ok ? 1 : 0;
+	counts[4] = sy.n_phases; counts[5] = sy.on_chip ? 1 : 0;
 	if (!sy.ok) return SRBA_OK;
 	if (row && tile_ij && src && upd) {
 		if (cap_tiles < counts[1] || cap_upd < counts[2]) return fail(SRBA_ERR_BAD_ARGUMENT, "schedule buffers too small");
@@ -783,6 +840,7 @@ int srba_b200_debug_ldl_schedule(const srba_problem_t *in, int32_t counts[4], in
 		std::memcpy(src, sy.src.data(), sy.src.size() * 4);
 		std::memcpy(upd, sy.upd.data(), sy.upd.size() * 4);
 		if (orow) std::memcpy(orow, sy.orow.data(), sy.orow.size() * 4);
+		if (phase) std::memcpy(phase, sy.phase.data(), sy.phase.size() * 4);
 	}
 	return SRBA_OK;
 }

@@ -32,7 +32,7 @@
 	X(int32_t, HApf_row) X(int32_t, HApf_col) X(int32_t, HApf_term_ptr) X(int32_t, HApf_term_a) X(int32_t, HApf_term_f)  \
 	X(int32_t, rowApf_ptr) X(int32_t, colApf_ptr) X(int32_t, colApf_idx)                                                 \
 	X(int32_t, S_row) X(int32_t, S_col) X(int32_t, S_HAp) X(int32_t, S_term_ptr) X(int32_t, S_term_rowblk) X(int32_t, S_term_colblk) \
-	X(int32_t, blkA_col) X(int32_t, blkF_col) X(int32_t, ldl_row) X(int32_t, ldl_tile_ij) X(int32_t, ldl_src) X(int32_t, ldl_upd) X(int32_t, ldl_orow)
+	X(int32_t, blkA_col) X(int32_t, blkF_col) X(int32_t, ldl_row) X(int32_t, ldl_tile_ij) X(int32_t, ldl_src) X(int32_t, ldl_upd) X(int32_t, ldl_orow) X(int32_t, ldl_phase)
 
 // (type, name) of every workspace array.
 #define SRBA_WS_ARRAYS(X)                                                                                               \
@@ -73,6 +73,7 @@ struct DevProblem {
 	int32_t chol_mode;   // SRBA_CHOL_*
 	int32_t panel_cap;   // SRBA_CHOL_BLOCKED: columns of the staged 8-row panel that fit the scratch
 	int32_t ldl_n_tiles; // SRBA_CHOL_REG: 3x3 tiles of the filled pattern incl. the right-hand-side column
+	int32_t ldl_n_phases; // barrier-separated elimination phases (1 or 2 independent block rows each)
 	int32_t ldl_tiles_in_ws; // 1: the tiles do not fit on chip and live in the workspace array ldl_tiles (L2-resident)
 	int32_t s_alias_hap; // 1: no Schur terms and S block b == H_Ap block b -> the reduced blocks ARE the H_Ap blocks
 	uint32_t sm_scratch; // byte offset of the Cholesky scratch inside the CTA's dynamic shared memory

@@ -1070,8 +1070,8 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 	const int NTR = n / 3;
 	const bool tiles_in_ws = v.h->ldl_tiles_in_ws != 0;
 	double *tile = tiles_in_ws ? v.ldl_tiles : scr;                    // ntiles x 12 (on chip unless the pattern is too large)
-	double *sInv = tiles_in_ws ? scr : scr + 12 * (size_t)ntiles;      // 3 x 12 : inverse pivot blocks of rows k-1, k, k+1 (slot = row % 3)
-	double *sAcc = sInv + 36;                  // 3*NTR : backward-pass accumulators
+	double *sInv = tiles_in_ws ? scr : scr + 12 * (size_t)ntiles;      // 6 x 12 : inverse pivot blocks of the previous, current and next phase (slot = row % 6)
+	double *sAcc = sInv + 72;                  // 3*NTR : backward-pass accumulators
 	const int4 *rowinfo = reinterpret_cast<const int4 *>(v.ldl_row);  // {first tile, end tile | has_superdiag << 30, first update, end update}
 	const int32_t *tij = v.ldl_tile_ij, *upd = v.ldl_upd, *src = v.ldl_src, *orow = v.ldl_orow;
 	const int tid = threadIdx.x, NT = LM_THREADS;
@@ -1082,7 +1082,11 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 	// cyclic cofactor of a symmetric 3x3: C(a,b) = d(a1,b1) d(a2,b2) - d(a1,b2) d(a2,b1)
 	const int a1 = wa == 2 ? 0 : wa + 1, a2 = wa == 0 ? 2 : wa - 1, b1 = wb == 2 ? 0 : wb + 1, b2 = wb == 0 ? 2 : wb - 1;
 	const int o11 = b1 * 4 + a1, o22 = b2 * 4 + a2, o12 = b2 * 4 + a1, o21 = b1 * 4 + a2;
-	int4 ri = rowinfo[0], rn = rowinfo[NTR > 1 ? 1 : NTR];
+	// phase records (4 x int4): {first row, rows, first update, end of row 0's updates | end update, pivots of the next phase,
+	// pivot tile 0, pivot tile 1 | link 0, link 1, first tile, first tile of the second row | end tile, -, -, -}
+	const int4 *phase = reinterpret_cast<const int4 *>(v.ldl_phase);
+	const int nph = v.h->ldl_n_phases;
+	int4 pa = phase[0], pb = phase[1], pc = phase[2], pd = phase[3];
 	// pivot-block inversion by 9 lanes: own cofactor, determinant, one reciprocal
 	auto invert_pivot = [&](const double *D, double *inv) {
 		const double d00 = D[0], d01 = D[4], d02 = D[8], d11 = D[5], d12 = D[9], d22 = D[10];
@@ -1093,16 +1097,19 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 		// discarded by the single check after the loop
 		if (d00 <= 0 || d00 * d11 - d01 * d01 <= 0 || det <= 0) sh.chol_ok = 0;
 	};
-	// the first pivot block does not wait for the gather: its 9 lanes fetch their own elements and invert it while the
-	// other warps gather the remaining tiles
+	// the pivot blocks of the first phase (one or two rows) do not wait for the gather: their 9-lane groups fetch their own
+	// elements and invert them while the other warps gather the remaining tiles
 	if (warp == iwarp) {
 		if (lane == 0) sh.chol_ok = 1;
-		if (lane < 9) tile[eo] = v.S[(src[0] & 0x1fffffff) + wa * P + wb] + (wa == wb ? lambda : 0.0);
 		__syncwarp();
-		if (lane < 9) invert_pivot(tile, sInv);
+		const bool mine = lane < 9 * pa.y;   // group g handles row g of phase 0
+		const int pt = mine ? rowinfo[wg].x : 0;
+		if (mine) tile[pt * 12 + eo] = v.S[(src[pt] & 0x1fffffff) + wa * P + wb] + (wa == wb ? lambda : 0.0);
+		__syncwarp();
+		if (mine) invert_pivot(tile + pt * 12, sInv + wg * 12);
 	}
 	// gather: tile element <- reduced block element (+lambda on the diagonal); tile column NTR = reduced gradient.
-	// 9 lanes per tile (3 tiles per warp and round); ldl_src: >= 0 offset of the tile's (0,0) in S (bit 30: diagonal tile),
+	// 9 lanes per tile (3 tiles per warp and round); ldl_src: >= 0 offset of the tile's (0,0) in S (bit 30: diagonal tile, bit 29: the tile is the transpose),
 	// -1 fill-in, <= -2 right-hand side of row -src-2
 	if (lane < 27) {
 		const double dl = wa == wb ? lambda : 0.0;
@@ -1115,26 +1122,33 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 			tile[tl * 12 + eo] = val;
 		}
 	}
+	int2 u_first = make_int2(0, 0);
+	if (warp != iwarp && tid < (pb.x - pa.z) * 9) u_first = *reinterpret_cast<const int2 *>(upd + 2 * (pa.z + tid / 9));
 	__syncthreads();
 #ifdef SRBA_SOLVER_TIMERS
 	const long long c_loop = clock64();
 #endif
-	int prev_r0 = 0, prev_r1 = 0;  // tiles of row k-1 still to be turned into W
-	int2 u_first = make_int2(0, 0);
-	if (tid < (ri.w - ri.z) * 9) u_first = *reinterpret_cast<const int2 *>(upd + 2 * (ri.z + tid / 9));
+	int prev_t0 = 0, prev_tm = 0, prev_t1 = 0;  // tiles of the previous phase's rows, still to be turned into W
+	int slot0 = 0, prev_slot0 = 0;              // inverse-pivot slot (row % 6) of the first row of the current / previous phase
+	const int NTU = NT - 32;                    // the warp that carries the pivot chain takes no update items
 #pragma unroll 1
-	for (int k = 0; k <= NTR; k++) {
-		const int r0 = ri.x, r1 = ri.y & 0x3fffffff, has_sd = ri.y >> 30, u0 = ri.z, nitems = (ri.w - ri.z) * 9;
-		const int4 rnn = rowinfo[k + 2 < NTR ? k + 2 : NTR];  // two rows ahead: off the critical path; row NTR is a sentinel
-		const double *Ik = sInv + (k % 3) * 12;
-		// ---- U: T(i,j) -= T(k,i)^t inv(D_k) T(k,j) for the pairs of row-k tiles (x: dst | tile(k,i) << 16, y: tile(k,j)).
-		// The first update descriptor of a row is fetched before the previous row's barrier, and two items are in flight per
-		// thread: for large areas the lists and tiles live in L2 and their latency would otherwise sit on every iteration.
-		{
+	for (int m = 0; m <= nph; m++) {
+		const int nrows = pa.y, u0 = pa.z, umid = pa.w, nitems = (pb.x - pa.z) * 9, nnext = pb.y;
+		const int mn = 4 * (m < nph ? m + 1 : nph);
+		const int4 na = phase[mn], nb = phase[mn + 1], nc = phase[mn + 2], nd = phase[mn + 3];
+		const int slot1 = slot0 + 1 >= 6 ? slot0 - 5 : slot0 + 1;
+		const double *Ik0 = sInv + slot0 * 12, *Ik1 = sInv + slot1 * 12;
+		int nslot0 = slot0 + nrows;
+		if (nslot0 >= 6) nslot0 -= 6;
+		if (warp != iwarp) {
+			// ---- U: T(i,j) -= T(k,i)^t inv(D_k) T(k,j) for the pairs of tiles of the phase's rows (x: dst | tile(k,i) << 16,
+			// y: tile(k,j)).  The first descriptor of a phase is fetched before the previous barrier, and two items are in
+			// flight per thread: for large areas the lists and tiles live in L2.
 #pragma unroll 2
-			for (int q = tid; q < nitems; q += NT) {
+			for (int q = tid; q < nitems; q += NTU) {
 				const int ui = q / 9, e = q - ui * 9, b = e / 3, a = e - b * 3;
 				const int2 u = q == tid ? u_first : *reinterpret_cast<const int2 *>(upd + 2 * (u0 + ui));
+				const double *Ik = (u0 + ui < umid) ? Ik0 : Ik1;
 				const double *Ti = tile + (u.x >> 16) * 12 + a * 4;
 				const double *Tj = tile + u.y * 12 + b * 4;
 				const double2 p01 = *reinterpret_cast<const double2 *>(Ti), t01 = *reinterpret_cast<const double2 *>(Tj);
@@ -1147,48 +1161,56 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 				double *dst = tile + (u.x & 0xffff) * 12 + b * 4 + a;
 				*dst = *dst - p01.x * w0 - p01.y * w1 - p2 * w2;
 			}
-		}
-		// first update descriptor of the NEXT row, in the shadow of this row's barrier
-		u_first = make_int2(0, 0);
-		if (tid < (rn.w - rn.z) * 9) u_first = *reinterpret_cast<const int2 *>(upd + 2 * (rn.z + tid / 9));
-		// ---- P: the next pivot block gets its row-k update from the super-diagonal tile and is inverted right away
-		if (warp == iwarp) {
-			if (k + 1 < NTR) {
-				double *Dn = tile + rn.x * 12;
-				if (lane < 9 && has_sd) {
-					const double *Ts = tile + (r0 + 1) * 12;
-					const double2 p01 = *reinterpret_cast<const double2 *>(Ts + wa * 4), t01 = *reinterpret_cast<const double2 *>(Ts + wb * 4);
-					const double p2 = Ts[wa * 4 + 2], t2 = Ts[wb * 4 + 2];
-					const double2 i0 = *reinterpret_cast<const double2 *>(Ik), i1 = *reinterpret_cast<const double2 *>(Ik + 4);
-					const double i02 = Ik[2], i12 = Ik[6], i22 = Ik[10];
-					const double w0 = i0.x * t01.x + i0.y * t01.y + i02 * t2;
-					const double w1 = i0.y * t01.x + i1.y * t01.y + i12 * t2;
-					const double w2 = i02 * t01.x + i12 * t01.y + i22 * t2;
-					Dn[eo] = Dn[eo] - p01.x * w0 - p01.y * w1 - p2 * w2;
-				}
-				__syncwarp();
-				if (lane < 9) invert_pivot(Dn, sInv + ((k + 1) % 3) * 12);
-			}
-		} else if (k > 0) {
-			// ---- W: the tiles of row k-1 become W = inv(D_{k-1}) T in place (3 tiles per warp and round, top warps first)
-			const double *Ip = sInv + ((k - 1) % 3) * 12;
+			// first update descriptor of the NEXT phase, in the shadow of this phase's barrier
+			u_first = make_int2(0, 0);
+			if (tid < (nb.x - na.z) * 9) u_first = *reinterpret_cast<const int2 *>(upd + 2 * (na.z + tid / 9));
+			// ---- W: the off-diagonal tiles of the previous phase's rows become W = inv(D) T in place (3 tiles per warp and round)
+			if (m > 0) {
 #pragma unroll 1
-			for (int base = prev_r0 + 1 + 3 * (iwarp - 1 - warp); base < prev_r1; base += 3 * (nwarps - 1)) {
-				const int tl = base + wg;
-				const bool act = lane < 27 && tl < prev_r1;
-				double w = 0.0;
-				if (act) {
-					const double *Tc = tile + tl * 12 + wb * 4;
-					const double2 t01 = *reinterpret_cast<const double2 *>(Tc);
-					const double2 i01 = *reinterpret_cast<const double2 *>(Ip + wa * 4);
-					w = i01.x * t01.x + i01.y * t01.y + Ip[wa * 4 + 2] * Tc[2];
+				for (int base = prev_t0 + 3 * (iwarp - 1 - warp); base < prev_t1; base += 3 * (nwarps - 1)) {
+					const int tl = base + wg;
+					const bool second = tl >= prev_tm;
+					const bool act = lane < 27 && tl < prev_t1 && tl != prev_t0 && tl != prev_tm;  // not the diagonal tiles
+					double w = 0.0;
+					if (act) {
+						int sl = prev_slot0 + (second ? 1 : 0);
+						if (sl >= 6) sl -= 6;
+						const double *Ip = sInv + sl * 12;
+						const double *Tc = tile + tl * 12 + wb * 4;
+						const double2 t01 = *reinterpret_cast<const double2 *>(Tc);
+						const double2 i01 = *reinterpret_cast<const double2 *>(Ip + wa * 4);
+						w = i01.x * t01.x + i01.y * t01.y + Ip[wa * 4 + 2] * Tc[2];
+					}
+					__syncwarp();
+					if (act) tile[tl * 12 + eo] = w;
 				}
-				__syncwarp();
-				if (act) tile[tl * 12 + eo] = w;
 			}
+		} else {
+			// ---- P: the pivot blocks of the next phase (one 9-lane group each) get this phase's update through their link
+			// tile (bit 30: it belongs to the phase's second row) and are inverted right away
+			const bool mine = lane < 9 * nnext;
+			const int pt = wg == 0 ? pb.z : pb.w, link = wg == 0 ? pc.x : pc.y;
+			double *Dn = tile + pt * 12;
+			if (mine && link >= 0) {
+				const double *Ts = tile + (link & 0x3fffffff) * 12;
+				const double *Ik = (link >> 30) ? Ik1 : Ik0;
+				const double2 p01 = *reinterpret_cast<const double2 *>(Ts + wa * 4), t01 = *reinterpret_cast<const double2 *>(Ts + wb * 4);
+				const double p2 = Ts[wa * 4 + 2], t2 = Ts[wb * 4 + 2];
+				const double2 i0 = *reinterpret_cast<const double2 *>(Ik), i1 = *reinterpret_cast<const double2 *>(Ik + 4);
+				const double i02 = Ik[2], i12 = Ik[6], i22 = Ik[10];
+				const double w0 = i0.x * t01.x + i0.y * t01.y + i02 * t2;
+				const double w1 = i0.y * t01.x + i1.y * t01.y + i12 * t2;
+				const double w2 = i02 * t01.x + i12 * t01.y + i22 * t2;
+				Dn[eo] = Dn[eo] - p01.x * w0 - p01.y * w1 - p2 * w2;
+			}
+			__syncwarp();
+			int ns = nslot0 + wg;
+			if (ns >= 6) ns -= 6;
+			if (mine) invert_pivot(Dn, sInv + ns * 12);
 		}
-		prev_r0 = r0; prev_r1 = r1;
-		ri = rn; rn = rnn;
+		prev_t0 = pc.z; prev_tm = nrows > 1 ? pc.w : pd.x; prev_t1 = pd.x;
+		prev_slot0 = slot0; slot0 = nslot0;
+		pa = na; pb = nb; pc = nc; pd = nd;
 		__syncthreads();
 	}
 	if (!sh.chol_ok) return false;
@@ -1685,7 +1707,7 @@ extern "C" SrbaKernelCfg srba_kernel_cfg(int model) {
 extern "C" int srba_chol_reg_scratch_doubles(int model, int n_dense, int n_tiles_on_chip) {
 	const SrbaKernelCfg c = srba_kernel_cfg(model);
 	const int NTR = n_dense / 3;
-	const long need = 12L * n_tiles_on_chip + 36 + 3L * NTR + 1;
+	const long need = 12L * n_tiles_on_chip + 72 + 3L * NTR + 1;
 	if (need * 8 > (long)c.smem_bytes * 7 / 8) return -1;
 	return (int)need;
 }
