@@ -532,14 +532,16 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 // SRBA_B200_THREADS overrides the thread count (default: hardware threads, at most 16).
 std::atomic<bool> g_forked{false};  // worker threads do not survive fork(): a forked child packs serially
 class WorkerPool {
+	// Workers SPIN on an atomic generation counter for a short while after their last job (a batch call issues eight
+	// parallel_for rounds within ~1 ms, and a condition-variable wake-up costs as much as packing a chunk), then sleep.
 	std::vector<std::thread> th_;
 	std::mutex m_;
-	std::condition_variable cv_, done_;
+	std::condition_variable cv_;
 	const std::function<void(int)> *fn_ = nullptr;
-	int n_ = 0, active_ = 0;
-	std::atomic<int> next_{0};
-	uint64_t gen_ = 0;
-	bool stop_ = false;
+	int n_ = 0;
+	std::atomic<int> next_{0}, active_{0}, sleepers_{0};
+	std::atomic<uint64_t> gen_{0};
+	std::atomic<bool> stop_{false};
 	void work() {
 		for (;;) {
 			const int i = next_.fetch_add(1, std::memory_order_relaxed);
@@ -550,17 +552,22 @@ class WorkerPool {
 	void loop() {
 		uint64_t seen = 0;
 		for (;;) {
-			{
-				std::unique_lock<std::mutex> lk(m_);
-				cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
-				if (stop_) return;
-				seen = gen_;
+			const auto t0 = std::chrono::steady_clock::now();
+			int spins = 0;
+			while (gen_.load(std::memory_order_acquire) == seen && !stop_.load(std::memory_order_relaxed)) {
+				if (++spins < 2048) continue;
+				spins = 0;
+				if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(300)) {
+					std::unique_lock<std::mutex> lk(m_);
+					sleepers_.fetch_add(1);
+					cv_.wait(lk, [&] { return stop_.load() || gen_.load() != seen; });
+					sleepers_.fetch_sub(1);
+				}
 			}
+			if (stop_.load()) return;
+			seen = gen_.load(std::memory_order_acquire);
 			work();
-			{
-				std::lock_guard<std::mutex> lk(m_);
-				if (--active_ == 0) done_.notify_one();
-			}
+			active_.fetch_sub(1, std::memory_order_acq_rel);
 		}
 	}
 
@@ -576,7 +583,7 @@ public:
 		if (g_forked.load()) { for (auto &t : th_) t.detach(); return; }
 		{
 			std::lock_guard<std::mutex> lk(m_);
-			stop_ = true;
+			stop_.store(true);
 		}
 		cv_.notify_all();
 		for (auto &t : th_) t.join();
@@ -584,14 +591,15 @@ public:
 	int threads() const { return (int)th_.size() + 1; }
 	void parallel_for(int n, const std::function<void(int)> &f) {
 		if (n < 16 || th_.empty() || g_forked.load()) { for (int i = 0; i < n; i++) f(i); return; }
-		{
+		fn_ = &f; n_ = n; next_.store(0);
+		active_.store((int)th_.size(), std::memory_order_release);
+		gen_.fetch_add(1, std::memory_order_acq_rel);
+		if (sleepers_.load() > 0) {
 			std::lock_guard<std::mutex> lk(m_);
-			fn_ = &f; n_ = n; next_.store(0); active_ = (int)th_.size(); gen_++;
+			cv_.notify_all();
 		}
-		cv_.notify_all();
 		work();
-		std::unique_lock<std::mutex> lk(m_);
-		done_.wait(lk, [&] { return active_ == 0; });
+		while (active_.load(std::memory_order_acquire) != 0) { /* the stragglers finish their last item */ }
 	}
 };
 WorkerPool &workers() {
