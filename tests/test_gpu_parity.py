@@ -278,3 +278,44 @@ def test_se2_loop_closure_areas_parity():
     eo, ep, worst, ns = run_parallel(kw, ds["frames"], check_state_every=40)
     print("loop-closure tour: worst relative increment error %.3e over %d decision-comparable trials" % (worst, ns))
     assert ns > 500
+
+
+def test_full_size_bench_batch_properties():
+    """BASELINE config #4 at full size (the 256-area batch bench.py times): size-independent properties.  Every area's
+    final error is <= its initial error (LM only accepts decreasing steps), the batch is deterministic (two runs are
+    bit-identical), the staged batch API and the pipelined host-buffer call agree bit for bit, and the flattened index
+    structures are consistent (every observation row is covered by its Jacobian blocks)."""
+    import ctypes as C
+    import os
+    import sys
+    from srba_b200 import _capi as K
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+    import bench
+    ds, eng, flats = bench.build_problems(seed=1, areas=256, n_kfs=700)
+    assert len(flats) == 256
+    for f in flats:
+        p = f.p
+        rows = f.array("row_ptr", p.n_obs + 1, np.int32)
+        assert rows[0] == 0 and rows[-1] == p.n_blkA + p.n_blkF and np.all(np.diff(rows) >= 1)
+        assert int(f.array("obs_mult", p.n_obs, np.int32).sum()) == p.n_total_obs_rows
+    b = sb.Batch(flats)
+    b.upload(); b.run(); b.download()
+    first = [b.unpack(i) for i in range(b.n)]
+    b.run(); b.download()
+    trials = 0
+    for i, r in enumerate(first):
+        r2 = b.unpack(i)
+        assert r2.stats == r.stats and np.array_equal(r2.edge_pose, r.edge_pose) and np.array_equal(r2.slot_pose, r.slot_pose)
+        st = r.stats
+        assert st["status"] == 0 and st["num_trials"] >= 1
+        assert st["total_sqr_error_final"] <= st["total_sqr_error_init"] * (1 + 1e-12)
+        assert np.isfinite(r.edge_pose).all() and np.isfinite(r.slot_pose).all()
+        trials += st["num_trials"]
+    n = len(flats)
+    parr = (C.POINTER(K.Problem) * n)(*[f.problem for f in flats])
+    bufs = [sb.ResultBuffers(f.p) for f in flats]
+    rarr = (C.POINTER(K.Result) * n)(*[C.pointer(x.r) for x in bufs])
+    assert K.lib().srba_b200_optimize_batch(n, parr, rarr) == 0
+    for r, x in zip(first, bufs):
+        assert x.r.stats.as_dict() == r.stats and np.array_equal(x.edge_pose, r.edge_pose) and np.array_equal(x.slot_pose, r.slot_pose)
+    print("256-area batch: %d LM trials, all deterministic" % trials)
