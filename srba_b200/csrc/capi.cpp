@@ -477,7 +477,7 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 		w[SRBA_W_dense] = (h.chol_mode == SRBA_CHOL_BLOCKED || want_dense) ? (uint64_t)h.n_dense * h.ld_dense * 8 : 0;
 		w[SRBA_W_ldl_tiles] = (h.chol_mode == SRBA_CHOL_REG && h.ldl_tiles_in_ws) ? (uint64_t)h.ldl_n_tiles * 12 * 8 : 0;
 		w[SRBA_W_valid] = p.n_obs; w[SRBA_W_blk_ok] = p.n_blkA + p.n_blkF; w[SRBA_W_lm_inv] = p.n_unk_lms;
-		w[SRBA_W_slot_listed] = 2 * p.n_pairs; w[SRBA_W_pair_refresh] = p.n_pairs; w[SRBA_W_listed_idx] = (uint64_t)2 * p.n_pairs * 4; w[SRBA_W_refresh_idx] = (uint64_t)p.n_pairs * 4;
+		w[SRBA_W_slot_listed] = 2 * p.n_pairs; w[SRBA_W_listed_idx] = (uint64_t)2 * p.n_pairs * 4; w[SRBA_W_refresh_idx] = (uint64_t)p.n_pairs * 4;
 	}
 	Layout W;
 	for (int a = 0; a < SRBA_W_COUNT; a++) { h.ws_off[a] = W.add(ws_bytes[a]); h.ws_sm[a] = SRBA_NOT_IN_SMEM; }
@@ -491,7 +491,7 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 		struct Cand { int is_img, id; };
 		static const Cand order[] = {
 			{0, SRBA_W_edge_cur}, {0, SRBA_W_edge_bak}, {0, SRBA_W_grad}, {0, SRBA_W_delta}, {0, SRBA_W_lm_cur}, {0, SRBA_W_lm_bak},
-			{0, SRBA_W_valid}, {0, SRBA_W_lm_inv}, {0, SRBA_W_pair_refresh}, {0, SRBA_W_slot_listed}, {0, SRBA_W_listed_idx}, {0, SRBA_W_refresh_idx},
+			{0, SRBA_W_valid}, {0, SRBA_W_lm_inv}, {0, SRBA_W_slot_listed}, {0, SRBA_W_listed_idx}, {0, SRBA_W_refresh_idx},
 			{0, SRBA_W_resid0}, {0, SRBA_W_resid1}, {0, SRBA_W_slot}, {0, SRBA_W_HAp}, {0, SRBA_W_Hf}, {0, SRBA_W_Hf_inv},
 			{1, SRBA_I_ldl_phase}, {1, SRBA_I_ldl_row}, {1, SRBA_I_ldl_tile_ij}, {1, SRBA_I_ldl_upd}, {1, SRBA_I_ldl_src}, {1, SRBA_I_ldl_orow}, {1, SRBA_I_unk_edge}, {1, SRBA_I_unk_lm}, {1, SRBA_I_obs_slot}, {1, SRBA_I_obs_z}, {1, SRBA_I_obs_mult}, {1, SRBA_I_obs_lm},
 			{1, SRBA_I_pair_path_ptr}, {1, SRBA_I_path_edge}, {1, SRBA_I_path_dir},

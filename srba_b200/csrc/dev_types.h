@@ -16,8 +16,8 @@
 
 // (type, name) of every array of the input image, in srba_problem_t order + derived ones: block -> column, and the
 // symbolic factorisation of the reduced system at 3x3-tile granularity (tiles numbered row-major, diagonal first, the
-// right-hand side as tile column NTR):  ldl_row[4*(NTR+1)] per row {first tile, end tile | has_superdiag<<30, first
-// update, end update} (+ sentinel);  ldl_tile_ij (ti<<16|tj);  ldl_src: where the tile comes from (offset into the reduced
+// right-hand side as tile column NTR):  ldl_row[4*(NTR+1)] per row {first tile, end tile, first update, end update}
+// (+ sentinel);  ldl_phase[16*(phases+1)]: the barrier-separated elimination phases of 1 or 2 independent rows (capi.cpp);  ldl_tile_ij (ti<<16|tj);  ldl_src: where the tile comes from (offset into the reduced
 // blocks, -1 fill-in, -2-row right-hand side);  ldl_upd: per eliminated row the updates {dst tile | tile(k,i)<<16,
 // tile(k,j)} (the one that hits the next pivot block is implicit);  ldl_orow: tile row in elimination order -> tile row in the
 // reference's unknown order (the packer re-orders areas with loop closures by minimum degree).
@@ -41,7 +41,7 @@
 	X(double, HAp) X(double, HApf) X(double, Hf) X(double, Hf_inv) X(double, W) X(double, Sblk)                          \
 	X(double, grad) X(double, delta) X(double, dense)                                                                    \
 	X(int32_t, listed_idx) X(int32_t, refresh_idx) X(double, ldl_tiles)                                                                                             \
-	X(uint8_t, valid) X(uint8_t, blk_ok) X(uint8_t, lm_inv) X(uint8_t, slot_listed) X(uint8_t, pair_refresh)
+	X(uint8_t, valid) X(uint8_t, blk_ok) X(uint8_t, lm_inv) X(uint8_t, slot_listed)
 
 enum {
 #define X(T, name) SRBA_I_##name,

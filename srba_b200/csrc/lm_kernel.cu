@@ -225,15 +225,6 @@ struct Shared {
 
 // Team-wide reductions with ONE barrier: warp partials go to one of three scratch rows (a row is reused only after at
 // least one other barrier), then every thread combines them in the same fixed order -- identical result on all threads.
-__device__ __forceinline__ double team_sum(double v, Shared &sh, int buf) {
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-	if ((threadIdx.x & 31) == 0) sh.red[buf][threadIdx.x >> 5] = v;
-	__syncthreads();
-	double s = 0;
-	for (int i = 0; i < LM_THREADS / 32; i++) s += sh.red[buf][i];
-	return s;
-}
 // two sums at once (second value in the upper half of the row)
 __device__ __forceinline__ double team_sum2(double v, double w, double &wsum, Shared &sh, int buf) {
 #pragma unroll
@@ -1072,7 +1063,7 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 	double *tile = tiles_in_ws ? v.ldl_tiles : scr;                    // ntiles x 12 (on chip unless the pattern is too large)
 	double *sInv = tiles_in_ws ? scr : scr + 12 * (size_t)ntiles;      // 6 x 12 : inverse pivot blocks of the previous, current and next phase (slot = row % 6)
 	double *sAcc = sInv + 72;                  // 3*NTR : backward-pass accumulators
-	const int4 *rowinfo = reinterpret_cast<const int4 *>(v.ldl_row);  // {first tile, end tile | has_superdiag << 30, first update, end update}
+	const int4 *rowinfo = reinterpret_cast<const int4 *>(v.ldl_row);  // {first tile, end tile, first update, end update}
 	const int32_t *tij = v.ldl_tile_ij, *upd = v.ldl_upd, *src = v.ldl_src, *orow = v.ldl_orow;
 	const int tid = threadIdx.x, NT = LM_THREADS;
 	const int lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
@@ -1453,7 +1444,6 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 	// F/G. validity reset + recompute_all_Jacobians (:269-276)
 	stage_jacobians<P, OBSK>(v, true);
 	__syncthreads();
-	for (int t = threadIdx.x; t < h->n_pairs; t += LM_THREADS) v.pair_refresh[t] = v.slot_listed[2 * t] | v.slot_listed[2 * t + 1];
 	if (threadIdx.x < 32) {  // compact list of the listed directed entries (ascending), built once by one warp
 		int cnt = 0;
 		for (int base = 0; base < 2 * h->n_pairs; base += 32) {
