@@ -168,7 +168,8 @@ int srba_b200_batch_stage_cycles(srba_batch_t *b, int32_t i, uint64_t out[24]);
 void srba_b200_batch_algorithmic_bytes(const srba_batch_t *b, double out[5]);
 
 /* Host-only: how the packer would lay problem `in` out.  out[0..7] = image bytes, global workspace bytes, result bytes,
- * shared-memory bytes planned (Cholesky scratch + on-chip arena), dense solver (0 register-resident tiles, 1 blocked),
+ * shared-memory bytes planned (solver scratch + on-chip arena), solver (0 block-sparse L D L^t, 1 dense blocked; +2 when
+ * the problem is solved by an 8-CTA cluster),
  * image arrays on chip, workspace arrays on chip, shared-memory budget of the model's kernel.  No device needed. */
 int srba_b200_problem_plan(const srba_problem_t *in, int64_t out[8]);
 

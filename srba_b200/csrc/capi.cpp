@@ -367,8 +367,20 @@ int model_index(const srba_model_t &m) {
 	return m.pose_kind == SRBA_POSE_SE2 ? 0 : (m.obs_kind == SRBA_OBS_CARTESIAN3D ? 1 : (m.obs_kind == SRBA_OBS_MONO ? 2 : 3));
 }
 
+// FMAs of one linearisation + Schur reduction: areas above ~1e6 are throughput-bound on one SM (SE(3) landmark areas),
+// below they are latency-bound (graph-SLAM areas, even with loop closures) and gain nothing from more SMs.
+bool heavy_problem(const srba_problem_t &p) {
+	const int P = p.model.pose_kind == SRBA_POSE_SE2 ? 3 : 6, o = obs_dims(p.model.obs_kind);
+	const double w = (double)p.n_blkA * o * P * 10 + (double)p.n_blkF * o * 3 * 10 + ((double)p.n_HAp_terms * P * P + (double)p.n_HApf_terms * P * 3) * o +
+	                 (double)p.n_S_terms * P * P * 3;
+	return w > 1e6;
+}
+// A cluster takes 8 SMs: it shortens the LATENCY of a heavy area, while a batch with many heavy areas already fills the
+// GPU with one CTA per area.
+bool clusters_pay(int n_heavy) { return n_heavy > 0 && n_heavy <= 36; }
+
 // Fills the header's layout fields; when `base` != NULL also copies the arrays.
-void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_cap, int want_dense, TileSymbolic &sy) {
+void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_cap, int want_dense, TileSymbolic &sy, bool allow_cluster) {
 	std::memset(&h, 0, sizeof(h));
 	h.model = p.model;
 	h.n_edges = p.n_edges; h.n_unk_edges = p.n_unk_edges; h.n_lms = p.n_lms; h.n_unk_lms = p.n_unk_lms; h.n_pairs = p.n_pairs;
@@ -392,12 +404,25 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 		else sy.clear();
 	}
 	static const bool force_blocked = [] { const char *e = std::getenv("SRBA_B200_SOLVER"); return e && std::string(e) == "blocked"; }();  // tests
-	const int reg_scratch = (sy.ok && !force_blocked) ? srba_chol_reg_scratch_doubles(model, h.n_dense, sy.on_chip ? (int)sy.tile_ij.size() : 0) : -1;
+	// ---- team size: large areas (their core arrays overflow one SM's shared memory: SE(3) landmark areas, SE(2) areas
+	// with loop closures) are solved by a CLUSTER of 8 CTAs with everything in the L2-resident workspace
+	// (lm_kernel_cluster.cu); SRBA_B200_CLUSTER=0/1 forces the choice (tests)
+	static const int force_cluster = [] { const char *e = std::getenv("SRBA_B200_CLUSTER"); return e ? std::atoi(e) : -1; }();
+	bool cluster = false;
+	if (sy.ok && !force_blocked) {
+		const uint64_t demand = (uint64_t)sy.tile_ij.size() * 96 + (uint64_t)2 * p.n_pairs * S * 8 + (uint64_t)p.n_blkA * o * P * 8 + (uint64_t)p.n_blkF * o * 3 * 8 +
+		                        (uint64_t)p.n_HAp * P * P * 8 + (uint64_t)2 * p.n_HApf * P * 3 * 8;
+		cluster = force_cluster >= 0 ? force_cluster != 0 : (allow_cluster && heavy_problem(p) && demand > (uint64_t)cfg.smem_bytes);
+	}
+	h.cluster = cluster ? 1 : 0;
+	const SrbaKernelCfg kcfg = cluster ? srba_kernel_cfg(model + 4) : cfg;
+	const bool tiles_on_chip = sy.on_chip && !cluster;
+	const int reg_scratch = (sy.ok && !force_blocked) ? srba_chol_reg_scratch_doubles(cluster ? model + 4 : model, h.n_dense, tiles_on_chip ? (int)sy.tile_ij.size() : 0) : -1;
 	uint64_t scratch_bytes;
 	if (reg_scratch >= 0) {
 		h.chol_mode = SRBA_CHOL_REG;
 		h.ldl_n_tiles = (int)sy.tile_ij.size();
-		h.ldl_tiles_in_ws = sy.on_chip ? 0 : 1;
+		h.ldl_tiles_in_ws = tiles_on_chip ? 0 : 1;
 		h.ldl_n_phases = sy.n_phases;
 		scratch_bytes = (uint64_t)reg_scratch * 8;
 	} else {
@@ -487,7 +512,7 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 	{
 		Layout A;
 		h.sm_scratch = (uint32_t)A.add(scratch_bytes);
-		const uint64_t budget = (uint64_t)cfg.smem_bytes;
+		const uint64_t budget = cluster ? 0 : (uint64_t)kcfg.smem_bytes;  // a cluster keeps every array in the global workspace
 		struct Cand { int is_img, id; };
 		static const Cand order[] = {
 			{0, SRBA_W_edge_cur}, {0, SRBA_W_edge_bak}, {0, SRBA_W_grad}, {0, SRBA_W_delta}, {0, SRBA_W_lm_cur}, {0, SRBA_W_lm_bak},
@@ -649,9 +674,9 @@ struct srba_batch {
 	std::vector<TileSymbolic> sym;
 	std::vector<uint64_t> img_off, ws_off, res_off;
 	std::vector<int32_t> order;      // grouped by model, cost-descending inside each group
-	int group_begin[5] = {0, 0, 0, 0, 0};
-	int group_max_n[4] = {0, 0, 0, 0};
-	int group_smem[4] = {0, 0, 0, 0};  // largest planned shared-memory arena of each model group
+	int group_begin[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // 4 models x {one CTA, 8-CTA cluster} per problem
+	int group_max_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	int group_smem[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // largest planned shared-memory arena of each group
 	uint64_t tab_img_off = 0, tab_ws_off = 0, tab_res_off = 0, tab_order = 0;
 	uint64_t img_bytes = 0, ws_bytes = 0, res_bytes = 0;
 	char *h_img = nullptr, *h_res = nullptr;
@@ -681,9 +706,9 @@ void srba_b200_batch_destroy(srba_batch_t *b) {
 	delete b;
 }
 
-static srba_batch_t *batch_create_impl(int32_t n, const srba_problem_t *const *in, int32_t trace_cap, Pool *pool);
+static srba_batch_t *batch_create_impl(int32_t n, const srba_problem_t *const *in, int32_t trace_cap, Pool *pool, int allow_cluster = -1);
 srba_batch_t *srba_b200_batch_create(int32_t n, const srba_problem_t *const *in, int32_t trace_cap) { return batch_create_impl(n, in, trace_cap, nullptr); }
-static srba_batch_t *batch_create_impl(int32_t n, const srba_problem_t *const *in, int32_t trace_cap, Pool *pool) {
+static srba_batch_t *batch_create_impl(int32_t n, const srba_problem_t *const *in, int32_t trace_cap, Pool *pool, int allow_cluster) {
 	if (n <= 0 || !in) { fail(SRBA_ERR_BAD_ARGUMENT, "empty batch"); return nullptr; }
 	if (srba_b200_device_count() <= 0) { fail(SRBA_ERR_NO_DEVICE, "no CUDA device: the srba_b200 hot path has no CPU fallback"); return nullptr; }
 	for (int i = 0; i < n; i++)
@@ -704,7 +729,13 @@ static srba_batch_t *batch_create_impl(int32_t n, const srba_problem_t *const *i
 	b->tab_res_off = I.add((uint64_t)n * 8);
 	b->tab_order = I.add((uint64_t)n * 4);
 	uint64_t ws = 0, rs = 0;
-	workers().parallel_for(n, [&](int i) { pack_problem(*in[i], b->hdr[i], nullptr, tcap, want_dense, b->sym[i]); });  // layout + symbolic
+	if (allow_cluster < 0) {  // decided for this batch alone
+		int n_heavy = 0;
+		for (int i = 0; i < n; i++) n_heavy += heavy_problem(*in[i]) ? 1 : 0;
+		allow_cluster = clusters_pay(n_heavy) ? 1 : 0;
+	}
+	const bool ac = allow_cluster != 0;
+	workers().parallel_for(n, [&](int i) { pack_problem(*in[i], b->hdr[i], nullptr, tcap, want_dense, b->sym[i], ac); });  // layout + symbolic
 	for (int i = 0; i < n; i++) {
 		b->img_off[i] = I.add(b->hdr[i].img_bytes);
 		b->ws_off[i] = ws; ws += b->hdr[i].ws_bytes;
@@ -712,16 +743,16 @@ static srba_batch_t *batch_create_impl(int32_t n, const srba_problem_t *const *i
 	}
 	b->img_bytes = I.total(); b->ws_bytes = std::max<uint64_t>(ws, 16); b->res_bytes = std::max<uint64_t>(rs, 16);
 	std::iota(b->order.begin(), b->order.end(), 0);
-	auto model_of = [&](int i) { return model_index(b->hdr[i].model); };
+	auto model_of = [&](int i) { return model_index(b->hdr[i].model) + 4 * b->hdr[i].cluster; };
 	std::stable_sort(b->order.begin(), b->order.end(), [&](int a, int c) {
 		const int ma = model_of(a), mc = model_of(c);
 		if (ma != mc) return ma < mc;
 		return problem_cost(b->hdr[a]) > problem_cost(b->hdr[c]);
 	});
 	{
-		int cnt[4] = {0, 0, 0, 0};
+		int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 		for (int i = 0; i < n; i++) { const int g = model_of(i); cnt[g]++; b->group_max_n[g] = std::max(b->group_max_n[g], b->hdr[i].n_dense); b->group_smem[g] = std::max(b->group_smem[g], (int)b->hdr[i].sm_bytes); }
-		for (int g = 0; g < 4; g++) b->group_begin[g + 1] = b->group_begin[g] + cnt[g];
+		for (int g = 0; g < 8; g++) b->group_begin[g + 1] = b->group_begin[g] + cnt[g];
 	}
 	bool ok;
 	if (pool) {
@@ -744,7 +775,7 @@ static srba_batch_t *batch_create_impl(int32_t n, const srba_problem_t *const *i
 	std::memcpy(b->h_img + b->tab_ws_off, b->ws_off.data(), (size_t)n * 8);
 	std::memcpy(b->h_img + b->tab_res_off, b->res_off.data(), (size_t)n * 8);
 	std::memcpy(b->h_img + b->tab_order, b->order.data(), (size_t)n * 4);
-	workers().parallel_for(n, [&](int i) { pack_problem(*in[i], b->hdr[i], b->h_img + b->img_off[i], tcap, want_dense, b->sym[i]); });  // copy
+	workers().parallel_for(n, [&](int i) { pack_problem(*in[i], b->hdr[i], b->h_img + b->img_off[i], tcap, want_dense, b->sym[i], ac); });  // copy
 	return b;
 }
 
@@ -759,7 +790,7 @@ int srba_b200_batch_run(srba_batch_t *b, void *stream) {
 	if (!b) return fail(SRBA_ERR_BAD_ARGUMENT, "null batch");
 	if (!b->uploaded) return fail(SRBA_ERR_BAD_ARGUMENT, "batch_run before batch_upload");
 	b->launches = 0;
-	for (int g = 0; g < 4; g++) {
+	for (int g = 0; g < 8; g++) {
 		const int cnt = b->group_begin[g + 1] - b->group_begin[g];
 		if (!cnt) continue;
 		// one CTA per problem, dispatched in cost-descending order (largest first)
@@ -859,12 +890,12 @@ int srba_b200_problem_plan(const srba_problem_t *in, int64_t out[8]) {
 	if (rc != SRBA_OK) return rc;
 	DevProblem h;
 	TileSymbolic sy;
-	pack_problem(*in, h, nullptr, 0, 0, sy);
+	pack_problem(*in, h, nullptr, 0, 0, sy, true);
 	int n_img = 0, n_ws = 0;
 	for (int a = 0; a < SRBA_I_COUNT; a++) n_img += (h.img_sm[a] != SRBA_NOT_IN_SMEM && h.img_len[a]) ? 1 : 0;
 	for (int a = 0; a < SRBA_W_COUNT; a++) n_ws += h.ws_sm[a] != SRBA_NOT_IN_SMEM ? 1 : 0;
 	out[0] = (int64_t)h.img_bytes; out[1] = (int64_t)h.ws_bytes; out[2] = (int64_t)h.res_bytes; out[3] = h.sm_bytes;
-	out[4] = h.chol_mode; out[5] = n_img; out[6] = n_ws; out[7] = srba_kernel_cfg(model_index(in->model)).smem_bytes;
+	out[4] = h.chol_mode + 2 * h.cluster; out[5] = n_img; out[6] = n_ws; out[7] = srba_kernel_cfg(model_index(in->model) + 4 * h.cluster).smem_bytes;
 	return SRBA_OK;
 }
 
@@ -885,6 +916,9 @@ int srba_b200_optimize_batch(int32_t n, const srba_problem_t *const *in, srba_re
 	// and solved, chunk c+1 is being packed on the host cores, and results come back chunk by chunk.  All chunks fit the
 	// GPU together (2 CTAs/SM), so the kernels overlap; only the first pack and the last copy-back stay exposed.
 	const int K = n >= 64 ? SRBA_MAX_CHUNKS : 1;
+	int n_heavy = 0;
+	for (int i = 0; i < n; i++) n_heavy += (in[i] && heavy_problem(*in[i])) ? 1 : 0;
+	const int allow_cluster = clusters_pay(n_heavy) ? 1 : 0;
 	srba_batch_t *bt[SRBA_MAX_CHUNKS] = {nullptr, nullptr, nullptr, nullptr};
 	int begin[SRBA_MAX_CHUNKS + 1];
 	for (int c = 0; c <= K; c++) begin[c] = (int)((int64_t)n * c / K);
@@ -893,7 +927,7 @@ int srba_b200_optimize_batch(int32_t n, const srba_problem_t *const *in, srba_re
 	for (int c = 0; c < K && rc == SRBA_OK; c++) {
 		Pool &pool = g_pool[c];
 		const auto tp = now();
-		bt[c] = batch_create_impl(begin[c + 1] - begin[c], in + begin[c], want_dense ? -tcap : tcap, &pool);
+		bt[c] = batch_create_impl(begin[c + 1] - begin[c], in + begin[c], want_dense ? -tcap : tcap, &pool, allow_cluster);
 		t_pack += ms(tp, now());
 		if (!bt[c]) { rc = g_code != SRBA_OK ? g_code : SRBA_ERR_INTERNAL; break; }
 		if (!pool.stream && cudaStreamCreateWithFlags(&pool.stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(SRBA_ERR_CUDA, "cudaStreamCreate failed"); break; }

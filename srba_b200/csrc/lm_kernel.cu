@@ -18,8 +18,25 @@
 
 #include "dev_types.h"
 
-// CTA size is a launch parameter (per-model, srba_kernel_cfg): every stage strides by the run-time block size.
+// One TEAM solves one problem.  Normally the team is one CTA; lm_kernel_cluster.cu compiles this file again with
+// SRBA_CLUSTER = 8 so that a thread-block CLUSTER of 8 CTAs (8 SMs) shares a large problem: stage loops stride over the
+// whole cluster, barriers are cluster barriers, reductions are exchanged through distributed shared memory, and every
+// mutable array lives in the (L2-resident) global workspace.  CTA size is a launch parameter (srba_kernel_cfg).
+#ifdef SRBA_CLUSTER
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+#define LM_RANK ((int)cg::this_cluster().block_rank())
+#define LM_NCTA SRBA_CLUSTER
+#define LM_TID ((int)(cg::this_cluster().block_rank() * blockDim.x + threadIdx.x))
+#define LM_THREADS ((int)(blockDim.x * SRBA_CLUSTER))
+#define LM_BARRIER() cg::this_cluster().sync()
+#else
+#define LM_RANK 0
+#define LM_NCTA 1
+#define LM_TID ((int)threadIdx.x)
 #define LM_THREADS ((int)blockDim.x)
+#define LM_BARRIER() __syncthreads()
+#endif
 #define LM_MAX_WARPS 32
 #define MAXO 4
 
@@ -225,14 +242,23 @@ struct Shared {
 
 // Team-wide reductions with ONE barrier: warp partials go to one of three scratch rows (a row is reused only after at
 // least one other barrier), then every thread combines them in the same fixed order -- identical result on all threads.
+// In a cluster every CTA publishes its warp partials, one cluster barrier, then every thread of every CTA combines all
+// partials (CTA 0 first) -- the same bits everywhere, so all CTAs take the same LM decisions.
 // two sums at once (second value in the upper half of the row)
 __device__ __forceinline__ double team_sum2(double v, double w, double &wsum, Shared &sh, int buf) {
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) { v += __shfl_down_sync(0xffffffffu, v, o); w += __shfl_down_sync(0xffffffffu, w, o); }
 	if ((threadIdx.x & 31) == 0) { sh.red[buf][threadIdx.x >> 5] = v; sh.red[buf][LM_MAX_WARPS + (threadIdx.x >> 5)] = w; }
-	__syncthreads();
+	LM_BARRIER();
 	double s = 0, t = 0;
-	for (int i = 0; i < LM_THREADS / 32; i++) { s += sh.red[buf][i]; t += sh.red[buf][LM_MAX_WARPS + i]; }
+	for (int c = 0; c < LM_NCTA; c++) {
+#ifdef SRBA_CLUSTER
+		const double *red = cg::this_cluster().map_shared_rank(&sh.red[buf][0], c);
+#else
+		const double *red = &sh.red[buf][0];
+#endif
+		for (int i = 0; i < (int)blockDim.x / 32; i++) { s += red[i]; t += red[LM_MAX_WARPS + i]; }
+	}
 	wsum = t;
 	return s;
 }
@@ -240,9 +266,16 @@ __device__ __forceinline__ double team_max(double v, Shared &sh, int buf) {
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
 	if ((threadIdx.x & 31) == 0) sh.red[buf][threadIdx.x >> 5] = v;
-	__syncthreads();
-	double s = sh.red[buf][0];
-	for (int i = 1; i < LM_THREADS / 32; i++) s = fmax(s, sh.red[buf][i]);
+	LM_BARRIER();
+	double s = 0;
+	for (int c = 0; c < LM_NCTA; c++) {
+#ifdef SRBA_CLUSTER
+		const double *red = cg::this_cluster().map_shared_rank(&sh.red[buf][0], c);
+#else
+		const double *red = &sh.red[buf][0];
+#endif
+		for (int i = 0; i < (int)blockDim.x / 32; i++) s = (c == 0 && i == 0) ? red[0] : fmax(s, red[i]);
+	}
 	return s;
 }
 
@@ -254,7 +287,7 @@ __device__ __noinline__ void stage_chain(const View &vs, int n_refresh) {
 	constexpr int S = PoseOps<P>::S;
 	// n_refresh < 0: every pair (update_numeric(set,false)); otherwise the compact list of pairs holding a listed pose
 	const int n = n_refresh < 0 ? v.h->n_pairs : n_refresh;
-	for (int q = threadIdx.x; q < n; q += LM_THREADS) {
+	for (int q = LM_TID; q < n; q += LM_THREADS) {
 		const int t = n_refresh < 0 ? q : v.refresh_idx[q];
 		double accum[S], tmp[S];
 		const int k0 = v.pair_path_ptr[t], k1 = v.pair_path_ptr[t + 1];
@@ -442,10 +475,10 @@ __device__ __noinline__ void stage_jacobians(const View &vs, bool first) {
 	constexpr int O = ObsDims<OBSK>::O;
 	const int nA = v.h->n_blkA, nF = (OBSK == SRBA_OBS_RELPOSES2D) ? 0 : v.h->n_blkF;
 	const bool can_fail = (OBSK == SRBA_OBS_MONO || OBSK == SRBA_OBS_STEREO);
-	for (int i = threadIdx.x; i < v.h->n_obs; i += LM_THREADS) v.valid[i] = 1;
-	__syncthreads();
+	for (int i = LM_TID; i < v.h->n_obs; i += LM_THREADS) v.valid[i] = 1;
+	LM_BARRIER();
 	// pass 1: evaluate every block into its slot of JA/JF scratch (fresh), remember ok flags
-	for (int b = threadIdx.x; b < nA + nF; b += LM_THREADS) {
+	for (int b = LM_TID; b < nA + nF; b += LM_THREADS) {
 		if (b < nA) {
 			double J[O * P];
 			const bool ok = jacob_dh_dAp<P, OBSK>(v, b, J);
@@ -468,9 +501,9 @@ __device__ __noinline__ void stage_jacobians(const View &vs, bool first) {
 		}
 	}
 	if (can_fail) {
-		__syncthreads();
+		LM_BARRIER();
 		// pass 2: commit according to the walk order of each row
-		for (int b = threadIdx.x; b < nA + nF; b += LM_THREADS) {
+		for (int b = LM_TID; b < nA + nF; b += LM_THREADS) {
 			const int obs = b < nA ? v.blkA_obs[b] : v.blkF_obs[b - nA];
 			int first_bad = -1, my_pos = -1;
 			for (int k = v.row_ptr[obs]; k < v.row_ptr[obs + 1]; k++) {
@@ -511,7 +544,7 @@ __device__ __noinline__ void stage_jacobians(const View &vs, bool first) {
 			}
 		}
 	} else if (first) {
-		for (int b = threadIdx.x; b < nA + nF; b += LM_THREADS) {
+		for (int b = LM_TID; b < nA + nF; b += LM_THREADS) {
 			if (b < nA) { if (v.blkA_slotA[b] >= 0) v.slot_listed[v.blkA_slotA[b]] = 1; v.slot_listed[v.blkA_slotD[b]] = 1; }
 			else if (v.blkF_slot[b - nA] >= 0) v.slot_listed[v.blkF_slot[b - nA]] = 1;
 		}
@@ -547,7 +580,7 @@ __device__ __noinline__ void stage_hessian(const View &vs) {
 	const double scale = (h->model.noise_kind == SRBA_NOISE_IDENTITY) ? 1.0 / h->model.noise_std : 1.0;
 	const bool do_scale = (h->model.noise_kind == SRBA_NOISE_IDENTITY);
 	const int nAp = h->n_HAp * P * P, nApf = h->n_HApf * P * 3, nf = h->n_unk_lms * 9;
-	for (int it = threadIdx.x; it < nAp + nApf + nf; it += LM_THREADS) {
+	for (int it = LM_TID; it < nAp + nApf + nf; it += LM_THREADS) {
 		if (it < nAp) {
 			const int blk = it / (P * P), e = it % (P * P), a = e / P, b = e % P;
 			double s = 0;
@@ -594,7 +627,7 @@ __device__ __noinline__ double stage_residuals(const View &vs, double *resid, Sh
 	constexpr int O = ObsDims<OBSK>::O;
 	const DevProblem *h = v.h;
 	double local = 0;
-	for (int i = threadIdx.x; i < h->n_obs; i += LM_THREADS) {
+	for (int i = LM_TID; i < h->n_obs; i += LM_THREADS) {
 		const int s = v.obs_slot[i];
 		const double *z = v.obs_z + (size_t)i * O;
 		double r[O];
@@ -664,7 +697,7 @@ __device__ __noinline__ double stage_gradient(const View &vs, const double *resi
 	const double scale = ident ? 1.0 / h->model.noise_std : 1.0;
 	const int nAp = h->n_unk_edges * P;
 	double gmax = 0;
-	for (int it = threadIdx.x; it < h->n_scalars; it += LM_THREADS) {
+	for (int it = LM_TID; it < h->n_scalars; it += LM_THREADS) {
 		double g = 0;
 		if (it < nAp) {
 			const int col = it / P, a = it % P;
@@ -771,7 +804,7 @@ __device__ __noinline__ void stage_schur(const View &vs, double lambda) {
 	const int nf = h->n_unk_lms, n = h->n_dense;
 	if (nf == 0 && h->s_alias_hap) return;
 	// (1) inv(Hf_kk + lambda I)
-	for (int k = threadIdx.x; k < nf; k += LM_THREADS) {
+	for (int k = LM_TID; k < nf; k += LM_THREADS) {
 		double M[9], inv[9];
 #pragma unroll
 		for (int i = 0; i < 9; i++) M[i] = v.Hf[(size_t)k * 9 + i];
@@ -783,9 +816,9 @@ __device__ __noinline__ void stage_schur(const View &vs, double lambda) {
 			for (int i = 0; i < 9; i++) v.Hf_inv[(size_t)k * 9 + i] = inv[i];
 		}
 	}
-	__syncthreads();
+	LM_BARRIER();
 	// (2) W_ik = HApf_ik * inv_k
-	for (int it = threadIdx.x; it < h->n_HApf * P * 3; it += LM_THREADS) {
+	for (int it = LM_TID; it < h->n_HApf * P * 3; it += LM_THREADS) {
 		const int blk = it / (P * 3), e = it % (P * 3), a = e / 3, b = e % 3;
 		const int k = v.HApf_col[blk];
 		if (!v.lm_inv[k]) continue;
@@ -793,10 +826,10 @@ __device__ __noinline__ void stage_schur(const View &vs, double lambda) {
 		const double *inv = v.Hf_inv + (size_t)k * 9;
 		v.W[it] = Hb[a * 3 + 0] * inv[0 * 3 + b] + Hb[a * 3 + 1] * inv[1 * 3 + b] + Hb[a * 3 + 2] * inv[2 * 3 + b];
 	}
-	__syncthreads();
+	LM_BARRIER();
 	// (3) reduced blocks; (4) reduced gradient
 	const int nS = h->s_alias_hap ? 0 : h->n_S * P * P;
-	for (int it = threadIdx.x; it < nS + n; it += LM_THREADS) {
+	for (int it = LM_TID; it < nS + n; it += LM_THREADS) {
 		if (it < nS) {
 			const int blk = it / (P * P), e = it % (P * P), a = e / P, b = e % P;
 			const int hb = v.S_HAp[blk];
@@ -834,10 +867,10 @@ __device__ __noinline__ void stage_dense_fill(const View &vs, double lambda) {
 	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	const DevProblem *h = v.h;
 	const int n = h->n_dense, ld = h->ld_dense;
-	for (size_t i = threadIdx.x; i < (size_t)n * ld; i += LM_THREADS) v.dense[i] = 0;
-	__syncthreads();
+	for (size_t i = LM_TID; i < (size_t)n * ld; i += LM_THREADS) v.dense[i] = 0;
+	LM_BARRIER();
 	const int nS = h->n_S * P * P;
-	for (int it = threadIdx.x; it < nS + n; it += LM_THREADS) {
+	for (int it = LM_TID; it < nS + n; it += LM_THREADS) {
 		if (it < nS) {
 			const int blk = it / (P * P), e = it % (P * P), a = e / P, b = e % P;
 			const int row = v.S_row[blk], col = v.S_col[blk];
@@ -1062,12 +1095,21 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 	const bool tiles_in_ws = v.h->ldl_tiles_in_ws != 0;
 	double *tile = tiles_in_ws ? v.ldl_tiles : scr;                    // ntiles x 12 (on chip unless the pattern is too large)
 	double *sInv = tiles_in_ws ? scr : scr + 12 * (size_t)ntiles;      // 6 x 12 : inverse pivot blocks of the previous, current and next phase (slot = row % 6)
+	int *chol_ok = &sh.chol_ok;
+#ifdef SRBA_CLUSTER
+	// the pivot chain and the backward pass run on CTA 0: its scratch and flag are read by the other CTAs through
+	// distributed shared memory; the tiles themselves live in the global workspace (the packer guarantees tiles_in_ws)
+	sInv = cg::this_cluster().map_shared_rank(sInv, 0);
+	chol_ok = cg::this_cluster().map_shared_rank(chol_ok, 0);
+#endif
 	double *sAcc = sInv + 72;                  // 3*NTR : backward-pass accumulators
 	const int4 *rowinfo = reinterpret_cast<const int4 *>(v.ldl_row);  // {first tile, end tile, first update, end update}
 	const int32_t *tij = v.ldl_tile_ij, *upd = v.ldl_upd, *src = v.ldl_src, *orow = v.ldl_orow;
-	const int tid = threadIdx.x, NT = LM_THREADS;
+	const int tid = LM_TID, NT = LM_THREADS;   // team-wide thread id / size (one CTA, or the 8 CTAs of a cluster)
 	const int lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
-	const int iwarp = nwarps - 1;              // the warp that carries the pivot chain (its lanes 0..8)
+	const int iwarp = ((int)blockDim.x >> 5) - 1;  // the warp that carries the pivot chain (its lanes 0..17): last warp of CTA 0
+	const int utid = warp < iwarp ? tid : tid - 32; // thread id among the warps that take update items (all but the pivot warp)
+	const int wslot = warp < iwarp ? iwarp - 1 - warp : warp - 1;  // same for the W step
 	// coordinates of this lane inside a 9-lane tile group: element (wa,wb) at column-major padded offset eo
 	const int wg = lane / 9, we = lane - wg * 9, wb = we / 3, wa = we - wb * 3, eo = wb * 4 + wa;
 	// cyclic cofactor of a symmetric 3x3: C(a,b) = d(a1,b1) d(a2,b2) - d(a1,b2) d(a2,b1)
@@ -1086,12 +1128,12 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 		inv[eo] = c / det;
 		// leading minors == LLT's scalar pivots up to positive factors; garbage after a failure is harmless and is
 		// discarded by the single check after the loop
-		if (d00 <= 0 || d00 * d11 - d01 * d01 <= 0 || det <= 0) sh.chol_ok = 0;
+		if (d00 <= 0 || d00 * d11 - d01 * d01 <= 0 || det <= 0) *chol_ok = 0;
 	};
 	// the pivot blocks of the first phase (one or two rows) do not wait for the gather: their 9-lane groups fetch their own
 	// elements and invert them while the other warps gather the remaining tiles
 	if (warp == iwarp) {
-		if (lane == 0) sh.chol_ok = 1;
+		if (lane == 0) *chol_ok = 1;
 		__syncwarp();
 		const bool mine = lane < 9 * pa.y;   // group g handles row g of phase 0
 		const int pt = mine ? rowinfo[wg].x : 0;
@@ -1114,8 +1156,8 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 		}
 	}
 	int2 u_first = make_int2(0, 0);
-	if (warp != iwarp && tid < (pb.x - pa.z) * 9) u_first = *reinterpret_cast<const int2 *>(upd + 2 * (pa.z + tid / 9));
-	__syncthreads();
+	if (warp != iwarp && utid < (pb.x - pa.z) * 9) u_first = *reinterpret_cast<const int2 *>(upd + 2 * (pa.z + utid / 9));
+	LM_BARRIER();
 #ifdef SRBA_SOLVER_TIMERS
 	const long long c_loop = clock64();
 #endif
@@ -1136,9 +1178,9 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 			// y: tile(k,j)).  The first descriptor of a phase is fetched before the previous barrier, and two items are in
 			// flight per thread: for large areas the lists and tiles live in L2.
 #pragma unroll 2
-			for (int q = tid; q < nitems; q += NTU) {
+			for (int q = utid; q < nitems; q += NTU) {
 				const int ui = q / 9, e = q - ui * 9, b = e / 3, a = e - b * 3;
-				const int2 u = q == tid ? u_first : *reinterpret_cast<const int2 *>(upd + 2 * (u0 + ui));
+				const int2 u = q == utid ? u_first : *reinterpret_cast<const int2 *>(upd + 2 * (u0 + ui));
 				const double *Ik = (u0 + ui < umid) ? Ik0 : Ik1;
 				const double *Ti = tile + (u.x >> 16) * 12 + a * 4;
 				const double *Tj = tile + u.y * 12 + b * 4;
@@ -1154,11 +1196,11 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 			}
 			// first update descriptor of the NEXT phase, in the shadow of this phase's barrier
 			u_first = make_int2(0, 0);
-			if (tid < (nb.x - na.z) * 9) u_first = *reinterpret_cast<const int2 *>(upd + 2 * (na.z + tid / 9));
+			if (utid < (nb.x - na.z) * 9) u_first = *reinterpret_cast<const int2 *>(upd + 2 * (na.z + utid / 9));
 			// ---- W: the off-diagonal tiles of the previous phase's rows become W = inv(D) T in place (3 tiles per warp and round)
 			if (m > 0) {
 #pragma unroll 1
-				for (int base = prev_t0 + 3 * (iwarp - 1 - warp); base < prev_t1; base += 3 * (nwarps - 1)) {
+				for (int base = prev_t0 + 3 * wslot; base < prev_t1; base += 3 * (nwarps - 1)) {
 					const int tl = base + wg;
 					const bool second = tl >= prev_tm;
 					const bool act = lane < 27 && tl < prev_t1 && tl != prev_t0 && tl != prev_tm;  // not the diagonal tiles
@@ -1202,9 +1244,9 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 		prev_t0 = pc.z; prev_tm = nrows > 1 ? pc.w : pd.x; prev_t1 = pd.x;
 		prev_slot0 = slot0; slot0 = nslot0;
 		pa = na; pb = nb; pc = nc; pd = nd;
-		__syncthreads();
+		LM_BARRIER();
 	}
-	if (!sh.chol_ok) return false;
+	if (!*chol_ok) return false;
 #ifdef SRBA_SOLVER_TIMERS
 	const long long c_back = clock64();
 #endif
@@ -1260,10 +1302,10 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 			}
 		}
 	}
-	__syncthreads();
+	LM_BARRIER();
 #pragma unroll 1
 	for (int i = tid; i < n; i += NT) { const int r = i / 3; v.delta[3 * orow[r] + (i - 3 * r)] = sAcc[i]; }  // back to the reference's unknown order
-	__syncthreads();
+	LM_BARRIER();
 #ifdef SRBA_SOLVER_TIMERS
 	if (tid == 0) {
 		const long long c_end = clock64();
@@ -1321,7 +1363,7 @@ __device__ __noinline__ void stage_features(const View &vs) {
 	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	const DevProblem *h = v.h;
 	const int n = h->n_dense;
-	for (int k = threadIdx.x; k < h->n_unk_lms; k += LM_THREADS) {
+	for (int k = LM_TID; k < h->n_unk_lms; k += LM_THREADS) {
 		double *d = v.delta + n + (size_t)k * 3;
 		if (!v.lm_inv[k]) { d[0] = 0; d[1] = 0; d[2] = 0; continue; }  // delta_eps.tail().setZero()
 		double *gf = v.grad + n + (size_t)k * 3;
@@ -1349,7 +1391,7 @@ __device__ __noinline__ void stage_update(const View &vs, int n_listed) {
 	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	constexpr int S = PoseOps<P>::S;
 	const DevProblem *h = v.h;
-	for (int i = threadIdx.x; i < h->n_unk_edges; i += LM_THREADS) {
+	for (int i = LM_TID; i < h->n_unk_edges; i += LM_THREADS) {
 		double *ep = v.edge_cur + (size_t)v.unk_edge[i] * S;
 		double oldp[S], incr[S], np[S];
 #pragma unroll
@@ -1359,14 +1401,14 @@ __device__ __noinline__ void stage_update(const View &vs, int n_listed) {
 #pragma unroll
 		for (int k = 0; k < S; k++) ep[k] = np[k];
 	}
-	for (int i = threadIdx.x; i < h->n_unk_lms; i += LM_THREADS) {
+	for (int i = LM_TID; i < h->n_unk_lms; i += LM_THREADS) {
 		double *lp = v.lm_cur + (size_t)v.unk_lm[i] * 3;
 		const double *d = v.delta + h->n_dense + (size_t)i * 3;
 #pragma unroll
 		for (int k = 0; k < 3; k++) { v.lm_bak[(size_t)i * 3 + k] = lp[k]; lp[k] += d[k]; }
 	}
 	// only the LISTED directed entries are ever restored (optimize_edges.h:664-670): back up just those, compactly
-	for (int q = threadIdx.x; q < n_listed * S; q += LM_THREADS) v.slot_bak[q] = v.slot[(size_t)v.listed_idx[q / S] * S + (q % S)];
+	for (int q = LM_TID; q < n_listed * S; q += LM_THREADS) v.slot_bak[q] = v.slot[(size_t)v.listed_idx[q / S] * S + (q % S)];
 }
 // rejected step (impl/optimize_edges.h:660-680): only the LISTED directed entries of the numeric ST are restored.
 template <int P>
@@ -1374,9 +1416,9 @@ __device__ __noinline__ void stage_restore(const View &vs, int n_listed) {
 	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	constexpr int S = PoseOps<P>::S;
 	const DevProblem *h = v.h;
-	for (int i = threadIdx.x; i < h->n_unk_edges * S; i += LM_THREADS) v.edge_cur[(size_t)v.unk_edge[i / S] * S + (i % S)] = v.edge_bak[i];
-	for (int i = threadIdx.x; i < h->n_unk_lms * 3; i += LM_THREADS) v.lm_cur[(size_t)v.unk_lm[i / 3] * 3 + (i % 3)] = v.lm_bak[i];
-	for (int q = threadIdx.x; q < n_listed * S; q += LM_THREADS) v.slot[(size_t)v.listed_idx[q / S] * S + (q % S)] = v.slot_bak[q];
+	for (int i = LM_TID; i < h->n_unk_edges * S; i += LM_THREADS) v.edge_cur[(size_t)v.unk_edge[i / S] * S + (i % S)] = v.edge_bak[i];
+	for (int i = LM_TID; i < h->n_unk_lms * 3; i += LM_THREADS) v.lm_cur[(size_t)v.unk_lm[i / 3] * 3 + (i % 3)] = v.lm_bak[i];
+	for (int q = LM_TID; q < n_listed * S; q += LM_THREADS) v.slot[(size_t)v.listed_idx[q / S] * S + (q % S)] = v.slot_bak[q];
 }
 
 // ------------------------------------------------------------------------------------------------ the LM program
@@ -1385,7 +1427,7 @@ __device__ __noinline__ void stage_restore(const View &vs, int n_listed) {
 #ifdef SRBA_SOLVER_TIMERS
 #define STAGE(id)                                            \
 	do {                                                     \
-		if (threadIdx.x == 0) {                              \
+		if (LM_TID == 0) {                              \
 			const unsigned long long t_ = clock64();         \
 			sh.stage_cycles[id] += t_ - sh.t_last;           \
 			sh.t_last = t_;                                  \
@@ -1407,7 +1449,7 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 	{
 		const uint32_t *src = reinterpret_cast<const uint32_t *>(gh);
 		uint32_t *dst = reinterpret_cast<uint32_t *>(&sh.hdr);
-		for (int i = threadIdx.x; i < (int)(sizeof(DevProblem) / 4); i += LM_THREADS) dst[i] = src[i];
+		for (int i = threadIdx.x; i < (int)(sizeof(DevProblem) / 4); i += blockDim.x) dst[i] = src[i];  // every CTA of the team keeps its own copy
 	}
 	__syncthreads();
 	const DevProblem *h = &sh.hdr;
@@ -1420,7 +1462,7 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 		const uint4 *src = reinterpret_cast<const uint4 *>(img + h->img_off[a]);
 		uint4 *dst = reinterpret_cast<uint4 *>(dyn + h->img_sm[a]);
 		const int n16 = (int)((h->img_len[a] + 15) >> 4);
-		for (int i = threadIdx.x; i < n16; i += LM_THREADS) dst[i] = src[i];
+		for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
 	}
 	const int n = h->n_dense, nsc = h->n_scalars;
 	const int nObsRows = h->n_total_obs_rows;
@@ -1429,21 +1471,22 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 	{
 		const double *ge = reinterpret_cast<const double *>(img + h->img_off[SRBA_I_edge_pose]);
 		const double *gl = reinterpret_cast<const double *>(img + h->img_off[SRBA_I_lm_pos]);
-		for (size_t i = threadIdx.x; i < (size_t)h->n_edges * S; i += LM_THREADS) v.edge_cur[i] = ge[i];
-		for (size_t i = threadIdx.x; i < (size_t)h->n_lms * 3; i += LM_THREADS) v.lm_cur[i] = gl[i];
+		for (size_t i = LM_TID; i < (size_t)h->n_edges * S; i += LM_THREADS) v.edge_cur[i] = ge[i];
+		for (size_t i = LM_TID; i < (size_t)h->n_lms * 3; i += LM_THREADS) v.lm_cur[i] = gl[i];
 	}
-	for (int i = threadIdx.x; i < 2 * h->n_pairs; i += LM_THREADS) v.slot_listed[i] = 0;
+	for (int i = LM_TID; i < 2 * h->n_pairs; i += LM_THREADS) v.slot_listed[i] = 0;
 	if (threadIdx.x == 0) {
 		if (h->model.sensor_pose_kind == SRBA_SENSORPOSE_SE3) PoseOps<6>::inverse(sh.sensor_inv, h->model.sensor_pose);
 		sh.status = SRBA_OK;
 	}
-	__syncthreads();
+	LM_BARRIER();
 	// E. update_numeric(set,false)  (optimize_edges.h:256)
 	stage_chain<P>(v, -1);
-	__syncthreads();
+	LM_BARRIER();
 	// F/G. validity reset + recompute_all_Jacobians (:269-276)
 	stage_jacobians<P, OBSK>(v, true);
-	__syncthreads();
+	LM_BARRIER();
+	// (in a cluster every CTA builds the same two lists: identical values to the same addresses, and its own counts)
 	if (threadIdx.x < 32) {  // compact list of the listed directed entries (ascending), built once by one warp
 		int cnt = 0;
 		for (int base = 0; base < 2 * h->n_pairs; base += 32) {
@@ -1468,16 +1511,16 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 	}
 	// J. Hessian (:329-331)
 	stage_hessian<P, OBSK>(v);
-	__syncthreads();
+	LM_BARRIER();
 	// L. lambda0 = tau * max diag (:365-390)
 	double dmax = 0;
-	for (int b = threadIdx.x; b < h->n_HAp; b += LM_THREADS)
+	for (int b = LM_TID; b < h->n_HAp; b += LM_THREADS)
 		if (v.HAp_row[b] == v.HAp_col[b]) {
 			double m = v.HAp[(size_t)b * P * P];
 			for (int k = 1; k < P; k++) m = fmax(m, v.HAp[(size_t)b * P * P + k * P + k]);
 			dmax = fmax(dmax, m);
 		}
-	for (int k = threadIdx.x; k < h->n_unk_lms; k += LM_THREADS)
+	for (int k = LM_TID; k < h->n_unk_lms; k += LM_THREADS)
 		dmax = fmax(dmax, fmax(v.Hf[(size_t)k * 9], fmax(v.Hf[(size_t)k * 9 + 4], v.Hf[(size_t)k * 9 + 8])));
 	dmax = team_max(dmax, sh, 1);
 	// M. residuals (:395-404)
@@ -1515,7 +1558,7 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 		}
 	};
 	if (threadIdx.x == 0) advance();
-	__syncthreads();
+	LM_BARRIER();
 	STAGE(ST_INIT);
 
 	{
@@ -1524,15 +1567,15 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 			const int trial = sh.trials;
 			if (!(h->n_unk_lms == 0 && h->s_alias_hap)) {  // relative graph-SLAM: the reduced system IS H_Ap
 				stage_schur<P>(v, lambda);
-				__syncthreads();
+				LM_BARRIER();
 			}
 			const bool reg = (h->chol_mode == SRBA_CHOL_REG);
 			if (!reg || h->want_dense) {
 				stage_dense_fill<P>(v, lambda);
-				__syncthreads();
+				LM_BARRIER();
 				if (h->want_dense) {  // extra_results.hessian = denseH of the last solve (lev-marq_solvers.h:582-586)
-					for (size_t i = threadIdx.x; i < (size_t)n * n; i += LM_THREADS) v.r_dense[i] = v.dense[(i / n) * h->ld_dense + (i % n)];
-					__syncthreads();
+					for (size_t i = LM_TID; i < (size_t)n * n; i += LM_THREADS) v.r_dense[i] = v.dense[(i / n) * h->ld_dense + (i % n)];
+					LM_BARRIER();
 				}
 			}
 			STAGE(ST_SCHUR);
@@ -1554,8 +1597,8 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 					advance();
 				}
 				if (trial < h->trace_cap)
-					for (int i = threadIdx.x; i < nsc; i += LM_THREADS) v.r_trace_delta[(size_t)trial * nsc + i] = 0;
-				__syncthreads();
+					for (int i = LM_TID; i < nsc; i += LM_THREADS) v.r_trace_delta[(size_t)trial * nsc + i] = 0;
+				LM_BARRIER();
 				STAGE(ST_CTRL);
 				continue;
 			}
@@ -1563,19 +1606,19 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 			STAGE(ST_BACKSUB);
 			if (h->n_unk_lms > 0) {
 				stage_features<P>(v);
-				__syncthreads();
+				LM_BARRIER();
 			}
 			STAGE(ST_FEATURES);
 			stage_update<P>(v, sh.n_listed);
-			__syncthreads();
+			LM_BARRIER();
 			STAGE(ST_UPDATE);
 			stage_chain<P>(v, sh.n_refresh);  // update_numeric(set, true) (:565)
-			__syncthreads();
+			LM_BARRIER();
 			STAGE(ST_CHAIN);
 			double *new_resid = v.resid[sh.cur ^ 1];
 			// rho (:585): its denominator rides along in the residual reduction
 			double dl = 0;
-			for (int i = threadIdx.x; i < nsc; i += LM_THREADS) dl += v.delta[i] * (lambda * v.delta[i] + v.grad[i]);
+			for (int i = LM_TID; i < nsc; i += LM_THREADS) dl += v.delta[i] * (lambda * v.delta[i] + v.grad[i]);
 			double denom;
 			const double new_err = stage_residuals<P, OBSK>(v, new_resid, sh, dl, &denom);
 			STAGE(ST_RESID);
@@ -1589,16 +1632,16 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 					double *tr = v.r_trace + (size_t)trial * 6;
 					tr[0] = lambda; tr[1] = 1; tr[2] = rho; tr[3] = new_err; tr[4] = accept ? 1 : 0; tr[5] = do_relinearize ? 1 : 0;
 				}
-				for (int i = threadIdx.x; i < nsc; i += LM_THREADS) v.r_trace_delta[(size_t)trial * nsc + i] = v.delta[i];
+				for (int i = LM_TID; i < nsc; i += LM_THREADS) v.r_trace_delta[(size_t)trial * nsc + i] = v.delta[i];
 			}
 			STAGE(ST_RHO);
 			if (accept) {
 				if (do_relinearize) {  // :606-629
 					stage_jacobians<P, OBSK>(v, false);
-					__syncthreads();
+					LM_BARRIER();
 					STAGE(ST_JACOB);
 					stage_hessian<P, OBSK>(v);
-					__syncthreads();
+					LM_BARRIER();
 					STAGE(ST_HESS);
 				}
 				double gm = stage_gradient<P, OBSK>(v, new_resid);  // :633
@@ -1628,18 +1671,18 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 					advance();
 				}
 			}
-			__syncthreads();
+			LM_BARRIER();
 			STAGE(ST_CTRL);
 		}
 	}
-	__syncthreads();
+	LM_BARRIER();
 	// Q/S. outputs
-	for (size_t i = threadIdx.x; i < (size_t)h->n_unk_edges * S; i += LM_THREADS) v.r_edge_pose[i] = v.edge_cur[(size_t)v.unk_edge[i / S] * S + (i % S)];
-	for (int i = threadIdx.x; i < h->n_unk_lms * 3; i += LM_THREADS) v.r_lm_pos[i] = v.lm_cur[(size_t)v.unk_lm[i / 3] * 3 + (i % 3)];
-	for (size_t i = threadIdx.x; i < (size_t)2 * h->n_pairs * S; i += LM_THREADS) v.r_slot_pose[i] = v.slot[i];
-	for (int i = threadIdx.x; i < h->n_obs; i += LM_THREADS) v.r_obs_valid[i] = v.valid[i];
-	for (int i = threadIdx.x; i < h->n_unk_lms; i += LM_THREADS) v.r_lm_inv[i] = sh.trials > 0 ? v.lm_inv[i] : 0;
-	for (int i = threadIdx.x; i < h->n_unk_lms * 9; i += LM_THREADS) v.r_Hf_diag[i] = v.Hf[i];
+	for (size_t i = LM_TID; i < (size_t)h->n_unk_edges * S; i += LM_THREADS) v.r_edge_pose[i] = v.edge_cur[(size_t)v.unk_edge[i / S] * S + (i % S)];
+	for (int i = LM_TID; i < h->n_unk_lms * 3; i += LM_THREADS) v.r_lm_pos[i] = v.lm_cur[(size_t)v.unk_lm[i / 3] * 3 + (i % 3)];
+	for (size_t i = LM_TID; i < (size_t)2 * h->n_pairs * S; i += LM_THREADS) v.r_slot_pose[i] = v.slot[i];
+	for (int i = LM_TID; i < h->n_obs; i += LM_THREADS) v.r_obs_valid[i] = v.valid[i];
+	for (int i = LM_TID; i < h->n_unk_lms; i += LM_THREADS) v.r_lm_inv[i] = sh.trials > 0 ? v.lm_inv[i] : 0;
+	for (int i = LM_TID; i < h->n_unk_lms * 9; i += LM_THREADS) v.r_Hf_diag[i] = v.Hf[i];
 	if (threadIdx.x == 0) {
 		srba_stats_t *st = v.stats;
 		st->num_iters = sh.iter;
@@ -1668,25 +1711,30 @@ __global__ void __launch_bounds__(NT, MINB) srba_lm_batch_kernel(const char *img
                                                                           const uint64_t *res_off, const int32_t *order, int n_problems) {
 	__shared__ Shared sh;
 	extern __shared__ __align__(16) char dyn_smem[];
-	for (int q = blockIdx.x; q < n_problems; q += gridDim.x) {
+	for (int q = blockIdx.x / LM_NCTA; q < n_problems; q += gridDim.x / LM_NCTA) {
 		const int pi = order[q];
 		const char *pimg = img + img_off[pi];
 		const DevProblem *h = reinterpret_cast<const DevProblem *>(pimg);
 		lm_program<P, OBSK, TPT>(h, pimg, ws + ws_off[pi], res + res_off[pi], sh, dyn_smem);
-		__syncthreads();
+		LM_BARRIER();
 	}
 }
 
 }  // namespace
 
+#ifndef SRBA_CLUSTER
 // Per-model kernel configuration: CTA size, register tiles per thread, dynamic shared memory per CTA.
-//   SE2+RelativePoses2D: 128 regs -> 2 CTAs/SM, 2 x (108 KB dynamic + ~3 KB static + 1 KB reserved) of the SM's 228 KB;  SE3 models: 255 regs -> 1 CTA/SM, 220 KB.
+//   SE2+RelativePoses2D: 168 regs x 192 threads -> 2 CTAs/SM, 2 x (108 KB dynamic + ~5 KB static + 1 KB reserved) of the SM's
+//   228 KB;  SE3 models: 1024 threads x 64 regs -> 1 CTA/SM, 220 KB.
+//   Models 4..7 are the CLUSTER variants of 0..3 (lm_kernel_cluster.cu): 8 CTAs x 256 threads per problem, every mutable
+//   array in the global workspace, only the solver's pivot scratch on chip.
 #define SE2_NT 192
 #define SE3_NT 1024
 #define SE2_TPT 2
 #define SE3_TPT 4
 extern "C" SrbaKernelCfg srba_kernel_cfg(int model) {
 	SrbaKernelCfg c;
+	if (model >= 4) { c.threads = 256; c.tpt = 0; c.smem_bytes = 48 * 1024; return c; }
 	c.threads = model == 0 ? SE2_NT : SE3_NT;
 	c.tpt = model == 0 ? SE2_TPT : SE3_TPT;
 	c.smem_bytes = model == 0 ? 108 * 1024 : 220 * 1024;
@@ -1702,9 +1750,14 @@ extern "C" int srba_chol_reg_scratch_doubles(int model, int n_dense, int n_tiles
 	return (int)need;
 }
 
-// model: 0 = SE2+RelativePoses2D, 1 = SE3+Cartesian3D, 2 = SE3+Mono, 3 = SE3+Stereo.  `order` lists the problems of that model.
+extern "C" int srba_launch_lm_batch_cluster(int model, const char *img, const uint64_t *img_off, char *ws, const uint64_t *ws_off, char *res,
+                                            const uint64_t *res_off, const int32_t *order, int n_problems, int smem_bytes, void *stream);
+
+// model: 0 = SE2+RelativePoses2D, 1 = SE3+Cartesian3D, 2 = SE3+Mono, 3 = SE3+Stereo; 4..7 = the same on 8-CTA clusters.
+// `order` lists the problems of that group.
 extern "C" int srba_launch_lm_batch(int model, const char *img, const uint64_t *img_off, char *ws, const uint64_t *ws_off, char *res,
                                     const uint64_t *res_off, const int32_t *order, int n_problems, int grid, int smem_bytes, void *stream) {
+	if (model >= 4) return srba_launch_lm_batch_cluster(model - 4, img, img_off, ws, ws_off, res, res_off, order, n_problems, smem_bytes, stream);
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
 	// dynamic shared memory = the largest arena any problem of this group was planned with (<= the model's budget);
 	// what the batch does not need stays available to L1
@@ -1727,3 +1780,36 @@ extern "C" int srba_launch_lm_batch(int model, const char *img, const uint64_t *
 #undef LAUNCH
 	return (int)cudaGetLastError();
 }
+#else   // SRBA_CLUSTER: the same program on clusters of SRBA_CLUSTER CTAs (one cluster per problem)
+extern "C" int srba_launch_lm_batch_cluster(int model, const char *img, const uint64_t *img_off, char *ws, const uint64_t *ws_off, char *res,
+                                            const uint64_t *res_off, const int32_t *order, int n_problems, int smem_bytes, void *stream) {
+	constexpr int NT = 256;
+	const size_t smem = (size_t)std::min(std::max(smem_bytes, 1024), 48 * 1024);
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((unsigned)(n_problems * SRBA_CLUSTER), 1, 1);
+	cfg.blockDim = dim3(NT, 1, 1);
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = static_cast<cudaStream_t>(stream);
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = SRBA_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = 1;
+#define LAUNCH(P, OBSK)                                                                                                       \
+	do {                                                                                                                      \
+		auto kern = srba_lm_batch_kernel<P, OBSK, NT, 1, 0>;                                                                  \
+		cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                   \
+		const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, img, img_off, ws, ws_off, res, res_off, order, n_problems);      \
+		if (e != cudaSuccess) return (int)e;                                                                                  \
+	} while (0)
+	switch (model) {
+		case 0: LAUNCH(3, SRBA_OBS_RELPOSES2D); break;
+		case 1: LAUNCH(6, SRBA_OBS_CARTESIAN3D); break;
+		case 2: LAUNCH(6, SRBA_OBS_MONO); break;
+		case 3: LAUNCH(6, SRBA_OBS_STEREO); break;
+		default: return (int)cudaErrorInvalidValue;
+	}
+#undef LAUNCH
+	return (int)cudaGetLastError();
+}
+#endif

@@ -211,24 +211,27 @@ def test_batch_matches_single_and_is_repeatable():
     assert b.kernel_launches >= 1 and b.h2d_bytes > 0 and b.d2h_bytes > 0
 
 
-def test_blocked_fallback_matches_onchip_solver():
-    """The dense blocked Cholesky (systems whose tiles do not fit on chip) and the on-chip block-sparse L D L^t solver
-    factor the same reduced system: first increment within 1e-9 relative, final edges within 1e-6."""
+def test_blocked_fallback_and_cluster_team_match_the_default_path():
+    """Three ways to run the same LM program: the default (one CTA per area, on-chip block-sparse L D L^t), the dense blocked
+    Cholesky used when the tiles do not fit (SRBA_B200_SOLVER=blocked), and an 8-CTA thread-block cluster per area with
+    every array in the global workspace (SRBA_B200_CLUSTER=1; picked automatically for a few heavy SE(3) areas).
+    First increment within 1e-9 relative, final edges within 1e-6."""
     import json
     import os
     import subprocess
     import sys
     script = os.path.join(os.path.dirname(__file__), "_solve_flats.py")
     runs = []
-    for mode in ("", "blocked"):
-        env = dict(os.environ, SRBA_B200_SOLVER=mode)
-        out = subprocess.run([sys.executable, script], env=env, capture_output=True, text=True, check=True).stdout.strip().splitlines()[-1]
+    for extra in ({}, {"SRBA_B200_SOLVER": "blocked"}, {"SRBA_B200_CLUSTER": "1"}):
+        env = dict(os.environ, **extra)
+        out = subprocess.run([sys.executable, script], env=env, capture_output=True, text=True, check=True, timeout=300).stdout.strip().splitlines()[-1]
         runs.append(json.loads(out))
-    assert len(runs[0]) == len(runs[1]) >= 6
-    for a, b in zip(*runs):
-        assert a["n_unk"] == b["n_unk"] and a["trials"] > 0 and b["trials"] > 0
-        assert rel_err(a["first_delta"], b["first_delta"]) <= 1e-9
-        assert rel_err(a["edge"], b["edge"]) <= 1e-6
+    assert len(runs[0]) == len(runs[1]) == len(runs[2]) >= 6
+    for other in runs[1:]:
+        for a, b in zip(runs[0], other):
+            assert a["n_unk"] == b["n_unk"] and a["trials"] > 0 and b["trials"] > 0
+            assert rel_err(a["first_delta"], b["first_delta"]) <= 1e-9
+            assert rel_err(a["edge"], b["edge"]) <= 1e-6
 
 
 def test_pipelined_batch_call_matches_single_calls():
