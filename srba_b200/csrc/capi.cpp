@@ -399,7 +399,7 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 	const SrbaKernelCfg cfg = srba_kernel_cfg(model);
 	if (!base) {  // layout pass: symbolic factorisation (reused by the copy pass)
 		// tiles may take up to 3/4 of the CTA's shared memory (other arrays then spill to the L2-resident workspace)
-		const long max_tiles = std::min(32767L, ((long)cfg.smem_bytes * 3 / 4 / 8 - 73 - h.n_dense) / 12);
+		const long max_tiles = std::min(32767L, ((long)cfg.smem_bytes * 3 / 4 / 8 - 97 - h.n_dense) / 12);
 		if (max_tiles > 0) symbolic_tiles(p, P, max_tiles, sy);
 		else sy.clear();
 	}

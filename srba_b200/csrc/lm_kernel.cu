@@ -1102,7 +1102,8 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 	sInv = cg::this_cluster().map_shared_rank(sInv, 0);
 	chol_ok = cg::this_cluster().map_shared_rank(chol_ok, 0);
 #endif
-	double *sAcc = sInv + 72;                  // 3*NTR : backward-pass accumulators
+	double *sPiv = sInv + 72;                  // 2 x 12 : the two pivot blocks being updated + inverted (kept on chip even when the tiles live in L2)
+	double *sAcc = sPiv + 24;                  // 3*NTR : backward-pass accumulators
 	const int4 *rowinfo = reinterpret_cast<const int4 *>(v.ldl_row);  // {first tile, end tile, first update, end update}
 	const int32_t *tij = v.ldl_tile_ij, *upd = v.ldl_upd, *src = v.ldl_src, *orow = v.ldl_orow;
 	const int tid = LM_TID, NT = LM_THREADS;   // team-wide thread id / size (one CTA, or the 8 CTAs of a cluster)
@@ -1137,9 +1138,9 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 		__syncwarp();
 		const bool mine = lane < 9 * pa.y;   // group g handles row g of phase 0
 		const int pt = mine ? rowinfo[wg].x : 0;
-		if (mine) tile[pt * 12 + eo] = v.S[(src[pt] & 0x1fffffff) + wa * P + wb] + (wa == wb ? lambda : 0.0);
+		if (mine) sPiv[wg * 12 + eo] = v.S[(src[pt] & 0x1fffffff) + wa * P + wb] + (wa == wb ? lambda : 0.0);
 		__syncwarp();
-		if (mine) invert_pivot(tile + pt * 12, sInv + wg * 12);
+		if (mine) invert_pivot(sPiv + wg * 12, sInv + wg * 12);
 	}
 	// gather: tile element <- reduced block element (+lambda on the diagonal); tile column NTR = reduced gradient.
 	// 9 lanes per tile (3 tiles per warp and round); ldl_src: >= 0 offset of the tile's (0,0) in S (bit 30: diagonal tile, bit 29: the tile is the transpose),
@@ -1223,23 +1224,28 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 			// tile (bit 30: it belongs to the phase's second row) and are inverted right away
 			const bool mine = lane < 9 * nnext;
 			const int pt = wg == 0 ? pb.z : pb.w, link = wg == 0 ? pc.x : pc.y;
-			double *Dn = tile + pt * 12;
-			if (mine && link >= 0) {
-				const double *Ts = tile + (link & 0x3fffffff) * 12;
-				const double *Ik = (link >> 30) ? Ik1 : Ik0;
-				const double2 p01 = *reinterpret_cast<const double2 *>(Ts + wa * 4), t01 = *reinterpret_cast<const double2 *>(Ts + wb * 4);
-				const double p2 = Ts[wa * 4 + 2], t2 = Ts[wb * 4 + 2];
-				const double2 i0 = *reinterpret_cast<const double2 *>(Ik), i1 = *reinterpret_cast<const double2 *>(Ik + 4);
-				const double i02 = Ik[2], i12 = Ik[6], i22 = Ik[10];
-				const double w0 = i0.x * t01.x + i0.y * t01.y + i02 * t2;
-				const double w1 = i0.y * t01.x + i1.y * t01.y + i12 * t2;
-				const double w2 = i02 * t01.x + i12 * t01.y + i22 * t2;
-				Dn[eo] = Dn[eo] - p01.x * w0 - p01.y * w1 - p2 * w2;
+			const double *Dn = tile + pt * 12;
+			double *Dp = sPiv + wg * 12;
+			if (mine) {
+				double dv = Dn[eo];
+				if (link >= 0) {
+					const double *Ts = tile + (link & 0x3fffffff) * 12;
+					const double *Ik = (link >> 30) ? Ik1 : Ik0;
+					const double2 p01 = *reinterpret_cast<const double2 *>(Ts + wa * 4), t01 = *reinterpret_cast<const double2 *>(Ts + wb * 4);
+					const double p2 = Ts[wa * 4 + 2], t2 = Ts[wb * 4 + 2];
+					const double2 i0 = *reinterpret_cast<const double2 *>(Ik), i1 = *reinterpret_cast<const double2 *>(Ik + 4);
+					const double i02 = Ik[2], i12 = Ik[6], i22 = Ik[10];
+					const double w0 = i0.x * t01.x + i0.y * t01.y + i02 * t2;
+					const double w1 = i0.y * t01.x + i1.y * t01.y + i12 * t2;
+					const double w2 = i02 * t01.x + i12 * t01.y + i22 * t2;
+					dv = dv - p01.x * w0 - p01.y * w1 - p2 * w2;
+				}
+				Dp[eo] = dv;
 			}
 			__syncwarp();
 			int ns = nslot0 + wg;
 			if (ns >= 6) ns -= 6;
-			if (mine) invert_pivot(Dn, sInv + ns * 12);
+			if (mine) invert_pivot(Dp, sInv + ns * 12);
 		}
 		prev_t0 = pc.z; prev_tm = nrows > 1 ? pc.w : pd.x; prev_t1 = pd.x;
 		prev_slot0 = slot0; slot0 = nslot0;
@@ -1257,6 +1263,9 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 		if (NTR <= 32) ldl_backward_wavefront<1>(tile, rowinfo, tij, sX, NTR, lane);
 		else if (NTR <= 64) ldl_backward_wavefront<2>(tile, rowinfo, tij, sX, NTR, lane);
 		else if (NTR <= 128) ldl_backward_wavefront<4>(tile, rowinfo, tij, sX, NTR, lane);
+#ifdef SRBA_CLUSTER  /* 255 registers per thread: room for 8 rows per lane */
+		else if (NTR <= 256) ldl_backward_wavefront<8>(tile, rowinfo, tij, sX, NTR, lane);
+#endif
 		else {
 			// general size: lane (a, t) multiplies row a of the t-th tile of the row, a 3-step butterfly sums over the tiles;
 			// the next row's record, tile columns and W entries do not depend on x and are fetched one row ahead
@@ -1307,7 +1316,7 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 	for (int i = tid; i < n; i += NT) { const int r = i / 3; v.delta[3 * orow[r] + (i - 3 * r)] = sAcc[i]; }  // back to the reference's unknown order
 	LM_BARRIER();
 #ifdef SRBA_SOLVER_TIMERS
-	if (tid == 0) {
+	if (tid == 0) {  // team thread 0 == thread 0 of CTA 0
 		const long long c_end = clock64();
 		sh.dbg[0] += c_loop - c_entry; sh.dbg[1] += c_back - c_loop; sh.dbg[2] += c_end - c_back;
 	}
@@ -1699,8 +1708,10 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 		unsigned long long *sc = reinterpret_cast<unsigned long long *>(res + h->res_stage_cycles);
 		const unsigned long long t_ = clock64();
 		sh.stage_cycles[ST_OUT] += t_ - sh.t_last;
-		for (int i = 0; i < ST_COUNT; i++) sc[i] = sh.stage_cycles[i];
-		for (int i = 0; i < 8; i++) sc[16 + i] = sh.dbg[i];
+		if (LM_RANK == 0) {  // in a cluster every CTA keeps the same stage clocks; CTA 0 (which carries the pivot chain) reports
+			for (int i = 0; i < ST_COUNT; i++) sc[i] = sh.stage_cycles[i];
+			for (int i = 0; i < 8; i++) sc[16 + i] = sh.dbg[i];
+		}
 	}
 }
 
@@ -1745,7 +1756,7 @@ extern "C" SrbaKernelCfg srba_kernel_cfg(int model) {
 extern "C" int srba_chol_reg_scratch_doubles(int model, int n_dense, int n_tiles_on_chip) {
 	const SrbaKernelCfg c = srba_kernel_cfg(model);
 	const int NTR = n_dense / 3;
-	const long need = 12L * n_tiles_on_chip + 72 + 3L * NTR + 1;
+	const long need = 12L * n_tiles_on_chip + 96 + 3L * NTR + 1;
 	if (need * 8 > (long)c.smem_bytes * 7 / 8) return -1;
 	return (int)need;
 }
