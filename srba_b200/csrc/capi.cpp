@@ -151,10 +151,11 @@ struct TileSymbolic {
 	int n_phases = 0;
 	std::vector<int32_t> orow;      // NTR: tile row in elimination order -> tile row in the reference's unknown order
 	bool on_chip = false;           // the tiles fit the shared-memory budget (else they live in the L2-resident workspace)
+	bool wide = false;              // more than 32767 tiles: update descriptors are {dst, tile(k,i), tile(k,j)} (3 ints)
 	std::vector<int32_t> upd_ptr;   // NTR+1
 	std::vector<int32_t> upd;       // 2 per update: {dst tile | tile(k,i)<<16, tile(k,j)}; the update of the next pivot block is implicit
 	bool ok = false;                // false: too large for the on-chip solver (schedule not built)
-	void clear() { rs.clear(); row.clear(); phase.clear(); n_phases = 0; src.clear(); orow.clear(); on_chip = false; tile_ij.clear(); upd_ptr.clear(); upd.clear(); ok = false; }
+	void clear() { rs.clear(); row.clear(); phase.clear(); n_phases = 0; src.clear(); orow.clear(); on_chip = false; wide = false; tile_ij.clear(); upd_ptr.clear(); upd.clear(); ok = false; }
 };
 // Elimination order of the unknown edges (block level).  The reference's own order is kept whenever its fill fits on chip
 // (a relative graph-SLAM chain is block-banded in that order: no fill at all); areas with loop closures fill the whole band
@@ -202,7 +203,7 @@ void symbolic_tiles(const srba_problem_t &p, int P, long max_tiles_on_chip, Tile
 	const int q = P / 3, np = p.n_unk_edges, ntr = q * np, ntc = ntr + 1;
 	sy.clear();
 	sy.ntr = ntr;
-	if (ntr <= 0 || ntr > 2048) return;
+	if (ntr <= 0 || ntr > 4096) return;
 	// ---- elimination order
 	const int Wb = (np + 63) / 64;
 	std::vector<uint64_t> adj((size_t)np * Wb, 0);
@@ -228,7 +229,9 @@ void symbolic_tiles(const srba_problem_t &p, int P, long max_tiles_on_chip, Tile
 		const long tiles_md = elimination_fill(adj, np, Wb, q, nullptr, &md);
 		if (tiles_md < tiles) { perm = md; tiles = tiles_md; }
 	}
-	if (tiles > 32767) return;  // tile ids are packed in 15/16 bits; such systems use the blocked dense solver
+	if (tiles > (1L << 20)) return;  // > 96 MB of tiles: such systems use the blocked dense solver
+	static const bool force_wide = std::getenv("SRBA_B200_WIDE") != nullptr;  // test hook
+	sy.wide = tiles > 32767 || force_wide;  // tile ids no longer fit 15/16 bits: 3-int update descriptors
 	sy.on_chip = tiles <= max_tiles_on_chip;
 	std::vector<int> inv(np);
 	for (int i = 0; i < np; i++) inv[perm[i]] = i;
@@ -317,20 +320,25 @@ void symbolic_tiles(const srba_problem_t &p, int P, long max_tiles_on_chip, Tile
 	// update schedule: row k's pairs of tiles; the updates of the NEXT phase's pivot blocks are implicit (done by the lanes
 	// that invert those pivots)
 	sy.upd_ptr.assign(ntr + 1, 0);
+	int32_t n_upd = 0;
 	for (int k = 0; k < ntr; k++) {
-		sy.upd_ptr[k] = (int32_t)(sy.upd.size() / 2);
+		sy.upd_ptr[k] = n_upd;
 		for (int a = sy.rs[k] + 1; a < sy.rs[k + 1]; a++) {
 			const int i = sy.tile_ij[a] & 0xffff;
 			if (i >= ntr) break;  // the right-hand side is never a row
 			for (int b = a; b < sy.rs[k + 1]; b++) {
 				const int j = sy.tile_ij[b] & 0xffff;
 				if (i == j && phase_of[i] == phase_of[k] + 1) continue;  // next pivot block
-				sy.upd.push_back(find_tile(i, j) | (a << 16));  // dst | tile(k,i) << 16
-				sy.upd.push_back(b);                             // tile(k,j)
+				if (sy.wide) { sy.upd.push_back(find_tile(i, j)); sy.upd.push_back(a); sy.upd.push_back(b); }
+				else {
+					sy.upd.push_back(find_tile(i, j) | (a << 16));  // dst | tile(k,i) << 16
+					sy.upd.push_back(b);                             // tile(k,j)
+				}
+				n_upd++;
 			}
 		}
 	}
-	sy.upd_ptr[ntr] = (int32_t)(sy.upd.size() / 2);
+	sy.upd_ptr[ntr] = n_upd;
 	// per-row records
 	sy.row.assign(4 * (size_t)(ntr + 1), 0);
 	for (int k = 0; k <= ntr; k++) {
@@ -360,7 +368,7 @@ void symbolic_tiles(const srba_problem_t &p, int P, long max_tiles_on_chip, Tile
 	sy.n_phases = nph;
 	sy.src.resize(sy.tile_ij.size());
 	for (size_t t = 0; t < sy.tile_ij.size(); t++) sy.src[t] = srcmap[(size_t)(sy.tile_ij[t] >> 16) * ntc + (sy.tile_ij[t] & 0xffff)];
-	sy.ok = sy.tile_ij.size() <= 32767;
+	sy.ok = true;
 }
 
 int model_index(const srba_model_t &m) {
@@ -424,6 +432,7 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 		h.ldl_n_tiles = (int)sy.tile_ij.size();
 		h.ldl_tiles_in_ws = tiles_on_chip ? 0 : 1;
 		h.ldl_n_phases = sy.n_phases;
+		h.ldl_wide = sy.wide ? 1 : 0;
 		scratch_bytes = (uint64_t)reg_scratch * 8;
 	} else {
 		h.chol_mode = SRBA_CHOL_BLOCKED;
@@ -869,7 +878,7 @@ int srba_b200_debug_ldl_schedule(const srba_problem_t *in, int32_t counts[6], in
 	const int P = in->model.pose_kind == SRBA_POSE_SE2 ? 3 : 6;
 	TileSymbolic sy;
 	symbolic_tiles(*in, P, max_tiles_on_chip, sy);
-	counts[0] = sy.ntr; counts[1] = (int32_t)sy.tile_ij.size(); counts[2] = (int32_t)(sy.upd.size() / 2); counts[3] = sy.ok ? 1 : 0;
+	counts[0] = sy.ntr; counts[1] = (int32_t)sy.tile_ij.size(); counts[2] = (int32_t)(sy.upd.size() / (sy.wide ? 3 : 2)); counts[3] = (sy.ok && !sy.wide) ? 1 : 0;
 	counts[4] = sy.n_phases; counts[5] = sy.on_chip ? 1 : 0;
 	if (!sy.ok) return SRBA_OK;
 	if (row && tile_ij && src && upd) {

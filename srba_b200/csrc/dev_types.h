@@ -75,6 +75,7 @@ struct DevProblem {
 	int32_t panel_cap;   // SRBA_CHOL_BLOCKED: columns of the staged 8-row panel that fit the scratch
 	int32_t ldl_n_tiles; // SRBA_CHOL_REG: 3x3 tiles of the filled pattern incl. the right-hand-side column
 	int32_t ldl_n_phases; // barrier-separated elimination phases (1 or 2 independent block rows each)
+	int32_t ldl_wide;     // 1: update descriptors are 3 ints {dst, tile(k,i), tile(k,j)} (more than 32767 tiles)
 	int32_t ldl_tiles_in_ws; // 1: the tiles do not fit on chip and live in the workspace array ldl_tiles (L2-resident)
 	int32_t s_alias_hap; // 1: no Schur terms and S block b == H_Ap block b -> the reduced blocks ARE the H_Ap blocks
 	uint32_t sm_scratch; // byte offset of the Cholesky scratch inside the CTA's dynamic shared memory

@@ -1157,7 +1157,8 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 		}
 	}
 	int2 u_first = make_int2(0, 0);
-	if (warp != iwarp && utid < (pb.x - pa.z) * 9) u_first = *reinterpret_cast<const int2 *>(upd + 2 * (pa.z + utid / 9));
+	const bool wide = v.h->ldl_wide != 0;
+	if (!wide && warp != iwarp && utid < (pb.x - pa.z) * 9) u_first = *reinterpret_cast<const int2 *>(upd + 2 * (pa.z + utid / 9));
 	LM_BARRIER();
 #ifdef SRBA_SOLVER_TIMERS
 	const long long c_loop = clock64();
@@ -1181,10 +1182,15 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 #pragma unroll 2
 			for (int q = utid; q < nitems; q += NTU) {
 				const int ui = q / 9, e = q - ui * 9, b = e / 3, a = e - b * 3;
-				const int2 u = q == utid ? u_first : *reinterpret_cast<const int2 *>(upd + 2 * (u0 + ui));
+				int dsti, tii, tji;
+				if (wide) { const int32_t *w3 = upd + 3 * (size_t)(u0 + ui); dsti = w3[0]; tii = w3[1]; tji = w3[2]; }
+				else {
+					const int2 u = q == utid ? u_first : *reinterpret_cast<const int2 *>(upd + 2 * (u0 + ui));
+					dsti = u.x & 0xffff; tii = u.x >> 16; tji = u.y;
+				}
 				const double *Ik = (u0 + ui < umid) ? Ik0 : Ik1;
-				const double *Ti = tile + (u.x >> 16) * 12 + a * 4;
-				const double *Tj = tile + u.y * 12 + b * 4;
+				const double *Ti = tile + (size_t)tii * 12 + a * 4;
+				const double *Tj = tile + (size_t)tji * 12 + b * 4;
 				const double2 p01 = *reinterpret_cast<const double2 *>(Ti), t01 = *reinterpret_cast<const double2 *>(Tj);
 				const double p2 = Ti[2], t2 = Tj[2];
 				const double2 i0 = *reinterpret_cast<const double2 *>(Ik), i1 = *reinterpret_cast<const double2 *>(Ik + 4);
@@ -1192,12 +1198,12 @@ __device__ __noinline__ bool stage_ldl_solve_smem(const View &vs, Shared &sh, do
 				const double w0 = i0.x * t01.x + i0.y * t01.y + i02 * t2;
 				const double w1 = i0.y * t01.x + i1.y * t01.y + i12 * t2;
 				const double w2 = i02 * t01.x + i12 * t01.y + i22 * t2;
-				double *dst = tile + (u.x & 0xffff) * 12 + b * 4 + a;
+				double *dst = tile + (size_t)dsti * 12 + b * 4 + a;
 				*dst = *dst - p01.x * w0 - p01.y * w1 - p2 * w2;
 			}
 			// first update descriptor of the NEXT phase, in the shadow of this phase's barrier
 			u_first = make_int2(0, 0);
-			if (utid < (nb.x - na.z) * 9) u_first = *reinterpret_cast<const int2 *>(upd + 2 * (na.z + utid / 9));
+			if (!wide && utid < (nb.x - na.z) * 9) u_first = *reinterpret_cast<const int2 *>(upd + 2 * (na.z + utid / 9));
 			// ---- W: the off-diagonal tiles of the previous phase's rows become W = inv(D) T in place (3 tiles per warp and round)
 			if (m > 0) {
 #pragma unroll 1
@@ -1745,7 +1751,7 @@ __global__ void __launch_bounds__(NT, MINB) srba_lm_batch_kernel(const char *img
 #define SE3_TPT 4
 extern "C" SrbaKernelCfg srba_kernel_cfg(int model) {
 	SrbaKernelCfg c;
-	if (model >= 4) { c.threads = 256; c.tpt = 0; c.smem_bytes = 48 * 1024; return c; }
+	if (model >= 4) { c.threads = 256; c.tpt = 0; c.smem_bytes = 160 * 1024; return c; }
 	c.threads = model == 0 ? SE2_NT : SE3_NT;
 	c.tpt = model == 0 ? SE2_TPT : SE3_TPT;
 	c.smem_bytes = model == 0 ? 108 * 1024 : 220 * 1024;
@@ -1795,7 +1801,7 @@ extern "C" int srba_launch_lm_batch(int model, const char *img, const uint64_t *
 extern "C" int srba_launch_lm_batch_cluster(int model, const char *img, const uint64_t *img_off, char *ws, const uint64_t *ws_off, char *res,
                                             const uint64_t *res_off, const int32_t *order, int n_problems, int smem_bytes, void *stream) {
 	constexpr int NT = 256;
-	const size_t smem = (size_t)std::min(std::max(smem_bytes, 1024), 48 * 1024);
+	const size_t smem = (size_t)std::min(std::max(smem_bytes, 1024), 160 * 1024);
 	cudaLaunchConfig_t cfg = {};
 	cfg.gridDim = dim3((unsigned)(n_problems * SRBA_CLUSTER), 1, 1);
 	cfg.blockDim = dim3(NT, 1, 1);

@@ -214,7 +214,8 @@ def test_batch_matches_single_and_is_repeatable():
 def test_blocked_fallback_and_cluster_team_match_the_default_path():
     """Three ways to run the same LM program: the default (one CTA per area, on-chip block-sparse L D L^t), the dense blocked
     Cholesky used when the tiles do not fit (SRBA_B200_SOLVER=blocked), and an 8-CTA thread-block cluster per area with
-    every array in the global workspace (SRBA_B200_CLUSTER=1; picked automatically for a few heavy SE(3) areas).
+    every array in the global workspace (SRBA_B200_CLUSTER=1; picked automatically for a few heavy SE(3) areas), the latter
+    also with the 3-int update descriptors of systems with more than 32767 tiles (SRBA_B200_WIDE=1).
     First increment within 1e-9 relative, final edges within 1e-6."""
     import json
     import os
@@ -222,11 +223,11 @@ def test_blocked_fallback_and_cluster_team_match_the_default_path():
     import sys
     script = os.path.join(os.path.dirname(__file__), "_solve_flats.py")
     runs = []
-    for extra in ({}, {"SRBA_B200_SOLVER": "blocked"}, {"SRBA_B200_CLUSTER": "1"}):
+    for extra in ({}, {"SRBA_B200_SOLVER": "blocked"}, {"SRBA_B200_CLUSTER": "1"}, {"SRBA_B200_CLUSTER": "1", "SRBA_B200_WIDE": "1"}):
         env = dict(os.environ, **extra)
         out = subprocess.run([sys.executable, script], env=env, capture_output=True, text=True, check=True, timeout=300).stdout.strip().splitlines()[-1]
         runs.append(json.loads(out))
-    assert len(runs[0]) == len(runs[1]) == len(runs[2]) >= 6
+    assert len(runs[0]) == len(runs[1]) == len(runs[2]) == len(runs[3]) >= 6
     for other in runs[1:]:
         for a, b in zip(runs[0], other):
             assert a["n_unk"] == b["n_unk"] and a["trials"] > 0 and b["trials"] > 0
@@ -322,3 +323,30 @@ def test_full_size_bench_batch_properties():
     for r, x in zip(first, bufs):
         assert x.r.stats.as_dict() == r.stats and np.array_equal(x.edge_pose, r.edge_pose) and np.array_equal(x.slot_pose, r.slot_pose)
     print("256-area batch: %d LM trials, all deterministic" % trials)
+
+
+def test_whole_map_single_area_parity():
+    """BASELINE configs #2/#3 in their whole-map reading at a size the oracle finishes in seconds: every edge and landmark
+    of a 100-keyframe SE(3) map in ONE optimize_local_area(root, 10^6) problem (n_p ~ 110 -> a 660-dim reduced system that the
+    reference dense-fills; here: one heavy area -> 8-CTA cluster, minimum-degree block-sparse L D L^t on L2-resident tiles).
+    Same trial count, final error and edges within 1e-6 of the oracle."""
+    ds = D.landmark_slam_se3(n_kfs=100, n_lms=1000, seed=4, obs_kind="cartesian3d")
+    kw = dict(pose_kind=1, obs_kind=1, noise_kind=0, noise_std=1e-3, max_tree_depth=3, max_optimize_depth=3, submap_size=10, min_obs_to_loop_closure=4)
+    eo, ep = make_pair(kw)
+    for f in ds["frames"]:
+        D.feed(eo, f)
+        D.feed(ep, f, run_local_optimization=False)
+        inject_state(eo, ep)
+    io = eo.optimize_local_area(99, 10 ** 6)
+    ip = ep.optimize_local_area(99, 10 ** 6)
+    for key in INT_KEYS:
+        assert io[key] == ip[key], (key, io[key], ip[key])
+    assert io["num_kf2kf_edges_optimized"] >= 100 and io["num_lm_optimized"] >= 500
+    assert abs(io["total_sqr_error_init"] - ip["total_sqr_error_init"]) <= 1e-9 * io["total_sqr_error_init"]
+    assert abs(io["total_sqr_error_final"] - ip["total_sqr_error_final"]) <= 1e-6 * io["total_sqr_error_final"]
+    _, po_ = eo.edges()
+    _, pp_ = ep.edges()
+    assert rel_err(pp_, po_) <= 1e-6
+    _, _, lo = eo.unknown_lms()
+    _, _, lp = ep.unknown_lms()
+    assert rel_err(lp, lo) <= 1e-6
