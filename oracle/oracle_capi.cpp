@@ -104,6 +104,8 @@ void orc_default_params(orc_params_t *p) {
 	// ecps/local_areas_fixed_size.h:30-33
 	p->submap_size = 15;
 	p->min_obs_to_loop_closure = 4;
+	p->solver_kind = 0;  // solver_LM_schur_dense_cholesky (RbaEngine.h:44)
+	p->reserved_ = 0;
 }
 
 void *orc_create(const orc_params_t *p) {
@@ -395,6 +397,45 @@ int orc_schur_case(uint64_t n_p, uint64_t n_f, const uint8_t *visible, const dou
 	GUARD_END(-1)
 }
 
+
+// The three solver_engine<> variants (impl/lev-marq_solvers.h:27-209, 213-405, 409-591) on the system of orc_schur_case
+// (minus_grad = ones): one solve(lambda); returns delta_eps [6 n_p | 3 n_f] and the gradient vector as solve() leaves it.
+int orc_solver_case(int solver_kind, uint64_t n_p, uint64_t n_f, const uint8_t *visible, const double *JA, const double *JF, double lambda,
+                    double *out_delta, double *out_minus_grad_after, int *out_solved) {
+	GUARD_BEGIN
+	const int p = 6, f = 3, o = 3;
+	static char valid_true = 1;
+	std::vector<JacobColView> dh_dAp(n_p), dh_df(n_f);
+	size_t idx_obs = 0, ia = 0, jf = 0;
+	for (size_t nKF = 0; nKF <= n_p; nKF++)
+		for (size_t nLM = 0; nLM < n_f; nLM++) {
+			if (!visible[nKF * n_f + nLM]) continue;
+			if (nKF > 0) { JacobBlockRef r = {JA + (ia++) * o * p, &valid_true}; dh_dAp[nKF - 1].push_back(std::make_pair(idx_obs, r)); }
+			JacobBlockRef r = {JF + (jf++) * o * f, &valid_true};
+			dh_df[nLM].push_back(std::make_pair(idx_obs, r));
+			idx_obs++;
+		}
+	for (size_t j = 0; j < n_f; j++) std::sort(dh_df[j].begin(), dh_df[j].end(), [](const std::pair<size_t, JacobBlockRef> &a, const std::pair<size_t, JacobBlockRef> &b) { return a.first < b.first; });
+	std::vector<double> minus_grad(p * n_p + f * n_f, 1.0);
+	SparseBlockHessian HAp, Hf, HApf;
+	sparse_hessian_build_symbolic(HAp, Hf, HApf, dh_dAp, dh_df, p, f);
+	NoiseModel noise;
+	noise.kind = ORC_NOISE_IDENTITY; noise.o = o; noise.std_noise = 1.0;
+	sparse_hessian_update_numeric(HAp, noise);
+	sparse_hessian_update_numeric(Hf, noise);
+	sparse_hessian_update_numeric(HApf, noise);
+	std::unique_ptr<SolverBase> sv;
+	if (solver_kind == SOLVER_LM_SCHUR_DENSE_CHOLESKY) sv.reset(new SolverSchurDense(HAp, Hf, HApf, minus_grad, n_p, n_f, p, f));
+	else if (solver_kind == SOLVER_LM_SCHUR_SPARSE_CHOLESKY) sv.reset(new SolverSchurSparse(HAp, Hf, HApf, minus_grad, n_p, n_f, p, f));
+	else if (solver_kind == SOLVER_LM_NO_SCHUR_SPARSE_CHOLESKY) sv.reset(new SolverNoSchurSparse(HAp, Hf, HApf, minus_grad, n_p, n_f, p, f));
+	else throw std::runtime_error("orc_solver_case: unknown solver_kind");
+	const bool ok = sv->solve(lambda);
+	*out_solved = ok ? 1 : 0;
+	if (ok) std::copy(sv->delta_eps.begin(), sv->delta_eps.end(), out_delta);
+	std::copy(minus_grad.begin(), minus_grad.end(), out_minus_grad_after);
+	return 0;
+	GUARD_END(-1)
+}
 
 int orc_eval_dh_dAp(const orc_params_t *p, const double *A, const double *D, const double *edge_inv_pose, int normal_dir, const double *lm_pos, double *out_J) {
 	GUARD_BEGIN

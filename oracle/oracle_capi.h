@@ -32,6 +32,9 @@ typedef struct {
 	uint64_t max_iters;
 	double max_error_per_obs_to_stop, max_rho, max_lambda, min_error_reduction_ratio_to_relinearize;
 	uint64_t submap_size, min_obs_to_loop_closure;
+	int32_t solver_kind;        /* RBA_OPTIONS::solver_t (srba_options_solver.h:21-77): 0 Schur + dense Cholesky (default, RbaEngine.h:44),
+	                             * 1 Schur + sparse Cholesky, 2 no Schur + sparse Cholesky */
+	int32_t reserved_;
 } orc_params_t;
 
 /* TOptimizeExtraOutputInfo (RbaEngine.h:125-177), scalar part. */
@@ -121,6 +124,12 @@ void orc_reset_opt_timer(void *h);
  * (6np x 6np, symmetric-filled) and the reduced gradient head. */
 int orc_schur_case(uint64_t n_p, uint64_t n_f, const uint8_t *visible, const double *JA, const double *JF,
                    double lambda, double *out_HAp_dense, double *out_grad_Ap, uint64_t *out_n_invertible);
+
+/* Unit-level entry for the three solver_engine<> variants (impl/lev-marq_solvers.h:27-209,213-405,409-591): the system of
+ * orc_schur_case with minus_grad = ones, one solve(lambda).  out_delta: [6 n_p | 3 n_f]; out_minus_grad_after: the caller's
+ * gradient vector as solve() leaves it (mutated in place by the Schur variants, untouched without Schur). */
+int orc_solver_case(int solver_kind, uint64_t n_p, uint64_t n_f, const uint8_t *visible, const double *JA, const double *JF, double lambda,
+                    double *out_delta, double *out_minus_grad_after, int *out_solved);
 
 /* Unit-level entries for Jacobian checks (impl/jacobians.h:207-354, 888-1013 and the numeric recipe :90-186).
  * A may be NULL (identity). edge_inv_pose only read when normal_dir==0. */

@@ -16,6 +16,7 @@ POSE_SE2, POSE_SE3 = 0, 1
 OBS_RELPOSES2D, OBS_CARTESIAN3D, OBS_MONO, OBS_STEREO = 0, 1, 2, 3
 SENSORPOSE_NONE, SENSORPOSE_SE3 = 0, 1
 NOISE_IDENTITY, NOISE_CONST_MATRIX = 0, 1
+SOLVER_SCHUR_DENSE, SOLVER_SCHUR_SPARSE, SOLVER_NO_SCHUR_SPARSE = 0, 1, 2  # srba_options_solver.h:21-77
 OBS_DIMS = {OBS_RELPOSES2D: 3, OBS_CARTESIAN3D: 3, OBS_MONO: 2, OBS_STEREO: 4}
 INVALID = 2**64 - 1
 
@@ -32,6 +33,7 @@ class Params(C.Structure):
         ("max_error_per_obs_to_stop", C.c_double), ("max_rho", C.c_double), ("max_lambda", C.c_double),
         ("min_error_reduction_ratio_to_relinearize", C.c_double),
         ("submap_size", C.c_uint64), ("min_obs_to_loop_closure", C.c_uint64),
+        ("solver_kind", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
@@ -123,6 +125,8 @@ def lib(variant=""):
     L.orc_reset_opt_timer.argtypes = [vp]
     L.orc_schur_case.restype = C.c_int
     L.orc_schur_case.argtypes = [u64, u64, pu8, pdbl, pdbl, dbl, pdbl, pdbl, pu64]
+    L.orc_solver_case.restype = C.c_int
+    L.orc_solver_case.argtypes = [C.c_int, u64, u64, pu8, pdbl, pdbl, dbl, pdbl, pdbl, C.POINTER(C.c_int)]
     L.orc_eval_dh_dAp.restype = C.c_int
     L.orc_eval_dh_dAp.argtypes = [C.POINTER(Params), pdbl, pdbl, pdbl, C.c_int, pdbl, pdbl]
     L.orc_eval_dh_df.restype = C.c_int
@@ -363,6 +367,22 @@ def schur_case(n_p, n_f, visible, JA, JF, lam):
     if rc != 0:
         raise OracleError(L.orc_last_error().decode())
     return H, g, ninv.value
+
+
+def solver_case(solver_kind, n_p, n_f, visible, JA, JF, lam):
+    """One solve(lambda) of solver_engine<> variant `solver_kind` on the schur_case system (gradient = ones)."""
+    L = lib()
+    visible = np.ascontiguousarray(visible, dtype=np.uint8)
+    JA = np.ascontiguousarray(JA, dtype=np.float64)
+    JF = np.ascontiguousarray(JF, dtype=np.float64)
+    d = np.zeros(6 * n_p + 3 * n_f)
+    g = np.zeros(6 * n_p + 3 * n_f)
+    ok = C.c_int()
+    rc = L.orc_solver_case(solver_kind, n_p, n_f, _p(visible, C.c_uint8), _p(JA, C.c_double), _p(JF, C.c_double), C.c_double(lam), _p(d, C.c_double),
+                           _p(g, C.c_double), C.byref(ok))
+    if rc != 0:
+        raise OracleError(L.orc_last_error().decode())
+    return bool(ok.value), d, g
 
 
 def pose_compose(kind, a, b):

@@ -22,6 +22,7 @@
 #include <deque>
 #include <limits>
 #include <map>
+#include <memory>
 #include <queue>
 #include <set>
 #include <sstream>
@@ -615,11 +616,174 @@ class SchurComplement {
 	std::vector<TGradApSymbolicEntry> m_sym_GradAp_reduce;
 };
 
-// solver_engine<true,true>  (impl/lev-marq_solvers.h:409-591): LM with Schur + dense Cholesky.
-struct SolverSchurDense {
+// ---------------------------------------------------------------------------------------------
+// mrpt::math::CSparseMatrix + CSparseMatrix::CholeskyDecomp as the reference uses them (impl/lev-marq_solvers.h:84-184,
+// 296-362).  MRPT wraps T. Davis' CSparse (bundled inside MRPT 1.3.x, absent here): insert_submatrix() appends
+// triplets, compressFromTriplet() = cs_compress (duplicates summed when the factorisation walks the column),
+// CholeskyDecomp(A) = cs_schol(order 1) + cs_chol, update(A) = cs_chol again on the same symbolic analysis (throws
+// CExceptionNotDefPos when cs_chol meets a pivot d <= 0), backsub = P^t L^-t L^-1 P b.  Restated here: the up-looking
+// Cholesky of cs_chol (elimination tree, row reach, "d <= 0 -> not positive definite") on the UPPER triangle only, in
+// the NATURAL order -- cs_schol's AMD permutation is not reproduced (parity unpinned; any symmetric permutation gives
+// the same solution up to rounding and fails iff the matrix is not positive definite).
+// ---------------------------------------------------------------------------------------------
+struct CSparseMatrixLite {
+	size_t n;
+	std::vector<int> ti, tj;  // triplets (row, col)
+	std::vector<double> tx;
+	std::vector<int> Ap, Ai;  // compressed columns
+	std::vector<double> Ax;
+	CSparseMatrixLite() : n(0) {}
+	void clear(size_t n_) { n = n_; ti.clear(); tj.clear(); tx.clear(); Ap.clear(); Ai.clear(); Ax.clear(); }
+	void insert_submatrix(size_t row, size_t col, const double *M, int nr, int nc) {
+		for (int r = 0; r < nr; r++)
+			for (int c = 0; c < nc; c++) { ti.push_back((int)(row + r)); tj.push_back((int)(col + c)); tx.push_back(M[r * nc + c]); }
+	}
+	void compressFromTriplet() {  // cs_compress: counting sort by column, triplet order kept inside a column
+		Ap.assign(n + 1, 0);
+		for (size_t k = 0; k < tj.size(); k++) Ap[tj[k] + 1]++;
+		for (size_t c = 0; c < n; c++) Ap[c + 1] += Ap[c];
+		Ai.resize(ti.size()); Ax.resize(ti.size());
+		std::vector<int> w(Ap.begin(), Ap.end() - 1);
+		for (size_t k = 0; k < ti.size(); k++) { const int q = w[tj[k]]++; Ai[q] = ti[k]; Ax[q] = tx[k]; }
+	}
+	void getAsDenseUpper(std::vector<double> &D) const {
+		D.assign(n * n, 0.0);
+		for (size_t c = 0; c < n; c++)
+			for (int q = Ap[c]; q < Ap[c + 1]; q++) D[(size_t)Ai[q] * n + c] += Ax[q];
+	}
+};
+struct SparseCholeskyLite {
+	size_t n;
+	std::vector<int> parent;                                 // elimination tree (cs_etree)
+	std::vector<std::vector<std::pair<int, double> > > Lcol; // L by columns, diagonal first, rows ascending
+	bool has_symbolic;
+	SparseCholeskyLite() : n(0), has_symbolic(false) {}
+	void symbolic(const CSparseMatrixLite &A) {
+		n = A.n;
+		parent.assign(n, -1);
+		std::vector<int> ancestor(n, -1);
+		for (size_t k = 0; k < n; k++)
+			for (int q = A.Ap[k]; q < A.Ap[k + 1]; q++)
+				for (int i = A.Ai[q]; i != -1 && i < (int)k;) {  // walk from i to the root of its subtree, compressing the path
+					const int inext = ancestor[i];
+					ancestor[i] = (int)k;
+					if (inext == -1) parent[i] = (int)k;
+					i = inext;
+				}
+		has_symbolic = true;
+	}
+	// cs_chol: row k of L solves L(0:k-1,0:k-1) x = A(0:k-1,k); d = A(k,k) - x.x must be > 0.
+	bool numeric(const CSparseMatrixLite &A) {
+		if (!has_symbolic) symbolic(A);
+		Lcol.assign(n, std::vector<std::pair<int, double> >());
+		std::vector<double> x(n, 0.0);
+		std::vector<int> mark(n, -1), reach;
+		for (size_t k = 0; k < n; k++) {
+			reach.clear();
+			mark[k] = (int)k;
+			double d = 0;
+			for (int q = A.Ap[k]; q < A.Ap[k + 1]; q++) {
+				const int i = A.Ai[q];
+				if (i > (int)k) continue;  // upper triangle only
+				if (i == (int)k) { d += A.Ax[q]; continue; }
+				x[i] += A.Ax[q];  // duplicates summed
+				for (int t = i; t != -1 && mark[t] != (int)k; t = parent[t]) { mark[t] = (int)k; reach.push_back(t); }
+			}
+			std::sort(reach.begin(), reach.end());  // ascending = a topological order of the elimination tree
+			for (size_t r = 0; r < reach.size(); r++) {
+				const int i = reach[r];
+				const double lki = x[i] / Lcol[i][0].second;
+				x[i] = 0;
+				for (size_t q = 1; q < Lcol[i].size(); q++) x[Lcol[i][q].first] -= Lcol[i][q].second * lki;
+				d -= lki * lki;
+				Lcol[i].push_back(std::make_pair((int)k, lki));
+			}
+			if (d <= 0) return false;  // not positive definite
+			Lcol[k].push_back(std::make_pair((int)k, std::sqrt(d)));
+		}
+		return true;
+	}
+	void backsub(const double *b, double *out, size_t len) const {  // L L^t out = b
+		std::vector<double> y(b, b + len);
+		for (size_t j = 0; j < len; j++) {
+			y[j] /= Lcol[j][0].second;
+			for (size_t q = 1; q < Lcol[j].size(); q++) y[Lcol[j][q].first] -= Lcol[j][q].second * y[j];
+		}
+		for (size_t jj = len; jj-- > 0;) {
+			for (size_t q = 1; q < Lcol[jj].size(); q++) y[jj] -= Lcol[jj][q].second * y[Lcol[jj][q].first];
+			y[jj] /= Lcol[jj][0].second;
+		}
+		for (size_t j = 0; j < len; j++) out[j] = y[j];
+	}
+};
+
+// RBA_OPTIONS::solver_t (srba_options_solver.h:21-77) is a compile-time choice in the reference (optimize_edges.h:54);
+// here a run-time tag with the same three values.
+enum { SOLVER_LM_SCHUR_DENSE_CHOLESKY = 0, SOLVER_LM_SCHUR_SPARSE_CHOLESKY = 1, SOLVER_LM_NO_SCHUR_SPARSE_CHOLESKY = 2 };
+struct SolverBase {
+	std::vector<double> delta_eps;
+	virtual ~SolverBase() {}
+	virtual bool solve(const double lambda) = 0;
+	virtual void realize_lambda_changed() = 0;
+	virtual void realize_relinearized() = 0;
+	virtual bool was_ith_feature_invertible(const size_t i) = 0;
+	virtual void get_extra_results(std::vector<double> &denseH, bool &valid) = 0;  // hessian of the last solve, densified
+};
+
+// solver_engine<false,false>  (impl/lev-marq_solvers.h:27-209): LM without Schur, sparse Cholesky of the WHOLE system.
+// minus_grad is left untouched (unlike the Schur variants) and every landmark counts as invertible (:196-200).
+struct SolverNoSchurSparse : public SolverBase {
 	const size_t nUnknowns_k2k, nUnknowns_k2f;
 	const int p, f;
-	std::vector<double> delta_eps;
+	SparseBlockHessian &HAp, &Hf, &HApf;
+	std::vector<double> &minus_grad;
+	const size_t nUnknowns_scalars, idx_start_f;
+	CSparseMatrixLite sS;
+	bool sS_is_valid;
+	SparseCholeskyLite chol;
+	SolverNoSchurSparse(SparseBlockHessian &HAp_, SparseBlockHessian &Hf_, SparseBlockHessian &HApf_, std::vector<double> &minus_grad_, size_t n_k2k,
+	                    size_t n_k2f, int p_, int f_)
+	    : nUnknowns_k2k(n_k2k), nUnknowns_k2f(n_k2f), p(p_), f(f_), HAp(HAp_), Hf(Hf_), HApf(HApf_), minus_grad(minus_grad_),
+	      nUnknowns_scalars(p_ * n_k2k + f_ * n_k2f), idx_start_f(p_ * n_k2k), sS_is_valid(false) {}
+	void insert_diag_or_plain(SparseBlockHessian &H, size_t ncols, size_t off, int d, double lambda) {
+		double tmp[MAX_P * MAX_P];
+		for (size_t i = 0; i < ncols; i++) {  // only the upper-half triangle is stored (:93-116,135-158)
+			const SparseBlockHessian::col_t &col_i = H.getCol(i);
+			for (SparseBlockHessian::col_t::const_iterator it = col_i.begin(); it != col_i.end(); ++it) {
+				for (int k = 0; k < d * d; k++) tmp[k] = it->second.num[k];
+				if (it->first == i)
+					for (int k = 0; k < d; k++) tmp[k * d + k] += lambda;
+				sS.insert_submatrix(off + d * it->first, off + d * i, tmp, d, d);
+			}
+		}
+	}
+	bool solve(const double lambda) {  // :81-184
+		sS.clear(nUnknowns_scalars);
+		sS_is_valid = false;
+		insert_diag_or_plain(HAp, nUnknowns_k2k, 0, p, lambda);  // 1/3
+		for (size_t i = 0; i < nUnknowns_k2k; i++) {              // 2/3: HApf is row-compressed (:119-131)
+			const SparseBlockHessian::col_t &row_i = HApf.getCol(i);
+			for (SparseBlockHessian::col_t::const_iterator it = row_i.begin(); it != row_i.end(); ++it)
+				sS.insert_submatrix(p * i, idx_start_f + f * it->first, it->second.num, p, f);
+		}
+		insert_diag_or_plain(Hf, nUnknowns_k2f, idx_start_f, f, lambda);  // 3/3
+		sS.compressFromTriplet();
+		if (!chol.numeric(sS)) return false;  // CExceptionNotDefPos (:171-175)
+		sS_is_valid = true;
+		delta_eps.assign(nUnknowns_scalars, 0.0);
+		chol.backsub(&minus_grad[0], &delta_eps[0], nUnknowns_scalars);  // :182
+		return true;
+	}
+	void realize_relinearized() {}
+	void realize_lambda_changed() {}
+	bool was_ith_feature_invertible(const size_t) { return true; }
+	void get_extra_results(std::vector<double> &denseH, bool &valid) { valid = sS_is_valid; if (sS.Ap.empty()) denseH.clear(); else sS.getAsDenseUpper(denseH); }
+};
+
+// solver_engine<true,true>  (impl/lev-marq_solvers.h:409-591): LM with Schur + dense Cholesky.
+struct SolverSchurDense : public SolverBase {
+	const size_t nUnknowns_k2k, nUnknowns_k2f;
+	const int p, f;
 	SparseBlockHessian &HAp, &Hf, &HApf;
 	std::vector<double> &minus_grad;
 	SchurComplement schur_compl;
@@ -660,6 +824,50 @@ struct SolverSchurDense {
 	void realize_lambda_changed() { denseChol_is_uptodate = false; }   // :570-573
 	void realize_relinearized() { schur_compl.realize_HAp_changed(); }  // :574-580
 	bool was_ith_feature_invertible(const size_t i) { return schur_compl.was_ith_feature_invertible(i); }
+	void get_extra_results(std::vector<double> &out, bool &valid) { out.swap(denseH); valid = hessian_is_valid; }  // :582-586
+};
+
+// solver_engine<true,false>  (impl/lev-marq_solvers.h:213-405): LM with Schur + sparse Cholesky of the reduced system.
+struct SolverSchurSparse : public SolverBase {
+	const size_t nUnknowns_k2k, nUnknowns_k2f;
+	const int p, f;
+	SparseBlockHessian &HAp, &Hf, &HApf;
+	std::vector<double> &minus_grad;
+	CSparseMatrixLite sS;
+	bool sS_is_valid;
+	SparseCholeskyLite chol;
+	SchurComplement schur_compl;
+	SolverSchurSparse(SparseBlockHessian &HAp_, SparseBlockHessian &Hf_, SparseBlockHessian &HApf_, std::vector<double> &minus_grad_, size_t n_k2k,
+	                  size_t n_k2f, int p_, int f_)
+	    : nUnknowns_k2k(n_k2k), nUnknowns_k2f(n_k2f), p(p_), f(f_), HAp(HAp_), Hf(Hf_), HApf(HApf_), minus_grad(minus_grad_), sS_is_valid(false),
+	      schur_compl(HAp_, Hf_, HApf_, &minus_grad_[0], n_k2f != 0 ? &minus_grad_[p_ * n_k2k] : NULL, p_, f_) {}
+	bool solve(const double lambda) {  // :276-380
+		schur_compl.numeric_build_reduced_system(lambda);
+		const size_t n = nUnknowns_k2k * p;
+		sS.clear(n);
+		sS_is_valid = false;
+		double tmp[MAX_P * MAX_P];
+		for (size_t i = 0; i < nUnknowns_k2k; i++) {  // :296-321
+			const SparseBlockHessian::col_t &col_i = HAp.getCol(i);
+			for (SparseBlockHessian::col_t::const_iterator it = col_i.begin(); it != col_i.end(); ++it) {
+				for (int k = 0; k < p * p; k++) tmp[k] = it->second.num[k];
+				if (it->first == i)
+					for (int k = 0; k < p; k++) tmp[k * p + k] += lambda;
+				sS.insert_submatrix(p * it->first, p * i, tmp, p, p);
+			}
+		}
+		sS.compressFromTriplet();
+		if (!chol.numeric(sS)) return false;  // :347-351
+		sS_is_valid = true;
+		delta_eps.assign(nUnknowns_k2k * p + nUnknowns_k2f * f, 0.0);  // :359 "Important: It's initialized to zeros!"
+		if (n) chol.backsub(&minus_grad[0], &delta_eps[0], n);
+		if (nUnknowns_k2f != 0 && nUnknowns_k2k != 0) schur_compl.numeric_solve_for_features(&delta_eps[0], &delta_eps[n]);  // :371-375
+		return true;
+	}
+	void realize_relinearized() { schur_compl.realize_HAp_changed(); }
+	void realize_lambda_changed() {}
+	bool was_ith_feature_invertible(const size_t i) { return schur_compl.was_ith_feature_invertible(i); }
+	void get_extra_results(std::vector<double> &denseH, bool &valid) { valid = sS_is_valid; if (sS.Ap.empty()) denseH.clear(); else sS.getAsDenseUpper(denseH); }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1992,7 +2200,14 @@ struct Engine {
 			tr->n_scalars = nUnknowns_scalars;
 		}
 		// O (:431-436)
-		SolverSchurDense my_solver(HAp, Hf, HApf, minus_grad, nUnknowns_k2k, nUnknowns_k2f, P, LM_DIMS);
+		std::unique_ptr<SolverBase> my_solver_ptr;  // my_solver_t = solver_engine<USE_SCHUR,DENSE_CHOLESKY> (:54)
+		switch (parameters.solver_kind) {
+			case SOLVER_LM_SCHUR_DENSE_CHOLESKY: my_solver_ptr.reset(new SolverSchurDense(HAp, Hf, HApf, minus_grad, nUnknowns_k2k, nUnknowns_k2f, P, LM_DIMS)); break;
+			case SOLVER_LM_SCHUR_SPARSE_CHOLESKY: my_solver_ptr.reset(new SolverSchurSparse(HAp, Hf, HApf, minus_grad, nUnknowns_k2k, nUnknowns_k2f, P, LM_DIMS)); break;
+			case SOLVER_LM_NO_SCHUR_SPARSE_CHOLESKY: my_solver_ptr.reset(new SolverNoSchurSparse(HAp, Hf, HApf, minus_grad, nUnknowns_k2k, nUnknowns_k2f, P, LM_DIMS)); break;
+			default: throw std::runtime_error("optimize_edges: unknown solver_kind");
+		}
+		SolverBase &my_solver = *my_solver_ptr;
 		const double MAX_LAMBDA = parameters.max_lambda;
 		std::vector<k2k_edge_t> old_k2k_edge_unknowns;
 		std::vector<pose_t> old_span_tree;
@@ -2094,8 +2309,7 @@ struct Engine {
 				unknown_lms_inf_matrices[run_feat_ids[i]].assign(col_i.rbegin()->second.num, col_i.rbegin()->second.num + LM_DIMS * LM_DIMS);
 			}
 		}
-		last_dense_hessian.swap(my_solver.denseH);  // get_extra_results (:769)
-		last_hessian_valid = my_solver.hessian_is_valid;
+		my_solver.get_extra_results(last_dense_hessian, last_hessian_valid);  // :769
 		out_info.obs_rmse = RMSE;
 	}
 	std::vector<double> last_dense_hessian;
