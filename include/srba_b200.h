@@ -25,6 +25,15 @@ enum { SRBA_POSE_SE2 = 0, SRBA_POSE_SE3 = 1 };                                  
 enum { SRBA_OBS_RELPOSES2D = 0, SRBA_OBS_CARTESIAN3D = 1, SRBA_OBS_MONO = 2, SRBA_OBS_STEREO = 3 }; /* models/sensors.h */
 enum { SRBA_SENSORPOSE_NONE = 0, SRBA_SENSORPOSE_SE3 = 1 };                     /* srba_options_sensor_pose.h:32,92 */
 enum { SRBA_NOISE_IDENTITY = 0, SRBA_NOISE_CONST_MATRIX = 1 };                  /* srba_options_noise.h:25,79 */
+/* RBA_OPTIONS::solver_t (srba_options_solver.h:21-77), a compile-time choice in the reference (optimize_edges.h:54).
+ * All three run the same device program -- block-sparse L D L^t of the reduced system after eliminating the landmark
+ * blocks first (which IS a sparse Cholesky of the whole system in a landmarks-first order) -- and differ only where the
+ * reference's solver_engine<> specialisations differ observably (impl/lev-marq_solvers.h):
+ *   SCHUR_*          : solve() reduces the caller's gradient IN PLACE (schur.h:248-265,283-296), landmarks whose
+ *                      H_f + lambda I is not invertible are skipped (was_ith_feature_invertible);
+ *   NO_SCHUR_SPARSE  : the gradient is left untouched by solve() (:182), a non-invertible landmark block makes the
+ *                      factorisation fail (solve() returns false -> lambda is raised), every landmark counts as invertible (:196-200). */
+enum { SRBA_SOLVER_SCHUR_DENSE_CHOLESKY = 0, SRBA_SOLVER_SCHUR_SPARSE_CHOLESKY = 1, SRBA_SOLVER_NO_SCHUR_SPARSE_CHOLESKY = 2 };
 
 /* error codes */
 enum {
@@ -50,6 +59,8 @@ typedef struct {
 	int32_t use_robust_kernel;
 	double kernel_param;
 	double max_error_per_obs_to_stop, max_rho, max_lambda, min_error_reduction_ratio_to_relinearize;
+	int32_t solver_kind;      /* SRBA_SOLVER_* */
+	int32_t reserved_;
 } srba_model_t;
 
 /* One flattened optimize_edges() problem.  Index spaces:

@@ -31,6 +31,8 @@ typedef struct {
 	uint64_t max_iters;
 	double max_error_per_obs_to_stop, max_rho, max_lambda, min_error_reduction_ratio_to_relinearize;
 	uint64_t submap_size, min_obs_to_loop_closure;
+	int32_t solver_kind;        /* RBA_OPTIONS::solver_t (RbaEngine.h:44, srba_options_solver.h:21-77): SRBA_SOLVER_* of srba_b200.h */
+	int32_t reserved_;
 } srba_engine_params_t;
 
 /* TOptimizeExtraOutputInfo (RbaEngine.h:125-177), scalar part (+ two counters the reference does not expose). */

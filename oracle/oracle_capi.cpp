@@ -229,6 +229,24 @@ uint64_t orc_complete_spanning_tree(void *h, uint64_t root, uint64_t max_depth, 
 	return n;
 	GUARD_END(0)
 }
+double orc_eval_overall_squared_error(void *h) {
+	GUARD_BEGIN
+	double r = 0;
+	DISPATCH(h, r = E.eval_overall_squared_error());
+	return r;
+	GUARD_END(-1.0)
+}
+uint64_t orc_last_dense_hessian(void *h, double *out, uint64_t cap, int *valid) {
+	GUARD_BEGIN
+	uint64_t n = 0;
+	DISPATCH(h, {
+		n = E.last_dense_hessian.size();
+		if (out) std::copy(E.last_dense_hessian.begin(), E.last_dense_hessian.begin() + std::min<uint64_t>(n, cap), out);
+		if (valid) *valid = E.last_hessian_valid ? 1 : 0;
+	});
+	return n;
+	GUARD_END(0)
+}
 int64_t orc_find_path_bfs_len(void *h, uint64_t from, uint64_t to) {
 	GUARD_BEGIN
 	int64_t r = -1;

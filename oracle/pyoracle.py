@@ -125,6 +125,10 @@ def lib(variant=""):
     L.orc_reset_opt_timer.argtypes = [vp]
     L.orc_schur_case.restype = C.c_int
     L.orc_schur_case.argtypes = [u64, u64, pu8, pdbl, pdbl, dbl, pdbl, pdbl, pu64]
+    L.orc_eval_overall_squared_error.restype = dbl
+    L.orc_eval_overall_squared_error.argtypes = [vp]
+    L.orc_last_dense_hessian.restype = u64
+    L.orc_last_dense_hessian.argtypes = [vp, pdbl, u64, C.POINTER(C.c_int)]
     L.orc_solver_case.restype = C.c_int
     L.orc_solver_case.argtypes = [C.c_int, u64, u64, pu8, pdbl, pdbl, dbl, pdbl, pdbl, C.POINTER(C.c_int)]
     L.orc_eval_dh_dAp.restype = C.c_int
@@ -256,6 +260,17 @@ class OracleEngine:
         poses = np.zeros((n, self.nv))
         self.L.orc_complete_spanning_tree(self.h, root, max_depth, _p(ids, C.c_uint64), _p(poses, C.c_double), n)
         return ids, poses
+
+    def eval_overall_squared_error(self):
+        return self.L.orc_eval_overall_squared_error(self.h)
+
+    def last_dense_hessian(self):
+        valid = C.c_int()
+        n2 = self.L.orc_last_dense_hessian(self.h, None, 0, C.byref(valid))
+        H = np.zeros(n2)
+        self.L.orc_last_dense_hessian(self.h, _p(H, C.c_double), n2, C.byref(valid))
+        n = int(round(n2 ** 0.5))
+        return H.reshape(n, n), bool(valid.value)
 
     def find_path_bfs_len(self, a, b):
         return self.L.orc_find_path_bfs_len(self.h, a, b)

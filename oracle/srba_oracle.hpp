@@ -1427,6 +1427,47 @@ struct Engine {
 		}
 	}
 
+	// ------------------------------------------------------------------ impl/eval_overall_error.h:15-137
+	// One complete (unbounded-depth) BFS spanning tree per root = min(observer, base) of every observation; the pose of
+	// the larger id as seen from the root comes from that tree, its inverse serves the opposite direction (:72-76).
+	// No robust kernel here (:129 plain squaredNorm).
+	double eval_overall_squared_error() const {
+		double sqerr = 0;
+		std::map<TKeyFrameID, std::set<TKeyFrameID> > ob_pairs;  // minimum id first
+		for (typename std::deque<k2f_edge_t>::const_iterator itO = all_observations.begin(); itO != all_observations.end(); ++itO) {
+			const TKeyFrameID obs_id = itO->kf_id, base_id = itO->feat_rel_pos->id_frame_base;
+			ob_pairs[std::min(obs_id, base_id)].insert(std::max(obs_id, base_id));
+		}
+		std::map<TKeyFrameID, std::map<TKeyFrameID, pose_t> > all_rel_poses;  // [SOURCE][TARGET] = TARGET as seen from SOURCE
+		for (std::map<TKeyFrameID, std::set<TKeyFrameID> >::const_iterator it1 = ob_pairs.begin(); it1 != ob_pairs.end(); ++it1) {
+			const TKeyFrameID root = it1->first;
+			std::map<TKeyFrameID, pose_t> span_tree;
+			create_complete_spanning_tree(root, span_tree, std::numeric_limits<size_t>::max());
+			for (std::set<TKeyFrameID>::const_iterator w = it1->second.begin(); w != it1->second.end(); ++w) {
+				typename std::map<TKeyFrameID, pose_t>::const_iterator have = span_tree.find(*w);
+				if (have == span_tree.end()) continue;
+				all_rel_poses[root][*w] = have->second;
+				all_rel_poses[*w][root] = -have->second;
+			}
+		}
+		for (typename std::deque<k2f_edge_t>::const_iterator itO = all_observations.begin(); itO != all_observations.end(); ++itO) {
+			const TKeyFrameID obs_frame_id = itO->kf_id, base_id = itO->feat_rel_pos->id_frame_base;
+			const pose_t *base_pose_wrt_observer = NULL;
+			if (base_id == obs_frame_id) base_pose_wrt_observer = &aux_null_pose;
+			else {
+				typename std::map<TKeyFrameID, std::map<TKeyFrameID, pose_t> >::const_iterator m = all_rel_poses.find(obs_frame_id);
+				ORC_ASSERT(m != all_rel_poses.end());
+				typename std::map<TKeyFrameID, pose_t>::const_iterator itRelPose = m->second.find(base_id);
+				ORC_ASSERT(itRelPose != m->second.end());
+				base_pose_wrt_observer = &itRelPose->second;
+			}
+			double delta[MAX_OBS];
+			observe_error(delta, itO->obs_arr, *base_pose_wrt_observer, itO->feat_rel_pos->pos);
+			for (int k = 0; k < O; k++) sqerr += delta[k] * delta[k];
+		}
+		return sqerr;
+	}
+
 	// RbaEngine.h:385-396
 	const pose_t *get_kf_relative_pose(TKeyFrameID kf_query, TKeyFrameID kf_reference) const {
 		const frameid2pose_map_t *m = spanning_tree.num.find(kf_reference);

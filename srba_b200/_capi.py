@@ -26,7 +26,8 @@ class Model(C.Structure):
     _fields_ = [("pose_kind", i32), ("obs_kind", i32), ("sensor_pose_kind", i32), ("noise_kind", i32),
                 ("sensor_pose", dbl * 12), ("noise_std", dbl), ("noise_lambda", dbl * 16), ("cam_left", dbl * 4), ("cam_right", dbl * 4),
                 ("right_cam_R2L", dbl * 12), ("max_iters", i32), ("use_robust_kernel", i32), ("kernel_param", dbl),
-                ("max_error_per_obs_to_stop", dbl), ("max_rho", dbl), ("max_lambda", dbl), ("min_error_reduction_ratio_to_relinearize", dbl)]
+                ("max_error_per_obs_to_stop", dbl), ("max_rho", dbl), ("max_lambda", dbl), ("min_error_reduction_ratio_to_relinearize", dbl),
+                ("solver_kind", i32), ("reserved_", i32)]
 
 
 _PROBLEM_INTS = ["n_edges", "n_unk_edges", "n_lms", "n_unk_lms", "n_pairs", "n_path", "n_obs", "n_blkA", "n_blkF", "n_HAp", "n_HAp_terms",
@@ -64,7 +65,7 @@ class EngineParams(C.Structure):
                 ("max_tree_depth", u64), ("max_optimize_depth", u64), ("optimize_new_edges_alone", i32), ("use_robust_kernel", i32),
                 ("use_robust_kernel_stage1", i32), ("cov_recovery", i32), ("kernel_param", dbl), ("max_iters", u64),
                 ("max_error_per_obs_to_stop", dbl), ("max_rho", dbl), ("max_lambda", dbl), ("min_error_reduction_ratio_to_relinearize", dbl),
-                ("submap_size", u64), ("min_obs_to_loop_closure", u64)]
+                ("submap_size", u64), ("min_obs_to_loop_closure", u64), ("solver_kind", i32), ("reserved_", i32)]
 
 
 class OptInfo(C.Structure):

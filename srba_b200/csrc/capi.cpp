@@ -72,6 +72,8 @@ int validate(const srba_problem_t &p) {
 	if ((int64_t)o * p.n_total_obs_rows < (int64_t)P * p.n_unk_edges + 3LL * p.n_unk_lms)
 		return fail(SRBA_ERR_RANK_DEFICIENT, "OBS_DIMS*nObs < number of scalar unknowns (optimize_edges.h:355)");
 	if (m.noise_kind == SRBA_NOISE_IDENTITY && !(m.noise_std > 0)) return fail(SRBA_ERR_BAD_ARGUMENT, "noise_std must be > 0");
+	if (m.solver_kind < SRBA_SOLVER_SCHUR_DENSE_CHOLESKY || m.solver_kind > SRBA_SOLVER_NO_SCHUR_SPARSE_CHOLESKY)
+		return fail(SRBA_ERR_BAD_ARGUMENT, "solver_kind must be one of SRBA_SOLVER_* (srba_options_solver.h:21-77)");
 	return SRBA_OK;
 }
 
@@ -508,6 +510,9 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 		w[SRBA_W_Hf] = (uint64_t)p.n_unk_lms * 9 * 8; w[SRBA_W_Hf_inv] = w[SRBA_W_Hf]; w[SRBA_W_W] = w[SRBA_W_HApf];
 		w[SRBA_W_Sblk] = h.s_alias_hap ? 0 : (uint64_t)p.n_S * P * P * 8;
 		w[SRBA_W_grad] = (uint64_t)h.n_scalars * 8; w[SRBA_W_delta] = w[SRBA_W_grad];
+		// solver_engine<false,false> never touches the caller's gradient (lev-marq_solvers.h:182): the pristine copy the
+		// in-place Schur reduction starts from at every trial
+		w[SRBA_W_grad0] = (p.model.solver_kind == SRBA_SOLVER_NO_SCHUR_SPARSE_CHOLESKY && p.n_unk_lms > 0) ? w[SRBA_W_grad] : 0;
 		w[SRBA_W_dense] = (h.chol_mode == SRBA_CHOL_BLOCKED || want_dense) ? (uint64_t)h.n_dense * h.ld_dense * 8 : 0;
 		w[SRBA_W_ldl_tiles] = (h.chol_mode == SRBA_CHOL_REG && h.ldl_tiles_in_ws) ? (uint64_t)h.ldl_n_tiles * 12 * 8 : 0;
 		w[SRBA_W_valid] = p.n_obs; w[SRBA_W_blk_ok] = p.n_blkA + p.n_blkF; w[SRBA_W_lm_inv] = p.n_unk_lms;

@@ -39,7 +39,7 @@
 	X(double, edge_cur) X(double, edge_bak) X(double, lm_cur) X(double, lm_bak) X(double, slot) X(double, slot_bak)      \
 	X(double, JA) X(double, JF) X(double, resid0) X(double, resid1)                                                      \
 	X(double, HAp) X(double, HApf) X(double, Hf) X(double, Hf_inv) X(double, W) X(double, Sblk)                          \
-	X(double, grad) X(double, delta) X(double, dense)                                                                    \
+	X(double, grad) X(double, delta) X(double, dense) X(double, grad0)                                                                  \
 	X(int32_t, listed_idx) X(int32_t, refresh_idx) X(double, ldl_tiles)                                                                                             \
 	X(uint8_t, valid) X(uint8_t, blk_ok) X(uint8_t, lm_inv) X(uint8_t, slot_listed)
 

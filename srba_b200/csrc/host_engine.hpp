@@ -812,6 +812,8 @@ class RbaEngine : public EngineBase {
 		m.max_error_per_obs_to_stop = parameters.max_error_per_obs_to_stop;
 		m.max_rho = parameters.max_rho; m.max_lambda = parameters.max_lambda;
 		m.min_error_reduction_ratio_to_relinearize = parameters.min_error_reduction_ratio_to_relinearize;
+		m.solver_kind = parameters.solver_kind;  // RBA_OPTIONS::solver_t (optimize_edges.h:54)
+		m.reserved_ = 0;
 		F.p.n_edges = F.edge_ids_touched.size(); F.p.n_unk_edges = n_p; F.p.n_lms = F.lm_ids_touched.size(); F.p.n_unk_lms = n_f;
 		F.p.n_pairs = F.pairs.size(); F.p.n_path = F.path_edge.size(); F.p.n_obs = n_obs; F.p.n_blkA = nA; F.p.n_blkF = nF;
 		F.p.n_HAp = F.HAp_row.size(); F.p.n_HAp_terms = F.HAp_term_a.size(); F.p.n_HApf = F.HApf_row.size(); F.p.n_HApf_terms = F.HApf_term_a.size();

@@ -279,6 +279,13 @@ __device__ __forceinline__ double team_max(double v, Shared &sh, int buf) {
 	return s;
 }
 
+// solver_engine<false,false> (impl/lev-marq_solvers.h:27-209): the whole system is factorised and solve() leaves the
+// caller's gradient untouched, whereas the Schur variants reduce it in place (schur.h:248-265,283-296).  The device program
+// is the same (landmark blocks eliminated first); it restarts from a pristine copy of the gradient at every trial.
+__device__ __forceinline__ bool no_schur_solver(const DevProblem *h) {
+	return h->model.solver_kind == SRBA_SOLVER_NO_SCHUR_SPARSE_CHOLESKY && h->n_unk_lms > 0;
+}
+
 // ------------------------------------------------------------------------------------------------ stages
 // K1: numeric spanning tree.  update_numeric_only_all_from_node (impl/spantree_update_numeric.h:19-81)
 template <int P>
@@ -696,6 +703,7 @@ __device__ __noinline__ double stage_gradient(const View &vs, const double *resi
 	const bool ident = (h->model.noise_kind == SRBA_NOISE_IDENTITY);
 	const double scale = ident ? 1.0 / h->model.noise_std : 1.0;
 	const int nAp = h->n_unk_edges * P;
+	const bool keep = no_schur_solver(h);
 	double gmax = 0;
 	for (int it = LM_TID; it < h->n_scalars; it += LM_THREADS) {
 		double g = 0;
@@ -742,6 +750,7 @@ __device__ __noinline__ double stage_gradient(const View &vs, const double *resi
 		}
 		const double gv = ident ? g * scale : g;
 		v.grad[it] = gv;
+		if (keep) v.grad0[it] = gv;
 		gmax = fmax(gmax, fabs(gv));
 	}
 	return gmax;  // this thread's share of max |g| (optimize_edges.h:636-640)
@@ -1553,6 +1562,7 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 		v.stats->total_sqr_error_init = err0;
 	}
 	const double MAX_LAMBDA = h->model.max_lambda;
+	const bool keep_grad = no_schur_solver(h);
 	const double max_gradient_to_stop = 1e-15;
 	// P. LM iterations (:454-696).  The reference's two nested loops
 	//     while (iter < max_iters && !stop) { rho = 0; stop tests; while (rho <= 0 && !stop) { TRIAL } iter++; }
@@ -1580,9 +1590,17 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 		while (sh.go) {
 			const double lambda = sh.lambda;
 			const int trial = sh.trials;
+			bool lm_singular = false;
 			if (!(h->n_unk_lms == 0 && h->s_alias_hap)) {  // relative graph-SLAM: the reduced system IS H_Ap
+				if (keep_grad)  // (read again only after the two barriers inside stage_schur)
+					for (int i = LM_TID; i < nsc; i += LM_THREADS) v.grad[i] = v.grad0[i];
 				stage_schur<P>(v, lambda);
 				LM_BARRIER();
+				if (keep_grad) {  // a landmark block that cannot be eliminated = the whole-system Cholesky fails (:171-175)
+					double bad = 0;
+					for (int k = LM_TID; k < h->n_unk_lms; k += LM_THREADS) bad = fmax(bad, v.lm_inv[k] ? 0.0 : 1.0);
+					lm_singular = team_max(bad, sh, 2) > 0;
+				}
 			}
 			const bool reg = (h->chol_mode == SRBA_CHOL_REG);
 			if (!reg || h->want_dense) {
@@ -1599,7 +1617,7 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 			if (reg) ok = stage_ldl_solve_smem<P>(v, sh, scratch, lambda);
 			else ok = stage_cholesky(v, sh, scratch, h->panel_cap);
 			STAGE(ST_CHOL);
-			if (!ok) {  // not positive definite (:476-485)
+			if (!ok || lm_singular) {  // not positive definite (:476-485)
 				if (threadIdx.x == 0) {
 					if (trial < h->trace_cap) {
 						double *tr = v.r_trace + (size_t)trial * 6;
@@ -1633,7 +1651,8 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 			double *new_resid = v.resid[sh.cur ^ 1];
 			// rho (:585): its denominator rides along in the residual reduction
 			double dl = 0;
-			for (int i = LM_TID; i < nsc; i += LM_THREADS) dl += v.delta[i] * (lambda * v.delta[i] + v.grad[i]);
+			const double *gr = keep_grad ? v.grad0 : v.grad;  // the Schur variants see their own in-place reduced gradient here
+			for (int i = LM_TID; i < nsc; i += LM_THREADS) dl += v.delta[i] * (lambda * v.delta[i] + gr[i]);
 			double denom;
 			const double new_err = stage_residuals<P, OBSK>(v, new_resid, sh, dl, &denom);
 			STAGE(ST_RESID);
@@ -1696,7 +1715,7 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 	for (int i = LM_TID; i < h->n_unk_lms * 3; i += LM_THREADS) v.r_lm_pos[i] = v.lm_cur[(size_t)v.unk_lm[i / 3] * 3 + (i % 3)];
 	for (size_t i = LM_TID; i < (size_t)2 * h->n_pairs * S; i += LM_THREADS) v.r_slot_pose[i] = v.slot[i];
 	for (int i = LM_TID; i < h->n_obs; i += LM_THREADS) v.r_obs_valid[i] = v.valid[i];
-	for (int i = LM_TID; i < h->n_unk_lms; i += LM_THREADS) v.r_lm_inv[i] = sh.trials > 0 ? v.lm_inv[i] : 0;
+	for (int i = LM_TID; i < h->n_unk_lms; i += LM_THREADS) v.r_lm_inv[i] = keep_grad ? 1 : (sh.trials > 0 ? v.lm_inv[i] : 0);  // was_ith_feature_invertible (:196-200,386-389,587-590)
 	for (int i = LM_TID; i < h->n_unk_lms * 9; i += LM_THREADS) v.r_Hf_diag[i] = v.Hf[i];
 	if (threadIdx.x == 0) {
 		srba_stats_t *st = v.stats;

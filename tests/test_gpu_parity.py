@@ -172,6 +172,47 @@ def test_se3_landmark_slam_sequential_parity(obs_kind, name, std):
         assert rel_err(pp_, po_) <= 1e-6
 
 
+@pytest.mark.parametrize("solver_kind", [1, 2])
+@pytest.mark.parametrize("obs_kind,name,std", [(1, "cartesian3d", 1e-3), (3, "stereo", 0.5)])
+def test_sparse_cholesky_solver_variants_parity(solver_kind, obs_kind, name, std):
+    """SURVEY 8(a) row a19: RBA_OPTIONS::solver_t = solver_LM_schur_sparse_cholesky (1) / solver_LM_no_schur_sparse_cholesky (2)
+    (impl/lev-marq_solvers.h:213-405 / :27-209).  Same device program (landmark blocks eliminated first, block-sparse L D L^t);
+    variant 2 keeps the gradient pristine across trials (rho's denominator and re-solves after a rejection see the unreduced
+    gradient).  Trial-by-trial against the oracle's restatement of each variant, same bars as the default solver."""
+    ds = D.landmark_slam_se3(n_kfs=30, n_lms=250, seed=5, obs_kind=name)
+    kw = dict(pose_kind=1, obs_kind=obs_kind, noise_kind=0, noise_std=std, max_tree_depth=3, max_optimize_depth=3, submap_size=10,
+              min_obs_to_loop_closure=4, solver_kind=solver_kind)
+    if obs_kind != 1:
+        kw.update(sensor_pose_kind=1, sensor_pose=ds["sensor_pose_xyzypr"], cam_left=ds["cam"], cam_right=ds["cam"],
+                  right_cam_pose=[ds["baseline"], 0, 0, 1, 0, 0, 0], use_robust_kernel=1)
+    eo, ep, worst, ns = run_parallel(kw, ds["frames"])
+    print("solver %d %s: worst relative increment error %.3e over %d decision-comparable trials" % (solver_kind, name, worst, ns))
+    assert ns > 0
+    _, _, po_ = eo.unknown_lms()
+    _, _, pp_ = ep.unknown_lms()
+    assert rel_err(pp_, po_) <= 1e-6
+
+
+def test_no_schur_solver_differs_from_schur_only_after_a_rejected_step():
+    """The in-place gradient reduction of the Schur variants (schur.h:248-265) is the ONLY behavioural difference: on one
+    problem the first trial of solver 0 and solver 2 yields the same increment (<= 1e-9), and the rho of that trial differs
+    (its denominator uses the reduced vs the pristine gradient, optimize_edges.h:585)."""
+    ds = D.landmark_slam_se3(n_kfs=12, n_lms=120, seed=6, obs_kind="cartesian3d")
+    out = []
+    for kind in (0, 2):
+        kw = dict(pose_kind=1, obs_kind=1, noise_kind=0, noise_std=1e-3, max_tree_depth=3, max_optimize_depth=3, submap_size=10,
+                  min_obs_to_loop_closure=4, solver_kind=kind)
+        ep = sb.RbaEngine(sb.default_engine_params(**kw))
+        ep.trace(8)
+        for f in ds["frames"][:-1]:
+            D.feed(ep, f, run_local_optimization=False)
+        D.feed(ep, ds["frames"][-1])
+        out.append(ep.last_trace())
+    (t0, d0), (t2, d2) = out
+    assert rel_err(d2[0], d0[0]) <= 1e-9
+    assert t0[0, 2] != t2[0, 2]
+
+
 @pytest.mark.parametrize("inverse", [False, True])
 def test_fixed_transformations_on_gpu(inverse):
     """tests/fixed-transformations_unittest.cpp through the CUDA path: recovered increment within 1e-3 (reference tolerance :127)."""

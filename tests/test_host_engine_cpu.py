@@ -158,3 +158,29 @@ def test_symbols_and_no_device_error():
     D.feed(ep, ds["frames"][0])
     with pytest.raises(RuntimeError, match="no CUDA device"):
         D.feed(ep, ds["frames"][1])
+
+
+def test_solver_kind_reaches_the_flattened_problem_and_is_validated():
+    """RBA_OPTIONS::solver_t (srba_options_solver.h:21-77) is a run-time tag here: it travels engine params -> srba_model_t,
+    the packer sizes the pristine-gradient array only for the no-Schur variant, and an unknown tag is rejected."""
+    import ctypes as C
+    from srba_b200 import _capi as K
+    ds = D.landmark_slam_se3(n_kfs=12, n_lms=100, seed=2, obs_kind="cartesian3d")
+    plans = {}
+    for kind in (0, 1, 2, 7):
+        ep = sb.RbaEngine(sb.default_engine_params(pose_kind=1, obs_kind=1, noise_kind=0, noise_std=1e-3, max_tree_depth=3, max_optimize_depth=3,
+                                                   submap_size=10, min_obs_to_loop_closure=4, solver_kind=kind))
+        for f in ds["frames"]:
+            D.feed(ep, f, run_local_optimization=False)
+        flat = ep.flatten_local_area(11, 3)
+        assert flat.p.model.solver_kind == kind
+        out = (C.c_int64 * 8)()
+        rc = K.lib().srba_b200_problem_plan(flat.problem, out)
+        if kind == 7:
+            assert rc == -1  # SRBA_ERR_BAD_ARGUMENT
+            continue
+        assert rc == 0
+        plans[kind] = (out[1], flat.p.n_unk_edges * 6 + flat.p.n_unk_lms * 3)
+    assert plans[0][0] == plans[1][0]
+    extra = plans[2][0] - plans[0][0]
+    assert 8 * plans[2][1] <= extra <= 8 * plans[2][1] + 64  # one more gradient-sized array (16-byte aligned)
