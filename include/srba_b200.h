@@ -198,6 +198,31 @@ int srba_b200_problem_plan(const srba_problem_t *in, int64_t out[8]);
 int srba_b200_debug_ldl_schedule(const srba_problem_t *in, int32_t counts[6], int32_t *row, int32_t *tile_ij, int32_t *src, int32_t *upd,
                                  int32_t *orow, int32_t *phase, int32_t cap_tiles, int32_t cap_upd, int32_t max_tiles_on_chip);
 
+/* ---- Global diagnostics: RbaEngine::eval_overall_squared_error (impl/eval_overall_error.h:15-137) and the
+ * numeric half of create_complete_spanning_tree (impl/spantree_create_complete.h:91-125).
+ * The caller (host engine) runs the reference's BFS (adjacency-order tie-breaking, :35-83) and hands over, per needed
+ * keyframe pair, the CHAIN of k2k edges from the pair's root to its target as the BFS tree found it; the device composes
+ *   pose[target wrt root] = I (+) e_1 (+) e_2 ...   with e_k = inv_pose when path_dir[k] else (-inv_pose)   (:111-122)
+ * then evaluates every observation's error with the pose of its base keyframe as seen from its observer (the pair pose
+ * or its inverse, eval_overall_error.h:72-76; identity when observer == base, :98-101), sensor pose and sensor model as in
+ * the LM path, NO robust kernel (:129), and sums the squared norms in a fixed order (deterministic). */
+typedef struct {
+	srba_model_t model;             /* pose_kind, obs_kind, sensor pose, cameras (LM parameters ignored) */
+	int32_t n_edges, n_pairs, n_path, n_obs, n_lms, reserved_;
+	const double *edge_pose;        /* n_edges x S  k2k_edge_t::inv_pose */
+	const int32_t *pair_path_ptr;   /* n_pairs+1   CSR into path_edge/path_dir, root -> target order */
+	const int32_t *path_edge;       /* n_path      -> edge */
+	const uint8_t *path_dir;        /* n_path      1: compose inv_pose (edge.from is the new node), 0: compose its inverse (edge.to is) */
+	const double *obs_z;            /* n_obs x o   k2f_edge_t::obs.obs_arr */
+	const int32_t *obs_pair;        /* n_obs       -> pair, or -1 when observer == base */
+	const uint8_t *obs_inverse;     /* n_obs       1: the observer is the pair's target (use the inverse of the pair pose) */
+	const int32_t *obs_lm;          /* n_obs       -> lm (ignored for relative-pose observations) */
+	const double *lm_pos;           /* n_lms x 3   TRelativeLandmarkPos::pos */
+} srba_eval_problem_t;
+/* out_sqerr: the total; out_pair_pose (optional, n_pairs x S): the composed poses (what create_complete_spanning_tree
+ * returns for the targets).  n_obs may be 0 (poses only).  Two kernels + a fixed-order final sum, all on the device. */
+int srba_b200_eval_overall_squared_error(const srba_eval_problem_t *in, double *out_sqerr, double *out_pair_pose);
+
 const char *srba_b200_last_error(void);
 int srba_b200_device_count(void);
 const char *srba_b200_version(void);

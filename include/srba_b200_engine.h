@@ -93,6 +93,13 @@ uint64_t srba_engine_num_unknown_lms(void *h);
 void srba_engine_get_unknown_lms(void *h, uint64_t *ids, uint64_t *base, double *pos);
 void srba_engine_set_lm_pos(void *h, uint64_t id, const double *pos);
 uint64_t srba_engine_get_next_edge(void *h, uint64_t kf, uint64_t *target, uint64_t *next, uint64_t *dist, uint64_t cap);
+/* RbaEngine::eval_overall_squared_error() (RbaEngine.h:381, impl/eval_overall_error.h:15-137): BFS trees on the host, all
+ * numerics on the device through srba_b200_eval_overall_squared_error.  0 ok, -1 error (srba_engine_last_error). */
+int srba_engine_eval_overall_squared_error(void *h, double *out_sqerr);
+/* RbaEngine::create_complete_spanning_tree(root, span_tree, max_depth) (RbaEngine.h:343-348, impl/spantree_create_complete.h):
+ * ids ascending + pose of each as seen from root (S doubles each); returns the number of keyframes reached (call with NULL
+ * arrays for the size), -1 on error. */
+int64_t srba_engine_complete_spanning_tree(void *h, uint64_t root, uint64_t max_depth, uint64_t *ids, double *poses, uint64_t cap);
 uint64_t srba_engine_get_num(void *h, uint64_t kf, uint64_t *target, double *poses, uint64_t cap);
 /* overwrite one numeric spanning-tree entry num[src][dst] (state injection for tests / checkpoint restore) */
 void srba_engine_set_num(void *h, uint64_t src, uint64_t dst, const double *pose);

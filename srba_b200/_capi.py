@@ -85,7 +85,7 @@ class NewEdge(C.Structure):
 EXPORTED_SYMBOLS = [
     "srba_b200_optimize", "srba_b200_optimize_batch", "srba_b200_batch_create", "srba_b200_batch_upload", "srba_b200_batch_run",
     "srba_b200_batch_download", "srba_b200_batch_unpack", "srba_b200_batch_destroy", "srba_b200_batch_h2d_bytes", "srba_b200_batch_d2h_bytes",
-    "srba_b200_batch_kernel_launches", "srba_b200_batch_stage_cycles", "srba_b200_problem_plan", "srba_b200_debug_ldl_schedule", "srba_b200_batch_algorithmic_bytes", "srba_b200_last_error", "srba_b200_device_count", "srba_b200_version",
+    "srba_b200_batch_kernel_launches", "srba_b200_batch_stage_cycles", "srba_b200_problem_plan", "srba_b200_debug_ldl_schedule", "srba_b200_batch_algorithmic_bytes", "srba_b200_eval_overall_squared_error", "srba_b200_last_error", "srba_b200_device_count", "srba_b200_version",
     "srba_engine_default_params", "srba_engine_create", "srba_engine_destroy", "srba_engine_set_params", "srba_engine_define_new_keyframe",
     "srba_engine_optimize_local_area", "srba_engine_optimize_edges", "srba_engine_select_local_area", "srba_engine_flatten",
     "srba_engine_flatten_local_area", "srba_flat_problem", "srba_flat_apply", "srba_flat_ids", "srba_flat_destroy",
@@ -94,7 +94,7 @@ EXPORTED_SYMBOLS = [
     "srba_engine_set_edge_pose", "srba_engine_num_unknown_lms", "srba_engine_get_unknown_lms", "srba_engine_set_lm_pos",
     "srba_engine_get_next_edge", "srba_engine_get_num", "srba_engine_set_num", "srba_engine_get_all_edges_path", "srba_engine_alloc_keyframe",
     "srba_engine_create_kf2kf_edge", "srba_engine_flatten_seconds", "srba_engine_gpu_seconds", "srba_engine_total_trials",
-    "srba_engine_last_error",
+    "srba_engine_eval_overall_squared_error", "srba_engine_complete_spanning_tree", "srba_engine_last_error",
 ]
 
 _lib = None
@@ -185,6 +185,10 @@ def lib():
     L.srba_engine_get_num.restype = u64
     L.srba_engine_get_num.argtypes = [vp, u64, pu64, pdbl, u64]
     L.srba_engine_set_num.argtypes = [vp, u64, u64, pdbl]
+    L.srba_engine_eval_overall_squared_error.restype = C.c_int
+    L.srba_engine_eval_overall_squared_error.argtypes = [vp, pdbl]
+    L.srba_engine_complete_spanning_tree.restype = C.c_int64
+    L.srba_engine_complete_spanning_tree.argtypes = [vp, u64, u64, pu64, pdbl, u64]
     L.srba_engine_get_all_edges_path.restype = C.c_int64
     L.srba_engine_get_all_edges_path.argtypes = [vp, u64, u64, pu64, u64]
     L.srba_engine_create_kf2kf_edge.restype = u64

@@ -21,6 +21,10 @@
 
 #include "dev_types.h"
 
+extern "C" int srba_launch_eval_error(const srba_model_t *model, int n_pairs, int n_obs, const double *edge_pose, const int32_t *pair_path_ptr,
+                                      const int32_t *path_edge, const uint8_t *path_dir, const double *obs_z, const int32_t *obs_pair,
+                                      const uint8_t *obs_inverse, const int32_t *obs_lm, const double *lm_pos, double *pair_pose, double *partial,
+                                      double *total, int grid_chain, int grid_resid, void *stream);
 extern "C" int srba_launch_lm_batch(int model, const char *img, const uint64_t *img_off, char *ws, const uint64_t *ws_off, char *res,
                                     const uint64_t *res_off, const int32_t *order, int n_problems, int grid, int smem_bytes, void *stream);
 
@@ -707,6 +711,71 @@ int srba_b200_device_count(void) {
 	int n = 0;
 	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
 	return n;
+}
+
+// Global diagnostics: RbaEngine::eval_overall_squared_error (impl/eval_overall_error.h:15-137), see include/srba_b200.h.
+int srba_b200_eval_overall_squared_error(const srba_eval_problem_t *in, double *out_sqerr, double *out_pair_pose) {
+	if (!in || !out_sqerr) return fail(SRBA_ERR_BAD_ARGUMENT, "null argument");
+	const srba_eval_problem_t &p = *in;
+	const srba_model_t &m = p.model;
+	const bool se2 = m.pose_kind == SRBA_POSE_SE2;
+	if (se2 ? (m.obs_kind != SRBA_OBS_RELPOSES2D || m.sensor_pose_kind != SRBA_SENSORPOSE_NONE)
+	        : (m.pose_kind != SRBA_POSE_SE3 || m.obs_kind < SRBA_OBS_CARTESIAN3D || m.obs_kind > SRBA_OBS_STEREO))
+		return fail(SRBA_ERR_UNSUPPORTED_MODEL, "model combination not built (SE2+RelativePoses_2D, SE3+Cartesian_3D/Monocular/Stereo)");
+	if (p.n_edges < 0 || p.n_pairs < 0 || p.n_path < 0 || p.n_obs < 0 || p.n_lms < 0) return fail(SRBA_ERR_BAD_ARGUMENT, "negative count");
+	if ((p.n_pairs > 0 && (!p.pair_path_ptr || !p.edge_pose)) || (p.n_path > 0 && (!p.path_edge || !p.path_dir)) ||
+	    (p.n_obs > 0 && (!p.obs_z || !p.obs_pair || !p.obs_inverse)) || (!se2 && p.n_obs > 0 && (!p.obs_lm || !p.lm_pos)))
+		return fail(SRBA_ERR_BAD_ARGUMENT, "null array");
+	for (int t = 0; t < p.n_pairs; t++)
+		if (p.pair_path_ptr[t] > p.pair_path_ptr[t + 1] || p.pair_path_ptr[t] < 0 || p.pair_path_ptr[t + 1] > p.n_path) return fail(SRBA_ERR_BAD_ARGUMENT, "pair_path_ptr is not a CSR row pointer");
+	for (int k = 0; k < p.n_path; k++)
+		if (p.path_edge[k] < 0 || p.path_edge[k] >= p.n_edges) return fail(SRBA_ERR_BAD_ARGUMENT, "path_edge out of range");
+	for (int i = 0; i < p.n_obs; i++) {
+		if (p.obs_pair[i] < -1 || p.obs_pair[i] >= p.n_pairs) return fail(SRBA_ERR_BAD_ARGUMENT, "obs_pair out of range");
+		if (!se2 && (p.obs_lm[i] < 0 || p.obs_lm[i] >= p.n_lms)) return fail(SRBA_ERR_BAD_ARGUMENT, "obs_lm out of range");
+	}
+	if (srba_b200_device_count() <= 0) return fail(SRBA_ERR_NO_DEVICE, "no CUDA device (srba_b200 has no CPU fallback)");
+	const int S = se2 ? 3 : 12, o = obs_dims(m.obs_kind);
+	int dev = 0, sms = 148;
+	CUDA_TRY(cudaGetDevice(&dev));
+	CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+	// grids: whole waves of the SM count, 256-thread CTAs, at most 8 CTAs per SM (grid-stride loops take the rest)
+	auto grid_for = [&](int n) { const int need = (n + 255) / 256; return std::max(1, std::min(need, 8 * sms)); };
+	const int grid_chain = grid_for(p.n_pairs), grid_resid = grid_for(p.n_obs);
+	// one packed image, one H2D copy
+	Layout L;
+	const uint64_t o_edge = L.add((uint64_t)p.n_edges * S * 8), o_ptr = L.add((uint64_t)(p.n_pairs + 1) * 4), o_pe = L.add((uint64_t)p.n_path * 4),
+	               o_pd = L.add(p.n_path), o_z = L.add((uint64_t)p.n_obs * o * 8), o_op = L.add((uint64_t)p.n_obs * 4), o_oi = L.add(p.n_obs),
+	               o_ol = L.add((uint64_t)p.n_obs * 4), o_lm = L.add((uint64_t)p.n_lms * 3 * 8);
+	const uint64_t in_bytes = L.total();
+	const uint64_t o_pose = L.add((uint64_t)p.n_pairs * S * 8), o_part = L.add((uint64_t)grid_resid * 8), o_tot = L.add(8);
+	const uint64_t all_bytes = L.total();
+	char *h = nullptr, *d = nullptr;
+	if (cudaMallocHost(&h, all_bytes) != cudaSuccess) return fail(SRBA_ERR_CUDA, "cudaMallocHost failed");
+	if (cudaMalloc(&d, all_bytes) != cudaSuccess) { cudaFreeHost(h); return fail(SRBA_ERR_CUDA, "cudaMalloc failed"); }
+	auto put = [&](uint64_t off, const void *src, uint64_t bytes) { if (bytes && src) std::memcpy(h + off, src, bytes); };
+	put(o_edge, p.edge_pose, (uint64_t)p.n_edges * S * 8);
+	if (p.n_pairs > 0) put(o_ptr, p.pair_path_ptr, (uint64_t)(p.n_pairs + 1) * 4);
+	put(o_pe, p.path_edge, (uint64_t)p.n_path * 4); put(o_pd, p.path_dir, p.n_path);
+	put(o_z, p.obs_z, (uint64_t)p.n_obs * o * 8); put(o_op, p.obs_pair, (uint64_t)p.n_obs * 4); put(o_oi, p.obs_inverse, p.n_obs);
+	if (!se2) { put(o_ol, p.obs_lm, (uint64_t)p.n_obs * 4); put(o_lm, p.lm_pos, (uint64_t)p.n_lms * 3 * 8); }
+	int rc = SRBA_OK;
+	cudaError_t e = cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, 0);
+	if (e == cudaSuccess)
+		e = (cudaError_t)srba_launch_eval_error(&m, p.n_pairs, p.n_obs, (const double *)(d + o_edge), (const int32_t *)(d + o_ptr), (const int32_t *)(d + o_pe),
+		                                        (const uint8_t *)(d + o_pd), (const double *)(d + o_z), (const int32_t *)(d + o_op), (const uint8_t *)(d + o_oi),
+		                                        (const int32_t *)(d + o_ol), (const double *)(d + o_lm), (double *)(d + o_pose), (double *)(d + o_part),
+		                                        (double *)(d + o_tot), grid_chain, grid_resid, nullptr);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(h + o_pose, d + o_pose, all_bytes - o_pose, cudaMemcpyDeviceToHost, 0);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+	if (e != cudaSuccess) rc = fail(SRBA_ERR_CUDA, std::string("eval_overall_squared_error: ") + cudaGetErrorString(e));
+	else {
+		*out_sqerr = *reinterpret_cast<double *>(h + o_tot);
+		if (out_pair_pose && p.n_pairs > 0) std::memcpy(out_pair_pose, h + o_pose, (uint64_t)p.n_pairs * S * 8);
+	}
+	cudaFree(d);
+	cudaFreeHost(h);
+	return rc;
 }
 
 void srba_b200_batch_destroy(srba_batch_t *b) {

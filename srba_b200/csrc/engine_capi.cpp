@@ -257,6 +257,35 @@ uint64_t srba_engine_get_next_edge(void *h, uint64_t kf, uint64_t *target, uint6
 	});
 	return n;
 }
+int srba_engine_eval_overall_squared_error(void *h, double *out_sqerr) {
+	GUARD_BEGIN
+	DISPATCH(h, *out_sqerr = E.eval_overall_squared_error());
+	return 0;
+	GUARD_END(-1)
+}
+int64_t srba_engine_complete_spanning_tree(void *h, uint64_t root, uint64_t max_depth, uint64_t *ids, double *poses, uint64_t cap) {
+	GUARD_BEGIN
+	int64_t n = 0;
+	DISPATCH(h, {
+		typedef typename std::remove_reference<decltype(E)>::type EngT;
+		std::vector<TKeyFrameID> id_;
+		std::vector<double> pose_;
+		if (!ids && !poses) {  // size query: the integer BFS only
+			std::map<TKeyFrameID, typename EngT::BfsNode> prec;
+			E.complete_spanning_tree_bfs(root, max_depth, prec);
+			n = (int64_t)prec.size();
+		} else {
+			E.create_complete_spanning_tree(root, max_depth, id_, pose_);
+			n = (int64_t)id_.size();
+			for (uint64_t k = 0; k < std::min<uint64_t>(cap, id_.size()); k++) {
+				if (ids) ids[k] = id_[k];
+				if (poses) std::memcpy(poses + k * EngT::S, &pose_[k * EngT::S], sizeof(double) * EngT::S);
+			}
+		}
+	});
+	return n;
+	GUARD_END(-1)
+}
 uint64_t srba_engine_get_num(void *h, uint64_t kf, uint64_t *target, double *poses, uint64_t cap) {
 	uint64_t n = 0;
 	DISPATCH(h, {

@@ -190,6 +190,134 @@ class RbaEngine : public EngineBase {
 		return false;
 	}
 
+	// BFS half of create_complete_spanning_tree (impl/spantree_create_complete.h:35-83): visiting order = adjacency order,
+	// a keyframe's tree parent is the first dequeued neighbour that reaches it.  Stops early once every keyframe of `wanted`
+	// (if given) has been reached -- parents are final at first visit, so the tree below is the same.
+	struct BfsNode { TKeyFrameID prev; uint32_t edge; uint64_t dist; };
+	void complete_spanning_tree_bfs(TKeyFrameID root, uint64_t max_depth, std::map<TKeyFrameID, BfsNode> &prec, const std::set<TKeyFrameID> *wanted = nullptr) const {
+		prec.clear();
+		SRBA_CHECK(root < keyframes.size());
+		std::queue<TKeyFrameID> pending;
+		pending.push(root);
+		prec[root] = BfsNode{root, 0, 0};
+		size_t missing = 0;
+		if (wanted) for (TKeyFrameID w : *wanted) missing += (w != root) ? 1 : 0;
+		while (!pending.empty() && !(wanted && missing == 0)) {
+			const TKeyFrameID next_kf = pending.front();
+			pending.pop();
+			const uint64_t cur_dist = prec[next_kf].dist;
+			if (cur_dist >= max_depth) continue;
+			for (uint32_t e : keyframes[next_kf].adj_k2k) {
+				const TKeyFrameID nk = other_end(next_kf, e);
+				if (!prec.count(nk)) {
+					pending.push(nk);
+					prec[nk] = BfsNode{next_kf, e, cur_dist + 1};
+					if (wanted && wanted->count(nk)) missing--;
+				}
+			}
+		}
+	}
+	// chain of (edge, dir) from root to target through the BFS tree; dir 1: the edge's `from` is the node being reached
+	// (compose inv_pose), 0: its `to` is (compose -inv_pose)  (spantree_create_complete.h:117-122)
+	void bfs_chain(const std::map<TKeyFrameID, BfsNode> &prec, TKeyFrameID root, TKeyFrameID target, std::vector<int32_t> &edges, std::vector<uint8_t> &dirs) const {
+		std::vector<std::pair<int32_t, uint8_t> > rev;
+		for (TKeyFrameID node = target; node != root;) {
+			const BfsNode &b = prec.at(node);
+			rev.push_back(std::make_pair((int32_t)b.edge, (uint8_t)(k2k_edges[b.edge].to == node ? 0 : 1)));
+			node = b.prev;
+		}
+		for (size_t i = rev.size(); i-- > 0;) { edges.push_back(rev[i].first); dirs.push_back(rev[i].second); }
+	}
+	void fill_eval_model(srba_model_t &m) const {
+		std::memset(&m, 0, sizeof(m));
+		m.pose_kind = parameters.pose_kind; m.obs_kind = parameters.obs_kind; m.sensor_pose_kind = parameters.sensor_pose_kind; m.noise_kind = parameters.noise_kind;
+		std::memcpy(m.sensor_pose, sensor_pose3.v, sizeof(m.sensor_pose));
+		m.noise_std = parameters.noise_std;
+		std::memcpy(m.cam_left, parameters.cam_left, sizeof(m.cam_left));
+		std::memcpy(m.cam_right, parameters.cam_right, sizeof(m.cam_right));
+		std::memcpy(m.right_cam_R2L, right_cam_R2L.v, sizeof(m.right_cam_R2L));
+	}
+	std::vector<double> all_edge_poses() const {
+		std::vector<double> ep(k2k_edges.size() * S + 1);
+		for (size_t e = 0; e < k2k_edges.size(); e++) std::memcpy(&ep[e * S], k2k_edges[e].inv_pose.v, S * sizeof(double));
+		return ep;
+	}
+
+	// create_complete_spanning_tree (impl/spantree_create_complete.h:18-127): ids ascending (the reference returns a std::map),
+	// poses of every reached keyframe as seen from root, composed on the device.
+	void create_complete_spanning_tree(TKeyFrameID root, uint64_t max_depth, std::vector<TKeyFrameID> &ids, std::vector<double> &poses) const {
+		std::map<TKeyFrameID, BfsNode> prec;
+		complete_spanning_tree_bfs(root, max_depth, prec);
+		ids.clear();
+		std::vector<int32_t> ptr(1, 0), pe;
+		std::vector<uint8_t> pd;
+		for (const auto &kv : prec) {
+			ids.push_back(kv.first);
+			bfs_chain(prec, root, kv.first, pe, pd);
+			ptr.push_back((int32_t)pe.size());
+		}
+		srba_eval_problem_t q;
+		std::memset(&q, 0, sizeof(q));
+		fill_eval_model(q.model);
+		const std::vector<double> ep = all_edge_poses();
+		q.n_edges = (int32_t)k2k_edges.size(); q.n_pairs = (int32_t)ids.size(); q.n_path = (int32_t)pe.size();
+		q.edge_pose = ep.data(); q.pair_path_ptr = ptr.data(); q.path_edge = pe.data(); q.path_dir = pd.data();
+		poses.assign(ids.size() * S, 0.0);
+		double unused = 0;
+		if (srba_b200_eval_overall_squared_error(&q, &unused, poses.data()) != SRBA_OK)
+			throw std::runtime_error(std::string("srba_b200_eval_overall_squared_error failed: ") + srba_b200_last_error());
+	}
+
+	// eval_overall_squared_error (impl/eval_overall_error.h:15-137): integer work (pairs, BFS trees, chains) here, every pose
+	// composition, observation error and the sum on the device.
+	double eval_overall_squared_error() const {
+		std::map<TKeyFrameID, std::set<TKeyFrameID> > ob_pairs;  // minimum id first (:29-39)
+		for (const Observation &ob : all_observations) {
+			const TKeyFrameID base = all_lms[ob.lm].base;
+			if (base != ob.kf) ob_pairs[std::min(ob.kf, base)].insert(std::max(ob.kf, base));
+		}
+		std::map<std::pair<TKeyFrameID, TKeyFrameID>, int32_t> pair_idx;
+		std::vector<int32_t> ptr(1, 0), pe;
+		std::vector<uint8_t> pd;
+		std::map<TKeyFrameID, BfsNode> prec;
+		for (const auto &rp : ob_pairs) {
+			complete_spanning_tree_bfs(rp.first, std::numeric_limits<uint64_t>::max(), prec, &rp.second);
+			for (TKeyFrameID w : rp.second) {
+				if (!prec.count(w)) continue;  // not connected: the reference's ASSERT_ fires when the observation is evaluated (:106-110)
+				pair_idx[std::make_pair(rp.first, w)] = (int32_t)ptr.size() - 1;
+				bfs_chain(prec, rp.first, w, pe, pd);
+				ptr.push_back((int32_t)pe.size());
+			}
+		}
+		const size_t n_obs = all_observations.size();
+		std::vector<double> z(n_obs * O + 1), lm(all_lms.size() * 3 + 1);
+		std::vector<int32_t> op(n_obs + 1), ol(n_obs + 1);
+		std::vector<uint8_t> oi(n_obs + 1);
+		for (size_t i = 0; i < n_obs; i++) {
+			const Observation &ob = all_observations[i];
+			const TKeyFrameID base = all_lms[ob.lm].base;
+			for (int k = 0; k < O; k++) z[i * O + k] = ob.z[k];
+			ol[i] = (int32_t)ob.lm;
+			if (base == ob.kf) { op[i] = -1; oi[i] = 0; continue; }
+			const auto it = pair_idx.find(std::make_pair(std::min(ob.kf, base), std::max(ob.kf, base)));
+			SRBA_CHECK(it != pair_idx.end());  // ASSERT_(itRelPose != ...end())  (:109)
+			op[i] = it->second;
+			oi[i] = ob.kf > base ? 1 : 0;  // pose of base as seen from the observer: the tree pose when the observer is the root
+		}
+		for (size_t l = 0; l < all_lms.size(); l++) std::memcpy(&lm[l * 3], all_lms[l].pos, 3 * sizeof(double));
+		srba_eval_problem_t q;
+		std::memset(&q, 0, sizeof(q));
+		fill_eval_model(q.model);
+		const std::vector<double> ep = all_edge_poses();
+		q.n_edges = (int32_t)k2k_edges.size(); q.n_pairs = (int32_t)ptr.size() - 1; q.n_path = (int32_t)pe.size(); q.n_obs = (int32_t)n_obs; q.n_lms = (int32_t)all_lms.size();
+		q.edge_pose = ep.data(); q.pair_path_ptr = ptr.data(); q.path_edge = pe.data(); q.path_dir = pd.data();
+		q.obs_z = z.data(); q.obs_pair = op.data(); q.obs_inverse = oi.data(); q.obs_lm = ol.data(); q.lm_pos = lm.data();
+		double sqerr = 0;
+		if (srba_b200_eval_overall_squared_error(&q, &sqerr, nullptr) != SRBA_OK)
+			throw std::runtime_error(std::string("srba_b200_eval_overall_squared_error failed: ") + srba_b200_last_error());
+		return sqerr;
+	}
+
 	// update_symbolic_new_node (impl/spantree_update_symbolic.h:19-211)
 	void update_symbolic_new_node(TKeyFrameID new_node_id, TKeyFrameID e_first, TKeyFrameID e_second, uint64_t max_depth) {
 		SRBA_CHECK(max_depth >= 1);

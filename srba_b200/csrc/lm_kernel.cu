@@ -1816,6 +1816,140 @@ extern "C" int srba_launch_lm_batch(int model, const char *img, const uint64_t *
 #undef LAUNCH
 	return (int)cudaGetLastError();
 }
+
+// ------------------------------------------------------------------------------------------------ global diagnostics
+// RbaEngine::eval_overall_squared_error (impl/eval_overall_error.h:15-137).  Streaming kernels over the whole map (every
+// observation once, every needed pair once): HBM-bound by construction, grid = a multiple of the SM count.
+struct EvalArgs {
+	srba_model_t model;
+	int n_pairs, n_obs;
+	const double *edge_pose;
+	const int32_t *pair_path_ptr, *path_edge;
+	const uint8_t *path_dir;
+	const double *obs_z;
+	const int32_t *obs_pair;
+	const uint8_t *obs_inverse;
+	const int32_t *obs_lm;
+	const double *lm_pos;
+	double *pair_pose;   // n_pairs x S (device)
+	double *partial;     // one partial sum per CTA of the residual kernel
+	double *total;
+};
+
+// numeric half of create_complete_spanning_tree (impl/spantree_create_complete.h:91-125): one thread per target
+template <int P>
+__global__ void __launch_bounds__(256) srba_eval_chain_kernel(const EvalArgs a) {
+	constexpr int S = PoseOps<P>::S;
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < a.n_pairs; t += gridDim.x * blockDim.x) {
+		double accum[S], tmp[S];
+		PoseOps<P>::identity(accum);  // span_tree[root] = pose_t()  (:108)
+		for (int k = a.pair_path_ptr[t]; k < a.pair_path_ptr[t + 1]; k++) {
+			const double *ep = a.edge_pose + (size_t)a.path_edge[k] * S;
+			const double *rhs = ep;
+			if (!a.path_dir[k]) { PoseOps<P>::inverse(tmp, ep); rhs = tmp; }  // edge.to == kf: parent (+) (-inv_pose)  (:117-118)
+			PoseOps<P>::compose(accum, accum, rhs);
+		}
+#pragma unroll
+		for (int i = 0; i < S; i++) a.pair_pose[(size_t)t * S + i] = accum[i];
+	}
+}
+
+// sensor_model<>::observe_error on one observation (models/sensors.h:49-66,174-211,348-364,769-785), no robust kernel
+template <int P, int OBSK>
+__device__ __forceinline__ double eval_obs_sqerr(const EvalArgs &a, const double *sensor_inv, int i) {
+	constexpr int S = PoseOps<P>::S;
+	constexpr int O = ObsDims<OBSK>::O;
+	const double *z = a.obs_z + (size_t)i * O;
+	double Pp[S];
+	const int t = a.obs_pair[i];
+	if (t < 0) PoseOps<P>::identity(Pp);  // base == observer: aux_null_pose (:98-101)
+	else {
+#pragma unroll
+		for (int k = 0; k < S; k++) Pp[k] = a.pair_pose[(size_t)t * S + k];
+		if (a.obs_inverse[i]) PoseOps<P>::inverse(Pp, Pp);  // all_rel_poses[*it_want][root] = -pose  (:75)
+	}
+	double r[O];
+	if constexpr (P == 3) {
+		double sn, cs;
+		sincos(Pp[2], &sn, &cs);
+		r[0] = (z[0] - Pp[0]) * cs + (z[1] - Pp[1]) * sn;
+		r[1] = -(z[0] - Pp[0]) * sn + (z[1] - Pp[1]) * cs;
+		r[2] = wrapToPi(z[2] - Pp[2]);
+	} else {
+		if (a.model.sensor_pose_kind == SRBA_SENSORPOSE_SE3) PoseOps<6>::compose(Pp, sensor_inv, Pp);
+		double x[3];
+		compose_point3(Pp, a.lm_pos + (size_t)a.obs_lm[i] * 3, x);
+		double pred[O];
+		if (OBSK == SRBA_OBS_CARTESIAN3D) { pred[0] = x[0]; pred[1] = x[1]; pred[2] = x[2]; }
+		else {
+			pred[0] = a.model.cam_left[2] + a.model.cam_left[0] * x[0] / x[2];
+			pred[1] = a.model.cam_left[3] + a.model.cam_left[1] * x[1] / x[2];
+			if (OBSK == SRBA_OBS_STEREO) {
+				double rr[3];
+				compose_point3(a.model.right_cam_R2L, x, rr);
+				pred[2] = a.model.cam_right[2] + a.model.cam_right[0] * rr[0] / rr[2];
+				pred[O - 1] = a.model.cam_right[3] + a.model.cam_right[1] * rr[1] / rr[2];
+			}
+		}
+#pragma unroll
+		for (int k = 0; k < O; k++) r[k] = z[k] - pred[k];
+	}
+	double s2 = 0;
+#pragma unroll
+	for (int k = 0; k < O; k++) s2 += r[k] * r[k];
+	return s2;
+}
+
+template <int P, int OBSK>
+__global__ void __launch_bounds__(256) srba_eval_residual_kernel(const EvalArgs a) {
+	__shared__ double sensor_inv[12];
+	__shared__ double wsum[8];
+	if (threadIdx.x == 0 && P == 6 && a.model.sensor_pose_kind == SRBA_SENSORPOSE_SE3) PoseOps<6>::inverse(sensor_inv, a.model.sensor_pose);
+	__syncthreads();
+	double local = 0;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_obs; i += gridDim.x * blockDim.x) local += eval_obs_sqerr<P, OBSK>(a, sensor_inv, i);
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+	if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = local;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		double s = 0;
+		for (int w = 0; w < (int)blockDim.x / 32; w++) s += wsum[w];
+		a.partial[blockIdx.x] = s;
+	}
+}
+// fixed-order final sum of the CTA partials (deterministic for a given grid)
+__global__ void srba_eval_sum_kernel(const double *partial, int n, double *total) {
+	if (threadIdx.x == 0 && blockIdx.x == 0) {
+		double s = 0;
+		for (int i = 0; i < n; i++) s += partial[i];
+		*total = s;
+	}
+}
+
+// grid_resid = CTAs of the residual kernel (= length of `partial`).
+extern "C" int srba_launch_eval_error(const srba_model_t *model, int n_pairs, int n_obs, const double *edge_pose, const int32_t *pair_path_ptr,
+                                      const int32_t *path_edge, const uint8_t *path_dir, const double *obs_z, const int32_t *obs_pair,
+                                      const uint8_t *obs_inverse, const int32_t *obs_lm, const double *lm_pos, double *pair_pose, double *partial,
+                                      double *total, int grid_chain, int grid_resid, void *stream) {
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	EvalArgs a;
+	a.model = *model; a.n_pairs = n_pairs; a.n_obs = n_obs; a.edge_pose = edge_pose; a.pair_path_ptr = pair_path_ptr; a.path_edge = path_edge;
+	a.path_dir = path_dir; a.obs_z = obs_z; a.obs_pair = obs_pair; a.obs_inverse = obs_inverse; a.obs_lm = obs_lm; a.lm_pos = lm_pos;
+	a.pair_pose = pair_pose; a.partial = partial; a.total = total;
+	const bool se2 = model->pose_kind == SRBA_POSE_SE2;
+	if (n_pairs > 0) {
+		if (se2) srba_eval_chain_kernel<3><<<grid_chain, 256, 0, st>>>(a);
+		else srba_eval_chain_kernel<6><<<grid_chain, 256, 0, st>>>(a);
+	}
+	if (se2) srba_eval_residual_kernel<3, SRBA_OBS_RELPOSES2D><<<grid_resid, 256, 0, st>>>(a);
+	else if (model->obs_kind == SRBA_OBS_CARTESIAN3D) srba_eval_residual_kernel<6, SRBA_OBS_CARTESIAN3D><<<grid_resid, 256, 0, st>>>(a);
+	else if (model->obs_kind == SRBA_OBS_MONO) srba_eval_residual_kernel<6, SRBA_OBS_MONO><<<grid_resid, 256, 0, st>>>(a);
+	else if (model->obs_kind == SRBA_OBS_STEREO) srba_eval_residual_kernel<6, SRBA_OBS_STEREO><<<grid_resid, 256, 0, st>>>(a);
+	else return (int)cudaErrorInvalidValue;
+	srba_eval_sum_kernel<<<1, 32, 0, st>>>(partial, grid_resid, total);
+	return (int)cudaGetLastError();
+}
 #else   // SRBA_CLUSTER: the same program on clusters of SRBA_CLUSTER CTAs (one cluster per problem)
 extern "C" int srba_launch_lm_batch_cluster(int model, const char *img, const uint64_t *img_off, char *ws, const uint64_t *ws_off, char *res,
                                             const uint64_t *res_off, const int32_t *order, int n_problems, int smem_bytes, void *stream) {

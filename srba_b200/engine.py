@@ -258,6 +258,24 @@ class RbaEngine:
         self.L.srba_engine_get_num(self.h, kf, ptr(t, C.c_uint64), ptr(poses, C.c_double), n)
         return t, poses
 
+    def eval_overall_squared_error(self):
+        """RbaEngine::eval_overall_squared_error (impl/eval_overall_error.h:15-137): every observation of the map, poses from
+        complete BFS trees; BFS on the host, pose chains + observation errors + sum on the GPU."""
+        out = C.c_double()
+        if self.L.srba_engine_eval_overall_squared_error(self.h, C.byref(out)) != 0:
+            raise RuntimeError(self.L.srba_engine_last_error().decode())
+        return out.value
+
+    def complete_spanning_tree(self, root, max_depth=2 ** 64 - 1):
+        """RbaEngine::create_complete_spanning_tree (impl/spantree_create_complete.h:18-127): (ids ascending, poses wrt root)."""
+        n = self.L.srba_engine_complete_spanning_tree(self.h, root, max_depth, None, None, 0)
+        if n < 0:
+            raise RuntimeError(self.L.srba_engine_last_error().decode())
+        ids, poses = np.zeros(n, np.uint64), np.zeros((n, self.nv))
+        if self.L.srba_engine_complete_spanning_tree(self.h, root, max_depth, ptr(ids, C.c_uint64), ptr(poses, C.c_double), n) < 0:
+            raise RuntimeError(self.L.srba_engine_last_error().decode())
+        return ids, poses
+
     def set_num(self, src, dst, pose):
         p = np.ascontiguousarray(pose, dtype=np.float64)
         self.L.srba_engine_set_num(self.h, src, dst, ptr(p, C.c_double))

@@ -213,6 +213,76 @@ def test_no_schur_solver_differs_from_schur_only_after_a_rejected_step():
     assert t0[0, 2] != t2[0, 2]
 
 
+@pytest.mark.parametrize("name", ["cartesian3d", "stereo", "se2"])
+def test_reduced_system_matches_oracle_1e10(name):
+    """SURVEY 8(c), first fixture row: the reference's Schur property (tests/schur_unittest.cpp:258,267, tolerance 1e-10) on the
+    GPU Hessian + Schur stages.  One LM iteration from bit-identical state; the reduced system of the last solve
+    (extra_results.hessian, lev-marq_solvers.h:582-586: H_Ap - H_Apf (H_f + lambda I)^-1 H_Apf^t, + lambda on the diagonal)
+    from the device vs the oracle's dense H, upper triangle, <= 1e-10 of the largest entry."""
+    if name == "se2":
+        ds = D.graphslam_se2_tour(120, seed=4)
+        kw = dict(S2, noise_lambda=D.se2_noise_lambda(ds["sigma_xy"], ds["sigma_yaw"]), max_iters=1)
+    else:
+        kind = {"cartesian3d": 1, "stereo": 3}[name]
+        ds = D.landmark_slam_se3(n_kfs=30, n_lms=250, seed=5, obs_kind=name)
+        kw = dict(pose_kind=1, obs_kind=kind, noise_kind=0, noise_std=1e-3 if kind == 1 else 0.5, max_tree_depth=3, max_optimize_depth=3, submap_size=10,
+                  min_obs_to_loop_closure=4, max_iters=1)
+        if kind != 1:
+            kw.update(sensor_pose_kind=1, sensor_pose=ds["sensor_pose_xyzypr"], cam_left=ds["cam"], cam_right=ds["cam"],
+                      right_cam_pose=[ds["baseline"], 0, 0, 1, 0, 0, 0], use_robust_kernel=1)
+    eo, ep = make_pair(kw)
+    for f in ds["frames"]:
+        D.feed(eo, f)
+        D.feed(ep, f, run_local_optimization=False)
+        inject_state(eo, ep)
+    root = len(ds["frames"]) - 1
+    flat = ep.flatten_local_area(root, 3)
+    res = sb.optimize(flat, trace_cap=8, want_dense=True)
+    io = eo.optimize_local_area(root, 3)
+    Ho, valid = eo.last_dense_hessian()
+    assert valid and res.stats["hessian_valid"]
+    assert res.stats["num_trials"] == io["num_lm_trials"]
+    n = Ho.shape[0]
+    assert res.dense.shape == (n, n) and n == (3 if name == "se2" else 6) * flat.p.n_unk_edges
+    iu = np.triu_indices(n)
+    err = float(np.abs(res.dense[iu] - Ho[iu]).max() / np.abs(Ho[iu]).max())
+    print("%s: reduced system %dx%d, max |dH| / max |H| = %.2e" % (name, n, n, err))
+    assert err <= 1e-10
+
+
+@pytest.mark.parametrize("name", ["se2", "cartesian3d", "stereo", "mono"])
+def test_global_diagnostics_match_oracle(name):
+    """eval_overall_squared_error (impl/eval_overall_error.h:15-137) and create_complete_spanning_tree
+    (impl/spantree_create_complete.h:18-127) -- BFS on the host, pose chains / observation errors / sum on the device -- on a map
+    optimised by the oracle (state injected): tree ids bit-exact, tree poses <= 1e-9, total error <= 1e-9 relative."""
+    if name == "se2":
+        ds = D.graphslam_se2_tour(200, seed=2)
+        kw = dict(S2, noise_lambda=D.se2_noise_lambda(ds["sigma_xy"], ds["sigma_yaw"]))
+    else:
+        kind = {"cartesian3d": 1, "mono": 2, "stereo": 3}[name]
+        ds = D.landmark_slam_se3(n_kfs=40, n_lms=300, seed=7, obs_kind=name, lm_init_sigma=0.05 if name == "mono" else None)
+        kw = dict(pose_kind=1, obs_kind=kind, noise_kind=0, noise_std=1e-3 if kind == 1 else 0.5, max_tree_depth=3, max_optimize_depth=3, submap_size=10,
+                  min_obs_to_loop_closure=4)
+        if kind != 1:
+            kw.update(sensor_pose_kind=1, sensor_pose=ds["sensor_pose_xyzypr"], cam_left=ds["cam"], cam_right=ds["cam"],
+                      right_cam_pose=[ds["baseline"], 0, 0, 1, 0, 0, 0], use_robust_kernel=1)
+    eo, ep = make_pair(kw)
+    for f in ds["frames"]:
+        D.feed(eo, f)
+        D.feed(ep, f, run_local_optimization=False)
+        inject_state(eo, ep)
+    n = len(ds["frames"])
+    for root, depth in ((0, 2 ** 64 - 1), (n // 2, 4), (n - 1, 2 ** 64 - 1)):
+        io, po_ = eo.complete_spanning_tree(root, depth)
+        ip, pp_ = ep.complete_spanning_tree(root, depth)
+        assert io.tolist() == ip.tolist()
+        assert rel_err(pp_, po_) <= 1e-9, (root, depth, rel_err(pp_, po_))
+    so, sp = eo.eval_overall_squared_error(), ep.eval_overall_squared_error()
+    print("%s: overall squared error oracle %.12g, device %.12g over %d observations" % (name, so, sp, eo.num_observations))
+    assert so > 0 and abs(sp - so) <= 1e-9 * so
+    assert ep.eval_overall_squared_error() == sp  # fixed-order sum: deterministic
+
+
 @pytest.mark.parametrize("inverse", [False, True])
 def test_fixed_transformations_on_gpu(inverse):
     """tests/fixed-transformations_unittest.cpp through the CUDA path: recovered increment within 1e-3 (reference tolerance :127)."""

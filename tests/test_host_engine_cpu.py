@@ -184,3 +184,25 @@ def test_solver_kind_reaches_the_flattened_problem_and_is_validated():
     assert plans[0][0] == plans[1][0]
     extra = plans[2][0] - plans[0][0]
     assert 8 * plans[2][1] <= extra <= 8 * plans[2][1] + 64  # one more gradient-sized array (16-byte aligned)
+
+
+def test_complete_spanning_tree_bfs_reaches_the_same_keyframes_as_the_oracle():
+    """Integer half of create_complete_spanning_tree (impl/spantree_create_complete.h:35-83) on the host engine: same number of
+    keyframes reached as the oracle's restatement for several roots and depth limits (no device needed for the size query);
+    eval_overall_squared_error needs the device and says so."""
+    ds = D.graphslam_se2_tour(150, seed=2)
+    kw = dict(S2, noise_lambda=D.se2_noise_lambda(ds["sigma_xy"], ds["sigma_yaw"]))
+    eo = po.OracleEngine(po.default_params(**kw))
+    ep = sb.RbaEngine(sb.default_engine_params(**kw))
+    for f in ds["frames"]:
+        D.feed(eo, f, run_local_optimization=False)
+        D.feed(ep, f, run_local_optimization=False)
+    for root in (0, 37, 149):
+        for depth in (0, 1, 3, 7, 2 ** 64 - 1):
+            ids, _ = eo.complete_spanning_tree(root, depth)
+            n = ep.L.srba_engine_complete_spanning_tree(ep.h, root, depth, None, None, 0)
+            assert n == len(ids), (root, depth)
+    from srba_b200 import _capi as K
+    if K.lib().srba_b200_device_count() == 0:
+        with pytest.raises(RuntimeError, match="no CUDA device"):
+            ep.eval_overall_squared_error()
