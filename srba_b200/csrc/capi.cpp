@@ -209,7 +209,7 @@ void symbolic_tiles(const srba_problem_t &p, int P, long max_tiles_on_chip, Tile
 	const int q = P / 3, np = p.n_unk_edges, ntr = q * np, ntc = ntr + 1;
 	sy.clear();
 	sy.ntr = ntr;
-	if (ntr <= 0 || ntr > 4096) return;
+	if (ntr <= 0 || ntr > 16384) return;  // tile coordinates are packed (ti << 16) | tj; the pivot scratch (3 doubles per tile row) bounds what actually runs on chip
 	// ---- elimination order
 	const int Wb = (np + 63) / 64;
 	std::vector<uint64_t> adj((size_t)np * Wb, 0);
