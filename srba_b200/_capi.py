@@ -14,6 +14,7 @@ POSE_SE2, POSE_SE3 = 0, 1
 OBS_RELPOSES2D, OBS_CARTESIAN3D, OBS_MONO, OBS_STEREO = 0, 1, 2, 3
 SENSORPOSE_NONE, SENSORPOSE_SE3 = 0, 1
 NOISE_IDENTITY, NOISE_CONST_MATRIX = 0, 1
+SOLVER_SCHUR_DENSE, SOLVER_SCHUR_SPARSE, SOLVER_NO_SCHUR_SPARSE = 0, 1, 2  # RBA_OPTIONS::solver_t (srba_options_solver.h:21-77)
 OBS_DIMS = {OBS_RELPOSES2D: 3, OBS_CARTESIAN3D: 3, OBS_MONO: 2, OBS_STEREO: 4}
 INVALID = 2**64 - 1
 SRBA_OK, ERR_BAD_ARGUMENT, ERR_UNSUPPORTED_MODEL, ERR_RANK_DEFICIENT, ERR_CUDA, ERR_NO_DEVICE, ERR_INTERNAL = 0, -1, -2, -3, -4, -5, -6

@@ -139,7 +139,8 @@ def main(argv=None):
     if a.se2:
         if not a.graph_slam:
             ap.error("--se2 is built with --graph-slam (RelativePoses_2D) only")
-        sensor, kw = "relposes2d", dict(pose_kind=0, obs_kind=0, noise_kind=1)
+        # solver_t of the app's SE(2) instance: solver_LM_no_schur_sparse_cholesky (apps/srba-slam/instance_relative_graph_slam_se2.cpp:23)
+        sensor, kw = "relposes2d", dict(pose_kind=0, obs_kind=0, noise_kind=1, solver_kind=sb.SOLVER_NO_SCHUR_SPARSE)
     else:
         sensor = {"cartesian_3d": "cartesian3d", "monocularcamera": "mono", "stereocamera": "stereo"}[(a.obs or "Cartesian_3D").lower()]
         kw = dict(pose_kind=1, obs_kind={"cartesian3d": 1, "mono": 2, "stereo": 3}[sensor], noise_kind=0)

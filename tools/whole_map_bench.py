@@ -1,7 +1,7 @@
 """BASELINE configs #2/#3 "single local area" in their whole-map reading: builds an SE(3) landmark map
 with the product engine, then optimises EVERY keyframe-to-keyframe edge and landmark in one optimize_local_area(root, 10^6)
 problem (one heavy area -> an 8-CTA cluster, block-sparse L D L^t with minimum-degree order on L2-resident tiles).
-Usage: python tools/whole_map_bench.py [obs_kind] [n_kfs] [n_lms] [--cpu]"""
+Usage: python tools/whole_map_bench.py [obs_kind] [n_kfs] [n_lms] [depth] [--cpu]"""
 import ctypes as C
 import sys
 import time
@@ -16,9 +16,10 @@ from srba_b200 import datasets as D
 name = sys.argv[1] if len(sys.argv) > 1 else "cartesian3d"
 n_kfs = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 n_lms = int(sys.argv[3]) if len(sys.argv) > 3 else 2000
+depth = int(sys.argv[4]) if len(sys.argv) > 4 and sys.argv[4].isdigit() else 3
 kind = {"cartesian3d": 1, "mono": 2, "stereo": 3}[name]
 ds = D.landmark_slam_se3(n_kfs=n_kfs, n_lms=n_lms, seed=1, obs_kind=name, lm_init_sigma=0.05 if name == "mono" else None)
-kw = dict(pose_kind=1, obs_kind=kind, noise_kind=0, noise_std=1e-3 if kind == 1 else 0.5, max_tree_depth=3, max_optimize_depth=3, submap_size=10,
+kw = dict(pose_kind=1, obs_kind=kind, noise_kind=0, noise_std=1e-3 if kind == 1 else 0.5, max_tree_depth=depth, max_optimize_depth=depth, submap_size=10,
           min_obs_to_loop_closure=4)
 if kind != 1:
     kw.update(sensor_pose_kind=1, sensor_pose=ds["sensor_pose_xyzypr"], cam_left=ds["cam"], cam_right=ds["cam"], right_cam_pose=[ds["baseline"], 0, 0, 1, 0, 0, 0],
