@@ -93,6 +93,8 @@ uint64_t srba_engine_num_unknown_lms(void *h);
 void srba_engine_get_unknown_lms(void *h, uint64_t *ids, uint64_t *base, double *pos);
 void srba_engine_set_lm_pos(void *h, uint64_t id, const double *pos);
 uint64_t srba_engine_get_next_edge(void *h, uint64_t kf, uint64_t *target, uint64_t *next, uint64_t *dist, uint64_t cap);
+/* rba_state.all_observations_Jacob_validity (srba_types.h:722): one byte per observation; returns the number of observations. */
+uint64_t srba_engine_get_jacob_validity(void *h, uint8_t *out, uint64_t cap);
 /* RbaEngine::eval_overall_squared_error() (RbaEngine.h:381, impl/eval_overall_error.h:15-137): BFS trees on the host, all
  * numerics on the device through srba_b200_eval_overall_squared_error.  0 ok, -1 error (srba_engine_last_error). */
 int srba_engine_eval_overall_squared_error(void *h, double *out_sqerr);

@@ -229,6 +229,16 @@ uint64_t orc_complete_spanning_tree(void *h, uint64_t root, uint64_t max_depth, 
 	return n;
 	GUARD_END(0)
 }
+uint64_t orc_get_jacob_validity(void *h, uint8_t *out, uint64_t cap) {  /* all_observations_Jacob_validity (srba_types.h:722) */
+	GUARD_BEGIN
+	uint64_t n = 0;
+	DISPATCH(h, {
+		n = E.all_observations_Jacob_validity.size();
+		for (uint64_t i = 0; out && i < std::min<uint64_t>(n, cap); i++) out[i] = E.all_observations_Jacob_validity[i] ? 1 : 0;
+	});
+	return n;
+	GUARD_END(0)
+}
 double orc_eval_overall_squared_error(void *h) {
 	GUARD_BEGIN
 	double r = 0;

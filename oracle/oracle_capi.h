@@ -82,6 +82,8 @@ void orc_update_numeric_all(void *h);
 int orc_are_keyframes_connected(void *h, uint64_t a, uint64_t b);
 /* create_complete_spanning_tree (impl/spantree_create_complete.h:18-127): returns count; ids/poses may be NULL */
 uint64_t orc_complete_spanning_tree(void *h, uint64_t root, uint64_t max_depth, uint64_t *ids, double *poses, uint64_t cap);
+/* all_observations_Jacob_validity (srba_types.h:722), one byte per observation; returns the number of observations. */
+uint64_t orc_get_jacob_validity(void *h, uint8_t *out, uint64_t cap);
 /* RbaEngine::eval_overall_squared_error (impl/eval_overall_error.h:15-137): every observation, poses from complete BFS trees. */
 double orc_eval_overall_squared_error(void *h);
 /* extra_results.hessian of the last optimize_edges (optimize_edges.h:769): row-major n x n, upper triangle valid; returns n*n. */

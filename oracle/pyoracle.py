@@ -125,6 +125,8 @@ def lib(variant=""):
     L.orc_reset_opt_timer.argtypes = [vp]
     L.orc_schur_case.restype = C.c_int
     L.orc_schur_case.argtypes = [u64, u64, pu8, pdbl, pdbl, dbl, pdbl, pdbl, pu64]
+    L.orc_get_jacob_validity.restype = u64
+    L.orc_get_jacob_validity.argtypes = [vp, pu8, u64]
     L.orc_eval_overall_squared_error.restype = dbl
     L.orc_eval_overall_squared_error.argtypes = [vp]
     L.orc_last_dense_hessian.restype = u64
@@ -263,6 +265,12 @@ class OracleEngine:
 
     def eval_overall_squared_error(self):
         return self.L.orc_eval_overall_squared_error(self.h)
+
+    def jacob_validity(self):
+        n = self.L.orc_get_jacob_validity(self.h, None, 0)
+        v = np.zeros(n, np.uint8)
+        self.L.orc_get_jacob_validity(self.h, _p(v, C.c_uint8), n)
+        return v
 
     def last_dense_hessian(self):
         valid = C.c_int()

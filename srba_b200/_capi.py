@@ -95,7 +95,7 @@ EXPORTED_SYMBOLS = [
     "srba_engine_set_edge_pose", "srba_engine_num_unknown_lms", "srba_engine_get_unknown_lms", "srba_engine_set_lm_pos",
     "srba_engine_get_next_edge", "srba_engine_get_num", "srba_engine_set_num", "srba_engine_get_all_edges_path", "srba_engine_alloc_keyframe",
     "srba_engine_create_kf2kf_edge", "srba_engine_flatten_seconds", "srba_engine_gpu_seconds", "srba_engine_total_trials",
-    "srba_engine_eval_overall_squared_error", "srba_engine_complete_spanning_tree", "srba_engine_last_error",
+    "srba_engine_eval_overall_squared_error", "srba_engine_complete_spanning_tree", "srba_engine_get_jacob_validity", "srba_engine_last_error",
 ]
 
 _lib = None
@@ -186,6 +186,8 @@ def lib():
     L.srba_engine_get_num.restype = u64
     L.srba_engine_get_num.argtypes = [vp, u64, pu64, pdbl, u64]
     L.srba_engine_set_num.argtypes = [vp, u64, u64, pdbl]
+    L.srba_engine_get_jacob_validity.restype = u64
+    L.srba_engine_get_jacob_validity.argtypes = [vp, pu8, u64]
     L.srba_engine_eval_overall_squared_error.restype = C.c_int
     L.srba_engine_eval_overall_squared_error.argtypes = [vp, pdbl]
     L.srba_engine_complete_spanning_tree.restype = C.c_int64

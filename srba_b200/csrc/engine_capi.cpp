@@ -257,6 +257,14 @@ uint64_t srba_engine_get_next_edge(void *h, uint64_t kf, uint64_t *target, uint6
 	});
 	return n;
 }
+uint64_t srba_engine_get_jacob_validity(void *h, uint8_t *out, uint64_t cap) {
+	uint64_t n = 0;
+	DISPATCH(h, {
+		n = E.validity.size();
+		for (uint64_t i = 0; out && i < std::min<uint64_t>(n, cap); i++) out[i] = E.validity[i];
+	});
+	return n;
+}
 int srba_engine_eval_overall_squared_error(void *h, double *out_sqerr) {
 	GUARD_BEGIN
 	DISPATCH(h, *out_sqerr = E.eval_overall_squared_error());

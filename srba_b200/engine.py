@@ -258,6 +258,13 @@ class RbaEngine:
         self.L.srba_engine_get_num(self.h, kf, ptr(t, C.c_uint64), ptr(poses, C.c_double), n)
         return t, poses
 
+    def jacob_validity(self):
+        """rba_state.all_observations_Jacob_validity (srba_types.h:722)."""
+        n = self.L.srba_engine_get_jacob_validity(self.h, None, 0)
+        v = np.zeros(n, np.uint8)
+        self.L.srba_engine_get_jacob_validity(self.h, ptr(v, C.c_uint8), n)
+        return v
+
     def eval_overall_squared_error(self):
         """RbaEngine::eval_overall_squared_error (impl/eval_overall_error.h:15-137): every observation of the map, poses from
         complete BFS trees; BFS on the host, pose chains + observation errors + sum on the GPU."""

@@ -283,6 +283,46 @@ def test_global_diagnostics_match_oracle(name):
     assert ep.eval_overall_squared_error() == sp  # fixed-order sum: deterministic
 
 
+@pytest.mark.parametrize("name", ["stereo", "mono"])
+def test_invalid_observations_validity_protocol(name):
+    """Landmarks pushed BEHIND the camera: eval_jacob_dh_dx returns false for z <= 0 (models/sensors.h:92,237), the block is zeroed
+    and the observation's validity byte cleared (jacobians.h:321-327,971-977); Hessian terms with a cleared byte are skipped
+    (sparse_hessian_update_numeric.h:41) while the gradient is not.  Validity bytes bit-exact vs the oracle, same
+    initial error, first increment <= 1e-6."""
+    kind = {"mono": 2, "stereo": 3}[name]
+    ds = D.landmark_slam_se3(n_kfs=16, n_lms=160, seed=9, obs_kind=name, lm_init_sigma=0.05 if name == "mono" else None)
+    kw = dict(pose_kind=1, obs_kind=kind, noise_kind=0, noise_std=0.5, max_tree_depth=3, max_optimize_depth=3, submap_size=10, min_obs_to_loop_closure=4,
+              sensor_pose_kind=1, sensor_pose=ds["sensor_pose_xyzypr"], cam_left=ds["cam"], cam_right=ds["cam"],
+              right_cam_pose=[ds["baseline"], 0, 0, 1, 0, 0, 0], use_robust_kernel=1, max_iters=3)
+    eo, ep = make_pair(kw)
+    for f in ds["frames"]:
+        D.feed(eo, f, run_local_optimization=False)
+        D.feed(ep, f, run_local_optimization=False)
+    inject_state(eo, ep)
+    ids, _, pos = eo.unknown_lms()
+    assert len(ids) >= 20
+    for i in range(0, len(ids), 7):   # the robot frame looks along +x (sensor pose yaw -90, roll -90): mirror through the keyframe
+        q = -np.asarray(pos[i])
+        eo.set_lm_pos(int(ids[i]), q)
+        ep.set_lm_pos(int(ids[i]), q)
+    eo.trace_enable(True)
+    ep.trace(8)
+    io = eo.optimize_local_area(15, 3)
+    ip = ep.optimize_local_area(15, 3)
+    vo, vp = eo.jacob_validity(), ep.jacob_validity()
+    assert len(vo) == len(vp) and vo.tolist() == vp.tolist()
+    assert 0 < int((vo == 0).sum()) < len(vo)
+    for key in INT_KEYS:
+        assert io[key] == ip[key], key
+    assert abs(io["total_sqr_error_init"] - ip["total_sqr_error_init"]) <= 1e-9 * io["total_sqr_error_init"]
+    to = eo.traces()[-1]
+    tp, dp = ep.last_trace()
+    assert len(tp) and tp[0, 1] == to["trials"][0, 1]
+    if tp[0, 1]:
+        assert rel_err(dp[0], to["deltas"][0]) <= REL_TOL_INCREMENT
+    print("%s: %d of %d observations invalid; first increment rel. error %.2e" % (name, int((vo == 0).sum()), len(vo), rel_err(dp[0], to["deltas"][0])))
+
+
 @pytest.mark.parametrize("inverse", [False, True])
 def test_fixed_transformations_on_gpu(inverse):
     """tests/fixed-transformations_unittest.cpp through the CUDA path: recovered increment within 1e-3 (reference tolerance :127)."""
