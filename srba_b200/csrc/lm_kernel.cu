@@ -475,6 +475,7 @@ __device__ bool jacob_dh_df(const View &v, int b, double *J) {
 // K2a: recompute_all_Jacobians (impl/jacobians.h:1083-1117) with the validity protocol of SURVEY.md §9-5:
 // the first block of a row (in the reference's column-major walk) whose sensor model fails zeroes itself and clears the
 // row's validity byte; blocks walked before it keep their fresh value, blocks walked after it keep their PREVIOUS value.
+// (PREVIOUS = previous linearisation of the same call; at the first linearisation of a call they are zero, see below.)
 // `first` additionally records which numeric-ST entries the walk registers in list_of_required_num_poses (:226-230,:902-903).
 template <int P, int OBSK>
 __device__ __noinline__ void stage_jacobians(const View &vs, bool first) {
@@ -526,10 +527,13 @@ __device__ __noinline__ void stage_jacobians(const View &vs, bool first) {
 					jacob_dh_dAp<P, OBSK>(v, b, J);
 #pragma unroll
 					for (int i = 0; i < O * P; i++) dst[i] = J[i];
-				} else if (my_pos == first_bad) {
+				} else if (my_pos == first_bad || first) {
+					// the deciding block is zero-filled (:324-326).  Later blocks of the row keep their value from the previous
+					// linearisation; on the FIRST linearisation of a call that would be the value an earlier optimize_edges call
+					// left in lin_system (or an uninitialised Eigen matrix): not carried across calls here -- zero, deterministic
 #pragma unroll
 					for (int i = 0; i < O * P; i++) dst[i] = 0;
-					v.valid[obs] = 0;
+					if (my_pos == first_bad) v.valid[obs] = 0;
 				}
 			} else if (P == 6) {
 				const int f = b - nA;
@@ -539,10 +543,10 @@ __device__ __noinline__ void stage_jacobians(const View &vs, bool first) {
 					jacob_dh_df<OBSK>(v, f, J);
 #pragma unroll
 					for (int i = 0; i < O * 3; i++) dst[i] = J[i];
-				} else if (my_pos == first_bad) {
+				} else if (my_pos == first_bad || first) {
 #pragma unroll
 					for (int i = 0; i < O * 3; i++) dst[i] = 0;
-					v.valid[obs] = 0;
+					if (my_pos == first_bad) v.valid[obs] = 0;
 				}
 			}
 			if (first && visited_valid) {
