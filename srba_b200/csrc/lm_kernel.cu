@@ -707,7 +707,7 @@ __device__ __noinline__ double stage_gradient(const View &vs, const double *resi
 	const bool ident = (h->model.noise_kind == SRBA_NOISE_IDENTITY);
 	const double scale = ident ? 1.0 / h->model.noise_std : 1.0;
 	const int nAp = h->n_unk_edges * P;
-	const bool keep = no_schur_solver(h);
+	const bool keep = (OBSK != SRBA_OBS_RELPOSES2D) && no_schur_solver(h);
 	double gmax = 0;
 	for (int it = LM_TID; it < h->n_scalars; it += LM_THREADS) {
 		double g = 0;
@@ -1566,7 +1566,7 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 		v.stats->total_sqr_error_init = err0;
 	}
 	const double MAX_LAMBDA = h->model.max_lambda;
-	const bool keep_grad = no_schur_solver(h);
+	const bool keep_grad = (OBSK != SRBA_OBS_RELPOSES2D) && no_schur_solver(h);  // relative graph-SLAM has no landmark unknowns: compiled out
 	const double max_gradient_to_stop = 1e-15;
 	// P. LM iterations (:454-696).  The reference's two nested loops
 	//     while (iter < max_iters && !stop) { rho = 0; stop tests; while (rho <= 0 && !stop) { TRIAL } iter++; }
