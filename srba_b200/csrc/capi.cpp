@@ -13,6 +13,7 @@
 #include <thread>
 
 #include <pthread.h>
+#include <sched.h>
 #include <cstdio>
 #include <cstring>
 #include <numeric>
@@ -174,6 +175,7 @@ long elimination_fill(const std::vector<uint64_t> &adj0, int np, int Wb, int q, 
 	std::vector<uint64_t> alive(Wb, 0);
 	for (int i = 0; i < np; i++) alive[i >> 6] |= 1ull << (i & 63);
 	long tiles = (long)q * np;  // right-hand side
+	std::vector<uint64_t> nb(Wb);
 	for (int step = 0; step < np; step++) {
 		int pick = -1;
 		if (order) pick = (*order)[step];
@@ -188,7 +190,6 @@ long elimination_fill(const std::vector<uint64_t> &adj0, int np, int Wb, int q, 
 			md_order->push_back(pick);
 		}
 		alive[pick >> 6] &= ~(1ull << (pick & 63));
-		std::vector<uint64_t> nb(Wb);
 		int deg = 0;
 		for (int w = 0; w < Wb; w++) { nb[w] = adj[(size_t)pick * Wb + w] & alive[w]; deg += __builtin_popcountll(nb[w]); }
 		tiles += (long)q * (q + 1) / 2 + (long)q * q * deg;
@@ -295,7 +296,16 @@ void symbolic_tiles(const srba_problem_t &p, int P, long max_tiles_on_chip, Tile
 		}
 	}
 	sy.rs[ntr] = (int32_t)sy.tile_ij.size();
-	auto find_tile = [&](int i, int j) {  // id of tile (i,j): row i's tiles are contiguous, ascending column
+	// id of tile (i,j): small systems keep a dense (row, column) -> id table, large ones search the row (tiles of a row are
+	// contiguous, ascending column)
+	const bool dense_ids = (size_t)ntr * ntc <= (1u << 20);
+	std::vector<int32_t> tid;
+	if (dense_ids) {
+		tid.assign((size_t)ntr * ntc, -1);
+		for (size_t t = 0; t < sy.tile_ij.size(); t++) tid[(size_t)(sy.tile_ij[t] >> 16) * ntc + (sy.tile_ij[t] & 0xffff)] = (int32_t)t;
+	}
+	auto find_tile = [&](int i, int j) {
+		if (dense_ids) return tid[(size_t)i * ntc + j];
 		const int32_t key = (i << 16) | j;
 		const auto it = std::lower_bound(sy.tile_ij.begin() + sy.rs[i], sy.tile_ij.begin() + sy.rs[i + 1], key);
 		return (int32_t)(it - sy.tile_ij.begin());
@@ -326,6 +336,7 @@ void symbolic_tiles(const srba_problem_t &p, int P, long max_tiles_on_chip, Tile
 	// update schedule: row k's pairs of tiles; the updates of the NEXT phase's pivot blocks are implicit (done by the lanes
 	// that invert those pivots)
 	sy.upd_ptr.assign(ntr + 1, 0);
+	sy.upd.reserve(4 * sy.tile_ij.size());
 	int32_t n_upd = 0;
 	for (int k = 0; k < ntr; k++) {
 		sy.upd_ptr[k] = n_upd;
@@ -572,7 +583,7 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 
 // Small persistent worker pool for the host side of a batch call (packing / unpacking 256 problems is as long as the
 // kernel itself when done on one core).  parallel_for(n, f) runs f(0..n-1) on the caller + workers (dynamic chunks).
-// SRBA_B200_THREADS overrides the thread count (default: hardware threads, at most 16).
+// SRBA_B200_THREADS overrides the thread count (default: the process's CPUs / LOCAL_WORLD_SIZE, at most 16).
 std::atomic<bool> g_forked{false};  // worker threads do not survive fork(): a forked child packs serially
 class WorkerPool {
 	// Workers SPIN on an atomic generation counter for a short while after their last job (a batch call issues eight
@@ -616,7 +627,13 @@ class WorkerPool {
 
 public:
 	WorkerPool() {
+		// default: the CPUs this process may run on, shared evenly between the ranks of the node when launched one process
+		// per GPU (torchrun exports LOCAL_WORLD_SIZE): spinning workers of 8 ranks must not oversubscribe the host cores
 		int k = (int)std::thread::hardware_concurrency();
+		cpu_set_t cs;
+		CPU_ZERO(&cs);
+		if (sched_getaffinity(0, sizeof(cs), &cs) == 0 && CPU_COUNT(&cs) > 0) k = CPU_COUNT(&cs);
+		if (const char *lw = std::getenv("LOCAL_WORLD_SIZE")) { const int w = std::atoi(lw); if (w > 1) k = std::max(2, k / w); }
 		if (const char *e = std::getenv("SRBA_B200_THREADS")) k = std::atoi(e);
 		k = std::max(1, std::min(k, 16));
 		for (int i = 1; i < k; i++) th_.emplace_back([this] { loop(); });

@@ -63,7 +63,9 @@ import torch
 import torch.distributed as dist
 torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
 if world > 1:
-    dist.init_process_group("nccl")
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))))
 b = sb.Batch(flats)
 b.upload(); b.run(); b.download()   # warm-up (same inputs: the batch keeps the packed image)
 if world > 1:
@@ -82,6 +84,12 @@ if rank == 0:
                 n_gpus=world, ms=ms, lm_trials=tot, lm_iterations_per_s=tot / (ms * 1e-3), areas_per_s=n_areas / (ms * 1e-3),
                 rank0=dict(areas=b.n, trials_mean=trials / b.n, trials_max=max(s["num_trials"] for s in st), err_init=e0, err_final=e1,
                            rmse_median=float(np.median([s["obs_rmse"] for s in st])), h2d_bytes=int(b.h2d_bytes), d2h_bytes=int(b.d2h_bytes)))
+    import bench as B   # SURVEY 8(d) unique-touch byte model, evaluated on this rank's exact counts and trial counts
+    ab = B.algorithmic_bytes(flats, st)
+    peak, peak_src = B.measured_peaks()
+    line["roofline_rank0"] = dict(bound="hbm", algorithmic_bytes=ab["total_bytes"], achieved_gbs=ab["total_bytes"] / (ms * 1e-3) / 1e9, peak_gbs=peak,
+                                  frac=ab["total_bytes"] / (ms * 1e-3) / 1e9 / peak, peak_source=peak_src,
+                                  stage_bytes={k: ab[k] for k in ("chain", "assem_res", "assem_jh", "schur", "chol")}, chol_flop=ab["chol_flop"])
     print(json.dumps(line))
     if a.cpu_areas:
         from oracle import pyoracle as po
