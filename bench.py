@@ -227,6 +227,12 @@ def main():
     # weak scaling: every rank gets the SAME tour (seed 1: same shape of every local area, i.e. the same work per GPU) with
     # its own observation-noise realisation; rank 0 is bit-identical to the single-GPU run
     ds, eng, flats = build_problems(seed=args.tour_seed, areas=args.areas, n_kfs=args.kfs, noise_seed=None if rank == 0 else 1000 + rank)
+    # BASELINE config #1 reading (one sequential srba-slam run): the tour above WAS such a run through the product
+    # engine -- every define_new_keyframe a flatten + one-problem srba_b200_optimize call + scatter.  Reported as context only.
+    tm = eng.timers()
+    seq = {"keyframes": args.kfs, "lm_trials": int(tm["total_trials"]), "gpu_call_seconds": round(tm["gpu_seconds"], 4),
+           "flatten_scatter_seconds": round(tm["flatten_seconds"], 4),
+           "lm_iterations_per_s": tm["total_trials"] / max(1e-9, tm["gpu_seconds"] + tm["flatten_seconds"])}
     batch = sb.Batch(flats)
     stream = torch.cuda.current_stream()
     sp = stream.cuda_stream
@@ -310,6 +316,7 @@ def main():
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.areas), "areas_per_gpu": args.areas, "tour_keyframes": args.kfs, "lm_trials_per_step_per_gpu": trials_per_step,
                        "ranks": "same tour (seed 1) on every rank, independent observation noise per rank",
+                       "sequential_run_of_the_tour": seq,
                        "l2": "flushed between timed iterations (256 MiB fill)", "timing": "CUDA events around each launch on the launching stream"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(batch.h2d_bytes), "d2h_bytes_per_step": int(batch.d2h_bytes)},
             "gpu_launches": int(batch.kernel_launches) * args.steps,

@@ -581,8 +581,36 @@ __device__ __forceinline__ double jtj_elem(const DevProblem *h, const double *J1
 	return s;
 }
 
-// K2b: sparse_hessian_update_numeric x3 (impl/sparse_hessian_update_numeric.h:22-60): one thread per block element,
-// terms in ascending observation order, invalid rows skipped, identity noise scaled by 1/sigma afterwards.
+// One ROW of a J1^t Lambda J2 term: term[b] = sum_k c_k J2[k][b] with c = column a of J1 (times Lambda); the same products in
+// the same order as jtj_elem, with the J1 column loaded once for the M2 outputs.
+template <int O, int M2>
+__device__ __forceinline__ void jtj_row(const DevProblem *h, const double *J1, int m1, int a, const double *J2, double *term) {
+	double c[O];
+	if (h->model.noise_kind == SRBA_NOISE_IDENTITY) {
+#pragma unroll
+		for (int k = 0; k < O; k++) c[k] = J1[k * m1 + a];
+	} else {
+#pragma unroll
+		for (int k = 0; k < O; k++) {
+			double t = 0;
+#pragma unroll
+			for (int l = 0; l < O; l++) t += J1[l * m1 + a] * h->model.noise_lambda[l * O + k];
+			c[k] = t;
+		}
+	}
+#pragma unroll
+	for (int b = 0; b < M2; b++) {
+		double s2 = 0;
+#pragma unroll
+		for (int k = 0; k < O; k++) s2 += c[k] * J2[k * M2 + b];
+		term[b] = s2;
+	}
+}
+
+// K2b: sparse_hessian_update_numeric x3 (impl/sparse_hessian_update_numeric.h:22-60): terms in ascending observation order,
+// invalid rows skipped, identity noise scaled by 1/sigma afterwards.  SE(2): one thread per block element (everything on chip);
+// SE(3): one thread per block ROW -- the landmark areas are load-bound (J lives in L2), and a row shares the J1 column and the
+// index / validity loads between its 6 (or 3) outputs: 2.4x fewer load instructions for the same sums in the same order.
 template <int P, int OBSK>
 __device__ __noinline__ void stage_hessian(const View &vs) {
 	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
@@ -590,6 +618,56 @@ __device__ __noinline__ void stage_hessian(const View &vs) {
 	const DevProblem *h = v.h;
 	const double scale = (h->model.noise_kind == SRBA_NOISE_IDENTITY) ? 1.0 / h->model.noise_std : 1.0;
 	const bool do_scale = (h->model.noise_kind == SRBA_NOISE_IDENTITY);
+	if constexpr (P == 6) {
+		const int nApR = h->n_HAp * 6, nApfR = h->n_HApf * 6, nfR = h->n_unk_lms * 3;
+		for (int it = LM_TID; it < nApR + nApfR + nfR; it += LM_THREADS) {
+			if (it < nApR) {
+				const int blk = it / 6, a = it % 6;
+				double s[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll 2
+				for (int t = v.HAp_term_ptr[blk]; t < v.HAp_term_ptr[blk + 1]; t++) {
+					const int ba = v.HAp_term_a[t], bb = v.HAp_term_b[t];
+					double term[6];
+					jtj_row<O, 6>(h, v.JA + (size_t)ba * O * 6, 6, a, v.JA + (size_t)bb * O * 6, term);
+					const bool on = v.valid[v.blkA_obs[ba]];
+#pragma unroll
+					for (int b = 0; b < 6; b++) s[b] += on ? term[b] : 0.0;
+				}
+#pragma unroll
+				for (int b = 0; b < 6; b++) v.HAp[(size_t)it * 6 + b] = do_scale ? s[b] * scale : s[b];
+			} else if (it < nApR + nApfR) {
+				const int j = it - nApR;
+				const int blk = j / 6, a = j % 6;
+				double s[3] = {0, 0, 0};
+#pragma unroll 2
+				for (int t = v.HApf_term_ptr[blk]; t < v.HApf_term_ptr[blk + 1]; t++) {
+					const int ba = v.HApf_term_a[t], bf = v.HApf_term_f[t];
+					double term[3];
+					jtj_row<O, 3>(h, v.JA + (size_t)ba * O * 6, 6, a, v.JF + (size_t)bf * O * 3, term);
+					const bool on = v.valid[v.blkA_obs[ba]];
+#pragma unroll
+					for (int b = 0; b < 3; b++) s[b] += on ? term[b] : 0.0;
+				}
+#pragma unroll
+				for (int b = 0; b < 3; b++) v.HApf[(size_t)j * 3 + b] = do_scale ? s[b] * scale : s[b];
+			} else {
+				const int j = it - nApR - nApfR;
+				const int k = j / 3, a = j % 3;
+				double s[3] = {0, 0, 0};
+#pragma unroll 2
+				for (int bf = v.colF_ptr[k]; bf < v.colF_ptr[k + 1]; bf++) {
+					double term[3];
+					jtj_row<O, 3>(h, v.JF + (size_t)bf * O * 3, 3, a, v.JF + (size_t)bf * O * 3, term);
+					const bool on = v.valid[v.blkF_obs[bf]];
+#pragma unroll
+					for (int b = 0; b < 3; b++) s[b] += on ? term[b] : 0.0;
+				}
+#pragma unroll
+				for (int b = 0; b < 3; b++) v.Hf[(size_t)j * 3 + b] = do_scale ? s[b] * scale : s[b];
+			}
+		}
+		return;
+	}
 	const int nAp = h->n_HAp * P * P, nApf = h->n_HApf * P * 3, nf = h->n_unk_lms * 9;
 	for (int it = LM_TID; it < nAp + nApf + nf; it += LM_THREADS) {
 		if (it < nAp) {
@@ -840,7 +918,48 @@ __device__ __noinline__ void stage_schur(const View &vs, double lambda) {
 		v.W[it] = Hb[a * 3 + 0] * inv[0 * 3 + b] + Hb[a * 3 + 1] * inv[1 * 3 + b] + Hb[a * 3 + 2] * inv[2 * 3 + b];
 	}
 	LM_BARRIER();
-	// (3) reduced blocks; (4) reduced gradient
+	// (3) reduced blocks; (4) reduced gradient.  SE(3): one thread per block ROW (W row loaded once for the 6 outputs, index and
+	// invertibility loads shared) -- same sums, same order, 2.4x fewer load instructions in the stage that dominates landmark areas
+	if constexpr (P == 6) {
+		const int nSR = h->s_alias_hap ? 0 : h->n_S * 6;
+		for (int it = LM_TID; it < nSR + n; it += LM_THREADS) {
+			if (it < nSR) {
+				const int blk = it / 6, a = it % 6;
+				const int hb = v.S_HAp[blk];
+				double s[6];
+#pragma unroll
+				for (int b = 0; b < 6; b++) s[b] = hb >= 0 ? v.HAp[(size_t)hb * 36 + a * 6 + b] : 0.0;
+#pragma unroll 2
+				for (int t = v.S_term_ptr[blk]; t < v.S_term_ptr[blk + 1]; t++) {
+					const int rb = v.S_term_rowblk[t], cb = v.S_term_colblk[t];
+					const double *Wr = v.W + (size_t)rb * 18 + a * 3;
+					const double *Hc = v.HApf + (size_t)cb * 18;
+					const double w0 = Wr[0], w1 = Wr[1], w2 = Wr[2];
+					const bool on = v.lm_inv[v.HApf_col[rb]];  // non-invertible landmarks are skipped (schur.h:228): exact -0.0
+#pragma unroll
+					for (int b = 0; b < 6; b++) {
+						const double term = w0 * Hc[b * 3 + 0] + w1 * Hc[b * 3 + 1] + w2 * Hc[b * 3 + 2];
+						s[b] -= on ? term : 0.0;
+					}
+				}
+#pragma unroll
+				for (int b = 0; b < 6; b++) v.Sblk[(size_t)it * 6 + b] = s[b];
+			} else {
+				const int i = it - nSR;  // scalar of the pose part
+				const int ucol = i / 6, a = i % 6;
+				double g = v.grad[i];
+				for (int blk = v.rowApf_ptr[ucol]; blk < v.rowApf_ptr[ucol + 1]; blk++) {
+					const int k = v.HApf_col[blk];
+					if (!v.lm_inv[k]) continue;
+					const double *Wr = v.W + (size_t)blk * 18;
+					const double *gf = v.grad + n + (size_t)k * 3;
+					g -= Wr[a * 3 + 0] * gf[0] + Wr[a * 3 + 1] * gf[1] + Wr[a * 3 + 2] * gf[2];
+				}
+				v.grad[i] = g;
+			}
+		}
+		return;
+	}
 	const int nS = h->s_alias_hap ? 0 : h->n_S * P * P;
 	for (int it = LM_TID; it < nS + n; it += LM_THREADS) {
 		if (it < nS) {
