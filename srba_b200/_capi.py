@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libsrba_b200.so")
+SO_PATH = os.environ.get("SRBA_B200_LIB") or os.path.join(_HERE, "libsrba_b200.so")   # SRBA_B200_LIB: an experiment build (srba_b200/build.py)
 
 POSE_SE2, POSE_SE3 = 0, 1
 OBS_RELPOSES2D, OBS_CARTESIAN3D, OBS_MONO, OBS_STEREO = 0, 1, 2, 3

@@ -26,9 +26,11 @@ def build(force=False, verbose=False):
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = ["-DSRBA_SOLVER_TIMERS"] if os.environ.get("SRBA_SOLVER_TIMERS") else []   # per-phase clocks inside the solver (tools/stage_breakdown.py)
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + [os.path.join(CSRC, f) for f in SOURCES]
+    extra += os.environ.get("SRBA_B200_NVCC_EXTRA", "").split()   # experiment builds, e.g. "-DSE3_NT=512" (with SRBA_B200_LIB=<other .so> as the output)
+    out = os.environ.get("SRBA_B200_LIB", SO)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + [os.path.join(CSRC, f) for f in SOURCES]
     subprocess.check_call(cmd, cwd=CSRC)
-    return SO
+    return out
 
 
 if __name__ == "__main__":

@@ -1888,7 +1888,9 @@ __global__ void __launch_bounds__(NT, MINB) srba_lm_batch_kernel(const char *img
 //   Models 4..7 are the CLUSTER variants of 0..3 (lm_kernel_cluster.cu): 8 CTAs x 256 threads per problem, every mutable
 //   array in the global workspace, only the solver's pivot scratch on chip.
 #define SE2_NT 192
+#ifndef SE3_NT   /* compile-time experiment hook: threads per CTA of the SE(3) kernels (registers per thread = 65536 / SE3_NT) */
 #define SE3_NT 1024
+#endif
 #define SE2_TPT 2
 #define SE3_TPT 4
 extern "C" SrbaKernelCfg srba_kernel_cfg(int model) {
