@@ -680,7 +680,7 @@ struct Pool {
 	uint64_t h_img_cap = 0, h_res_cap = 0, d_img_cap = 0, d_ws_cap = 0, d_res_cap = 0;
 	cudaStream_t stream = nullptr;
 };
-#define SRBA_MAX_CHUNKS 4
+#define SRBA_MAX_CHUNKS 8
 static thread_local Pool g_pool[SRBA_MAX_CHUNKS];  // one buffer set per pipelined chunk of a batch call
 
 static bool pool_reserve_host(char **p, uint64_t *cap, uint64_t need) {
@@ -1015,11 +1015,15 @@ int srba_b200_optimize_batch(int32_t n, const srba_problem_t *const *in, srba_re
 	// A large batch is cut into up to SRBA_MAX_CHUNKS chunks, each with its own stream and buffers: while chunk c is copied
 	// and solved, chunk c+1 is being packed on the host cores, and results come back chunk by chunk.  All chunks fit the
 	// GPU together (2 CTAs/SM), so the kernels overlap; only the first pack and the last copy-back stay exposed.
-	const int K = n >= 64 ? SRBA_MAX_CHUNKS : 1;
+	static const int k_chunks = [] {  // SRBA_B200_CHUNKS=1..8 overrides the default of 4 pipelined chunks
+		const char *e = std::getenv("SRBA_B200_CHUNKS");
+		return e ? std::max(1, std::min(std::atoi(e), SRBA_MAX_CHUNKS)) : 4;
+	}();
+	const int K = n >= 64 ? k_chunks : 1;
 	int n_heavy = 0;
 	for (int i = 0; i < n; i++) n_heavy += (in[i] && heavy_problem(*in[i])) ? 1 : 0;
 	const int allow_cluster = clusters_pay(n_heavy) ? 1 : 0;
-	srba_batch_t *bt[SRBA_MAX_CHUNKS] = {nullptr, nullptr, nullptr, nullptr};
+	srba_batch_t *bt[SRBA_MAX_CHUNKS] = {};
 	int begin[SRBA_MAX_CHUNKS + 1];
 	for (int c = 0; c <= K; c++) begin[c] = (int)((int64_t)n * c / K);
 	int rc = SRBA_OK;

@@ -362,6 +362,51 @@ def test_batch_matches_single_and_is_repeatable():
     assert b.kernel_launches >= 1 and b.h2d_bytes > 0 and b.d2h_bytes > 0
 
 
+def test_ragged_mixed_model_batch_matches_single_calls():
+    """Ragged batch: SE(2) graph-SLAM areas, SE(3) Cartesian3D / stereo landmark areas of very different sizes (3 .. ~60 unknown
+    edges, 0 .. ~300 landmarks), all three solver tags, shuffled into ONE srba_b200_optimize_batch call (the launcher groups them by
+    kernel): every result bit-identical to the one-problem call."""
+    import ctypes as C
+    from srba_b200 import _capi as K
+    flats = []
+    ds = D.graphslam_se2_tour(90, seed=5)
+    ep = sb.RbaEngine(sb.default_engine_params(**dict(S2, noise_lambda=D.se2_noise_lambda(ds["sigma_xy"], ds["sigma_yaw"]))))
+    ep.record_problems(True)
+    for f in ds["frames"]:
+        D.feed(ep, f)
+    flats += [f for f in ep.take_recorded() if f.p.n_unk_edges >= 1][5::9]
+    keep = [ep]
+    for name, kind, solver in (("cartesian3d", 1, 0), ("stereo", 3, 2), ("cartesian3d", 1, 1)):
+        d3 = D.landmark_slam_se3(n_kfs=22, n_lms=200, seed=3 + solver, obs_kind=name)
+        kw = dict(pose_kind=1, obs_kind=kind, noise_kind=0, noise_std=1e-3 if kind == 1 else 0.5, max_tree_depth=3, max_optimize_depth=3, submap_size=10,
+                  min_obs_to_loop_closure=4, solver_kind=solver)
+        if kind != 1:
+            kw.update(sensor_pose_kind=1, sensor_pose=d3["sensor_pose_xyzypr"], cam_left=d3["cam"], cam_right=d3["cam"],
+                      right_cam_pose=[d3["baseline"], 0, 0, 1, 0, 0, 0], use_robust_kernel=1)
+        e3 = sb.RbaEngine(sb.default_engine_params(**kw))
+        e3.record_problems(True)
+        for f in d3["frames"]:
+            D.feed(e3, f)
+        flats += e3.take_recorded()[3::5]
+        keep.append(e3)
+    rng = np.random.default_rng(0)
+    flats = [flats[i] for i in rng.permutation(len(flats))]
+    kinds = {(f.p.model.pose_kind, f.p.model.obs_kind, f.p.model.solver_kind) for f in flats}
+    assert len(kinds) >= 4 and len(flats) >= 12
+    sizes = sorted(f.p.n_unk_edges for f in flats)
+    singles = [sb.optimize(f) for f in flats]
+    n = len(flats)
+    parr = (C.POINTER(K.Problem) * n)(*[f.problem for f in flats])
+    bufs = [sb.ResultBuffers(f.p) for f in flats]
+    rarr = (C.POINTER(K.Result) * n)(*[C.pointer(x.r) for x in bufs])
+    assert K.lib().srba_b200_optimize_batch(n, parr, rarr) == 0
+    for s_, x in zip(singles, bufs):
+        assert x.r.stats.as_dict() == s_.stats
+        assert np.array_equal(x.edge_pose, s_.edge_pose) and np.array_equal(x.lm_pos, s_.lm_pos) and np.array_equal(x.slot_pose, s_.slot_pose)
+        assert np.array_equal(x.obs_valid, s_.obs_valid)
+    print("ragged batch: %d problems, %d model/solver kinds, n_p %d..%d" % (n, len(kinds), sizes[0], sizes[-1]))
+
+
 def test_blocked_fallback_and_cluster_team_match_the_default_path():
     """Three ways to run the same LM program: the default (one CTA per area, on-chip block-sparse L D L^t), the dense blocked
     Cholesky used when the tiles do not fit (SRBA_B200_SOLVER=blocked), and an 8-CTA thread-block cluster per area with

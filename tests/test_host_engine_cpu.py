@@ -151,6 +151,17 @@ def test_symbols_and_no_device_error():
     L = K.lib()
     for s in K.EXPORTED_SYMBOLS:
         assert hasattr(L, s), s
+    # every function the two public headers declare is exported (and bound in _capi.EXPORTED_SYMBOLS), nothing else is listed
+    import os, re
+    declared = set()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for h in ("include/srba_b200.h", "include/srba_b200_engine.h"):
+        txt = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, h)).read(), flags=re.S)
+        declared |= set(re.findall(r"\b(srba_(?:b200|engine|flat)_[a-z0-9_]+)\s*\(", txt))
+    assert len(declared) >= 60
+    assert declared == set(K.EXPORTED_SYMBOLS), (sorted(declared - set(K.EXPORTED_SYMBOLS)), sorted(set(K.EXPORTED_SYMBOLS) - declared))
+    for s in declared:
+        assert hasattr(L, s), s
     if L.srba_b200_device_count() > 0:
         pytest.skip("a CUDA device is present")
     ds = D.graphslam_se2_tour(12, seed=1)
