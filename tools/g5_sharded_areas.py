@@ -63,8 +63,7 @@ import torch
 import torch.distributed as dist
 torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
 if world > 1:
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))))
 b = sb.Batch(flats)
 b.upload(); b.run(); b.download()   # warm-up (same inputs: the batch keeps the packed image)
