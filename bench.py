@@ -220,7 +220,11 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL prints its version banner / warnings on STDOUT: keep stdout to the one JSON line
+        # NCCL prints its version banner on STDOUT when NCCL_DEBUG (env or nccl.conf) is VERSION, and honours NCCL_DEBUG_FILE only above
+        # that level: raise VERSION/unset to WARN and send everything to stderr, so that stdout stays the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     # weak scaling: every rank gets the SAME tour (seed 1: same shape of every local area, i.e. the same work per GPU) with

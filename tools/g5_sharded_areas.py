@@ -63,6 +63,10 @@ import torch
 import torch.distributed as dist
 torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
 if world > 1:
+    # NCCL prints its version banner on STDOUT when NCCL_DEBUG (env or nccl.conf) is VERSION, and honours NCCL_DEBUG_FILE only above
+    # that level: raise VERSION/unset to WARN and send everything to stderr, so that stdout stays the one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))))
 b = sb.Batch(flats)
