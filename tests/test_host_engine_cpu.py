@@ -217,3 +217,53 @@ def test_complete_spanning_tree_bfs_reaches_the_same_keyframes_as_the_oracle():
     if K.lib().srba_b200_device_count() == 0:
         with pytest.raises(RuntimeError, match="no CUDA device"):
             ep.eval_overall_squared_error()
+
+
+def test_eval_overall_c_abi_validates_its_arguments():
+    """srba_b200_eval_overall_squared_error (include/srba_b200.h): malformed inputs are rejected on the host before any device work
+    (error codes instead of the reference's ASSERT_ exceptions, impl/eval_overall_error.h:106-110); a well-formed call without a
+    device reports SRBA_ERR_NO_DEVICE (no CPU fallback)."""
+    import ctypes as C
+    from srba_b200 import _capi as K
+    L = K.lib()
+
+    class EvalProblem(C.Structure):
+        _fields_ = [("model", K.Model), ("n_edges", C.c_int32), ("n_pairs", C.c_int32), ("n_path", C.c_int32), ("n_obs", C.c_int32), ("n_lms", C.c_int32),
+                    ("reserved_", C.c_int32), ("edge_pose", C.POINTER(C.c_double)), ("pair_path_ptr", C.POINTER(C.c_int32)), ("path_edge", C.POINTER(C.c_int32)),
+                    ("path_dir", C.POINTER(C.c_uint8)), ("obs_z", C.POINTER(C.c_double)), ("obs_pair", C.POINTER(C.c_int32)), ("obs_inverse", C.POINTER(C.c_uint8)),
+                    ("obs_lm", C.POINTER(C.c_int32)), ("lm_pos", C.POINTER(C.c_double))]
+
+    L.srba_b200_eval_overall_squared_error.restype = C.c_int
+    L.srba_b200_eval_overall_squared_error.argtypes = [C.POINTER(EvalProblem), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    edge = np.array([[1.0, 0.0, 0.1], [0.5, 0.2, -0.3]])
+    ptr_ = np.array([0, 2], np.int32)
+    pe, pd = np.array([0, 1], np.int32), np.array([1, 0], np.uint8)
+    z = np.array([[1.4, 0.3, -0.2], [0.0, 0.0, 0.0]])
+    op, oi = np.array([0, -1], np.int32), np.array([0, 0], np.uint8)
+
+    def problem(**over):
+        q = EvalProblem()
+        q.model.pose_kind, q.model.obs_kind = K.POSE_SE2, K.OBS_RELPOSES2D
+        q.n_edges, q.n_pairs, q.n_path, q.n_obs, q.n_lms = 2, 1, 2, 2, 0
+        q.edge_pose = edge.ctypes.data_as(C.POINTER(C.c_double)); q.pair_path_ptr = ptr_.ctypes.data_as(C.POINTER(C.c_int32))
+        q.path_edge = pe.ctypes.data_as(C.POINTER(C.c_int32)); q.path_dir = pd.ctypes.data_as(C.POINTER(C.c_uint8))
+        q.obs_z = z.ctypes.data_as(C.POINTER(C.c_double)); q.obs_pair = op.ctypes.data_as(C.POINTER(C.c_int32)); q.obs_inverse = oi.ctypes.data_as(C.POINTER(C.c_uint8))
+        for k, v in over.items():
+            setattr(q, k, v)
+        return q
+
+    out = C.c_double()
+    assert L.srba_b200_eval_overall_squared_error(None, C.byref(out), None) == K.ERR_BAD_ARGUMENT
+    assert L.srba_b200_eval_overall_squared_error(C.byref(problem(n_path=-1)), C.byref(out), None) == K.ERR_BAD_ARGUMENT
+    bad_edge = np.array([0, 7], np.int32)
+    assert L.srba_b200_eval_overall_squared_error(C.byref(problem(path_edge=bad_edge.ctypes.data_as(C.POINTER(C.c_int32)))), C.byref(out), None) == K.ERR_BAD_ARGUMENT
+    bad_pair = np.array([3, -1], np.int32)
+    assert L.srba_b200_eval_overall_squared_error(C.byref(problem(obs_pair=bad_pair.ctypes.data_as(C.POINTER(C.c_int32)))), C.byref(out), None) == K.ERR_BAD_ARGUMENT
+    q = problem()
+    q.model.obs_kind = K.OBS_STEREO   # SE2 is built with RelativePoses_2D only
+    assert L.srba_b200_eval_overall_squared_error(C.byref(q), C.byref(out), None) == K.ERR_UNSUPPORTED_MODEL
+    rc = L.srba_b200_eval_overall_squared_error(C.byref(problem()), C.byref(out), None)
+    if L.srba_b200_device_count() == 0:
+        assert rc == K.ERR_NO_DEVICE and b"no CUDA device" in L.srba_b200_last_error()
+    else:
+        assert rc == 0 and out.value > 0
