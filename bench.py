@@ -1,21 +1,27 @@
 #!/usr/bin/env python
 """bench.py — LM iterations/sec of the SRBA local-area optimiser (BASELINE.json metric) on B200.
 
-Workload (config.workload): G4 of SURVEY.md §8(d) — a batch of independent SE(2) relative graph-SLAM local-area
-problems (submap 10, depth 3), each one the exact optimize_local_area() input of one keyframe of a world-2d-30k-like
-tour, snapshotted from a sequential run of the product engine.  One STEP = one pass of the hot path over the whole batch
-(every problem runs its full Levenberg–Marquardt loop: Jacobians + Hessian + Schur + Cholesky + update per trial).
-One LM iteration = one solve(lambda) trial (impl/optimize_edges.h:471-476), accepted or rejected.
+Workload (config.workload): G4 of SURVEY.md §8(d) on the G1 dataset shape — a batch of independent SE(2) relative graph-SLAM
+local-area problems (submap 10, depth 3), each one the exact optimize_local_area() input of one keyframe of a
+world-2d-30k-like tour of 3 000 keyframes, snapshotted from a sequential run of the product engine.  The areas are
+sampled EVENLY OVER THE WHOLE TOUR, i.e. with the revisits and loop closures a 6 km tour of a 3x3 grid of 100 m blocks
+produces (n_p up to ~250 unknown edges; the distribution is printed in config.area_sizes).
+One STEP = one pass of the hot path over the whole batch (every problem runs its full Levenberg–Marquardt loop:
+Jacobians + Hessian + Schur + Cholesky + update per trial).  One LM iteration = one solve(lambda) trial
+(impl/optimize_edges.h:471-476), accepted or rejected.
 
-  value : whole-job LM iterations/sec with the packed inputs already resident in HBM (CUDA events around each launch)
+  value : whole-job LM iterations/sec with the packed inputs already resident in HBM (CUDA events around each step)
   e2e   : the same through srba_b200_optimize_batch() with HOST buffers (pack + H2D + kernel + D2H + unpack in the timed region)
   roofline / cpu_baseline / clocks : see DESIGN.md §Measurement
-Usage: python bench.py --gpus N --steps K --warmup W [--impl reference]
+  config.chain_like_case   : the round-1 workload (last 256 keyframes of a 700-keyframe tour: chain-like areas, n_p ~ 27)
+  config.areas_sweep       : throughput at 1 024 / 4 096 areas per GPU (N=1 only)
+  config.strong_scaling_256_areas_total : BASELINE config #4 read literally (256 areas IN TOTAL over the N ranks)
+Other BASELINE configs: `--config 2|3|5` (SE(3) mono / stereo whole-map single area, SE(3) Cartesian3D sharded depth-5 areas).
+Usage: python bench.py --gpus N --steps K --warmup W [--impl reference] [--config 4]
 """
 import argparse
 import ctypes as C
 import json
-import math
 import os
 import subprocess
 import sys
@@ -31,11 +37,12 @@ METRIC = "LM iterations/sec (Jacobian+Hessian+Schur solve) on 30k-LM local area"
 UNIT = "LM iterations/s"
 TOUR_PARAMS = dict(max_tree_depth=3, max_optimize_depth=3, submap_size=10, min_obs_to_loop_closure=1, max_error_per_obs_to_stop=1e-8,
                    pose_kind=0, obs_kind=0, noise_kind=1)
+FIXTURE = os.path.join(ROOT, "tests", "golden", "g4_tour3000_states.npz")
 
 
-def workload_name(areas):
-    return ("G4: %d independent SE2 relative graph-SLAM local areas (world-2d-30k-like tour, submap 10, depth 3), each the "
-            "optimize_local_area() input of one keyframe" % areas)
+def workload_name(areas, kfs):
+    return ("G4: %d independent SE2 relative graph-SLAM local areas sampled evenly over a %d-keyframe world-2d-30k-like tour (G1: submap 10, "
+            "depth 3, revisits and loop closures included), each the optimize_local_area() input of one keyframe" % (areas, kfs))
 
 
 def engine_kwargs(ds):
@@ -51,28 +58,56 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ldl_counts(flat):
+    """(tiles, updates) of the block-sparse L D L^t schedule the packer ships with this problem (host symbolic factorisation)."""
+    from srba_b200 import _capi as K
+    cnt = (C.c_int64 * 4)()
+    K.lib().srba_b200_problem_ldl_counts(flat.problem, cnt)
+    return int(cnt[0]), int(cnt[1])
+
+
 def algorithmic_bytes(flats, stats):
-    """SURVEY.md §8(d) unique-touch model, per launch: every trial pays chain + residual half of assembly + Schur + Cholesky
-    bytes; the Jacobian/Hessian half of the assembly is paid once at start and once per relinearisation."""
-    tot = dict(chain=0.0, assem_res=0.0, assem_jh=0.0, schur=0.0, chol=0.0, chol_flop=0.0)
+    """Unique-touch byte model of SURVEY.md §8(d), per launch, charging only what a trial really touches: the pose pairs
+    that hold a listed pose (update_numeric(set,true), not all pairs), the tiles of the filled block-sparse pattern (not a
+    dense n^2 system), no Schur stage when there are no landmark unknowns; the Jacobian/Hessian half of the assembly is paid
+    once at the start and once per relinearisation, incl. the materialised Jacobians (written, re-read: B_jacmat)."""
+    tot = dict(chain=0.0, assem_res=0.0, assem_jh=0.0, jacmat=0.0, schur=0.0, solve=0.0, update=0.0, dense_equiv_chol=0.0, chol_flop=0.0, solve_flop=0.0)
     for f, st in zip(flats, stats):
         p = f.p
         P = 3 if p.model.pose_kind == 0 else 6
         S = 24 if P == 3 else 96
         o = {0: 3, 1: 3, 2: 2, 3: 4}[p.model.obs_kind]
-        NT, trials, relin = p.n_pairs, st["num_trials"], st["num_relinearized"]
-        b_chain = NT * 4 + p.n_path * 5 + p.n_edges * S + 2 * NT * S
-        b_res = p.n_obs * (o * 8 + 8) + 2 * NT * S + p.n_lms * 24 + p.n_obs * (o * 8 + 1)
-        b_jh = p.n_blkA * 20 + p.n_blkF * 8 + (p.n_HAp * P * P + p.n_HApf * P * 3 + p.n_unk_lms * 9) * 8 + (p.n_unk_edges * P + p.n_unk_lms * 3) * 8
-        b_schur = (p.n_HApf * P * 3 + 2 * p.n_unk_lms * 9 + p.n_HAp * P * P) * 8 + 2 * p.n_S * P * P * 8 + (p.n_unk_edges * P + p.n_unk_lms * 3) * 16
+        trials, relin = st["num_trials"], st["num_relinearized"]
+        sa, sd = f.array("blkA_slotA", p.n_blkA, np.int64), f.array("blkA_slotD", p.n_blkA, np.int64)
+        sf = f.array("blkF_slot", p.n_blkF, np.int64) if p.n_blkF else np.zeros(0, np.int64)
+        listed = np.unique(np.concatenate([sa[sa >= 0], sd, sf[sf >= 0]]))
+        refresh = np.unique(listed // 2)
+        ptr = f.array("pair_path_ptr", p.n_pairs + 1, np.int64)
+        plen = np.diff(ptr)
+        osl = f.array("obs_slot", p.n_obs, np.int64)
+        n_obs_slots = len(np.unique(osl[osl >= 0]))
+        tiles, updates = ldl_counts(f)
+        nsc = p.n_unk_edges * P + p.n_unk_lms * 3
+        b_chain_all = p.n_pairs * 4 + p.n_path * 5 + p.n_edges * S + 2 * p.n_pairs * S
+        b_chain_trial = len(refresh) * 4 + int(plen[refresh].sum()) * 5 + p.n_edges * S + 2 * len(refresh) * S
+        b_res = p.n_obs * (o * 8 + 8) + n_obs_slots * S + (p.n_lms * 24 if P == 6 else 0) + p.n_obs * (o * 8 + 1)
+        b_jh = p.n_blkA * 20 + p.n_blkF * 8 + len(listed) * S + (p.n_HAp * P * P + p.n_HApf * P * 3 + p.n_unk_lms * 9) * 8 + nsc * 8
+        b_jm = 2 * (p.n_blkA * o * P + p.n_blkF * o * 3) * 8
+        b_schur = 0 if p.n_unk_lms == 0 else ((p.n_HApf * P * 3 + 2 * p.n_unk_lms * 9 + p.n_HAp * P * P) * 8 + 2 * p.n_S * P * P * 8 + nsc * 16)
+        b_solve = 2 * tiles * 72 + 2 * P * p.n_unk_edges * 8
+        b_upd = 3 * p.n_unk_edges * S + 2 * len(listed) * S + 3 * p.n_unk_lms * 24
         n = P * p.n_unk_edges
-        tot["chain"] += b_chain * (trials + 1)
+        tot["chain"] += b_chain_all + b_chain_trial * trials
         tot["assem_res"] += b_res * (trials + 1)
         tot["assem_jh"] += b_jh * (relin + 1)
+        tot["jacmat"] += b_jm * (relin + 1)
         tot["schur"] += b_schur * trials
-        tot["chol"] += n * n * 8.0 * trials
+        tot["solve"] += b_solve * trials
+        tot["update"] += b_upd * trials
+        tot["dense_equiv_chol"] += n * n * 8.0 * trials
         tot["chol_flop"] += (n ** 3 / 3.0 + 2 * n * n) * trials
-    tot["total_bytes"] = tot["chain"] + tot["assem_res"] + tot["assem_jh"] + tot["schur"] + tot["chol"]
+        tot["solve_flop"] += (updates * 81.0 + tiles * 27.0) * trials   # 27 FMA per tile update + 27 for W on the fly, 27 per W tile
+    tot["total_bytes"] = sum(tot[k] for k in ("chain", "assem_res", "assem_jh", "jacmat", "schur", "solve", "update"))
     return tot
 
 
@@ -118,75 +153,172 @@ class ClockSampler:
         return out
 
 
-def build_problems(seed, areas, n_kfs, noise_seed=None):
-    """Sequential product-engine run over the tour; returns the flattened local-area problem of the last `areas` keyframes."""
+def build_problems(seed, areas, n_kfs, noise_seed=None, last=False, extra_samples=()):
+    """Sequential product-engine run over the tour (every define_new_keyframe a flatten + one-problem GPU call + scatter);
+    returns the flattened local-area problems of `areas` keyframes sampled evenly over the whole tour (last=True: the last
+    `areas` keyframes, the chain-like round-1 workload).  extra_samples: further batch sizes to sample (areas sweep)."""
     import srba_b200 as sb
     from srba_b200 import datasets as D
     ds = D.graphslam_se2_tour(n_kfs, seed=seed, noise_seed=noise_seed)
     eng = sb.RbaEngine(sb.default_engine_params(**engine_kwargs(ds)))
-    flats = []
-    first = n_kfs - areas
+    picks = {areas: (np.arange(n_kfs - areas, n_kfs) if last else D.sample_keyframes(n_kfs, areas))}
+    for a in extra_samples:
+        picks[a] = D.sample_keyframes(n_kfs, a)
+    wanted = set(int(k) for v in picks.values() for k in v)
+    by_kf = {}
     for k, f in enumerate(ds["frames"]):
-        if k >= first:
+        if k in wanted:
             eng.record_problems(True)
         D.feed(eng, f)
-        if k >= first:
+        if k in wanted:
             rec = eng.take_recorded()
             eng.record_problems(False)
             assert rec, "keyframe %d produced no optimisation problem" % k
-            flats.append(rec[-1])   # the last optimize_edges call of define_new_keyframe is the local area (define_new_keyframe.h:97)
-    return ds, eng, flats
+            by_kf[k] = rec[-1]   # the last optimize_edges call of define_new_keyframe is the local area (define_new_keyframe.h:97)
+    sets = {a: [by_kf[int(k)] for k in v] for a, v in picks.items()}
+    return ds, eng, sets
+
+
+# ---------------------------------------------------------------------------------------------------------- CPU legs (oracle)
+def cpu_fixture_worker(args):
+    """Oracle on a share of the fixture's areas: the graph is rebuilt from the tour's frames (no optimisation), at each of this
+    worker's keyframes the touched edges get the stored pre-optimisation poses and optimize_local_area(k, 3) -- the problem of
+    the batch -- is timed ('opt' span, impl/optimize_edges.h:56,786), `reps` times from the same inputs.
+    Returns per repetition (seconds, LM trials)."""
+    mine, reps = args
+    from oracle import pyoracle as po
+    from srba_b200 import datasets as D
+    fx = np.load(FIXTURE)
+    ds = D.graphslam_se2_tour(int(fx["kfs"]), seed=int(fx["seed"]))
+    e = po.OracleEngine(po.default_params(**engine_kwargs(ds)))
+    at = {int(fx["kf"][i]): i for i in mine}
+    last = max(at) if at else -1
+    sec, tr = np.zeros(reps), np.zeros(reps)
+    for k, f in enumerate(ds["frames"]):
+        if k > last:
+            break
+        D.feed(e, f, run_local_optimization=False)
+        if k not in at:
+            continue
+        i = at[k]
+        ids = fx["edge_id"][fx["edge_ptr"][i]:fx["edge_ptr"][i + 1]]
+        poses = fx["edge_in"][fx["edge_ptr"][i]:fx["edge_ptr"][i + 1]]
+        for r in range(reps):
+            for eid, q in zip(ids, poses):
+                e.set_edge_pose(int(eid), q)
+            s0, t0 = e.opt_timer()
+            e.optimize_local_area(k, 3)
+            s1, t1 = e.opt_timer()
+            sec[r] += s1 - s0
+            tr[r] += t1 - t0
+    return sec.tolist(), tr.tolist()
 
 
 def cpu_pass(args):
-    """One oracle pass over the tour; returns (opt seconds, LM trials) of the sampled keyframes (every `stride`-th of the
-    last keyframes, starting at `offset`). Runs in a worker process."""
-    seed, n_kfs, first = args[:3]
-    stride, offset = (args[3], args[4]) if len(args) > 3 else (1, 0)
+    """Fallback when the workload is not the fixture's (other --kfs / --areas / --tour-seed): one oracle pass over the whole
+    tour WITH optimisation; returns (opt seconds, LM trials) of this worker's sampled keyframes."""
+    seed, n_kfs, sampled = args
     from oracle import pyoracle as po
     from srba_b200 import datasets as D
     ds = D.graphslam_se2_tour(n_kfs, seed=seed)
     e = po.OracleEngine(po.default_params(**engine_kwargs(ds)))
+    sampled = set(sampled)
     sec, trials = 0.0, 0
     for k, f in enumerate(ds["frames"]):
         s0, t0 = e.opt_timer()
         D.feed(e, f)
         s1, t1 = e.opt_timer()
-        if k >= first and (k - first) % stride == offset:
+        if k in sampled:
             sec += s1 - s0
             trials += t1 - t0
     return sec, trials
 
 
+def fixture_matches(args):
+    if not os.path.exists(FIXTURE):
+        return False
+    fx = np.load(FIXTURE)
+    from srba_b200 import datasets as D
+    return (int(fx["kfs"]) == args.kfs and int(fx["seed"]) == args.tour_seed and not args.chain_like
+            and fx["kf"].tolist() == D.sample_keyframes(args.kfs, args.areas).tolist())
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  The reference itself cannot be built here
-    (MRPT + Eigen absent), so this times the oracle port, one independent engine per host core."""
+    (MRPT + Eigen absent), so this times the oracle port, one independent single-threaded engine per host core
+    (BASELINE.md §2.3), on a bounded sample of the batch: every 4th of the 256 areas, dealt round-robin to the cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
-    cores = max(1, min(os.cpu_count() or 1, 16))
-    n_kfs, areas = args.ref_kfs, min(args.areas, args.ref_kfs - 40)
-    first = n_kfs - areas
+    from srba_b200 import datasets as D
+    cores = max(1, len(os.sched_getaffinity(0)))
     ctx = mp.get_context("spawn")
-    per_step = []
-    with ctx.Pool(cores) as pool:
-        for step in range(args.warmup + args.steps):
-            # the SAME tour/areas as the GPU arm (seed 1), the areas dealt round-robin to the cores
-            res = pool.map(cpu_pass, [(1, n_kfs, first, cores, w) for w in range(cores)])
-            if step >= args.warmup:
-                per_step.append((sum(t for _, t in res), max(s for s, _ in res)))
-    trials = sum(t for t, _ in per_step)
-    secs = sum(s for _, s in per_step)
-    val = trials / secs
+    reps = args.warmup + args.steps
+    if fixture_matches(args):
+        sample = list(range(0, args.areas, 4))
+        workers = min(cores, len(sample))
+        with ctx.Pool(workers) as pool:
+            res = pool.map(cpu_fixture_worker, [(sample[w::workers], reps) for w in range(workers)])
+        sec = np.array([r[0] for r in res])[:, args.warmup:]     # workers x steps
+        tr = np.array([r[1] for r in res])[:, args.warmup:]
+        step_s = sec.max(axis=0)                                   # a step lasts as long as its slowest core
+        val = float(tr.sum() / step_s.sum())
+        sample_txt = ("%d single-threaded oracle engines in parallel (one per host core) re-solve every 4th of the %d areas (%d areas, dealt round-robin) "
+                      "from the stored inputs of the %d-keyframe tour (tests/golden/g4_tour3000_states.npz); 'opt' span only; value = all LM trials / slowest core, per step"
+                      % (workers, args.areas, len(sample), args.kfs))
+        ms = 1e3 * float(step_s.mean())
+        used = workers
+    else:
+        sampled = (np.arange(args.kfs - args.areas, args.kfs) if args.chain_like else D.sample_keyframes(args.kfs, args.areas)).tolist()
+        per_step = []
+        with ctx.Pool(cores) as pool:
+            for step in range(reps):
+                res = pool.map(cpu_pass, [(args.tour_seed, args.kfs, sampled[w::cores]) for w in range(cores)])
+                if step >= args.warmup:
+                    per_step.append((sum(t for _, t in res), max(s for s, _ in res)))
+        val = sum(t for t, _ in per_step) / sum(s for _, s in per_step)
+        ms = 1e3 * sum(s for _, s in per_step) / max(1, len(per_step))
+        sample_txt = ("%d single-threaded oracle engines in parallel (one per core) each run the whole %d-keyframe tour and time their share of the %d sampled "
+                      "local areas; 'opt' span only; value = all LM trials / slowest core" % (cores, args.kfs, args.areas))
+        used = cores
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * secs / max(1, len(per_step)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": workload_name(areas), "areas_per_gpu": areas, "tour_keyframes": n_kfs, "note": "oracle port of the reference CPU path (the reference needs MRPT+Eigen, absent here)"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d single-threaded engines in parallel (one per core) share the same %d local areas (round-robin) of the %d-keyframe tour; 'opt' span only, value = all LM trials / slowest core" % (cores, areas, n_kfs)},
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.areas, args.kfs), "areas_per_gpu": args.areas, "tour_keyframes": args.kfs,
+                       "note": "oracle port of the reference CPU path (the reference needs MRPT+Eigen, absent here)"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": used, "kind": "port", "sample": sample_txt},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------- GPU arm
+def time_batch(batch, stream, flush, steps, warmup, torch):
+    """`steps` timed passes of a resident batch, L2 flushed before each; returns (total device ms, per-step ms list)."""
+    sp = stream.cuda_stream
+    for _ in range(warmup):
+        flush.fill_(1)
+        batch.run(sp)
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(steps):
+        flush.fill_(1)                      # L2 flush between timed iterations (untimed)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        batch.run(sp)
+        e1.record(stream)
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    per = [a.elapsed_time(b) for a, b in evs]
+    return sum(per), per
+
+
+def size_stats(flats):
+    out = {}
+    for name, get in (("n_p", lambda p: p.n_unk_edges), ("n_obs_rows", lambda p: p.n_total_obs_rows), ("n_blkA", lambda p: p.n_blkA),
+                      ("n_pairs", lambda p: p.n_pairs), ("n_HAp", lambda p: p.n_HAp)):
+        v = np.array([get(f.p) for f in flats])
+        out[name] = {"min": int(v.min()), "median": int(np.median(v)), "p95": int(np.percentile(v, 95)), "max": int(v.max())}
+    return out
 
 
 def main():
@@ -195,16 +327,20 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="srba_b200")
+    ap.add_argument("--config", type=int, default=4, help="BASELINE config: 4 (default; also #1's dataset) | 2 | 3 | 5 (see tools/bench_configs.py)")
     ap.add_argument("--areas", type=int, default=256, help="independent local areas per GPU (BASELINE config #4)")
-    ap.add_argument("--kfs", type=int, default=700, help="keyframes of the tour the areas are snapshotted from")
-    ap.add_argument("--ref-kfs", type=int, default=0, help="tour length of the CPU legs (default: same as --kfs, i.e. the very same problems)")
+    ap.add_argument("--kfs", type=int, default=3000, help="keyframes of the tour the areas are snapshotted from (SURVEY G1: 3 000)")
+    ap.add_argument("--chain-like", action="store_true", help="round-1 workload: the LAST `areas` keyframes of the tour (use with --kfs 700)")
+    ap.add_argument("--sweep", default="1024,4096", help="further batch sizes (areas per GPU) timed at N=1; '' to skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--tour-seed", type=int, default=1, help="seed of the tour geometry (1 = the workload every number in profiles/ is quoted on)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the chain-like case, the areas sweep and the strong-scaling reading")
+    ap.add_argument("--tour-seed", type=int, default=1, help="seed of the tour geometry")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.ref_kfs <= 0:
-        args.ref_kfs = args.kfs
+    if args.config != 4:
+        from tools import bench_configs
+        return bench_configs.main(args)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -227,14 +363,20 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    # weak scaling: every rank gets the SAME tour (seed 1: same shape of every local area, i.e. the same work per GPU) with
-    # its own observation-noise realisation; rank 0 is bit-identical to the single-GPU run
-    ds, eng, flats = build_problems(seed=args.tour_seed, areas=args.areas, n_kfs=args.kfs, noise_seed=None if rank == 0 else 1000 + rank)
+    extras = not args.no_extras
+    sweep = [int(x) for x in args.sweep.split(",") if x] if (extras and world == 1 and not args.chain_like) else []
+    # weak scaling: every rank gets the SAME tour (same shape of every local area, i.e. the same work per GPU) with its own
+    # observation-noise realisation; rank 0 is bit-identical to the single-GPU run
+    t_build = time.perf_counter()
+    ds, eng, sets = build_problems(seed=args.tour_seed, areas=args.areas, n_kfs=args.kfs, noise_seed=None if rank == 0 else 1000 + rank,
+                                   last=args.chain_like, extra_samples=sweep)
+    t_build = time.perf_counter() - t_build
+    flats = sets[args.areas]
     # BASELINE config #1 reading (one sequential srba-slam run): the tour above WAS such a run through the product
     # engine -- every define_new_keyframe a flatten + one-problem srba_b200_optimize call + scatter.  Reported as context only.
     tm = eng.timers()
     seq = {"keyframes": args.kfs, "lm_trials": int(tm["total_trials"]), "gpu_call_seconds": round(tm["gpu_seconds"], 4),
-           "flatten_scatter_seconds": round(tm["flatten_seconds"], 4),
+           "flatten_scatter_seconds": round(tm["flatten_seconds"], 4), "wall_seconds_incl_python": round(t_build, 2),
            "lm_iterations_per_s": tm["total_trials"] / max(1e-9, tm["gpu_seconds"] + tm["flatten_seconds"])}
     batch = sb.Batch(flats)
     stream = torch.cuda.current_stream()
@@ -242,30 +384,19 @@ def main():
     batch.upload(sp)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
-    def step():
-        flush.fill_(1)                      # L2 flush between timed iterations (untimed)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        batch.run(sp)
-        e1.record(stream)
-        return e0, e1
-
     torch.cuda.profiler.start()   # cudaProfilerStart: `ncu --profile-from-start off` then skips the set-up launches
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
+    time_batch(batch, stream, flush, 0, args.warmup, torch)
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     torch.cuda.synchronize()
-    evs = [step() for _ in range(args.steps)]
-    torch.cuda.synchronize()
+    dev_ms, per_step = time_batch(batch, stream, flush, args.steps, 0, torch)
     if world > 1:
         dist.barrier()
-    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     batch.download(sp)
     stats = [batch.stats(i) for i in range(batch.n)]
     trials_per_step = sum(s["num_trials"] for s in stats)
+    launches_per_step = int(batch.kernel_launches)
 
     # ---- e2e: the reference-facing C-ABI call with HOST buffers (pack + H2D + kernel + D2H + unpack), every step
     n = len(flats)
@@ -290,13 +421,25 @@ def main():
     clocks = sampler.stop() if sampler else None
     e2e_trials = sum(b.r.stats.num_trials for b in bufs)
 
-    tvec = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
-    cvec = torch.tensor([float(trials_per_step), float(e2e_trials)], dtype=torch.float64, device="cuda")
+    # ---- BASELINE config #4 read literally: 256 areas IN TOTAL, dealt round-robin to the N ranks (strong scaling)
+    strong_ms, strong_trials = dev_ms / max(1, args.steps), float(trials_per_step)
+    if extras and world > 1:
+        mine = flats[rank::world]
+        sb_ = sb.Batch(mine)
+        sb_.upload(sp)
+        ms_, _ = time_batch(sb_, stream, flush, max(3, args.steps // 2), 2, torch)
+        strong_ms = ms_ / max(3, args.steps // 2)
+        sb_.download(sp)
+        strong_trials = float(sum(sb_.stats(i)["num_trials"] for i in range(sb_.n)))
+        del sb_
+
+    tvec = torch.tensor([dev_ms, e2e_s, strong_ms], dtype=torch.float64, device="cuda")
+    cvec = torch.tensor([float(trials_per_step), float(e2e_trials), strong_trials], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tvec, op=dist.ReduceOp.MAX)
         dist.all_reduce(cvec, op=dist.ReduceOp.SUM)
-    dev_ms_max, e2e_s_max = tvec.tolist()
-    trials_all, e2e_trials_all = cvec.tolist()
+    dev_ms_max, e2e_s_max, strong_ms_max = tvec.tolist()
+    trials_all, e2e_trials_all, strong_trials_all = cvec.tolist()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -308,32 +451,77 @@ def main():
     ab = algorithmic_bytes(flats, stats)
     launch_s = dev_ms * 1e-3 / args.steps
     achieved = ab["total_bytes"] / launch_s / 1e9
-    traffic = None
+    ncu = {}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("srba_lm_batch_kernel_dram_bytes_per_launch")
+            ncu = json.load(open(tp))
         except Exception:
-            traffic = None
+            ncu = {}
+    config = {"workload": workload_name(args.areas, args.kfs) if not args.chain_like else
+              "G4 (chain-like case): the last %d keyframes of a %d-keyframe tour" % (args.areas, args.kfs),
+              "areas_per_gpu": args.areas, "tour_keyframes": args.kfs, "tour_seed": args.tour_seed, "lm_trials_per_step_per_gpu": trials_per_step,
+              "trials_per_area": {"mean": trials_per_step / max(1, n), "max": max(s["num_trials"] for s in stats)},
+              "area_sizes": size_stats(flats),
+              "ranks": "same tour on every rank, independent observation noise per rank",
+              "sequential_run_of_the_tour": seq,
+              "l2": "flushed between timed iterations (256 MiB fill)", "timing": "CUDA events around each step on the launching stream",
+              "kernel_launches_per_step": launches_per_step, "areas_per_s": n * world * args.steps / (dev_ms_max * 1e-3)}
+    if extras:
+        config["strong_scaling_256_areas_total"] = {"areas_total": n, "ms_per_step": strong_ms_max, "value": strong_trials_all / (strong_ms_max * 1e-3), "unit": UNIT,
+                                                    "note": "BASELINE config #4 read literally: the SAME %d areas dealt to the %d rank(s)" % (n, world)}
+    if extras and world == 1 and not args.chain_like:
+        sw = {}
+        for a in sweep:
+            bb = sb.Batch(sets[a])
+            bb.upload(sp)
+            k = max(2, min(args.steps, 5))
+            ms_, _ = time_batch(bb, stream, flush, k, 1, torch)
+            bb.download(sp)
+            tr_ = sum(bb.stats(i)["num_trials"] for i in range(bb.n))
+            sw[str(a)] = {"ms_per_step": ms_ / k, "value": tr_ * k / (ms_ * 1e-3), "areas_per_s": a * k / (ms_ * 1e-3), "lm_trials_per_step": tr_,
+                          "distinct_areas": len({id(f) for f in sets[a]})}
+            del bb
+        config["areas_sweep"] = sw
+        # the round-1 workload, for continuity: chain-like areas only
+        _, _, cs = build_problems(seed=1, areas=256, n_kfs=700, last=True)
+        bb = sb.Batch(cs[256])
+        bb.upload(sp)
+        ms_, _ = time_batch(bb, stream, flush, args.steps, 2, torch)
+        bb.download(sp)
+        tr_ = sum(bb.stats(i)["num_trials"] for i in range(bb.n))
+        config["chain_like_case"] = {"workload": "last 256 keyframes of a 700-keyframe tour (round-1 bench: chain-like areas)", "ms_per_step": ms_ / args.steps,
+                                     "value": tr_ * args.steps / (ms_ * 1e-3), "lm_trials_per_step": tr_, "area_sizes": size_stats(cs[256])}
+        del bb
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.areas), "areas_per_gpu": args.areas, "tour_keyframes": args.kfs, "lm_trials_per_step_per_gpu": trials_per_step,
-                       "ranks": "same tour (seed 1) on every rank, independent observation noise per rank",
-                       "sequential_run_of_the_tour": seq,
-                       "l2": "flushed between timed iterations (256 MiB fill)", "timing": "CUDA events around each launch on the launching stream"},
+            "config": config,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(batch.h2d_bytes), "d2h_bytes_per_step": int(batch.d2h_bytes)},
-            "gpu_launches": int(batch.kernel_launches) * args.steps,
+            "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "srba_lm_batch_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": ab["total_bytes"],
-                         "stage_bytes": {k: ab[k] for k in ("chain", "assem_res", "assem_jh", "schur", "chol")}, "chol_flop_per_launch": ab["chol_flop"]}}
+            "roofline": {"bound": "hbm", "kernel": "srba_lm_batch_kernel (all instantiations of a step)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu.get("srba_lm_batch_kernel_dram_bytes_per_launch"), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": ab["total_bytes"],
+                         "stage_bytes": {k: ab[k] for k in ("chain", "assem_res", "assem_jh", "jacmat", "schur", "solve", "update")},
+                         "accounting": "touched bytes only (refreshed pose pairs, tiles of the filled block-sparse pattern, no Schur stage without landmarks); "
+                                       "the round-1 figure also charged all pairs per trial and a dense n^2 Cholesky: dense_equiv_chol_bytes",
+                         "dense_equiv_chol_bytes": ab["dense_equiv_chol"], "dense_equiv_chol_flop": ab["chol_flop"], "solve_flop_per_launch": ab["solve_flop"],
+                         "issue_slot_util_pct": ncu.get("issue_slot_util_pct"), "fp64_pipe_util_pct": ncu.get("fp64_pipe_util_pct"),
+                         "ncu_source": ncu.get("source")}}
     if not args.no_cpu_baseline and world == 1:
-        first = args.ref_kfs - min(args.areas, args.ref_kfs - 40)
         t = time.perf_counter()
-        sec, tr = cpu_pass((1, args.ref_kfs, first))
-        line["cpu_baseline"] = {"value": tr / sec, "unit": UNIT, "cores": 1, "kind": "port",
-                                "sample": "oracle (g++ -O2, 1 thread): 'opt' span of the last %d local areas of a %d-keyframe tour with the same generator/parameters (%.1f s wall)"
-                                          % (args.ref_kfs - first, args.ref_kfs, time.perf_counter() - t)}
+        if fixture_matches(args):
+            sample = list(range(0, args.areas, 16))
+            sec, tr = cpu_fixture_worker((sample, 1))
+            sec, tr = sec[0], tr[0]
+            txt = ("oracle (g++ -O2, 1 thread): 'opt' span of every 16th of the %d areas (%d areas) re-solved from the stored inputs of the same tour "
+                   "(tests/golden/g4_tour3000_states.npz)" % (args.areas, len(sample)))
+        else:
+            from srba_b200 import datasets as D
+            sampled = (np.arange(args.kfs - args.areas, args.kfs) if args.chain_like else D.sample_keyframes(args.kfs, args.areas)).tolist()
+            sec, tr = cpu_pass((args.tour_seed, args.kfs, sampled))
+            txt = "oracle (g++ -O2, 1 thread): 'opt' span of the %d sampled local areas during a full sequential run of the %d-keyframe tour" % (len(sampled), args.kfs)
+        line["cpu_baseline"] = {"value": tr / sec, "unit": UNIT, "cores": 1, "kind": "port", "sample": txt + " (%.1f s wall)" % (time.perf_counter() - t)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

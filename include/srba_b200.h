@@ -8,8 +8,15 @@
  * result back.  One call == one optimize_edges() == steps D..S of SURVEY.md §3.3.
  *
  * Conventions: caller owns every buffer; plain pointers + sizes; no exceptions cross the boundary (negative return
- * codes, message via srba_b200_last_error()); the library keeps no state between calls except what a batch handle owns.
- * All reals are IEEE double, all local indices int32.
+ * codes, message via srba_b200_last_error()).  All reals are IEEE double, all local indices int32.
+ * State: the library keeps no PROBLEM state between calls except what a batch / area handle owns.  The synchronous entry
+ * points reuse a grow-only workspace (pinned + device buffers, streams) per calling host thread and CUDA device; it is
+ * rebuilt when the thread's current device changes and freed by srba_b200_release_workspace() or at thread exit.
+ * Threading: every entry point may be called concurrently from several host threads (the reference is single-threaded
+ * per engine, RbaEngine.h:623,628; distinct engines are independent).  Error strings and codes are per thread.  The
+ * internal pack/unpack worker pool serves one call at a time; a concurrent caller packs on its own thread.
+ * Arguments are validated structurally (counts, NULL arrays, CSR pointers, index ranges) before anything is dereferenced
+ * on the device: a malformed problem yields SRBA_ERR_BAD_ARGUMENT for the call, never a fault.
  *
  * Pose layout ("S" doubles):  SE(2): x,y,phi (S=3)  |  SE(3): R row-major (9) then t (3) (S=12).
  */
@@ -43,7 +50,10 @@ enum {
 	SRBA_ERR_RANK_DEFICIENT = -3, /* ASSERT_ABOVEEQ_(OBS_DIMS*nObs, nUnknowns)  optimize_edges.h:355 */
 	SRBA_ERR_CUDA = -4,
 	SRBA_ERR_NO_DEVICE = -5,
-	SRBA_ERR_INTERNAL = -6
+	SRBA_ERR_INTERNAL = -6,
+	SRBA_ERR_NON_FINITE = -7 /* raised on the DEVICE (srba_stats_t::status): the initial error / Hessian diagonal, or the error of a
+	                            trial, is not finite (NaN/Inf in the inputs or a diverged iterate).  The outputs still hold what
+	                            the reference's arithmetic yields (NaN propagates; "rho<=0" is false for NaN, optimize_edges.h:476) */
 };
 
 /* Sensor / noise / LM parameters read by the hot path (TAllParameters, RbaEngine.h:463-472; TSRBAParameters :424-460). */
@@ -184,6 +194,11 @@ void srba_b200_batch_algorithmic_bytes(const srba_batch_t *b, double out[5]);
  * image arrays on chip, workspace arrays on chip, shared-memory budget of the model's kernel.  No device needed. */
 int srba_b200_problem_plan(const srba_problem_t *in, int64_t out[8]);
 
+/* Host-only: size of the block-sparse L D L^t schedule the packer plans for `in` (its own elimination order and on-chip budget):
+ * out[0..3] = 3x3 tiles of the filled pattern incl. the right-hand side, tile updates per factorisation, barrier-separated phases,
+ * 1 when the tiles stay in shared memory.  All 0 when the problem falls back to the dense blocked solver. */
+int srba_b200_problem_ldl_counts(const srba_problem_t *in, int64_t out[4]);
+
 /* Host-only (tests): the symbolic factorisation the packer ships with a problem for the on-chip block-sparse L D L^t
  * solver -- 3x3 tiles numbered row-major (diagonal first, right-hand side as tile column NTR).  counts[6] = {NTR, tiles,
  * updates, ok, phases, tiles fit on chip}; row[4*(NTR+1)] = {first tile, end tile, first update, end update} per row;
@@ -224,6 +239,17 @@ typedef struct {
 int srba_b200_eval_overall_squared_error(const srba_eval_problem_t *in, double *out_sqerr, double *out_pair_pose);
 
 const char *srba_b200_last_error(void);
+/* Frees the calling thread's reusable workspace of the synchronous entry points (see "State" above). */
+void srba_b200_release_workspace(void);
+/* Execution options (tests / experiments; process-wide, initialised from the SRBA_B200_* environment variables):
+ *   "cluster"  -1 auto | 0 never | 1 always  an 8-CTA cluster team per heavy area
+ *   "blocked"   0 auto | 1                   dense blocked Cholesky instead of the block-sparse L D L^t
+ *   "wide"      0 auto | 1                   3-int solver update descriptors
+ *   "chunks"    1..8                         pipelined chunks of srba_b200_optimize_batch (default 4)
+ *   "big_se2"  -1 auto | 0 never | 1 always  the large-CTA kernel for SE(2) areas that overflow the small kernel's arena
+ * set returns SRBA_OK or SRBA_ERR_BAD_ARGUMENT (unknown name); get returns INT32_MIN for an unknown name. */
+int srba_b200_set_option(const char *name, int32_t value);
+int32_t srba_b200_get_option(const char *name);
 int srba_b200_device_count(void);
 const char *srba_b200_version(void);
 

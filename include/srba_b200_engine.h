@@ -52,7 +52,7 @@ typedef struct { /* TNewEdgeInfo srba_types.h:178-200 */
 void srba_engine_default_params(srba_engine_params_t *p);
 void *srba_engine_create(const srba_engine_params_t *p);
 void srba_engine_destroy(void *h);
-void srba_engine_set_params(void *h, const srba_engine_params_t *p);
+int srba_engine_set_params(void *h, const srba_engine_params_t *p); /* 0 ok; -1: rejected, engine unchanged (srba_engine_last_error) */
 
 int srba_engine_define_new_keyframe(void *h, uint64_t n_obs, const uint64_t *feat_id, const double *obs_data, const uint8_t *is_fixed,
                                     const uint8_t *is_unknown_with_init_val, const double *feat_rel_pos, int run_local_optimization,
@@ -74,6 +74,8 @@ void *srba_engine_flatten_local_area(void *h, uint64_t root, uint64_t win_size);
 const srba_problem_t *srba_flat_problem(const void *flat);
 int srba_flat_apply(void *h, const void *flat, const srba_result_t *res, srba_opt_info_t *out);
 void srba_flat_ids(const void *flat, uint64_t *k2k_ids, uint64_t *lm_ids, uint64_t *obs_global_idx, uint64_t *pair_from_to);
+/* global ids of the k2k edges behind srba_problem_t::edge_pose (local edge index -> k2k edge id); returns their number */
+uint64_t srba_flat_touched_edges(const void *flat, uint64_t *edge_ids, uint64_t cap);
 void srba_flat_destroy(void *flat);
 /* When on, every optimize_edges() call of the engine keeps its flattened problem (pre-optimisation snapshot). */
 void srba_engine_record_problems(void *h, int on);

@@ -17,7 +17,7 @@ NOISE_IDENTITY, NOISE_CONST_MATRIX = 0, 1
 SOLVER_SCHUR_DENSE, SOLVER_SCHUR_SPARSE, SOLVER_NO_SCHUR_SPARSE = 0, 1, 2  # RBA_OPTIONS::solver_t (srba_options_solver.h:21-77)
 OBS_DIMS = {OBS_RELPOSES2D: 3, OBS_CARTESIAN3D: 3, OBS_MONO: 2, OBS_STEREO: 4}
 INVALID = 2**64 - 1
-SRBA_OK, ERR_BAD_ARGUMENT, ERR_UNSUPPORTED_MODEL, ERR_RANK_DEFICIENT, ERR_CUDA, ERR_NO_DEVICE, ERR_INTERNAL = 0, -1, -2, -3, -4, -5, -6
+SRBA_OK, ERR_BAD_ARGUMENT, ERR_UNSUPPORTED_MODEL, ERR_RANK_DEFICIENT, ERR_CUDA, ERR_NO_DEVICE, ERR_INTERNAL, ERR_NON_FINITE = 0, -1, -2, -3, -4, -5, -6, -7
 
 i32, u64, dbl = C.c_int32, C.c_uint64, C.c_double
 pi32, pdbl, pu8, pu64 = C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)
@@ -86,10 +86,11 @@ class NewEdge(C.Structure):
 EXPORTED_SYMBOLS = [
     "srba_b200_optimize", "srba_b200_optimize_batch", "srba_b200_batch_create", "srba_b200_batch_upload", "srba_b200_batch_run",
     "srba_b200_batch_download", "srba_b200_batch_unpack", "srba_b200_batch_destroy", "srba_b200_batch_h2d_bytes", "srba_b200_batch_d2h_bytes",
-    "srba_b200_batch_kernel_launches", "srba_b200_batch_stage_cycles", "srba_b200_problem_plan", "srba_b200_debug_ldl_schedule", "srba_b200_batch_algorithmic_bytes", "srba_b200_eval_overall_squared_error", "srba_b200_last_error", "srba_b200_device_count", "srba_b200_version",
+    "srba_b200_batch_kernel_launches", "srba_b200_batch_stage_cycles", "srba_b200_problem_plan", "srba_b200_problem_ldl_counts", "srba_b200_debug_ldl_schedule", "srba_b200_batch_algorithmic_bytes", "srba_b200_eval_overall_squared_error", "srba_b200_last_error", "srba_b200_device_count", "srba_b200_version",
+    "srba_b200_release_workspace", "srba_b200_set_option", "srba_b200_get_option",
     "srba_engine_default_params", "srba_engine_create", "srba_engine_destroy", "srba_engine_set_params", "srba_engine_define_new_keyframe",
     "srba_engine_optimize_local_area", "srba_engine_optimize_edges", "srba_engine_select_local_area", "srba_engine_flatten",
-    "srba_engine_flatten_local_area", "srba_flat_problem", "srba_flat_apply", "srba_flat_ids", "srba_flat_destroy",
+    "srba_engine_flatten_local_area", "srba_flat_problem", "srba_flat_apply", "srba_flat_ids", "srba_flat_touched_edges", "srba_flat_destroy",
     "srba_engine_record_problems", "srba_engine_num_recorded", "srba_engine_take_recorded", "srba_engine_trace", "srba_engine_last_trace",
     "srba_engine_num_keyframes", "srba_engine_num_edges", "srba_engine_num_observations", "srba_engine_pose_nvals", "srba_engine_get_edge",
     "srba_engine_set_edge_pose", "srba_engine_num_unknown_lms", "srba_engine_get_unknown_lms", "srba_engine_set_lm_pos",
@@ -133,17 +134,24 @@ def lib():
     pi32 = C.POINTER(C.c_int32)
     L.srba_b200_debug_ldl_schedule.restype = C.c_int
     L.srba_b200_debug_ldl_schedule.argtypes = [pp, pi32, pi32, pi32, pi32, pi32, pi32, pi32, i32, i32, i32]
+    L.srba_b200_problem_ldl_counts.restype = C.c_int
+    L.srba_b200_problem_ldl_counts.argtypes = [pp, C.POINTER(C.c_int64)]
     L.srba_b200_problem_plan.restype = C.c_int
     L.srba_b200_problem_plan.argtypes = [pp, C.POINTER(C.c_int64)]
     L.srba_b200_last_error.restype = C.c_char_p
     L.srba_b200_version.restype = C.c_char_p
     L.srba_b200_device_count.restype = C.c_int
+    L.srba_b200_set_option.restype = C.c_int
+    L.srba_b200_set_option.argtypes = [C.c_char_p, i32]
+    L.srba_b200_get_option.restype = i32
+    L.srba_b200_get_option.argtypes = [C.c_char_p]
     # engine
     pep, poi = C.POINTER(EngineParams), C.POINTER(OptInfo)
     L.srba_engine_default_params.argtypes = [pep]
     L.srba_engine_create.restype = vp
     L.srba_engine_create.argtypes = [pep]
     L.srba_engine_destroy.argtypes = [vp]
+    L.srba_engine_set_params.restype = C.c_int
     L.srba_engine_set_params.argtypes = [vp, pep]
     L.srba_engine_define_new_keyframe.restype = C.c_int
     L.srba_engine_define_new_keyframe.argtypes = [vp, u64, pu64, pdbl, pu8, pu8, pdbl, C.c_int, pu64, C.POINTER(NewEdge), u64, pu64, poi, poi]
@@ -162,6 +170,8 @@ def lib():
     L.srba_flat_apply.restype = C.c_int
     L.srba_flat_apply.argtypes = [vp, vp, pr, poi]
     L.srba_flat_ids.argtypes = [vp, pu64, pu64, pu64, pu64]
+    L.srba_flat_touched_edges.restype = u64
+    L.srba_flat_touched_edges.argtypes = [vp, pu64, u64]
     L.srba_flat_destroy.argtypes = [vp]
     L.srba_engine_record_problems.argtypes = [vp, C.c_int]
     L.srba_engine_num_recorded.restype = u64
@@ -203,6 +213,15 @@ def lib():
     L.srba_engine_last_error.restype = C.c_char_p
     _lib = L
     return L
+
+
+def set_option(name, value):
+    """srba_b200_set_option (include/srba_b200.h): execution-mode hooks for tests / experiments; returns the previous value."""
+    L = lib()
+    old = L.srba_b200_get_option(name.encode())
+    if L.srba_b200_set_option(name.encode(), int(value)) != SRBA_OK:
+        raise ValueError("unknown srba_b200 option %r" % name)
+    return old
 
 
 def ptr(a, ct):

@@ -57,7 +57,97 @@ struct Layout {
 
 int obs_dims(int k) { return k == SRBA_OBS_MONO ? 2 : (k == SRBA_OBS_STEREO ? 4 : 3); }
 
-int validate(const srba_problem_t &p) {
+// Run-time execution options (srba_b200_set_option): test / experiment hooks, initialised once from the environment.
+//   cluster  -1 auto | 0 never | 1 always : 8-CTA cluster team per heavy area          (env SRBA_B200_CLUSTER)
+//   blocked   0 auto | 1 : dense blocked Cholesky instead of the block-sparse L D L^t   (env SRBA_B200_SOLVER=blocked)
+//   wide      0 auto | 1 : 3-int update descriptors                                     (env SRBA_B200_WIDE)
+//   chunks    1..8 pipelined chunks of srba_b200_optimize_batch                          (env SRBA_B200_CHUNKS, default 4)
+//   big_se2  -1 auto | 0 never | 1 always : large-CTA kernel for SE(2) areas that overflow the small kernel's arena
+enum { OPT_CLUSTER = 0, OPT_BLOCKED, OPT_WIDE, OPT_CHUNKS, OPT_BIG_SE2, OPT_COUNT };
+const char *const k_opt_names[OPT_COUNT] = {"cluster", "blocked", "wide", "chunks", "big_se2"};
+std::atomic<int> g_opt[OPT_COUNT];
+std::once_flag g_opt_once;
+void init_options() {
+	std::call_once(g_opt_once, [] {
+		const char *e;
+		g_opt[OPT_CLUSTER].store((e = std::getenv("SRBA_B200_CLUSTER")) ? std::atoi(e) : -1);
+		g_opt[OPT_BLOCKED].store(((e = std::getenv("SRBA_B200_SOLVER")) && std::string(e) == "blocked") ? 1 : 0);
+		g_opt[OPT_WIDE].store(std::getenv("SRBA_B200_WIDE") ? 1 : 0);
+		g_opt[OPT_CHUNKS].store((e = std::getenv("SRBA_B200_CHUNKS")) ? std::max(1, std::min(std::atoi(e), 8)) : 4);
+		g_opt[OPT_BIG_SE2].store((e = std::getenv("SRBA_B200_BIG_SE2")) ? std::atoi(e) : -1);
+	});
+}
+int option(int id) { init_options(); return g_opt[id].load(std::memory_order_relaxed); }
+
+// Structural validation of one caller-owned problem: the packer, the symbolic factorisation and the kernel all index
+// with these arrays, so a malformed problem must be rejected here, not found as a fault of the whole batch.  O(size);
+// returns NULL when the problem is well formed, else a static message (callable from worker threads).
+const char *validate_structure(const srba_problem_t &p) {
+	const int32_t counts[] = {p.n_edges, p.n_unk_edges, p.n_lms, p.n_unk_lms, p.n_pairs, p.n_path, p.n_obs, p.n_blkA, p.n_blkF, p.n_HAp, p.n_HAp_terms,
+	                          p.n_HApf, p.n_HApf_terms, p.n_S, p.n_S_terms, p.n_total_obs_rows};
+	for (int32_t c : counts)
+		if (c < 0) return "negative count";
+	if ((int64_t)2 * p.n_pairs > INT32_MAX) return "too many pose pairs";
+	struct Arr { const void *ptr; int64_t n; };
+	const Arr arrs[] = {{p.edge_pose, p.n_edges}, {p.unk_edge, p.n_unk_edges}, {p.lm_pos, p.n_lms}, {p.unk_lm, p.n_unk_lms}, {p.pair_path_ptr, p.n_pairs + 1},
+	                    {p.path_edge, p.n_path}, {p.path_dir, p.n_path}, {p.obs_z, p.n_obs}, {p.obs_slot, p.n_obs}, {p.obs_lm, p.n_obs}, {p.obs_mult, p.n_obs},
+	                    {p.colA_ptr, p.n_unk_edges + 1}, {p.blkA_obs, p.n_blkA}, {p.blkA_slotA, p.n_blkA}, {p.blkA_slotD, p.n_blkA}, {p.blkA_normal_dir, p.n_blkA},
+	                    {p.colF_ptr, p.n_unk_lms + 1}, {p.blkF_obs, p.n_blkF}, {p.blkF_slot, p.n_blkF}, {p.row_ptr, p.n_obs + 1}, {p.row_blk, p.n_blkA + p.n_blkF},
+	                    {p.HAp_row, p.n_HAp}, {p.HAp_col, p.n_HAp}, {p.HAp_term_ptr, p.n_HAp + 1}, {p.HAp_term_a, p.n_HAp_terms}, {p.HAp_term_b, p.n_HAp_terms},
+	                    {p.HApf_row, p.n_HApf}, {p.HApf_col, p.n_HApf}, {p.HApf_term_ptr, p.n_HApf + 1}, {p.HApf_term_a, p.n_HApf_terms}, {p.HApf_term_f, p.n_HApf_terms},
+	                    {p.rowApf_ptr, p.n_unk_edges + 1}, {p.colApf_ptr, p.n_unk_lms + 1}, {p.colApf_idx, p.n_HApf},
+	                    {p.S_row, p.n_S}, {p.S_col, p.n_S}, {p.S_HAp, p.n_S}, {p.S_term_ptr, p.n_S + 1}, {p.S_term_rowblk, p.n_S_terms}, {p.S_term_colblk, p.n_S_terms}};
+	for (const Arr &a : arrs)
+		if (a.n > 0 && !a.ptr) return "NULL array with a non-zero count";
+	auto csr = [](const int32_t *ptr, int n, int total) {
+		if (ptr[0] != 0 || ptr[n] != total) return false;
+		for (int i = 0; i < n; i++)
+			if (ptr[i] > ptr[i + 1]) return false;
+		return true;
+	};
+	auto in_range = [](const int32_t *a, int n, int lo, int hi) {  // every a[i] in [lo, hi)
+		for (int i = 0; i < n; i++)
+			if (a[i] < lo || a[i] >= hi) return false;
+		return true;
+	};
+	const int n_slots = 2 * p.n_pairs, n_blk = p.n_blkA + p.n_blkF;
+	if (!csr(p.pair_path_ptr, p.n_pairs, p.n_path)) return "pair_path_ptr is not a CSR row pointer over n_path";
+	if (!csr(p.colA_ptr, p.n_unk_edges, p.n_blkA)) return "colA_ptr is not a CSR row pointer over n_blkA";
+	if (!csr(p.colF_ptr, p.n_unk_lms, p.n_blkF)) return "colF_ptr is not a CSR row pointer over n_blkF";
+	if (!csr(p.row_ptr, p.n_obs, n_blk)) return "row_ptr is not a CSR row pointer over n_blkA + n_blkF";
+	if (!csr(p.HAp_term_ptr, p.n_HAp, p.n_HAp_terms)) return "HAp_term_ptr is not a CSR row pointer over n_HAp_terms";
+	if (!csr(p.HApf_term_ptr, p.n_HApf, p.n_HApf_terms)) return "HApf_term_ptr is not a CSR row pointer over n_HApf_terms";
+	if (!csr(p.rowApf_ptr, p.n_unk_edges, p.n_HApf)) return "rowApf_ptr is not a CSR row pointer over n_HApf";
+	if (!csr(p.colApf_ptr, p.n_unk_lms, p.n_HApf)) return "colApf_ptr is not a CSR row pointer over n_HApf";
+	if (!csr(p.S_term_ptr, p.n_S, p.n_S_terms)) return "S_term_ptr is not a CSR row pointer over n_S_terms";
+	if (!in_range(p.unk_edge, p.n_unk_edges, 0, p.n_edges)) return "unk_edge out of range";
+	if (!in_range(p.unk_lm, p.n_unk_lms, 0, p.n_lms)) return "unk_lm out of range";
+	if (!in_range(p.path_edge, p.n_path, 0, p.n_edges)) return "path_edge out of range";
+	if (!in_range(p.obs_slot, p.n_obs, -1, n_slots)) return "obs_slot out of range";
+	if (p.model.pose_kind == SRBA_POSE_SE3 && !in_range(p.obs_lm, p.n_obs, 0, p.n_lms)) return "obs_lm out of range";
+	if (!in_range(p.obs_mult, p.n_obs, 0, INT32_MAX)) return "obs_mult negative";
+	if (!in_range(p.blkA_obs, p.n_blkA, 0, p.n_obs)) return "blkA_obs out of range";
+	if (!in_range(p.blkA_slotA, p.n_blkA, -1, n_slots)) return "blkA_slotA out of range";
+	if (!in_range(p.blkA_slotD, p.n_blkA, 0, n_slots)) return "blkA_slotD out of range";
+	if (!in_range(p.blkF_obs, p.n_blkF, 0, p.n_obs)) return "blkF_obs out of range";
+	if (!in_range(p.blkF_slot, p.n_blkF, -1, n_slots)) return "blkF_slot out of range";
+	if (!in_range(p.row_blk, n_blk, 0, n_blk)) return "row_blk out of range";
+	if (!in_range(p.HAp_row, p.n_HAp, 0, p.n_unk_edges) || !in_range(p.HAp_col, p.n_HAp, 0, p.n_unk_edges)) return "HAp_row / HAp_col out of range";
+	if (!in_range(p.HAp_term_a, p.n_HAp_terms, 0, p.n_blkA) || !in_range(p.HAp_term_b, p.n_HAp_terms, 0, p.n_blkA)) return "HAp_term_a / HAp_term_b out of range";
+	if (!in_range(p.HApf_row, p.n_HApf, 0, p.n_unk_edges) || !in_range(p.HApf_col, p.n_HApf, 0, p.n_unk_lms)) return "HApf_row / HApf_col out of range";
+	if (!in_range(p.HApf_term_a, p.n_HApf_terms, 0, p.n_blkA) || !in_range(p.HApf_term_f, p.n_HApf_terms, 0, p.n_blkF)) return "HApf_term_a / HApf_term_f out of range";
+	if (!in_range(p.colApf_idx, p.n_HApf, 0, p.n_HApf)) return "colApf_idx out of range";
+	if (!in_range(p.S_row, p.n_S, 0, p.n_unk_edges) || !in_range(p.S_col, p.n_S, 0, p.n_unk_edges)) return "S_row / S_col out of range";
+	if (!in_range(p.S_HAp, p.n_S, -1, p.n_HAp)) return "S_HAp out of range";
+	if (!in_range(p.S_term_rowblk, p.n_S_terms, 0, p.n_HApf) || !in_range(p.S_term_colblk, p.n_S_terms, 0, p.n_HApf)) return "S_term_rowblk / S_term_colblk out of range";
+	for (int b = 0; b < p.n_S; b++)
+		if (p.S_row[b] > p.S_col[b]) return "reduced-system block below the diagonal (row > col)";
+	for (int b = 0; b < p.n_HAp; b++)
+		if (p.HAp_row[b] > p.HAp_col[b]) return "H_Ap block below the diagonal (row > col)";
+	return nullptr;
+}
+
+int validate(const srba_problem_t &p, bool deep = true) {
 	const srba_model_t &m = p.model;
 	if (m.pose_kind == SRBA_POSE_SE2) {
 		if (m.obs_kind != SRBA_OBS_RELPOSES2D || m.sensor_pose_kind != SRBA_SENSORPOSE_NONE)
@@ -71,14 +161,21 @@ int validate(const srba_problem_t &p) {
 	if (p.n_unk_edges <= 0)
 		return fail(SRBA_ERR_BAD_ARGUMENT, "n_unk_edges must be >0 (the reference dereferences an empty Schur table when only landmarks are optimised, schur.h:34,288)");
 	if (p.n_obs <= 0 || p.n_blkA <= 0) return fail(SRBA_ERR_BAD_ARGUMENT, "empty problem");
+	if (m.sensor_pose_kind != SRBA_SENSORPOSE_NONE && m.sensor_pose_kind != SRBA_SENSORPOSE_SE3) return fail(SRBA_ERR_BAD_ARGUMENT, "unknown sensor_pose_kind");
+	if (m.noise_kind != SRBA_NOISE_IDENTITY && m.noise_kind != SRBA_NOISE_CONST_MATRIX) return fail(SRBA_ERR_BAD_ARGUMENT, "unknown noise_kind");
 	const int P = m.pose_kind == SRBA_POSE_SE2 ? 3 : 6;
 	const int o = obs_dims(m.obs_kind);
-	// ASSERT_ABOVEEQ_(OBS_DIMS*nObs, POSE_DIMS*nUnknowns_k2k+LM_DIMS*nUnknowns_k2f)  optimize_edges.h:355
-	if ((int64_t)o * p.n_total_obs_rows < (int64_t)P * p.n_unk_edges + 3LL * p.n_unk_lms)
-		return fail(SRBA_ERR_RANK_DEFICIENT, "OBS_DIMS*nObs < number of scalar unknowns (optimize_edges.h:355)");
 	if (m.noise_kind == SRBA_NOISE_IDENTITY && !(m.noise_std > 0)) return fail(SRBA_ERR_BAD_ARGUMENT, "noise_std must be > 0");
 	if (m.solver_kind < SRBA_SOLVER_SCHUR_DENSE_CHOLESKY || m.solver_kind > SRBA_SOLVER_NO_SCHUR_SPARSE_CHOLESKY)
 		return fail(SRBA_ERR_BAD_ARGUMENT, "solver_kind must be one of SRBA_SOLVER_* (srba_options_solver.h:21-77)");
+	if (deep) {
+		if (const char *msg = validate_structure(p)) return fail(SRBA_ERR_BAD_ARGUMENT, msg);
+	} else {
+		if (p.n_total_obs_rows < 0 || p.n_unk_lms < 0) return fail(SRBA_ERR_BAD_ARGUMENT, "negative count");
+	}
+	// ASSERT_ABOVEEQ_(OBS_DIMS*nObs, POSE_DIMS*nUnknowns_k2k+LM_DIMS*nUnknowns_k2f)  optimize_edges.h:355
+	if ((int64_t)o * p.n_total_obs_rows < (int64_t)P * p.n_unk_edges + 3LL * p.n_unk_lms)
+		return fail(SRBA_ERR_RANK_DEFICIENT, "OBS_DIMS*nObs < number of scalar unknowns (optimize_edges.h:355)");
 	return SRBA_OK;
 }
 
@@ -237,8 +334,7 @@ void symbolic_tiles(const srba_problem_t &p, int P, long max_tiles_on_chip, Tile
 		if (tiles_md < tiles) { perm = md; tiles = tiles_md; }
 	}
 	if (tiles > (1L << 20)) return;  // > 96 MB of tiles: such systems use the blocked dense solver
-	static const bool force_wide = std::getenv("SRBA_B200_WIDE") != nullptr;  // test hook
-	sy.wide = tiles > 32767 || force_wide;  // tile ids no longer fit 15/16 bits: 3-int update descriptors
+	sy.wide = tiles > 32767 || option(OPT_WIDE) != 0;  // (test hook)  // tile ids no longer fit 15/16 bits: 3-int update descriptors
 	sy.on_chip = tiles <= max_tiles_on_chip;
 	std::vector<int> inv(np);
 	for (int i = 0; i < np; i++) inv[perm[i]] = i;
@@ -428,11 +524,11 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 		if (max_tiles > 0) symbolic_tiles(p, P, max_tiles, sy);
 		else sy.clear();
 	}
-	static const bool force_blocked = [] { const char *e = std::getenv("SRBA_B200_SOLVER"); return e && std::string(e) == "blocked"; }();  // tests
+	const bool force_blocked = option(OPT_BLOCKED) != 0;  // tests
 	// ---- team size: large areas (their core arrays overflow one SM's shared memory: SE(3) landmark areas, SE(2) areas
 	// with loop closures) are solved by a CLUSTER of 8 CTAs with everything in the L2-resident workspace
 	// (lm_kernel_cluster.cu); SRBA_B200_CLUSTER=0/1 forces the choice (tests)
-	static const int force_cluster = [] { const char *e = std::getenv("SRBA_B200_CLUSTER"); return e ? std::atoi(e) : -1; }();
+	const int force_cluster = option(OPT_CLUSTER);
 	bool cluster = false;
 	if (sy.ok && !force_blocked) {
 		const uint64_t demand = (uint64_t)sy.tile_ij.size() * 96 + (uint64_t)2 * p.n_pairs * S * 8 + (uint64_t)p.n_blkA * o * P * 8 + (uint64_t)p.n_blkF * o * 3 * 8 +
@@ -589,7 +685,7 @@ class WorkerPool {
 	// Workers SPIN on an atomic generation counter for a short while after their last job (a batch call issues eight
 	// parallel_for rounds within ~1 ms, and a condition-variable wake-up costs as much as packing a chunk), then sleep.
 	std::vector<std::thread> th_;
-	std::mutex m_;
+	std::mutex m_, job_m_;
 	std::condition_variable cv_;
 	const std::function<void(int)> *fn_ = nullptr;
 	int n_ = 0;
@@ -649,8 +745,12 @@ public:
 		for (auto &t : th_) t.join();
 	}
 	int threads() const { return (int)th_.size() + 1; }
+	// Safe for concurrent callers: one job at a time owns the workers; a caller that finds the pool busy (another host
+	// thread is inside a batch call) runs its own loop serially instead of waiting.
 	void parallel_for(int n, const std::function<void(int)> &f) {
 		if (n < 16 || th_.empty() || g_forked.load()) { for (int i = 0; i < n; i++) f(i); return; }
+		std::unique_lock<std::mutex> job(job_m_, std::try_to_lock);
+		if (!job.owns_lock()) { for (int i = 0; i < n; i++) f(i); return; }
 		fn_ = &f; n_ = n; next_.store(0);
 		active_.store((int)th_.size(), std::memory_order_release);
 		gen_.fetch_add(1, std::memory_order_acq_rel);
@@ -673,15 +773,48 @@ double problem_cost(const DevProblem &h) {
 }
 }  // namespace
 
-// Grow-only buffer pool reused by the synchronous entry points (srba_b200_optimize / _optimize_batch): the library
-// keeps no problem state between calls, only this reusable workspace (SURVEY.md §8b "optional reusable device workspace").
+// Grow-only buffer pool reused by the synchronous entry points (srba_b200_optimize / _optimize_batch): the library keeps
+// no PROBLEM state between calls, only this reusable workspace (SURVEY.md §8b "optional reusable device workspace"),
+// one set per calling host thread and CUDA device.  It is rebuilt when the thread's current device changes, released by
+// srba_b200_release_workspace() and when the thread exits.
 struct Pool {
 	char *h_img = nullptr, *h_res = nullptr, *d_img = nullptr, *d_ws = nullptr, *d_res = nullptr;
 	uint64_t h_img_cap = 0, h_res_cap = 0, d_img_cap = 0, d_ws_cap = 0, d_res_cap = 0;
 	cudaStream_t stream = nullptr;
+	int device = -1;
+	void release() {
+		if (device >= 0) {
+			int cur = -1;
+			const bool sw = cudaGetDevice(&cur) == cudaSuccess && cur != device && cudaSetDevice(device) == cudaSuccess;
+			if (h_img) cudaFreeHost(h_img);
+			if (h_res) cudaFreeHost(h_res);
+			if (d_img) cudaFree(d_img);
+			if (d_ws) cudaFree(d_ws);
+			if (d_res) cudaFree(d_res);
+			if (stream) cudaStreamDestroy(stream);
+			if (sw) cudaSetDevice(cur);
+			cudaGetLastError();  // a context already torn down at process exit is not an error worth keeping
+		}
+		h_img = h_res = d_img = d_ws = d_res = nullptr;
+		h_img_cap = h_res_cap = d_img_cap = d_ws_cap = d_res_cap = 0;
+		stream = nullptr;
+		device = -1;
+	}
 };
 #define SRBA_MAX_CHUNKS 8
-static thread_local Pool g_pool[SRBA_MAX_CHUNKS];  // one buffer set per pipelined chunk of a batch call
+struct PoolSet {
+	Pool p[SRBA_MAX_CHUNKS];  // one buffer set per pipelined chunk of a batch call
+	~PoolSet() { if (!g_forked.load()) for (Pool &q : p) q.release(); }
+};
+static thread_local PoolSet g_pools;
+// the calling thread's pool for chunk c on its CURRENT device (buffers of another device are released first)
+static Pool &pool_for(int c) {
+	Pool &q = g_pools.p[c];
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+	if (q.device != dev) { q.release(); q.device = dev; }
+	return q;
+}
 
 static bool pool_reserve_host(char **p, uint64_t *cap, uint64_t need) {
 	if (*cap >= need) return true;
@@ -723,6 +856,21 @@ struct srba_batch {
 extern "C" {
 
 const char *srba_b200_last_error(void) { return g_err.c_str(); }
+int srba_b200_set_option(const char *name, int32_t value) {
+	init_options();
+	for (int i = 0; name && i < OPT_COUNT; i++)
+		if (std::strcmp(name, k_opt_names[i]) == 0) { g_opt[i].store(value); return SRBA_OK; }
+	return fail(SRBA_ERR_BAD_ARGUMENT, "unknown option");
+}
+void srba_b200_release_workspace(void) {
+	for (Pool &q : g_pools.p) q.release();
+}
+int32_t srba_b200_get_option(const char *name) {
+	init_options();
+	for (int i = 0; name && i < OPT_COUNT; i++)
+		if (std::strcmp(name, k_opt_names[i]) == 0) return g_opt[i].load();
+	return INT32_MIN;
+}
 const char *srba_b200_version(void) { return "srba_b200 0.1 (sm_100a)"; }
 int srba_b200_device_count(void) {
 	int n = 0;
@@ -812,10 +960,18 @@ static srba_batch_t *batch_create_impl(int32_t n, const srba_problem_t *const *i
 	if (n <= 0 || !in) { fail(SRBA_ERR_BAD_ARGUMENT, "empty batch"); return nullptr; }
 	if (srba_b200_device_count() <= 0) { fail(SRBA_ERR_NO_DEVICE, "no CUDA device: the srba_b200 hot path has no CPU fallback"); return nullptr; }
 	for (int i = 0; i < n; i++)
-		if (!in[i] || validate(*in[i]) != SRBA_OK) {
+		if (!in[i] || validate(*in[i], false) != SRBA_OK) {
 			if (!in[i]) fail(SRBA_ERR_BAD_ARGUMENT, "null problem");
 			return nullptr;
 		}
+	{  // structural checks (O(size) per problem) on the worker pool, before anything dereferences the caller's index arrays
+		std::atomic<const char *> bad{nullptr};
+		workers().parallel_for(n, [&](int i) {
+			if (bad.load(std::memory_order_relaxed)) return;
+			if (const char *msg = validate_structure(*in[i])) { const char *expect = nullptr; bad.compare_exchange_strong(expect, msg); }
+		});
+		if (bad.load()) { fail(SRBA_ERR_BAD_ARGUMENT, bad.load()); return nullptr; }
+	}
 	srba_batch_t *b = new srba_batch();
 	b->n = n;
 	b->hdr.resize(n);
@@ -930,6 +1086,7 @@ int srba_b200_batch_unpack(srba_batch_t *b, int32_t i, srba_result_t *out) {
 	out->trace_len = tl > 0 ? tl : 0;
 	if (out->trace && tl > 0) std::memcpy(out->trace, r + h.res_trace, (size_t)tl * 6 * 8);
 	if (out->trace_delta && tl > 0) std::memcpy(out->trace_delta, r + h.res_trace_delta, (size_t)tl * h.n_scalars * 8);
+	if (out->stats.status != SRBA_OK) g_err = "device-side error status (srba_stats_t::status)";
 	return out->stats.status;
 }
 
@@ -999,6 +1156,21 @@ int srba_b200_problem_plan(const srba_problem_t *in, int64_t out[8]) {
 	return SRBA_OK;
 }
 
+int srba_b200_problem_ldl_counts(const srba_problem_t *in, int64_t out[4]) {
+	if (!in || !out) return fail(SRBA_ERR_BAD_ARGUMENT, "null argument");
+	const int rc = validate(*in);
+	if (rc != SRBA_OK) return rc;
+	DevProblem h;
+	TileSymbolic sy;
+	pack_problem(*in, h, nullptr, 0, 0, sy, true);
+	const bool reg = h.chol_mode == SRBA_CHOL_REG;
+	out[0] = reg ? (int64_t)sy.tile_ij.size() : 0;
+	out[1] = reg ? (int64_t)(sy.upd.size() / (sy.wide ? 3 : 2)) : 0;
+	out[2] = reg ? sy.n_phases : 0;
+	out[3] = (reg && !h.ldl_tiles_in_ws) ? 1 : 0;
+	return SRBA_OK;
+}
+
 int srba_b200_optimize_batch(int32_t n, const srba_problem_t *const *in, srba_result_t *const *out) {
 	if (!out) return fail(SRBA_ERR_BAD_ARGUMENT, "null out");
 	int tcap = 0, want_dense = 0;
@@ -1015,10 +1187,7 @@ int srba_b200_optimize_batch(int32_t n, const srba_problem_t *const *in, srba_re
 	// A large batch is cut into up to SRBA_MAX_CHUNKS chunks, each with its own stream and buffers: while chunk c is copied
 	// and solved, chunk c+1 is being packed on the host cores, and results come back chunk by chunk.  All chunks fit the
 	// GPU together (2 CTAs/SM), so the kernels overlap; only the first pack and the last copy-back stay exposed.
-	static const int k_chunks = [] {  // SRBA_B200_CHUNKS=1..8 overrides the default of 4 pipelined chunks
-		const char *e = std::getenv("SRBA_B200_CHUNKS");
-		return e ? std::max(1, std::min(std::atoi(e), SRBA_MAX_CHUNKS)) : 4;
-	}();
+	const int k_chunks = std::max(1, std::min(option(OPT_CHUNKS), SRBA_MAX_CHUNKS));  // default 4 pipelined chunks
 	const int K = n >= 64 ? k_chunks : 1;
 	int n_heavy = 0;
 	for (int i = 0; i < n; i++) n_heavy += (in[i] && heavy_problem(*in[i])) ? 1 : 0;
@@ -1029,7 +1198,7 @@ int srba_b200_optimize_batch(int32_t n, const srba_problem_t *const *in, srba_re
 	int rc = SRBA_OK;
 	double t_pack = 0;
 	for (int c = 0; c < K && rc == SRBA_OK; c++) {
-		Pool &pool = g_pool[c];
+		Pool &pool = pool_for(c);
 		const auto tp = now();
 		bt[c] = batch_create_impl(begin[c + 1] - begin[c], in + begin[c], want_dense ? -tcap : tcap, &pool, allow_cluster);
 		t_pack += ms(tp, now());
@@ -1045,7 +1214,7 @@ int srba_b200_optimize_batch(int32_t n, const srba_problem_t *const *in, srba_re
 	for (int c = 0; c < K; c++) {
 		if (!bt[c]) continue;
 		const auto tw = now();
-		if (cudaStreamSynchronize(g_pool[c].stream) != cudaSuccess && rc == SRBA_OK) rc = fail(SRBA_ERR_CUDA, std::string("kernel execution: ") + cudaGetErrorString(cudaGetLastError()));
+		if (cudaStreamSynchronize(g_pools.p[c].stream) != cudaSuccess && rc == SRBA_OK) rc = fail(SRBA_ERR_CUDA, std::string("kernel execution: ") + cudaGetErrorString(cudaGetLastError()));
 		const auto tu = now();
 		t_wait += ms(tw, tu);
 		if (rc == SRBA_OK) {
@@ -1057,7 +1226,8 @@ int srba_b200_optimize_batch(int32_t n, const srba_problem_t *const *in, srba_re
 				const int r = srba_b200_batch_unpack(b, i, o[i]);
 				if (r != SRBA_OK) { int expect = SRBA_OK; first_bad.compare_exchange_strong(expect, r); }
 			});
-			if (first_bad.load() != SRBA_OK) rc = first_bad.load();
+			if (first_bad.load() != SRBA_OK)
+				rc = fail(first_bad.load(), "a problem of the batch ended with a device-side error (srba_stats_t::status; SRBA_ERR_NON_FINITE: NaN/Inf inputs or a diverged iterate)");
 		}
 		t_unpack += ms(tu, now());
 		srba_b200_batch_destroy(bt[c]);

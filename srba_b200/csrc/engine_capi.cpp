@@ -73,7 +73,13 @@ void srba_engine_destroy(void *h) {
 	if (!H) return;
 	delete H->e2; delete H->e3; delete H;
 }
-void srba_engine_set_params(void *h, const srba_engine_params_t *p) { try { DISPATCH(h, E.set_params(*p)); } catch (const std::exception &e) { g_eng_err = e.what(); } }
+int srba_engine_set_params(void *h, const srba_engine_params_t *p) {  // validated BEFORE anything is assigned (host_engine.hpp set_params)
+	GUARD_BEGIN
+	if (!h || !p) throw std::runtime_error("srba_engine_set_params: null argument");
+	DISPATCH(h, E.set_params(*p));
+	return 0;
+	GUARD_END(-1)
+}
 
 int srba_engine_define_new_keyframe(void *h, uint64_t n_obs, const uint64_t *feat_id, const double *obs_data, const uint8_t *is_fixed,
                                     const uint8_t *is_unk, const double *frp, int run_local_optimization, uint64_t *out_kf_id,
@@ -176,6 +182,7 @@ int srba_flat_apply(void *h, const void *flat, const srba_result_t *res, srba_op
 	GUARD_BEGIN
 	srba_opt_info_t info;
 	std::memset(&info, 0, sizeof(info));
+	if (!h || !flat || !res) throw std::runtime_error("srba_flat_apply: null argument");
 	DISPATCH(h, E.apply(*static_cast<const FlatHandle *>(flat)->fp, *res, info));
 	if (out) *out = info;
 	return 0;
@@ -188,6 +195,11 @@ void srba_flat_ids(const void *flat, uint64_t *k2k_ids, uint64_t *lm_ids, uint64
 	if (obs_global_idx) std::copy(F.obs_global.begin(), F.obs_global.end(), obs_global_idx);
 	if (pair_from_to) for (size_t t = 0; t < F.pairs.size(); t++) { pair_from_to[2 * t] = F.pairs[t].first; pair_from_to[2 * t + 1] = F.pairs[t].second; }
 }
+uint64_t srba_flat_touched_edges(const void *flat, uint64_t *edge_ids, uint64_t cap) {
+	const FlatProblem &F = *static_cast<const FlatHandle *>(flat)->fp;
+	if (edge_ids) for (size_t i = 0; i < F.edge_ids_touched.size() && i < cap; i++) edge_ids[i] = F.edge_ids_touched[i];
+	return F.edge_ids_touched.size();
+}
 void srba_flat_destroy(void *flat) { delete static_cast<FlatHandle *>(flat); }
 
 void srba_engine_record_problems(void *h, int on) { static_cast<Handle *>(h)->base()->record_problems = on != 0; }
@@ -197,6 +209,10 @@ void *srba_engine_take_recorded(void *h, uint64_t i) {
 	if (i >= b->recorded.size() || !b->recorded[i]) return nullptr;
 	FlatHandle *fh = new FlatHandle();
 	fh->fp = std::move(b->recorded[i]);
+	// pop semantics: once every slot has been taken the list is emptied, so it does not grow (and get rescanned) forever
+	bool all_taken = true;
+	for (const auto &r : b->recorded) if (r) { all_taken = false; break; }
+	if (all_taken) b->recorded.clear();
 	return fh;
 }
 void srba_engine_trace(void *h, int trace_cap) { static_cast<Handle *>(h)->base()->trace_cap = trace_cap; }
@@ -215,12 +231,15 @@ uint64_t srba_engine_num_observations(void *h) { uint64_t r = 0; DISPATCH(h, r =
 int srba_engine_pose_nvals(void *h) { return static_cast<Handle *>(h)->e2 ? 3 : 12; }
 void srba_engine_get_edge(void *h, uint64_t id, uint64_t *from, uint64_t *to, double *inv_pose) {
 	DISPATCH(h, {
+		if (id >= E.k2k_edges.size()) { if (from) *from = srba_b200::INVALID_ID; if (to) *to = srba_b200::INVALID_ID; break; }
 		if (from) *from = E.k2k_edges[id].from;
 		if (to) *to = E.k2k_edges[id].to;
 		if (inv_pose) std::memcpy(inv_pose, E.k2k_edges[id].inv_pose.v, sizeof(E.k2k_edges[id].inv_pose.v));
 	});
 }
-void srba_engine_set_edge_pose(void *h, uint64_t id, const double *inv_pose) { DISPATCH(h, std::memcpy(E.k2k_edges[id].inv_pose.v, inv_pose, sizeof(E.k2k_edges[id].inv_pose.v))); }
+void srba_engine_set_edge_pose(void *h, uint64_t id, const double *inv_pose) {
+	DISPATCH(h, if (inv_pose && id < E.k2k_edges.size()) std::memcpy(E.k2k_edges[id].inv_pose.v, inv_pose, sizeof(E.k2k_edges[id].inv_pose.v)));
+}
 uint64_t srba_engine_num_unknown_lms(void *h) {
 	uint64_t r = 0;
 	DISPATCH(h, for (const auto &L : E.all_lms) r += (L.exists && !L.known) ? 1 : 0);
@@ -312,7 +331,7 @@ uint64_t srba_engine_get_num(void *h, uint64_t kf, uint64_t *target, double *pos
 void srba_engine_set_num(void *h, uint64_t src, uint64_t dst, const double *pose) {
 	DISPATCH(h, {
 		typedef typename std::remove_reference<decltype(E)>::type EngT;
-		std::memcpy(EngT::grow(E.num, src)[dst].v, pose, sizeof(double) * EngT::S);
+		if (pose && src < E.keyframes.size() && dst < E.keyframes.size()) std::memcpy(EngT::grow(E.num, src)[dst].v, pose, sizeof(double) * EngT::S);
 	});
 }
 int64_t srba_engine_get_all_edges_path(void *h, uint64_t from, uint64_t to, uint64_t *edge_ids, uint64_t cap) {

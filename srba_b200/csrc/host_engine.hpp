@@ -133,13 +133,15 @@ class RbaEngine : public EngineBase {
 	SE3 sensor_pose3, right_cam_R2L;
 
 	explicit RbaEngine(const srba_engine_params_t &p) { set_params(p); }
-	void set_params(const srba_engine_params_t &p) {
+	void set_params(const srba_engine_params_t &p) {  // checks first: a rejected parameter set leaves the engine untouched
+		SRBA_CHECK(p.pose_kind == (P == 3 ? SRBA_POSE_SE2 : SRBA_POSE_SE3));
+		if (P == 3) SRBA_CHECK(p.obs_kind == SRBA_OBS_RELPOSES2D && p.sensor_pose_kind == SRBA_SENSORPOSE_NONE);
+		if (P == 6) SRBA_CHECK(p.obs_kind == SRBA_OBS_CARTESIAN3D || p.obs_kind == SRBA_OBS_MONO || p.obs_kind == SRBA_OBS_STEREO);
+		SRBA_CHECK(p.max_tree_depth >= 1);
 		parameters = p;
 		O = obs_dims_of(p.obs_kind);
 		sensor_pose3 = SE3::from_xyzypr(p.sensor_pose);
 		right_cam_R2L = SE3::from_xyzquat(p.right_cam_pose).inverse();
-		if (P == 3) SRBA_CHECK(p.obs_kind == SRBA_OBS_RELPOSES2D && p.sensor_pose_kind == SRBA_SENSORPOSE_NONE);
-		if (P == 6) SRBA_CHECK(p.obs_kind != SRBA_OBS_RELPOSES2D);
 	}
 	template <class V> static typename V::value_type &grow(V &v, size_t i) { if (i >= v.size()) v.resize(i + 1); return v[i]; }
 

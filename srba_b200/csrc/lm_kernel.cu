@@ -1683,6 +1683,7 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 		sh.iter = 0; sh.stop = 0; sh.trials = 0; sh.accepted = 0; sh.relin = 0; sh.cholfail = 0; sh.cur = 0;
 		sh.need_outer = 1; sh.rho = 0;
 		v.stats->total_sqr_error_init = err0;
+		if (!isfinite(err0) || !isfinite(dmax)) sh.status = SRBA_ERR_NON_FINITE;  // non-finite inputs: reported, the loop below still mirrors the reference
 	}
 	const double MAX_LAMBDA = h->model.max_lambda;
 	const bool keep_grad = (OBSK != SRBA_OBS_RELPOSES2D) && no_schur_solver(h);  // relative graph-SLAM has no landmark unknowns: compiled out
@@ -1825,6 +1826,7 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 					sh.nu *= 2.0;
 					sh.stop = (sh.lambda > MAX_LAMBDA);
 					sh.rho = rho;  // <=0 or NaN: NaN also leaves the while in the reference ("rho<=0" false)
+					if (!isfinite(new_err) || !isfinite(rho)) sh.status = SRBA_ERR_NON_FINITE;  // a non-finite iterate
 					advance();
 				}
 			}

@@ -89,6 +89,13 @@ def graphslam_se2_tour(n_kfs=3000, seed=1, cell=100.0, ncells=3, step=2.0, max_t
     return dict(frames=frames, gt=gt, sigma_xy=sigma_xy, sigma_yaw=sig_yaw)
 
 
+def sample_keyframes(n_kfs, areas, first=100):
+    """The keyframes whose local areas make up a G4 batch: `areas` keyframes spread evenly over [first, n_kfs) -- the whole
+    tour, revisits and loop closures included (with repetition when the tour has fewer keyframes than `areas`)."""
+    first = min(first, max(0, n_kfs - 1))
+    return np.linspace(first, n_kfs - 1, areas).round().astype(int)
+
+
 def se2_noise_lambda(sigma_xy, sigma_yaw):
     """Constant information matrix diag(1/sxy^2, 1/sxy^2, 1/syaw^2) (CDatasetParser_RelGraphSLAM2D.h:45-52), row-major 3x3 in a 16-vector."""
     nl = np.zeros(16)

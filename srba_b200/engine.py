@@ -41,7 +41,9 @@ class FlatProblem:
         k2k, lms = np.zeros(p.n_unk_edges, np.uint64), np.zeros(p.n_unk_lms, np.uint64)
         obs, pairs = np.zeros(p.n_obs, np.uint64), np.zeros((p.n_pairs, 2), np.uint64)
         self.L.srba_flat_ids(self.h, ptr(k2k, C.c_uint64), ptr(lms, C.c_uint64), ptr(obs, C.c_uint64), ptr(pairs, C.c_uint64))
-        return dict(k2k_ids=k2k, lm_ids=lms, obs_global=obs, pairs=pairs)
+        touched = np.zeros(p.n_edges, np.uint64)
+        self.L.srba_flat_touched_edges(self.h, ptr(touched, C.c_uint64), p.n_edges)
+        return dict(k2k_ids=k2k, lm_ids=lms, obs_global=obs, pairs=pairs, edge_ids_touched=touched)
 
 
 class ResultBuffers:
@@ -114,8 +116,9 @@ class RbaEngine:
         return RuntimeError(self.L.srba_engine_last_error().decode())
 
     def set_params(self, params):
+        if self.L.srba_engine_set_params(self.h, C.byref(params)) != 0:
+            raise self._err()
         self.params = params
-        self.L.srba_engine_set_params(self.h, C.byref(params))
 
     def define_new_keyframe(self, feat_id, obs_data, is_fixed=None, is_unknown_with_init_val=None, feat_rel_pos=None,
                             run_local_optimization=True):
@@ -126,13 +129,16 @@ class RbaEngine:
         iu = np.zeros(n, np.uint8) if is_unknown_with_init_val is None else np.ascontiguousarray(is_unknown_with_init_val, dtype=np.uint8)
         frp = np.zeros((n, 3)) if feat_rel_pos is None else np.ascontiguousarray(feat_rel_pos, dtype=np.float64).reshape(n, 3)
         kf, ne = C.c_uint64(), C.c_uint64()
-        edges = (K.NewEdge * 16)()
+        cap = n + 2   # the edge-creation policy creates at most one edge per observed base area + the link to the submap centre
+        edges = (K.NewEdge * cap)()
         opt, stg1 = K.OptInfo(), K.OptInfo()
         rc = self.L.srba_engine_define_new_keyframe(self.h, n, ptr(feat_id, C.c_uint64), ptr(obs_data, C.c_double), ptr(is_fixed, C.c_uint8),
-                                                    ptr(iu, C.c_uint8), ptr(frp, C.c_double), int(run_local_optimization), C.byref(kf), edges, 16,
+                                                    ptr(iu, C.c_uint8), ptr(frp, C.c_double), int(run_local_optimization), C.byref(kf), edges, cap,
                                                     C.byref(ne), C.byref(opt), C.byref(stg1))
         if rc != 0:
             raise self._err()
+        if ne.value > cap:
+            raise RuntimeError("define_new_keyframe created %d edges, more than the %d-entry output buffer" % (ne.value, cap))
         return {"kf_id": kf.value,
                 "created_edges": [dict(id=e.id, has_approx_init_val=bool(e.has_approx_init_val),
                                        loopclosure_observer_kf=e.loopclosure_observer_kf, loopclosure_base_kf=e.loopclosure_base_kf)
@@ -289,7 +295,10 @@ class RbaEngine:
 
     def all_edges_path(self, frm, to):
         buf = np.zeros(64, np.uint64)
-        n = self.L.srba_engine_get_all_edges_path(self.h, frm, to, ptr(buf, C.c_uint64), 64)
+        n = self.L.srba_engine_get_all_edges_path(self.h, frm, to, ptr(buf, C.c_uint64), len(buf))
+        if n > len(buf):   # longer than the first guess: ask again with the reported length
+            buf = np.zeros(n, np.uint64)
+            n = self.L.srba_engine_get_all_edges_path(self.h, frm, to, ptr(buf, C.c_uint64), len(buf))
         return None if n < 0 else buf[:n].copy()
 
     def alloc_keyframe(self):

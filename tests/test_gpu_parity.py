@@ -51,6 +51,40 @@ def strict_prefix(trials, err_init):
     return len(trials)
 
 
+class ParityStats:
+    """What a trial-by-trial comparison covered: LM trials of the oracle, how many were decision-comparable (strict prefix),
+    how many accepted increments were compared per vector, and the worst relative increment error."""
+
+    def __init__(self):
+        self.total, self.compared, self.increments, self.worst = 0, 0, 0, 0.0
+
+    def __str__(self):
+        return ("%d of %d oracle LM trials decision-comparable (%.0f %%), %d accepted increments compared per vector, worst |d_gpu - d_oracle|_inf / |d_oracle|_inf = %.3e"
+                % (self.compared, self.total, 100.0 * self.compared / max(1, self.total), self.increments, self.worst))
+
+
+def compare_trials(tp, dp, to_trials, to_deltas, err_init, stats, where=""):
+    """Trial-by-trial comparison of one optimize_edges call on the strict prefix: lambda schedule, Cholesky ok / not PD,
+    accept / relinearise decisions identical; new total error of accepted trials 1e-6; EVERY accepted increment within
+    REL_TOL_INCREMENT of the oracle's, per vector (max-norm of the difference over max-norm of the oracle's increment)."""
+    n = min(strict_prefix(to_trials, err_init), len(tp), len(to_trials))
+    stats.total += len(to_trials)
+    stats.compared += n
+    np.testing.assert_allclose(tp[:n, 0], to_trials[:n, 0], rtol=1e-9, err_msg=str(where))   # lambda schedule
+    assert tp[:n, 1].tolist() == to_trials[:n, 1].tolist(), where                             # Cholesky ok / not PD
+    assert tp[:n, 4].tolist() == to_trials[:n, 4].tolist(), where                             # accepted
+    assert tp[:n, 5].tolist() == to_trials[:n, 5].tolist(), where                             # relinearised
+    acc = to_trials[:n, 4] > 0   # rejected trials may be wild steps of a near-singular system: decision only
+    np.testing.assert_allclose(tp[:n, 3][acc], to_trials[:n, 3][acc], rtol=1e-6, atol=1e-16, err_msg=str(where))  # new total error
+    for j in range(n):
+        if to_trials[j, 1] and to_trials[j, 4]:
+            e_ = rel_err(dp[j], to_deltas[j])
+            stats.worst = max(stats.worst, e_)
+            stats.increments += 1
+            assert e_ <= REL_TOL_INCREMENT, (where, j, e_)
+    return n
+
+
 def run_parallel(kw, frames, check_state_every=10, strict=True, state_tol=1e-6, inject=True):
     """Runs the oracle and the GPU engine keyframe by keyframe.  inject=True: after every keyframe the oracle's state is
     copied into the GPU engine, so EVERY optimize call of both starts from bit-identical inputs ("same inputs" parity);
@@ -58,7 +92,7 @@ def run_parallel(kw, frames, check_state_every=10, strict=True, state_tol=1e-6, 
     eo, ep = make_pair(kw)
     eo.trace_enable(True)
     ep.trace(96)
-    worst_delta, n_strict_trials = 0.0, 0
+    st = ParityStats()
     for k, f in enumerate(frames):
         eo.trace_clear()
         ro, rp = D.feed(eo, f), D.feed(ep, f)
@@ -72,27 +106,10 @@ def run_parallel(kw, frames, check_state_every=10, strict=True, state_tol=1e-6, 
         if io["num_lm_trials"] > 0:
             to = eo.traces()[-1]
             tp, dp = ep.last_trace()
-            n = min(strict_prefix(to["trials"], io["total_sqr_error_init"]), len(tp), len(to["trials"]))
             if strict:
-                assert n > 0 or len(to["trials"]) == 0 or not to["trials"][0, 1] or True
-                np.testing.assert_allclose(tp[:n, 0], to["trials"][:n, 0], rtol=1e-9)          # lambda schedule
-                assert tp[:n, 1].tolist() == to["trials"][:n, 1].tolist()                        # Cholesky ok / not PD
-                assert tp[:n, 4].tolist() == to["trials"][:n, 4].tolist()                        # accepted
-                assert tp[:n, 5].tolist() == to["trials"][:n, 5].tolist()                        # relinearised
-                acc = to["trials"][:n, 4] > 0   # rejected trials may be wild steps of a near-singular system: decision only
-                np.testing.assert_allclose(tp[:n, 3][acc], to["trials"][:n, 3][acc], rtol=1e-6, atol=1e-16)  # new total error
-                n_strict_trials += n
-                # increments delta_eps: <= 1e-6 relative (north_star).  The denominator is floored at the largest
-                # increment of the same call so that converged-phase increments (rounding noise) are judged on the
-                # scale at which the poses actually move.
-                scale = float(np.abs(to["deltas"][:max(n, 1)]).max())
-                for j in range(n):
-                    if to["trials"][j, 1] and to["trials"][j, 4]:
-                        e_ = float(np.abs(dp[j] - to["deltas"][j]).max() / max(scale, 1e-300))
-                        worst_delta = max(worst_delta, e_)
-                        assert e_ <= REL_TOL_INCREMENT, (k, j, e_)
+                compare_trials(tp, dp, to["trials"], to["deltas"], io["total_sqr_error_init"], st, where=k)
             same_inputs = abs(io["total_sqr_error_init"] - ip["total_sqr_error_init"]) <= 1e-12 * max(io["total_sqr_error_init"], 1e-30)
-            if len(tp) and to["trials"][0, 1] and tp[0, 1] and (strict or same_inputs):  # the first increment, strict per-vector sense
+            if len(tp) and to["trials"][0, 1] and tp[0, 1] and (strict or same_inputs):  # the first increment
                 assert rel_err(dp[0], to["deltas"][0]) <= REL_TOL_INCREMENT, (k, rel_err(dp[0], to["deltas"][0]))
             assert abs(io["total_sqr_error_final"] - ip["total_sqr_error_final"]) <= 1e-6 * max(io["total_sqr_error_final"], 1e-30) + 1e-20 or not strict, (k, io, ip)
         if strict and (k % check_state_every == 0 or k == len(frames) - 1):
@@ -107,7 +124,8 @@ def run_parallel(kw, frames, check_state_every=10, strict=True, state_tol=1e-6, 
                     assert rel_err(p2, p1) <= state_tol, (k, kf)
         if inject:
             inject_state(eo, ep)
-    return eo, ep, worst_delta, n_strict_trials
+    print("parity coverage:", st)
+    return eo, ep, st.worst, st.compared
 
 
 def test_se2_graph_slam_sequential_parity():
@@ -152,10 +170,12 @@ def test_se2_reference_fixture_submaps():
     assert [0, 10] in ft.tolist()   # tests/submaps_edge_init_values.cpp: the 10<=>0 loop-closure edge
 
 
-@pytest.mark.parametrize("obs_kind,name,std", [(1, "cartesian3d", 1e-3), (3, "stereo", 0.5), (2, "mono", 0.5)])
-def test_se3_landmark_slam_sequential_parity(obs_kind, name, std):
+@pytest.mark.parametrize("obs_kind,name,std,depth", [(1, "cartesian3d", 1e-3, 3), (1, "cartesian3d", 1e-3, 4), (1, "cartesian3d", 1e-3, 5),
+                                                     (3, "stereo", 0.5, 3), (3, "stereo", 0.5, 4), (3, "stereo", 0.5, 5), (2, "mono", 0.5, 3)])
+def test_se3_landmark_slam_sequential_parity(obs_kind, name, std, depth):
+    """max_tree_depth = max_optimize_depth = 3 / 4 / 5: BASELINE config #3 is depth 4, config #5 depth 5."""
     ds = D.landmark_slam_se3(n_kfs=40, n_lms=300, seed=2, obs_kind=name, lm_init_sigma=0.05 if name == "mono" else None)
-    kw = dict(pose_kind=1, obs_kind=obs_kind, noise_kind=0, noise_std=std, max_tree_depth=3, max_optimize_depth=3, submap_size=10,
+    kw = dict(pose_kind=1, obs_kind=obs_kind, noise_kind=0, noise_std=std, max_tree_depth=depth, max_optimize_depth=depth, submap_size=10,
               min_obs_to_loop_closure=4)
     if obs_kind != 1:
         kw.update(sensor_pose_kind=1, sensor_pose=ds["sensor_pose_xyzypr"], cam_left=ds["cam"], cam_right=ds["cam"],
@@ -164,7 +184,7 @@ def test_se3_landmark_slam_sequential_parity(obs_kind, name, std):
     # does not converge in 20 iterations, so only indexing, initial error and the first increment are compared there.
     strict = name != "mono"
     eo, ep, worst, ns = run_parallel(kw, ds["frames"], strict=strict, state_tol=1e-6 if strict else 1e-2)
-    print("%s: worst relative increment error %.3e over %d decision-comparable trials" % (name, worst, ns))
+    print("%s depth %d: worst relative increment error %.3e over %d decision-comparable trials" % (name, depth, worst, ns))
     io, _, po_ = eo.unknown_lms()
     ip, _, pp_ = ep.unknown_lms()
     assert io.tolist() == ip.tolist()
@@ -481,7 +501,8 @@ def test_se2_loop_closure_areas_parity():
 
 
 def test_full_size_bench_batch_properties():
-    """BASELINE config #4 at full size (the 256-area batch bench.py times): size-independent properties.  Every area's
+    """BASELINE config #4 at full size (the 256-area batch bench.py times, snapshotted from the product's own sequential run of
+    the 3 000-keyframe tour): size-independent properties.  Every area's
     final error is <= its initial error (LM only accepts decreasing steps), the batch is deterministic (two runs are
     bit-identical), the staged batch API and the pipelined host-buffer call agree bit for bit, and the flattened index
     structures are consistent (every observation row is covered by its Jacobian blocks)."""
@@ -491,7 +512,8 @@ def test_full_size_bench_batch_properties():
     from srba_b200 import _capi as K
     sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
     import bench
-    ds, eng, flats = bench.build_problems(seed=1, areas=256, n_kfs=700)
+    ds, eng, sets = bench.build_problems(seed=1, areas=256, n_kfs=3000)
+    flats = sets[256]
     assert len(flats) == 256
     for f in flats:
         p = f.p
@@ -546,3 +568,167 @@ def test_whole_map_single_area_parity():
     _, _, lo = eo.unknown_lms()
     _, _, lp = ep.unknown_lms()
     assert rel_err(lp, lo) <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ execution modes of heavy SE(3) areas
+def _plan(flat):
+    import ctypes as C
+    from srba_b200 import _capi as K
+    out = (C.c_int64 * 8)()
+    assert K.lib().srba_b200_problem_plan(flat.problem, out) == 0
+    return list(out)
+
+
+@pytest.fixture
+def one_cta_per_area():
+    """Forces the execution mode BASELINE config #5 runs in (more than 36 heavy areas in a batch): ONE CTA per heavy area, its
+    arrays beyond the 220 KB arena in the global workspace -- never an 8-CTA cluster team."""
+    from srba_b200 import _capi as K
+    old = K.set_option("cluster", 0)
+    yield
+    K.set_option("cluster", old)
+
+
+@pytest.mark.parametrize("obs_kind,name,std", [(1, "cartesian3d", 1e-3), (3, "stereo", 0.5)])
+def test_heavy_se3_areas_one_cta_mode_sequential_parity(one_cta_per_area, obs_kind, name, std):
+    """Heavy depth-5 areas (thousands of Jacobian blocks: JA alone overflows one SM's shared memory) solved by ONE 1024-thread CTA
+    each with the overflow in the global workspace == the mode of the config #5 number.  A one-problem call would pick the
+    cluster team; the option pins the other mode.  Trial by trial against the oracle, same bars as every sequential test."""
+    ds = D.landmark_slam_se3(n_kfs=36, n_lms=700, seed=11, obs_kind=name)
+    kw = dict(pose_kind=1, obs_kind=obs_kind, noise_kind=0, noise_std=std, max_tree_depth=5, max_optimize_depth=5, submap_size=10, min_obs_to_loop_closure=4)
+    if obs_kind != 1:
+        kw.update(sensor_pose_kind=1, sensor_pose=ds["sensor_pose_xyzypr"], cam_left=ds["cam"], cam_right=ds["cam"],
+                  right_cam_pose=[ds["baseline"], 0, 0, 1, 0, 0, 0], use_robust_kernel=1)
+    eo, ep, worst, ns = run_parallel(kw, ds["frames"])
+    flat = ep.flatten_local_area(len(ds["frames"]) - 1, 5)
+    plan = _plan(flat)
+    # plan[4]: solver + 2 * cluster; plan[6]: workspace arrays on chip (of 27): a heavy area leaves several of them in global memory
+    assert plan[4] < 2 and plan[6] < 27 and flat.p.n_blkA * ds["frames"][0]["obs"].shape[1] * 6 * 8 > 220 * 1024, (plan, flat.sizes())
+    print("%s heavy one-CTA mode: n_blkA %d, %d / 27 workspace arrays on chip; worst rel. increment error %.3e over %d decision-comparable trials"
+          % (name, flat.p.n_blkA, plan[6], worst, ns))
+    assert ns > 30
+    _, _, po_ = eo.unknown_lms()
+    _, _, pp_ = ep.unknown_lms()
+    assert rel_err(pp_, po_) <= 1e-6
+
+
+def _restore(eng, edge_poses, lm_ids, lm_pos):
+    for i in range(len(edge_poses)):
+        eng.set_edge_pose(i, edge_poses[i])
+    for i, q in zip(lm_ids, lm_pos):
+        eng.set_lm_pos(int(i), q)
+
+
+def test_g5_mode_batch_of_heavy_areas_vs_oracle():
+    """BASELINE config #5 at a size the oracle finishes in seconds: one SE(3) + Cartesian3D map built WITHOUT optimisation, the depth-5
+    local areas of every 6th keyframe -- more than 36 heavy areas, so the batch call runs them one CTA per area with the overflow in
+    the global workspace (no cluster teams: the mode of the 1 000-area number) -- as independent problems with snapshot semantics
+    (SURVEY 8e).  Each area against the oracle started from the same snapshot: counts bit-exact, initial error 1e-9, decisions and
+    increments trial by trial on the strict prefix, final unknown edges and landmarks <= 1e-6."""
+    depth = 5
+    ds = D.landmark_slam_se3(n_kfs=260, n_lms=2600, seed=12, obs_kind="cartesian3d")
+    kw = dict(pose_kind=1, obs_kind=1, noise_kind=0, noise_std=1e-3, max_tree_depth=depth, max_optimize_depth=depth, submap_size=10, min_obs_to_loop_closure=4)
+    eo, ep = make_pair(kw)
+    for f in ds["frames"]:
+        D.feed(eo, f, run_local_optimization=False)
+        D.feed(ep, f, run_local_optimization=False)
+    inject_state(eo, ep)
+    _, edges0 = eo.edges()
+    lm_ids, _, lm0 = eo.unknown_lms()
+    roots = list(range(17, 260, 6))
+    flats = [ep.flatten_local_area(r, depth) for r in roots]
+    plans = [_plan(f) for f in flats]
+    assert len(flats) > 36 and all(p[4] < 2 for p in plans) and sum(p[6] < 27 for p in plans) > 36, [p[4:7] for p in plans]
+    b = sb.Batch(flats, trace_cap=96)
+    b.upload(); b.run(); b.download()
+    eo.trace_enable(True)
+    st = ParityStats()
+    worst_edge = worst_lm = 0.0
+    for i, (r, flat) in enumerate(zip(roots, flats)):
+        _restore(eo, edges0, lm_ids, lm0)   # snapshot semantics: every area reads the pre-batch state
+        eo.trace_clear()
+        io = eo.optimize_local_area(r, depth)
+        res = b.unpack(i)
+        p = flat.p
+        assert (io["num_kf2kf_edges_optimized"], io["num_kf2lm_edges_optimized"], io["num_observations"], io["num_jacobians"]) == \
+               (p.n_unk_edges, p.n_unk_lms, p.n_total_obs_rows, p.n_blkA + p.n_blkF), (r, io, flat.sizes())
+        assert abs(io["total_sqr_error_init"] - res.stats["total_sqr_error_init"]) <= 1e-9 * io["total_sqr_error_init"], r
+        to = eo.traces()[-1]
+        tp, dp = res.trace_rows()
+        n = compare_trials(tp, dp, to["trials"], to["deltas"], io["total_sqr_error_init"], st, where=r)
+        if n == len(to["trials"]):   # every trial decision-comparable: same trial count, same final state
+            assert res.stats["num_trials"] == io["num_lm_trials"], r
+        assert abs(io["total_sqr_error_final"] - res.stats["total_sqr_error_final"]) <= 1e-6 * io["total_sqr_error_final"], r
+        ids = flat.ids()
+        _, eposes = eo.edges()
+        worst_edge = max(worst_edge, rel_err(res.edge_pose, eposes[ids["k2k_ids"].astype(int)]))
+        all_ids, _, lpos = eo.unknown_lms()
+        pos_of = dict(zip(all_ids.tolist(), lpos))
+        worst_lm = max(worst_lm, rel_err(res.lm_pos, np.array([pos_of[int(j)] for j in ids["lm_ids"]])))
+    print("G5-mode batch: %d heavy areas (n_p %d..%d, n_f %d..%d, n_blkA up to %d); %s; final edges %.2e, landmarks %.2e"
+          % (len(flats), min(f.p.n_unk_edges for f in flats), max(f.p.n_unk_edges for f in flats), min(f.p.n_unk_lms for f in flats),
+             max(f.p.n_unk_lms for f in flats), max(f.p.n_blkA for f in flats), st, worst_edge, worst_lm))
+    assert st.compared > 100 and worst_edge <= 1e-6 and worst_lm <= 1e-6
+
+
+def g4_fixture_flats(ep_kw=None):
+    """The 256 problems of bench.py's default batch, rebuilt from tests/golden/g4_tour3000_states.npz: the product's host engine
+    builds the graph of the 3 000-keyframe tour (no optimisation), and at every sampled keyframe the touched k2k edges get the
+    oracle's pre-optimisation poses before the local area is flattened -- bit-identical numeric inputs to what the oracle solved."""
+    import os
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "g4_tour3000_states.npz"))
+    ds = D.graphslam_se2_tour(int(fx["kfs"]), seed=int(fx["seed"]))
+    kw = dict(S2, noise_lambda=D.se2_noise_lambda(ds["sigma_xy"], ds["sigma_yaw"]))
+    ep = sb.RbaEngine(sb.default_engine_params(**kw))
+    at = {int(k): i for i, k in enumerate(fx["kf"])}
+    flats = [None] * len(at)
+    for k, f in enumerate(ds["frames"]):
+        D.feed(ep, f, run_local_optimization=False)
+        if k in at:
+            i = at[k]
+            for e, pose in zip(fx["edge_id"][fx["edge_ptr"][i]:fx["edge_ptr"][i + 1]], fx["edge_in"][fx["edge_ptr"][i]:fx["edge_ptr"][i + 1]]):
+                ep.set_edge_pose(int(e), pose)
+            flats[i] = ep.flatten_local_area(k, 3)
+    return fx, ep, flats
+
+
+def test_bench_batch_vs_oracle_fixture():
+    """The exact batch bench.py times (256 areas sampled over the 3 000-keyframe G1 tour, loop closures included) against the
+    ORACLE's answers on bit-identical inputs (committed fixture, generated by tests/golden/make_g4_states.py: the oracle needs
+    ~25 minutes for the tour).  Per area: same unknowns, initial error 1e-9, lambda / accept / relinearise decisions on the strict
+    prefix, first increment and final unknown edges <= 1e-6, same trial count whenever every trial is decision-comparable."""
+    fx, ep, flats = g4_fixture_flats()
+    assert len(flats) == 256
+    b = sb.Batch(flats, trace_cap=96)
+    b.upload(); b.run(); b.download()
+    st = ParityStats()
+    worst_edge = worst_d0 = 0.0
+    same_count = 0
+    for i, flat in enumerate(flats):
+        res = b.unpack(i)
+        ids = flat.ids()
+        assert ids["k2k_ids"].astype(np.int64).tolist() == fx["unk_id"][fx["unk_ptr"][i]:fx["unk_ptr"][i + 1]].tolist(), i
+        assert flat.p.n_total_obs_rows == int(fx["n_obs"][i])
+        assert abs(res.stats["total_sqr_error_init"] - fx["err_init"][i]) <= 1e-9 * fx["err_init"][i], i
+        to = fx["trials"][fx["trials_ptr"][i]:fx["trials_ptr"][i + 1]]
+        tp, dp = res.trace_rows()
+        n = min(strict_prefix(to, fx["err_init"][i]), len(tp), len(to))
+        st.total += len(to); st.compared += n
+        np.testing.assert_allclose(tp[:n, 0], to[:n, 0], rtol=1e-9)
+        for col in (1, 4, 5):
+            assert tp[:n, col].tolist() == to[:n, col].tolist(), (i, col)
+        acc = to[:n, 4] > 0
+        np.testing.assert_allclose(tp[:n, 3][acc], to[:n, 3][acc], rtol=1e-6, atol=1e-16)
+        d0 = fx["delta0"][fx["delta0_ptr"][i]:fx["delta0_ptr"][i + 1]]
+        if n > 0 and to[0, 1]:
+            worst_d0 = max(worst_d0, rel_err(dp[0], d0))
+            st.increments += 1
+        if n == len(to):
+            assert res.stats["num_trials"] == int(fx["num_trials"][i]), i
+            same_count += 1
+        assert abs(res.stats["total_sqr_error_final"] - fx["err_final"][i]) <= 1e-6 * fx["err_final"][i], i
+        worst_edge = max(worst_edge, rel_err(res.edge_pose, fx["unk_out"][fx["unk_ptr"][i]:fx["unk_ptr"][i + 1]]))
+    st.worst = worst_d0
+    print("bench batch vs oracle fixture: %s; %d areas with every trial comparable (identical trial counts); final unknown edges %.2e"
+          % (st, same_count, worst_edge))
+    assert worst_d0 <= REL_TOL_INCREMENT and worst_edge <= 1e-6 and st.compared > 2000
