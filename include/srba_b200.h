@@ -190,9 +190,12 @@ void srba_b200_batch_algorithmic_bytes(const srba_batch_t *b, double out[5]);
 
 /* Host-only: how the packer would lay problem `in` out.  out[0..7] = image bytes, global workspace bytes, result bytes,
  * shared-memory bytes planned (solver scratch + on-chip arena), solver (0 block-sparse L D L^t, 1 dense blocked; +2 when
- * the problem is solved by an 8-CTA cluster),
+ * the problem is solved by an 8-CTA cluster, +4 by the grid-wide wave pipeline),
  * image arrays on chip, workspace arrays on chip, shared-memory budget of the model's kernel.  No device needed. */
 int srba_b200_problem_plan(const srba_problem_t *in, int64_t out[8]);
+/* The same for problem i of a batch, as the batch really planned it (execution modes depend on the batch: how many heavy
+ * areas it holds).  out[4] = solver + 2 * (8-CTA cluster team) + 4 * (grid-wide wave pipeline). */
+int srba_b200_batch_problem_plan(const srba_batch_t *b, int32_t i, int64_t out[8]);
 
 /* Host-only: size of the block-sparse L D L^t schedule the packer plans for `in` (its own elimination order and on-chip budget):
  * out[0..3] = 3x3 tiles of the filled pattern incl. the right-hand side, tile updates per factorisation, barrier-separated phases,
@@ -212,6 +215,15 @@ int srba_b200_problem_ldl_counts(const srba_problem_t *in, int64_t out[4]);
  * Call with NULL arrays to get the counts first. */
 int srba_b200_debug_ldl_schedule(const srba_problem_t *in, int32_t counts[6], int32_t *row, int32_t *tile_ij, int32_t *src, int32_t *upd,
                                  int32_t *orow, int32_t *phase, int32_t cap_tiles, int32_t cap_upd, int32_t max_tiles_on_chip);
+
+/* Host-only (tests): the LEVEL schedule the packer ships with problems that run in the grid-wide wave pipeline (multi-CTA solver).
+ * Tile rows sorted by elimination level.  counts[6] = {NTR, tiles, levels, destinations, contributions, ok};
+ * row2[2*(NTR+1)] = {first tile, end tile} per row (+ sentinel); tile_ij / src / orow as in srba_b200_debug_ldl_schedule;
+ * lv[2*(levels+1)] = {first row, first destination} per level (+ sentinel); gu = [destination tile (n_dst) | contribution pointer
+ * (n_dst+1) | (tile(k,a), tile(k,b)) per contribution]: destination T(a,b) -= sum T(k,a)^t inv(D_k) T(k,b) over its contributions.
+ * Call with NULL arrays to get the counts first. */
+int srba_b200_debug_level_schedule(const srba_problem_t *in, int32_t counts[6], int32_t *row2, int32_t *tile_ij, int32_t *src, int32_t *orow, int32_t *lv,
+                                   int32_t *gu);
 
 /* ---- Global diagnostics: RbaEngine::eval_overall_squared_error (impl/eval_overall_error.h:15-137) and the
  * numeric half of create_complete_spanning_tree (impl/spantree_create_complete.h:91-125).
@@ -246,7 +258,8 @@ void srba_b200_release_workspace(void);
  *   "blocked"   0 auto | 1                   dense blocked Cholesky instead of the block-sparse L D L^t
  *   "wide"      0 auto | 1                   3-int solver update descriptors
  *   "chunks"    1..8                         pipelined chunks of srba_b200_optimize_batch (default 4)
- *   "big_se2"  -1 auto | 0 never | 1 always  the large-CTA kernel for SE(2) areas that overflow the small kernel's arena
+ *   "wave"     -1 auto | 0 never | 1 always  the grid-wide lock-step pipeline: one kernel launch per LM stage over ALL areas
+ *                                            (auto: areas whose arrays overflow one CTA's shared-memory arena)
  * set returns SRBA_OK or SRBA_ERR_BAD_ARGUMENT (unknown name); get returns INT32_MIN for an unknown name. */
 int srba_b200_set_option(const char *name, int32_t value);
 int32_t srba_b200_get_option(const char *name);

@@ -60,6 +60,10 @@ int srba_engine_define_new_keyframe(void *h, uint64_t n_obs, const uint64_t *fea
                                     srba_opt_info_t *out_opt, srba_opt_info_t *out_opt_stg1);
 int srba_engine_optimize_local_area(void *h, uint64_t root, uint64_t win_size, int optimize_k2k_edges, int optimize_landmarks,
                                     uint64_t max_visitable_kf_id, uint64_t dont_optimize_landmarks_seen_less_than_n_times, srba_opt_info_t *out);
+/* optimize_local_area(root, win_size, out, default TOptimizeLocalAreaParams, observation_indices_to_optimize) (RbaEngine.h:235-241;
+ * impl/optimize_edges.h:218-234): the residual rows are the listed observations (indices into all_observations, repeats counted).  As in
+ * the reference the list must contain every observation of the selected unknowns (else -1: the ASSERT_ of compute_minus_gradient.h:55). */
+int srba_engine_optimize_local_area_obs(void *h, uint64_t root, uint64_t win_size, uint64_t n_obs_idx, const uint64_t *obs_idx, srba_opt_info_t *out);
 int srba_engine_optimize_edges(void *h, uint64_t n_k2k, const uint64_t *k2k, uint64_t n_lm, const uint64_t *lms, srba_opt_info_t *out);
 
 /* Unknown selection of optimize_local_area WITHOUT optimising (impl/bfs_visitor.h + VisitorOptimizeLocalArea). Returns counts. */
@@ -71,6 +75,7 @@ int srba_engine_select_local_area(void *h, uint64_t root, uint64_t win_size, uin
  * into the engine exactly as optimize_edges would have (edges, landmarks, numeric spanning tree, validity, info matrices). */
 void *srba_engine_flatten(void *h, uint64_t n_k2k, const uint64_t *k2k, uint64_t n_lm, const uint64_t *lms);
 void *srba_engine_flatten_local_area(void *h, uint64_t root, uint64_t win_size);
+void *srba_engine_flatten_local_area_obs(void *h, uint64_t root, uint64_t win_size, uint64_t n_obs_idx, const uint64_t *obs_idx); /* with observation_indices_to_optimize */
 const srba_problem_t *srba_flat_problem(const void *flat);
 int srba_flat_apply(void *h, const void *flat, const srba_result_t *res, srba_opt_info_t *out);
 void srba_flat_ids(const void *flat, uint64_t *k2k_ids, uint64_t *lm_ids, uint64_t *obs_global_idx, uint64_t *pair_from_to);

@@ -174,6 +174,23 @@ int orc_optimize_local_area(void *h, uint64_t root, uint64_t win_size, int optim
 	GUARD_END(-1)
 }
 
+int orc_optimize_local_area_obs(void *h, uint64_t root, uint64_t win_size, uint64_t n_obs_idx, const uint64_t *obs_idx, orc_opt_info_t *out) {
+	GUARD_BEGIN
+	DISPATCH(h, {
+		typedef typename std::remove_reference<decltype(E)>::type EngT;
+		std::vector<size_t> lst(obs_idx, obs_idx + n_obs_idx);
+		orc_opt_info_t info;
+		std::memset(&info, 0, sizeof(info));
+		E.optimize_local_area(root, static_cast<unsigned int>(std::min<uint64_t>(win_size, 0xffffffffu)), info, typename EngT::TOptimizeLocalAreaParams(), lst);
+		if (out) *out = info;
+	});
+	return 0;
+	GUARD_END(-1)
+}
+void orc_set_num(void *h, uint64_t src, uint64_t dst, const double *pose) {
+	DISPATCH(h, E.spanning_tree.num[src][dst].pose.fromFlat(pose));
+}
+
 int orc_optimize_edges(void *h, uint64_t n_k2k, const uint64_t *k2k, uint64_t n_lm, const uint64_t *lms, orc_opt_info_t *out) {
 	GUARD_BEGIN
 	DISPATCH(h, {

@@ -72,6 +72,9 @@ int orc_optimize_local_area(void *h, uint64_t root, uint64_t win_size, int optim
                             int optimize_landmarks, uint64_t max_visitable_kf_id,
                             uint64_t dont_optimize_landmarks_seen_less_than_n_times, orc_opt_info_t *out);
 /* protected optimize_edges (impl/optimize_edges.h:44-793) */
+/* optimize_local_area(root, win_size, out, default params, observation_indices_to_optimize)  (RbaEngine.h:235-241) */
+int orc_optimize_local_area_obs(void *h, uint64_t root, uint64_t win_size, uint64_t n_obs_idx, const uint64_t *obs_idx, orc_opt_info_t *out);
+void orc_set_num(void *h, uint64_t src, uint64_t dst, const double *pose); /* spanning_tree.num[src][dst].pose (test support) */
 int orc_optimize_edges(void *h, uint64_t n_k2k, const uint64_t *k2k, uint64_t n_lm, const uint64_t *lms,
                        orc_opt_info_t *out);
 

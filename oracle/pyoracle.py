@@ -86,6 +86,9 @@ def lib(variant=""):
                                           C.POINTER(OptInfo), C.POINTER(OptInfo)]
     L.orc_optimize_local_area.restype = C.c_int
     L.orc_optimize_local_area.argtypes = [vp, u64, u64, C.c_int, C.c_int, u64, u64, C.POINTER(OptInfo)]
+    L.orc_optimize_local_area_obs.restype = C.c_int
+    L.orc_optimize_local_area_obs.argtypes = [vp, u64, u64, u64, pu64, C.POINTER(OptInfo)]
+    L.orc_set_num.argtypes = [vp, u64, u64, C.POINTER(C.c_double)]
     L.orc_optimize_edges.restype = C.c_int
     L.orc_optimize_edges.argtypes = [vp, u64, pu64, u64, pu64, C.POINTER(OptInfo)]
     L.orc_alloc_keyframe.restype = u64
@@ -222,8 +225,14 @@ class OracleEngine:
                 "optimize_results": opt.as_dict(), "optimize_results_stg1": stg1.as_dict()}
 
     def optimize_local_area(self, root, win_size, optimize_k2k_edges=True, optimize_landmarks=True, max_visitable_kf_id=INVALID,
-                            dont_optimize_landmarks_seen_less_than_n_times=2):
+                            dont_optimize_landmarks_seen_less_than_n_times=2, observation_indices_to_optimize=None):
         o = OptInfo()
+        if observation_indices_to_optimize is not None and len(observation_indices_to_optimize):
+            lst = np.ascontiguousarray(observation_indices_to_optimize, dtype=np.uint64)
+            rc = self.L.orc_optimize_local_area_obs(self.h, root, win_size, len(lst), _p(lst, C.c_uint64), C.byref(o))
+            if rc != 0:
+                raise OracleError(self.L.orc_last_error().decode())
+            return o.as_dict()
         rc = self.L.orc_optimize_local_area(self.h, root, win_size, int(optimize_k2k_edges), int(optimize_landmarks), max_visitable_kf_id,
                                             dont_optimize_landmarks_seen_less_than_n_times, C.byref(o))
         if rc != 0:
@@ -330,6 +339,10 @@ class OracleEngine:
     def set_lm_pos(self, lm_id, pos):
         p = np.ascontiguousarray(pos, dtype=np.float64)
         self.L.orc_set_lm_pos(self.h, lm_id, _p(p, C.c_double))
+
+    def set_num(self, src, dst, pose):
+        p = np.ascontiguousarray(pose, dtype=np.float64)
+        self.L.orc_set_num(self.h, src, dst, _p(p, C.c_double))
 
     def next_edge(self, kf):
         n = self.L.orc_get_next_edge(self.h, kf, None, None, None, 0)

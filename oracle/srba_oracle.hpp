@@ -139,17 +139,47 @@ inline bool fullpiv_lu_inverse3(const double *Ain, double *inv) {
 // A is n x n row-major, only the upper triangle is read; U overwrites it (A = U^T U).
 // Returns false when a pivot is <= 0 (Eigen's llt_inplace: "if (x<=0) return k").
 // ---------------------------------------------------------------------------------------------
+// Blocked right-looking evaluation order (cache-friendly, vectorisable -- Eigen's own LLT is blocked too), arranged so that every
+// element receives exactly the operations of the textbook recurrence  u_kj = (a_kj - sum_{r<k} u_rk u_rj) / u_kk  with r ASCENDING:
+// bit-identical to the unblocked loop, ~10x faster on the 1 000-2 000-dim systems of loop-closure areas.  (Entries below the
+// diagonal are scratch: never read.)
 inline bool dense_llt_upper(std::vector<double> &A, size_t n) {
-	for (size_t k = 0; k < n; k++) {
-		double x = A[k * n + k];
-		for (size_t r = 0; r < k; r++) x -= A[r * n + k] * A[r * n + k];
-		if (x <= 0) return false;
-		x = std::sqrt(x);
-		A[k * n + k] = x;
-		for (size_t j = k + 1; j < n; j++) {
-			double s = A[k * n + j];
-			for (size_t r = 0; r < k; r++) s -= A[r * n + k] * A[r * n + j];
-			A[k * n + j] = s / x;
+	const size_t B = 48;
+	double *a = A.data();
+	for (size_t kb = 0; kb < n; kb += B) {
+		const size_t ke = std::min(kb + B, n);
+		for (size_t k = kb; k < ke; k++) {  // rows of the panel: contributions of the panel's earlier rows, then the pivot
+			double *rk = a + k * n;
+			for (size_t r = kb; r < k; r++) {
+				const double *rr = a + r * n;
+				const double m = rr[k];
+				for (size_t j = k; j < n; j++) rk[j] -= m * rr[j];
+			}
+			double x = rk[k];
+			if (x <= 0) return false;
+			x = std::sqrt(x);
+			rk[k] = x;
+			for (size_t j = k + 1; j < n; j++) rk[j] = rk[j] / x;
+		}
+		size_t i = ke;
+		for (; i + 4 <= n; i += 4) {  // trailing rows, four at a time (each panel row is streamed once per four rows)
+			double *r0 = a + i * n, *r1 = r0 + n, *r2 = r1 + n, *r3 = r2 + n;
+			for (size_t r = kb; r < ke; r++) {
+				const double *rr = a + r * n;
+				const double m0 = rr[i], m1 = rr[i + 1], m2 = rr[i + 2], m3 = rr[i + 3];
+				for (size_t j = i; j < n; j++) {
+					const double u = rr[j];
+					r0[j] -= m0 * u; r1[j] -= m1 * u; r2[j] -= m2 * u; r3[j] -= m3 * u;
+				}
+			}
+		}
+		for (; i < n; i++) {
+			double *ri = a + i * n;
+			for (size_t r = kb; r < ke; r++) {
+				const double *rr = a + r * n;
+				const double m = rr[i];
+				for (size_t j = i; j < n; j++) ri[j] -= m * rr[j];
+			}
 		}
 	}
 	return true;
@@ -1872,10 +1902,12 @@ struct Engine {
 			}
 		}
 	}
-	void optimize_local_area(TKeyFrameID root_id, unsigned int win_size, orc_opt_info_t &out_info, const TOptimizeLocalAreaParams &params = TOptimizeLocalAreaParams()) {
+	void optimize_local_area(TKeyFrameID root_id, unsigned int win_size, orc_opt_info_t &out_info, const TOptimizeLocalAreaParams &params = TOptimizeLocalAreaParams(),
+	                         const std::vector<size_t> &observation_indices_to_optimize = std::vector<size_t>()) {  // RbaEngine.h:235-241
 		std::vector<size_t> k2k_edges_to_optimize, lm_IDs_to_optimize;
 		select_local_area(root_id, win_size, params, k2k_edges_to_optimize, lm_IDs_to_optimize);
-		if (!k2k_edges_to_optimize.empty() || !lm_IDs_to_optimize.empty()) optimize_edges(k2k_edges_to_optimize, lm_IDs_to_optimize, out_info);
+		if (!k2k_edges_to_optimize.empty() || !lm_IDs_to_optimize.empty())
+			optimize_edges(k2k_edges_to_optimize, lm_IDs_to_optimize, out_info, observation_indices_to_optimize);  // optimize_local_area.h:54
 	}
 
 	// ------------------------------------------------------------------ impl/jacobians.h
@@ -2093,7 +2125,8 @@ struct Engine {
 	}
 
 	// ------------------------------------------------------------------ impl/optimize_edges.h:44-793
-	void optimize_edges(const std::vector<size_t> &run_k2k_edges_in, const std::vector<size_t> &run_feat_ids_in, orc_opt_info_t &out_info) {
+	void optimize_edges(const std::vector<size_t> &run_k2k_edges_in, const std::vector<size_t> &run_feat_ids_in, orc_opt_info_t &out_info,
+	                    const std::vector<size_t> &in_observation_indices_to_optimize = std::vector<size_t>()) {
 		const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();  // m_profiler.enter("opt") :56
 		struct Leave {
 			Engine *e; std::chrono::steady_clock::time_point t0;
@@ -2146,6 +2179,15 @@ struct Engine {
 		// C. involved observations (:171-234).  NOTE the dAp loop does NOT de-duplicate.
 		std::map<size_t, size_t> obs_global_idx2residual_idx;
 		std::vector<TObsUsed> involved_obs;
+		if (!in_observation_indices_to_optimize.empty()) {  // :218-234: use only those observations, in the caller's order
+			for (size_t i = 0; i < in_observation_indices_to_optimize.size(); i++) {
+				const size_t global_obs_idx = in_observation_indices_to_optimize[i];
+				ORC_ASSERT(global_obs_idx < all_observations.size());
+				obs_global_idx2residual_idx[global_obs_idx] = involved_obs.size();
+				TObsUsed o = {global_obs_idx, &all_observations[global_obs_idx]};
+				involved_obs.push_back(o);
+			}
+		} else
 		for (size_t i = 0; i < nUnknowns_k2k; i++)
 			for (typename colAp_t::iterator it = dh_dAp[i]->begin(); it != dh_dAp[i]->end(); ++it) {
 				const size_t global_obs_idx = it->first;
@@ -2153,6 +2195,7 @@ struct Engine {
 				TObsUsed o = {global_obs_idx, &all_observations[global_obs_idx]};
 				involved_obs.push_back(o);
 			}
+		if (in_observation_indices_to_optimize.empty())
 		for (size_t i = 0; i < nUnknowns_k2f; i++)
 			for (typename colF_t::iterator it = dh_df[i]->begin(); it != dh_df[i]->end(); ++it) {
 				const size_t global_obs_idx = it->first;

@@ -86,11 +86,11 @@ class NewEdge(C.Structure):
 EXPORTED_SYMBOLS = [
     "srba_b200_optimize", "srba_b200_optimize_batch", "srba_b200_batch_create", "srba_b200_batch_upload", "srba_b200_batch_run",
     "srba_b200_batch_download", "srba_b200_batch_unpack", "srba_b200_batch_destroy", "srba_b200_batch_h2d_bytes", "srba_b200_batch_d2h_bytes",
-    "srba_b200_batch_kernel_launches", "srba_b200_batch_stage_cycles", "srba_b200_problem_plan", "srba_b200_problem_ldl_counts", "srba_b200_debug_ldl_schedule", "srba_b200_batch_algorithmic_bytes", "srba_b200_eval_overall_squared_error", "srba_b200_last_error", "srba_b200_device_count", "srba_b200_version",
+    "srba_b200_batch_kernel_launches", "srba_b200_batch_stage_cycles", "srba_b200_problem_plan", "srba_b200_batch_problem_plan", "srba_b200_problem_ldl_counts", "srba_b200_debug_ldl_schedule", "srba_b200_debug_level_schedule", "srba_b200_batch_algorithmic_bytes", "srba_b200_eval_overall_squared_error", "srba_b200_last_error", "srba_b200_device_count", "srba_b200_version",
     "srba_b200_release_workspace", "srba_b200_set_option", "srba_b200_get_option",
     "srba_engine_default_params", "srba_engine_create", "srba_engine_destroy", "srba_engine_set_params", "srba_engine_define_new_keyframe",
-    "srba_engine_optimize_local_area", "srba_engine_optimize_edges", "srba_engine_select_local_area", "srba_engine_flatten",
-    "srba_engine_flatten_local_area", "srba_flat_problem", "srba_flat_apply", "srba_flat_ids", "srba_flat_touched_edges", "srba_flat_destroy",
+    "srba_engine_optimize_local_area", "srba_engine_optimize_local_area_obs", "srba_engine_optimize_edges", "srba_engine_select_local_area", "srba_engine_flatten",
+    "srba_engine_flatten_local_area", "srba_engine_flatten_local_area_obs", "srba_flat_problem", "srba_flat_apply", "srba_flat_ids", "srba_flat_touched_edges", "srba_flat_destroy",
     "srba_engine_record_problems", "srba_engine_num_recorded", "srba_engine_take_recorded", "srba_engine_trace", "srba_engine_last_trace",
     "srba_engine_num_keyframes", "srba_engine_num_edges", "srba_engine_num_observations", "srba_engine_pose_nvals", "srba_engine_get_edge",
     "srba_engine_set_edge_pose", "srba_engine_num_unknown_lms", "srba_engine_get_unknown_lms", "srba_engine_set_lm_pos",
@@ -134,8 +134,12 @@ def lib():
     pi32 = C.POINTER(C.c_int32)
     L.srba_b200_debug_ldl_schedule.restype = C.c_int
     L.srba_b200_debug_ldl_schedule.argtypes = [pp, pi32, pi32, pi32, pi32, pi32, pi32, pi32, i32, i32, i32]
+    L.srba_b200_debug_level_schedule.restype = C.c_int
+    L.srba_b200_debug_level_schedule.argtypes = [pp, pi32, pi32, pi32, pi32, pi32, pi32, pi32]
     L.srba_b200_problem_ldl_counts.restype = C.c_int
     L.srba_b200_problem_ldl_counts.argtypes = [pp, C.POINTER(C.c_int64)]
+    L.srba_b200_batch_problem_plan.restype = C.c_int
+    L.srba_b200_batch_problem_plan.argtypes = [vp, i32, C.POINTER(C.c_int64)]
     L.srba_b200_problem_plan.restype = C.c_int
     L.srba_b200_problem_plan.argtypes = [pp, C.POINTER(C.c_int64)]
     L.srba_b200_last_error.restype = C.c_char_p
@@ -157,6 +161,8 @@ def lib():
     L.srba_engine_define_new_keyframe.argtypes = [vp, u64, pu64, pdbl, pu8, pu8, pdbl, C.c_int, pu64, C.POINTER(NewEdge), u64, pu64, poi, poi]
     L.srba_engine_optimize_local_area.restype = C.c_int
     L.srba_engine_optimize_local_area.argtypes = [vp, u64, u64, C.c_int, C.c_int, u64, u64, poi]
+    L.srba_engine_optimize_local_area_obs.restype = C.c_int
+    L.srba_engine_optimize_local_area_obs.argtypes = [vp, u64, u64, u64, pu64, poi]
     L.srba_engine_optimize_edges.restype = C.c_int
     L.srba_engine_optimize_edges.argtypes = [vp, u64, pu64, u64, pu64, poi]
     L.srba_engine_select_local_area.restype = C.c_int
@@ -165,6 +171,8 @@ def lib():
     L.srba_engine_flatten.argtypes = [vp, u64, pu64, u64, pu64]
     L.srba_engine_flatten_local_area.restype = vp
     L.srba_engine_flatten_local_area.argtypes = [vp, u64, u64]
+    L.srba_engine_flatten_local_area_obs.restype = vp
+    L.srba_engine_flatten_local_area_obs.argtypes = [vp, u64, u64, u64, pu64]
     L.srba_flat_problem.restype = pp
     L.srba_flat_problem.argtypes = [vp]
     L.srba_flat_apply.restype = C.c_int

@@ -47,6 +47,13 @@ class Batch:
         self._chk(self.L.srba_b200_batch_unpack(self.h, i, C.byref(res.r)))
         return res
 
+    def plan(self, i):
+        """srba_b200_batch_problem_plan: [image bytes, workspace bytes, result bytes, shared memory, solver + 2 cluster + 4 wave,
+        image arrays on chip, workspace arrays on chip, shared-memory budget] of problem i as this batch planned it."""
+        out = (C.c_int64 * 8)()
+        self._chk(self.L.srba_b200_batch_problem_plan(self.h, i, out))
+        return list(out)
+
     def stats(self, i):
         r = K.Result()
         self.L.srba_b200_batch_unpack(self.h, i, C.byref(r))

@@ -8,9 +8,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libsrba_b200.so")
-SOURCES = ["lm_kernel.cu", "lm_kernel_cluster.cu", "capi.cpp", "engine_capi.cpp"]
-HEADERS = ["dev_types.h", "host_engine.hpp", "host_pose.hpp", "../../include/srba_b200.h", "../../include/srba_b200_engine.h"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared", "-Xcompiler", "-fPIC",
+SOURCES = ["lm_kernel.cu", "lm_kernel_cluster.cu", "lm_kernel_wave.cu", "capi.cpp", "engine_capi.cpp"]
+HEADERS = ["dev_types.h", "lm_wave.cuh", "host_engine.hpp", "host_pose.hpp", "../../include/srba_b200.h", "../../include/srba_b200_engine.h"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--threads", "0", "--shared", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=default", "-Xcompiler", "-pthread", "-cudart", "static"]
 
 

@@ -29,6 +29,17 @@ extern "C" int srba_launch_eval_error(const srba_model_t *model, int n_pairs, in
 extern "C" int srba_launch_lm_batch(int model, const char *img, const uint64_t *img_off, char *ws, const uint64_t *ws_off, char *res,
                                     const uint64_t *res_off, const int32_t *order, int n_problems, int grid, int smem_bytes, void *stream);
 
+// grid-wide lock-step pipeline for heavy areas (lm_wave.cuh)
+struct SrbaWaveDims {
+	int n_areas;
+	int max_pairs, max_blocks, max_hess_items, max_obs, max_scalars, max_unk, max_schur2, max_schur3, max_lms, max_edges_S, max_out;
+	int has_lms, solve_smem_bytes;
+};
+extern "C" size_t srba_wave_scratch_bytes(int n_areas);
+extern "C" int srba_launch_lm_wave(int model, const char *img, const uint64_t *img_off, char *ws, const uint64_t *ws_off, char *res, const uint64_t *res_off,
+                                   const int32_t *order, const SrbaWaveDims *dims, char *scratch, int *h_active_pinned, void *stream, int64_t *launches);
+#define SRBA_WAVE_SOLVE_SMEM_MAX (200 * 1024)
+
 namespace {
 thread_local std::string g_err;
 thread_local int g_code = SRBA_OK;
@@ -62,9 +73,9 @@ int obs_dims(int k) { return k == SRBA_OBS_MONO ? 2 : (k == SRBA_OBS_STEREO ? 4 
 //   blocked   0 auto | 1 : dense blocked Cholesky instead of the block-sparse L D L^t   (env SRBA_B200_SOLVER=blocked)
 //   wide      0 auto | 1 : 3-int update descriptors                                     (env SRBA_B200_WIDE)
 //   chunks    1..8 pipelined chunks of srba_b200_optimize_batch                          (env SRBA_B200_CHUNKS, default 4)
-//   big_se2  -1 auto | 0 never | 1 always : large-CTA kernel for SE(2) areas that overflow the small kernel's arena
-enum { OPT_CLUSTER = 0, OPT_BLOCKED, OPT_WIDE, OPT_CHUNKS, OPT_BIG_SE2, OPT_COUNT };
-const char *const k_opt_names[OPT_COUNT] = {"cluster", "blocked", "wide", "chunks", "big_se2"};
+//   wave     -1 auto | 0 never | 1 always : grid-wide lock-step pipeline (lm_wave.cuh) for areas that overflow one CTA's arena
+enum { OPT_CLUSTER = 0, OPT_BLOCKED, OPT_WIDE, OPT_CHUNKS, OPT_WAVE, OPT_COUNT };
+const char *const k_opt_names[OPT_COUNT] = {"cluster", "blocked", "wide", "chunks", "wave"};
 std::atomic<int> g_opt[OPT_COUNT];
 std::once_flag g_opt_once;
 void init_options() {
@@ -74,7 +85,7 @@ void init_options() {
 		g_opt[OPT_BLOCKED].store(((e = std::getenv("SRBA_B200_SOLVER")) && std::string(e) == "blocked") ? 1 : 0);
 		g_opt[OPT_WIDE].store(std::getenv("SRBA_B200_WIDE") ? 1 : 0);
 		g_opt[OPT_CHUNKS].store((e = std::getenv("SRBA_B200_CHUNKS")) ? std::max(1, std::min(std::atoi(e), 8)) : 4);
-		g_opt[OPT_BIG_SE2].store((e = std::getenv("SRBA_B200_BIG_SE2")) ? std::atoi(e) : -1);
+		g_opt[OPT_WAVE].store((e = std::getenv("SRBA_B200_WAVE")) ? std::atoi(e) : -1);
 	});
 }
 int option(int id) { init_options(); return g_opt[id].load(std::memory_order_relaxed); }
@@ -259,7 +270,11 @@ struct TileSymbolic {
 	std::vector<int32_t> upd_ptr;   // NTR+1
 	std::vector<int32_t> upd;       // 2 per update: {dst tile | tile(k,i)<<16, tile(k,j)}; the update of the next pivot block is implicit
 	bool ok = false;                // false: too large for the on-chip solver (schedule not built)
-	void clear() { rs.clear(); row.clear(); phase.clear(); n_phases = 0; src.clear(); orow.clear(); on_chip = false; wide = false; tile_ij.clear(); upd_ptr.clear(); upd.clear(); ok = false; }
+	// level schedule (symbolic_levels, wave mode): `phase` holds 2 ints per level (+ sentinel) {first row, first dst entry}, `upd` holds
+	// [dst tile (n_dst) | contribution pointer (n_dst + 1) | 1 pad | (tile(k,a), tile(k,b)) x n_contrib]
+	bool levels = false;
+	int n_dst = 0, n_contrib = 0;
+	void clear() { rs.clear(); row.clear(); phase.clear(); n_phases = 0; src.clear(); orow.clear(); on_chip = false; wide = false; tile_ij.clear(); upd_ptr.clear(); upd.clear(); ok = false; levels = false; n_dst = n_contrib = 0; }
 };
 // Elimination order of the unknown edges (block level).  The reference's own order is kept whenever its fill fits on chip
 // (a relative graph-SLAM chain is block-banded in that order: no fill at all); areas with loop closures fill the whole band
@@ -484,6 +499,199 @@ void symbolic_tiles(const srba_problem_t &p, int P, long max_tiles_on_chip, Tile
 	sy.ok = true;
 }
 
+// LEVEL schedule of the block-sparse L D L^t for the wave pipeline's multi-CTA solver (lm_wave.cuh: wave_solve_kernel).
+// Elimination order: minimum degree, eliminating a maximal independent set of minimum-degree nodes per round (same fill as greedy
+// minimum degree, shorter elimination trees).  The tile rows are then SORTED BY LEVEL -- level(j) = 1 + max level(i) over the rows
+// i that hold a tile in column j, i.e. the rows whose elimination updates row j -- which is a topological order of the same
+// elimination (same filled pattern), so that all rows of a level are consecutive and can be eliminated together:
+//   per level:  A  every row: invert its 3x3 pivot block, W(k,.) = inv(D_k) T(k,.)               (one warp per row)
+//               B  every tile (a,b) that some row k of the level updates: T(a,b) -= sum_k T(k,a)^t W(k,b), contributions of one
+//                  destination grouped (one 9-lane group owns the destination: no atomics, fixed summation order)
+// and the backward pass walks the levels downwards, one warp per row.  Two team barriers per level instead of one per block row:
+// a 641-edge loop-closure area has 150 levels for 641 rows, and every phase has enough independent work for thousands of threads.
+void symbolic_levels(const srba_problem_t &p, int P, TileSymbolic &sy) {
+	const int q = P / 3, np = p.n_unk_edges, ntr = q * np, ntc = ntr + 1;
+	sy.clear();
+	sy.ntr = ntr;
+	if (ntr <= 0 || ntr > 32000) return;
+	// ---- elimination order (block level): rounds of independent minimum-degree nodes
+	const int Wb = (np + 63) / 64;
+	std::vector<uint64_t> adj((size_t)np * Wb, 0), alive(Wb, 0), blocked(Wb), nb(Wb);
+	for (int b = 0; b < p.n_S; b++) {
+		const int r = p.S_row[b], c = p.S_col[b];
+		if (r == c) continue;
+		adj[(size_t)r * Wb + (c >> 6)] |= 1ull << (c & 63);
+		adj[(size_t)c * Wb + (r >> 6)] |= 1ull << (r & 63);
+	}
+	for (int i = 0; i < np; i++) alive[i >> 6] |= 1ull << (i & 63);
+	std::vector<int> perm, deg(np);
+	perm.reserve(np);
+	while ((int)perm.size() < np) {
+		int dmin = 1 << 30;
+		for (int i = 0; i < np; i++) {
+			if (!(alive[i >> 6] >> (i & 63) & 1)) { deg[i] = -1; continue; }
+			int d = 0;
+			for (int w = 0; w < Wb; w++) d += __builtin_popcountll(adj[(size_t)i * Wb + w] & alive[w]);
+			deg[i] = d;
+			dmin = std::min(dmin, d);
+		}
+		std::fill(blocked.begin(), blocked.end(), 0);
+		for (int i = 0; i < np; i++) {
+			if (deg[i] != dmin || (blocked[i >> 6] >> (i & 63) & 1)) continue;
+			// eliminate i: its alive neighbours become a clique and are blocked for this round
+			alive[i >> 6] &= ~(1ull << (i & 63));
+			for (int w = 0; w < Wb; w++) { nb[w] = adj[(size_t)i * Wb + w] & alive[w]; blocked[w] |= nb[w]; }
+			for (int w = 0; w < Wb; w++) {
+				uint64_t m = nb[w];
+				while (m) {
+					const int j = w * 64 + __builtin_ctzll(m);
+					m &= m - 1;
+					for (int w2 = 0; w2 < Wb; w2++) adj[(size_t)j * Wb + w2] |= nb[w2];
+					adj[(size_t)j * Wb + (j >> 6)] &= ~(1ull << (j & 63));
+				}
+			}
+			perm.push_back(i);
+		}
+	}
+	std::vector<int> inv(np);
+	for (int i = 0; i < np; i++) inv[perm[i]] = i;
+	// ---- filled pattern at tile level in that order (row bitsets, column ntr = right-hand side) + where every tile comes from
+	const int W = (ntc + 63) / 64;
+	std::vector<uint64_t> rows((size_t)ntr * W, 0);
+	auto setbit = [&](int r, int c) { rows[(size_t)r * W + (c >> 6)] |= 1ull << (c & 63); };
+	struct Src { int64_t key; int32_t val; };
+	std::vector<Src> srcs;
+	srcs.reserve((size_t)p.n_S * q * q);
+	for (int r = 0; r < ntr; r++) { setbit(r, r); setbit(r, ntr); }
+	for (int b = 0; b < p.n_S; b++) {
+		const int pr = inv[p.S_row[b]], pc = inv[p.S_col[b]];
+		for (int a = 0; a < q; a++)
+			for (int c = 0; c < q; c++) {
+				const int32_t off = b * P * P + a * 3 * P + c * 3;  // sub-block (a,c) of the stored block (row <= col in the reference's order)
+				int ti = q * pr + a, tj = q * pc + c, flags = 0;
+				if (pr == pc) { if (a > c) continue; if (a == c) flags = 1 << 30; }
+				else if (pr > pc) { std::swap(ti, tj); flags = 1 << 29; }  // the tile is the TRANSPOSE of the stored sub-block
+				setbit(ti, tj);
+				srcs.push_back(Src{((int64_t)ti << 32) | tj, off | flags});
+			}
+	}
+	for (int k = 0; k < ntr; k++) {
+		const uint64_t *rk = &rows[(size_t)k * W];
+		for (int w = k >> 6; w < W; w++) {
+			uint64_t m = rk[w];
+			if (w == (k >> 6)) m &= ~((2ull << (k & 63)) - 1);  // bits > k
+			while (m) {
+				const int i = w * 64 + __builtin_ctzll(m);
+				m &= m - 1;
+				if (i >= ntr) continue;
+				uint64_t *ri = &rows[(size_t)i * W];
+				for (int w2 = i >> 6; w2 < W; w2++) {
+					uint64_t add = rk[w2];
+					if (w2 == (i >> 6)) add &= ~((1ull << (i & 63)) - 1);  // bits >= i
+					ri[w2] |= add;
+				}
+			}
+		}
+	}
+	// ---- levels, rows sorted by level (stable): rank[old row] = new row
+	std::vector<int> level(ntr, 0), order(ntr), rank(ntr);
+	for (int k = 0; k < ntr; k++) {
+		const uint64_t *rk = &rows[(size_t)k * W];
+		for (int w = k >> 6; w < W; w++) {
+			uint64_t m = rk[w];
+			if (w == (k >> 6)) m &= ~((2ull << (k & 63)) - 1);
+			while (m) {
+				const int j = w * 64 + __builtin_ctzll(m);
+				m &= m - 1;
+				if (j < ntr) level[j] = std::max(level[j], level[k] + 1);
+			}
+		}
+	}
+	std::iota(order.begin(), order.end(), 0);
+	std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return level[a] < level[b]; });
+	for (int r = 0; r < ntr; r++) rank[order[r]] = r;
+	const int nlev = level[order[ntr - 1]] + 1;
+	sy.orow.resize(ntr);
+	for (int r = 0; r < ntr; r++) { const int o = order[r]; sy.orow[r] = q * perm[o / q] + o % q; }
+	// ---- tile numbering in the new order: row-major, diagonal first, ascending column, right-hand side last
+	std::sort(srcs.begin(), srcs.end(), [](const Src &a, const Src &b) { return a.key < b.key; });
+	sy.rs.assign(ntr + 1, 0);
+	std::vector<int> cols;
+	for (int r = 0; r < ntr; r++) {
+		sy.rs[r] = (int32_t)sy.tile_ij.size();
+		const int o = order[r];
+		const uint64_t *ro = &rows[(size_t)o * W];
+		cols.clear();
+		for (int w = o >> 6; w < W; w++) {
+			uint64_t m = ro[w];
+			if (w == (o >> 6)) m &= ~((1ull << (o & 63)) - 1);
+			while (m) { const int c = w * 64 + __builtin_ctzll(m); m &= m - 1; cols.push_back(c < ntr ? rank[c] : ntr); }
+		}
+		std::sort(cols.begin(), cols.end());  // (every column of old row o ranks above r: its level is higher)
+		for (int c : cols) {
+			sy.tile_ij.push_back((r << 16) | c);
+			int32_t sv = -1;
+			if (c == ntr) sv = -2 - sy.orow[r];
+			else {
+				const int oc = order[c];
+				const int64_t key = ((int64_t)std::min(o, oc) << 32) | std::max(o, oc);  // stored with old ti < tj
+				auto it = std::lower_bound(srcs.begin(), srcs.end(), key, [](const Src &a, int64_t k) { return a.key < k; });
+				if (it != srcs.end() && it->key == key) sv = it->val;
+			}
+			sy.src.push_back(sv);
+		}
+	}
+	sy.rs[ntr] = (int32_t)sy.tile_ij.size();
+	const int ntiles = (int)sy.tile_ij.size();
+	sy.row.assign(4 * (size_t)(ntr + 1), 0);
+	for (int k = 0; k <= ntr; k++) { sy.row[4 * (size_t)k] = sy.rs[std::min(k, ntr)]; sy.row[4 * (size_t)k + 1] = sy.rs[std::min(k + 1, ntr)]; }
+	auto find_tile = [&](int i, int j) {
+		const int32_t key = (i << 16) | j;
+		return (int32_t)(std::lower_bound(sy.tile_ij.begin() + sy.rs[i], sy.tile_ij.begin() + sy.rs[i + 1], key) - sy.tile_ij.begin());
+	};
+	// ---- per level: destinations with their contributions (ascending source row)
+	std::vector<int32_t> dst, cptr(1, 0), cab, slot(ntiles, -1);
+	sy.phase.assign(2 * (size_t)(nlev + 1), 0);
+	int r = 0;
+	for (int L = 0; L < nlev; L++) {
+		sy.phase[2 * (size_t)L] = r;
+		sy.phase[2 * (size_t)L + 1] = (int32_t)dst.size();
+		const int r0 = r, d0 = (int)dst.size();
+		while (r < ntr && level[order[r]] == L) r++;
+		std::vector<std::vector<int32_t> > lists;
+		for (int k = r0; k < r; k++)
+			for (int a = sy.rs[k] + 1; a < sy.rs[k + 1] - 1; a++) {  // tile (k,i): off-diagonal, not the right-hand side
+				const int i = sy.tile_ij[a] & 0xffff;
+				for (int b = a; b < sy.rs[k + 1]; b++) {           // tile (k,j), j >= i, right-hand side included
+					const int j = sy.tile_ij[b] & 0xffff;
+					const int32_t d = find_tile(i, j);
+					if (slot[d] < 0) { slot[d] = (int32_t)lists.size(); lists.emplace_back(); dst.push_back(d); }
+					lists[slot[d]].push_back(a);
+					lists[slot[d]].push_back(b);
+				}
+			}
+		for (int e = d0; e < (int)dst.size(); e++) {
+			const std::vector<int32_t> &l = lists[e - d0];
+			cab.insert(cab.end(), l.begin(), l.end());
+			cptr.push_back((int32_t)(cab.size() / 2));
+			slot[dst[e]] = -1;
+		}
+	}
+	sy.phase[2 * (size_t)nlev] = ntr;
+	sy.phase[2 * (size_t)nlev + 1] = (int32_t)dst.size();
+	sy.n_phases = nlev;
+	sy.n_dst = (int)dst.size();
+	sy.n_contrib = (int)(cab.size() / 2);
+	sy.upd.clear();
+	sy.upd.reserve(dst.size() + cptr.size() + cab.size());
+	sy.upd.insert(sy.upd.end(), dst.begin(), dst.end());
+	sy.upd.insert(sy.upd.end(), cptr.begin(), cptr.end());
+	sy.upd.push_back(0);  // pad: the (a,b) pairs start at the even offset 2 n_dst + 2 (read as int2)
+	sy.upd.insert(sy.upd.end(), cab.begin(), cab.end());
+	sy.levels = true;
+	sy.ok = true;
+}
+
 int model_index(const srba_model_t &m) {
 	return m.pose_kind == SRBA_POSE_SE2 ? 0 : (m.obs_kind == SRBA_OBS_CARTESIAN3D ? 1 : (m.obs_kind == SRBA_OBS_MONO ? 2 : 3));
 }
@@ -518,33 +726,51 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 	// ---- dense solver: register-resident block-sparse tiles when the filled pattern fits the model kernel's register file
 	const int model = model_index(p.model);
 	const SrbaKernelCfg cfg = srba_kernel_cfg(model);
-	if (!base) {  // layout pass: symbolic factorisation (reused by the copy pass)
-		// tiles may take up to 3/4 of the CTA's shared memory (other arrays then spill to the L2-resident workspace)
-		const long max_tiles = std::min(32767L, ((long)cfg.smem_bytes * 3 / 4 / 8 - 97 - h.n_dense) / 12);
-		if (max_tiles > 0) symbolic_tiles(p, P, max_tiles, sy);
-		else sy.clear();
-	}
 	const bool force_blocked = option(OPT_BLOCKED) != 0;  // tests
-	// ---- team size: large areas (their core arrays overflow one SM's shared memory: SE(3) landmark areas, SE(2) areas
-	// with loop closures) are solved by a CLUSTER of 8 CTAs with everything in the L2-resident workspace
-	// (lm_kernel_cluster.cu); SRBA_B200_CLUSTER=0/1 forces the choice (tests)
-	const int force_cluster = option(OPT_CLUSTER);
-	bool cluster = false;
-	if (sy.ok && !force_blocked) {
-		const uint64_t demand = (uint64_t)sy.tile_ij.size() * 96 + (uint64_t)2 * p.n_pairs * S * 8 + (uint64_t)p.n_blkA * o * P * 8 + (uint64_t)p.n_blkF * o * 3 * 8 +
-		                        (uint64_t)p.n_HAp * P * P * 8 + (uint64_t)2 * p.n_HApf * P * 3 * 8;
-		cluster = force_cluster >= 0 ? force_cluster != 0 : (allow_cluster && heavy_problem(p) && demand > (uint64_t)cfg.smem_bytes);
+	// ---- execution mode.  An area whose core arrays fit one CTA's shared-memory arena runs the persistent one-CTA LM program.
+	// Larger areas (SE(3) landmark areas, SE(2) areas with loop closures) keep every array in the global workspace and run
+	//   WAVE    : the grid-wide lock-step pipeline (lm_wave.cuh) with the level-scheduled multi-CTA solver -- the default for such areas;
+	//   CLUSTER : an 8-CTA cluster team (lm_kernel_cluster.cu) -- when the wave mode is switched off and few heavy areas share the batch;
+	//   else one CTA with the overflow in the global workspace.  Options "wave" / "cluster" force the choice (tests).
+	const int force_cluster = option(OPT_CLUSTER), force_wave = option(OPT_WAVE);
+	const uint64_t demand_no_tiles = (uint64_t)2 * p.n_pairs * S * 8 + (uint64_t)p.n_blkA * o * P * 8 + (uint64_t)p.n_blkF * o * 3 * 8 + (uint64_t)p.n_HAp * P * P * 8 +
+	                                 (uint64_t)2 * p.n_HApf * P * 3 * 8;
+	const bool wave_allowed = !want_dense && !force_blocked && force_cluster != 1 && force_wave != 0;
+	bool cluster = false, wave = false;
+	if (!base) {  // layout pass: symbolic factorisation (reused by the copy pass)
+		if (wave_allowed && (force_wave == 1 || demand_no_tiles > (uint64_t)cfg.smem_bytes)) { symbolic_levels(p, P, sy); wave = sy.ok; }
+		if (!wave) {
+			// tiles may take up to 3/4 of the CTA's shared memory (other arrays then spill to the L2-resident workspace)
+			const long max_tiles = std::min(32767L, ((long)cfg.smem_bytes * 3 / 4 / 8 - 97 - h.n_dense) / 12);
+			if (max_tiles > 0) symbolic_tiles(p, P, max_tiles, sy);
+			else sy.clear();
+			if (wave_allowed && sy.ok && demand_no_tiles + (uint64_t)sy.tile_ij.size() * 96 > (uint64_t)cfg.smem_bytes) {
+				TileSymbolic lv;
+				symbolic_levels(p, P, lv);
+				if (lv.ok) { sy = std::move(lv); wave = true; }
+			}
+		}
+	} else
+		wave = sy.levels;
+	if (sy.ok && !force_blocked && !wave) {
+		const bool overflows = demand_no_tiles + (uint64_t)sy.tile_ij.size() * 96 > (uint64_t)cfg.smem_bytes;
+		if (force_cluster == 1) cluster = true;
+		else if (force_cluster < 0) cluster = allow_cluster && heavy_problem(p) && overflows;
 	}
 	h.cluster = cluster ? 1 : 0;
+	h.wave = wave ? 1 : 0;
 	const SrbaKernelCfg kcfg = cluster ? srba_kernel_cfg(model + 4) : cfg;
-	const bool tiles_on_chip = sy.on_chip && !cluster;
-	const int reg_scratch = (sy.ok && !force_blocked) ? srba_chol_reg_scratch_doubles(cluster ? model + 4 : model, h.n_dense, tiles_on_chip ? (int)sy.tile_ij.size() : 0) : -1;
+	const bool tiles_on_chip = sy.on_chip && !cluster && !wave;
+	int reg_scratch = (sy.ok && !force_blocked) ? srba_chol_reg_scratch_doubles(cluster ? model + 4 : model, h.n_dense, tiles_on_chip ? (int)sy.tile_ij.size() : 0) : -1;
+	if (wave) reg_scratch = 0;  // the wave solver keeps tiles, W tiles and the solution in the global workspace
 	uint64_t scratch_bytes;
 	if (reg_scratch >= 0) {
 		h.chol_mode = SRBA_CHOL_REG;
 		h.ldl_n_tiles = (int)sy.tile_ij.size();
 		h.ldl_tiles_in_ws = tiles_on_chip ? 0 : 1;
 		h.ldl_n_phases = sy.n_phases;
+		h.ldl_n_dst = sy.n_dst;
+		h.ldl_n_contrib = sy.n_contrib;
 		h.ldl_wide = sy.wide ? 1 : 0;
 		scratch_bytes = (uint64_t)reg_scratch * 8;
 	} else {
@@ -625,7 +851,8 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 		// in-place Schur reduction starts from at every trial
 		w[SRBA_W_grad0] = (p.model.solver_kind == SRBA_SOLVER_NO_SCHUR_SPARSE_CHOLESKY && p.n_unk_lms > 0) ? w[SRBA_W_grad] : 0;
 		w[SRBA_W_dense] = (h.chol_mode == SRBA_CHOL_BLOCKED || want_dense) ? (uint64_t)h.n_dense * h.ld_dense * 8 : 0;
-		w[SRBA_W_ldl_tiles] = (h.chol_mode == SRBA_CHOL_REG && h.ldl_tiles_in_ws) ? (uint64_t)h.ldl_n_tiles * 12 * 8 : 0;
+		// (wave: T tiles, W tiles and the solution x of the level solver)
+		w[SRBA_W_ldl_tiles] = (h.chol_mode == SRBA_CHOL_REG && h.ldl_tiles_in_ws) ? (uint64_t)h.ldl_n_tiles * 12 * 8 * (wave ? 2 : 1) + (wave ? (uint64_t)h.n_dense * 8 + 64 : 0) : 0;
 		w[SRBA_W_valid] = p.n_obs; w[SRBA_W_blk_ok] = p.n_blkA + p.n_blkF; w[SRBA_W_lm_inv] = p.n_unk_lms;
 		w[SRBA_W_slot_listed] = 2 * p.n_pairs; w[SRBA_W_listed_idx] = (uint64_t)2 * p.n_pairs * 4; w[SRBA_W_refresh_idx] = (uint64_t)p.n_pairs * 4;
 	}
@@ -637,7 +864,7 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 	{
 		Layout A;
 		h.sm_scratch = (uint32_t)A.add(scratch_bytes);
-		const uint64_t budget = cluster ? 0 : (uint64_t)kcfg.smem_bytes;  // a cluster keeps every array in the global workspace
+		const uint64_t budget = (cluster || wave) ? 0 : (uint64_t)kcfg.smem_bytes;  // clusters and waves keep every array in the global workspace
 		struct Cand { int is_img, id; };
 		static const Cand order[] = {
 			{0, SRBA_W_edge_cur}, {0, SRBA_W_edge_bak}, {0, SRBA_W_grad}, {0, SRBA_W_delta}, {0, SRBA_W_lm_cur}, {0, SRBA_W_lm_bak},
@@ -842,9 +1069,14 @@ struct srba_batch {
 	std::vector<TileSymbolic> sym;
 	std::vector<uint64_t> img_off, ws_off, res_off;
 	std::vector<int32_t> order;      // grouped by model, cost-descending inside each group
-	int group_begin[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // 4 models x {one CTA, 8-CTA cluster} per problem
-	int group_max_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-	int group_smem[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // largest planned shared-memory arena of each group
+	int group_begin[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // 4 models x {one CTA, 8-CTA cluster, grid-wide wave} per problem
+	int group_max_n[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+	int group_smem[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // largest planned shared-memory arena of each group
+	SrbaWaveDims wave_dims[4];      // per model: stage grids of the wave group
+	uint64_t wave_scratch_off[4] = {0, 0, 0, 0};  // offset of the wave group's state / views / partials inside d_ws
+	int *h_wave_active = nullptr;   // 2 pinned ints: areas still iterating (read back with one trial of lag)
+	cudaStream_t side_stream = nullptr;  // one-CTA / cluster groups run here while the wave groups use the caller's stream
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 	uint64_t tab_img_off = 0, tab_ws_off = 0, tab_res_off = 0, tab_order = 0;
 	uint64_t img_bytes = 0, ws_bytes = 0, res_bytes = 0;
 	char *h_img = nullptr, *h_res = nullptr;
@@ -945,6 +1177,10 @@ int srba_b200_eval_overall_squared_error(const srba_eval_problem_t *in, double *
 
 void srba_b200_batch_destroy(srba_batch_t *b) {
 	if (!b) return;
+	if (b->h_wave_active) cudaFreeHost(b->h_wave_active);
+	if (b->side_stream) cudaStreamDestroy(b->side_stream);
+	if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+	if (b->ev_join) cudaEventDestroy(b->ev_join);
 	if (b->pooled) { delete b; return; }
 	if (b->h_img) cudaFreeHost(b->h_img);
 	if (b->h_res) cudaFreeHost(b->h_res);
@@ -997,19 +1233,43 @@ static srba_batch_t *batch_create_impl(int32_t n, const srba_problem_t *const *i
 		b->ws_off[i] = ws; ws += b->hdr[i].ws_bytes;
 		b->res_off[i] = rs; rs += b->hdr[i].res_bytes;
 	}
-	b->img_bytes = I.total(); b->ws_bytes = std::max<uint64_t>(ws, 16); b->res_bytes = std::max<uint64_t>(rs, 16);
 	std::iota(b->order.begin(), b->order.end(), 0);
-	auto model_of = [&](int i) { return model_index(b->hdr[i].model) + 4 * b->hdr[i].cluster; };
+	auto model_of = [&](int i) { return model_index(b->hdr[i].model) + 4 * b->hdr[i].cluster + 8 * b->hdr[i].wave; };
 	std::stable_sort(b->order.begin(), b->order.end(), [&](int a, int c) {
 		const int ma = model_of(a), mc = model_of(c);
 		if (ma != mc) return ma < mc;
 		return problem_cost(b->hdr[a]) > problem_cost(b->hdr[c]);
 	});
 	{
-		int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+		int cnt[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 		for (int i = 0; i < n; i++) { const int g = model_of(i); cnt[g]++; b->group_max_n[g] = std::max(b->group_max_n[g], b->hdr[i].n_dense); b->group_smem[g] = std::max(b->group_smem[g], (int)b->hdr[i].sm_bytes); }
-		for (int g = 0; g < 8; g++) b->group_begin[g + 1] = b->group_begin[g] + cnt[g];
+		for (int g = 0; g < 12; g++) b->group_begin[g + 1] = b->group_begin[g] + cnt[g];
+		// wave groups: stage grids sized for the largest area, scratch (views, LM state, partials) appended to the workspace
+		ws = (ws + 255) / 256 * 256;
+		for (int m = 0; m < 4; m++) {
+			SrbaWaveDims &d = b->wave_dims[m];
+			std::memset(&d, 0, sizeof(d));
+			d.n_areas = cnt[8 + m];
+			if (!d.n_areas) continue;
+			for (int q = b->group_begin[8 + m]; q < b->group_begin[9 + m]; q++) {
+				const DevProblem &h = b->hdr[b->order[q]];
+				const int P = m == 0 ? 3 : 6, S = m == 0 ? 3 : 12;
+				auto mx = [](int &a, int64_t v) { a = (int)std::max<int64_t>(a, std::min<int64_t>(v, INT32_MAX)); };
+				mx(d.max_pairs, h.n_pairs); mx(d.max_blocks, (int64_t)h.n_blkA + h.n_blkF);
+				mx(d.max_hess_items, P == 6 ? (int64_t)6 * h.n_HAp + 6 * h.n_HApf + 3 * h.n_unk_lms : (int64_t)9 * h.n_HAp);
+				mx(d.max_obs, h.n_obs); mx(d.max_scalars, h.n_scalars);
+				mx(d.max_unk, std::max<int64_t>(std::max(h.n_unk_edges, h.n_unk_lms), (int64_t)2 * h.n_pairs * S));
+				mx(d.max_schur2, (int64_t)h.n_HApf * P * 3); mx(d.max_schur3, (int64_t)h.n_S * (P == 6 ? 6 : 9) + h.n_dense); mx(d.max_lms, h.n_unk_lms);
+				mx(d.max_edges_S, std::max<int64_t>((int64_t)h.n_edges * S, 2 * (int64_t)h.n_pairs));
+				mx(d.max_out, (int64_t)2 * h.n_pairs * S);
+				if (h.n_unk_lms > 0) d.has_lms = 1;
+				mx(d.solve_smem_bytes, (int64_t)(96 + 3 * (h.n_dense / 3) + 1) * 8);
+			}
+			b->wave_scratch_off[m] = ws;
+			ws += (srba_wave_scratch_bytes(d.n_areas) + 255) / 256 * 256;
+		}
 	}
+	b->img_bytes = I.total(); b->ws_bytes = std::max<uint64_t>(ws, 16); b->res_bytes = std::max<uint64_t>(rs, 16);
 	bool ok;
 	if (pool) {
 		b->pooled = true;
@@ -1046,17 +1306,41 @@ int srba_b200_batch_run(srba_batch_t *b, void *stream) {
 	if (!b) return fail(SRBA_ERR_BAD_ARGUMENT, "null batch");
 	if (!b->uploaded) return fail(SRBA_ERR_BAD_ARGUMENT, "batch_run before batch_upload");
 	b->launches = 0;
+	cudaStream_t main_st = static_cast<cudaStream_t>(stream);
+	const bool any_wave = b->group_begin[12] > b->group_begin[8], any_cta = b->group_begin[8] > 0;
+	// The wave groups are driven from the host (one launch sequence per LM trial) on the caller's stream; the one-CTA / cluster
+	// groups of the same batch run meanwhile on a side stream, forked from and joined back into the caller's stream.
+	cudaStream_t cta_st = main_st;
+	if (any_wave && any_cta) {
+		if (!b->side_stream) {
+			CUDA_TRY(cudaStreamCreateWithFlags(&b->side_stream, cudaStreamNonBlocking));
+			CUDA_TRY(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+			CUDA_TRY(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
+		}
+		cta_st = b->side_stream;
+		CUDA_TRY(cudaEventRecord(b->ev_fork, main_st));
+		CUDA_TRY(cudaStreamWaitEvent(cta_st, b->ev_fork, 0));
+	}
+	const uint64_t *t_img = reinterpret_cast<const uint64_t *>(b->d_img + b->tab_img_off), *t_ws = reinterpret_cast<const uint64_t *>(b->d_img + b->tab_ws_off),
+	               *t_res = reinterpret_cast<const uint64_t *>(b->d_img + b->tab_res_off);
+	const int32_t *t_order = reinterpret_cast<const int32_t *>(b->d_img + b->tab_order);
 	for (int g = 0; g < 8; g++) {
 		const int cnt = b->group_begin[g + 1] - b->group_begin[g];
 		if (!cnt) continue;
-		// one CTA per problem, dispatched in cost-descending order (largest first)
-		const int rc = srba_launch_lm_batch(g, b->d_img, reinterpret_cast<const uint64_t *>(b->d_img + b->tab_img_off), b->d_ws,
-		                                    reinterpret_cast<const uint64_t *>(b->d_img + b->tab_ws_off), b->d_res,
-		                                    reinterpret_cast<const uint64_t *>(b->d_img + b->tab_res_off),
-		                                    reinterpret_cast<const int32_t *>(b->d_img + b->tab_order) + b->group_begin[g], cnt, cnt, b->group_smem[g], stream);
+		// one CTA (or one cluster) per problem, dispatched in cost-descending order (largest first)
+		const int rc = srba_launch_lm_batch(g, b->d_img, t_img, b->d_ws, t_ws, b->d_res, t_res, t_order + b->group_begin[g], cnt, cnt, b->group_smem[g], cta_st);
 		if (rc != 0) return fail(SRBA_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
 		b->launches++;
 	}
+	if (any_wave && any_cta) CUDA_TRY(cudaEventRecord(b->ev_join, cta_st));
+	for (int m = 0; m < 4; m++) {
+		if (!b->wave_dims[m].n_areas) continue;
+		if (!b->h_wave_active) CUDA_TRY(cudaMallocHost(&b->h_wave_active, 2 * sizeof(int)));
+		const int rc = srba_launch_lm_wave(m, b->d_img, t_img, b->d_ws, t_ws, b->d_res, t_res, t_order + b->group_begin[8 + m], &b->wave_dims[m],
+		                                   b->d_ws + b->wave_scratch_off[m], b->h_wave_active, main_st, &b->launches);
+		if (rc != 0) return fail(SRBA_ERR_CUDA, std::string("wave pipeline: ") + cudaGetErrorString((cudaError_t)rc));
+	}
+	if (any_wave && any_cta) CUDA_TRY(cudaStreamWaitEvent(main_st, b->ev_join, 0));
 	return SRBA_OK;
 }
 
@@ -1141,6 +1425,29 @@ int srba_b200_debug_ldl_schedule(const srba_problem_t *in, int32_t counts[6], in
 	return SRBA_OK;
 }
 
+int srba_b200_debug_level_schedule(const srba_problem_t *in, int32_t counts[6], int32_t *row2, int32_t *tile_ij, int32_t *src, int32_t *orow, int32_t *lv,
+                                   int32_t *gu) {
+	if (!in || !counts) return fail(SRBA_ERR_BAD_ARGUMENT, "null argument");
+	const int rc = validate(*in);
+	if (rc != SRBA_OK) return rc;
+	const int P = in->model.pose_kind == SRBA_POSE_SE2 ? 3 : 6;
+	TileSymbolic sy;
+	symbolic_levels(*in, P, sy);
+	counts[0] = sy.ntr; counts[1] = (int32_t)sy.tile_ij.size(); counts[2] = sy.n_phases; counts[3] = sy.n_dst; counts[4] = sy.n_contrib; counts[5] = sy.ok ? 1 : 0;
+	if (!sy.ok) return SRBA_OK;
+	if (row2) for (int k = 0; k <= sy.ntr; k++) { row2[2 * k] = sy.row[4 * (size_t)k]; row2[2 * k + 1] = sy.row[4 * (size_t)k + 1]; }
+	if (tile_ij) std::memcpy(tile_ij, sy.tile_ij.data(), sy.tile_ij.size() * 4);
+	if (src) std::memcpy(src, sy.src.data(), sy.src.size() * 4);
+	if (orow) std::memcpy(orow, sy.orow.data(), sy.orow.size() * 4);
+	if (lv) std::memcpy(lv, sy.phase.data(), sy.phase.size() * 4);
+	if (gu) {  // without the alignment pad of the device image
+		const size_t head = 2 * (size_t)sy.n_dst + 1;
+		std::memcpy(gu, sy.upd.data(), head * 4);
+		std::memcpy(gu + head, sy.upd.data() + head + 1, 2 * (size_t)sy.n_contrib * 4);
+	}
+	return SRBA_OK;
+}
+
 int srba_b200_problem_plan(const srba_problem_t *in, int64_t out[8]) {
 	if (!in || !out) return fail(SRBA_ERR_BAD_ARGUMENT, "null argument");
 	const int rc = validate(*in);
@@ -1152,7 +1459,18 @@ int srba_b200_problem_plan(const srba_problem_t *in, int64_t out[8]) {
 	for (int a = 0; a < SRBA_I_COUNT; a++) n_img += (h.img_sm[a] != SRBA_NOT_IN_SMEM && h.img_len[a]) ? 1 : 0;
 	for (int a = 0; a < SRBA_W_COUNT; a++) n_ws += h.ws_sm[a] != SRBA_NOT_IN_SMEM ? 1 : 0;
 	out[0] = (int64_t)h.img_bytes; out[1] = (int64_t)h.ws_bytes; out[2] = (int64_t)h.res_bytes; out[3] = h.sm_bytes;
-	out[4] = h.chol_mode + 2 * h.cluster; out[5] = n_img; out[6] = n_ws; out[7] = srba_kernel_cfg(model_index(in->model) + 4 * h.cluster).smem_bytes;
+	out[4] = h.chol_mode + 2 * h.cluster + 4 * h.wave; out[5] = n_img; out[6] = n_ws; out[7] = srba_kernel_cfg(model_index(in->model) + 4 * h.cluster).smem_bytes;
+	return SRBA_OK;
+}
+
+int srba_b200_batch_problem_plan(const srba_batch_t *b, int32_t i, int64_t out[8]) {
+	if (!b || !out || i < 0 || i >= b->n) return fail(SRBA_ERR_BAD_ARGUMENT, "bad arguments");
+	const DevProblem &h = b->hdr[i];
+	int n_img = 0, n_ws = 0;
+	for (int a = 0; a < SRBA_I_COUNT; a++) n_img += (h.img_sm[a] != SRBA_NOT_IN_SMEM && h.img_len[a]) ? 1 : 0;
+	for (int a = 0; a < SRBA_W_COUNT; a++) n_ws += h.ws_sm[a] != SRBA_NOT_IN_SMEM ? 1 : 0;
+	out[0] = (int64_t)h.img_bytes; out[1] = (int64_t)h.ws_bytes; out[2] = (int64_t)h.res_bytes; out[3] = h.sm_bytes;
+	out[4] = h.chol_mode + 2 * h.cluster + 4 * h.wave; out[5] = n_img; out[6] = n_ws; out[7] = srba_kernel_cfg(model_index(h.model) + 4 * h.cluster).smem_bytes;
 	return SRBA_OK;
 }
 

@@ -72,6 +72,10 @@ struct DevProblem {
 	int32_t want_dense;  // copy the dense reduced Hessian of the last solve into the result blob
 	int32_t chol_mode;   // SRBA_CHOL_*
 	int32_t cluster;     // 1: solved by an 8-CTA cluster (lm_kernel_cluster.cu), every array in the global workspace
+	int32_t wave;        // 1: solved by the grid-wide lock-step pipeline (lm_wave.cuh), every array in the global workspace
+	int32_t ldl_n_dst;   // wave: destinations / contributions of the level schedule (capi.cpp: symbolic_levels): ldl_phase holds
+	int32_t ldl_n_contrib;  //    {first row, first destination} per level, ldl_upd [dst | contribution pointer | (tile(k,a), tile(k,b))]
+	int32_t pad0_;
 	int32_t panel_cap;   // SRBA_CHOL_BLOCKED: columns of the staged 8-row panel that fit the scratch
 	int32_t ldl_n_tiles; // SRBA_CHOL_REG: 3x3 tiles of the filled pattern incl. the right-hand-side column
 	int32_t ldl_n_phases; // barrier-separated elimination phases (1 or 2 independent block rows each)

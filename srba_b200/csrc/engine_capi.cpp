@@ -123,6 +123,20 @@ int srba_engine_optimize_local_area(void *h, uint64_t root, uint64_t win_size, i
 	return 0;
 	GUARD_END(-1)
 }
+int srba_engine_optimize_local_area_obs(void *h, uint64_t root, uint64_t win_size, uint64_t n_obs_idx, const uint64_t *obs_idx, srba_opt_info_t *out) {
+	GUARD_BEGIN
+	if (!h || (n_obs_idx && !obs_idx)) throw std::runtime_error("srba_engine_optimize_local_area_obs: null argument");
+	DISPATCH(h, {
+		typedef typename std::remove_reference<decltype(E)>::type EngT;
+		std::vector<size_t> lst(obs_idx, obs_idx + n_obs_idx);
+		srba_opt_info_t info;
+		std::memset(&info, 0, sizeof(info));
+		E.optimize_local_area(root, win_size, info, typename EngT::TOptimizeLocalAreaParams(), lst);
+		if (out) *out = info;
+	});
+	return 0;
+	GUARD_END(-1)
+}
 int srba_engine_optimize_edges(void *h, uint64_t n_k2k, const uint64_t *k2k, uint64_t n_lm, const uint64_t *lms, srba_opt_info_t *out) {
 	GUARD_BEGIN
 	DISPATCH(h, {
@@ -170,6 +184,21 @@ void *srba_engine_flatten_local_area(void *h, uint64_t root, uint64_t win_size) 
 		std::vector<size_t> a, b;
 		E.select_local_area(root, win_size, typename EngT::TOptimizeLocalAreaParams(), a, b);
 		if (!a.empty() || !b.empty()) fp = E.flatten(a, b);
+	});
+	if (!fp) return nullptr;
+	FlatHandle *fh = new FlatHandle();
+	fh->fp = std::move(fp);
+	return fh;
+	GUARD_END(nullptr)
+}
+void *srba_engine_flatten_local_area_obs(void *h, uint64_t root, uint64_t win_size, uint64_t n_obs_idx, const uint64_t *obs_idx) {
+	GUARD_BEGIN
+	std::unique_ptr<FlatProblem> fp;
+	DISPATCH(h, {
+		typedef typename std::remove_reference<decltype(E)>::type EngT;
+		std::vector<size_t> a, b, lst(obs_idx, obs_idx + n_obs_idx);
+		E.select_local_area(root, win_size, typename EngT::TOptimizeLocalAreaParams(), a, b);
+		if (!a.empty() || !b.empty()) fp = E.flatten(a, b, lst);
 	});
 	if (!fp) return nullptr;
 	FlatHandle *fh = new FlatHandle();

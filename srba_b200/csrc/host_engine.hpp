@@ -706,14 +706,17 @@ class RbaEngine : public EngineBase {
 			}
 		}
 	}
-	void optimize_local_area(TKeyFrameID root_id, uint64_t win_size, srba_opt_info_t &out_info, const TOptimizeLocalAreaParams &prm) {
+	// observation_indices_to_optimize (RbaEngine.h:235-241): empty = every observation of the selected unknowns
+	void optimize_local_area(TKeyFrameID root_id, uint64_t win_size, srba_opt_info_t &out_info, const TOptimizeLocalAreaParams &prm,
+	                         const std::vector<size_t> &observation_indices_to_optimize = std::vector<size_t>()) {
 		std::vector<size_t> k2k, lms;
 		select_local_area(root_id, win_size, prm, k2k, lms);
-		if (!k2k.empty() || !lms.empty()) optimize_edges(k2k, lms, out_info);
+		if (!k2k.empty() || !lms.empty()) optimize_edges(k2k, lms, out_info, observation_indices_to_optimize);
 	}
 
 	// ------------------------------------------------------------ flatten: optimize_edges.h:71-312 + schur.h:25-159 as CSR
-	std::unique_ptr<FlatProblem> flatten(const std::vector<size_t> &k2k_in, const std::vector<size_t> &lms_in) {
+	std::unique_ptr<FlatProblem> flatten(const std::vector<size_t> &k2k_in, const std::vector<size_t> &lms_in,
+	                                     const std::vector<size_t> &obs_indices_in = std::vector<size_t>()) {
 		std::unique_ptr<FlatProblem> fp(new FlatProblem());
 		FlatProblem &F = *fp;
 		std::memset(&F.p, 0, sizeof(F.p));
@@ -753,15 +756,29 @@ class RbaEngine : public EngineBase {
 			F.obs_mult.push_back(0);
 			return l;
 		};
+		// in_observation_indices_to_optimize (:218-234): the residual rows are the caller's list (in its order, repeats counted);
+		// compute_minus_gradient ASSERT_s that every block of an unknown column finds its observation in that list
+		// (compute_minus_gradient.h:55-56,79-80), so the list must cover the columns; extra observations only add residual rows.
+		const bool user_list = !obs_indices_in.empty();
+		for (size_t g : obs_indices_in) {
+			SRBA_CHECK(g < all_observations.size());
+			F.obs_mult[obs_local(g)]++;
+		}
 		F.colA_ptr.push_back(0);
 		for (int i = 0; i < n_p; i++) {
-			for (uint32_t g : colA[F.k2k_ids[i]]) { const int l = obs_local(g); F.obs_mult[l]++; F.blkA_obs.push_back(l); }
+			for (uint32_t g : colA[F.k2k_ids[i]]) {
+				if (user_list && !local_obs.count(g)) throw std::runtime_error("ASSERT_(it_obs!=obs_global_idx2residual_idx.end()): an observation of an unknown column is missing from observation_indices_to_optimize (compute_minus_gradient.h:55)");
+				const int l = obs_local(g);
+				if (!user_list) F.obs_mult[l]++;
+				F.blkA_obs.push_back(l);
+			}
 			F.colA_ptr.push_back(F.blkA_obs.size());
 		}
 		F.colF_ptr.push_back(0);
 		for (int i = 0; i < n_f; i++) {
 			for (uint32_t g : colF[all_lms[F.lm_ids[i]].fcol]) {
 				const bool fresh = !local_obs.count(g);
+				if (user_list && fresh) throw std::runtime_error("ASSERT_(it_obs!=obs_global_idx2residual_idx.end()): an observation of an unknown column is missing from observation_indices_to_optimize (compute_minus_gradient.h:79)");
 				const int l = obs_local(g);
 				if (fresh) F.obs_mult[l] = 1;
 				F.blkF_obs.push_back(l);
@@ -819,7 +836,9 @@ class RbaEngine : public EngineBase {
 		}
 		auto slot_of = [&](TKeyFrameID src, TKeyFrameID dst) -> int {  // slot of num[src][dst]
 			auto it = pair_idx.find(std::make_pair(std::max(src, dst), std::min(src, dst)));
-			if (it == pair_idx.end()) throw std::runtime_error("srba_b200: numeric spanning-tree entry needed by a Jacobian is not in the touched rows");
+			// (reachable only through observation_indices_to_optimize: an EXTRA observation whose base pose the reference would read
+			// from a stale, un-refreshed numeric spanning-tree entry -- not carried across the boundary)
+			if (it == pair_idx.end()) throw std::runtime_error("srba_b200: a listed observation needs a numeric spanning-tree entry outside the rows refreshed for the unknowns (unsupported)");
 			return 2 * it->second + (src > dst ? 0 : 1);
 		};
 		// landmarks touched
@@ -983,10 +1002,11 @@ class RbaEngine : public EngineBase {
 	}
 
 	// optimize_edges (impl/optimize_edges.h:44-793) == flatten -> srba_b200_optimize -> scatter
-	void optimize_edges(const std::vector<size_t> &k2k_in, const std::vector<size_t> &lms_in, srba_opt_info_t &out_info) {
+	void optimize_edges(const std::vector<size_t> &k2k_in, const std::vector<size_t> &lms_in, srba_opt_info_t &out_info,
+	                    const std::vector<size_t> &in_observation_indices_to_optimize = std::vector<size_t>()) {
 		std::memset(&out_info, 0, sizeof(out_info));
 		const auto t0 = std::chrono::steady_clock::now();
-		std::unique_ptr<FlatProblem> fp = flatten(k2k_in, lms_in);
+		std::unique_ptr<FlatProblem> fp = flatten(k2k_in, lms_in, in_observation_indices_to_optimize);
 		if (!fp) return;  // "Skipping optimization since no observation depends on any of the given variables" (:132-138)
 		FlatProblem &F = *fp;
 		const int S_ = S;

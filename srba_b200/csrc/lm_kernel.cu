@@ -12,6 +12,8 @@
 // CPU path only by FMA contraction.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <stdint.h>
@@ -30,6 +32,18 @@ namespace cg = cooperative_groups;
 #define LM_TID ((int)(cg::this_cluster().block_rank() * blockDim.x + threadIdx.x))
 #define LM_THREADS ((int)(blockDim.x * SRBA_CLUSTER))
 #define LM_BARRIER() cg::this_cluster().sync()
+#elif defined(SRBA_WAVE)
+// lm_kernel_wave.cu compiles this file a third time: the team of a stage is the ROW OF CTAs (blockIdx.x) a grid-wide stage kernel
+// assigns to one area (blockIdx.y); barrier-separated phases of a stage are separate launches (lm_wave.cuh), so LM_BARRIER is
+// only ever reached by the one-CTA-per-area kernels (solver, list compaction).
+#include <cooperative_groups.h>
+__shared__ int g_wave_gx;  // CTAs of this area's team in the running stage kernel (wave_team, lm_wave.cuh)
+#define LM_RANK 0
+#define LM_NCTA 1
+#define LM_TID ((int)(blockIdx.x * blockDim.x + threadIdx.x))
+#define LM_THREADS ((int)blockDim.x * g_wave_gx)
+#define LM_BARRIER() __syncthreads()
+#define LM_STAGE __device__ __forceinline__
 #else
 #define LM_RANK 0
 #define LM_NCTA 1
@@ -287,9 +301,14 @@ __device__ __forceinline__ bool no_schur_solver(const DevProblem *h) {
 }
 
 // ------------------------------------------------------------------------------------------------ stages
+// Stage functions are OUT OF LINE in the monolithic one-CTA / cluster program (its hot loop must fit the instruction cache) and
+// INLINED into the single-stage kernels of the wave pipeline (each kernel then loads only the View fields its stage uses).
+#ifndef LM_STAGE
+#define LM_STAGE __device__ __noinline__
+#endif
 // K1: numeric spanning tree.  update_numeric_only_all_from_node (impl/spantree_update_numeric.h:19-81)
 template <int P>
-__device__ __noinline__ void stage_chain(const View &vs, int n_refresh) {
+LM_STAGE void stage_chain(const View &vs, int n_refresh) {
 	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	constexpr int S = PoseOps<P>::S;
 	// n_refresh < 0: every pair (update_numeric(set,false)); otherwise the compact list of pairs holding a listed pose
@@ -477,17 +496,21 @@ __device__ bool jacob_dh_df(const View &v, int b, double *J) {
 // row's validity byte; blocks walked before it keep their fresh value, blocks walked after it keep their PREVIOUS value.
 // (PREVIOUS = previous linearisation of the same call; at the first linearisation of a call they are zero, see below.)
 // `first` additionally records which numeric-ST entries the walk registers in list_of_required_num_poses (:226-230,:902-903).
+// `phase`: 0 = the whole stage with team barriers between its phases (one CTA / one cluster per area); 1, 2, 3 = only that
+// barrier-separated phase (grid-wide wave mode, lm_wave.cuh: the launch boundary is the barrier).
 template <int P, int OBSK>
-__device__ __noinline__ void stage_jacobians(const View &vs, bool first) {
+LM_STAGE void stage_jacobians(const View &vs, bool first, int phase = 0) {
 	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	constexpr int O = ObsDims<OBSK>::O;
 	const int nA = v.h->n_blkA, nF = (OBSK == SRBA_OBS_RELPOSES2D) ? 0 : v.h->n_blkF;
 	const bool can_fail = (OBSK == SRBA_OBS_MONO || OBSK == SRBA_OBS_STEREO);
-	for (int i = LM_TID; i < v.h->n_obs; i += LM_THREADS) v.valid[i] = 1;
-	LM_BARRIER();
+	if (phase == 0 || phase == 1)
+		for (int i = LM_TID; i < v.h->n_obs; i += LM_THREADS) v.valid[i] = 1;
+	if (phase == 0) LM_BARRIER();
 	// pass 1: evaluate every block into its slot of JA/JF scratch (fresh), remember ok flags
-	for (int b = LM_TID; b < nA + nF; b += LM_THREADS) {
-		if (b < nA) {
+	// (two loops, not one loop with a branch on the block kind: warps stay convergent)
+	if (phase == 0 || phase == 2) {
+		for (int b = LM_TID; b < nA; b += LM_THREADS) {
 			double J[O * P];
 			const bool ok = jacob_dh_dAp<P, OBSK>(v, b, J);
 			v.blk_ok[b] = ok;
@@ -496,22 +519,26 @@ __device__ __noinline__ void stage_jacobians(const View &vs, bool first) {
 #pragma unroll
 				for (int i = 0; i < O * P; i++) dst[i] = J[i];
 			}
-		} else if (P == 6) {
-			const int f = b - nA;
-			double J[O * 3];
-			const bool ok = jacob_dh_df<OBSK>(v, f, J);
-			v.blk_ok[b] = ok;
-			if (!can_fail) {
-				double *dst = v.JF + (size_t)f * O * 3;
-#pragma unroll
-				for (int i = 0; i < O * 3; i++) dst[i] = J[i];
-			}
 		}
+		if (P == 6)
+			for (int f = LM_TID; f < nF; f += LM_THREADS) {
+				double J[O * 3];
+				const bool ok = jacob_dh_df<OBSK>(v, f, J);
+				v.blk_ok[nA + f] = ok;
+				if (!can_fail) {
+					double *dst = v.JF + (size_t)f * O * 3;
+#pragma unroll
+					for (int i = 0; i < O * 3; i++) dst[i] = J[i];
+				}
+			}
 	}
+	if (phase == 2) return;
 	if (can_fail) {
-		LM_BARRIER();
+		if (phase == 0) LM_BARRIER();
 		// pass 2: commit according to the walk order of each row
-		for (int b = LM_TID; b < nA + nF; b += LM_THREADS) {
+		if (phase == 0 || phase == 3)
+		for (int part = 0; part < 2; part++)   // dh_dAp blocks, then dh_df blocks: no warp mixes the two kinds
+		for (int b = (part ? nA : 0) + LM_TID; b < (part ? nA + nF : nA); b += LM_THREADS) {
 			const int obs = b < nA ? v.blkA_obs[b] : v.blkF_obs[b - nA];
 			int first_bad = -1, my_pos = -1;
 			for (int k = v.row_ptr[obs]; k < v.row_ptr[obs + 1]; k++) {
@@ -554,7 +581,7 @@ __device__ __noinline__ void stage_jacobians(const View &vs, bool first) {
 				else if (v.blkF_slot[b - nA] >= 0) v.slot_listed[v.blkF_slot[b - nA]] = 1;
 			}
 		}
-	} else if (first) {
+	} else if (first && (phase == 0 || phase == 3)) {
 		for (int b = LM_TID; b < nA + nF; b += LM_THREADS) {
 			if (b < nA) { if (v.blkA_slotA[b] >= 0) v.slot_listed[v.blkA_slotA[b]] = 1; v.slot_listed[v.blkA_slotD[b]] = 1; }
 			else if (v.blkF_slot[b - nA] >= 0) v.slot_listed[v.blkF_slot[b - nA]] = 1;
@@ -612,7 +639,7 @@ __device__ __forceinline__ void jtj_row(const DevProblem *h, const double *J1, i
 // SE(3): one thread per block ROW -- the landmark areas are load-bound (J lives in L2), and a row shares the J1 column and the
 // index / validity loads between its 6 (or 3) outputs: 2.4x fewer load instructions for the same sums in the same order.
 template <int P, int OBSK>
-__device__ __noinline__ void stage_hessian(const View &vs) {
+LM_STAGE void stage_hessian(const View &vs) {
 	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	constexpr int O = ObsDims<OBSK>::O;
 	const DevProblem *h = v.h;
@@ -709,8 +736,9 @@ __device__ __noinline__ void stage_hessian(const View &vs) {
 
 // reprojection_residuals (impl/reprojection_residuals.h:16-81) + sensor_model<>::observe_error; returns the team-wide
 // total squared error INCLUDING the duplicated rows of optimize_edges.h:177-193 (obs_mult).
+// Returns THIS THREAD's share of the total; the caller reduces it over the team (team_sum2 / per-CTA partials in wave mode).
 template <int P, int OBSK>
-__device__ __noinline__ double stage_residuals(const View &vs, double *resid, Shared &sh, double extra, double *extra_sum) {
+LM_STAGE double stage_residuals(const View &vs, double *resid, const double *sensor_inv) {
 	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	constexpr int S = PoseOps<P>::S;
 	constexpr int O = ObsDims<OBSK>::O;
@@ -734,7 +762,7 @@ __device__ __noinline__ double stage_residuals(const View &vs, double *resid, Sh
 #pragma unroll
 				for (int k = 0; k < 12; k++) Pp[k] = v.slot[(size_t)s * 12 + k];
 			} else PoseOps<6>::identity(Pp);
-			if (h->model.sensor_pose_kind == SRBA_SENSORPOSE_SE3) PoseOps<6>::compose(Pp, sh.sensor_inv, Pp);
+			if (h->model.sensor_pose_kind == SRBA_SENSORPOSE_SE3) PoseOps<6>::compose(Pp, sensor_inv, Pp);
 			double x[3];
 			compose_point3(Pp, v.lm_cur + (size_t)v.obs_lm[i] * 3, x);
 			double pred[O];
@@ -769,16 +797,12 @@ __device__ __noinline__ double stage_residuals(const View &vs, double *resid, Sh
 		for (int k = 0; k < O; k++) resid[(size_t)i * O + k] = r[k];
 		local += contrib * (double)v.obs_mult[i];
 	}
-	// `extra` rides along in the same reduction (the denominator of rho, optimize_edges.h:585)
-	double es = 0;
-	const double tot = team_sum2(local, extra, es, sh, 0);
-	*extra_sum = es;
-	return tot;
+	return local;
 }
 
 // compute_minus_gradient (impl/compute_minus_gradient.h:20-91): one thread per scalar unknown, blocks in ascending obs.
 template <int P, int OBSK>
-__device__ __noinline__ double stage_gradient(const View &vs, const double *resid) {
+LM_STAGE double stage_gradient(const View &vs, const double *resid) {
 	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	constexpr int O = ObsDims<OBSK>::O;
 	const DevProblem *h = v.h;
@@ -889,12 +913,13 @@ __device__ bool fullpiv_lu_inverse3(const double *Ain, double *inv) {
 // lev-marq_solvers.h:506-509) and reduces the gradient head IN PLACE (quirk SURVEY.md §9-1).  Without landmark unknowns
 // (relative graph-SLAM) the reduced system IS H_Ap and this stage is empty.
 template <int P>
-__device__ __noinline__ void stage_schur(const View &vs, double lambda) {
+LM_STAGE void stage_schur(const View &vs, double lambda, int phase = 0) {  // `phase` as in stage_jacobians
 	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	const DevProblem *h = v.h;
 	const int nf = h->n_unk_lms, n = h->n_dense;
 	if (nf == 0 && h->s_alias_hap) return;
 	// (1) inv(Hf_kk + lambda I)
+	if (phase == 0 || phase == 1)
 	for (int k = LM_TID; k < nf; k += LM_THREADS) {
 		double M[9], inv[9];
 #pragma unroll
@@ -907,8 +932,9 @@ __device__ __noinline__ void stage_schur(const View &vs, double lambda) {
 			for (int i = 0; i < 9; i++) v.Hf_inv[(size_t)k * 9 + i] = inv[i];
 		}
 	}
-	LM_BARRIER();
+	if (phase == 0) LM_BARRIER();
 	// (2) W_ik = HApf_ik * inv_k
+	if (phase == 0 || phase == 2)
 	for (int it = LM_TID; it < h->n_HApf * P * 3; it += LM_THREADS) {
 		const int blk = it / (P * 3), e = it % (P * 3), a = e / 3, b = e % 3;
 		const int k = v.HApf_col[blk];
@@ -917,7 +943,8 @@ __device__ __noinline__ void stage_schur(const View &vs, double lambda) {
 		const double *inv = v.Hf_inv + (size_t)k * 9;
 		v.W[it] = Hb[a * 3 + 0] * inv[0 * 3 + b] + Hb[a * 3 + 1] * inv[1 * 3 + b] + Hb[a * 3 + 2] * inv[2 * 3 + b];
 	}
-	LM_BARRIER();
+	if (phase == 0) LM_BARRIER();
+	if (phase == 1 || phase == 2) return;
 	// (3) reduced blocks; (4) reduced gradient.  SE(3): one thread per block ROW (W row loaded once for the 6 outputs, index and
 	// invertibility loads shared) -- same sums, same order, 2.4x fewer load instructions in the stage that dominates landmark areas
 	if constexpr (P == 6) {
@@ -1506,7 +1533,7 @@ __device__ __noinline__ void stage_backsub(const View &vs, Shared &sh) {
 
 // K5a: SchurComplement::numeric_solve_for_features (impl/schur.h:271-311): mutates the gradient tail in place.
 template <int P>
-__device__ __noinline__ void stage_features(const View &vs) {
+LM_STAGE void stage_features(const View &vs) {
 	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	const DevProblem *h = v.h;
 	const int n = h->n_dense;
@@ -1534,7 +1561,7 @@ __device__ __noinline__ void stage_features(const View &vs) {
 
 // K5b: back-up + manifold update (impl/optimize_edges.h:491-557)
 template <int P>
-__device__ __noinline__ void stage_update(const View &vs, int n_listed) {
+LM_STAGE void stage_update(const View &vs, int n_listed) {
 	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	constexpr int S = PoseOps<P>::S;
 	const DevProblem *h = v.h;
@@ -1559,7 +1586,7 @@ __device__ __noinline__ void stage_update(const View &vs, int n_listed) {
 }
 // rejected step (impl/optimize_edges.h:660-680): only the LISTED directed entries of the numeric ST are restored.
 template <int P>
-__device__ __noinline__ void stage_restore(const View &vs, int n_listed) {
+LM_STAGE void stage_restore(const View &vs, int n_listed) {
 	const View v = vs;  // field-wise copy into registers: no aliasing with the stores below
 	constexpr int S = PoseOps<P>::S;
 	const DevProblem *h = v.h;
@@ -1672,7 +1699,7 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 	dmax = team_max(dmax, sh, 1);
 	// M. residuals (:395-404)
 	double unused_sum;
-	const double err0 = stage_residuals<P, OBSK>(v, v.resid[0], sh, 0.0, &unused_sum);
+	const double err0 = team_sum2(stage_residuals<P, OBSK>(v, v.resid[0], sh.sensor_inv), 0.0, unused_sum, sh, 0);
 	// N. gradient (:422-426)
 	stage_gradient<P, OBSK>(v, v.resid[0]);
 	if (threadIdx.x == 0) {
@@ -1777,8 +1804,8 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 			double dl = 0;
 			const double *gr = keep_grad ? v.grad0 : v.grad;  // the Schur variants see their own in-place reduced gradient here
 			for (int i = LM_TID; i < nsc; i += LM_THREADS) dl += v.delta[i] * (lambda * v.delta[i] + gr[i]);
-			double denom;
-			const double new_err = stage_residuals<P, OBSK>(v, new_resid, sh, dl, &denom);
+			double denom;  // `dl` rides along in the same reduction (the denominator of rho, optimize_edges.h:585)
+			const double new_err = team_sum2(stage_residuals<P, OBSK>(v, new_resid, sh.sensor_inv), dl, denom, sh, 0);
 			STAGE(ST_RESID);
 			const double err = sh.err;
 			const double rho = (err - new_err) / denom;
@@ -1883,7 +1910,9 @@ __global__ void __launch_bounds__(NT, MINB) srba_lm_batch_kernel(const char *img
 
 }  // namespace
 
-#ifndef SRBA_CLUSTER
+#if defined(SRBA_WAVE)
+#include "lm_wave.cuh"
+#elif !defined(SRBA_CLUSTER)
 // Per-model kernel configuration: CTA size, register tiles per thread, dynamic shared memory per CTA.
 //   SE2+RelativePoses2D: 168 regs x 192 threads -> 2 CTAs/SM, 2 x (108 KB dynamic + ~5 KB static + 1 KB reserved) of the SM's
 //   228 KB;  SE3 models: 1024 threads x 64 regs -> 1 CTA/SM, 220 KB.

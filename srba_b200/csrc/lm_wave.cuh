@@ -1,0 +1,699 @@
+// Grid-wide ("wave") execution of the LM program for batches of HEAVY areas: the same stages as lm_program (lm_kernel.cu), but
+// every barrier-separated stage is ONE KERNEL LAUNCH over all areas of the batch -- blockIdx.y = area, blockIdx.x = the CTAs
+// that share the area's items -- and the areas advance in lock step, trial by trial, each with its own accept / reject /
+// relinearise / stop decisions kept in a small per-area state record in global memory (regime 2):
+//
+//   per trial:  [schur 1|2|3] -> solve (one CTA per area: the block-sparse L D L^t is a sequential recurrence) -> [features] ->
+//               update -> chain (listed pairs) -> residuals (+ rho denominator, per-CTA partial sums) -> ctrl1 (rho, decisions,
+//               trace) -> accepted & relinearise: jacobians (2 launches), hessian -> accepted: gradient | rejected: restore ->
+//               ctrl2 (lambda / nu schedule, stop rules, next trial or done)
+//
+// Why: with one CTA per heavy area (lm_program) 148 co-resident areas keep 148 x 8 MB of workspace live -- 10x the L2 -- and
+// every stage runs at the occupancy the WHOLE program's register / shared-memory footprint allows (1024 threads x 64 registers
+// with 2 KB spill frames).  Here a launch touches only the arrays of its stage, each stage kernel gets its own register
+// budget (no spills) and as many CTAs per area as it has items, so the streams over Jacobian blocks / Hessian terms / Schur
+// triplets run at full occupancy across all SMs.  Reductions (sum r^2, rho denominator, max |g|, max diag) are per-CTA
+// partials combined by the control kernels in a fixed order: deterministic for a given launch configuration.
+// The arithmetic of every stage is the code of lm_kernel.cu (same functions, LM_TID / LM_THREADS = position in the area's
+// row of CTAs), so parity arguments carry over; only the grouping of the reductions differs.
+#pragma once
+
+namespace {
+
+enum { WP_ERR = 0, WP_DENOM, WP_GMAX, WP_KINDS };  // per-CTA partials
+#define WAVE_PART_CTAS 64                           // at most this many CTAs per area in a reducing stage
+
+struct WaveArea {  // what `Shared` holds in the one-CTA program (impl/optimize_edges.h:361-363,452-459)
+	double lambda, nu, err, rmse, rho, new_err, trial_lambda;
+	int iter, stop, trials, accepted, relin, cholfail, cur, status, n_listed, n_refresh, need_outer, go;
+	int trial_ok, accept, do_relin, chol_fail;
+	double sensor_inv[12];
+};
+
+struct WaveArgs {
+	const char *img;
+	const uint64_t *img_off;
+	char *ws;
+	const uint64_t *ws_off;
+	char *res;
+	const uint64_t *res_off;
+	const int32_t *order;  // the problems of the wave group
+	int n;                 // number of areas
+	View *views;           // n
+	WaveArea *st;          // n
+	double *partials;      // n x WP_KINDS x WAVE_PART_CTAS
+	int *active;           // [0]: areas still iterating after the last ctrl2
+};
+
+// Team of an area in a stage kernel: as many CTAs as the AREA has items (a function of the area alone, so that the grouping of
+// its reductions -- hence every bit of its result -- does not depend on which other areas share the batch); the launch grid is
+// sized for the largest area of the group and the surplus CTAs of smaller areas leave at once.
+__device__ __forceinline__ int wave_team_ctas(int64_t items, int threads, int cap) { return (int)max((int64_t)1, min((items + threads - 1) / threads, (int64_t)cap)); }
+__device__ __forceinline__ bool wave_team(int64_t items, int cap) {
+	const int gx = wave_team_ctas(items, (int)blockDim.x, cap);
+	if ((int)blockIdx.x >= gx) return false;
+	if (threadIdx.x == 0) g_wave_gx = gx;
+	__syncthreads();
+	return true;
+}
+#define WAVE_CAP 256  // CTAs per area in a non-reducing stage
+
+__device__ __forceinline__ double *wave_part(const WaveArgs &a, int area, int kind) { return a.partials + ((size_t)area * WP_KINDS + kind) * WAVE_PART_CTAS; }
+
+// sum / max of one value per thread over the CTA; result valid in thread 0
+__device__ __forceinline__ double cta_sum(double v, double *scr) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+	if ((threadIdx.x & 31) == 0) scr[threadIdx.x >> 5] = v;
+	__syncthreads();
+	double s = 0;
+	if (threadIdx.x == 0)
+		for (int i = 0; i < (int)blockDim.x / 32; i++) s += scr[i];
+	__syncthreads();
+	return s;
+}
+__device__ __forceinline__ double cta_max(double v, double *scr) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+	if ((threadIdx.x & 31) == 0) scr[threadIdx.x >> 5] = v;
+	__syncthreads();
+	double s = 0;
+	if (threadIdx.x == 0)
+		for (int i = 0; i < (int)blockDim.x / 32; i++) s = i == 0 ? scr[0] : fmax(s, scr[i]);
+	__syncthreads();
+	return s;
+}
+
+// the scalar control flow between two trials (lm_program::advance)
+__device__ void wave_advance(WaveArea &s, const DevProblem *h) {
+	for (;;) {
+		if (s.need_outer) {
+			if (!(s.iter < h->model.max_iters && !s.stop)) { s.go = 0; return; }
+			s.rho = 0;
+			if (s.lambda >= h->model.max_lambda) s.stop = 1;
+			if (s.rmse < h->model.max_error_per_obs_to_stop) s.stop = 1;
+			s.need_outer = 0;
+		}
+		if (s.rho <= 0 && !s.stop) { s.go = 1; return; }
+		s.iter++;
+		s.need_outer = 1;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ set-up
+__global__ void wave_views_kernel(const WaveArgs a) {
+	const int area = blockIdx.x * blockDim.x + threadIdx.x;
+	if (area >= a.n) return;
+	const int pi = a.order[area];
+	const char *pimg = a.img + a.img_off[pi];
+	make_view(a.views[area], reinterpret_cast<const DevProblem *>(pimg), pimg, a.ws + a.ws_off[pi], a.res + a.res_off[pi], nullptr);
+}
+
+__global__ void wave_dump_kernel(const WaveArgs a, int tag) {
+	const View &v = a.views[0];
+	const DevProblem *h = v.h;
+	printf("[wave dump %d] n=%d views=%p h=%p wave=%d n_lms=%d n_pairs=%d nA=%d nF=%d ws_sm[lm_cur]=%u ws_off[lm_cur]=%llu lm_cur=%p slot=%p blkF_slot=%p obs_lm=%p blkF_obs=%p JF=%p ws=%p\n", tag, a.n, a.views, h,
+	       h->wave, h->n_lms, h->n_pairs, h->n_blkA, h->n_blkF, h->ws_sm[SRBA_W_lm_cur], (unsigned long long)h->ws_off[SRBA_W_lm_cur], v.lm_cur, v.slot, v.blkF_slot, v.obs_lm, v.blkF_obs, v.JF, a.ws);
+}
+
+template <int P>
+__global__ void __launch_bounds__(256) wave_init_kernel(const WaveArgs a) {
+	constexpr int S = PoseOps<P>::S;
+	const int area = blockIdx.y;
+	const View v = a.views[area];
+	const DevProblem *h = v.h;
+	if (!wave_team(max((int64_t)h->n_edges * S, (int64_t)2 * h->n_pairs), WAVE_CAP)) return;
+	const char *pimg = reinterpret_cast<const char *>(h);
+	const double *ge = reinterpret_cast<const double *>(pimg + h->img_off[SRBA_I_edge_pose]);
+	const double *gl = reinterpret_cast<const double *>(pimg + h->img_off[SRBA_I_lm_pos]);
+	for (size_t i = LM_TID; i < (size_t)h->n_edges * S; i += LM_THREADS) v.edge_cur[i] = ge[i];
+	for (size_t i = LM_TID; i < (size_t)h->n_lms * 3; i += LM_THREADS) v.lm_cur[i] = gl[i];
+	for (int i = LM_TID; i < 2 * h->n_pairs; i += LM_THREADS) v.slot_listed[i] = 0;
+	if (LM_TID == 0) {
+		WaveArea &s = a.st[area];
+		if (h->model.sensor_pose_kind == SRBA_SENSORPOSE_SE3) PoseOps<6>::inverse(s.sensor_inv, h->model.sensor_pose);
+		s.status = SRBA_OK;
+		s.go = 1;  // the set-up stages below run for every area
+		s.trial_ok = 0; s.accept = 0; s.do_relin = 0; s.cur = 0;
+	}
+}
+
+// compact lists of the listed directed entries and of the pairs that hold one (lm_program, after the first linearisation)
+__global__ void __launch_bounds__(64) wave_lists_kernel(const WaveArgs a) {
+	const int area = blockIdx.y;
+	const View v = a.views[area];
+	const DevProblem *h = v.h;
+	WaveArea &s = a.st[area];
+	if (threadIdx.x < 32) {
+		int cnt = 0;
+		for (int base = 0; base < 2 * h->n_pairs; base += 32) {
+			const int sidx = base + threadIdx.x;
+			const bool on = sidx < 2 * h->n_pairs && v.slot_listed[sidx];
+			const unsigned m = __ballot_sync(0xffffffffu, on);
+			if (on) v.listed_idx[cnt + __popc(m & ((1u << threadIdx.x) - 1))] = sidx;
+			cnt += __popc(m);
+		}
+		if (threadIdx.x == 0) s.n_listed = cnt;
+	} else {
+		const int l = threadIdx.x - 32;
+		int cnt = 0;
+		for (int base = 0; base < h->n_pairs; base += 32) {
+			const int t = base + l;
+			const bool on = t < h->n_pairs && (v.slot_listed[2 * t] | v.slot_listed[2 * t + 1]);
+			const unsigned m = __ballot_sync(0xffffffffu, on);
+			if (on) v.refresh_idx[cnt + __popc(m & ((1u << l) - 1))] = t;
+			cnt += __popc(m);
+		}
+		if (l == 0) s.n_refresh = cnt;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ stage kernels
+// `when`: which areas take part -- 0: every area still iterating (go); 1: go and the solve of this trial succeeded;
+// 2: ... and the step was accepted and relinearises; 3: ... accepted; 4: ... rejected; 5: set-up (all areas)
+enum { WHEN_GO = 0, WHEN_TRIAL_OK, WHEN_RELIN, WHEN_ACCEPT, WHEN_REJECT, WHEN_SETUP };
+__device__ __forceinline__ bool wave_on(const WaveArea &s, int when) {
+	if (when == WHEN_SETUP) return true;
+	if (!s.go) return false;
+	if (when == WHEN_GO) return true;
+	if (!s.trial_ok) return false;
+	if (when == WHEN_TRIAL_OK) return true;
+	if (when == WHEN_RELIN) return s.accept && s.do_relin;
+	if (when == WHEN_ACCEPT) return s.accept;
+	return !s.accept;
+}
+
+template <int P>
+__global__ void __launch_bounds__(256) wave_chain_kernel(const WaveArgs a, int when) {
+	const int area = blockIdx.y;
+	const WaveArea &s = a.st[area];
+	if (!wave_on(s, when)) return;
+	if (!wave_team(when == WHEN_SETUP ? a.views[area].h->n_pairs : s.n_refresh, WAVE_CAP)) return;
+	stage_chain<P>(a.views[area], when == WHEN_SETUP ? -1 : s.n_refresh);
+}
+
+// launch A: validity reset + evaluation (phases 1, 2); launch B: commit by walk order / listed marks (phase 3)
+template <int P, int OBSK>
+__global__ void __launch_bounds__(128) wave_jacobians_kernel(const WaveArgs a, int when, int second) {
+	const int area = blockIdx.y;
+	if (!wave_on(a.st[area], when)) return;
+	{
+		const DevProblem *h = a.views[area].h;
+		if (!wave_team((int64_t)h->n_blkA + h->n_blkF, WAVE_CAP)) return;
+	}
+	const bool first = when == WHEN_SETUP;
+	if (!second) {
+		stage_jacobians<P, OBSK>(a.views[area], first, 1);
+		stage_jacobians<P, OBSK>(a.views[area], first, 2);
+	} else
+		stage_jacobians<P, OBSK>(a.views[area], first, 3);
+}
+
+template <int P, int OBSK>
+__global__ void __launch_bounds__(128) wave_hessian_kernel(const WaveArgs a, int when) {
+	const int area = blockIdx.y;
+	if (!wave_on(a.st[area], when)) return;
+	{
+		const DevProblem *h = a.views[area].h;
+		if (!wave_team(P == 6 ? (int64_t)6 * h->n_HAp + 6 * h->n_HApf + 3 * h->n_unk_lms : (int64_t)9 * h->n_HAp, WAVE_CAP)) return;
+	}
+	stage_hessian<P, OBSK>(a.views[area]);
+}
+
+// residuals into resid[cur] (set-up) or resid[cur ^ 1] (trial) + this CTA's partial of the total and of rho's denominator
+template <int P, int OBSK>
+__global__ void __launch_bounds__(256) wave_residuals_kernel(const WaveArgs a, int when) {
+	__shared__ double scr[8];
+	const int area = blockIdx.y;
+	const WaveArea &s = a.st[area];
+	if (!wave_on(s, when)) return;
+	const View &v = a.views[area];
+	const DevProblem *h = v.h;
+	if (!wave_team(h->n_obs, WAVE_PART_CTAS)) return;
+	const bool setup = when == WHEN_SETUP;
+	double *resid = v.resid[setup ? 0 : (s.cur ^ 1)];
+	double dl = 0;
+	if (!setup) {  // rho (:585)
+		const bool keep_grad = (OBSK != SRBA_OBS_RELPOSES2D) && no_schur_solver(h);
+		const double *gr = keep_grad ? v.grad0 : v.grad;
+		const double lambda = s.trial_lambda;
+		for (int i = LM_TID; i < h->n_scalars; i += LM_THREADS) dl += v.delta[i] * (lambda * v.delta[i] + gr[i]);
+	}
+	const double local = stage_residuals<P, OBSK>(a.views[area], resid, s.sensor_inv);
+	const double se = cta_sum(local, scr), sd = cta_sum(dl, scr);
+	if (threadIdx.x == 0) { wave_part(a, area, WP_ERR)[blockIdx.x] = se; wave_part(a, area, WP_DENOM)[blockIdx.x] = sd; }
+}
+
+// accepted (or set-up): gradient from the new residuals + partial of max |g|;  rejected: restore
+template <int P, int OBSK>
+__global__ void __launch_bounds__(128) wave_gradient_or_restore_kernel(const WaveArgs a, int setup) {
+	__shared__ double scr[8];
+	const int area = blockIdx.y;
+	const WaveArea &s = a.st[area];
+	if (!setup && (!s.go || !s.trial_ok)) return;
+	const View &v = a.views[area];
+	if (!wave_team(v.h->n_scalars, WAVE_PART_CTAS)) return;  // (restore: the same team strides over its three lists)
+	if (setup || s.accept) {
+		const double gm = stage_gradient<P, OBSK>(v, v.resid[setup ? 0 : (s.cur ^ 1)]);
+		const double m = cta_max(gm, scr);
+		if (threadIdx.x == 0) wave_part(a, area, WP_GMAX)[blockIdx.x] = m;
+	} else
+		stage_restore<P>(v, s.n_listed);
+}
+
+template <int P, int OBSK>
+__global__ void __launch_bounds__(128) wave_schur_kernel(const WaveArgs a, int phase) {
+	const int area = blockIdx.y;
+	const WaveArea &s = a.st[area];
+	if (!s.go) return;
+	const View &v = a.views[area];
+	const DevProblem *h = v.h;
+	if (h->n_unk_lms == 0 && h->s_alias_hap) return;
+	if (!wave_team(phase == 1 ? (int64_t)h->n_unk_lms : phase == 2 ? (int64_t)h->n_HApf * P * 3 : (int64_t)h->n_S * (P == 6 ? 6 : 9) + h->n_dense, WAVE_CAP)) return;
+	if (phase == 1 && (OBSK != SRBA_OBS_RELPOSES2D) && no_schur_solver(h))  // (grad is next read by phase 3)
+		for (int i = LM_TID; i < h->n_scalars; i += LM_THREADS) v.grad[i] = v.grad0[i];
+	stage_schur<P>(v, s.lambda, phase);
+}
+
+// The reduced system of one area, solved by a CLUSTER of WAVE_SOLVE_CTAS CTAs with the LEVEL schedule of the packer (capi.cpp:
+// symbolic_levels): block-sparse L D L^t on 3x3 tiles kept in the global workspace (L2), the rows of one elimination level
+// processed together --
+//   A  one warp per row: pivot block inverted (cofactors; rejected exactly when a leading minor is <= 0, i.e. when Eigen::LLT would
+//      meet a non-positive pivot, lev-marq_solvers.h:527-534), W(k,.) = inv(D_k) T(k,.) written next to T;
+//   B  one 9-lane group per destination tile: T(a,b) -= sum_k T(k,a)^t W(k,b) over the contributions of this level, in ascending
+//      source row (deterministic, no atomics);
+// two cluster barriers per level; the backward pass x_k = y_k - sum_j W(k,j) x_j walks the levels downwards, one warp per row.
+// Solves what Eigen::LLT<Upper> + solve see after the dense fill (impl/lev-marq_solvers.h:492-549).  Afterwards CTA 0 books a failed
+// factorisation (not positive definite, optimize_edges.h:476-485) -- the later stages of this trial skip the area (trial_ok = 0).
+#define WAVE_SOLVE_CTAS 8
+#define WAVE_SOLVE_NT 256
+template <int P, int OBSK>
+__global__ void __launch_bounds__(WAVE_SOLVE_NT) wave_solve_kernel(const WaveArgs a) {
+	cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
+	const int area = blockIdx.y;
+	WaveArea &s = a.st[area];
+	if (!s.go) return;  // (the same decision in every CTA of the cluster)
+	const View &vg = a.views[area];
+	const DevProblem *h = vg.h;
+	const double lambda = s.lambda;
+	const int n = h->n_dense, ntiles = h->ldl_n_tiles, nlev = h->ldl_n_phases, ndst = h->ldl_n_dst, NTR = n / 3;
+	double *T = vg.ldl_tiles, *Wt = T + (size_t)ntiles * 12, *x = Wt + (size_t)ntiles * 12;
+	const int2 *rowinfo = reinterpret_cast<const int2 *>(vg.ldl_row);   // (4 ints per row: .x first tile, .y end tile of row r at rowinfo[2 r])
+	const int32_t *tij = vg.ldl_tile_ij, *src = vg.ldl_src, *orow = vg.ldl_orow;
+	const int2 *lvl = reinterpret_cast<const int2 *>(vg.ldl_phase);      // {first row, first destination} per level
+	const int32_t *dst = vg.ldl_upd, *cptr = dst + ndst;
+	const int2 *cab = reinterpret_cast<const int2 *>(dst + 2 * ndst + 2);  // (pointer list padded to an even count)
+	const double *S = vg.S, *grad = vg.grad;
+	const int tid = (int)(blockIdx.x * blockDim.x + threadIdx.x), NTH = (int)(gridDim.x * blockDim.x);
+	const int lane = tid & 31, gwarp = tid >> 5, NW = NTH >> 5;
+	const int wg = lane / 9, we = lane - wg * 9, wb = we / 3, wa = we - wb * 3, eo = wb * 4 + wa;  // 9-lane tile group: element (wa,wb)
+	const bool glane = lane < 27;
+	const bool keep_grad = (OBSK != SRBA_OBS_RELPOSES2D) && no_schur_solver(h);
+	if (tid == 0) s.chol_fail = 0;
+	// gather: tile element <- reduced block element (+lambda on the diagonal); tile column NTR = reduced gradient
+	if (glane) {
+		const double dl = wa == wb ? lambda : 0.0;
+		for (int tl = 3 * gwarp + wg; tl < ntiles; tl += 3 * NW) {
+			const int so = src[tl];
+			double val = 0.0;
+			if (so >= 0) val = S[(so & 0x1fffffff) + ((so >> 29) & 1 ? wb * P + wa : wa * P + wb)] + ((so >> 30) ? dl : 0.0);
+			else if (so <= -2 && wb == 0) val = grad[3 * (-so - 2) + wa];
+			T[(size_t)tl * 12 + eo] = val;
+		}
+	}
+	cl.sync();
+	if (keep_grad) {  // a landmark block that cannot be eliminated = the whole-system Cholesky fails (lev-marq_solvers.h:171-175)
+		for (int k = tid; k < h->n_unk_lms; k += NTH)
+			if (!vg.lm_inv[k]) s.chol_fail = 1;
+	}
+	for (int L = 0; L < nlev; L++) {
+		const int2 l0 = lvl[L], l1 = lvl[L + 1];
+		// ---- A: rows of the level
+		for (int r = l0.x + gwarp; r < l1.x; r += NW) {
+			const int t0 = rowinfo[2 * r].x, t1 = rowinfo[2 * r].y;
+			const double *D = T + (size_t)t0 * 12;
+			const double d00 = D[0], d01 = D[4], d02 = D[8], d11 = D[5], d12 = D[9], d22 = D[10];
+			const double c00 = d11 * d22 - d12 * d12, c01 = d02 * d12 - d01 * d22, c02 = d01 * d12 - d02 * d11;
+			const double c11 = d00 * d22 - d02 * d02, c12 = d01 * d02 - d00 * d12, c22 = d00 * d11 - d01 * d01;
+			const double det = d00 * c00 + d01 * c01 + d02 * c02;
+			if (lane == 0 && (d00 <= 0 || c22 <= 0 || det <= 0)) s.chol_fail = 1;
+			const double idet = 1.0 / det;
+			// row wa of inv(D) (symmetric)
+			const double i0 = (wa == 0 ? c00 : wa == 1 ? c01 : c02) * idet, i1 = (wa == 0 ? c01 : wa == 1 ? c11 : c12) * idet,
+			             i2 = (wa == 0 ? c02 : wa == 1 ? c12 : c22) * idet;
+			if (glane)
+				for (int tl = t0 + 1 + wg; tl < t1; tl += 3) {
+					const double *Tc = T + (size_t)tl * 12 + wb * 4;
+					Wt[(size_t)tl * 12 + eo] = i0 * Tc[0] + i1 * Tc[1] + i2 * Tc[2];
+				}
+		}
+		cl.sync();
+		// ---- B: destinations of the level
+		if (glane)
+			for (int e = l0.y + gwarp * 3 + wg; e < l1.y; e += NW * 3) {
+				const int c1 = cptr[e + 1];
+				double acc = 0.0;
+				for (int c = cptr[e]; c < c1; c++) {
+					const int2 ab = cab[c];
+					const double *Ta = T + (size_t)ab.x * 12 + wa * 4, *Wb = Wt + (size_t)ab.y * 12 + wb * 4;
+					acc += Ta[0] * Wb[0] + Ta[1] * Wb[1] + Ta[2] * Wb[2];
+				}
+				double *d = T + (size_t)dst[e] * 12 + eo;
+				*d -= acc;
+			}
+		cl.sync();
+	}
+	// ---- backward pass by descending level: lane (t, a) = row a of the t-th (mod 8) off-diagonal tile of the row
+	{
+		const int t8 = lane >> 2, ra = lane & 3;
+		for (int L = nlev - 1; L >= 0; L--) {
+			const int r0 = lvl[L].x, r1 = lvl[L + 1].x;
+			for (int r = r0 + gwarp; r < r1; r += NW) {
+				const int t0 = rowinfo[2 * r].x, t1 = rowinfo[2 * r].y, m = t1 - t0 - 2;
+				double p = 0.0;
+				if (ra < 3)
+					for (int t = t8; t < m; t += 8) {
+						const int tl = t0 + 1 + t;
+						const double *xj = x + 3 * (tij[tl] & 0xffff);
+						const double *Wr = Wt + (size_t)tl * 12 + ra;
+						p += Wr[0] * xj[0] + Wr[4] * xj[1] + Wr[8] * xj[2];
+					}
+				p += __shfl_xor_sync(0xffffffffu, p, 4);
+				p += __shfl_xor_sync(0xffffffffu, p, 8);
+				p += __shfl_xor_sync(0xffffffffu, p, 16);
+				if (lane < 3) x[3 * r + lane] = Wt[(size_t)(t1 - 1) * 12 + lane] - p;
+			}
+			cl.sync();
+		}
+	}
+	for (int i = tid; i < n; i += NTH) { const int r = i / 3; vg.delta[3 * orow[r] + (i - 3 * r)] = x[i]; }  // back to the reference's unknown order
+	if (blockIdx.x != 0) return;
+	// ---- CTA 0: outcome of the factorisation
+	const bool failed = s.chol_fail != 0;
+	const int trial = s.trials;
+	const int nsc = h->n_scalars;
+	__syncthreads();
+	if (failed) {
+		if (trial < h->trace_cap)
+			for (int i = threadIdx.x; i < nsc; i += blockDim.x) vg.r_trace_delta[(size_t)trial * nsc + i] = 0;
+		if (threadIdx.x == 0) {
+			if (trial < h->trace_cap) {
+				double *tr = vg.r_trace + (size_t)trial * 6;
+				tr[0] = lambda; tr[1] = 0; tr[2] = 0; tr[3] = 0; tr[4] = 0; tr[5] = 0;
+			}
+			s.trials++; s.cholfail++;
+			s.lambda *= s.nu;
+			s.nu *= 2.;
+			s.stop = (s.lambda > h->model.max_lambda);
+			s.trial_ok = 0;
+			wave_advance(s, h);
+			if (s.go) atomicAdd(a.active, 1);
+		}
+	} else if (threadIdx.x == 0) {
+		s.trial_ok = 1;
+		s.trial_lambda = lambda;
+	}
+}
+
+template <int P>
+__global__ void __launch_bounds__(128) wave_features_kernel(const WaveArgs a) {
+	const int area = blockIdx.y;
+	const WaveArea &s = a.st[area];
+	if (!s.go || !s.trial_ok) return;
+	if (!wave_team(a.views[area].h->n_unk_lms, WAVE_CAP)) return;
+	stage_features<P>(a.views[area]);
+}
+
+template <int P>
+__global__ void __launch_bounds__(128) wave_update_kernel(const WaveArgs a) {
+	const int area = blockIdx.y;
+	const WaveArea &s = a.st[area];
+	if (!s.go || !s.trial_ok) return;
+	{
+		const DevProblem *h = a.views[area].h;
+		if (!wave_team(max(max((int64_t)h->n_unk_edges, (int64_t)h->n_unk_lms), (int64_t)s.n_listed * PoseOps<P>::S), WAVE_CAP)) return;
+	}
+	stage_update<P>(a.views[area], s.n_listed);
+}
+
+// ------------------------------------------------------------------------------------------------ control kernels (one CTA per area)
+// After the set-up stages: lambda0 = tau * max diag (optimize_edges.h:365-390), initial error, first advance().
+template <int P, int OBSK>
+__global__ void __launch_bounds__(128) wave_ctrl_init_kernel(const WaveArgs a) {
+	__shared__ double scr[8];
+	const int area = blockIdx.y;
+	const View v = a.views[area];
+	const DevProblem *h = v.h;
+	WaveArea &s = a.st[area];
+	double dmax = 0;
+	for (int b = threadIdx.x; b < h->n_HAp; b += blockDim.x)
+		if (v.HAp_row[b] == v.HAp_col[b]) {
+			double m = v.HAp[(size_t)b * P * P];
+			for (int k = 1; k < P; k++) m = fmax(m, v.HAp[(size_t)b * P * P + k * P + k]);
+			dmax = fmax(dmax, m);
+		}
+	for (int k = threadIdx.x; k < h->n_unk_lms; k += blockDim.x)
+		dmax = fmax(dmax, fmax(v.Hf[(size_t)k * 9], fmax(v.Hf[(size_t)k * 9 + 4], v.Hf[(size_t)k * 9 + 8])));
+	dmax = cta_max(dmax, scr);
+	if (threadIdx.x == 0) {
+		double err0 = 0;
+		const double *pe = wave_part(a, area, WP_ERR);
+		const int gx_resid = wave_team_ctas(h->n_obs, 256, WAVE_PART_CTAS);  // the residual kernel's team (256-thread CTAs)
+		for (int i = 0; i < gx_resid; i++) err0 += pe[i];
+		s.nu = 2;
+		s.lambda = 1e-3 * dmax;
+		s.err = err0;
+		s.rmse = sqrt(err0 / h->n_total_obs_rows);
+		s.iter = 0; s.stop = 0; s.trials = 0; s.accepted = 0; s.relin = 0; s.cholfail = 0; s.cur = 0;
+		s.need_outer = 1; s.rho = 0; s.trial_ok = 0; s.accept = 0; s.do_relin = 0;
+		v.stats->total_sqr_error_init = err0;
+		if (!isfinite(err0) || !isfinite(dmax)) s.status = SRBA_ERR_NON_FINITE;
+		wave_advance(s, h);
+		if (s.go) atomicAdd(a.active, 1);
+	}
+}
+
+// rho, accept / relinearise decisions (optimize_edges.h:585-605), trace
+template <int P, int OBSK>
+__global__ void __launch_bounds__(128) wave_ctrl1_kernel(const WaveArgs a) {
+	const int area = blockIdx.y;
+	WaveArea &s = a.st[area];
+	if (!s.go || !s.trial_ok) return;
+	const View v = a.views[area];
+	const DevProblem *h = v.h;
+	__shared__ int sh_trial;
+	if (threadIdx.x == 0) {
+		double new_err = 0, denom = 0;
+		const double *pe = wave_part(a, area, WP_ERR), *pd = wave_part(a, area, WP_DENOM);
+		const int gx_resid = wave_team_ctas(h->n_obs, 256, WAVE_PART_CTAS);
+		for (int i = 0; i < gx_resid; i++) { new_err += pe[i]; denom += pd[i]; }
+		const double err = s.err;
+		const double rho = (err - new_err) / denom;
+		const double error_reduction_ratio = err > 0 ? (err - new_err) / err : 0;
+		const bool accept = rho > 0;
+		const bool do_relinearize = accept && (error_reduction_ratio < 0 || error_reduction_ratio > h->model.min_error_reduction_ratio_to_relinearize);
+		s.new_err = new_err; s.rho = rho; s.accept = accept ? 1 : 0; s.do_relin = do_relinearize ? 1 : 0;
+		const int trial = s.trials;
+		sh_trial = trial;
+		if (trial < h->trace_cap) {
+			double *tr = v.r_trace + (size_t)trial * 6;
+			tr[0] = s.trial_lambda; tr[1] = 1; tr[2] = rho; tr[3] = new_err; tr[4] = accept ? 1 : 0; tr[5] = do_relinearize ? 1 : 0;
+		}
+	}
+	__syncthreads();
+	const int trial = sh_trial, nsc = h->n_scalars;
+	if (trial < h->trace_cap)
+		for (int i = threadIdx.x; i < nsc; i += blockDim.x) v.r_trace_delta[(size_t)trial * nsc + i] = v.delta[i];
+}
+
+// end of a trial: state update after an accepted (optimize_edges.h:633-656) or rejected (:658-690) step, next trial or done
+template <int P, int OBSK>
+__global__ void __launch_bounds__(32) wave_ctrl2_kernel(const WaveArgs a) {
+	const int area = blockIdx.x * blockDim.x + threadIdx.x;
+	if (area >= a.n) return;
+	WaveArea &s = a.st[area];
+	if (!s.go || !s.trial_ok) return;   // (a failed factorisation was already booked by the solve kernel)
+	const DevProblem *h = a.views[area].h;
+	const double rho = s.rho, new_err = s.new_err;
+	if (s.accept) {
+		double gm = 0;
+		const double *pg = wave_part(a, area, WP_GMAX);
+		const int gx_grad = wave_team_ctas(h->n_scalars, 128, WAVE_PART_CTAS);  // the gradient kernel's team (128-thread CTAs)
+		for (int i = 0; i < gx_grad; i++) gm = i == 0 ? pg[0] : fmax(gm, pg[i]);
+		s.cur ^= 1;
+		s.err = new_err;
+		s.rmse = sqrt(new_err / h->n_total_obs_rows);
+		s.trials++; s.accepted++; s.relin += s.do_relin;
+		if (gm <= 1e-15) s.stop = 1;  // max_gradient_to_stop (optimize_edges.h:362)
+		if (s.rmse < h->model.max_error_per_obs_to_stop) s.stop = 1;
+		if (rho > h->model.max_rho) s.stop = 1;
+		s.lambda *= 1.0 / 3.0;
+		s.nu = 2.0;
+	} else {
+		s.trials++;
+		s.lambda *= s.nu;
+		s.nu *= 2.0;
+		s.stop = (s.lambda > h->model.max_lambda);
+		if (!isfinite(new_err) || !isfinite(rho)) s.status = SRBA_ERR_NON_FINITE;
+	}
+	s.trial_ok = 0;
+	wave_advance(s, h);
+	if (s.go) atomicAdd(a.active, 1);
+}
+
+// Q/S. outputs
+template <int P, int OBSK>
+__global__ void __launch_bounds__(256) wave_output_kernel(const WaveArgs a) {
+	constexpr int S = PoseOps<P>::S;
+	const int area = blockIdx.y;
+	const View v = a.views[area];
+	const DevProblem *h = v.h;
+	const WaveArea &s = a.st[area];
+	if (!wave_team((int64_t)2 * h->n_pairs * S, WAVE_CAP)) return;
+	const bool keep_grad = (OBSK != SRBA_OBS_RELPOSES2D) && no_schur_solver(h);
+	for (size_t i = LM_TID; i < (size_t)h->n_unk_edges * S; i += LM_THREADS) v.r_edge_pose[i] = v.edge_cur[(size_t)v.unk_edge[i / S] * S + (i % S)];
+	for (int i = LM_TID; i < h->n_unk_lms * 3; i += LM_THREADS) v.r_lm_pos[i] = v.lm_cur[(size_t)v.unk_lm[i / 3] * 3 + (i % 3)];
+	for (size_t i = LM_TID; i < (size_t)2 * h->n_pairs * S; i += LM_THREADS) v.r_slot_pose[i] = v.slot[i];
+	for (int i = LM_TID; i < h->n_obs; i += LM_THREADS) v.r_obs_valid[i] = v.valid[i];
+	for (int i = LM_TID; i < h->n_unk_lms; i += LM_THREADS) v.r_lm_inv[i] = keep_grad ? 1 : (s.trials > 0 ? v.lm_inv[i] : 0);
+	for (int i = LM_TID; i < h->n_unk_lms * 9; i += LM_THREADS) v.r_Hf_diag[i] = v.Hf[i];
+	if (LM_TID == 0) {
+		srba_stats_t *st = v.stats;
+		st->num_iters = s.iter;
+		st->num_trials = s.trials;
+		st->num_accepted = s.accepted;
+		st->num_relinearized = s.relin;
+		st->num_chol_failures = s.cholfail;
+		st->num_jacobians = h->n_blkA + ((OBSK == SRBA_OBS_RELPOSES2D) ? 0 : h->n_blkF);
+		st->hessian_valid = s.trials > 0;
+		st->status = s.status;
+		st->total_sqr_error_final = s.err;
+		st->obs_rmse = s.rmse;
+		st->lambda_final = s.lambda;
+		unsigned long long *sc = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(v.stats) - h->res_stats + h->res_stage_cycles);
+		for (int i = 0; i < 24; i++) sc[i] = 0;
+	}
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ host driver
+// Per-stage maxima of the item counts over the areas of the group (the grid of a stage kernel is sized for the largest area;
+// the CTAs of smaller areas beyond their items find their loops empty).
+struct SrbaWaveDims {
+	int n_areas;
+	int max_pairs, max_blocks, max_hess_items, max_obs, max_scalars, max_unk, max_schur2, max_schur3, max_lms, max_edges_S, max_out;
+	int has_lms, solve_smem_bytes;
+};
+
+namespace {
+inline int wave_gx(int items, int threads, int cap = WAVE_CAP) { return std::max(1, std::min((items + threads - 1) / threads, cap)); }
+
+template <int P, int OBSK>
+int wave_run(const WaveArgs &a, const SrbaWaveDims &d, int *h_active_pinned, cudaStream_t st, int64_t *launches) {
+	constexpr bool can_fail = (OBSK == SRBA_OBS_MONO || OBSK == SRBA_OBS_STEREO);
+	const int n = d.n_areas;
+	auto grid = [&](int gx) { return dim3((unsigned)gx, (unsigned)n, 1); };
+	const int gx_chain = wave_gx(d.max_pairs, 256), gx_jac = wave_gx(d.max_blocks, 128), gx_hess = wave_gx(d.max_hess_items, 128);
+	const int gx_resid = wave_gx(d.max_obs, 256, WAVE_PART_CTAS), gx_grad = wave_gx(d.max_scalars, 128, WAVE_PART_CTAS), gx_upd = wave_gx(d.max_unk, 128);
+	const int gx_s1 = wave_gx(d.max_lms, 128), gx_s2 = wave_gx(d.max_schur2, 128), gx_s3 = wave_gx(d.max_schur3, 128);
+	const int gx_init = wave_gx(d.max_edges_S, 256), gx_out = wave_gx(d.max_out, 256);
+	int64_t nl = 0;
+	cudaLaunchConfig_t scfg = {};  // the solver: one cluster of WAVE_SOLVE_CTAS CTAs per area
+	scfg.gridDim = dim3(WAVE_SOLVE_CTAS, (unsigned)n, 1);
+	scfg.blockDim = dim3(WAVE_SOLVE_NT, 1, 1);
+	scfg.dynamicSmemBytes = 0;
+	scfg.stream = st;
+	cudaLaunchAttribute sattr[1];
+	sattr[0].id = cudaLaunchAttributeClusterDimension;
+	sattr[0].val.clusterDim.x = WAVE_SOLVE_CTAS; sattr[0].val.clusterDim.y = 1; sattr[0].val.clusterDim.z = 1;
+	scfg.attrs = sattr;
+	scfg.numAttrs = 1;
+	auto solve = wave_solve_kernel<P, OBSK>;
+	cudaMemsetAsync(a.active, 0, sizeof(int), st);
+	// ---- set-up: E (numeric spanning tree), F/G (Jacobians), lists, J (Hessian), M (residuals), N (gradient), L (lambda0)
+	wave_views_kernel<<<(n + 127) / 128, 128, 0, st>>>(a);
+	static const bool dbg = std::getenv("SRBA_WAVE_DEBUG") != nullptr;
+	if (dbg) { wave_dump_kernel<<<1, 1, 0, st>>>(a, 0); cudaStreamSynchronize(st); fprintf(stderr, "[wave] after views: %s\n", cudaGetErrorString(cudaGetLastError())); }
+	wave_init_kernel<P><<<grid(gx_init), 256, 0, st>>>(a);
+	if (dbg) { wave_dump_kernel<<<1, 1, 0, st>>>(a, 1); cudaStreamSynchronize(st); fprintf(stderr, "[wave] after init: %s\n", cudaGetErrorString(cudaGetLastError())); }
+	wave_chain_kernel<P><<<grid(gx_chain), 256, 0, st>>>(a, WHEN_SETUP);
+	if (dbg) { wave_dump_kernel<<<1, 1, 0, st>>>(a, 2); cudaStreamSynchronize(st); fprintf(stderr, "[wave] after chain: %s\n", cudaGetErrorString(cudaGetLastError())); }
+	wave_jacobians_kernel<P, OBSK><<<grid(gx_jac), 128, 0, st>>>(a, WHEN_SETUP, 0);
+	wave_jacobians_kernel<P, OBSK><<<grid(gx_jac), 128, 0, st>>>(a, WHEN_SETUP, 1);
+	wave_lists_kernel<<<grid(1), 64, 0, st>>>(a);
+	wave_hessian_kernel<P, OBSK><<<grid(gx_hess), 128, 0, st>>>(a, WHEN_SETUP);
+	wave_residuals_kernel<P, OBSK><<<grid(gx_resid), 256, 0, st>>>(a, WHEN_SETUP);
+	wave_gradient_or_restore_kernel<P, OBSK><<<grid(gx_grad), 128, 0, st>>>(a, 1);
+	wave_ctrl_init_kernel<P, OBSK><<<grid(1), 128, 0, st>>>(a);
+	nl += 10;
+	// ---- trials, all areas in lock step.  The count of areas that still iterate is read back with one trial of lag, so the
+	// next trial is already queued while the host waits (a trial queued after the last area finished finds every area idle).
+	cudaEvent_t ev[2];
+	cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+	cudaMemcpyAsync(&h_active_pinned[0], a.active, sizeof(int), cudaMemcpyDeviceToHost, st);
+	cudaEventRecord(ev[0], st);
+	int rc = 0;
+	for (int t = 0;; t++) {
+		cudaMemsetAsync(a.active, 0, sizeof(int), st);
+		if (d.has_lms) {
+			wave_schur_kernel<P, OBSK><<<grid(gx_s1), 128, 0, st>>>(a, 1);
+			wave_schur_kernel<P, OBSK><<<grid(gx_s2), 128, 0, st>>>(a, 2);
+			wave_schur_kernel<P, OBSK><<<grid(gx_s3), 128, 0, st>>>(a, 3);
+			nl += 3;
+		}
+		{ const cudaError_t e = cudaLaunchKernelEx(&scfg, solve, a); if (e != cudaSuccess) { rc = (int)e; break; } }
+		if (d.has_lms) { wave_features_kernel<P><<<grid(gx_s1), 128, 0, st>>>(a); nl++; }
+		wave_update_kernel<P><<<grid(gx_upd), 128, 0, st>>>(a);
+		wave_chain_kernel<P><<<grid(gx_chain), 256, 0, st>>>(a, WHEN_TRIAL_OK);
+		wave_residuals_kernel<P, OBSK><<<grid(gx_resid), 256, 0, st>>>(a, WHEN_TRIAL_OK);
+		wave_ctrl1_kernel<P, OBSK><<<grid(1), 128, 0, st>>>(a);
+		wave_jacobians_kernel<P, OBSK><<<grid(gx_jac), 128, 0, st>>>(a, WHEN_RELIN, 0);
+		if (can_fail) { wave_jacobians_kernel<P, OBSK><<<grid(gx_jac), 128, 0, st>>>(a, WHEN_RELIN, 1); nl++; }
+		wave_hessian_kernel<P, OBSK><<<grid(gx_hess), 128, 0, st>>>(a, WHEN_RELIN);
+		wave_gradient_or_restore_kernel<P, OBSK><<<grid(gx_grad), 128, 0, st>>>(a, 0);
+		wave_ctrl2_kernel<P, OBSK><<<(n + 31) / 32, 32, 0, st>>>(a);
+		nl += 9;
+		cudaMemcpyAsync(&h_active_pinned[(t + 1) & 1], a.active, sizeof(int), cudaMemcpyDeviceToHost, st);
+		cudaEventRecord(ev[(t + 1) & 1], st);
+		// wait for the count that PRECEDES the trial just queued
+		if (cudaEventSynchronize(ev[t & 1]) != cudaSuccess) { rc = (int)cudaGetLastError(); break; }
+		if (h_active_pinned[t & 1] == 0) break;  // nobody was iterating when trial t was queued: it was idle, done
+		if (t > 100000) { rc = (int)cudaErrorUnknown; break; }
+	}
+	wave_output_kernel<P, OBSK><<<grid(gx_out), 256, 0, st>>>(a);
+	nl++;
+	cudaEventDestroy(ev[0]);
+	cudaEventDestroy(ev[1]);
+	if (launches) *launches += nl;
+	if (rc) return rc;
+	return (int)cudaGetLastError();
+}
+}  // namespace
+
+// model: 0 = SE2+RelativePoses2D, 1 = SE3+Cartesian3D, 2 = SE3+Mono, 3 = SE3+Stereo.  scratch: device memory of
+// srba_wave_scratch_bytes(n) bytes; h_active_pinned: 2 ints of pinned host memory.  Blocks the host until every area is done.
+extern "C" size_t srba_wave_scratch_bytes(int n_areas) {
+	auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+	return al(sizeof(View) * (size_t)n_areas) + al(sizeof(WaveArea) * (size_t)n_areas) + al(sizeof(double) * (size_t)n_areas * WP_KINDS * WAVE_PART_CTAS) + 256;
+}
+extern "C" int srba_launch_lm_wave(int model, const char *img, const uint64_t *img_off, char *ws, const uint64_t *ws_off, char *res, const uint64_t *res_off,
+                                   const int32_t *order, const SrbaWaveDims *dims, char *scratch, int *h_active_pinned, void *stream, int64_t *launches) {
+	auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+	WaveArgs a;
+	a.img = img; a.img_off = img_off; a.ws = ws; a.ws_off = ws_off; a.res = res; a.res_off = res_off; a.order = order; a.n = dims->n_areas;
+	size_t off = 0;
+	a.views = reinterpret_cast<View *>(scratch + off); off += al(sizeof(View) * (size_t)a.n);
+	a.st = reinterpret_cast<WaveArea *>(scratch + off); off += al(sizeof(WaveArea) * (size_t)a.n);
+	a.partials = reinterpret_cast<double *>(scratch + off); off += al(sizeof(double) * (size_t)a.n * WP_KINDS * WAVE_PART_CTAS);
+	a.active = reinterpret_cast<int *>(scratch + off);
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	switch (model) {
+		case 0: return wave_run<3, SRBA_OBS_RELPOSES2D>(a, *dims, h_active_pinned, st, launches);
+		case 1: return wave_run<6, SRBA_OBS_CARTESIAN3D>(a, *dims, h_active_pinned, st, launches);
+		case 2: return wave_run<6, SRBA_OBS_MONO>(a, *dims, h_active_pinned, st, launches);
+		case 3: return wave_run<6, SRBA_OBS_STEREO>(a, *dims, h_active_pinned, st, launches);
+	}
+	return (int)cudaErrorInvalidValue;
+}

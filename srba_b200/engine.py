@@ -146,8 +146,13 @@ class RbaEngine:
                 "optimize_results": opt.as_dict(), "optimize_results_stg1": stg1.as_dict()}
 
     def optimize_local_area(self, root, win_size, optimize_k2k_edges=True, optimize_landmarks=True, max_visitable_kf_id=K.INVALID,
-                            dont_optimize_landmarks_seen_less_than_n_times=2):
+                            dont_optimize_landmarks_seen_less_than_n_times=2, observation_indices_to_optimize=None):
         o = K.OptInfo()
+        if observation_indices_to_optimize is not None and len(observation_indices_to_optimize):   # RbaEngine.h:235-241
+            lst = np.ascontiguousarray(observation_indices_to_optimize, dtype=np.uint64)
+            if self.L.srba_engine_optimize_local_area_obs(self.h, root, win_size, len(lst), ptr(lst, C.c_uint64), C.byref(o)) != 0:
+                raise self._err()
+            return o.as_dict()
         rc = self.L.srba_engine_optimize_local_area(self.h, root, win_size, int(optimize_k2k_edges), int(optimize_landmarks), max_visitable_kf_id,
                                                     dont_optimize_landmarks_seen_less_than_n_times, C.byref(o))
         if rc != 0:
@@ -178,7 +183,13 @@ class RbaEngine:
         h = self.L.srba_engine_flatten(self.h, len(a), ptr(a, C.c_uint64), len(b), ptr(b, C.c_uint64))
         return FlatProblem(h) if h else None
 
-    def flatten_local_area(self, root, win_size):
+    def flatten_local_area(self, root, win_size, observation_indices_to_optimize=None):
+        if observation_indices_to_optimize is not None and len(observation_indices_to_optimize):
+            lst = np.ascontiguousarray(observation_indices_to_optimize, dtype=np.uint64)
+            h = self.L.srba_engine_flatten_local_area_obs(self.h, root, win_size, len(lst), ptr(lst, C.c_uint64))
+            if not h:
+                raise self._err()
+            return FlatProblem(h)
         h = self.L.srba_engine_flatten_local_area(self.h, root, win_size)
         return FlatProblem(h) if h else None
 

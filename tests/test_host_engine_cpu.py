@@ -267,3 +267,36 @@ def test_eval_overall_c_abi_validates_its_arguments():
         assert rc == K.ERR_NO_DEVICE and b"no CUDA device" in L.srba_b200_last_error()
     else:
         assert rc == 0 and out.value > 0
+
+
+def test_observation_indices_to_optimize_flattening_and_oracle_semantics():
+    """RbaEngine::optimize_local_area(..., observation_indices_to_optimize) (RbaEngine.h:235-241, impl/optimize_edges.h:218-234): the
+    residual rows are the caller's list (repeats counted in nObs), the list must cover every observation of the unknown columns
+    (the ASSERT_ of compute_minus_gradient.h:55), Jacobian blocks / Hessian terms are unchanged.  Host flattening vs the oracle."""
+    ds = D.graphslam_se2_tour(60, seed=3)
+    kw = dict(S2, noise_lambda=D.se2_noise_lambda(ds["sigma_xy"], ds["sigma_yaw"]))
+    eo, ep = make_pair(kw)
+    for f in ds["frames"]:
+        D.feed(eo, f)
+        D.feed(ep, f, run_local_optimization=False)
+        inject_state(eo, ep)
+    root = 59
+    base = ep.flatten_local_area(root, 3)
+    obs = base.ids()["obs_global"]
+    lst = np.concatenate([obs[::-1], obs[:3]])            # every involved observation, reversed, three of them twice
+    flat = ep.flatten_local_area(root, 3, observation_indices_to_optimize=lst)
+    p, q = flat.p, base.p
+    assert (p.n_unk_edges, p.n_blkA, p.n_HAp, p.n_HAp_terms, p.n_obs) == (q.n_unk_edges, q.n_blkA, q.n_HAp, q.n_HAp_terms, q.n_obs)
+    assert p.n_total_obs_rows == len(lst)
+    assert flat.ids()["obs_global"].tolist() == obs[::-1].tolist()      # residual order = the caller's (first touch)
+    mult = dict(zip(flat.ids()["obs_global"].tolist(), flat.array("obs_mult", p.n_obs, np.int32).tolist()))
+    assert all(mult[int(g)] == (2 if g in obs[:3] else 1) for g in obs)
+    # total error over the listed rows == the oracle's initial error for the same list (state is identical: injected)
+    io = eo.optimize_local_area(root, 3, observation_indices_to_optimize=lst)
+    assert io["num_observations"] == len(lst)
+    assert abs(flat_total_error(flat, flat_pose_chain(flat)) - io["total_sqr_error_init"]) <= 1e-9 * io["total_sqr_error_init"]
+    # a list that misses an observation of an unknown column: both raise (the reference ASSERT_s)
+    with pytest.raises(RuntimeError):
+        ep.flatten_local_area(root, 3, observation_indices_to_optimize=obs[1:])
+    with pytest.raises(po.OracleError):
+        eo.optimize_local_area(root, 3, observation_indices_to_optimize=obs[1:])

@@ -171,3 +171,122 @@ def test_plan_fits_the_shared_memory_budget():
         assert L.srba_b200_problem_plan(fl.problem, out) == 0
         img, ws, res, sm, chol, n_img, n_ws, budget = list(out)
         assert 0 < sm <= budget and chol == 0 and n_ws >= 10 and img > 0 and res > 0
+
+
+# ------------------------------------------------------------------------------------------------ level schedule (wave pipeline)
+def level_schedule(flat):
+    L = K.lib()
+    counts = (C.c_int32 * 6)()
+    assert L.srba_b200_debug_level_schedule(flat.problem, counts, None, None, None, None, None, None) == 0
+    ntr, ntiles, nlev, ndst, ncon, ok = list(counts)
+    assert ok == 1
+    row2 = np.zeros(2 * (ntr + 1), np.int32); tij = np.zeros(ntiles, np.int32); src = np.zeros(ntiles, np.int32); orow = np.zeros(ntr, np.int32)
+    lv = np.zeros(2 * (nlev + 1), np.int32); gu = np.zeros(ndst + ndst + 1 + 2 * ncon, np.int32)
+    p32 = C.POINTER(C.c_int32)
+    assert L.srba_b200_debug_level_schedule(flat.problem, counts, *[a.ctypes.data_as(p32) for a in (row2, tij, src, orow, lv, gu)]) == 0
+    return ntr, row2.reshape(-1, 2), tij, src, orow, lv.reshape(-1, 2), gu[:ndst], gu[ndst:2 * ndst + 1], gu[2 * ndst + 1:].reshape(-1, 2)
+
+
+def emulate_levels(flat, P, rng):
+    """The level schedule executed step by step in numpy: per level A (pivot inverse, W = inv(D) T), then B (grouped destination
+    updates T(a,b) -= sum_k T(k,a)^t W(k,b)); backward pass by descending level.  Compared with a dense solve."""
+    p = flat.p
+    n_p, n = p.n_unk_edges, P * p.n_unk_edges
+    S_row, S_col = flat.array("S_row", p.n_S, np.int32), flat.array("S_col", p.n_S, np.int32)
+    blocks = rng.normal(size=(p.n_S, P, P))
+    A = np.zeros((n, n))
+    for b in range(p.n_S):
+        r, c = S_row[b], S_col[b]
+        if r == c:
+            blocks[b] = blocks[b] @ blocks[b].T + (4.0 * P + 0.3 * n_p) * np.eye(P)
+        A[P * r:P * r + P, P * c:P * c + P] = blocks[b]
+        A[P * c:P * c + P, P * r:P * r + P] = blocks[b].T
+    g = rng.normal(size=n)
+    lam = 0.37
+    Sflat = blocks.reshape(-1)
+    ntr, row, tij, src, orow, lv, dst, cptr, cab = level_schedule(flat)
+    assert sorted(orow.tolist()) == list(range(ntr)) and ntr == n // 3
+    T = np.zeros((len(tij), 3, 3))
+    for t in range(len(tij)):
+        ti, tj = tij[t] >> 16, tij[t] & 0xffff
+        assert ti <= tj <= ntr
+        if src[t] >= 0:
+            off = src[t] & 0x1fffffff
+            for a in range(3):
+                T[t, a] = Sflat[off + a * P: off + a * P + 3]
+            if (src[t] >> 29) & 1:
+                T[t] = T[t].T.copy()
+            assert bool(src[t] >> 30) == (ti == tj)
+            if ti == tj:
+                T[t] += lam * np.eye(3)
+        elif src[t] <= -2:
+            assert tj == ntr and -src[t] - 2 == orow[ti]
+            T[t, :, 0] = g[3 * orow[ti]:3 * orow[ti] + 3]
+    for k in range(ntr):   # rows contiguous, diagonal first, right-hand side last
+        cols = [tij[t] & 0xffff for t in range(row[k, 0], row[k, 1])]
+        assert cols[0] == k and cols[-1] == ntr and cols == sorted(cols) and all(tij[t] >> 16 == k for t in range(row[k, 0], row[k, 1]))
+    nlev = len(lv) - 1
+    assert lv[0, 0] == 0 and lv[-1, 0] == ntr and lv[-1, 1] == len(dst) and np.all(np.diff(lv[:, 0]) >= 1)
+    Wt = np.zeros_like(T)
+    for L in range(nlev):
+        rows_L = range(lv[L, 0], lv[L + 1, 0])
+        for k in rows_L:
+            Dinv = np.linalg.inv(T[row[k, 0]])
+            assert np.all(np.linalg.eigvalsh(T[row[k, 0]]) > 0)
+            for t in range(row[k, 0] + 1, row[k, 1]):
+                assert lv[L + 1, 0] <= (tij[t] & 0xffff)   # every column of a row lies in a HIGHER level (or is the right-hand side)
+                Wt[t] = Dinv @ T[t]
+        seen = set()
+        for e in range(lv[L, 1], lv[L + 1, 1]):
+            d = dst[e]
+            assert d not in seen   # one owner per destination and level
+            seen.add(d)
+            acc = np.zeros((3, 3))
+            last_k = -1
+            for c in range(cptr[e], cptr[e + 1]):
+                ta, tb = cab[c]
+                k = tij[ta] >> 16
+                assert k in rows_L and k == (tij[tb] >> 16) and k > last_k   # ascending source row, all of this level
+                last_k = k
+                assert (tij[d] >> 16) == (tij[ta] & 0xffff) and (tij[d] & 0xffff) == (tij[tb] & 0xffff)
+                acc += T[ta].T @ Wt[tb]
+            T[d] -= acc
+        # completeness: every pair of tiles of every row of the level is somebody's contribution
+        want = sum((row[k, 1] - row[k, 0] - 2) * (row[k, 1] - row[k, 0] - 1) // 2 + (row[k, 1] - row[k, 0] - 2) for k in rows_L)
+        assert want == cptr[lv[L + 1, 1]] - cptr[lv[L, 1]]
+    x = np.zeros((ntr, 3))
+    for L in range(nlev - 1, -1, -1):
+        for k in range(lv[L, 0], lv[L + 1, 0]):
+            acc = Wt[row[k, 1] - 1][:, 0].copy()
+            for t in range(row[k, 0] + 1, row[k, 1] - 1):
+                acc -= Wt[t] @ x[tij[t] & 0xffff]
+            x[k] = acc
+    ref = np.linalg.solve(A + lam * np.eye(n), g)
+    xo = np.zeros(n)
+    for t in range(ntr):
+        xo[3 * orow[t]:3 * orow[t] + 3] = x[t]
+    return xo, ref, nlev, ntr
+
+
+@pytest.mark.parametrize("kind", ["se2", "se3", "se2_loops"])
+def test_level_schedule_solves_the_reduced_system(kind):
+    rng = np.random.default_rng(12)
+    if kind == "se2_loops":   # a tour that revisits its path: loop closures, fill-in, several rows per level
+        ds = D.graphslam_se2_tour(420, seed=2)
+        kw = dict(pose_kind=0, obs_kind=0, noise_kind=1, noise_lambda=D.se2_noise_lambda(ds["sigma_xy"], ds["sigma_yaw"]), max_tree_depth=3,
+                  max_optimize_depth=3, submap_size=10, min_obs_to_loop_closure=1)
+        e = sb.RbaEngine(sb.default_engine_params(**kw))
+        flats = []
+        for k, f in enumerate(ds["frames"]):
+            D.feed(e, f, run_local_optimization=False)
+            if k in (300, 419):
+                flats.append(e.flatten_local_area(k, 3))
+        P = 3
+    else:
+        flats, P = (flats_se2(), 3) if kind == "se2" else (flats_se3(), 6)
+    for fl in flats:
+        x, ref, nlev, ntr = emulate_levels(fl, P, rng)
+        assert np.abs(x - ref).max() <= 1e-10 * max(1.0, np.abs(ref).max())
+        assert nlev <= ntr
+        if kind == "se2" and ntr >= 16:
+            assert nlev <= 0.6 * ntr   # independent minimum-degree rounds: a chain is halved per round, not peeled from its ends
