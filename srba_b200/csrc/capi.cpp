@@ -33,7 +33,7 @@ extern "C" int srba_launch_lm_batch(int model, const char *img, const uint64_t *
 struct SrbaWaveDims {
 	int n_areas;
 	int max_pairs, max_blocks, max_hess_items, max_obs, max_scalars, max_unk, max_schur2, max_schur3, max_lms, max_edges_S, max_out;
-	int has_lms, solve_smem_bytes;
+	int has_lms, n_big, n_solo, max_tail_rows;
 };
 extern "C" size_t srba_wave_scratch_bytes(int n_areas);
 extern "C" int srba_launch_lm_wave(int model, const char *img, const uint64_t *img_off, char *ws, const uint64_t *ws_off, char *res, const uint64_t *res_off,
@@ -273,7 +273,7 @@ struct TileSymbolic {
 	// level schedule (symbolic_levels, wave mode): `phase` holds 2 ints per level (+ sentinel) {first row, first dst entry}, `upd` holds
 	// [dst tile (n_dst) | contribution pointer (n_dst + 1) | 1 pad | (tile(k,a), tile(k,b)) x n_contrib]
 	bool levels = false;
-	int n_dst = 0, n_contrib = 0;
+	int n_dst = 0, n_contrib = 0, tail_level = 0;
 	void clear() { rs.clear(); row.clear(); phase.clear(); n_phases = 0; src.clear(); orow.clear(); on_chip = false; wide = false; tile_ij.clear(); upd_ptr.clear(); upd.clear(); ok = false; levels = false; n_dst = n_contrib = 0; }
 };
 // Elimination order of the unknown edges (block level).  The reference's own order is kept whenever its fill fits on chip
@@ -509,7 +509,7 @@ void symbolic_tiles(const srba_problem_t &p, int P, long max_tiles_on_chip, Tile
 //                  destination grouped (one 9-lane group owns the destination: no atomics, fixed summation order)
 // and the backward pass walks the levels downwards, one warp per row.  Two team barriers per level instead of one per block row:
 // a 641-edge loop-closure area has 150 levels for 641 rows, and every phase has enough independent work for thousands of threads.
-void symbolic_levels(const srba_problem_t &p, int P, TileSymbolic &sy) {
+void symbolic_levels(const srba_problem_t &p, int P, TileSymbolic &sy, bool debug_format = false) {
 	const int q = P / 3, np = p.n_unk_edges, ntr = q * np, ntc = ntr + 1;
 	sy.clear();
 	sy.ntr = ntr;
@@ -680,14 +680,38 @@ void symbolic_levels(const srba_problem_t &p, int P, TileSymbolic &sy) {
 	sy.phase[2 * (size_t)nlev] = ntr;
 	sy.phase[2 * (size_t)nlev + 1] = (int32_t)dst.size();
 	sy.n_phases = nlev;
+	// the tail: the last levels holding at most SRBA_WAVE_TAIL_ROWS tile rows in total (dense elimination in shared memory)
+	sy.tail_level = nlev;
+	while (sy.tail_level > 0 && ntr - sy.phase[2 * (size_t)(sy.tail_level - 1)] <= SRBA_WAVE_TAIL_ROWS) sy.tail_level--;
 	sy.n_dst = (int)dst.size();
 	sy.n_contrib = (int)(cab.size() / 2);
 	sy.upd.clear();
-	sy.upd.reserve(dst.size() + cptr.size() + cab.size());
-	sy.upd.insert(sy.upd.end(), dst.begin(), dst.end());
-	sy.upd.insert(sy.upd.end(), cptr.begin(), cptr.end());
-	sy.upd.push_back(0);  // pad: the (a,b) pairs start at the even offset 2 n_dst + 2 (read as int2)
-	sy.upd.insert(sy.upd.end(), cab.begin(), cab.end());
+	if (debug_format) {  // srba_b200_debug_level_schedule: [dst | contribution pointer | 1 pad | (tile(k,a), tile(k,b)) x n_contrib]
+		sy.upd.reserve(dst.size() + cptr.size() + cab.size());
+		sy.upd.insert(sy.upd.end(), dst.begin(), dst.end());
+		sy.upd.insert(sy.upd.end(), cptr.begin(), cptr.end());
+		sy.upd.push_back(0);
+		sy.upd.insert(sy.upd.end(), cab.begin(), cab.end());
+	} else {
+		// device format (lm_wave.cuh: wave_solve_fwd_kernel), 16-byte records so that a destination with ONE contribution -- almost all of
+		// them -- costs two dependent loads:  [n_dst x {dst, tile(k,a), tile(k,b), diagonal tile of row k} : the FIRST contribution]
+		// [n_dst + 1 pointers into the further contributions, padded to 4 ints] [{tile(k,a), tile(k,b), diagonal tile of row k, 0} ...]
+		const size_t nd = dst.size();
+		std::vector<int32_t> xptr(1, 0), extra;
+		sy.upd.reserve(4 * nd + nd + 4);
+		for (size_t e = 0; e < nd; e++) {
+			const int c0 = cptr[e], c1 = cptr[e + 1];
+			for (int c = c0; c < c1; c++) {
+				const int32_t ta = cab[2 * (size_t)c], tb = cab[2 * (size_t)c + 1], td = sy.rs[sy.tile_ij[ta] >> 16];
+				if (c == c0) { sy.upd.push_back(dst[e]); sy.upd.push_back(ta); sy.upd.push_back(tb); sy.upd.push_back(td); }
+				else { extra.push_back(ta); extra.push_back(tb); extra.push_back(td); extra.push_back(0); }
+			}
+			xptr.push_back((int32_t)(extra.size() / 4));
+		}
+		while (xptr.size() % 4) xptr.push_back(xptr.back());
+		sy.upd.insert(sy.upd.end(), xptr.begin(), xptr.end());
+		sy.upd.insert(sy.upd.end(), extra.begin(), extra.end());
+	}
 	sy.levels = true;
 	sy.ok = true;
 }
@@ -735,7 +759,11 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 	const int force_cluster = option(OPT_CLUSTER), force_wave = option(OPT_WAVE);
 	const uint64_t demand_no_tiles = (uint64_t)2 * p.n_pairs * S * 8 + (uint64_t)p.n_blkA * o * P * 8 + (uint64_t)p.n_blkF * o * 3 * 8 + (uint64_t)p.n_HAp * P * P * 8 +
 	                                 (uint64_t)2 * p.n_HApf * P * 3 * 8;
-	const bool wave_allowed = !want_dense && !force_blocked && force_cluster != 1 && force_wave != 0;
+	// Measured (profiles/r02_*): the wave pipeline wins on SE(2) loop-closure areas (hundreds of unknown edges, 100-240 elimination levels:
+	// 109 ms vs 172 ms per 256-area batch); on SE(3) landmark areas (n_p ~ 90, reduced system ~30 % dense) the level solver's tile
+	// traffic through L2 makes it slower than one CTA per area (540 vs 345 ms per 1 000 areas), so "auto" keeps those on the one-CTA /
+	// cluster-team program and the wave mode is opt-in there (option "wave" = 1).
+	const bool wave_allowed = !want_dense && !force_blocked && force_cluster != 1 && force_wave != 0 && (force_wave == 1 || model == 0);
 	bool cluster = false, wave = false;
 	if (!base) {  // layout pass: symbolic factorisation (reused by the copy pass)
 		if (wave_allowed && (force_wave == 1 || demand_no_tiles > (uint64_t)cfg.smem_bytes)) { symbolic_levels(p, P, sy); wave = sy.ok; }
@@ -770,6 +798,7 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 		h.ldl_tiles_in_ws = tiles_on_chip ? 0 : 1;
 		h.ldl_n_phases = sy.n_phases;
 		h.ldl_n_dst = sy.n_dst;
+		h.ldl_tail_level = sy.tail_level;
 		h.ldl_n_contrib = sy.n_contrib;
 		h.ldl_wide = sy.wide ? 1 : 0;
 		scratch_bytes = (uint64_t)reg_scratch * 8;
@@ -1263,7 +1292,9 @@ static srba_batch_t *batch_create_impl(int32_t n, const srba_problem_t *const *i
 				mx(d.max_edges_S, std::max<int64_t>((int64_t)h.n_edges * S, 2 * (int64_t)h.n_pairs));
 				mx(d.max_out, (int64_t)2 * h.n_pairs * S);
 				if (h.n_unk_lms > 0) d.has_lms = 1;
-				mx(d.solve_smem_bytes, (int64_t)(96 + 3 * (h.n_dense / 3) + 1) * 8);
+				const TileSymbolic &sy = b->sym[b->order[q]];
+				if (sy.tail_level > 0) { if (sy.n_dst >= SRBA_WAVE_TEAM_DST_PER_LEVEL * sy.tail_level) d.n_big++; else d.n_solo++; }
+				mx(d.max_tail_rows, (int64_t)sy.ntr - sy.phase[2 * (size_t)sy.tail_level]);
 			}
 			b->wave_scratch_off[m] = ws;
 			ws += (srba_wave_scratch_bytes(d.n_areas) + 255) / 256 * 256;
@@ -1432,7 +1463,7 @@ int srba_b200_debug_level_schedule(const srba_problem_t *in, int32_t counts[6], 
 	if (rc != SRBA_OK) return rc;
 	const int P = in->model.pose_kind == SRBA_POSE_SE2 ? 3 : 6;
 	TileSymbolic sy;
-	symbolic_levels(*in, P, sy);
+	symbolic_levels(*in, P, sy, true);
 	counts[0] = sy.ntr; counts[1] = (int32_t)sy.tile_ij.size(); counts[2] = sy.n_phases; counts[3] = sy.n_dst; counts[4] = sy.n_contrib; counts[5] = sy.ok ? 1 : 0;
 	if (!sy.ok) return SRBA_OK;
 	if (row2) for (int k = 0; k <= sy.ntr; k++) { row2[2 * k] = sy.row[4 * (size_t)k]; row2[2 * k + 1] = sy.row[4 * (size_t)k + 1]; }

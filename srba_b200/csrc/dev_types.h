@@ -13,6 +13,10 @@
 #include "../../include/srba_b200.h"
 
 #define SRBA_NOT_IN_SMEM 0xFFFFFFFFu
+// wave solver: tile rows of the trailing dense triangle that one CTA keeps in shared memory ((R+1)(R+2)/2 tiles of 72 B + row buffers)
+#define SRBA_WAVE_TAIL_ROWS 70
+// wave solver: an area whose levels below the tail hold at least this many destination tiles on average runs them as an 8-CTA cluster team
+#define SRBA_WAVE_TEAM_DST_PER_LEVEL 600
 
 // (type, name) of every array of the input image, in srba_problem_t order + derived ones: block -> column, and the
 // symbolic factorisation of the reduced system at 3x3-tile granularity (tiles numbered row-major, diagonal first, the
@@ -75,7 +79,7 @@ struct DevProblem {
 	int32_t wave;        // 1: solved by the grid-wide lock-step pipeline (lm_wave.cuh), every array in the global workspace
 	int32_t ldl_n_dst;   // wave: destinations / contributions of the level schedule (capi.cpp: symbolic_levels): ldl_phase holds
 	int32_t ldl_n_contrib;  //    {first row, first destination} per level, ldl_upd [dst | contribution pointer | (tile(k,a), tile(k,b))]
-	int32_t pad0_;
+	int32_t ldl_tail_level; // wave: first level of the TAIL -- the last <= SRBA_WAVE_TAIL_ROWS tile rows, eliminated densely in one CTA's shared memory
 	int32_t panel_cap;   // SRBA_CHOL_BLOCKED: columns of the staged 8-row panel that fit the scratch
 	int32_t ldl_n_tiles; // SRBA_CHOL_REG: 3x3 tiles of the filled pattern incl. the right-hand-side column
 	int32_t ldl_n_phases; // barrier-separated elimination phases (1 or 2 independent block rows each)

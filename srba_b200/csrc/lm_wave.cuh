@@ -43,6 +43,7 @@ struct WaveArgs {
 	WaveArea *st;          // n
 	double *partials;      // n x WP_KINDS x WAVE_PART_CTAS
 	int *active;           // [0]: areas still iterating after the last ctrl2
+	int *big, *solo;       // areas (positions in `order`) that have elimination levels below the tail: cluster teams / one CTA; [n] = fill counter
 };
 
 // Team of an area in a stage kernel: as many CTAs as the AREA has items (a function of the area alone, so that the grouping of
@@ -107,6 +108,11 @@ __global__ void wave_views_kernel(const WaveArgs a) {
 	const int pi = a.order[area];
 	const char *pimg = a.img + a.img_off[pi];
 	make_view(a.views[area], reinterpret_cast<const DevProblem *>(pimg), pimg, a.ws + a.ws_off[pi], a.res + a.res_off[pi], nullptr);
+	const DevProblem *h = reinterpret_cast<const DevProblem *>(pimg);
+	if (h->ldl_tail_level > 0) {  // levels below the tail: forward / backward kernels, as a cluster team or solo
+		if (h->ldl_n_dst >= SRBA_WAVE_TEAM_DST_PER_LEVEL * h->ldl_tail_level) a.big[atomicAdd(&a.big[a.n], 1)] = area;
+		else a.solo[atomicAdd(&a.solo[a.n], 1)] = area;
+	}
 }
 
 __global__ void wave_dump_kernel(const WaveArgs a, int tag) {
@@ -134,7 +140,7 @@ __global__ void __launch_bounds__(256) wave_init_kernel(const WaveArgs a) {
 		if (h->model.sensor_pose_kind == SRBA_SENSORPOSE_SE3) PoseOps<6>::inverse(s.sensor_inv, h->model.sensor_pose);
 		s.status = SRBA_OK;
 		s.go = 1;  // the set-up stages below run for every area
-		s.trial_ok = 0; s.accept = 0; s.do_relin = 0; s.cur = 0;
+		s.trial_ok = 0; s.accept = 0; s.do_relin = 0; s.cur = 0; s.chol_fail = 0;
 	}
 }
 
@@ -275,124 +281,309 @@ __global__ void __launch_bounds__(128) wave_schur_kernel(const WaveArgs a, int p
 	stage_schur<P>(v, s.lambda, phase);
 }
 
-// The reduced system of one area, solved by a CLUSTER of WAVE_SOLVE_CTAS CTAs with the LEVEL schedule of the packer (capi.cpp:
-// symbolic_levels): block-sparse L D L^t on 3x3 tiles kept in the global workspace (L2), the rows of one elimination level
-// processed together --
-//   A  one warp per row: pivot block inverted (cofactors; rejected exactly when a leading minor is <= 0, i.e. when Eigen::LLT would
-//      meet a non-positive pivot, lev-marq_solvers.h:527-534), W(k,.) = inv(D_k) T(k,.) written next to T;
-//   B  one 9-lane group per destination tile: T(a,b) -= sum_k T(k,a)^t W(k,b) over the contributions of this level, in ascending
-//      source row (deterministic, no atomics);
-// two cluster barriers per level; the backward pass x_k = y_k - sum_j W(k,j) x_j walks the levels downwards, one warp per row.
-// Solves what Eigen::LLT<Upper> + solve see after the dense fill (impl/lev-marq_solvers.h:492-549).  Afterwards CTA 0 books a failed
-// factorisation (not positive definite, optimize_edges.h:476-485) -- the later stages of this trial skip the area (trial_ok = 0).
+// ------------------------------------------------------------------------------------------------ the reduced system
+// Block-sparse L D L^t on 3x3 tiles with the LEVEL schedule of the packer (capi.cpp: symbolic_levels), solving what Eigen::LLT<Upper> +
+// solve see after the dense fill (impl/lev-marq_solvers.h:492-549).  Four launches per trial:
+//   fwd    (areas with levels below the tail; a CLUSTER of WAVE_SOLVE_CTAS CTAs each)  gather + the levels below the tail, tiles in the
+//          global workspace (L2):  A  W(k,.) = inv(D_k) T(k,.), one 9-lane group per tile (pivot block inverted by cofactors; rejected
+//          exactly when a leading minor is <= 0, i.e. when Eigen::LLT would meet a non-positive pivot, lev-marq_solvers.h:527-534);
+//          B  one 9-lane group per destination tile: T(a,b) -= sum_k T(k,a)^t W(k,b) over the contributions of this level, in ascending
+//          source row (deterministic, no atomics); two cluster barriers per level;
+//   tail   (every area; one CTA)  the last <= SRBA_WAVE_TAIL_ROWS tile rows -- the dense trailing front of a minimum-degree order, one
+//          row per level -- as a DENSE upper triangle in shared memory: one thread per destination tile, two CTA barriers per row,
+//          then their back-substitution in one warp;
+//   bwd    (as fwd)  x_k = y_k - sum_j W(k,j) x_j down the levels below the tail, one warp per row;
+//   finish (every area; one CTA)  increments back in the reference's unknown order; a failed factorisation (not positive definite,
+//          optimize_edges.h:476-485) is booked -- the later stages of this trial skip the area (trial_ok = 0).
 #define WAVE_SOLVE_CTAS 8
-#define WAVE_SOLVE_NT 256
-template <int P, int OBSK>
-__global__ void __launch_bounds__(WAVE_SOLVE_NT) wave_solve_kernel(const WaveArgs a) {
-	cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
-	const int area = blockIdx.y;
+#define WAVE_SOLVE_NT 1024
+#define WAVE_TAIL_NT 1024
+
+// Team of an area in the forward / backward kernels: a cluster of WAVE_SOLVE_CTAS x WAVE_SOLVE_NT threads when its levels are wide (many
+// destination tiles per level, list a.big), otherwise one CTA of WAVE_SOLO_NT threads (list a.solo; several per SM, CTA barriers).
+// The same predicate on the host (capi.cpp: batch_create_impl) sizes the two launches.
+#define WAVE_SOLO_NT 512
+#define WAVE_TEAM_SYNC()                                       \
+	do {                                                       \
+		if (TEAM) cooperative_groups::this_cluster().sync();   \
+		else __syncthreads();                                  \
+	} while (0)
+
+#ifdef SRBA_WAVE_TIMERS
+__device__ __forceinline__ unsigned long long wave_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define WT_DECL unsigned long long wt_ = wave_now(); unsigned long long *wsc_ = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(vg.stats) - h->res_stats + h->res_stage_cycles)
+#define WT_ADD(slot) do { if (tid == 0) { const unsigned long long n_ = wave_now(); wsc_[slot] += n_ - wt_; wt_ = n_; } } while (0)
+#else
+#define WT_DECL
+#define WT_ADD(slot)
+#endif
+
+// pivot block (upper part of a symmetric 3x3) -> cofactors / determinant; `bad` = a leading minor is <= 0
+struct Piv3 { double c00, c01, c02, c11, c12, c22, idet; bool bad; };
+__device__ __forceinline__ Piv3 piv3(double d00, double d01, double d02, double d11, double d12, double d22) {
+	Piv3 p;
+	p.c00 = d11 * d22 - d12 * d12; p.c01 = d02 * d12 - d01 * d22; p.c02 = d01 * d12 - d02 * d11;
+	p.c11 = d00 * d22 - d02 * d02; p.c12 = d01 * d02 - d00 * d12; p.c22 = d00 * d11 - d01 * d01;
+	const double det = d00 * p.c00 + d01 * p.c01 + d02 * p.c02;
+	p.bad = d00 <= 0 || p.c22 <= 0 || det <= 0;
+	p.idet = 1.0 / det;
+	return p;
+}
+// element (wa, wb) of tile `tl` of the reduced system: reduced block element (+lambda on the diagonal) / reduced gradient / fill-in
+template <int P>
+__device__ __forceinline__ double wave_tile_src(int so, int wa, int wb, const double *S, const double *grad, double lambda) {
+	if (so >= 0) return S[(so & 0x1fffffff) + ((so >> 29) & 1 ? wb * P + wa : wa * P + wb)] + (((so >> 30) && wa == wb) ? lambda : 0.0);
+	if (so <= -2 && wb == 0) return grad[3 * (-so - 2) + wa];
+	return 0.0;
+}
+
+// One contribution T(k,a)^t inv(D_k) T(k,b) to element (wa, wb) of a destination tile: D_k is final when the level of row k runs, so
+// inv(D_k) T(k,b) is formed on the fly (no separate W pass, no barrier for it).
+__device__ __forceinline__ double wave_contrib(const double *T, int ta, int tb, int td, int wa, int wb) {
+	const double *D = T + (size_t)td * 12, *Ta = T + (size_t)ta * 12 + wa * 4, *Tb = T + (size_t)tb * 12 + wb * 4;
+	const double d00 = D[0], d01 = D[4], d02 = D[8], d11 = D[5], d12 = D[9], d22 = D[10];
+	const double a0 = Ta[0], a1 = Ta[1], a2 = Ta[2], b0 = Tb[0], b1 = Tb[1], b2 = Tb[2];
+	const Piv3 pv = piv3(d00, d01, d02, d11, d12, d22);
+	const double w0 = pv.c00 * b0 + pv.c01 * b1 + pv.c02 * b2, w1 = pv.c01 * b0 + pv.c11 * b1 + pv.c12 * b2, w2 = pv.c02 * b0 + pv.c12 * b1 + pv.c22 * b2;
+	return (a0 * w0 + a1 * w1 + a2 * w2) * pv.idet;
+}
+
+// TEAM: a cluster of WAVE_SOLVE_CTAS CTAs per area (areas with wide levels, list a.big); otherwise one CTA per area (list a.solo)
+template <int P, int OBSK, bool TEAM>
+__global__ void __launch_bounds__(TEAM ? WAVE_SOLVE_NT : WAVE_SOLO_NT) wave_solve_fwd_kernel(const WaveArgs a) {
+	const int area = TEAM ? a.big[blockIdx.y] : a.solo[blockIdx.y];
 	WaveArea &s = a.st[area];
 	if (!s.go) return;  // (the same decision in every CTA of the cluster)
 	const View &vg = a.views[area];
 	const DevProblem *h = vg.h;
 	const double lambda = s.lambda;
-	const int n = h->n_dense, ntiles = h->ldl_n_tiles, nlev = h->ldl_n_phases, ndst = h->ldl_n_dst, NTR = n / 3;
-	double *T = vg.ldl_tiles, *Wt = T + (size_t)ntiles * 12, *x = Wt + (size_t)ntiles * 12;
-	const int2 *rowinfo = reinterpret_cast<const int2 *>(vg.ldl_row);   // (4 ints per row: .x first tile, .y end tile of row r at rowinfo[2 r])
-	const int32_t *tij = vg.ldl_tile_ij, *src = vg.ldl_src, *orow = vg.ldl_orow;
+	const int ntiles = h->ldl_n_tiles, L0 = h->ldl_tail_level, ndst = h->ldl_n_dst;
+	double *T = vg.ldl_tiles;
+	const int32_t *src = vg.ldl_src;
 	const int2 *lvl = reinterpret_cast<const int2 *>(vg.ldl_phase);      // {first row, first destination} per level
-	const int32_t *dst = vg.ldl_upd, *cptr = dst + ndst;
-	const int2 *cab = reinterpret_cast<const int2 *>(dst + 2 * ndst + 2);  // (pointer list padded to an even count)
+	const int4 *drec = reinterpret_cast<const int4 *>(vg.ldl_upd);       // {destination, first contribution (a, b, diagonal)}
+	const int32_t *xptr = vg.ldl_upd + 4 * (size_t)ndst;                 // further contributions of a destination (rare)
+	const int4 *xrec = reinterpret_cast<const int4 *>(xptr + ((ndst + 1 + 3) & ~3));
 	const double *S = vg.S, *grad = vg.grad;
 	const int tid = (int)(blockIdx.x * blockDim.x + threadIdx.x), NTH = (int)(gridDim.x * blockDim.x);
 	const int lane = tid & 31, gwarp = tid >> 5, NW = NTH >> 5;
 	const int wg = lane / 9, we = lane - wg * 9, wb = we / 3, wa = we - wb * 3, eo = wb * 4 + wa;  // 9-lane tile group: element (wa,wb)
 	const bool glane = lane < 27;
-	const bool keep_grad = (OBSK != SRBA_OBS_RELPOSES2D) && no_schur_solver(h);
-	if (tid == 0) s.chol_fail = 0;
-	// gather: tile element <- reduced block element (+lambda on the diagonal); tile column NTR = reduced gradient
-	if (glane) {
-		const double dl = wa == wb ? lambda : 0.0;
-		for (int tl = 3 * gwarp + wg; tl < ntiles; tl += 3 * NW) {
-			const int so = src[tl];
-			double val = 0.0;
-			if (so >= 0) val = S[(so & 0x1fffffff) + ((so >> 29) & 1 ? wb * P + wa : wa * P + wb)] + ((so >> 30) ? dl : 0.0);
-			else if (so <= -2 && wb == 0) val = grad[3 * (-so - 2) + wa];
-			T[(size_t)tl * 12 + eo] = val;
+	WT_DECL;
+	// gather: every tile (the tail kernel reads its rows from here too)
+	if (glane)
+		for (int tl = 3 * gwarp + wg; tl < ntiles; tl += 3 * NW) T[(size_t)tl * 12 + eo] = wave_tile_src<P>(src[tl], wa, wb, S, grad, lambda);
+	WAVE_TEAM_SYNC();
+	WT_ADD(0);
+	for (int L = 0; L < L0; L++) {
+		const int e1 = lvl[L + 1].y;
+		if (glane)
+			for (int e = lvl[L].y + gwarp * 3 + wg; e < e1; e += NW * 3) {
+				const int4 rec = drec[e];
+				const int x0 = xptr[e], x1 = xptr[e + 1];
+				double *dp = T + (size_t)rec.x * 12 + eo;
+				const double cur = *dp;
+				double acc = wave_contrib(T, rec.y, rec.z, rec.w, wa, wb);
+				for (int c = x0; c < x1; c++) {
+					const int4 xr = xrec[c];
+					acc += wave_contrib(T, xr.x, xr.y, xr.z, wa, wb);
+				}
+				*dp = cur - acc;
+			}
+		WT_ADD(3);
+		WAVE_TEAM_SYNC();
+		WT_ADD(4);
+	}
+}
+
+// local tile index of (i, j), j in i..r (r = right-hand side), in the dense upper triangle of r rows
+__device__ __forceinline__ int tail_base(int i, int r) { return i * (r + 1) - (i * (i - 1)) / 2; }
+__host__ __device__ inline size_t wave_tail_smem_bytes(int r) {
+	const size_t ntl = (size_t)r * (r + 3) / 2;
+	return ntl * 72 + 2 * (size_t)(r + 1) * 72 + ntl * 4 + (size_t)3 * r * 8 + 64;
+}
+
+template <int P, int OBSK>
+__global__ void __launch_bounds__(WAVE_TAIL_NT) wave_solve_tail_kernel(const WaveArgs a) {
+	extern __shared__ double tail_sm[];
+	const int area = blockIdx.x;
+	WaveArea &s = a.st[area];
+	if (!s.go) return;
+	const View &vg = a.views[area];
+	const DevProblem *h = vg.h;
+	const double lambda = s.lambda;
+	const int ntiles = h->ldl_n_tiles, L0 = h->ldl_tail_level, ntr = h->n_dense / 3;
+	const int2 *lvl = reinterpret_cast<const int2 *>(vg.ldl_phase);
+	const int2 *rowinfo = reinterpret_cast<const int2 *>(vg.ldl_row);
+	const int row0 = lvl[L0].x, r = ntr - row0;
+	if (r <= 0) return;
+	const int ntl = r * (r + 3) / 2;
+	double *Tl = tail_sm;                                  // ntl tiles of 9 doubles, row-major M[row * 3 + col]
+	double *Wbuf = Tl + (size_t)ntl * 9;                   // 2 x (r + 1) tiles: W(k, .) of the current / previous pivot row
+	uint32_t *ij = reinterpret_cast<uint32_t *>(Wbuf + (size_t)2 * (r + 1) * 9);  // local tile -> (i << 16 | j)
+	double *xs = reinterpret_cast<double *>(ij + ntl + (ntl & 1));
+	double *T = vg.ldl_tiles, *x = T + (size_t)ntiles * 24;
+	const int32_t *tij = vg.ldl_tile_ij, *src = vg.ldl_src;
+	const int nt = (int)blockDim.x, t_ = (int)threadIdx.x;
+	for (int i = t_; i < ntl * 9; i += nt) Tl[i] = 0.0;
+	for (int i = t_; i < r; i += nt) {
+		const int b0 = tail_base(i, r);
+		for (int j = i; j <= r; j++) ij[b0 + j - i] = ((uint32_t)i << 16) | (uint32_t)j;
+	}
+	__syncthreads();
+	{  // the rows of the tail: from the global tiles (areas with levels below the tail: updated by them) or straight from the reduced blocks
+		const bool from_T = L0 > 0;
+		const int g0 = rowinfo[2 * row0].x;
+		for (int q = t_; q < (ntiles - g0) * 9; q += nt) {
+			const int tl = g0 + q / 9, e = q % 9, wa = e / 3, wb = e % 3;
+			const int gij = tij[tl], i = (gij >> 16) - row0, gj = gij & 0xffff, j = gj == ntr ? r : gj - row0;
+			Tl[(size_t)(tail_base(i, r) + j - i) * 9 + e] = from_T ? T[(size_t)tl * 12 + wb * 4 + wa] : wave_tile_src<P>(src[tl], wa, wb, vg.S, vg.grad, lambda);
 		}
 	}
-	cl.sync();
-	if (keep_grad) {  // a landmark block that cannot be eliminated = the whole-system Cholesky fails (lev-marq_solvers.h:171-175)
-		for (int k = tid; k < h->n_unk_lms; k += NTH)
-			if (!vg.lm_inv[k]) s.chol_fail = 1;
+	__syncthreads();
+	for (int k = 0; k < r; k++) {
+		const int bk = tail_base(k, r);
+		double *buf = Wbuf + (size_t)(k & 1) * (r + 1) * 9;
+		const double *prev = Wbuf + (size_t)((k & 1) ^ 1) * (r + 1) * 9;
+		// ---- 1: W(k, j) = inv(D_k) T(k, j), j = k+1..r; the previous row's W goes to its place (read by the back-substitution)
+		{
+			const double *D = Tl + (size_t)bk * 9;
+			const Piv3 pv = piv3(D[0], D[1], D[2], D[4], D[5], D[8]);
+			if (t_ == 0 && pv.bad) s.chol_fail = 1;
+			for (int q = t_; q < (r - k) * 9; q += nt) {
+				const int jj = 1 + q / 9, e = q % 9, wa = e / 3, wb = e % 3;
+				const double i0 = (wa == 0 ? pv.c00 : wa == 1 ? pv.c01 : pv.c02) * pv.idet, i1 = (wa == 0 ? pv.c01 : wa == 1 ? pv.c11 : pv.c12) * pv.idet,
+				             i2 = (wa == 0 ? pv.c02 : wa == 1 ? pv.c12 : pv.c22) * pv.idet;
+				const double *Tc = Tl + (size_t)(bk + jj) * 9 + wb;
+				buf[jj * 9 + e] = i0 * Tc[0] + i1 * Tc[3] + i2 * Tc[6];
+			}
+			if (k > 0) {
+				const int bp = tail_base(k - 1, r);
+				for (int q = t_; q < (r - k + 1) * 9; q += nt) Tl[(size_t)(bp + 1) * 9 + q] = prev[9 + q];
+			}
+		}
+		__syncthreads();
+		// ---- 2: T(i, j) -= T(k, i)^t W(k, j), k < i <= j: the tiles of the rows below k are one contiguous range; one thread per tile
+		for (int u = tail_base(k + 1, r) + t_; u < ntl; u += nt) {
+			const uint32_t c = ij[u];
+			const int i = (int)(c >> 16), j = (int)(c & 0xffffu);
+			const double *A = Tl + (size_t)(bk + i - k) * 9, *B = buf + (size_t)(j - k) * 9;
+			double *Cc = Tl + (size_t)u * 9;
+			const double a0 = A[0], a1 = A[1], a2 = A[2], a3 = A[3], a4 = A[4], a5 = A[5], a6 = A[6], a7 = A[7], a8 = A[8];
+			const double b0 = B[0], b1 = B[1], b2 = B[2], b3 = B[3], b4 = B[4], b5 = B[5], b6 = B[6], b7 = B[7], b8 = B[8];
+			Cc[0] -= a0 * b0 + a3 * b3 + a6 * b6; Cc[1] -= a0 * b1 + a3 * b4 + a6 * b7; Cc[2] -= a0 * b2 + a3 * b5 + a6 * b8;
+			Cc[3] -= a1 * b0 + a4 * b3 + a7 * b6; Cc[4] -= a1 * b1 + a4 * b4 + a7 * b7; Cc[5] -= a1 * b2 + a4 * b5 + a7 * b8;
+			Cc[6] -= a2 * b0 + a5 * b3 + a8 * b6; Cc[7] -= a2 * b1 + a5 * b4 + a8 * b7; Cc[8] -= a2 * b2 + a5 * b5 + a8 * b8;
+		}
+		__syncthreads();
 	}
-	for (int L = 0; L < nlev; L++) {
-		const int2 l0 = lvl[L], l1 = lvl[L + 1];
-		// ---- A: rows of the level
-		for (int r = l0.x + gwarp; r < l1.x; r += NW) {
-			const int t0 = rowinfo[2 * r].x, t1 = rowinfo[2 * r].y;
+	{  // W of the last row (its right-hand-side tile only)
+		const double *last = Wbuf + (size_t)((r - 1) & 1) * (r + 1) * 9;
+		if (t_ < 9) Tl[(size_t)(tail_base(r - 1, r) + 1) * 9 + t_] = last[9 + t_];
+	}
+	__syncthreads();
+	// ---- back-substitution inside the tail: x_i = W(i, rhs) - sum_{j > i} W(i, j) x_j, one warp
+	if (t_ < 32) {
+		for (int i = r - 1; i >= 0; i--) {
+			const int bi = tail_base(i, r);
+			double p0 = 0, p1 = 0, p2 = 0;
+			for (int j = i + 1 + t_; j < r; j += 32) {
+				const double *Wij = Tl + (size_t)(bi + j - i) * 9, *xj = xs + 3 * j;
+				const double x0 = xj[0], x1 = xj[1], x2 = xj[2];
+				p0 += Wij[0] * x0 + Wij[1] * x1 + Wij[2] * x2;
+				p1 += Wij[3] * x0 + Wij[4] * x1 + Wij[5] * x2;
+				p2 += Wij[6] * x0 + Wij[7] * x1 + Wij[8] * x2;
+			}
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) {
+				p0 += __shfl_xor_sync(0xffffffffu, p0, o); p1 += __shfl_xor_sync(0xffffffffu, p1, o); p2 += __shfl_xor_sync(0xffffffffu, p2, o);
+			}
+			if (t_ < 3) xs[3 * i + t_] = Tl[(size_t)(bi + r - i) * 9 + 3 * t_] - (t_ == 0 ? p0 : t_ == 1 ? p1 : p2);
+			__syncwarp();
+		}
+	}
+	__syncthreads();
+	for (int i = t_; i < 3 * r; i += nt) x[3 * row0 + i] = xs[i];
+}
+
+// x_k = inv(D_k) (y_k - sum_j T(k,j) x_j) down the levels below the tail, one warp per row; the pivot blocks are final here: a block with a
+// non-positive leading minor books the failed factorisation.
+template <int P, int OBSK, bool TEAM>
+__global__ void __launch_bounds__(TEAM ? WAVE_SOLVE_NT : WAVE_SOLO_NT) wave_solve_bwd_kernel(const WaveArgs a) {
+	const int area = TEAM ? a.big[blockIdx.y] : a.solo[blockIdx.y];
+	WaveArea &s = a.st[area];
+	if (!s.go) return;
+	const View &vg = a.views[area];
+	const DevProblem *h = vg.h;
+	const int ntiles = h->ldl_n_tiles, L0 = h->ldl_tail_level;
+	const double *T = vg.ldl_tiles;
+	double *x = vg.ldl_tiles + (size_t)ntiles * 24;
+	const int2 *rowinfo = reinterpret_cast<const int2 *>(vg.ldl_row);
+	const int32_t *tij = vg.ldl_tile_ij;
+	const int2 *lvl = reinterpret_cast<const int2 *>(vg.ldl_phase);
+	const int tid = (int)(blockIdx.x * blockDim.x + threadIdx.x), NTH = (int)(gridDim.x * blockDim.x);
+	const int lane = tid & 31, gwarp = tid >> 5, NW = NTH >> 5;
+	WT_DECL;
+	for (int L = L0 - 1; L >= 0; L--) {
+		const int r0 = lvl[L].x, r1 = lvl[L + 1].x;
+		for (int r = r0 + gwarp; r < r1; r += NW) {
+			const int2 ri = rowinfo[2 * r];
+			const int t0 = ri.x, t1 = ri.y;
 			const double *D = T + (size_t)t0 * 12;
 			const double d00 = D[0], d01 = D[4], d02 = D[8], d11 = D[5], d12 = D[9], d22 = D[10];
-			const double c00 = d11 * d22 - d12 * d12, c01 = d02 * d12 - d01 * d22, c02 = d01 * d12 - d02 * d11;
-			const double c11 = d00 * d22 - d02 * d02, c12 = d01 * d02 - d00 * d12, c22 = d00 * d11 - d01 * d01;
-			const double det = d00 * c00 + d01 * c01 + d02 * c02;
-			if (lane == 0 && (d00 <= 0 || c22 <= 0 || det <= 0)) s.chol_fail = 1;
-			const double idet = 1.0 / det;
-			// row wa of inv(D) (symmetric)
-			const double i0 = (wa == 0 ? c00 : wa == 1 ? c01 : c02) * idet, i1 = (wa == 0 ? c01 : wa == 1 ? c11 : c12) * idet,
-			             i2 = (wa == 0 ? c02 : wa == 1 ? c12 : c22) * idet;
-			if (glane)
-				for (int tl = t0 + 1 + wg; tl < t1; tl += 3) {
-					const double *Tc = T + (size_t)tl * 12 + wb * 4;
-					Wt[(size_t)tl * 12 + eo] = i0 * Tc[0] + i1 * Tc[1] + i2 * Tc[2];
-				}
-		}
-		cl.sync();
-		// ---- B: destinations of the level
-		if (glane)
-			for (int e = l0.y + gwarp * 3 + wg; e < l1.y; e += NW * 3) {
-				const int c1 = cptr[e + 1];
-				double acc = 0.0;
-				for (int c = cptr[e]; c < c1; c++) {
-					const int2 ab = cab[c];
-					const double *Ta = T + (size_t)ab.x * 12 + wa * 4, *Wb = Wt + (size_t)ab.y * 12 + wb * 4;
-					acc += Ta[0] * Wb[0] + Ta[1] * Wb[1] + Ta[2] * Wb[2];
-				}
-				double *d = T + (size_t)dst[e] * 12 + eo;
-				*d -= acc;
+			double p0 = 0, p1 = 0, p2 = 0;
+			for (int tl = t0 + 1 + lane; tl < t1 - 1; tl += 32) {
+				const double *xj = x + 3 * (tij[tl] & 0xffff);
+				const double *Tr = T + (size_t)tl * 12;
+				const double x0 = xj[0], x1 = xj[1], x2 = xj[2];
+				p0 += Tr[0] * x0 + Tr[4] * x1 + Tr[8] * x2;
+				p1 += Tr[1] * x0 + Tr[5] * x1 + Tr[9] * x2;
+				p2 += Tr[2] * x0 + Tr[6] * x1 + Tr[10] * x2;
 			}
-		cl.sync();
-	}
-	// ---- backward pass by descending level: lane (t, a) = row a of the t-th (mod 8) off-diagonal tile of the row
-	{
-		const int t8 = lane >> 2, ra = lane & 3;
-		for (int L = nlev - 1; L >= 0; L--) {
-			const int r0 = lvl[L].x, r1 = lvl[L + 1].x;
-			for (int r = r0 + gwarp; r < r1; r += NW) {
-				const int t0 = rowinfo[2 * r].x, t1 = rowinfo[2 * r].y, m = t1 - t0 - 2;
-				double p = 0.0;
-				if (ra < 3)
-					for (int t = t8; t < m; t += 8) {
-						const int tl = t0 + 1 + t;
-						const double *xj = x + 3 * (tij[tl] & 0xffff);
-						const double *Wr = Wt + (size_t)tl * 12 + ra;
-						p += Wr[0] * xj[0] + Wr[4] * xj[1] + Wr[8] * xj[2];
-					}
-				p += __shfl_xor_sync(0xffffffffu, p, 4);
-				p += __shfl_xor_sync(0xffffffffu, p, 8);
-				p += __shfl_xor_sync(0xffffffffu, p, 16);
-				if (lane < 3) x[3 * r + lane] = Wt[(size_t)(t1 - 1) * 12 + lane] - p;
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) {
+				p0 += __shfl_xor_sync(0xffffffffu, p0, o); p1 += __shfl_xor_sync(0xffffffffu, p1, o); p2 += __shfl_xor_sync(0xffffffffu, p2, o);
 			}
-			cl.sync();
+			if (lane == 0) {
+				const Piv3 pv = piv3(d00, d01, d02, d11, d12, d22);
+				if (pv.bad) s.chol_fail = 1;
+				const double *y = T + (size_t)(t1 - 1) * 12;
+				const double y0 = y[0] - p0, y1 = y[1] - p1, y2 = y[2] - p2;
+				x[3 * r + 0] = (pv.c00 * y0 + pv.c01 * y1 + pv.c02 * y2) * pv.idet;
+				x[3 * r + 1] = (pv.c01 * y0 + pv.c11 * y1 + pv.c12 * y2) * pv.idet;
+				x[3 * r + 2] = (pv.c02 * y0 + pv.c12 * y1 + pv.c22 * y2) * pv.idet;
+			}
 		}
+		WT_ADD(5);
+		WAVE_TEAM_SYNC();
+		WT_ADD(6);
 	}
-	for (int i = tid; i < n; i += NTH) { const int r = i / 3; vg.delta[3 * orow[r] + (i - 3 * r)] = x[i]; }  // back to the reference's unknown order
-	if (blockIdx.x != 0) return;
-	// ---- CTA 0: outcome of the factorisation
-	const bool failed = s.chol_fail != 0;
+}
+
+template <int P, int OBSK>
+__global__ void __launch_bounds__(256) wave_solve_finish_kernel(const WaveArgs a) {
+	__shared__ int sh_fail;
+	const int area = blockIdx.x;
+	WaveArea &s = a.st[area];
+	if (!s.go) return;
+	const View &vg = a.views[area];
+	const DevProblem *h = vg.h;
+	const int n = h->n_dense;
+	const double *x = vg.ldl_tiles + (size_t)h->ldl_n_tiles * 24;
+	const int32_t *orow = vg.ldl_orow;
+	const bool keep_grad = (OBSK != SRBA_OBS_RELPOSES2D) && no_schur_solver(h);
+	if (threadIdx.x == 0) sh_fail = s.chol_fail;
+	__syncthreads();
+	if (keep_grad) {  // a landmark block that cannot be eliminated = the whole-system Cholesky fails (lev-marq_solvers.h:171-175)
+		for (int k = threadIdx.x; k < h->n_unk_lms; k += blockDim.x)
+			if (!vg.lm_inv[k]) sh_fail = 1;
+	}
+	for (int i = threadIdx.x; i < n; i += blockDim.x) { const int r = i / 3; vg.delta[3 * orow[r] + (i - 3 * r)] = x[i]; }  // back to the reference's unknown order
+	__syncthreads();
+	const bool failed = sh_fail != 0;
 	const int trial = s.trials;
 	const int nsc = h->n_scalars;
-	__syncthreads();
+	const double lambda = s.lambda;
 	if (failed) {
 		if (trial < h->trace_cap)
 			for (int i = threadIdx.x; i < nsc; i += blockDim.x) vg.r_trace_delta[(size_t)trial * nsc + i] = 0;
@@ -406,12 +597,14 @@ __global__ void __launch_bounds__(WAVE_SOLVE_NT) wave_solve_kernel(const WaveArg
 			s.nu *= 2.;
 			s.stop = (s.lambda > h->model.max_lambda);
 			s.trial_ok = 0;
+			s.chol_fail = 0;
 			wave_advance(s, h);
 			if (s.go) atomicAdd(a.active, 1);
 		}
 	} else if (threadIdx.x == 0) {
 		s.trial_ok = 1;
 		s.trial_lambda = lambda;
+		s.chol_fail = 0;
 	}
 }
 
@@ -571,7 +764,9 @@ __global__ void __launch_bounds__(256) wave_output_kernel(const WaveArgs a) {
 		st->obs_rmse = s.rmse;
 		st->lambda_final = s.lambda;
 		unsigned long long *sc = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(v.stats) - h->res_stats + h->res_stage_cycles);
+#ifndef SRBA_WAVE_TIMERS
 		for (int i = 0; i < 24; i++) sc[i] = 0;
+#endif
 	}
 }
 
@@ -583,7 +778,7 @@ __global__ void __launch_bounds__(256) wave_output_kernel(const WaveArgs a) {
 struct SrbaWaveDims {
 	int n_areas;
 	int max_pairs, max_blocks, max_hess_items, max_obs, max_scalars, max_unk, max_schur2, max_schur3, max_lms, max_edges_S, max_out;
-	int has_lms, solve_smem_bytes;
+	int has_lms, n_big, n_solo, max_tail_rows;  // n_big / n_solo: areas with levels below the tail (cluster team / one CTA); largest dense tail (tile rows)
 };
 
 namespace {
@@ -599,8 +794,8 @@ int wave_run(const WaveArgs &a, const SrbaWaveDims &d, int *h_active_pinned, cud
 	const int gx_s1 = wave_gx(d.max_lms, 128), gx_s2 = wave_gx(d.max_schur2, 128), gx_s3 = wave_gx(d.max_schur3, 128);
 	const int gx_init = wave_gx(d.max_edges_S, 256), gx_out = wave_gx(d.max_out, 256);
 	int64_t nl = 0;
-	cudaLaunchConfig_t scfg = {};  // the solver: one cluster of WAVE_SOLVE_CTAS CTAs per area
-	scfg.gridDim = dim3(WAVE_SOLVE_CTAS, (unsigned)n, 1);
+	cudaLaunchConfig_t scfg = {};  // forward / backward levels below the tail: one cluster of WAVE_SOLVE_CTAS CTAs per area that has such levels
+	scfg.gridDim = dim3(WAVE_SOLVE_CTAS, (unsigned)std::max(1, d.n_big), 1);
 	scfg.blockDim = dim3(WAVE_SOLVE_NT, 1, 1);
 	scfg.dynamicSmemBytes = 0;
 	scfg.stream = st;
@@ -609,7 +804,13 @@ int wave_run(const WaveArgs &a, const SrbaWaveDims &d, int *h_active_pinned, cud
 	sattr[0].val.clusterDim.x = WAVE_SOLVE_CTAS; sattr[0].val.clusterDim.y = 1; sattr[0].val.clusterDim.z = 1;
 	scfg.attrs = sattr;
 	scfg.numAttrs = 1;
-	auto solve = wave_solve_kernel<P, OBSK>;
+	auto solve_fwd = wave_solve_fwd_kernel<P, OBSK, true>;
+	auto solve_bwd = wave_solve_bwd_kernel<P, OBSK, true>;
+	auto solve_tail = wave_solve_tail_kernel<P, OBSK>;
+	const size_t tail_smem = wave_tail_smem_bytes(std::max(1, d.max_tail_rows));
+	if (cudaFuncSetAttribute(solve_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem) != cudaSuccess) return (int)cudaGetLastError();
+	cudaMemsetAsync(a.big + n, 0, sizeof(int), st);
+	cudaMemsetAsync(a.solo + n, 0, sizeof(int), st);
 	cudaMemsetAsync(a.active, 0, sizeof(int), st);
 	// ---- set-up: E (numeric spanning tree), F/G (Jacobians), lists, J (Hessian), M (residuals), N (gradient), L (lambda0)
 	wave_views_kernel<<<(n + 127) / 128, 128, 0, st>>>(a);
@@ -643,7 +844,13 @@ int wave_run(const WaveArgs &a, const SrbaWaveDims &d, int *h_active_pinned, cud
 			wave_schur_kernel<P, OBSK><<<grid(gx_s3), 128, 0, st>>>(a, 3);
 			nl += 3;
 		}
-		{ const cudaError_t e = cudaLaunchKernelEx(&scfg, solve, a); if (e != cudaSuccess) { rc = (int)e; break; } }
+		if (d.n_solo) { wave_solve_fwd_kernel<P, OBSK, false><<<dim3(1, (unsigned)d.n_solo, 1), WAVE_SOLO_NT, 0, st>>>(a); nl++; }
+		if (d.n_big) { const cudaError_t e = cudaLaunchKernelEx(&scfg, solve_fwd, a); if (e != cudaSuccess) { rc = (int)e; break; } nl++; }
+		solve_tail<<<n, WAVE_TAIL_NT, tail_smem, st>>>(a);
+		if (d.n_solo) { wave_solve_bwd_kernel<P, OBSK, false><<<dim3(1, (unsigned)d.n_solo, 1), WAVE_SOLO_NT, 0, st>>>(a); nl++; }
+		if (d.n_big) { const cudaError_t e = cudaLaunchKernelEx(&scfg, solve_bwd, a); if (e != cudaSuccess) { rc = (int)e; break; } nl++; }
+		wave_solve_finish_kernel<P, OBSK><<<n, 256, 0, st>>>(a);
+		nl++;
 		if (d.has_lms) { wave_features_kernel<P><<<grid(gx_s1), 128, 0, st>>>(a); nl++; }
 		wave_update_kernel<P><<<grid(gx_upd), 128, 0, st>>>(a);
 		wave_chain_kernel<P><<<grid(gx_chain), 256, 0, st>>>(a, WHEN_TRIAL_OK);
@@ -676,7 +883,8 @@ int wave_run(const WaveArgs &a, const SrbaWaveDims &d, int *h_active_pinned, cud
 // srba_wave_scratch_bytes(n) bytes; h_active_pinned: 2 ints of pinned host memory.  Blocks the host until every area is done.
 extern "C" size_t srba_wave_scratch_bytes(int n_areas) {
 	auto al = [](size_t x) { return (x + 255) / 256 * 256; };
-	return al(sizeof(View) * (size_t)n_areas) + al(sizeof(WaveArea) * (size_t)n_areas) + al(sizeof(double) * (size_t)n_areas * WP_KINDS * WAVE_PART_CTAS) + 256;
+	return al(sizeof(View) * (size_t)n_areas) + al(sizeof(WaveArea) * (size_t)n_areas) + al(sizeof(double) * (size_t)n_areas * WP_KINDS * WAVE_PART_CTAS) + 256 +
+	       2 * al(sizeof(int) * ((size_t)n_areas + 1));
 }
 extern "C" int srba_launch_lm_wave(int model, const char *img, const uint64_t *img_off, char *ws, const uint64_t *ws_off, char *res, const uint64_t *res_off,
                                    const int32_t *order, const SrbaWaveDims *dims, char *scratch, int *h_active_pinned, void *stream, int64_t *launches) {
@@ -687,7 +895,9 @@ extern "C" int srba_launch_lm_wave(int model, const char *img, const uint64_t *i
 	a.views = reinterpret_cast<View *>(scratch + off); off += al(sizeof(View) * (size_t)a.n);
 	a.st = reinterpret_cast<WaveArea *>(scratch + off); off += al(sizeof(WaveArea) * (size_t)a.n);
 	a.partials = reinterpret_cast<double *>(scratch + off); off += al(sizeof(double) * (size_t)a.n * WP_KINDS * WAVE_PART_CTAS);
-	a.active = reinterpret_cast<int *>(scratch + off);
+	a.active = reinterpret_cast<int *>(scratch + off); off += 256;
+	a.big = reinterpret_cast<int *>(scratch + off); off += al(sizeof(int) * ((size_t)a.n + 1));
+	a.solo = reinterpret_cast<int *>(scratch + off);
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
 	switch (model) {
 		case 0: return wave_run<3, SRBA_OBS_RELPOSES2D>(a, *dims, h_active_pinned, st, launches);

@@ -645,18 +645,17 @@ def _restore(eng, edge_poses, lm_ids, lm_pos):
 def test_g5_mode_batch_of_heavy_areas_vs_oracle(mode):
     """BASELINE config #5 at a size the oracle finishes in seconds: one SE(3) + Cartesian3D map built WITHOUT optimisation, the depth-5
     local areas of every 6th keyframe -- 41 heavy areas -- as independent problems with snapshot semantics, in the two
-    modes a batch of heavy areas can run in: "wave" = the grid-wide lock-step pipeline (default; the mode of the round-2 config #5
-    number), "one_cta" = one CTA per area with the overflow in the global workspace (the mode of the round-1 number).
+    modes a batch of heavy areas can run in: "wave" = the grid-wide lock-step pipeline (opt-in for SE(3) areas, default for SE(2)
+    loop-closure areas), "one_cta" = one CTA per area with the overflow in the global workspace (the mode of the config #5 number).
     Each area against the oracle started from the same snapshot: counts bit-exact, initial error 1e-9, decisions and
     increments trial by trial on the strict prefix, final unknown edges and landmarks <= 1e-6."""
     from srba_b200 import _capi as K
-    old = (K.set_option("cluster", 0), K.set_option("wave", 0)) if mode == "one_cta" else None
+    old = (K.set_option("cluster", 0), K.set_option("wave", 0)) if mode == "one_cta" else (K.set_option("cluster", -1), K.set_option("wave", 1))
     try:
         _g5_mode_batch(mode)
     finally:
-        if old:
-            K.set_option("cluster", old[0])
-            K.set_option("wave", old[1])
+        K.set_option("cluster", old[0])
+        K.set_option("wave", old[1])
 
 
 def _g5_mode_batch(mode):

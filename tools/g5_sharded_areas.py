@@ -25,9 +25,11 @@ ap.add_argument("--lms", type=int, default=100000)
 ap.add_argument("--depth", type=int, default=5)
 ap.add_argument("--stride", type=int, default=10)
 ap.add_argument("--max-areas", type=int, default=0)
+ap.add_argument("--wave", type=int, default=-1, help="-1 auto | 0 one CTA per area | 1 wave pipeline for every area")
 ap.add_argument("--plan-only", action="store_true")
 ap.add_argument("--cpu-areas", type=int, default=0, help="also time the oracle (1 thread) on the first K areas of rank 0")
 a = ap.parse_args()
+K.set_option("wave", a.wave)
 rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 ds = D.landmark_slam_se3(n_kfs=a.kfs, n_lms=a.lms, seed=1, obs_kind="cartesian3d")
@@ -92,7 +94,7 @@ if rank == 0:
     peak, peak_src = B.measured_peaks()
     line["roofline_rank0"] = dict(bound="hbm", algorithmic_bytes=ab["total_bytes"], achieved_gbs=ab["total_bytes"] / (ms * 1e-3) / 1e9, peak_gbs=peak,
                                   frac=ab["total_bytes"] / (ms * 1e-3) / 1e9 / peak, peak_source=peak_src,
-                                  stage_bytes={k: ab[k] for k in ("chain", "assem_res", "assem_jh", "schur", "chol")}, chol_flop=ab["chol_flop"])
+                                  stage_bytes={k: ab[k] for k in ("chain", "assem_res", "assem_jh", "jacmat", "schur", "solve", "update")}, dense_equiv_chol_flop=ab["chol_flop"])
     print(json.dumps(line))
     if a.cpu_areas:
         from oracle import pyoracle as po
