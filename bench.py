@@ -181,11 +181,10 @@ def build_problems(seed, areas, n_kfs, noise_seed=None, last=False, extra_sample
 
 # ---------------------------------------------------------------------------------------------------------- CPU legs (oracle)
 def cpu_fixture_worker(args):
-    """Oracle on a share of the fixture's areas: the graph is rebuilt from the tour's frames (no optimisation), at each of this
-    worker's keyframes the touched edges get the stored pre-optimisation poses and optimize_local_area(k, 3) -- the problem of
-    the batch -- is timed ('opt' span, impl/optimize_edges.h:56,786), `reps` times from the same inputs.
-    Returns per repetition (seconds, LM trials)."""
-    mine, reps = args
+    """Oracle on a share of the fixture's areas, ONE pass: the graph is rebuilt from the tour's frames (no optimisation), at each of
+    this worker's keyframes the touched edges get the stored pre-optimisation poses and optimize_local_area(k, 3) -- the problem of
+    the batch -- is timed ('opt' span, impl/optimize_edges.h:56,786).  Returns per area, in keyframe order: (seconds, LM trials, n_p)."""
+    mine = sorted(set(args))
     from oracle import pyoracle as po
     from srba_b200 import datasets as D
     fx = np.load(FIXTURE)
@@ -193,7 +192,7 @@ def cpu_fixture_worker(args):
     e = po.OracleEngine(po.default_params(**engine_kwargs(ds)))
     at = {int(fx["kf"][i]): i for i in mine}
     last = max(at) if at else -1
-    sec, tr = np.zeros(reps), np.zeros(reps)
+    out = []
     for k, f in enumerate(ds["frames"]):
         if k > last:
             break
@@ -203,15 +202,25 @@ def cpu_fixture_worker(args):
         i = at[k]
         ids = fx["edge_id"][fx["edge_ptr"][i]:fx["edge_ptr"][i + 1]]
         poses = fx["edge_in"][fx["edge_ptr"][i]:fx["edge_ptr"][i + 1]]
-        for r in range(reps):
-            for eid, q in zip(ids, poses):
-                e.set_edge_pose(int(eid), q)
-            s0, t0 = e.opt_timer()
-            e.optimize_local_area(k, 3)
-            s1, t1 = e.opt_timer()
-            sec[r] += s1 - s0
-            tr[r] += t1 - t0
-    return sec.tolist(), tr.tolist()
+        for eid, q in zip(ids, poses):
+            e.set_edge_pose(int(eid), q)
+        s0, t0 = e.opt_timer()
+        e.optimize_local_area(k, 3)
+        s1, t1 = e.opt_timer()
+        out.append((s1 - s0, t1 - t0, int(fx["n_p"][i]) if "n_p" in fx else -1))
+    return out
+
+
+def cpu_sample(n_areas, workers, per_worker):
+    """Bounded sample of the batch for the CPU legs: workers x per_worker areas evenly spaced over the batch (with wrap-around when
+    that exceeds the batch), dealt round-robin; every worker solves its areas once, in keyframe order, concurrently with the others.
+    Returns a list (per worker) of per-area (seconds, trials, n_p)."""
+    import multiprocessing as mp
+    m = workers * per_worker
+    idx = [int(j * n_areas / m) % n_areas for j in range(m)]
+    shares = [sorted(set(idx[w::workers])) for w in range(workers)]
+    with mp.get_context("spawn").Pool(workers) as pool:
+        return pool.map(cpu_fixture_worker, shares)
 
 
 def cpu_pass(args):
@@ -246,33 +255,40 @@ def fixture_matches(args):
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  The reference itself cannot be built here
     (MRPT + Eigen absent), so this times the oracle port, one independent single-threaded engine per host core
-    (BASELINE.md §2.3), on a bounded sample of the batch: every 4th of the 256 areas, dealt round-robin to the cores."""
+    (BASELINE.md §2.3).  A STEP is a bounded sample of the batch: one local area per core (the areas of all steps are spaced evenly
+    over the 256-area batch, loop-closure areas included); value = LM trials / (core-seconds / cores), i.e. the CPU throughput with
+    every core busy and perfect load balance."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
     from srba_b200 import datasets as D
     cores = max(1, len(os.sched_getaffinity(0)))
-    ctx = mp.get_context("spawn")
     reps = args.warmup + args.steps
     if fixture_matches(args):
-        sample = list(range(0, args.areas, 4))
-        workers = min(cores, len(sample))
-        with ctx.Pool(workers) as pool:
-            res = pool.map(cpu_fixture_worker, [(sample[w::workers], reps) for w in range(workers)])
-        sec = np.array([r[0] for r in res])[:, args.warmup:]     # workers x steps
-        tr = np.array([r[1] for r in res])[:, args.warmup:]
-        step_s = sec.max(axis=0)                                   # a step lasts as long as its slowest core
-        val = float(tr.sum() / step_s.sum())
-        sample_txt = ("%d single-threaded oracle engines in parallel (one per host core) re-solve every 4th of the %d areas (%d areas, dealt round-robin) "
-                      "from the stored inputs of the %d-keyframe tour (tests/golden/g4_tour3000_states.npz); 'opt' span only; value = all LM trials / slowest core, per step"
-                      % (workers, args.areas, len(sample), args.kfs))
-        ms = 1e3 * float(step_s.mean())
-        used = workers
-    else:
+        res = cpu_sample(args.areas, cores, reps)
+        sec = np.zeros(reps)
+        tr = np.zeros(reps)
+        for wi, w in enumerate(res):
+            # a worker solves its areas in keyframe order (the graph grows with the tour); which STEP an area counts for is shuffled, so that
+            # the warm-up steps are not systematically the early -- small -- areas of the tour
+            label = np.random.RandomState(1234 + wi).permutation(reps)
+            for j, (s_, t_, _) in enumerate(w):
+                sec[label[j % reps]] += s_
+                tr[label[j % reps]] += t_
+        sec, tr = sec[args.warmup:], tr[args.warmup:]
+        val = float(cores * tr.sum() / sec.sum())
+        ms = 1e3 * float(sec.mean() / cores)
+        n_p = [q for w in res for (_, _, q) in w]
+        sample_txt = ("%d single-threaded oracle engines in parallel (one per host core); each step = one local area per core, the %d areas of all steps spaced "
+                      "evenly over the %d-area batch of the %d-keyframe tour (n_p %d..%d, median %d; inputs: tests/golden/g4_tour3000_states.npz), each solved "
+                      "once; 'opt' span only; value = cores x LM trials / core-seconds of the timed steps (perfect load balance)"
+                      % (cores, len(n_p), args.areas, args.kfs, min(n_p), max(n_p), int(np.median(n_p))))
+        used = cores
+    elif args.kfs <= 1000:
         sampled = (np.arange(args.kfs - args.areas, args.kfs) if args.chain_like else D.sample_keyframes(args.kfs, args.areas)).tolist()
         per_step = []
-        with ctx.Pool(cores) as pool:
+        with mp.get_context("spawn").Pool(cores) as pool:
             for step in range(reps):
                 res = pool.map(cpu_pass, [(args.tour_seed, args.kfs, sampled[w::cores]) for w in range(cores)])
                 if step >= args.warmup:
@@ -282,6 +298,10 @@ def run_reference(args):
         sample_txt = ("%d single-threaded oracle engines in parallel (one per core) each run the whole %d-keyframe tour and time their share of the %d sampled "
                       "local areas; 'opt' span only; value = all LM trials / slowest core" % (cores, args.kfs, args.areas))
         used = cores
+    else:
+        print(json.dumps({"impl": "reference", "unavailable": "no oracle fixture for --kfs %d --areas %d --tour-seed %d (a sequential oracle run of such a tour takes hours): "
+                          "run tests/golden/make_g4_states.py" % (args.kfs, args.areas, args.tour_seed)}))
+        return
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.areas, args.kfs), "areas_per_gpu": args.areas, "tour_keyframes": args.kfs,
@@ -338,11 +358,16 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.impl == "reference":
+        if args.config != 4:
+            if int(os.environ.get("RANK", "0")) == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "the oracle needs minutes to hours per LM iteration on the whole-map / 1 000-area problems of config "
+                                  "%d (profiles/r01_v7_whole_map_*.txt, r01_v8_g5_sharded_areas.txt hold one-off CPU timings)" % args.config}))
+            return
+        return run_reference(args)
     if args.config != 4:
         from tools import bench_configs
         return bench_configs.main(args)
-    if args.impl == "reference":
-        return run_reference(args)
 
     import torch
     import torch.distributed as dist
@@ -510,18 +535,24 @@ def main():
                          "ncu_source": ncu.get("source")}}
     if not args.no_cpu_baseline and world == 1:
         t = time.perf_counter()
+        cores = max(1, len(os.sched_getaffinity(0)))
         if fixture_matches(args):
-            sample = list(range(0, args.areas, 16))
-            sec, tr = cpu_fixture_worker((sample, 1))
-            sec, tr = sec[0], tr[0]
-            txt = ("oracle (g++ -O2, 1 thread): 'opt' span of every 16th of the %d areas (%d areas) re-solved from the stored inputs of the same tour "
-                   "(tests/golden/g4_tour3000_states.npz)" % (args.areas, len(sample)))
-        else:
+            res = cpu_sample(args.areas, cores, 2)
+            sec = sum(s_ for w in res for (s_, _, _) in w)
+            tr = sum(t_ for w in res for (_, t_, _) in w)
+            n_p = [q for w in res for (_, _, q) in w]
+            txt = ("oracle (g++ -O2), single-thread rate: %d areas spaced evenly over the %d-area batch (n_p %d..%d, median %d; inputs: tests/golden/g4_tour3000_states.npz), "
+                   "each solved once by one of %d concurrent single-threaded engines; 'opt' span only; value = LM trials / summed engine seconds"
+                   % (len(n_p), args.areas, min(n_p), max(n_p), int(np.median(n_p)), cores))
+            line["cpu_baseline"] = {"value": tr / sec, "unit": UNIT, "cores": 1, "kind": "port", "sample": txt + " (%.1f s wall)" % (time.perf_counter() - t)}
+        elif args.kfs <= 1000:
             from srba_b200 import datasets as D
             sampled = (np.arange(args.kfs - args.areas, args.kfs) if args.chain_like else D.sample_keyframes(args.kfs, args.areas)).tolist()
             sec, tr = cpu_pass((args.tour_seed, args.kfs, sampled))
             txt = "oracle (g++ -O2, 1 thread): 'opt' span of the %d sampled local areas during a full sequential run of the %d-keyframe tour" % (len(sampled), args.kfs)
-        line["cpu_baseline"] = {"value": tr / sec, "unit": UNIT, "cores": 1, "kind": "port", "sample": txt + " (%.1f s wall)" % (time.perf_counter() - t)}
+            line["cpu_baseline"] = {"value": tr / sec, "unit": UNIT, "cores": 1, "kind": "port", "sample": txt + " (%.1f s wall)" % (time.perf_counter() - t)}
+        else:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": "no oracle fixture for this tour (tests/golden/make_g4_states.py)"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

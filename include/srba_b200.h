@@ -172,6 +172,14 @@ typedef struct srba_batch srba_batch_t;
 /* Packs n problems into one pinned host image + sizes the device image/workspace.  Problems are copied. */
 srba_batch_t *srba_b200_batch_create(int32_t n, const srba_problem_t *const *in, int32_t trace_cap);
 int srba_b200_batch_upload(srba_batch_t *b, void *cuda_stream);    /* one H2D copy of the packed image */
+/* Persistent problem handles: a batch keeps its SYMBOLIC structure -- CSR index arrays, Hessian / Schur term lists, the
+ * elimination schedule of the reduced system, the shared-memory plan -- resident on the device between runs.  When only the NUMERIC
+ * inputs of a problem change (the same unknowns and observations re-optimised from new edge poses / landmark positions / measurements,
+ * e.g. after neighbouring areas moved), batch_update_values overwrites those arrays in the pinned image (counts as in the problem the
+ * batch was created from; a NULL array keeps its values) and batch_upload_values copies just them: no symbolic work, no re-pack.
+ * Replaces the per-call rebuilds of impl/sparse_hessian_build_symbolic.h:22-237 and impl/schur.h:25-159 for repeated solves. */
+int srba_b200_batch_update_values(srba_batch_t *b, int32_t i, const double *edge_pose, const double *lm_pos, const double *obs_z);
+int srba_b200_batch_upload_values(srba_batch_t *b, void *cuda_stream);
 int srba_b200_batch_run(srba_batch_t *b, void *cuda_stream);       /* device-resident: whole LM loop for every problem */
 int srba_b200_batch_download(srba_batch_t *b, void *cuda_stream);  /* one D2H copy of the packed results + stream sync */
 int srba_b200_batch_unpack(srba_batch_t *b, int32_t i, srba_result_t *out); /* host: copy problem i's results out */

@@ -36,6 +36,20 @@ class Batch:
     def upload(self, stream=0):
         self._chk(self.L.srba_b200_batch_upload(self.h, C.c_void_p(stream)))
 
+    def update_values(self, i, edge_pose=None, lm_pos=None, obs_z=None):
+        """srba_b200_batch_update_values: new numeric inputs for problem i (same structure); None keeps an array."""
+        def p(a):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            self._keep.append(a)
+            return a.ctypes.data_as(C.POINTER(C.c_double))
+        self._keep = []
+        self._chk(self.L.srba_b200_batch_update_values(self.h, i, p(edge_pose), p(lm_pos), p(obs_z)))
+
+    def upload_values(self, stream=0):
+        self._chk(self.L.srba_b200_batch_upload_values(self.h, C.c_void_p(stream)))
+
     def run(self, stream=0):
         self._chk(self.L.srba_b200_batch_run(self.h, C.c_void_p(stream)))
 

@@ -15,6 +15,7 @@
 #include <pthread.h>
 #include <sched.h>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -1097,6 +1098,7 @@ struct srba_batch {
 	std::vector<DevProblem> hdr;
 	std::vector<TileSymbolic> sym;
 	std::vector<uint64_t> img_off, ws_off, res_off;
+	std::vector<int32_t> dirty_values;  // problems whose numeric inputs changed in the pinned image since the last upload (batch_update_values)
 	std::vector<int32_t> order;      // grouped by model, cost-descending inside each group
 	int group_begin[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // 4 models x {one CTA, 8-CTA cluster, grid-wide wave} per problem
 	int group_max_n[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -1330,6 +1332,45 @@ int srba_b200_batch_upload(srba_batch_t *b, void *stream) {
 	if (!b) return fail(SRBA_ERR_BAD_ARGUMENT, "null batch");
 	CUDA_TRY(cudaMemcpyAsync(b->d_img, b->h_img, b->img_bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
 	b->uploaded = true;
+	return SRBA_OK;
+}
+
+int srba_b200_batch_update_values(srba_batch_t *b, int32_t i, const double *edge_pose, const double *lm_pos, const double *obs_z) {
+	if (!b || i < 0 || i >= b->n) return fail(SRBA_ERR_BAD_ARGUMENT, "bad batch_update_values arguments");
+	const DevProblem &h = b->hdr[i];
+	char *base = b->h_img + b->img_off[i];
+	const double *srcs[3] = {edge_pose, lm_pos, obs_z};
+	const int ids[3] = {SRBA_I_edge_pose, SRBA_I_lm_pos, SRBA_I_obs_z};
+	for (int k = 0; k < 3; k++) {
+		if (!srcs[k] || !h.img_len[ids[k]]) continue;
+		const size_t n = h.img_len[ids[k]] / 8;
+		for (size_t j = 0; j < n; j++)
+			if (!std::isfinite(srcs[k][j])) return fail(SRBA_ERR_NON_FINITE, "batch_update_values: non-finite input value");
+		std::memcpy(base + h.img_off[ids[k]], srcs[k], h.img_len[ids[k]]);
+		b->dirty_values.push_back(i);
+	}
+	return SRBA_OK;
+}
+
+int srba_b200_batch_upload_values(srba_batch_t *b, void *stream) {
+	if (!b) return fail(SRBA_ERR_BAD_ARGUMENT, "null batch");
+	if (!b->uploaded) return srba_b200_batch_upload(b, stream);   // nothing resident yet: the whole image
+	std::sort(b->dirty_values.begin(), b->dirty_values.end());
+	b->dirty_values.erase(std::unique(b->dirty_values.begin(), b->dirty_values.end()), b->dirty_values.end());
+	if (b->dirty_values.size() > 64) {  // many small copies cost more than one large one
+		b->dirty_values.clear();
+		return srba_b200_batch_upload(b, stream);
+	}
+	const int ids[3] = {SRBA_I_edge_pose, SRBA_I_lm_pos, SRBA_I_obs_z};
+	for (int32_t i : b->dirty_values) {
+		const DevProblem &h = b->hdr[i];
+		for (int k = 0; k < 3; k++) {
+			if (!h.img_len[ids[k]]) continue;
+			const uint64_t off = b->img_off[i] + h.img_off[ids[k]];
+			CUDA_TRY(cudaMemcpyAsync(b->d_img + off, b->h_img + off, h.img_len[ids[k]], cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+		}
+	}
+	b->dirty_values.clear();
 	return SRBA_OK;
 }
 

@@ -90,9 +90,44 @@ def write_dataset(path, frames, sensor, graph_slam=False):
                 f.write("%d %d %s\n" % (k, int(fr["feat_id"][i]), " ".join(repr(float(x)) for x in vals)))
 
 
-def run_slam(engine, frames, profile_prefix=None, verbose=0):
-    """One define_new_keyframe() per frame (srba-run-generic-impl.h:451-465); returns per-keyframe rows and a summary."""
+def load_sensor_params(path, sensor):
+    """--sensor-params-cfg-file (apps/srba-slam/instance_se3_lm3d_monocular.cpp:24-28, instance_se3_lm3d_stereo.cpp:24-31): an MRPT
+    .ini file; monocular: section [CAMERA] with cx, cy, fx, fy (mrpt::utils::TCamera::loadFromConfigFile); stereo: sections
+    [CAMERA_LEFT], [CAMERA_RIGHT] and [CAMERA_LEFT2RIGHT_POSE] with pose_quaternion=[x y z qr qx qy qz] (TStereoCamera)."""
+    import configparser
+    cp = configparser.ConfigParser(inline_comment_prefixes=("//", ";", "#"), strict=False)
+    cp.read_string(open(path).read())
+    sec = {k.upper(): v for k, v in cp.items()}
+
+    def cam(name):
+        if name not in sec:
+            raise ValueError("section [%s] missing in %s" % (name, path))
+        c = sec[name]
+        return [float(c["fx"]), float(c["fy"]), float(c["cx"]), float(c["cy"])]
+
+    def vec(txt):
+        return [float(x) for x in txt.replace("[", " ").replace("]", " ").replace(",", " ").split()]
+    if sensor == "mono":
+        return dict(cam_left=cam("CAMERA"))
+    pose = vec(sec["CAMERA_LEFT2RIGHT_POSE"]["pose_quaternion"])
+    if len(pose) != 7 or pose[0] == 0:
+        raise ValueError("ASSERT_(baseline!=0) (instance_se3_lm3d_stereo.cpp:30)")
+    return dict(cam_left=cam("CAMERA_LEFT"), cam_right=cam("CAMERA_RIGHT"), right_cam_pose=pose)
+
+
+def run_slam(engine, frames, profile_prefix=None, verbose=0, profile_stats_length=10):
+    """One define_new_keyframe() per frame (srba-run-generic-impl.h:451-465); returns per-keyframe rows and a summary.
+    profile_prefix: the two files of --profile-stats (srba-run-generic-impl.h:201-202,623-647,778-829): <prefix>_means.csv and
+    <prefix>_calls.csv, one row per segment of `profile_stats_length` keyframes, tab-separated, columns = timed sections (mean seconds
+    per call within the segment / number of calls) plus total_num_kfs / total_num_lms / total_num_obs; the timers restart after
+    every segment.  Sections of this implementation: define_new_keyframe (wall), opt = the optimize_edges span (flatten + GPU call +
+    scatter, impl/optimize_edges.h:56,786), opt.gpu_call = inside srba_b200_optimize.  A per-keyframe table goes to
+    <prefix>_keyframes.csv."""
     rows, t_all = [], time.perf_counter()
+    seg_ts, seg_means, seg_calls = [], {}, {}
+    acc = dict(define_new_keyframe=[0.0, 0], opt=[0.0, 0], **{"opt.gpu_call": [0.0, 0]})
+    timers = getattr(engine, "timers", None) or (lambda: dict(gpu_seconds=0.0, flatten_seconds=0.0))   # (the oracle engine of the CPU tests has no GPU timers)
+    tm_prev = timers()
     for k, fr in enumerate(frames):
         t0 = time.perf_counter()
         r = engine.define_new_keyframe(fr["feat_id"], fr["obs"], is_fixed=fr["is_fixed"], is_unknown_with_init_val=fr["is_unknown_with_init_val"],
@@ -103,6 +138,22 @@ def run_slam(engine, frames, profile_prefix=None, verbose=0):
                      o.get("num_lm_trials", 0), o["obs_rmse"]))
         if verbose:
             print("KF %d: %d new edges, %d obs, rmse %.3g, %.2f ms" % (k, rows[-1][2], rows[-1][3], rows[-1][7], 1e3 * dt))
+        if profile_prefix:
+            tm = timers()
+            n_opt = (1 if o["num_observations"] else 0) + (1 if r["optimize_results_stg1"]["num_observations"] else 0)
+            acc["define_new_keyframe"][0] += dt; acc["define_new_keyframe"][1] += 1
+            acc["opt"][0] += (tm["gpu_seconds"] - tm_prev["gpu_seconds"]) + (tm["flatten_seconds"] - tm_prev["flatten_seconds"]); acc["opt"][1] += n_opt
+            acc["opt.gpu_call"][0] += tm["gpu_seconds"] - tm_prev["gpu_seconds"]; acc["opt.gpu_call"][1] += n_opt
+            tm_prev = tm
+            if k % max(1, profile_stats_length) == 0:   # (curFrameIdx % SAVE_TIMING_SEGMENT_LENGTH) == 0  (:625)
+                seg_ts.append(k)
+                for name, (sec, n) in acc.items():
+                    seg_means.setdefault(name, []).append(sec / n if n else 0.0)
+                    seg_calls.setdefault(name, []).append(n)
+                    acc[name] = [0.0, 0]
+                seg_means.setdefault("total_num_kfs", []).append(engine.num_keyframes)
+                seg_means.setdefault("total_num_lms", []).append(len(engine.unknown_lms()[0]))   # landmarks with unknown relative position
+                seg_means.setdefault("total_num_obs", []).append(engine.num_observations)
     total = time.perf_counter() - t_all
     a = np.array(rows, float)
     summary = dict(keyframes=len(rows), seconds=total, mean_kf_ms=1e3 * a[:, 1].mean(), lm_trials=int(a[:, 6].sum()), final_rmse=float(a[-1, 7]),
@@ -110,6 +161,12 @@ def run_slam(engine, frames, profile_prefix=None, verbose=0):
     if profile_prefix:
         np.savetxt(profile_prefix + "_keyframes.csv", a, delimiter=",", header="kf,define_new_keyframe_s,new_edges,obs,k2k_opt,lm_opt,lm_trials,obs_rmse",
                    comments="")
+        for suffix, table in (("_means.csv", seg_means), ("_calls.csv", seg_calls)):
+            names = sorted(table)
+            with open(profile_prefix + suffix, "w") as f:
+                f.write("timestep" + "".join('\t "%s"' % n for n in names) + "\n")
+                for i, ts in enumerate(seg_ts):
+                    f.write(str(ts) + "".join("\t%g" % table[n][i] for n in names) + "\n")
     return rows, summary
 
 
@@ -132,6 +189,8 @@ def main(argv=None):
     ap.add_argument("--add-noise", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--profile-stats", default=None)
+    ap.add_argument("--profile-stats-length", type=int, default=10, help="Length in KFs of each saved profiled segment")
+    ap.add_argument("--sensor-params-cfg-file", default=None, help="Config file from where to load the sensor parameters (mandatory for camera observations)")
     ap.add_argument("--verbose", type=int, default=0)
     a = ap.parse_args(argv)
     import srba_b200 as sb
@@ -144,6 +203,13 @@ def main(argv=None):
     else:
         sensor = {"cartesian_3d": "cartesian3d", "monocularcamera": "mono", "stereocamera": "stereo"}[(a.obs or "Cartesian_3D").lower()]
         kw = dict(pose_kind=1, obs_kind={"cartesian3d": 1, "mono": 2, "stereo": 3}[sensor], noise_kind=0)
+        if sensor in ("mono", "stereo"):
+            # the app's camera instances: sensor_pose_on_robot_se3 with the camera pointing forwards (camera +Z = robot +X),
+            # apps/srba-slam/srba-run-generic-impl.h:72-80, instance_se3_lm3d_monocular.cpp:38, instance_se3_lm3d_stereo.cpp:41; calibration from
+            # the mandatory --sensor-params-cfg-file (instance_se3_lm3d_monocular.cpp:24-28, instance_se3_lm3d_stereo.cpp:24-31)
+            if not a.sensor_params_cfg_file:
+                ap.error("--sensor-params-cfg-file is mandatory for this type of observations.")
+            kw.update(sensor_pose_kind=1, sensor_pose=[0, 0, 0, np.deg2rad(-90.0), 0.0, np.deg2rad(-90.0)], **load_sensor_params(a.sensor_params_cfg_file, sensor))
     frames, npar = load_dataset(a.dataset, sensor, graph_slam=a.graph_slam, add_noise=a.add_noise, noise=a.noise, noise_ang_deg=a.noise_ang, seed=a.seed)
     if sensor == "relposes2d":
         kw["noise_lambda"] = D.se2_noise_lambda(npar["sigma_xy"], npar["sigma_yaw"])
@@ -153,7 +219,7 @@ def main(argv=None):
               min_obs_to_loop_closure=a.min_obs_to_loop_closure if a.min_obs_to_loop_closure is not None else (1 if a.graph_slam else 4),
               max_error_per_obs_to_stop=1e-8)   # srba-run-generic-impl.h:127,178-182
     eng = sb.RbaEngine(sb.default_engine_params(**kw))
-    _, summary = run_slam(eng, frames, a.profile_stats, a.verbose)
+    _, summary = run_slam(eng, frames, a.profile_stats, a.verbose, a.profile_stats_length)
     print("%(keyframes)d keyframes in %(seconds).2f s (%(mean_kf_ms).3f ms per define_new_keyframe), %(lm_trials)d LM trials, final obs RMSE %(final_rmse).4g" % summary)
     return summary
 

@@ -1,0 +1,114 @@
+"""The drop-in facade shim/srba.h (the reference's public template API over the C ABI of this repo).
+CPU: the reference's tutorials (ported in tests/shim/*.cpp with their SRBA API calls unchanged) and an instantiation of the
+remaining model / option combinations compile with g++ -std=c++11 -Wall -Werror and link against libsrba_b200.so.
+GPU: the two tutorials RUN through the facade (define_new_keyframe / optimize_local_area / get_k2k_edges on the CUDA path) and
+reproduce the oracle's results on the same embedded datasets (tests/golden/reference_fixtures.json, extracted from the
+reference's examples/cpp/tutorial-srba-*.cpp) within 1e-6; ground truth of the tutorial as in tests/test_oracle_tutorials.py."""
+import math
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from fixtures import FX, T_from_flat12, T_from_xyzq, se2_noise_lambda
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "shim")
+PROGRAMS = ["tutorial_cartesian3d_se3", "tutorial_relative_graph_slam_se2", "instantiate_all"]
+
+
+def build_programs(out_dir):
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    from srba_b200 import build as B
+    so = B.build()
+    exes = {}
+    for name in PROGRAMS:
+        exe = os.path.join(out_dir, name)
+        subprocess.check_call([gxx, "-std=c++11", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "shim"), "-o", exe, os.path.join(SRC, name + ".cpp"),
+                               "-L", os.path.dirname(so), "-lsrba_b200", "-Wl,-rpath," + os.path.dirname(so)])
+        exes[name] = exe
+    return exes
+
+
+def test_facade_compiles_and_links(tmp_path):
+    exes = build_programs(str(tmp_path))
+    out = subprocess.check_output([exes["instantiate_all"]]).decode()   # constructs the engines' parameter structs only: no device needed
+    assert out.split() == ["ok", "2", "4", "6"]
+
+
+def write_c3d(path):
+    fx = FX["tutorial_cartesian3d"]
+    with open(path, "w") as f:
+        for key in ("observations_0", "observations_10"):
+            rows = fx[key]["rows"]
+            f.write("%d\n" % len(rows))
+            for r in rows:
+                f.write("%d %.17g %.17g %.17g\n" % (int(r[0]), r[1], r[2], r[3]))
+
+
+@pytest.mark.gpu
+def test_tutorial_cartesian3d_through_the_facade(tmp_path):
+    from oracle import pyoracle as po
+    exes = build_programs(str(tmp_path))
+    data = os.path.join(str(tmp_path), "c3d.txt")
+    write_c3d(data)
+    out = subprocess.check_output([exes["tutorial_cartesian3d_se3"], data]).decode()
+    res = [l for l in out.splitlines() if l.startswith("RESULT")][0].split()
+    la = [l for l in out.splitlines() if l.startswith("LOCALAREA")][0].split()
+    vals = dict(zip(res[1:13:2], res[2:14:2]))
+    pose = np.array([float(x) for x in res[res.index("pose") + 1:]])
+    T = np.eye(4); T[:3, :3] = pose[:9].reshape(3, 3); T[:3, 3] = pose[9:]
+    # the oracle on the same data, same parameters (tests/test_oracle_tutorials.py::test_tutorial_cartesian3d)
+    fx = FX["tutorial_cartesian3d"]
+    p = po.default_params(pose_kind=po.POSE_SE3, obs_kind=po.OBS_CARTESIAN3D, use_robust_kernel=1, noise_std=0.1, max_tree_depth=3, max_optimize_depth=3)
+    e = po.OracleEngine(p)
+    d0, d1 = np.array(fx["observations_0"]["rows"]), np.array(fx["observations_10"]["rows"])
+    e.define_new_keyframe(d0[:, 0].astype(np.uint64), d0[:, 1:])
+    r1 = e.define_new_keyframe(d1[:, 0].astype(np.uint64), d1[:, 1:])
+    P = np.linalg.inv(T_from_flat12(e.get_edge(0)[2]))
+    assert int(vals["kf"]) == 1 and int(vals["edges"]) == 1 and int(vals["obs"]) == r1["optimize_results"]["num_observations"]
+    assert abs(float(vals["err_init"]) - r1["optimize_results"]["total_sqr_error_init"]) <= 1e-9 * r1["optimize_results"]["total_sqr_error_init"]
+    assert np.abs(T - P).max() <= 1e-6 * np.abs(P).max()
+    # tutorial ground truth (KF#1 wrt KF#0)
+    GT = FX["tutorial_gt"]
+    P_GT = np.linalg.inv(T_from_xyzq(GT["robot_pose0_xyzq"])) @ T_from_xyzq(GT["robot_pose10_xyzq"])
+    assert np.abs(T[:3, 3] - P_GT[:3, 3]).max() < 2e-3 and np.abs(T[:3, :3] - P_GT[:3, :3]).max() < 2e-3
+    # optimize_local_area (+ observation_indices_to_optimize with every observation listed) ran through the facade
+    assert int(la[2]) > 0 and int(la[4]) == 1 and int(la[6]) > 0 and int(la[la.index("listed") + 2]) == e.num_observations
+    print("facade, cartesian3d tutorial: relative pose vs oracle %.2e, rmse %.3g" % (np.abs(T - P).max(), float(vals["rmse"])))
+
+
+@pytest.mark.gpu
+def test_tutorial_relative_graph_slam_se2_through_the_facade(tmp_path):
+    from oracle import pyoracle as po
+    exes = build_programs(str(tmp_path))
+    ds = FX["tutorial_relgraphslam_se2"]["dataset"]["rows"]
+    data = os.path.join(str(tmp_path), "se2.txt")
+    with open(data, "w") as f:
+        f.write("%d\n" % len(ds))
+        for r in ds:
+            f.write("%d %d %s\n" % (int(r[0]), int(r[1]), " ".join("%.17g" % v for v in r[2:8])))
+    out = subprocess.check_output([exes["tutorial_relative_graph_slam_se2"], data]).decode()
+    res = [l for l in out.splitlines() if l.startswith("RESULT")][0].split()
+    edges = np.array([[float(x) for x in l.split()[1:]] for l in out.splitlines() if l.startswith("EDGE")])
+    p = po.default_params(pose_kind=po.POSE_SE2, obs_kind=po.OBS_RELPOSES2D, noise_kind=po.NOISE_CONST_MATRIX, noise_lambda=se2_noise_lambda(0.001, math.radians(0.05)),
+                          max_tree_depth=3, max_optimize_depth=3, submap_size=5, min_obs_to_loop_closure=1)
+    e = po.OracleEngine(p)
+    idx, nkf = 0, int(max(r[0] for r in ds)) + 1
+    for kf in range(nkf):
+        ids, obs, fixed = [kf], [[0, 0, 0]], [1]
+        while idx < len(ds) and int(ds[idx][0]) == kf:
+            d = ds[idx]
+            ids.append(int(d[1])); obs.append([d[2], d[3], d[5]]); fixed.append(0)
+            idx += 1
+        e.define_new_keyframe(ids, obs, is_fixed=fixed)
+    ft, po_ = e.edges()
+    assert int(res[2]) == nkf and int(res[4]) == len(ft) == len(edges)
+    assert edges[:, 1:3].astype(int).tolist() == np.asarray(ft).astype(int).tolist()      # same edges (from, to): bit-exact graph
+    assert np.abs(edges[:, 3:6] - po_).max() <= 1e-6 * np.abs(po_).max()
+    assert float(res[6]) < 1e-4
+    print("facade, relative graph-SLAM tutorial: %d keyframes, %d edges, edge poses vs oracle %.2e" % (nkf, len(ft), np.abs(edges[:, 3:6] - po_).max()))

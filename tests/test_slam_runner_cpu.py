@@ -46,3 +46,26 @@ def test_runner_drives_an_engine(tmp_path):
     assert summary["keyframes"] == 30 and summary["final_rmse"] < 1e-6      # noise-free data: the map is recovered exactly
     tab = np.loadtxt(str(tmp_path / "prof_keyframes.csv"), delimiter=",", skiprows=1)
     assert tab.shape == (30, 8)
+    # --profile-stats files (srba-run-generic-impl.h:623-647,778-829): one row per segment of 10 keyframes, tab-separated
+    means = open(str(tmp_path / "prof_means.csv")).read().splitlines()
+    calls = open(str(tmp_path / "prof_calls.csv")).read().splitlines()
+    assert means[0].startswith("timestep\t") and '"define_new_keyframe"' in means[0] and '"opt"' in means[0] and '"total_num_kfs"' in means[0]
+    assert [l.split("\t")[0] for l in means[1:]] == ["0", "10", "20"] and len(calls) == 4
+    cols = [c.strip().strip('"') for c in means[0].split("\t")]
+    assert [float(l.split("\t")[cols.index("total_num_kfs")]) for l in means[1:]] == [1, 11, 21]
+
+
+def test_sensor_params_cfg_file(tmp_path):
+    """--sensor-params-cfg-file as the app's camera instances read it (instance_se3_lm3d_monocular.cpp:24-28, instance_se3_lm3d_stereo.cpp:24-31)."""
+    mono = tmp_path / "mono.ini"
+    mono.write_text("[CAMERA]\nresolution = [800 600]\ncx = 400\ncy = 300\nfx = 200\nfy = 200\ndist = [0 0 0 0 0]\n")
+    assert R.load_sensor_params(str(mono), "mono") == dict(cam_left=[200.0, 200.0, 400.0, 300.0])
+    st = tmp_path / "stereo.ini"
+    st.write_text("[CAMERA_LEFT]\nresolution=[1024 768]\ncx=512\ncy=384\nfx=200\nfy=150\n[CAMERA_RIGHT]\ncx=512\ncy=384\nfx=200\nfy=150\n"
+                  "[CAMERA_LEFT2RIGHT_POSE]\npose_quaternion=[0.2 0 0 1 0 0 0]\n")
+    p = R.load_sensor_params(str(st), "stereo")
+    assert p["cam_left"] == [200.0, 150.0, 512.0, 384.0] and p["cam_right"] == p["cam_left"] and p["right_cam_pose"] == [0.2, 0, 0, 1, 0, 0, 0]
+    bad = tmp_path / "bad.ini"
+    bad.write_text("[CAMERA_LEFT]\ncx=1\ncy=1\nfx=1\nfy=1\n[CAMERA_RIGHT]\ncx=1\ncy=1\nfx=1\nfy=1\n[CAMERA_LEFT2RIGHT_POSE]\npose_quaternion=[0 0 0 1 0 0 0]\n")
+    with pytest.raises(ValueError):
+        R.load_sensor_params(str(bad), "stereo")      # ASSERT_(baseline != 0)
