@@ -20,6 +20,15 @@
 
 #include "dev_types.h"
 
+#ifndef SRBA_SCHUR_DMMA
+// SE(3) Schur block products on the FP64 tensor pipe (mma.sync.m8n8k4.f64, one warp per block) instead of one thread per block row with
+// scalar DFMA.  Measured (profiles/r02_dmma_schur.txt): in isolation at full occupancy the DMMA kernel is 1.9x faster (tensor pipe 28 %
+// active); INSIDE the product kernels it is slower -- config #5, 1 000 areas: 373 vs 345 ms (one CTA per area), 603 vs 540 ms (wave) --
+// because the stage is bound by dependent gathers at low occupancy, where 1 024 independent row-threads keep more loads in flight than
+// 32 warps.  Parity tests pass with either setting.  Default: off.
+#define SRBA_SCHUR_DMMA 0
+#endif
+
 // One TEAM solves one problem.  Normally the team is one CTA; lm_kernel_cluster.cu compiles this file again with
 // SRBA_CLUSTER = 8 so that a thread-block CLUSTER of 8 CTAs (8 SMs) shares a large problem: stage loops stride over the
 // whole cluster, barriers are cluster barriers, reductions are exchanged through distributed shared memory, and every
@@ -947,6 +956,51 @@ LM_STAGE void stage_schur(const View &vs, double lambda, int phase = 0) {  // `p
 	if (phase == 1 || phase == 2) return;
 	// (3) reduced blocks; (4) reduced gradient.  SE(3): one thread per block ROW (W row loaded once for the 6 outputs, index and
 	// invertibility loads shared) -- same sums, same order, 2.4x fewer load instructions in the stage that dominates landmark areas
+#if SRBA_SCHUR_DMMA
+	// SE(3): the reduced blocks on the FP64 TENSOR pipe.  S_ij = H_ij - sum_k W_ik (6x3) HApf_jk^t (3x6) is one small GEMM per block with a
+	// gathered inner dimension 3K (K = landmarks seen from both edges, ~33 on depth-5 areas): one warp per block, mma.sync.m8n8k4.f64 with the
+	// 6x6 output padded to 8x8 and four inner indices per instruction; A = -W (zero for non-invertible landmarks, schur.h:228), C starts
+	// at the H_Ap block.  tools/microbench/dmma_schur.cu + profiles/r02_dmma_schur.txt: 1.9x the one-thread-per-row DFMA version on
+	// L2-resident operands (tensor pipe 28 % active vs FP64 pipe 11 %).  The association of the sum inside one MMA (4 terms) is the
+	// hardware's: results differ from the scalar order at rounding level.
+	if constexpr (P == 6) {
+		const int lane = LM_TID & 31, warp = LM_TID >> 5, nwarp = LM_THREADS >> 5;
+		const int row = lane >> 2, kk = lane & 3, col = 2 * kk;   // A: output row / inner offset; B: output column = lane >> 2; C: (row, col), (row, col + 1)
+		const bool live = row < 6;
+		if (!h->s_alias_hap)
+			for (int blk = warp; blk < h->n_S; blk += nwarp) {
+				const int hb = v.S_HAp[blk];
+				double c0 = 0.0, c1 = 0.0;
+				if (live && col < 6 && hb >= 0) { c0 = v.HAp[(size_t)hb * 36 + row * 6 + col]; c1 = v.HAp[(size_t)hb * 36 + row * 6 + col + 1]; }
+				const int t0 = v.S_term_ptr[blk], nq = 3 * (v.S_term_ptr[blk + 1] - t0);
+				for (int q0 = 0; q0 < nq; q0 += 4) {
+					const int q = q0 + kk;
+					double a = 0.0, b = 0.0;
+					if (live && q < nq) {
+						const int t = t0 + q / 3, comp = q - 3 * (q / 3);
+						const int rb = v.S_term_rowblk[t], cb = v.S_term_colblk[t];
+						a = v.lm_inv[v.HApf_col[rb]] ? -v.W[(size_t)rb * 18 + row * 3 + comp] : 0.0;
+						b = v.HApf[(size_t)cb * 18 + row * 3 + comp];   // (for B, `row` is the output column)
+					}
+					asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+				}
+				if (live && col < 6) { v.Sblk[(size_t)blk * 36 + row * 6 + col] = c0; v.Sblk[(size_t)blk * 36 + row * 6 + col + 1] = c1; }
+			}
+		for (int i = LM_TID; i < n; i += LM_THREADS) {  // (4) reduced gradient: scalar of the pose part
+			const int ucol = i / 6, a = i % 6;
+			double g = v.grad[i];
+			for (int blk = v.rowApf_ptr[ucol]; blk < v.rowApf_ptr[ucol + 1]; blk++) {
+				const int k = v.HApf_col[blk];
+				if (!v.lm_inv[k]) continue;
+				const double *Wr = v.W + (size_t)blk * 18;
+				const double *gf = v.grad + n + (size_t)k * 3;
+				g -= Wr[a * 3 + 0] * gf[0] + Wr[a * 3 + 1] * gf[1] + Wr[a * 3 + 2] * gf[2];
+			}
+			v.grad[i] = g;
+		}
+		return;
+	}
+#else
 	if constexpr (P == 6) {
 		const int nSR = h->s_alias_hap ? 0 : h->n_S * 6;
 		for (int it = LM_TID; it < nSR + n; it += LM_THREADS) {
@@ -987,6 +1041,7 @@ LM_STAGE void stage_schur(const View &vs, double lambda, int phase = 0) {  // `p
 		}
 		return;
 	}
+#endif
 	const int nS = h->s_alias_hap ? 0 : h->n_S * P * P;
 	for (int it = LM_TID; it < nS + n; it += LM_THREADS) {
 		if (it < nS) {

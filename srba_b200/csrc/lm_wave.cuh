@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(128) wave_schur_kernel(const WaveArgs a, int p
 	const View &v = a.views[area];
 	const DevProblem *h = v.h;
 	if (h->n_unk_lms == 0 && h->s_alias_hap) return;
-	if (!wave_team(phase == 1 ? (int64_t)h->n_unk_lms : phase == 2 ? (int64_t)h->n_HApf * P * 3 : (int64_t)h->n_S * (P == 6 ? 6 : 9) + h->n_dense, WAVE_CAP)) return;
+	if (!wave_team(phase == 1 ? (int64_t)h->n_unk_lms : phase == 2 ? (int64_t)h->n_HApf * P * 3 : (int64_t)h->n_S * (P == 6 ? (SRBA_SCHUR_DMMA ? 32 : 6) : 9) + h->n_dense, WAVE_CAP)) return;
 	if (phase == 1 && (OBSK != SRBA_OBS_RELPOSES2D) && no_schur_solver(h))  // (grad is next read by phase 3)
 		for (int i = LM_TID; i < h->n_scalars; i += LM_THREADS) v.grad[i] = v.grad0[i];
 	stage_schur<P>(v, s.lambda, phase);
