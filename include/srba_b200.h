@@ -196,6 +196,11 @@ int srba_b200_batch_stage_cycles(srba_batch_t *b, int32_t i, uint64_t out[24]);
  * out[0]=B_chain out[1]=B_assem out[2]=B_schur out[3]=B_chol out[4]=F_chol(flop) */
 void srba_b200_batch_algorithmic_bytes(const srba_batch_t *b, double out[5]);
 
+/* Measurement hook (bench.py's roofline line): when enabled, batch_run brackets every launch of the dominant kernel of the wave pipeline (the
+ * cluster-team forward solver, wave_solve_fwd_kernel) with CUDA events; get: out[0] = summed milliseconds, out[1] = launches since enabling. */
+void srba_b200_kernel_timing(int32_t enable);
+void srba_b200_kernel_timing_get(double out[2]);
+
 /* Host-only: how the packer would lay problem `in` out.  out[0..7] = image bytes, global workspace bytes, result bytes,
  * shared-memory bytes planned (solver scratch + on-chip arena), solver (0 block-sparse L D L^t, 1 dense blocked; +2 when
  * the problem is solved by an 8-CTA cluster, +4 by the grid-wide wave pipeline),
@@ -209,6 +214,10 @@ int srba_b200_batch_problem_plan(const srba_batch_t *b, int32_t i, int64_t out[8
  * out[0..3] = 3x3 tiles of the filled pattern incl. the right-hand side, tile updates per factorisation, barrier-separated phases,
  * 1 when the tiles stay in shared memory.  All 0 when the problem falls back to the dense blocked solver. */
 int srba_b200_problem_ldl_counts(const srba_problem_t *in, int64_t out[4]);
+/* Host-only: the level schedule of a problem that "auto" runs in the wave pipeline (all 0 otherwise): out[0..7] = tiles, destination entries,
+ * tile updates (contributions), elimination levels, first level of the dense tail, 1 when its forward / backward levels run as a cluster
+ * team, tiles of the rows below the tail, destination entries of the levels below the tail. */
+int srba_b200_problem_wave_counts(const srba_problem_t *in, int64_t out[8]);
 
 /* Host-only (tests): the symbolic factorisation the packer ships with a problem for the on-chip block-sparse L D L^t
  * solver -- 3x3 tiles numbered row-major (diagonal first, right-hand side as tile column NTR).  counts[6] = {NTR, tiles,

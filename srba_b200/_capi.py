@@ -86,7 +86,7 @@ class NewEdge(C.Structure):
 EXPORTED_SYMBOLS = [
     "srba_b200_optimize", "srba_b200_optimize_batch", "srba_b200_batch_create", "srba_b200_batch_upload", "srba_b200_batch_run",
     "srba_b200_batch_download", "srba_b200_batch_unpack", "srba_b200_batch_destroy", "srba_b200_batch_h2d_bytes", "srba_b200_batch_d2h_bytes",
-    "srba_b200_batch_update_values", "srba_b200_batch_upload_values", "srba_b200_batch_kernel_launches", "srba_b200_batch_stage_cycles", "srba_b200_problem_plan", "srba_b200_batch_problem_plan", "srba_b200_problem_ldl_counts", "srba_b200_debug_ldl_schedule", "srba_b200_debug_level_schedule", "srba_b200_batch_algorithmic_bytes", "srba_b200_eval_overall_squared_error", "srba_b200_last_error", "srba_b200_device_count", "srba_b200_version",
+    "srba_b200_kernel_timing", "srba_b200_kernel_timing_get", "srba_b200_batch_update_values", "srba_b200_batch_upload_values", "srba_b200_batch_kernel_launches", "srba_b200_batch_stage_cycles", "srba_b200_problem_plan", "srba_b200_batch_problem_plan", "srba_b200_problem_ldl_counts", "srba_b200_problem_wave_counts", "srba_b200_debug_ldl_schedule", "srba_b200_debug_level_schedule", "srba_b200_batch_algorithmic_bytes", "srba_b200_eval_overall_squared_error", "srba_b200_last_error", "srba_b200_device_count", "srba_b200_version",
     "srba_b200_release_workspace", "srba_b200_set_option", "srba_b200_get_option",
     "srba_engine_default_params", "srba_engine_create", "srba_engine_destroy", "srba_engine_set_params", "srba_engine_define_new_keyframe",
     "srba_engine_optimize_local_area", "srba_engine_optimize_local_area_obs", "srba_engine_optimize_edges", "srba_engine_select_local_area", "srba_engine_flatten",
@@ -121,6 +121,8 @@ def lib():
         f = getattr(L, "srba_b200_batch_" + n)
         f.restype = C.c_int
         f.argtypes = [vp, vp]
+    L.srba_b200_kernel_timing.argtypes = [i32]
+    L.srba_b200_kernel_timing_get.argtypes = [pdbl]
     L.srba_b200_batch_update_values.restype = C.c_int
     L.srba_b200_batch_update_values.argtypes = [vp, i32, pdbl, pdbl, pdbl]
     L.srba_b200_batch_upload_values.restype = C.c_int

@@ -39,7 +39,8 @@ struct SrbaWaveDims {
 extern "C" size_t srba_wave_scratch_bytes(int n_areas);
 extern "C" int srba_launch_lm_wave(int model, const char *img, const uint64_t *img_off, char *ws, const uint64_t *ws_off, char *res, const uint64_t *res_off,
                                    const int32_t *order, const SrbaWaveDims *dims, char *scratch, int *h_active_pinned, void *stream, int64_t *launches);
-#define SRBA_WAVE_SOLVE_SMEM_MAX (200 * 1024)
+extern "C" void srba_wave_timing_enable(int on);
+extern "C" void srba_wave_timing_get(double *ms, long *launches);
 
 namespace {
 thread_local std::string g_err;
@@ -651,7 +652,8 @@ void symbolic_levels(const srba_problem_t &p, int P, TileSymbolic &sy, bool debu
 		return (int32_t)(std::lower_bound(sy.tile_ij.begin() + sy.rs[i], sy.tile_ij.begin() + sy.rs[i + 1], key) - sy.tile_ij.begin());
 	};
 	// ---- per level: destinations with their contributions (ascending source row)
-	std::vector<int32_t> dst, cptr(1, 0), cab, slot(ntiles, -1);
+	std::vector<int32_t> dst, cptr(1, 0), cab, slot(ntiles, -1), trip, cnt;
+	std::vector<size_t> pos;
 	sy.phase.assign(2 * (size_t)(nlev + 1), 0);
 	int r = 0;
 	for (int L = 0; L < nlev; L++) {
@@ -659,24 +661,32 @@ void symbolic_levels(const srba_problem_t &p, int P, TileSymbolic &sy, bool debu
 		sy.phase[2 * (size_t)L + 1] = (int32_t)dst.size();
 		const int r0 = r, d0 = (int)dst.size();
 		while (r < ntr && level[order[r]] == L) r++;
-		std::vector<std::vector<int32_t> > lists;
+		// contributions of the level grouped by destination (first-seen order), ascending source row inside a destination: two passes
+		// over a flat triple list (count, then place) -- no per-destination containers
+		trip.clear();
+		cnt.clear();
 		for (int k = r0; k < r; k++)
 			for (int a = sy.rs[k] + 1; a < sy.rs[k + 1] - 1; a++) {  // tile (k,i): off-diagonal, not the right-hand side
 				const int i = sy.tile_ij[a] & 0xffff;
 				for (int b = a; b < sy.rs[k + 1]; b++) {           // tile (k,j), j >= i, right-hand side included
 					const int j = sy.tile_ij[b] & 0xffff;
 					const int32_t d = find_tile(i, j);
-					if (slot[d] < 0) { slot[d] = (int32_t)lists.size(); lists.emplace_back(); dst.push_back(d); }
-					lists[slot[d]].push_back(a);
-					lists[slot[d]].push_back(b);
+					if (slot[d] < 0) { slot[d] = (int32_t)cnt.size(); cnt.push_back(0); dst.push_back(d); }
+					cnt[slot[d]]++;
+					trip.push_back(slot[d]); trip.push_back(a); trip.push_back(b);
 				}
 			}
-		for (int e = d0; e < (int)dst.size(); e++) {
-			const std::vector<int32_t> &l = lists[e - d0];
-			cab.insert(cab.end(), l.begin(), l.end());
-			cptr.push_back((int32_t)(cab.size() / 2));
-			slot[dst[e]] = -1;
+		const size_t base = cab.size() / 2;
+		pos.resize(cnt.size());
+		size_t run = base;
+		for (size_t e = 0; e < cnt.size(); e++) { pos[e] = run; run += cnt[e]; cptr.push_back((int32_t)run); }
+		cab.resize(2 * run);
+		for (size_t q = 0; q < trip.size(); q += 3) {
+			const size_t at = pos[trip[q]]++;
+			cab[2 * at] = trip[q + 1];
+			cab[2 * at + 1] = trip[q + 2];
 		}
+		for (int e = d0; e < (int)dst.size(); e++) slot[dst[e]] = -1;
 	}
 	sy.phase[2 * (size_t)nlev] = ntr;
 	sy.phase[2 * (size_t)nlev + 1] = (int32_t)dst.size();
@@ -728,6 +738,16 @@ bool heavy_problem(const srba_problem_t &p) {
 	const double w = (double)p.n_blkA * o * P * 10 + (double)p.n_blkF * o * 3 * 10 + ((double)p.n_HAp_terms * P * P + (double)p.n_HApf_terms * P * 3) * o +
 	                 (double)p.n_S_terms * P * P * 3;
 	return w > 1e6;
+}
+// Would "auto" send this problem to the grid-wide wave pipeline?  (pack_problem's rule on the array sizes alone: an SE(2) area whose core
+// arrays overflow one CTA's shared-memory arena; areas that overflow only through their tiles are found at pack time.)
+bool wave_candidate(const srba_problem_t &p) {
+	const int fw = option(OPT_WAVE);
+	if (fw == 0 || option(OPT_CLUSTER) == 1 || option(OPT_BLOCKED) != 0) return false;
+	if (fw == 1) return true;
+	if (p.model.pose_kind != SRBA_POSE_SE2) return false;
+	const uint64_t demand = (uint64_t)2 * p.n_pairs * 3 * 8 + (uint64_t)p.n_blkA * 3 * 3 * 8 + (uint64_t)p.n_HAp * 9 * 8;
+	return demand > (uint64_t)srba_kernel_cfg(0).smem_bytes;
 }
 // A cluster takes 8 SMs: it shortens the LATENCY of a heavy area, while a batch with many heavy areas already fills the
 // GPU with one CTA per area.
@@ -1357,7 +1377,7 @@ int srba_b200_batch_upload_values(srba_batch_t *b, void *stream) {
 	if (!b->uploaded) return srba_b200_batch_upload(b, stream);   // nothing resident yet: the whole image
 	std::sort(b->dirty_values.begin(), b->dirty_values.end());
 	b->dirty_values.erase(std::unique(b->dirty_values.begin(), b->dirty_values.end()), b->dirty_values.end());
-	if (b->dirty_values.size() > 64) {  // many small copies cost more than one large one
+	if (b->dirty_values.size() > 2048) {  // (thousands of small copies cost more than one large one)
 		b->dirty_values.clear();
 		return srba_b200_batch_upload(b, stream);
 	}
@@ -1520,6 +1540,13 @@ int srba_b200_debug_level_schedule(const srba_problem_t *in, int32_t counts[6], 
 	return SRBA_OK;
 }
 
+void srba_b200_kernel_timing(int32_t enable) { srba_wave_timing_enable(enable); }
+void srba_b200_kernel_timing_get(double out[2]) {
+	long n = 0;
+	srba_wave_timing_get(&out[0], &n);
+	out[1] = (double)n;
+}
+
 int srba_b200_problem_plan(const srba_problem_t *in, int64_t out[8]) {
 	if (!in || !out) return fail(SRBA_ERR_BAD_ARGUMENT, "null argument");
 	const int rc = validate(*in);
@@ -1555,9 +1582,26 @@ int srba_b200_problem_ldl_counts(const srba_problem_t *in, int64_t out[4]) {
 	pack_problem(*in, h, nullptr, 0, 0, sy, true);
 	const bool reg = h.chol_mode == SRBA_CHOL_REG;
 	out[0] = reg ? (int64_t)sy.tile_ij.size() : 0;
-	out[1] = reg ? (int64_t)(sy.upd.size() / (sy.wide ? 3 : 2)) : 0;
+	out[1] = reg ? (sy.levels ? (int64_t)sy.n_contrib : (int64_t)(sy.upd.size() / (sy.wide ? 3 : 2))) : 0;
 	out[2] = reg ? sy.n_phases : 0;
 	out[3] = (reg && !h.ldl_tiles_in_ws) ? 1 : 0;
+	return SRBA_OK;
+}
+
+int srba_b200_problem_wave_counts(const srba_problem_t *in, int64_t out[8]) {
+	if (!in || !out) return fail(SRBA_ERR_BAD_ARGUMENT, "null argument");
+	const int rc = validate(*in);
+	if (rc != SRBA_OK) return rc;
+	DevProblem h;
+	TileSymbolic sy;
+	pack_problem(*in, h, nullptr, 0, 0, sy, true);
+	for (int k = 0; k < 8; k++) out[k] = 0;
+	if (!h.wave || !sy.levels) return SRBA_OK;
+	const int tail_row = sy.phase[2 * (size_t)sy.tail_level];
+	out[0] = (int64_t)sy.tile_ij.size(); out[1] = sy.n_dst; out[2] = sy.n_contrib; out[3] = sy.n_phases; out[4] = sy.tail_level;
+	out[5] = (sy.tail_level > 0 && sy.n_dst >= SRBA_WAVE_TEAM_DST_PER_LEVEL * sy.tail_level) ? 1 : 0;
+	out[6] = sy.rs[tail_row];                       // tiles of the rows below the tail
+	out[7] = sy.phase[2 * (size_t)sy.tail_level + 1];  // destination entries of the levels below the tail
 	return SRBA_OK;
 }
 
@@ -1578,9 +1622,14 @@ int srba_b200_optimize_batch(int32_t n, const srba_problem_t *const *in, srba_re
 	// and solved, chunk c+1 is being packed on the host cores, and results come back chunk by chunk.  All chunks fit the
 	// GPU together (2 CTAs/SM), so the kernels overlap; only the first pack and the last copy-back stay exposed.
 	const int k_chunks = std::max(1, std::min(option(OPT_CHUNKS), SRBA_MAX_CHUNKS));  // default 4 pipelined chunks
-	const int K = n >= 64 ? k_chunks : 1;
-	int n_heavy = 0;
-	for (int i = 0; i < n; i++) n_heavy += (in[i] && heavy_problem(*in[i])) ? 1 : 0;
+	int n_heavy = 0, n_wave = 0;
+	for (int i = 0; i < n; i++) {
+		n_heavy += (in[i] && heavy_problem(*in[i])) ? 1 : 0;
+		n_wave += (in[i] && wave_candidate(*in[i])) ? 1 : 0;
+	}
+	// Areas of the grid-wide wave pipeline advance in lock step, one host-driven launch sequence per LM trial for the whole group: cutting
+	// such a batch into chunks would repeat that sequence per chunk (and the host blocks inside each), so it stays one piece.
+	const int K = (n >= 64 && n_wave == 0) ? k_chunks : 1;
 	const int allow_cluster = clusters_pay(n_heavy) ? 1 : 0;
 	srba_batch_t *bt[SRBA_MAX_CHUNKS] = {};
 	int begin[SRBA_MAX_CHUNKS + 1];

@@ -16,6 +16,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <vector>
 #include <stdint.h>
 
 #include "dev_types.h"

@@ -781,6 +781,14 @@ struct SrbaWaveDims {
 	int has_lms, n_big, n_solo, max_tail_rows;  // n_big / n_solo: areas with levels below the tail (cluster team / one CTA); largest dense tail (tile rows)
 };
 
+// Optional CUDA-event timing of the dominant kernel (the cluster-team forward solver) for bench.py's roofline line: a pair of events around
+// every launch of it, read after the run.  Off by default (srba_b200_kernel_timing).
+static int g_wave_time_kernels = 0;
+static double g_wave_fwd_team_ms = 0.0;
+static long g_wave_fwd_team_launches = 0;
+extern "C" void srba_wave_timing_enable(int on) { g_wave_time_kernels = on; g_wave_fwd_team_ms = 0.0; g_wave_fwd_team_launches = 0; }
+extern "C" void srba_wave_timing_get(double *ms, long *launches) { *ms = g_wave_fwd_team_ms; *launches = g_wave_fwd_team_launches; }
+
 namespace {
 inline int wave_gx(int items, int threads, int cap = WAVE_CAP) { return std::max(1, std::min((items + threads - 1) / threads, cap)); }
 
@@ -811,6 +819,17 @@ int wave_run(const WaveArgs &a, const SrbaWaveDims &d, int *h_active_pinned, cud
 	if (cudaFuncSetAttribute(solve_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem) != cudaSuccess) return (int)cudaGetLastError();
 	cudaMemsetAsync(a.big + n, 0, sizeof(int), st);
 	cudaMemsetAsync(a.solo + n, 0, sizeof(int), st);
+	const bool both = d.n_big > 0 && d.n_solo > 0;
+	const bool timing = g_wave_time_kernels != 0;
+	std::vector<cudaEvent_t> tev;
+	cudaStream_t side = st;
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+	if (both) {
+		if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess) return (int)cudaGetLastError();
+		cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+		cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
+		scfg.stream = side;
+	}
 	cudaMemsetAsync(a.active, 0, sizeof(int), st);
 	// ---- set-up: E (numeric spanning tree), F/G (Jacobians), lists, J (Hessian), M (residuals), N (gradient), L (lambda0)
 	wave_views_kernel<<<(n + 127) / 128, 128, 0, st>>>(a);
@@ -844,11 +863,23 @@ int wave_run(const WaveArgs &a, const SrbaWaveDims &d, int *h_active_pinned, cud
 			wave_schur_kernel<P, OBSK><<<grid(gx_s3), 128, 0, st>>>(a, 3);
 			nl += 3;
 		}
+		// the cluster teams of the few wide areas run on a side stream next to the one-CTA areas (fork / join per phase)
+		if (both) { cudaEventRecord(ev_fork, st); cudaStreamWaitEvent(side, ev_fork, 0); }
 		if (d.n_solo) { wave_solve_fwd_kernel<P, OBSK, false><<<dim3(1, (unsigned)d.n_solo, 1), WAVE_SOLO_NT, 0, st>>>(a); nl++; }
-		if (d.n_big) { const cudaError_t e = cudaLaunchKernelEx(&scfg, solve_fwd, a); if (e != cudaSuccess) { rc = (int)e; break; } nl++; }
+		if (d.n_big) {
+			cudaEvent_t t0 = nullptr, t1 = nullptr;
+			if (timing) { cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventRecord(t0, scfg.stream); }
+			const cudaError_t e = cudaLaunchKernelEx(&scfg, solve_fwd, a);
+			if (e != cudaSuccess) { rc = (int)e; break; }
+			nl++;
+			if (timing) { cudaEventRecord(t1, scfg.stream); tev.push_back(t0); tev.push_back(t1); }
+		}
+		if (both) { cudaEventRecord(ev_join, side); cudaStreamWaitEvent(st, ev_join, 0); }
 		solve_tail<<<n, WAVE_TAIL_NT, tail_smem, st>>>(a);
+		if (both) { cudaEventRecord(ev_fork, st); cudaStreamWaitEvent(side, ev_fork, 0); }
 		if (d.n_solo) { wave_solve_bwd_kernel<P, OBSK, false><<<dim3(1, (unsigned)d.n_solo, 1), WAVE_SOLO_NT, 0, st>>>(a); nl++; }
 		if (d.n_big) { const cudaError_t e = cudaLaunchKernelEx(&scfg, solve_bwd, a); if (e != cudaSuccess) { rc = (int)e; break; } nl++; }
+		if (both) { cudaEventRecord(ev_join, side); cudaStreamWaitEvent(st, ev_join, 0); }
 		wave_solve_finish_kernel<P, OBSK><<<n, 256, 0, st>>>(a);
 		nl++;
 		if (d.has_lms) { wave_features_kernel<P><<<grid(gx_s1), 128, 0, st>>>(a); nl++; }
@@ -873,6 +904,21 @@ int wave_run(const WaveArgs &a, const SrbaWaveDims &d, int *h_active_pinned, cud
 	nl++;
 	cudaEventDestroy(ev[0]);
 	cudaEventDestroy(ev[1]);
+	if (timing) {
+		cudaStreamSynchronize(st);
+		if (both) cudaStreamSynchronize(side);
+		for (size_t i = 0; i + 1 < tev.size(); i += 2) {
+			float ms = 0;
+			if (cudaEventElapsedTime(&ms, tev[i], tev[i + 1]) == cudaSuccess) { g_wave_fwd_team_ms += ms; g_wave_fwd_team_launches++; }
+			cudaEventDestroy(tev[i]); cudaEventDestroy(tev[i + 1]);
+		}
+	}
+	if (both) {  // (every side-stream launch was joined back into `st`)
+		cudaStreamSynchronize(side);
+		cudaEventDestroy(ev_fork);
+		cudaEventDestroy(ev_join);
+		cudaStreamDestroy(side);
+	}
 	if (launches) *launches += nl;
 	if (rc) return rc;
 	return (int)cudaGetLastError();
