@@ -1310,7 +1310,7 @@ static srba_batch_t *batch_create_impl(int32_t n, const srba_problem_t *const *i
 				mx(d.max_hess_items, P == 6 ? (int64_t)6 * h.n_HAp + 6 * h.n_HApf + 3 * h.n_unk_lms : (int64_t)9 * h.n_HAp);
 				mx(d.max_obs, h.n_obs); mx(d.max_scalars, h.n_scalars);
 				mx(d.max_unk, std::max<int64_t>(std::max(h.n_unk_edges, h.n_unk_lms), (int64_t)2 * h.n_pairs * S));
-				mx(d.max_schur2, (int64_t)h.n_HApf * P * 3); mx(d.max_schur3, (int64_t)h.n_S * (P == 6 ? 32 : 9) + h.n_dense);  // (32: room for the one-warp-per-block DMMA build, SRBA_SCHUR_DMMA) mx(d.max_lms, h.n_unk_lms);
+				mx(d.max_schur2, (int64_t)h.n_HApf * P * 3); mx(d.max_schur3, (int64_t)h.n_S * (P == 6 ? 32 : 9) + h.n_dense); mx(d.max_lms, h.n_unk_lms);  // (x 32: room for the one-warp-per-block DMMA build, SRBA_SCHUR_DMMA)
 				mx(d.max_edges_S, std::max<int64_t>((int64_t)h.n_edges * S, 2 * (int64_t)h.n_pairs));
 				mx(d.max_out, (int64_t)2 * h.n_pairs * S);
 				if (h.n_unk_lms > 0) d.has_lms = 1;

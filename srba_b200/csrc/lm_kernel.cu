@@ -21,6 +21,9 @@
 
 #include "dev_types.h"
 
+#ifndef SRBA_TMA_STAGING
+#define SRBA_TMA_STAGING 1   // arena staging by cp.async.bulk + mbarrier (0: 16-byte load/store loop)
+#endif
 #ifndef SRBA_SCHUR_DMMA
 // SE(3) Schur block products on the FP64 tensor pipe (mma.sync.m8n8k4.f64, one warp per block) instead of one thread per block row with
 // scalar DFMA.  Measured (profiles/r02_dmma_schur.txt): in isolation at full occupancy the DMMA kernel is 1.9x faster (tensor pipe 28 %
@@ -1687,6 +1690,35 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 	__syncthreads();
 	const View &v = sh.view;
 	double *scratch = reinterpret_cast<double *>(dyn + h->sm_scratch);
+#if SRBA_TMA_STAGING
+	// Staging of the read-only index arrays the packer placed in the arena: ONE thread issues a bulk asynchronous copy (TMA, cp.async.bulk
+	// global -> shared, SASS UBLKCP) per array, all completing on one mbarrier whose transaction count is the total byte count; the other
+	// threads go straight to the barrier wait instead of executing a 16-byte load/store loop.
+	{
+		__shared__ __align__(8) unsigned long long stage_bar;
+		const unsigned bar = (unsigned)__cvta_generic_to_shared(&stage_bar);
+		if (threadIdx.x == 0) {
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+			unsigned total = 0;
+			for (int a = 0; a < SRBA_I_COUNT; a++)
+				if (h->img_sm[a] != SRBA_NOT_IN_SMEM) total += (unsigned)(((h->img_len[a] + 15) >> 4) << 4);
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
+			for (int a = 0; a < SRBA_I_COUNT; a++) {
+				if (h->img_sm[a] == SRBA_NOT_IN_SMEM) continue;
+				const unsigned bytes = (unsigned)(((h->img_len[a] + 15) >> 4) << 4);
+				if (!bytes) continue;
+				const unsigned dst = (unsigned)__cvta_generic_to_shared(dyn + h->img_sm[a]);
+				asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(img + h->img_off[a]), "r"(bytes), "r"(bar)
+				             : "memory");
+			}
+		}
+		__syncthreads();
+		unsigned done = 0;
+		while (!done)
+			asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar) : "memory");
+	}
+#else
 	for (int a = 0; a < SRBA_I_COUNT; a++) {
 		if (h->img_sm[a] == SRBA_NOT_IN_SMEM) continue;
 		const uint4 *src = reinterpret_cast<const uint4 *>(img + h->img_off[a]);
@@ -1694,6 +1726,7 @@ __device__ void lm_program(const DevProblem *gh, const char *img, char *ws, char
 		const int n16 = (int)((h->img_len[a] + 15) >> 4);
 		for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
 	}
+#endif
 	const int n = h->n_dense, nsc = h->n_scalars;
 	const int nObsRows = h->n_total_obs_rows;
 

@@ -51,7 +51,8 @@ struct WaveArgs {
 // sized for the largest area of the group and the surplus CTAs of smaller areas leave at once.
 __device__ __forceinline__ int wave_team_ctas(int64_t items, int threads, int cap) { return (int)max((int64_t)1, min((items + threads - 1) / threads, (int64_t)cap)); }
 __device__ __forceinline__ bool wave_team(int64_t items, int cap) {
-	const int gx = wave_team_ctas(items, (int)blockDim.x, cap);
+	// (never more CTAs than the launch holds: a grid sized too small on the host must cost time, not silently drop items)
+	const int gx = min(wave_team_ctas(items, (int)blockDim.x, cap), (int)gridDim.x);
 	if ((int)blockIdx.x >= gx) return false;
 	if (threadIdx.x == 0) g_wave_gx = gx;
 	__syncthreads();

@@ -11,6 +11,7 @@ A step = one pass of the hot path over the config's problem set (every problem r
 `value` device-timed with the packed problems resident in HBM; `e2e` through srba_b200_optimize_batch with host buffers."""
 import ctypes as C
 import json
+import math
 import os
 import sys
 import time
@@ -55,8 +56,24 @@ def main(args):
                   use_robust_kernel=1)
     eng = sb.RbaEngine(sb.default_engine_params(**kw))
     t0 = time.perf_counter()
-    for f in ds["frames"]:
-        D.feed(eng, f, run_local_optimization=cfg["whole_map"])   # whole-map configs: a real sequential SLAM run builds the map first
+    if cfg["obs"] == "mono":
+        # monocular BA is scale-free and landmark_matcher<MonocularCamera> gives no edge initial value, so the map is built with
+        # define_new_keyframe(..., run_local_optimization=false), landmark guesses (is_unknown_with_init_val, sigma 5 cm) and perturbed
+        # ground-truth edge values (sigma 1 cm / 0.5 deg); the whole-map call below does all the optimisation
+        for f in ds["frames"]:
+            D.feed(eng, f, run_local_optimization=False)
+        rng = np.random.default_rng(7)
+        ft, _ = eng.edges()
+        for i, (a_, b_) in enumerate(ft.astype(int)):
+            Tab = np.linalg.inv(ds["gt"][b_]) @ ds["gt"][a_]        # inv_pose: pose of `from` as seen from `to` (srba_types.h:88)
+            w = rng.normal(0, math.radians(0.5), 3)
+            Wm = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+            R = Tab[:3, :3] @ (np.eye(3) + Wm + 0.5 * Wm @ Wm)
+            U, _, Vt = np.linalg.svd(R)
+            eng.set_edge_pose(i, np.concatenate([(U @ Vt).ravel(), Tab[:3, 3] + rng.normal(0, 0.01, 3)]))
+    else:
+        for f in ds["frames"]:
+            D.feed(eng, f, run_local_optimization=cfg["whole_map"])   # whole-map stereo: a real sequential SLAM run builds the map first
     t_map = time.perf_counter() - t0
     t0 = time.perf_counter()
     if cfg["whole_map"]:
