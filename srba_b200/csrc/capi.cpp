@@ -745,7 +745,7 @@ bool wave_candidate(const srba_problem_t &p) {
 	const int fw = option(OPT_WAVE);
 	if (fw == 0 || option(OPT_CLUSTER) == 1 || option(OPT_BLOCKED) != 0) return false;
 	if (fw == 1) return true;
-	if (p.model.pose_kind != SRBA_POSE_SE2) return false;
+	if (p.model.pose_kind != SRBA_POSE_SE2) return p.n_unk_edges >= SRBA_WAVE_SE3_MIN_EDGES;
 	const uint64_t demand = (uint64_t)2 * p.n_pairs * 3 * 8 + (uint64_t)p.n_blkA * 3 * 3 * 8 + (uint64_t)p.n_HAp * 9 * 8;
 	return demand > (uint64_t)srba_kernel_cfg(0).smem_bytes;
 }
@@ -783,8 +783,10 @@ void pack_problem(const srba_problem_t &p, DevProblem &h, char *base, int trace_
 	// Measured (profiles/r02_*): the wave pipeline wins on SE(2) loop-closure areas (hundreds of unknown edges, 100-240 elimination levels:
 	// 109 ms vs 172 ms per 256-area batch); on SE(3) landmark areas (n_p ~ 90, reduced system ~30 % dense) the level solver's tile
 	// traffic through L2 makes it slower than one CTA per area (540 vs 345 ms per 1 000 areas), so "auto" keeps those on the one-CTA /
-	// cluster-team program and the wave mode is opt-in there (option "wave" = 1).
-	const bool wave_allowed = !want_dense && !force_blocked && force_cluster != 1 && force_wave != 0 && (force_wave == 1 || model == 0);
+	// cluster-team program and the wave mode is opt-in there (option "wave" = 1) -- except whole-map-scale SE(3) problems (hundreds of unknown
+	// edges in ONE area: BASELINE configs #2 / #3), where the level schedule + cluster team beat the sequential block-row elimination of the
+	// 8-CTA cluster program 2.9x / 4.1x (9.5 -> 3.3 ms and 52.9 -> 12.9 ms per LM iteration, profiles/r02_bench_config{2,3}*.json).
+	const bool wave_allowed = !want_dense && !force_blocked && force_cluster != 1 && force_wave != 0 && (force_wave == 1 || model == 0 || p.n_unk_edges >= SRBA_WAVE_SE3_MIN_EDGES);
 	bool cluster = false, wave = false;
 	if (!base) {  // layout pass: symbolic factorisation (reused by the copy pass)
 		if (wave_allowed && (force_wave == 1 || demand_no_tiles > (uint64_t)cfg.smem_bytes)) { symbolic_levels(p, P, sy); wave = sy.ok; }

@@ -17,6 +17,8 @@
 #define SRBA_WAVE_TAIL_ROWS 70
 // wave solver: an area whose levels below the tail hold at least this many destination tiles on average runs them as an 8-CTA cluster team
 #define SRBA_WAVE_TEAM_DST_PER_LEVEL 600
+// "auto" execution mode: SE(3) problems with at least this many unknown edges (whole-map scale) take the wave pipeline
+#define SRBA_WAVE_SE3_MIN_EDGES 256
 
 // (type, name) of every array of the input image, in srba_problem_t order + derived ones: block -> column, and the
 // symbolic factorisation of the reduced system at 3x3-tile granularity (tiles numbered row-major, diagonal first, the
