@@ -479,13 +479,9 @@ def main():
         strong_trials = float(sum(sb_.stats(i)["num_trials"] for i in range(sb_.n)))
         del sb_
 
-    tvec = torch.tensor([dev_ms, e2e_s, strong_ms], dtype=torch.float64, device="cuda")
-    cvec = torch.tensor([float(trials_per_step), float(e2e_trials), strong_trials], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tvec, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cvec, op=dist.ReduceOp.SUM)
-    dev_ms_max, e2e_s_max, strong_ms_max = tvec.tolist()
-    trials_all, e2e_trials_all, strong_trials_all = cvec.tolist()
+    from srba_b200 import parallel as PL   # time = MAX over ranks, work = SUM over ranks (the only collectives: no data-path exchange)
+    (dev_ms_max, e2e_s_max, strong_ms_max), (trials_all, e2e_trials_all, strong_trials_all) = PL.reduce_max_sum(
+        [dev_ms, e2e_s, strong_ms], [trials_per_step, e2e_trials, strong_trials], device="cuda")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -1280,7 +1280,13 @@ static srba_batch_t *batch_create_impl(int32_t n, const srba_problem_t *const *i
 		allow_cluster = clusters_pay(n_heavy) ? 1 : 0;
 	}
 	const bool ac = allow_cluster != 0;
-	workers().parallel_for(n, [&](int i) { pack_problem(*in[i], b->hdr[i], nullptr, tcap, want_dense, b->sym[i], ac); });  // layout + symbolic
+	// (largest problems first: the symbolic schedule of a 600-edge loop-closure area takes tens of ms, started last it would be the tail of the pool)
+	std::vector<int32_t> by_cost(n);
+	std::iota(by_cost.begin(), by_cost.end(), 0);
+	std::stable_sort(by_cost.begin(), by_cost.end(), [&](int a, int c) {
+		return (int64_t)in[a]->n_unk_edges * in[a]->n_unk_edges + in[a]->n_blkA > (int64_t)in[c]->n_unk_edges * in[c]->n_unk_edges + in[c]->n_blkA;
+	});
+	workers().parallel_for(n, [&](int q) { const int i = by_cost[q]; pack_problem(*in[i], b->hdr[i], nullptr, tcap, want_dense, b->sym[i], ac); });  // layout + symbolic
 	for (int i = 0; i < n; i++) {
 		b->img_off[i] = I.add(b->hdr[i].img_bytes);
 		b->ws_off[i] = ws; ws += b->hdr[i].ws_bytes;
@@ -1346,7 +1352,7 @@ static srba_batch_t *batch_create_impl(int32_t n, const srba_problem_t *const *i
 	std::memcpy(b->h_img + b->tab_ws_off, b->ws_off.data(), (size_t)n * 8);
 	std::memcpy(b->h_img + b->tab_res_off, b->res_off.data(), (size_t)n * 8);
 	std::memcpy(b->h_img + b->tab_order, b->order.data(), (size_t)n * 4);
-	workers().parallel_for(n, [&](int i) { pack_problem(*in[i], b->hdr[i], b->h_img + b->img_off[i], tcap, want_dense, b->sym[i], ac); });  // copy
+	workers().parallel_for(n, [&](int q) { const int i = by_cost[q]; pack_problem(*in[i], b->hdr[i], b->h_img + b->img_off[i], tcap, want_dense, b->sym[i], ac); });  // copy
 	return b;
 }
 

@@ -21,6 +21,18 @@ def reduce_timing(elapsed_ms, n_trials, device="cpu"):
     return float(t.item()), float(c.item())
 
 
+def reduce_max_sum(max_values, sum_values, device="cpu"):
+    """Element-wise MAX over ranks of `max_values` (timings) and SUM over ranks of `sum_values` (counts); lists of floats in and out.
+    Identity when torch.distributed is not initialised.  What bench.py / tools/bench_configs.py use for their multi-rank lines."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [float(v) for v in max_values], [float(v) for v in sum_values]
+    t = torch.tensor([float(v) for v in max_values], dtype=torch.float64, device=device)
+    c = torch.tensor([float(v) for v in sum_values], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    return t.tolist(), c.tolist()
+
+
 def gather_unknowns(local_ids, local_values, device="cpu"):
     """Optional: all ranks receive every rank's optimised unknowns (ids int64 [k], values float64 [k, d]).
     Sizes may differ per rank; padded all_gather."""

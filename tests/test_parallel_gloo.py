@@ -27,6 +27,8 @@ def _worker(rank, world, port, q):
     ms = float(sum(i + 1 for i in mine))
     trials = float(sum(i + 2 for i in mine))
     tmax, ttot = P.reduce_timing(ms, trials)
+    (m1, m2), (s1,) = P.reduce_max_sum([ms, -ms], [trials])   # the helper bench.py / tools/bench_configs.py use
+    assert (m1, s1) == (tmax, ttot) and m2 <= 0
     ids = torch.tensor(mine, dtype=torch.int64)
     vals = torch.stack([ids.double(), ids.double() * 2], dim=1)
     gi, gv = P.gather_unknowns(ids, vals)

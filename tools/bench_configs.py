@@ -121,13 +121,7 @@ def main(args):
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None
     e2e_trials = sum(b_.r.stats.num_trials for b_ in bufs)
-    tvec = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
-    cvec = torch.tensor([float(trials), float(e2e_trials)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tvec, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cvec, op=dist.ReduceOp.SUM)
-    dev_ms_max, e2e_s_max = tvec.tolist()
-    trials_all, e2e_trials_all = cvec.tolist()
+    (dev_ms_max, e2e_s_max), (trials_all, e2e_trials_all) = PL.reduce_max_sum([dev_ms, e2e_s], [trials, e2e_trials], device="cuda")
     if rank == 0:
         peak, peak_src = B.measured_peaks()
         ab = B.algorithmic_bytes(flats, stats)
