@@ -512,6 +512,9 @@ void symbolic_tiles(const srba_problem_t &p, int P, long max_tiles_on_chip, Tile
 // and the backward pass walks the levels downwards, one warp per row.  Two team barriers per level instead of one per block row:
 // a 641-edge loop-closure area has 150 levels for 641 rows, and every phase has enough independent work for thousands of threads.
 void symbolic_levels(const srba_problem_t &p, int P, TileSymbolic &sy, bool debug_format = false) {
+	static const bool sym_timing = std::getenv("SRBA_B200_SYM_TIMING") != nullptr;
+	auto sym_t0 = std::chrono::steady_clock::now();
+#define SYM_T(name) do { if (sym_timing) { auto n_ = std::chrono::steady_clock::now(); std::fprintf(stderr, "[sym] %s %.2f ms\n", name, std::chrono::duration<double, std::milli>(n_ - sym_t0).count()); sym_t0 = n_; } } while (0)
 	const int q = P / 3, np = p.n_unk_edges, ntr = q * np, ntc = ntr + 1;
 	sy.clear();
 	sy.ntr = ntr;
@@ -555,6 +558,7 @@ void symbolic_levels(const srba_problem_t &p, int P, TileSymbolic &sy, bool debu
 			perm.push_back(i);
 		}
 	}
+	SYM_T("order");
 	std::vector<int> inv(np);
 	for (int i = 0; i < np; i++) inv[perm[i]] = i;
 	// ---- filled pattern at tile level in that order (row bitsets, column ntr = right-hand side) + where every tile comes from
@@ -595,6 +599,7 @@ void symbolic_levels(const srba_problem_t &p, int P, TileSymbolic &sy, bool debu
 			}
 		}
 	}
+	SYM_T("fill");
 	// ---- levels, rows sorted by level (stable): rank[old row] = new row
 	std::vector<int> level(ntr, 0), order(ntr), rank(ntr);
 	for (int k = 0; k < ntr; k++) {
@@ -615,6 +620,7 @@ void symbolic_levels(const srba_problem_t &p, int P, TileSymbolic &sy, bool debu
 	const int nlev = level[order[ntr - 1]] + 1;
 	sy.orow.resize(ntr);
 	for (int r = 0; r < ntr; r++) { const int o = order[r]; sy.orow[r] = q * perm[o / q] + o % q; }
+	SYM_T("levels");
 	// ---- tile numbering in the new order: row-major, diagonal first, ascending column, right-hand side last
 	std::sort(srcs.begin(), srcs.end(), [](const Src &a, const Src &b) { return a.key < b.key; });
 	sy.rs.assign(ntr + 1, 0);
@@ -651,6 +657,7 @@ void symbolic_levels(const srba_problem_t &p, int P, TileSymbolic &sy, bool debu
 		const int32_t key = (i << 16) | j;
 		return (int32_t)(std::lower_bound(sy.tile_ij.begin() + sy.rs[i], sy.tile_ij.begin() + sy.rs[i + 1], key) - sy.tile_ij.begin());
 	};
+	SYM_T("tiles");
 	// ---- per level: destinations with their contributions (ascending source row)
 	std::vector<int32_t> dst, cptr(1, 0), cab, slot(ntiles, -1), trip, cnt;
 	std::vector<size_t> pos;
@@ -668,9 +675,10 @@ void symbolic_levels(const srba_problem_t &p, int P, TileSymbolic &sy, bool debu
 		for (int k = r0; k < r; k++)
 			for (int a = sy.rs[k] + 1; a < sy.rs[k + 1] - 1; a++) {  // tile (k,i): off-diagonal, not the right-hand side
 				const int i = sy.tile_ij[a] & 0xffff;
+				int32_t d = sy.rs[i];   // row i holds every column j >= i of row k (fill): both lists ascend, so one merge walk finds the tiles
 				for (int b = a; b < sy.rs[k + 1]; b++) {           // tile (k,j), j >= i, right-hand side included
-					const int j = sy.tile_ij[b] & 0xffff;
-					const int32_t d = find_tile(i, j);
+					const int32_t key = (i << 16) | (sy.tile_ij[b] & 0xffff);
+					while (sy.tile_ij[d] != key) d++;
 					if (slot[d] < 0) { slot[d] = (int32_t)cnt.size(); cnt.push_back(0); dst.push_back(d); }
 					cnt[slot[d]]++;
 					trip.push_back(slot[d]); trip.push_back(a); trip.push_back(b);
@@ -688,6 +696,7 @@ void symbolic_levels(const srba_problem_t &p, int P, TileSymbolic &sy, bool debu
 		}
 		for (int e = d0; e < (int)dst.size(); e++) slot[dst[e]] = -1;
 	}
+	SYM_T("dests");
 	sy.phase[2 * (size_t)nlev] = ntr;
 	sy.phase[2 * (size_t)nlev + 1] = (int32_t)dst.size();
 	sy.n_phases = nlev;
@@ -707,22 +716,25 @@ void symbolic_levels(const srba_problem_t &p, int P, TileSymbolic &sy, bool debu
 		// device format (lm_wave.cuh: wave_solve_fwd_kernel), 16-byte records so that a destination with ONE contribution -- almost all of
 		// them -- costs two dependent loads:  [n_dst x {dst, tile(k,a), tile(k,b), diagonal tile of row k} : the FIRST contribution]
 		// [n_dst + 1 pointers into the further contributions, padded to 4 ints] [{tile(k,a), tile(k,b), diagonal tile of row k, 0} ...]
-		const size_t nd = dst.size();
-		std::vector<int32_t> xptr(1, 0), extra;
-		sy.upd.reserve(4 * nd + nd + 4);
+		const size_t nd = dst.size(), n_extra = cab.size() / 2 - nd, xlen = (nd + 1 + 3) & ~(size_t)3;
+		sy.upd.resize(4 * nd + xlen + 4 * n_extra);
+		int32_t *rec = sy.upd.data(), *xptr = rec + 4 * nd, *extra = xptr + xlen;
+		size_t nx = 0;
 		for (size_t e = 0; e < nd; e++) {
 			const int c0 = cptr[e], c1 = cptr[e + 1];
-			for (int c = c0; c < c1; c++) {
-				const int32_t ta = cab[2 * (size_t)c], tb = cab[2 * (size_t)c + 1], td = sy.rs[sy.tile_ij[ta] >> 16];
-				if (c == c0) { sy.upd.push_back(dst[e]); sy.upd.push_back(ta); sy.upd.push_back(tb); sy.upd.push_back(td); }
-				else { extra.push_back(ta); extra.push_back(tb); extra.push_back(td); extra.push_back(0); }
+			xptr[e] = (int32_t)nx;
+			{
+				const int32_t ta = cab[2 * (size_t)c0], tb = cab[2 * (size_t)c0 + 1];
+				rec[4 * e] = dst[e]; rec[4 * e + 1] = ta; rec[4 * e + 2] = tb; rec[4 * e + 3] = sy.rs[sy.tile_ij[ta] >> 16];
 			}
-			xptr.push_back((int32_t)(extra.size() / 4));
+			for (int c = c0 + 1; c < c1; c++, nx++) {
+				const int32_t ta = cab[2 * (size_t)c], tb = cab[2 * (size_t)c + 1];
+				extra[4 * nx] = ta; extra[4 * nx + 1] = tb; extra[4 * nx + 2] = sy.rs[sy.tile_ij[ta] >> 16]; extra[4 * nx + 3] = 0;
+			}
 		}
-		while (xptr.size() % 4) xptr.push_back(xptr.back());
-		sy.upd.insert(sy.upd.end(), xptr.begin(), xptr.end());
-		sy.upd.insert(sy.upd.end(), extra.begin(), extra.end());
+		for (size_t e = nd; e < xlen; e++) xptr[e] = (int32_t)nx;
 	}
+	SYM_T("format");
 	sy.levels = true;
 	sy.ok = true;
 }
