@@ -510,8 +510,8 @@ __global__ void __launch_bounds__(WAVE_TAIL_NT) wave_solve_tail_kernel(const Wav
 // x_k = inv(D_k) (y_k - sum_j T(k,j) x_j) down the levels below the tail, one warp per row; the pivot blocks are final here: a block with a
 // non-positive leading minor books the failed factorisation.
 template <int P, int OBSK, bool TEAM>
-__global__ void __launch_bounds__(TEAM ? WAVE_SOLVE_NT : WAVE_SOLO_NT) wave_solve_bwd_kernel(const WaveArgs a) {
-	const int area = TEAM ? a.big[blockIdx.y] : a.solo[blockIdx.y];
+__global__ void __launch_bounds__(TEAM ? WAVE_SOLVE_NT : WAVE_SOLO_NT) wave_solve_bwd_kernel(const WaveArgs a, int big_list) {
+	const int area = (TEAM || big_list) ? a.big[blockIdx.y] : a.solo[blockIdx.y];
 	WaveArea &s = a.st[area];
 	if (!s.go) return;
 	const View &vg = a.views[area];
@@ -814,7 +814,6 @@ int wave_run(const WaveArgs &a, const SrbaWaveDims &d, int *h_active_pinned, cud
 	scfg.attrs = sattr;
 	scfg.numAttrs = 1;
 	auto solve_fwd = wave_solve_fwd_kernel<P, OBSK, true>;
-	auto solve_bwd = wave_solve_bwd_kernel<P, OBSK, true>;
 	auto solve_tail = wave_solve_tail_kernel<P, OBSK>;
 	const size_t tail_smem = wave_tail_smem_bytes(std::max(1, d.max_tail_rows));
 	if (cudaFuncSetAttribute(solve_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem) != cudaSuccess) return (int)cudaGetLastError();
@@ -878,8 +877,10 @@ int wave_run(const WaveArgs &a, const SrbaWaveDims &d, int *h_active_pinned, cud
 		if (both) { cudaEventRecord(ev_join, side); cudaStreamWaitEvent(st, ev_join, 0); }
 		solve_tail<<<n, WAVE_TAIL_NT, tail_smem, st>>>(a);
 		if (both) { cudaEventRecord(ev_fork, st); cudaStreamWaitEvent(side, ev_fork, 0); }
-		if (d.n_solo) { wave_solve_bwd_kernel<P, OBSK, false><<<dim3(1, (unsigned)d.n_solo, 1), WAVE_SOLO_NT, 0, st>>>(a); nl++; }
-		if (d.n_big) { const cudaError_t e = cudaLaunchKernelEx(&scfg, solve_bwd, a); if (e != cudaSuccess) { rc = (int)e; break; } nl++; }
+		// The back-substitution has at most a handful of rows per level (one warp each): a cluster only adds barrier latency there, so the
+		// wide areas run it with ONE CTA as well (CTA barriers, all of them resident at once) -- on the side stream, next to the solo areas.
+		if (d.n_solo) { wave_solve_bwd_kernel<P, OBSK, false><<<dim3(1, (unsigned)d.n_solo, 1), WAVE_SOLO_NT, 0, st>>>(a, 0); nl++; }
+		if (d.n_big) { wave_solve_bwd_kernel<P, OBSK, false><<<dim3(1, (unsigned)d.n_big, 1), WAVE_SOLO_NT, 0, scfg.stream>>>(a, 1); nl++; }
 		if (both) { cudaEventRecord(ev_join, side); cudaStreamWaitEvent(st, ev_join, 0); }
 		wave_solve_finish_kernel<P, OBSK><<<n, 256, 0, st>>>(a);
 		nl++;

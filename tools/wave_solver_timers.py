@@ -16,6 +16,6 @@ for i, f in enumerate(flats):
     b.L.srba_b200_batch_stage_cycles(b.h, i, out.ctypes.data_as(C.POINTER(C.c_uint64)))
     rows.append((f.p.n_unk_edges, b.stats(i)["num_trials"], out[:7].astype(np.float64) / 1e3))
 rows.sort(key=lambda r: -r[0])
-print("n_p trials | us per trial: gather A syncA B syncB | bwd row sync")
+print("n_p trials | us per trial: gather - - B syncB | bwd row sync")
 for n_p, tr, t in rows[:10] + rows[100:104] + rows[200:203]:
     print(n_p, tr, " ".join("%8.1f" % (x / max(1, tr)) for x in t))
