@@ -16,7 +16,9 @@
 // wave solver: tile rows of the trailing dense triangle that one CTA keeps in shared memory ((R+1)(R+2)/2 tiles of 72 B + row buffers)
 #define SRBA_WAVE_TAIL_ROWS 70
 // wave solver: an area whose levels below the tail hold at least this many destination tiles on average runs them as an 8-CTA cluster team
+#ifndef SRBA_WAVE_TEAM_DST_PER_LEVEL
 #define SRBA_WAVE_TEAM_DST_PER_LEVEL 600
+#endif
 // "auto" execution mode: SE(3) problems with at least this many unknown edges (whole-map scale) take the wave pipeline
 #define SRBA_WAVE_SE3_MIN_EDGES 256
 
