@@ -658,81 +658,77 @@ void symbolic_levels(const srba_problem_t &p, int P, TileSymbolic &sy, bool debu
 		return (int32_t)(std::lower_bound(sy.tile_ij.begin() + sy.rs[i], sy.tile_ij.begin() + sy.rs[i + 1], key) - sy.tile_ij.begin());
 	};
 	SYM_T("tiles");
-	// ---- per level: destinations with their contributions (ascending source row)
-	std::vector<int32_t> dst, cptr(1, 0), cab, slot(ntiles, -1), trip, cnt;
-	std::vector<size_t> pos;
+	// ---- per level: destinations with their contributions (ascending source row).  Built directly in the device format (lm_wave.cuh:
+	// wave_solve_fwd_kernel): 16-byte records so that a destination with ONE contribution -- almost all of them -- costs two dependent loads:
+	//   [n_dst x {dst, tile(k,a), tile(k,b), diagonal tile of row k} : the FIRST contribution of each destination]
+	//   [n_dst + 1 pointers into the further contributions, padded to 4 ints] [{tile(k,a), tile(k,b), diagonal tile of row k, 0} ...]
+	// One pass: the first contribution of a destination writes its record; the rare further ones go to a side list that is bucketed by
+	// destination entry afterwards (stable: ascending source row is kept).
+	std::vector<int32_t> rec, ex, slot(ntiles, -1), touched;
+	rec.reserve(16 * (size_t)ntiles);
 	sy.phase.assign(2 * (size_t)(nlev + 1), 0);
-	int r = 0;
+	int r = 0, ne = 0;
 	for (int L = 0; L < nlev; L++) {
 		sy.phase[2 * (size_t)L] = r;
-		sy.phase[2 * (size_t)L + 1] = (int32_t)dst.size();
-		const int r0 = r, d0 = (int)dst.size();
+		sy.phase[2 * (size_t)L + 1] = ne;
+		const int r0 = r;
 		while (r < ntr && level[order[r]] == L) r++;
-		// contributions of the level grouped by destination (first-seen order), ascending source row inside a destination: two passes
-		// over a flat triple list (count, then place) -- no per-destination containers
-		trip.clear();
-		cnt.clear();
-		for (int k = r0; k < r; k++)
-			for (int a = sy.rs[k] + 1; a < sy.rs[k + 1] - 1; a++) {  // tile (k,i): off-diagonal, not the right-hand side
+		touched.clear();
+		for (int k = r0; k < r; k++) {
+			const int32_t td = sy.rs[k], k_end = sy.rs[k + 1];
+			for (int a = td + 1; a < k_end - 1; a++) {  // tile (k,i): off-diagonal, not the right-hand side
 				const int i = sy.tile_ij[a] & 0xffff;
 				int32_t d = sy.rs[i];   // row i holds every column j >= i of row k (fill): both lists ascend, so one merge walk finds the tiles
-				for (int b = a; b < sy.rs[k + 1]; b++) {           // tile (k,j), j >= i, right-hand side included
+				for (int b = a; b < k_end; b++) {           // tile (k,j), j >= i, right-hand side included
 					const int32_t key = (i << 16) | (sy.tile_ij[b] & 0xffff);
 					while (sy.tile_ij[d] != key) d++;
-					if (slot[d] < 0) { slot[d] = (int32_t)cnt.size(); cnt.push_back(0); dst.push_back(d); }
-					cnt[slot[d]]++;
-					trip.push_back(slot[d]); trip.push_back(a); trip.push_back(b);
+					if (slot[d] < 0) {
+						slot[d] = ne++;
+						touched.push_back(d);
+						rec.push_back(d); rec.push_back(a); rec.push_back(b); rec.push_back(td);
+					} else { ex.push_back(slot[d]); ex.push_back(a); ex.push_back(b); ex.push_back(td); }
 				}
 			}
-		const size_t base = cab.size() / 2;
-		pos.resize(cnt.size());
-		size_t run = base;
-		for (size_t e = 0; e < cnt.size(); e++) { pos[e] = run; run += cnt[e]; cptr.push_back((int32_t)run); }
-		cab.resize(2 * run);
-		for (size_t q = 0; q < trip.size(); q += 3) {
-			const size_t at = pos[trip[q]]++;
-			cab[2 * at] = trip[q + 1];
-			cab[2 * at + 1] = trip[q + 2];
 		}
-		for (int e = d0; e < (int)dst.size(); e++) slot[dst[e]] = -1;
+		for (int32_t d : touched) slot[d] = -1;
 	}
 	SYM_T("dests");
 	sy.phase[2 * (size_t)nlev] = ntr;
-	sy.phase[2 * (size_t)nlev + 1] = (int32_t)dst.size();
+	sy.phase[2 * (size_t)nlev + 1] = ne;
 	sy.n_phases = nlev;
 	// the tail: the last levels holding at most SRBA_WAVE_TAIL_ROWS tile rows in total (dense elimination in shared memory)
 	sy.tail_level = nlev;
 	while (sy.tail_level > 0 && ntr - sy.phase[2 * (size_t)(sy.tail_level - 1)] <= SRBA_WAVE_TAIL_ROWS) sy.tail_level--;
-	sy.n_dst = (int)dst.size();
-	sy.n_contrib = (int)(cab.size() / 2);
+	const size_t nd = (size_t)ne, n_extra = ex.size() / 4, xlen = (nd + 1 + 3) & ~(size_t)3;
+	sy.n_dst = ne;
+	sy.n_contrib = (int)(nd + n_extra);
+	// further contributions bucketed by destination entry (counting sort, stable)
+	std::vector<int32_t> xptr(xlen, 0), extra(4 * n_extra);
+	for (size_t q = 0; q < n_extra; q++) xptr[(size_t)ex[4 * q] + 1]++;
+	for (size_t e = 0; e < nd; e++) xptr[e + 1] += xptr[e];
+	for (size_t e = nd + 1; e < xlen; e++) xptr[e] = xptr[nd];
+	{
+		std::vector<int32_t> at(xptr.begin(), xptr.begin() + nd);
+		for (size_t q = 0; q < n_extra; q++) {
+			const size_t w = (size_t)at[ex[4 * q]]++;
+			extra[4 * w] = ex[4 * q + 1]; extra[4 * w + 1] = ex[4 * q + 2]; extra[4 * w + 2] = ex[4 * q + 3]; extra[4 * w + 3] = 0;
+		}
+	}
 	sy.upd.clear();
 	if (debug_format) {  // srba_b200_debug_level_schedule: [dst | contribution pointer | 1 pad | (tile(k,a), tile(k,b)) x n_contrib]
-		sy.upd.reserve(dst.size() + cptr.size() + cab.size());
-		sy.upd.insert(sy.upd.end(), dst.begin(), dst.end());
-		sy.upd.insert(sy.upd.end(), cptr.begin(), cptr.end());
+		sy.upd.reserve(2 * nd + 2 + 2 * (nd + n_extra));
+		for (size_t e = 0; e < nd; e++) sy.upd.push_back(rec[4 * e]);
+		for (size_t e = 0; e <= nd; e++) sy.upd.push_back((int32_t)(e + (size_t)xptr[e]));   // first + further contributions before entry e
 		sy.upd.push_back(0);
-		sy.upd.insert(sy.upd.end(), cab.begin(), cab.end());
-	} else {
-		// device format (lm_wave.cuh: wave_solve_fwd_kernel), 16-byte records so that a destination with ONE contribution -- almost all of
-		// them -- costs two dependent loads:  [n_dst x {dst, tile(k,a), tile(k,b), diagonal tile of row k} : the FIRST contribution]
-		// [n_dst + 1 pointers into the further contributions, padded to 4 ints] [{tile(k,a), tile(k,b), diagonal tile of row k, 0} ...]
-		const size_t nd = dst.size(), n_extra = cab.size() / 2 - nd, xlen = (nd + 1 + 3) & ~(size_t)3;
-		sy.upd.resize(4 * nd + xlen + 4 * n_extra);
-		int32_t *rec = sy.upd.data(), *xptr = rec + 4 * nd, *extra = xptr + xlen;
-		size_t nx = 0;
 		for (size_t e = 0; e < nd; e++) {
-			const int c0 = cptr[e], c1 = cptr[e + 1];
-			xptr[e] = (int32_t)nx;
-			{
-				const int32_t ta = cab[2 * (size_t)c0], tb = cab[2 * (size_t)c0 + 1];
-				rec[4 * e] = dst[e]; rec[4 * e + 1] = ta; rec[4 * e + 2] = tb; rec[4 * e + 3] = sy.rs[sy.tile_ij[ta] >> 16];
-			}
-			for (int c = c0 + 1; c < c1; c++, nx++) {
-				const int32_t ta = cab[2 * (size_t)c], tb = cab[2 * (size_t)c + 1];
-				extra[4 * nx] = ta; extra[4 * nx + 1] = tb; extra[4 * nx + 2] = sy.rs[sy.tile_ij[ta] >> 16]; extra[4 * nx + 3] = 0;
-			}
+			sy.upd.push_back(rec[4 * e + 1]); sy.upd.push_back(rec[4 * e + 2]);
+			for (int32_t c = xptr[e]; c < xptr[e + 1]; c++) { sy.upd.push_back(extra[4 * (size_t)c]); sy.upd.push_back(extra[4 * (size_t)c + 1]); }
 		}
-		for (size_t e = nd; e < xlen; e++) xptr[e] = (int32_t)nx;
+	} else {
+		sy.upd.resize(4 * nd + xlen + 4 * n_extra);
+		std::memcpy(sy.upd.data(), rec.data(), 4 * nd * sizeof(int32_t));
+		std::memcpy(sy.upd.data() + 4 * nd, xptr.data(), xlen * sizeof(int32_t));
+		if (n_extra) std::memcpy(sy.upd.data() + 4 * nd + xlen, extra.data(), 4 * n_extra * sizeof(int32_t));
 	}
 	SYM_T("format");
 	sy.levels = true;

@@ -290,3 +290,56 @@ def test_level_schedule_solves_the_reduced_system(kind):
         assert nlev <= ntr
         if kind == "se2" and ntr >= 16:
             assert nlev <= 0.6 * ntr   # independent minimum-degree rounds: a chain is halved per round, not peeled from its ends
+
+
+def test_wave_counts_and_execution_mode_policy():
+    """srba_b200_problem_wave_counts / srba_b200_problem_plan (host-only): which problems "auto" sends to the grid-wide wave pipeline --
+    SE(2) areas that overflow one CTA's arena (loop closures), not chain-like SE(2) areas, not SE(3) landmark areas of local-area size --
+    and the shape of their level schedule (dense tail of at most SRBA_WAVE_TAIL_ROWS = 70 tile rows, team flag)."""
+    import ctypes as C
+    from srba_b200 import _capi as K
+    L = K.lib()
+
+    def counts(flat):
+        o8, o = (C.c_int64 * 8)(), (C.c_int64 * 8)()
+        assert L.srba_b200_problem_wave_counts(flat.problem, o8) == 0 and L.srba_b200_problem_plan(flat.problem, o) == 0
+        return list(o8), list(o)
+    # a tour that keeps revisiting its corridors: areas with hundreds of unknown edges
+    ds = D.graphslam_se2_tour(1500, seed=1)
+    kw = dict(pose_kind=0, obs_kind=0, noise_kind=1, noise_lambda=D.se2_noise_lambda(ds["sigma_xy"], ds["sigma_yaw"]), max_tree_depth=3, max_optimize_depth=3,
+              submap_size=10, min_obs_to_loop_closure=1)
+    ep = sb.RbaEngine(sb.default_engine_params(**kw))
+    small = big = None
+    for k, f in enumerate(ds["frames"]):
+        D.feed(ep, f, run_local_optimization=False)
+        if k == 60:
+            small = ep.flatten_local_area(k, 3)
+        if k > 800 and k % 20 == 0:     # keep the largest area met on the way
+            fl = ep.flatten_local_area(k, 3)
+            if big is None or fl.p.n_unk_edges > big.p.n_unk_edges:
+                big = fl
+    w, plan = counts(small)
+    assert w == [0] * 8 and plan[4] < 4 and plan[6] > 0          # chain-like: the one-CTA program with its arrays on chip
+    w, plan = counts(big)
+    assert big.p.n_unk_edges > 100 and plan[4] & 4 and plan[6] == 0   # wave pipeline, every array in the global workspace
+    tiles, ndst, ncontrib, levels, tail_level, team, tiles_below, dst_below = w
+    assert tiles > 0 and ncontrib >= ndst > 0 and 0 <= tail_level <= levels and tiles_below <= tiles and dst_below <= ndst
+    assert team == (1 if tail_level > 0 and ndst >= 600 * tail_level else 0)
+    old = K.set_option("wave", 0)
+    try:
+        assert counts(big)[0] == [0] * 8 and not (counts(big)[1][4] & 4)
+    finally:
+        K.set_option("wave", old)
+    # SE(3) landmark areas of local-area size stay on the one-CTA / cluster program unless the wave mode is forced
+    d3 = D.landmark_slam_se3(n_kfs=40, n_lms=400, seed=3, obs_kind="cartesian3d")
+    e3 = sb.RbaEngine(sb.default_engine_params(pose_kind=1, obs_kind=1, noise_kind=0, noise_std=1e-3, max_tree_depth=4, max_optimize_depth=4, submap_size=10,
+                                               min_obs_to_loop_closure=4))
+    for f in d3["frames"]:
+        D.feed(e3, f, run_local_optimization=False)
+    f3 = e3.flatten_local_area(39, 4)
+    assert counts(f3)[0] == [0] * 8
+    old = K.set_option("wave", 1)
+    try:
+        assert counts(f3)[0][0] > 0 and counts(f3)[1][4] & 4
+    finally:
+        K.set_option("wave", old)
