@@ -14,6 +14,7 @@
 // std::exception from ASSERT_ macros; this header throws std::runtime_error carrying srba_engine_last_error().
 // NOT provided (outside SURVEY.md 8): OpenGL/dot export, config-file loading, the four models BASELINE does not name.
 #pragma once
+#include <cmath>
 #include <cstring>
 #include <deque>
 #include <limits>
@@ -312,14 +313,18 @@ public:
 		srba_opt_info_t o;
 		std::memset(&o, 0, sizeof(o));
 		int rc;
+		const bool feedback = parameters.srba.feedback_user_iteration != NULL;
+		if (feedback) srba_engine_trace(m_h, 8 * (int)parameters.srba.max_iters + 16);
 		if (!observation_indices_to_optimize.empty()) {
 			std::vector<uint64_t> idx(observation_indices_to_optimize.begin(), observation_indices_to_optimize.end());
 			rc = srba_engine_optimize_local_area_obs(m_h, root_id, win_size, idx.size(), idx.data(), &o);
 		} else
 			rc = srba_engine_optimize_local_area(m_h, root_id, win_size, params.optimize_k2k_edges, params.optimize_landmarks, params.max_visitable_kf_id,
 			                                     params.dont_optimize_landmarks_seen_less_than_n_times, &o);
+		if (feedback) srba_engine_trace(m_h, 0);
 		if (rc != 0) throw std::runtime_error(srba_engine_last_error());
 		to_info(o, out_info);
+		if (feedback && o.num_observations > 0) replay_feedback(o);
 		{  // optimized index lists (RbaEngine.h:146-147): the unknown selection of this very call
 			uint64_t nk = 0, nl = 0;
 			srba_engine_select_local_area(m_h, root_id, win_size, NULL, 0, &nk, NULL, 0, &nl);
@@ -331,6 +336,25 @@ public:
 		m_state_dirty = true;
 	}
 
+private:
+	/** parameters.srba.feedback_user_iteration replayed AFTER the call from the per-trial trace of the device loop: (0, initial error, RMSE) as
+	  * optimize_edges.h:417-418, then (iter, new error, new RMSE) for every accepted step with the value `iter` had (:595-596).
+	  * (define_new_keyframe runs up to three optimize_edges calls internally and does not replay them.) */
+	void replay_feedback(const srba_opt_info_t &o) {
+		const uint64_t n = srba_engine_last_trace(m_h, NULL, NULL, 0, NULL);
+		std::vector<double> tr(6 * n + 6);
+		srba_engine_last_trace(m_h, tr.data(), NULL, n, NULL);
+		const double nobs = (double)o.num_observations;
+		(*parameters.srba.feedback_user_iteration)(0u, o.total_sqr_error_init, std::sqrt(o.total_sqr_error_init / nobs));
+		unsigned iter = 0;
+		for (uint64_t t = 0; t < n; t++)
+			if (tr[6 * t + 1] != 0 && tr[6 * t + 4] != 0) {
+				(*parameters.srba.feedback_user_iteration)(iter, tr[6 * t + 3], std::sqrt(tr[6 * t + 3] / nobs));
+				iter++;
+			}
+	}
+
+public:
 	double eval_overall_squared_error() const {  // RbaEngine.h:381
 		const_cast<RbaEngine *>(this)->sync_params();
 		double e = 0;

@@ -139,12 +139,14 @@ void RbaEngine<KF2KF_POSE_TYPE, LM_TYPE, OBS_TYPE, RBA_OPTIONS>::optimize_edges(
 		m_profiler.leave("opt");
 		return;
 	}
-	srba_result_t res = flat->make_result_buffers(access_t::POSE_NVALS);
+	// (the per-trial trace is only requested when the user installed parameters.srba.feedback_user_iteration)
+	srba_result_t res = flat->make_result_buffers(access_t::POSE_NVALS, parameters.srba.feedback_user_iteration ? 8 * (int)parameters.srba.max_iters + 16 : 0);
 	if (srba_b200_optimize(&flat->p, &res) != SRBA_OK) {
 		m_profiler.leave("opt");
 		throw std::runtime_error(srba_b200_last_error());   // (the reference throws from its ASSERT_ macros)
 	}
 	srba_b200_shim::scatter<access_t>(rba_state, *flat, res);
+	srba_b200_shim::replay_feedback(parameters.srba.feedback_user_iteration, *flat, res);   // optimize_edges.h:417-418,595-596 (after the call, not during)
 	// landmark information matrices (optimize_edges.h:722-751, crpLandmarksApprox): the final H_f diagonal blocks of invertible landmarks
 	rba_state.unknown_lms_inf_matrices.clear();
 	if (parameters.srba.cov_recovery == crpLandmarksApprox)
@@ -166,6 +168,14 @@ void RbaEngine<KF2KF_POSE_TYPE, LM_TYPE, OBS_TYPE, RBA_OPTIONS>::optimize_edges(
 	out_info.total_sqr_error_init = res.stats.total_sqr_error_init;
 	out_info.total_sqr_error_final = res.stats.total_sqr_error_final;
 	out_info.obs_rmse = res.stats.obs_rmse;
+	if (parameters.srba.compute_sparsity_stats) {   // optimize_edges.h:315-327: stored blocks vs rows x columns of the active part
+		out_info.sparsity_dh_dAp_nnz = flat->p.n_blkA; out_info.sparsity_dh_dAp_max_size = (size_t)flat->p.n_obs * flat->p.n_unk_edges;
+		out_info.sparsity_dh_df_nnz = flat->p.n_blkF; out_info.sparsity_dh_df_max_size = (size_t)flat->p.n_obs * flat->p.n_unk_lms;
+		out_info.sparsity_HAp_nnz = flat->p.n_HAp; out_info.sparsity_HAp_max_size = (size_t)flat->p.n_unk_edges * flat->p.n_unk_edges;
+		out_info.sparsity_Hf_nnz = flat->p.n_unk_lms; out_info.sparsity_Hf_max_size = (size_t)flat->p.n_unk_lms * flat->p.n_unk_lms;
+		out_info.sparsity_HApf_nnz = flat->p.n_HApf; out_info.sparsity_HApf_max_size = (size_t)flat->p.n_unk_edges * flat->p.n_unk_lms;
+	}
+	// (HAp_condition_number, optimize_edges.h:753-765, needs a dense SVD of H_Ap: not provided -- left at 0)
 	out_info.optimized_k2k_edge_indices.assign(flat->k2k_ids.begin(), flat->k2k_ids.end());
 	out_info.optimized_landmark_indices.assign(flat->lm_ids.begin(), flat->lm_ids.end());
 	m_profiler.leave("opt");

@@ -19,6 +19,7 @@
 //   A::POSE_NVALS (3: x y phi | 12: R row-major + t), A::OBS_DIMS
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -46,6 +47,7 @@ struct Flat {
 	// caller-owned result buffers sized for this problem
 	std::vector<double> r_edge_pose, r_lm_pos, r_slot_pose, r_Hf_diag;
 	std::vector<uint8_t> r_obs_valid, r_lm_inv;
+	std::vector<double> r_trace;   // 6 per LM trial: lambda, solved_ok, rho, new total squared error, accepted, relinearised
 
 	void bind() {
 #define SRBA_SHIM_BIND(name) p.name = name.empty() ? NULL : &name[0];
@@ -58,8 +60,9 @@ struct Flat {
 		SRBA_SHIM_BIND(S_term_rowblk) SRBA_SHIM_BIND(S_term_colblk)
 #undef SRBA_SHIM_BIND
 	}
-	/** srba_result_t over buffers owned by this object (trace / dense Hessian not requested) */
-	srba_result_t make_result_buffers(int pose_nvals) {
+	/** srba_result_t over buffers owned by this object; trace_cap > 0: the per-trial trace (lambda, rho, errors, decisions) of up to that many
+	  * LM trials comes back too -- what feedback_user_iteration is replayed from (impl/optimize_edges.h:417-418,595-596) */
+	srba_result_t make_result_buffers(int pose_nvals, int trace_cap = 0) {
 		r_edge_pose.assign((size_t)p.n_unk_edges * pose_nvals, 0.0);
 		r_lm_pos.assign((size_t)p.n_unk_lms * 3, 0.0);
 		r_slot_pose.assign((size_t)2 * p.n_pairs * pose_nvals, 0.0);
@@ -74,6 +77,11 @@ struct Flat {
 		r.Hf_diag = r_Hf_diag.empty() ? NULL : &r_Hf_diag[0];
 		r.obs_valid = r_obs_valid.empty() ? NULL : &r_obs_valid[0];
 		r.lm_invertible = r_lm_inv.empty() ? NULL : &r_lm_inv[0];
+		if (trace_cap > 0) {
+			r_trace.assign((size_t)trace_cap * 6, 0.0);
+			r.trace = &r_trace[0];
+			r.trace_cap = trace_cap;
+		}
 		return r;
 	}
 };
@@ -331,6 +339,21 @@ void scatter(ST &st, const Flat &F, const srba_result_t &r) {
 		A::set_num(st, F.pairs[t].second, F.pairs[t].first, r.slot_pose + (2 * t + 1) * S);
 	}
 	for (size_t l = 0; l < F.obs_global.size(); l++) A::set_validity(st, F.obs_global[l], (char)r.obs_valid[l]);
+}
+
+/** parameters.srba.feedback_user_iteration(iter, total_sq_err, mean_sqroot_error) replayed from the trace of a finished call: once with the
+  * initial error (optimize_edges.h:417-418), then once per ACCEPTED step with the outer iteration counter it had (:595-596). */
+template <class CALLBACK>
+void replay_feedback(CALLBACK cb, const Flat &F, const srba_result_t &r) {
+	if (!cb) return;
+	const double n = (double)F.p.n_total_obs_rows;
+	cb(0u, r.stats.total_sqr_error_init, std::sqrt(r.stats.total_sqr_error_init / n));
+	unsigned iter = 0;
+	for (int t = 0; t < r.trace_len; t++)
+		if (r.trace[6 * t + 1] != 0 && r.trace[6 * t + 4] != 0) {
+			cb(iter, r.trace[6 * t + 3], std::sqrt(r.trace[6 * t + 3] / n));
+			iter++;
+		}
 }
 
 }  // namespace srba_b200_shim

@@ -142,7 +142,9 @@ public:
 	struct TOptimizeExtraOutputInfo {  // RbaEngine.h:125-177
 		size_t num_observations, num_jacobians, num_kf2kf_edges_optimized, num_kf2lm_edges_optimized, num_total_scalar_optimized, num_kf_optimized, num_lm_optimized,
 		    num_span_tree_numeric_updates;
-		double obs_rmse, total_sqr_error_init, total_sqr_error_final;
+		double obs_rmse, total_sqr_error_init, total_sqr_error_final, HAp_condition_number;
+		size_t sparsity_dh_dAp_nnz, sparsity_dh_dAp_max_size, sparsity_dh_df_nnz, sparsity_dh_df_max_size, sparsity_HAp_nnz, sparsity_HAp_max_size, sparsity_Hf_nnz,
+		    sparsity_Hf_max_size, sparsity_HApf_nnz, sparsity_HApf_max_size;
 		std::vector<size_t> optimized_k2k_edge_indices, optimized_landmark_indices;
 		void clear();
 	};
@@ -150,6 +152,8 @@ public:
 		size_t max_iters;
 		bool use_robust_kernel;
 		double kernel_param, max_error_per_obs_to_stop, max_rho, max_lambda, min_error_reduction_ratio_to_relinearize;
+		void (*feedback_user_iteration)(unsigned int iter, const double total_sq_err, const double mean_sqroot_error);
+		bool compute_condition_number, compute_sparsity_stats;
 		TCovarianceRecoveryPolicy cov_recovery;
 	};
 	struct TAllParameters {  // RbaEngine.h:463-472

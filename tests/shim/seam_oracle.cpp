@@ -49,6 +49,10 @@ struct OracleAccess {
 	static void set_validity(ST &st, size_t g, char v) { st.all_observations_Jacob_validity[g] = v; }
 };
 
+struct FeedbackCall { unsigned iter; double err, rmse; };
+static std::vector<FeedbackCall> g_feedback;
+static void record_feedback(unsigned int iter, const double total_sq_err, const double mean_sqroot_error) { g_feedback.push_back({iter, total_sq_err, mean_sqroot_error}); }
+
 #define CHECK(c) do { if (!(c)) { std::printf("FAILED: %s (line %d)\n", #c, __LINE__); return 1; } } while (0)
 template <class T>
 static bool same(const T *a, const T *b, size_t n) { return n == 0 || std::memcmp(a, b, n * sizeof(T)) == 0; }
@@ -131,7 +135,7 @@ static int run(const orc_params_t &prm, std::istream &f, bool run_gpu) {
 	std::printf("FLATTEN identical: n_p %d n_f %d n_obs %d blkA %d blkF %d pairs %d HAp %d HApf %d S %d S_terms %d\n", p.n_unk_edges, p.n_unk_lms, p.n_obs, p.n_blkA, p.n_blkF,
 	            p.n_pairs, p.n_HAp, p.n_HApf, p.n_S, p.n_S_terms);
 	if (run_gpu) {
-		srba_result_t res = F->make_result_buffers(S);
+		srba_result_t res = F->make_result_buffers(S, 256);   // with the per-trial trace: feedback_user_iteration is replayed from it
 		const int rc = srba_b200_optimize(&F->p, &res);
 		if (rc != SRBA_OK) { std::printf("FAILED: srba_b200_optimize: %s\n", srba_b200_last_error()); return 1; }
 		// snapshot of the unknowns before scattering, then the oracle's own CPU solution from the same state
@@ -153,6 +157,18 @@ static int run(const orc_params_t &prm, std::istream &f, bool run_gpu) {
 		std::printf("GPU through the seam shim vs the oracle's CPU optimize_local_area: trials %d vs %llu, edges %.3e, landmarks %.3e (relative)\n", res.stats.num_trials,
 		            (unsigned long long)info.num_lm_trials, worst / scale, worst_lm / scale_lm);
 		CHECK(worst <= 1e-6 * scale && worst_lm <= 1e-6 * scale_lm);
+		// feedback_user_iteration replay (optimize_edges.h:417-418,595-596): (0, initial error), then one call per accepted step
+		g_feedback.clear();
+		srba_b200_shim::replay_feedback(&record_feedback, *F, res);
+		CHECK(!g_feedback.empty() && g_feedback[0].iter == 0 && g_feedback[0].err == res.stats.total_sqr_error_init);
+		CHECK(std::fabs(g_feedback[0].err - info.total_sqr_error_init) <= 1e-9 * info.total_sqr_error_init);
+		CHECK(g_feedback.size() >= 2 && g_feedback.size() <= 1 + (size_t)res.stats.num_iters && (uint64_t)res.stats.num_iters == info.num_iters);  // final `iter` also counts the closing pass
+		for (size_t i = 1; i < g_feedback.size(); i++) {
+			CHECK(g_feedback[i].iter == i - 1 && g_feedback[i].err < g_feedback[i - 1].err);
+			CHECK(std::fabs(g_feedback[i].rmse - std::sqrt(g_feedback[i].err / p.n_total_obs_rows)) <= 1e-15 + 1e-12 * g_feedback[i].rmse);
+		}
+		CHECK(g_feedback.back().err == res.stats.total_sqr_error_final);
+		std::printf("FEEDBACK ok: %d calls\n", (int)g_feedback.size());
 		// scatter: the GPU result written back into the pointer graph (edges, landmarks, numeric spanning tree, validity)
 		srba_b200_shim::scatter<A>(eo, *F, res);
 		eo.k2k_edges[F->k2k_ids[0]].inv_pose.toFlat(v.data());

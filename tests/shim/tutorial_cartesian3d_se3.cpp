@@ -29,6 +29,15 @@ static vector<basic_euclidean_dataset_entry_t> read_block(istream &f) {
 	return v;
 }
 
+static int g_fb_calls = 0;
+static unsigned g_fb_first_iter = 99;
+static double g_fb_first_err = -1, g_fb_last_err = -1;
+static void on_iteration(unsigned int iter, const double total_sq_err, const double mean_sqroot_error) {
+	if (!g_fb_calls++) { g_fb_first_iter = iter; g_fb_first_err = total_sq_err; }
+	g_fb_last_err = total_sq_err;
+	(void)mean_sqroot_error;
+}
+
 int main(int argc, char **argv) {
 	ifstream f(argv[1]);
 	const vector<basic_euclidean_dataset_entry_t> observations_0 = read_block(f), observations_10 = read_block(f);
@@ -81,7 +90,11 @@ int main(int argc, char **argv) {
 	printf("\n");
 	// optimize_local_area + observation_indices_to_optimize through the facade (RbaEngine.h:235-241)
 	my_srba_t::TOptimizeExtraOutputInfo info;
+	rba.parameters.srba.feedback_user_iteration = &on_iteration;   // RbaEngine.h:307 (replayed after the call)
 	rba.optimize_local_area(1, 3, info);
+	rba.parameters.srba.feedback_user_iteration = NULL;
+	printf("FEEDBACK calls %d first_iter %u first_err %.17g last_err %.17g init %.17g final %.17g\n", g_fb_calls, g_fb_first_iter, g_fb_first_err, g_fb_last_err,
+	       info.total_sqr_error_init, info.total_sqr_error_final);
 	vector<size_t> all_obs;
 	for (size_t i = 0; i < rba.get_rba_state().num_observations; i++) all_obs.push_back(i);
 	my_srba_t::TOptimizeExtraOutputInfo info2;

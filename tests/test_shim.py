@@ -79,6 +79,9 @@ def test_tutorial_cartesian3d_through_the_facade(tmp_path):
     assert np.abs(T[:3, 3] - P_GT[:3, 3]).max() < 2e-3 and np.abs(T[:3, :3] - P_GT[:3, :3]).max() < 2e-3
     # optimize_local_area (+ observation_indices_to_optimize with every observation listed) ran through the facade
     assert int(la[2]) > 0 and int(la[4]) == 1 and int(la[6]) > 0 and int(la[la.index("listed") + 2]) == e.num_observations
+    fb = [l for l in out.splitlines() if l.startswith("FEEDBACK")][0].split()
+    fbv = dict(zip(fb[1::2], fb[2::2]))
+    assert int(fbv["calls"]) >= 1 and int(fbv["first_iter"]) == 0 and float(fbv["first_err"]) == float(fbv["init"]) and float(fbv["last_err"]) == float(fbv["final"])
     print("facade, cartesian3d tutorial: relative pose vs oracle %.2e, rmse %.3g" % (np.abs(T - P).max(), float(vals["rmse"])))
 
 
