@@ -75,6 +75,9 @@ int srba_engine_select_local_area(void *h, uint64_t root, uint64_t win_size, uin
  * into the engine exactly as optimize_edges would have (edges, landmarks, numeric spanning tree, validity, info matrices). */
 void *srba_engine_flatten(void *h, uint64_t n_k2k, const uint64_t *k2k, uint64_t n_lm, const uint64_t *lms);
 void *srba_engine_flatten_local_area(void *h, uint64_t root, uint64_t win_size);
+/* The local areas of n keyframes of the CURRENT map state as independent problems (snapshot semantics): flattened by up to n_threads host
+ * threads (<= 0: one per hardware thread); out[i] = flat handle, or NULL when area i has no unknowns.  0, or -1 with every handle released. */
+int srba_engine_flatten_local_areas(void *h, uint64_t n, const uint64_t *roots, uint64_t win_size, int n_threads, void **out);
 void *srba_engine_flatten_local_area_obs(void *h, uint64_t root, uint64_t win_size, uint64_t n_obs_idx, const uint64_t *obs_idx); /* with observation_indices_to_optimize */
 const srba_problem_t *srba_flat_problem(const void *flat);
 int srba_flat_apply(void *h, const void *flat, const srba_result_t *res, srba_opt_info_t *out);

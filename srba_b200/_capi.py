@@ -90,7 +90,7 @@ EXPORTED_SYMBOLS = [
     "srba_b200_release_workspace", "srba_b200_set_option", "srba_b200_get_option",
     "srba_engine_default_params", "srba_engine_create", "srba_engine_destroy", "srba_engine_set_params", "srba_engine_define_new_keyframe",
     "srba_engine_optimize_local_area", "srba_engine_optimize_local_area_obs", "srba_engine_optimize_edges", "srba_engine_select_local_area", "srba_engine_flatten",
-    "srba_engine_flatten_local_area", "srba_engine_flatten_local_area_obs", "srba_flat_problem", "srba_flat_apply", "srba_flat_ids", "srba_flat_touched_edges", "srba_flat_destroy",
+    "srba_engine_flatten_local_area", "srba_engine_flatten_local_area_obs", "srba_engine_flatten_local_areas", "srba_flat_problem", "srba_flat_apply", "srba_flat_ids", "srba_flat_touched_edges", "srba_flat_destroy",
     "srba_engine_record_problems", "srba_engine_num_recorded", "srba_engine_take_recorded", "srba_engine_trace", "srba_engine_last_trace",
     "srba_engine_num_keyframes", "srba_engine_num_edges", "srba_engine_num_observations", "srba_engine_pose_nvals", "srba_engine_get_edge",
     "srba_engine_set_edge_pose", "srba_engine_num_unknown_lms", "srba_engine_get_unknown_lms", "srba_engine_set_lm_pos",
@@ -177,6 +177,8 @@ def lib():
     L.srba_engine_flatten.argtypes = [vp, u64, pu64, u64, pu64]
     L.srba_engine_flatten_local_area.restype = vp
     L.srba_engine_flatten_local_area.argtypes = [vp, u64, u64]
+    L.srba_engine_flatten_local_areas.restype = C.c_int
+    L.srba_engine_flatten_local_areas.argtypes = [vp, u64, pu64, u64, i32, C.POINTER(vp)]
     L.srba_engine_flatten_local_area_obs.restype = vp
     L.srba_engine_flatten_local_area_obs.argtypes = [vp, u64, u64, u64, pu64]
     L.srba_flat_problem.restype = pp

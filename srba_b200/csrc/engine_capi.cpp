@@ -1,6 +1,10 @@
 // C view of srba_b200::RbaEngine (include/srba_b200_engine.h).
 #include "host_engine.hpp"
 
+#include <atomic>
+#include <mutex>
+#include <thread>
+
 using namespace srba_b200;
 
 namespace {
@@ -205,6 +209,49 @@ void *srba_engine_flatten_local_area_obs(void *h, uint64_t root, uint64_t win_si
 	fh->fp = std::move(fp);
 	return fh;
 	GUARD_END(nullptr)
+}
+// Snapshot semantics (the local areas of many keyframes of ONE map state as independent problems): flatten() and
+// select_local_area() only read the engine, so the areas are flattened by several host threads at once.
+int srba_engine_flatten_local_areas(void *h, uint64_t n, const uint64_t *roots, uint64_t win_size, int n_threads, void **out) {
+	GUARD_BEGIN
+	if (!h || (n && (!roots || !out))) throw std::runtime_error("srba_engine_flatten_local_areas: null argument");
+	for (uint64_t i = 0; i < n; i++) out[i] = nullptr;
+	unsigned nt = n_threads > 0 ? (unsigned)n_threads : std::max(1u, std::thread::hardware_concurrency());
+	nt = (unsigned)std::min<uint64_t>(nt, std::max<uint64_t>(n, 1));
+	std::atomic<uint64_t> next(0);
+	std::mutex err_mutex;
+	std::string err;
+	auto work = [&]() {
+		for (;;) {
+			const uint64_t i = next.fetch_add(1);
+			if (i >= n) return;
+			try {
+				std::unique_ptr<FlatProblem> fp;
+				DISPATCH(h, {
+					typedef typename std::remove_reference<decltype(E)>::type EngT;
+					std::vector<size_t> a, b;
+					E.select_local_area(roots[i], win_size, typename EngT::TOptimizeLocalAreaParams(), a, b);
+					if (!a.empty() || !b.empty()) fp = E.flatten(a, b);
+				});
+				if (fp) { FlatHandle *fh = new FlatHandle(); fh->fp = std::move(fp); out[i] = fh; }
+			} catch (const std::exception &e) {
+				std::lock_guard<std::mutex> lk(err_mutex);
+				if (err.empty()) err = e.what();
+				next.store(n);   // stop handing out work
+				return;
+			}
+		}
+	};
+	std::vector<std::thread> pool;
+	for (unsigned t = 1; t < nt; t++) pool.emplace_back(work);
+	work();
+	for (std::thread &t : pool) t.join();
+	if (!err.empty()) {
+		for (uint64_t i = 0; i < n; i++) { delete static_cast<FlatHandle *>(out[i]); out[i] = nullptr; }
+		throw std::runtime_error(err);
+	}
+	return 0;
+	GUARD_END(-1)
 }
 const srba_problem_t *srba_flat_problem(const void *flat) { return flat ? &static_cast<const FlatHandle *>(flat)->fp->p : nullptr; }
 int srba_flat_apply(void *h, const void *flat, const srba_result_t *res, srba_opt_info_t *out) {

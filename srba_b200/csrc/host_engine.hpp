@@ -45,6 +45,38 @@ static const uint64_t INVALID_ID = static_cast<uint64_t>(-1);
 
 inline int obs_dims_of(int k) { return k == SRBA_OBS_MONO ? 2 : (k == SRBA_OBS_STEREO ? 4 : 3); }
 
+// (block key, term) record of the symbolic Hessian / Schur construction, and its stable sort by (hi, lo): two counting-sort passes
+struct TermRec { int32_t hi, lo, a, b; };
+inline void sort_terms(std::vector<TermRec> &v, int n_hi, int n_lo) {
+	if (v.size() < 2) return;
+	std::vector<TermRec> tmp(v.size());
+	std::vector<uint32_t> cnt((size_t)std::max(n_hi, n_lo) + 1);
+	std::fill(cnt.begin(), cnt.begin() + n_lo + 1, 0u);
+	for (const TermRec &r : v) cnt[r.lo + 1]++;
+	for (int i = 0; i < n_lo; i++) cnt[i + 1] += cnt[i];
+	for (const TermRec &r : v) tmp[cnt[r.lo]++] = r;
+	std::fill(cnt.begin(), cnt.begin() + n_hi + 1, 0u);
+	for (const TermRec &r : tmp) cnt[r.hi + 1]++;
+	for (int i = 0; i < n_hi; i++) cnt[i + 1] += cnt[i];
+	for (const TermRec &r : tmp) v[cnt[r.hi]++] = r;
+}
+
+// Per-thread id -> local-index tables of flatten(): entry i is valid when its stamp equals the stamp of the current call.
+struct FlattenScratch {
+	uint32_t stamp = 0;
+	std::vector<uint32_t> obs_stamp, lm_stamp, edge_stamp, kf_stamp;
+	std::vector<int32_t> obs_local, lm_local, edge_local, kf_first;
+	static FlattenScratch &get() { static thread_local FlattenScratch s; return s; }
+	void begin(size_t n_obs, size_t n_lm, size_t n_edge, size_t n_kf) {
+		if (++stamp == 0) {   // wrapped: forget everything
+			for (std::vector<uint32_t> *v : {&obs_stamp, &lm_stamp, &edge_stamp, &kf_stamp}) std::fill(v->begin(), v->end(), 0u);
+			stamp = 1;
+		}
+		auto grow = [](std::vector<uint32_t> &st, std::vector<int32_t> &loc, size_t n) { if (st.size() < n) { st.resize(n + n / 2, 0u); loc.resize(n + n / 2, -1); } };
+		grow(obs_stamp, obs_local, n_obs); grow(lm_stamp, lm_local, n_lm); grow(edge_stamp, edge_local, n_edge); grow(kf_stamp, kf_first, n_kf);
+	}
+};
+
 // A flattened optimize_edges() problem + the ids needed to scatter the result back.
 struct FlatProblem {
 	srba_problem_t p;
@@ -741,17 +773,18 @@ class RbaEngine : public EngineBase {
 		F.info.num_kf_optimized = touched_KFs.size();
 		F.info.num_lm_optimized = touched_LMs.size();
 		if (P * n_p + 3 * n_f == 0) return nullptr;
-		std::unordered_map<uint64_t, int> ucol_of_edge, fcol_of_lm;
-		for (int i = 0; i < n_p; i++) ucol_of_edge[F.k2k_ids[i]] = i;
-		for (int i = 0; i < n_f; i++) fcol_of_lm[F.lm_ids[i]] = i;
+		// id -> local index tables: stamped arrays kept per thread (no hashing, no per-call clearing; flatten() only READS the engine, so
+		// several threads may flatten different areas of one engine at the same time -- srba_engine_flatten_local_areas)
+		FlattenScratch &sc = FlattenScratch::get();
+		sc.begin(all_observations.size(), all_lms.size(), k2k_edges.size(), keyframes.size());
+		const uint32_t stamp = sc.stamp;
 
 		// C. involved observations (:171-217): first-touch order, duplicates counted in obs_mult
-		std::unordered_map<uint64_t, int> local_obs;
+		auto obs_known = [&](uint64_t g) -> bool { return sc.obs_stamp[g] == stamp; };
 		auto obs_local = [&](uint64_t g) -> int {
-			auto it = local_obs.find(g);
-			if (it != local_obs.end()) return it->second;
+			if (sc.obs_stamp[g] == stamp) return sc.obs_local[g];
 			const int l = F.obs_global.size();
-			local_obs[g] = l;
+			sc.obs_stamp[g] = stamp; sc.obs_local[g] = l;
 			F.obs_global.push_back(g);
 			F.obs_mult.push_back(0);
 			return l;
@@ -767,7 +800,7 @@ class RbaEngine : public EngineBase {
 		F.colA_ptr.push_back(0);
 		for (int i = 0; i < n_p; i++) {
 			for (uint32_t g : colA[F.k2k_ids[i]]) {
-				if (user_list && !local_obs.count(g)) throw std::runtime_error("ASSERT_(it_obs!=obs_global_idx2residual_idx.end()): an observation of an unknown column is missing from observation_indices_to_optimize (compute_minus_gradient.h:55)");
+				if (user_list && !obs_known(g)) throw std::runtime_error("ASSERT_(it_obs!=obs_global_idx2residual_idx.end()): an observation of an unknown column is missing from observation_indices_to_optimize (compute_minus_gradient.h:55)");
 				const int l = obs_local(g);
 				if (!user_list) F.obs_mult[l]++;
 				F.blkA_obs.push_back(l);
@@ -777,7 +810,7 @@ class RbaEngine : public EngineBase {
 		F.colF_ptr.push_back(0);
 		for (int i = 0; i < n_f; i++) {
 			for (uint32_t g : colF[all_lms[F.lm_ids[i]].fcol]) {
-				const bool fresh = !local_obs.count(g);
+				const bool fresh = !obs_known(g);
 				if (user_list && fresh) throw std::runtime_error("ASSERT_(it_obs!=obs_global_idx2residual_idx.end()): an observation of an unknown column is missing from observation_indices_to_optimize (compute_minus_gradient.h:79)");
 				const int l = obs_local(g);
 				if (fresh) F.obs_mult[l] = 1;
@@ -790,7 +823,12 @@ class RbaEngine : public EngineBase {
 		for (int m : F.obs_mult) n_rows_dup += m;
 
 		// D. needed spanning-tree roots (jacobians.h:1020-1076) and the pose-pair table of the touched rows
-		std::set<TKeyFrameID> roots;
+		std::vector<TKeyFrameID> roots;   // ascending, unique (the reference's std::set order)
+		auto add_root = [&](TKeyFrameID kf) {
+			if (sc.kf_stamp[kf] == stamp) return;
+			sc.kf_stamp[kf] = stamp; sc.kf_first[kf] = -1;
+			roots.push_back(kf);
+		};
 		std::vector<int> blkA_row(nA);  // index into rows[] of each dh_dAp block
 		for (int i = 0; i < n_p; i++)
 			for (int b = F.colA_ptr[i]; b < F.colA_ptr[i + 1]; b++) {
@@ -799,19 +837,17 @@ class RbaEngine : public EngineBase {
 				for (uint32_t k = 0; k < ob.row_len; k++) if (rows[ob.row_begin + k].edge == F.k2k_ids[i]) { r = ob.row_begin + k; break; }
 				SRBA_CHECK(r >= 0);
 				blkA_row[b] = r;
-				roots.insert(rows[r].kf_d); roots.insert(ob.kf); roots.insert(all_lms[ob.lm].base);
+				add_root(rows[r].kf_d); add_root(ob.kf); add_root(all_lms[ob.lm].base);
 			}
 		for (int b = 0; b < nF; b++) {
 			const Observation &ob = all_observations[F.obs_global[F.blkF_obs[b]]];
-			roots.insert(all_lms[ob.lm].base); roots.insert(ob.kf);
+			add_root(all_lms[ob.lm].base); add_root(ob.kf);
 		}
-		std::map<std::pair<uint64_t, uint64_t>, int> pair_idx;
-		std::unordered_map<uint64_t, int> local_edge;
+		std::sort(roots.begin(), roots.end());
 		auto edge_local = [&](uint64_t e) -> int {
-			auto it = local_edge.find(e);
-			if (it != local_edge.end()) return it->second;
+			if (sc.edge_stamp[e] == stamp) return sc.edge_local[e];
 			const int l = F.edge_ids_touched.size();
-			local_edge[e] = l;
+			sc.edge_stamp[e] = stamp; sc.edge_local[e] = l;
 			F.edge_ids_touched.push_back(e);
 			return l;
 		};
@@ -821,8 +857,8 @@ class RbaEngine : public EngineBase {
 		for (TKeyFrameID from : roots) {
 			if (from >= all_edges.size()) continue;
 			span_updates += all_edges[from].size();
+			sc.kf_first[from] = (int32_t)F.pairs.size();   // the pairs of one root are contiguous and ascending in `to`
 			for (const auto &kv : all_edges[from]) {
-				pair_idx[std::make_pair(from, kv.first)] = F.pairs.size();
 				F.pairs.push_back(std::make_pair(from, kv.first));
 				TKeyFrameID cur = from;
 				for (uint32_t e : kv.second) {
@@ -835,19 +871,23 @@ class RbaEngine : public EngineBase {
 			}
 		}
 		auto slot_of = [&](TKeyFrameID src, TKeyFrameID dst) -> int {  // slot of num[src][dst]
-			auto it = pair_idx.find(std::make_pair(std::max(src, dst), std::min(src, dst)));
+			const TKeyFrameID from = std::max(src, dst), to = std::min(src, dst);
+			int idx = -1;
+			if (sc.kf_stamp[from] == stamp && sc.kf_first[from] >= 0) {
+				const auto first = F.pairs.begin() + sc.kf_first[from], last = first + all_edges[from].size();
+				const auto it = std::lower_bound(first, last, std::make_pair(from, to));
+				if (it != last && it->second == to) idx = (int)(it - F.pairs.begin());
+			}
 			// (reachable only through observation_indices_to_optimize: an EXTRA observation whose base pose the reference would read
 			// from a stale, un-refreshed numeric spanning-tree entry -- not carried across the boundary)
-			if (it == pair_idx.end()) throw std::runtime_error("srba_b200: a listed observation needs a numeric spanning-tree entry outside the rows refreshed for the unknowns (unsupported)");
-			return 2 * it->second + (src > dst ? 0 : 1);
+			if (idx < 0) throw std::runtime_error("srba_b200: a listed observation needs a numeric spanning-tree entry outside the rows refreshed for the unknowns (unsupported)");
+			return 2 * idx + (src > dst ? 0 : 1);
 		};
 		// landmarks touched
-		std::unordered_map<uint64_t, int> local_lm;
 		auto lm_local = [&](uint64_t id) -> int {
-			auto it = local_lm.find(id);
-			if (it != local_lm.end()) return it->second;
+			if (sc.lm_stamp[id] == stamp) return sc.lm_local[id];
 			const int l = F.lm_ids_touched.size();
-			local_lm[id] = l;
+			sc.lm_stamp[id] = stamp; sc.lm_local[id] = l;
 			F.lm_ids_touched.push_back(id);
 			return l;
 		};
@@ -876,71 +916,93 @@ class RbaEngine : public EngineBase {
 			const Observation &ob = all_observations[F.obs_global[F.blkF_obs[b]]];
 			F.blkF_slot[b] = ob.first_obs_of_unknown ? -1 : slot_of(ob.kf, all_lms[ob.lm].base);
 		}
-		// rows in walk order (dAp columns in unknown order, then the df block)
-		std::vector<std::vector<int> > row_lists(n_obs);
-		for (int b = 0; b < nA; b++) row_lists[F.blkA_obs[b]].push_back(b);
-		for (int b = 0; b < nF; b++) row_lists[F.blkF_obs[b]].push_back(nA + b);
-		F.row_ptr.push_back(0);
-		for (int l = 0; l < n_obs; l++) { for (int b : row_lists[l]) F.row_blk.push_back(b); F.row_ptr.push_back(F.row_blk.size()); }
+		// rows in walk order (dAp columns in unknown order, then the df block): a stable counting sort of the blocks by observation
+		F.row_ptr.assign(n_obs + 1, 0);
+		for (int b = 0; b < nA; b++) F.row_ptr[F.blkA_obs[b] + 1]++;
+		for (int b = 0; b < nF; b++) F.row_ptr[F.blkF_obs[b] + 1]++;
+		for (int l = 0; l < n_obs; l++) F.row_ptr[l + 1] += F.row_ptr[l];
+		F.row_blk.resize(nA + nF);
+		{
+			std::vector<int32_t> fill(F.row_ptr.begin(), F.row_ptr.end() - 1);
+			for (int b = 0; b < nA; b++) F.row_blk[fill[F.blkA_obs[b]]++] = b;
+			for (int b = 0; b < nF; b++) F.row_blk[fill[F.blkF_obs[b]]++] = nA + b;
+		}
 
-		// I. Hessian symbolic (sparse_hessian_build_symbolic.h): terms of every block in ascending GLOBAL observation index
+		// I. Hessian symbolic (sparse_hessian_build_symbolic.h): terms of every block in ascending GLOBAL observation index.  The terms
+		// are generated in that order as (block key, term) records and grouped by a stable two-pass counting sort on the key -- the
+		// blocks come out in the order of the reference's std::map keys, the terms of a block in generation order.
 		std::vector<int> obs_sorted(n_obs);
 		for (int l = 0; l < n_obs; l++) obs_sorted[l] = l;
 		std::sort(obs_sorted.begin(), obs_sorted.end(), [&](int a, int b) { return F.obs_global[a] < F.obs_global[b]; });
 		std::vector<int> blkA_ucol(nA), blkF_fcol(nF);
 		for (int i = 0; i < n_p; i++) for (int b = F.colA_ptr[i]; b < F.colA_ptr[i + 1]; b++) blkA_ucol[b] = i;
 		for (int i = 0; i < n_f; i++) for (int b = F.colF_ptr[i]; b < F.colF_ptr[i + 1]; b++) blkF_fcol[b] = i;
-		std::map<std::pair<int, int>, std::vector<std::pair<int, int> > > HAp_terms;   // key (col,row) -> (blk_row, blk_col)
-		std::map<std::pair<int, int>, std::vector<std::pair<int, int> > > HApf_terms;  // key (row,fcol) -> (blkA, blkF)
+		std::vector<TermRec> tA, tApf, tS;   // HAp: key (col,row) -> (blk_row, blk_col); HApf: key (row,fcol) -> (blkA, blkF)
+		tA.reserve((size_t)nA * 2); tApf.reserve(nA);
 		for (int l : obs_sorted) {
-			const std::vector<int> &rl = row_lists[l];
-			for (size_t x = 0; x < rl.size(); x++) {
-				if (rl[x] >= nA) continue;
-				for (size_t y = 0; y < rl.size(); y++) {
-					if (rl[y] >= nA) { HApf_terms[std::make_pair(blkA_ucol[rl[x]], blkF_fcol[rl[y] - nA])].push_back(std::make_pair(rl[x], rl[y] - nA)); continue; }
-					const int ci = blkA_ucol[rl[x]], cj = blkA_ucol[rl[y]];
-					if (ci <= cj && (ci < cj || x == y)) HAp_terms[std::make_pair(cj, ci)].push_back(std::make_pair(rl[x], rl[y]));
+			const int r0 = F.row_ptr[l], r1 = F.row_ptr[l + 1];
+			for (int x = r0; x < r1; x++) {
+				const int bx = F.row_blk[x];
+				if (bx >= nA) continue;
+				const int ci = blkA_ucol[bx];
+				for (int y = r0; y < r1; y++) {
+					const int by = F.row_blk[y];
+					if (by >= nA) { tApf.push_back(TermRec{ci, blkF_fcol[by - nA], bx, by - nA}); continue; }
+					const int cj = blkA_ucol[by];
+					if (ci <= cj && (ci < cj || x == y)) tA.push_back(TermRec{cj, ci, bx, by});
 				}
 			}
 		}
-		std::map<std::pair<int, int>, int> HAp_index;  // (row,col) -> block id
+		sort_terms(tA, n_p, n_p);
 		F.HAp_term_ptr.push_back(0);
-		for (const auto &kv : HAp_terms) {
-			HAp_index[std::make_pair(kv.first.second, kv.first.first)] = F.HAp_row.size();
-			F.HAp_row.push_back(kv.first.second); F.HAp_col.push_back(kv.first.first);
-			for (const auto &t : kv.second) { F.HAp_term_a.push_back(t.first); F.HAp_term_b.push_back(t.second); }
-			F.HAp_term_ptr.push_back(F.HAp_term_a.size());
+		for (size_t t = 0; t < tA.size(); t++) {
+			if (t == 0 || tA[t].hi != tA[t - 1].hi || tA[t].lo != tA[t - 1].lo) {
+				if (t) F.HAp_term_ptr.push_back(F.HAp_term_a.size());
+				tS.push_back(TermRec{tA[t].hi, tA[t].lo, -1, (int32_t)F.HAp_row.size()});   // every H_Ap block is a block of the reduced system
+				F.HAp_row.push_back(tA[t].lo); F.HAp_col.push_back(tA[t].hi);
+			}
+			F.HAp_term_a.push_back(tA[t].a); F.HAp_term_b.push_back(tA[t].b);
 		}
+		if (!tA.empty()) F.HAp_term_ptr.push_back(F.HAp_term_a.size());
+		sort_terms(tApf, n_p, n_f);
 		F.HApf_term_ptr.push_back(0);
 		F.rowApf_ptr.assign(n_p + 1, 0);
-		std::vector<std::vector<int> > lm_cols(n_f);
-		for (const auto &kv : HApf_terms) {
-			const int id = F.HApf_row.size();
-			F.HApf_row.push_back(kv.first.first); F.HApf_col.push_back(kv.first.second);
-			F.rowApf_ptr[kv.first.first + 1]++;
-			lm_cols[kv.first.second].push_back(id);
-			for (const auto &t : kv.second) { F.HApf_term_a.push_back(t.first); F.HApf_term_f.push_back(t.second); }
-			F.HApf_term_ptr.push_back(F.HApf_term_a.size());
+		F.colApf_ptr.assign(n_f + 1, 0);
+		for (size_t t = 0; t < tApf.size(); t++) {
+			if (t == 0 || tApf[t].hi != tApf[t - 1].hi || tApf[t].lo != tApf[t - 1].lo) {
+				if (t) F.HApf_term_ptr.push_back(F.HApf_term_a.size());
+				F.HApf_row.push_back(tApf[t].hi); F.HApf_col.push_back(tApf[t].lo);
+				F.rowApf_ptr[tApf[t].hi + 1]++;
+				F.colApf_ptr[tApf[t].lo + 1]++;
+			}
+			F.HApf_term_a.push_back(tApf[t].a); F.HApf_term_f.push_back(tApf[t].b);
 		}
+		if (!tApf.empty()) F.HApf_term_ptr.push_back(F.HApf_term_a.size());
 		for (int i = 0; i < n_p; i++) F.rowApf_ptr[i + 1] += F.rowApf_ptr[i];
-		F.colApf_ptr.push_back(0);
-		for (int k = 0; k < n_f; k++) { for (int id : lm_cols[k]) F.colApf_idx.push_back(id); F.colApf_ptr.push_back(F.colApf_idx.size()); }
+		for (int k = 0; k < n_f; k++) F.colApf_ptr[k + 1] += F.colApf_ptr[k];
+		F.colApf_idx.resize(F.HApf_row.size());   // blocks of each landmark column, ascending edge row
+		{
+			std::vector<int32_t> fill(F.colApf_ptr.begin(), F.colApf_ptr.end() - 1);
+			for (size_t id = 0; id < F.HApf_col.size(); id++) F.colApf_idx[fill[F.HApf_col[id]]++] = (int32_t)id;
+		}
 		// O. Schur symbolic (schur.h:56-157): block (row j <= col i) gets one triplet per shared landmark, ascending k
-		std::map<std::pair<int, int>, std::vector<std::pair<int, int> > > S_terms;  // key (col,row) -> (HApf(row,k), HApf(col,k))
-		for (const auto &kv : HAp_terms) S_terms[kv.first];
 		for (int k = 0; k < n_f; k++) {
-			const std::vector<int> &E = lm_cols[k];  // ascending edge row
-			for (size_t x = 0; x < E.size(); x++)
-				for (size_t y = x; y < E.size(); y++) S_terms[std::make_pair(F.HApf_row[E[y]], F.HApf_row[E[x]])].push_back(std::make_pair(E[x], E[y]));
+			const int32_t *E = F.colApf_idx.data() + F.colApf_ptr[k];
+			const int nE = F.colApf_ptr[k + 1] - F.colApf_ptr[k];
+			for (int x = 0; x < nE; x++)
+				for (int y = x; y < nE; y++) tS.push_back(TermRec{F.HApf_row[E[y]], F.HApf_row[E[x]], E[x], E[y]});   // key (col,row) -> (HApf(row,k), HApf(col,k))
 		}
+		sort_terms(tS, n_p, n_p);
 		F.S_term_ptr.push_back(0);
-		for (const auto &kv : S_terms) {
-			F.S_row.push_back(kv.first.second); F.S_col.push_back(kv.first.first);
-			auto it = HAp_index.find(std::make_pair(kv.first.second, kv.first.first));
-			F.S_HAp.push_back(it == HAp_index.end() ? -1 : it->second);
-			for (const auto &t : kv.second) { F.S_term_rowblk.push_back(t.first); F.S_term_colblk.push_back(t.second); }
-			F.S_term_ptr.push_back(F.S_term_rowblk.size());
+		for (size_t t = 0; t < tS.size(); t++) {
+			if (t == 0 || tS[t].hi != tS[t - 1].hi || tS[t].lo != tS[t - 1].lo) {
+				if (t) F.S_term_ptr.push_back(F.S_term_rowblk.size());
+				F.S_row.push_back(tS[t].lo); F.S_col.push_back(tS[t].hi); F.S_HAp.push_back(-1);
+			}
+			if (tS[t].a < 0) F.S_HAp.back() = tS[t].b;
+			else { F.S_term_rowblk.push_back(tS[t].a); F.S_term_colblk.push_back(tS[t].b); }
 		}
+		if (!tS.empty()) F.S_term_ptr.push_back(F.S_term_rowblk.size());
 		// values
 		F.edge_pose.resize(F.edge_ids_touched.size() * S);
 		for (size_t i = 0; i < F.edge_ids_touched.size(); i++) std::memcpy(&F.edge_pose[i * S], k2k_edges[F.edge_ids_touched[i]].inv_pose.v, S * sizeof(double));

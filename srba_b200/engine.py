@@ -193,6 +193,15 @@ class RbaEngine:
         h = self.L.srba_engine_flatten_local_area(self.h, root, win_size)
         return FlatProblem(h) if h else None
 
+    def flatten_local_areas(self, roots, win_size, n_threads=0):
+        """The local areas of many keyframes of the current map state as independent problems (snapshot semantics), flattened
+        by n_threads host threads (0 = all); a list with None where an area has no unknowns."""
+        r = np.ascontiguousarray(roots, dtype=np.uint64)
+        out = (C.c_void_p * max(1, len(r)))()
+        if self.L.srba_engine_flatten_local_areas(self.h, len(r), ptr(r, C.c_uint64), win_size, int(n_threads), out) != 0:
+            raise self._err()
+        return [FlatProblem(out[i]) if out[i] else None for i in range(len(r))]
+
     def apply(self, flat, res):
         o = K.OptInfo()
         rc = self.L.srba_flat_apply(self.h, flat.h, C.byref(res.r), C.byref(o))

@@ -300,3 +300,55 @@ def test_observation_indices_to_optimize_flattening_and_oracle_semantics():
         ep.flatten_local_area(root, 3, observation_indices_to_optimize=obs[1:])
     with pytest.raises(po.OracleError):
         eo.optimize_local_area(root, 3, observation_indices_to_optimize=obs[1:])
+
+
+def flat_arrays(flat, S, O):
+    """Every array of a flattened problem (include/srba_b200.h: srba_problem_t) as numpy copies."""
+    p = flat.p
+    counts = dict(edge_pose=p.n_edges * S, unk_edge=p.n_unk_edges, lm_pos=p.n_lms * 3, unk_lm=p.n_unk_lms, pair_path_ptr=p.n_pairs + 1, path_edge=p.n_path, path_dir=p.n_path,
+                  obs_z=p.n_obs * O, obs_slot=p.n_obs, obs_lm=p.n_obs, obs_mult=p.n_obs, colA_ptr=p.n_unk_edges + 1, blkA_obs=p.n_blkA, blkA_slotA=p.n_blkA, blkA_slotD=p.n_blkA,
+                  blkA_normal_dir=p.n_blkA, colF_ptr=p.n_unk_lms + 1, blkF_obs=p.n_blkF, blkF_slot=p.n_blkF, row_ptr=p.n_obs + 1, row_blk=p.n_blkA + p.n_blkF,
+                  HAp_row=p.n_HAp, HAp_col=p.n_HAp, HAp_term_ptr=p.n_HAp + 1, HAp_term_a=p.n_HAp_terms, HAp_term_b=p.n_HAp_terms, HApf_row=p.n_HApf, HApf_col=p.n_HApf,
+                  HApf_term_ptr=p.n_HApf + 1, HApf_term_a=p.n_HApf_terms, HApf_term_f=p.n_HApf_terms, rowApf_ptr=p.n_unk_edges + 1, colApf_ptr=p.n_unk_lms + 1,
+                  colApf_idx=p.n_HApf, S_row=p.n_S, S_col=p.n_S, S_HAp=p.n_S, S_term_ptr=p.n_S + 1, S_term_rowblk=p.n_S_terms, S_term_colblk=p.n_S_terms)
+    out = {k: np.zeros(0) if n == 0 else flat.array(k, n, np.float64 if k in ("edge_pose", "lm_pos", "obs_z") else (np.uint8 if k in ("path_dir", "blkA_normal_dir") else np.int32)) for k, n in counts.items()}
+    out.update(flat.ids())
+    out["sizes"] = np.array(list(flat.sizes().values()))
+    return out
+
+
+def test_flatten_local_areas_in_parallel_equals_one_by_one():
+    """srba_engine_flatten_local_areas (snapshot semantics): the local areas of many keyframes of one map state, flattened by
+    several host threads that only READ the engine, are the problems flatten_local_area gives one at a time -- every array, bit for bit.
+    A root without unknowns (or unknown to the map) gives None."""
+    ds = D.landmark_slam_se3(n_kfs=120, n_lms=1200, seed=4, obs_kind="cartesian3d")
+    ep = sb.RbaEngine(sb.default_engine_params(pose_kind=1, obs_kind=1, noise_kind=0, noise_std=1e-3, max_tree_depth=4, max_optimize_depth=4, submap_size=10, min_obs_to_loop_closure=4))
+    for f in ds["frames"]:
+        D.feed(ep, f, run_local_optimization=False)
+    roots = list(range(0, 120, 3))
+    one = [ep.flatten_local_area(r, 4) for r in roots]
+    for nt in (1, 3, 0):
+        many = ep.flatten_local_areas(roots, 4, nt)
+        assert len(many) == len(one)
+        for a, b in zip(one, many):
+            assert (a is None) == (b is None)
+            if a is None:
+                continue
+            fa, fb = flat_arrays(a, 12, 3), flat_arrays(b, 12, 3)
+            assert fa.keys() == fb.keys()
+            for k in fa:
+                assert np.array_equal(fa[k], fb[k]), k
+    assert ep.flatten_local_areas([], 4) == []
+    assert ep.flatten_local_area(10 ** 7, 4) is None                     # an unknown keyframe has no area: None, as one by one
+    bad = ep.flatten_local_areas([6, 10 ** 7], 4, 2)
+    assert bad[0] is not None and bad[1] is None
+    # same through the SE(2) engine (the other instantiation) on a loop-closure tour
+    ds2 = D.graphslam_se2_tour(150, seed=2)
+    e2 = sb.RbaEngine(sb.default_engine_params(**dict(S2, noise_lambda=D.se2_noise_lambda(ds2["sigma_xy"], ds2["sigma_yaw"]))))
+    for f in ds2["frames"]:
+        D.feed(e2, f, run_local_optimization=False)
+    roots = list(range(10, 150, 7))
+    for a, b in zip([e2.flatten_local_area(r, 3) for r in roots], e2.flatten_local_areas(roots, 3, 4)):
+        fa, fb = flat_arrays(a, 3, 3), flat_arrays(b, 3, 3)
+        for k in fa:
+            assert np.array_equal(fa[k], fb[k]), k

@@ -82,7 +82,9 @@ def main(args):
     else:
         roots = list(range(9, n_kfs, 10))
         n_units = len(roots)
-        flats = [f for f in (eng.flatten_local_area(roots[i], cfg["depth"]) for i in PL.shard_indices(len(roots), rank, world)) if f is not None]
+        # snapshot semantics: the areas of one map state, flattened by this rank's share of the host cores (srba_engine_flatten_local_areas)
+        mine = [roots[i] for i in PL.shard_indices(len(roots), rank, world)]
+        flats = [f for f in eng.flatten_local_areas(mine, cfg["depth"], max(1, len(os.sched_getaffinity(0)) // int(os.environ.get("LOCAL_WORLD_SIZE", world)))) if f is not None]
     t_flat = time.perf_counter() - t0
     batch = sb.Batch(flats)
     stream = torch.cuda.current_stream()

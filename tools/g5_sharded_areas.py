@@ -44,7 +44,7 @@ if a.max_areas:
     roots = roots[:a.max_areas]
 mine = [roots[i] for i in PL.shard_indices(len(roots), rank, world)]
 t0 = time.perf_counter()
-flats = [eng.flatten_local_area(r, a.depth) for r in mine]
+flats = eng.flatten_local_areas(mine, a.depth, max(1, len(os.sched_getaffinity(0)) // int(os.environ.get("LOCAL_WORLD_SIZE", world))))   # host threads, engine read-only
 flats = [f for f in flats if f is not None]
 t_flat = time.perf_counter() - t0
 sz = np.array([[f.p.n_unk_edges, f.p.n_unk_lms, f.p.n_obs, f.p.n_blkA, f.p.n_S, f.p.n_S_terms] for f in flats])
