@@ -35,6 +35,7 @@ struct SrbaWaveDims {
 	int n_areas;
 	int max_pairs, max_blocks, max_hess_items, max_obs, max_scalars, max_unk, max_schur2, max_schur3, max_lms, max_edges_S, max_out;
 	int has_lms, n_big, n_solo, max_tail_rows;
+	int max_bwd_smem;
 };
 extern "C" size_t srba_wave_scratch_bytes(int n_areas);
 extern "C" int srba_launch_lm_wave(int model, const char *img, const uint64_t *img_off, char *ws, const uint64_t *ws_off, char *res, const uint64_t *res_off,
@@ -1333,6 +1334,7 @@ static srba_batch_t *batch_create_impl(int32_t n, const srba_problem_t *const *i
 				const TileSymbolic &sy = b->sym[b->order[q]];
 				if (sy.tail_level > 0) { if (sy.n_dst >= SRBA_WAVE_TEAM_DST_PER_LEVEL * sy.tail_level) d.n_big++; else d.n_solo++; }
 				mx(d.max_tail_rows, (int64_t)sy.ntr - sy.phase[2 * (size_t)sy.tail_level]);
+				if (sy.tail_level > 0) mx(d.max_bwd_smem, (int64_t)h.n_dense * 8 + (int64_t)sy.phase[2 * (size_t)sy.tail_level] * 8 + ((int64_t)sy.tail_level + 1) * 4 + 16);
 			}
 			b->wave_scratch_off[m] = ws;
 			ws += (srba_wave_scratch_bytes(d.n_areas) + 255) / 256 * 256;

@@ -296,8 +296,18 @@ __global__ void __launch_bounds__(128) wave_schur_kernel(const WaveArgs a, int p
 //   bwd    (as fwd)  x_k = y_k - sum_j W(k,j) x_j down the levels below the tail, one warp per row;
 //   finish (every area; one CTA)  increments back in the reference's unknown order; a failed factorisation (not positive definite,
 //          optimize_edges.h:476-485) is booked -- the later stages of this trial skip the area (trial_ok = 0).
-#define WAVE_SOLVE_CTAS 8
+#ifndef WAVE_SOLVE_CTAS
+#define WAVE_SOLVE_CTAS 8      // > 8: non-portable cluster size (tools/variant_bench.py experiments)
+#endif
+#ifndef WAVE_SOLVE_NT
 #define WAVE_SOLVE_NT 1024
+#endif
+#ifndef WAVE_TEAM_MIN_CTAS
+#define WAVE_TEAM_MIN_CTAS (1024 / WAVE_SOLVE_NT)   // resident team CTAs per SM the register budget is set for
+#endif
+#ifndef WAVE_FWD_UNROLL
+#define WAVE_FWD_UNROLL 1      // U > 1: U destination entries per thread and pass in the forward levels (independent load chains)
+#endif
 #define WAVE_TAIL_NT 1024
 
 // Team of an area in the forward / backward kernels: a cluster of WAVE_SOLVE_CTAS x WAVE_SOLVE_NT threads when its levels are wide (many
@@ -351,7 +361,7 @@ __device__ __forceinline__ double wave_contrib(const double *T, int ta, int tb, 
 
 // TEAM: a cluster of WAVE_SOLVE_CTAS CTAs per area (areas with wide levels, list a.big); otherwise one CTA per area (list a.solo)
 template <int P, int OBSK, bool TEAM>
-__global__ void __launch_bounds__(TEAM ? WAVE_SOLVE_NT : WAVE_SOLO_NT) wave_solve_fwd_kernel(const WaveArgs a) {
+__global__ void __launch_bounds__(TEAM ? WAVE_SOLVE_NT : WAVE_SOLO_NT, TEAM ? WAVE_TEAM_MIN_CTAS : 1) wave_solve_fwd_kernel(const WaveArgs a) {
 	const int area = TEAM ? a.big[blockIdx.y] : a.solo[blockIdx.y];
 	WaveArea &s = a.st[area];
 	if (!s.go) return;  // (the same decision in every CTA of the cluster)
@@ -378,6 +388,29 @@ __global__ void __launch_bounds__(TEAM ? WAVE_SOLVE_NT : WAVE_SOLO_NT) wave_solv
 	WT_ADD(0);
 	for (int L = 0; L < L0; L++) {
 		const int e1 = lvl[L + 1].y;
+#if WAVE_FWD_UNROLL > 1
+		if (glane)
+			for (int e = lvl[L].y + gwarp * 3 + wg; e < e1; e += NW * 3 * WAVE_FWD_UNROLL) {
+				int4 rc[WAVE_FWD_UNROLL];
+				int xa[WAVE_FWD_UNROLL], xb[WAVE_FWD_UNROLL];
+				double cur[WAVE_FWD_UNROLL], acc[WAVE_FWD_UNROLL];
+#pragma unroll
+				for (int u = 0; u < WAVE_FWD_UNROLL; u++) {
+					const int f = e + u * NW * 3, g = f < e1 ? f : e;
+					rc[u] = drec[g]; xa[u] = xptr[g]; xb[u] = f < e1 ? xptr[g + 1] : xa[u];
+				}
+#pragma unroll
+				for (int u = 0; u < WAVE_FWD_UNROLL; u++) cur[u] = T[(size_t)rc[u].x * 12 + eo];
+#pragma unroll
+				for (int u = 0; u < WAVE_FWD_UNROLL; u++) acc[u] = wave_contrib(T, rc[u].y, rc[u].z, rc[u].w, wa, wb);
+#pragma unroll
+				for (int u = 0; u < WAVE_FWD_UNROLL; u++)
+					for (int c = xa[u]; c < xb[u]; c++) { const int4 xr = xrec[c]; acc[u] += wave_contrib(T, xr.x, xr.y, xr.z, wa, wb); }
+#pragma unroll
+				for (int u = 0; u < WAVE_FWD_UNROLL; u++)
+					if (e + u * NW * 3 < e1) T[(size_t)rc[u].x * 12 + eo] = cur[u] - acc[u];
+			}
+#else
 		if (glane)
 			for (int e = lvl[L].y + gwarp * 3 + wg; e < e1; e += NW * 3) {
 				const int4 rec = drec[e];
@@ -391,6 +424,7 @@ __global__ void __launch_bounds__(TEAM ? WAVE_SOLVE_NT : WAVE_SOLO_NT) wave_solv
 				}
 				*dp = cur - acc;
 			}
+#endif
 		WT_ADD(3);
 		WAVE_TEAM_SYNC();
 		WT_ADD(4);
@@ -426,6 +460,10 @@ __global__ void __launch_bounds__(WAVE_TAIL_NT) wave_solve_tail_kernel(const Wav
 	double *T = vg.ldl_tiles, *x = T + (size_t)ntiles * 24;
 	const int32_t *tij = vg.ldl_tile_ij, *src = vg.ldl_src;
 	const int nt = (int)blockDim.x, t_ = (int)threadIdx.x;
+#ifdef SRBA_WAVE_TIMERS
+	const int tid = t_;
+#endif
+	WT_DECL;
 	for (int i = t_; i < ntl * 9; i += nt) Tl[i] = 0.0;
 	for (int i = t_; i < r; i += nt) {
 		const int b0 = tail_base(i, r);
@@ -478,6 +516,7 @@ __global__ void __launch_bounds__(WAVE_TAIL_NT) wave_solve_tail_kernel(const Wav
 		}
 		__syncthreads();
 	}
+	WT_ADD(7);
 	{  // W of the last row (its right-hand-side tile only)
 		const double *last = Wbuf + (size_t)((r - 1) & 1) * (r + 1) * 9;
 		if (t_ < 9) Tl[(size_t)(tail_base(r - 1, r) + 1) * 9 + t_] = last[9 + t_];
@@ -504,61 +543,166 @@ __global__ void __launch_bounds__(WAVE_TAIL_NT) wave_solve_tail_kernel(const Wav
 		}
 	}
 	__syncthreads();
+	WT_ADD(8);
 	for (int i = t_; i < 3 * r; i += nt) x[3 * row0 + i] = xs[i];
 }
 
 // x_k = inv(D_k) (y_k - sum_j T(k,j) x_j) down the levels below the tail, one warp per row; the pivot blocks are final here: a block with a
-// non-positive leading minor books the failed factorisation.
-template <int P, int OBSK, bool TEAM>
-__global__ void __launch_bounds__(TEAM ? WAVE_SOLVE_NT : WAVE_SOLO_NT) wave_solve_bwd_kernel(const WaveArgs a, int big_list) {
-	const int area = (TEAM || big_list) ? a.big[blockIdx.y] : a.solo[blockIdx.y];
+// non-positive leading minor books the failed factorisation.  ONE CTA per area (a level has a handful of rows: a cluster would only add
+// barrier latency).  The chain of a level is  level bounds -> row bounds -> column indices -> x  -- four dependent memory round trips when
+// everything sits in global memory, times 80-240 levels.  So the CTA first stages the level bounds, the row bounds and x (the tail's
+// solution; then every level's) in shared memory, and each warp loads the pivot block, the right-hand side and its first 32 tiles + column
+// indices of its row of the NEXT level while the current level is being solved: after a barrier only shared-memory reads of x remain.
+// Levels with few rows (the chain of a dense front: ONE row of 40-70 tiles per level) split each row over 2-4 warps.
+// The levels of such a chain rotate over four groups of warps, each loading its next row four levels ahead (registers).
+// `smem_bytes` = the launch's dynamic shared memory; an area that needs more runs the same loop on the global arrays.
+struct BwdRow {
+	int r, t0, t1, j;
+	double d00, d01, d02, d11, d12, d22, y0, y1, y2, m0, m1, m2, m3, m4, m5, m6, m7, m8;
+};
+template <int P, int OBSK>
+__global__ void __launch_bounds__(WAVE_SOLO_NT) wave_solve_bwd_kernel(const WaveArgs a, int big_list, int smem_bytes) {
+	extern __shared__ double bwd_sm[];
+	__shared__ double bwd_part[3 * (WAVE_SOLO_NT / 32)];
+	const int area = big_list ? a.big[blockIdx.y] : a.solo[blockIdx.y];
 	WaveArea &s = a.st[area];
 	if (!s.go) return;
 	const View &vg = a.views[area];
 	const DevProblem *h = vg.h;
-	const int ntiles = h->ldl_n_tiles, L0 = h->ldl_tail_level;
+	const int ntiles = h->ldl_n_tiles, L0 = h->ldl_tail_level, nx = h->n_dense;
 	const double *T = vg.ldl_tiles;
-	double *x = vg.ldl_tiles + (size_t)ntiles * 24;
+	double *xg = vg.ldl_tiles + (size_t)ntiles * 24;
 	const int2 *rowinfo = reinterpret_cast<const int2 *>(vg.ldl_row);
 	const int32_t *tij = vg.ldl_tile_ij;
 	const int2 *lvl = reinterpret_cast<const int2 *>(vg.ldl_phase);
-	const int tid = (int)(blockIdx.x * blockDim.x + threadIdx.x), NTH = (int)(gridDim.x * blockDim.x);
-	const int lane = tid & 31, gwarp = tid >> 5, NW = NTH >> 5;
+	const int tid = (int)threadIdx.x, NTH = (int)blockDim.x, lane = tid & 31, warp = tid >> 5, NW = NTH >> 5;
+	if (L0 <= 0) return;
+	const int row0 = lvl[L0].x;   // rows below the tail
+	const bool staged = (size_t)nx * 8 + (size_t)row0 * 8 + (size_t)(L0 + 1) * 4 + 16 <= (size_t)smem_bytes;
+	double *x = staged ? bwd_sm : xg;
+	int2 *srow = reinterpret_cast<int2 *>(bwd_sm + nx);
+	int *slvl = reinterpret_cast<int *>(srow + row0);
+	if (staged) {
+		for (int i = 3 * row0 + tid; i < nx; i += NTH) x[i] = xg[i];
+		for (int i = tid; i < row0; i += NTH) srow[i] = rowinfo[2 * i];
+		for (int i = tid; i <= L0; i += NTH) slvl[i] = lvl[i].x;
+		__syncthreads();
+	}
+	auto level_row = [&](int L) -> int { return staged ? slvl[L] : lvl[L].x; };
+	// A level with few rows (the chain of a dense front: one row of 40-70 tiles per level) gives each row to a group of G warps
+	auto group_of = [&](int n_rows) -> int { return 4 * n_rows <= NW ? 4 : (2 * n_rows <= NW ? 2 : 1); };
+	// everything of this warp's share of its first row in level L that does not depend on x
+	auto fetch_row = [&](int r, int G, BwdRow &q) {
+		const int2 ri = staged ? srow[r] : rowinfo[2 * r];
+		q.r = r; q.t0 = ri.x; q.t1 = ri.y;
+		const double *D = T + (size_t)ri.x * 12, *y = T + (size_t)(ri.y - 1) * 12;
+		q.d00 = D[0]; q.d01 = D[4]; q.d02 = D[8]; q.d11 = D[5]; q.d12 = D[9]; q.d22 = D[10];
+		q.y0 = y[0]; q.y1 = y[1]; q.y2 = y[2];
+		const int tl = ri.x + 1 + 32 * (warp % G) + lane;
+		q.j = -1;
+		if (tl < ri.y - 1) {
+			const double *Tr = T + (size_t)tl * 12;
+			q.j = tij[tl] & 0xffff;
+			q.m0 = Tr[0]; q.m1 = Tr[1]; q.m2 = Tr[2]; q.m3 = Tr[4]; q.m4 = Tr[5]; q.m5 = Tr[6]; q.m6 = Tr[8]; q.m7 = Tr[9]; q.m8 = Tr[10];
+		}
+	};
+	// Chain levels (ONE row) rotate over the NW / 4 groups of four warps: level L belongs to group L mod (NW / 4), which loads its row of
+	// level L - NW / 4 as soon as it has finished level L -- several levels of lead over the memory round trip.
+	const int NG = NW / 4, group = warp / 4;
+	BwdRow pre;
+	int pre_L = -1;
+	auto prefetch_chain = [&](int L) {
+		if (L < 0 || L % NG != group) return;
+		const int r0 = level_row(L);
+		if (level_row(L + 1) - r0 != 1) return;
+		fetch_row(r0, 4, pre);
+		pre_L = L;
+	};
+	double *part = reinterpret_cast<double *>(bwd_part);
+	// partial sum_j T(k,j) x_j of this warp's share of the row (all lanes hold it)
+	auto row_partial = [&](const BwdRow &q, int G, double &p0, double &p1, double &p2) {
+		p0 = p1 = p2 = 0;
+		if (q.j >= 0) {
+			const double x0 = x[3 * q.j], x1 = x[3 * q.j + 1], x2 = x[3 * q.j + 2];
+			p0 = q.m0 * x0 + q.m3 * x1 + q.m6 * x2;
+			p1 = q.m1 * x0 + q.m4 * x1 + q.m7 * x2;
+			p2 = q.m2 * x0 + q.m5 * x1 + q.m8 * x2;
+		}
+		for (int tl = q.t0 + 1 + 32 * (G + warp % G) + lane; tl < q.t1 - 1; tl += 32 * G) {   // rows longer than one pass of the group
+			const double *xj = x + 3 * (tij[tl] & 0xffff);
+			const double *Tr = T + (size_t)tl * 12;
+			const double x0 = xj[0], x1 = xj[1], x2 = xj[2];
+			p0 += Tr[0] * x0 + Tr[4] * x1 + Tr[8] * x2;
+			p1 += Tr[1] * x0 + Tr[5] * x1 + Tr[9] * x2;
+			p2 += Tr[2] * x0 + Tr[6] * x1 + Tr[10] * x2;
+		}
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) {
+			p0 += __shfl_xor_sync(0xffffffffu, p0, o); p1 += __shfl_xor_sync(0xffffffffu, p1, o); p2 += __shfl_xor_sync(0xffffffffu, p2, o);
+		}
+	};
+	auto finish_row = [&](const BwdRow &q, double p0, double p1, double p2) {   // one lane
+		const Piv3 pv = piv3(q.d00, q.d01, q.d02, q.d11, q.d12, q.d22);
+		if (pv.bad) s.chol_fail = 1;
+		const double y0 = q.y0 - p0, y1 = q.y1 - p1, y2 = q.y2 - p2;
+		x[3 * q.r + 0] = (pv.c00 * y0 + pv.c01 * y1 + pv.c02 * y2) * pv.idet;
+		x[3 * q.r + 1] = (pv.c01 * y0 + pv.c11 * y1 + pv.c12 * y2) * pv.idet;
+		x[3 * q.r + 2] = (pv.c02 * y0 + pv.c12 * y1 + pv.c22 * y2) * pv.idet;
+	};
+	for (int d = 0; d < NG; d++) prefetch_chain(L0 - 1 - d);
 	WT_DECL;
 	for (int L = L0 - 1; L >= 0; L--) {
-		const int r0 = lvl[L].x, r1 = lvl[L + 1].x;
-		for (int r = r0 + gwarp; r < r1; r += NW) {
-			const int2 ri = rowinfo[2 * r];
-			const int t0 = ri.x, t1 = ri.y;
-			const double *D = T + (size_t)t0 * 12;
-			const double d00 = D[0], d01 = D[4], d02 = D[8], d11 = D[5], d12 = D[9], d22 = D[10];
-			double p0 = 0, p1 = 0, p2 = 0;
-			for (int tl = t0 + 1 + lane; tl < t1 - 1; tl += 32) {
-				const double *xj = x + 3 * (tij[tl] & 0xffff);
-				const double *Tr = T + (size_t)tl * 12;
-				const double x0 = xj[0], x1 = xj[1], x2 = xj[2];
-				p0 += Tr[0] * x0 + Tr[4] * x1 + Tr[8] * x2;
-				p1 += Tr[1] * x0 + Tr[5] * x1 + Tr[9] * x2;
-				p2 += Tr[2] * x0 + Tr[6] * x1 + Tr[10] * x2;
+		const int r0 = level_row(L), r1 = level_row(L + 1), n_rows = r1 - r0;
+		double p0, p1, p2;
+		if (n_rows == 1) {
+			const bool mine = (L % NG == group);
+			if (mine) {
+				if (pre_L != L) fetch_row(r0, 4, pre);
+				row_partial(pre, 4, p0, p1, p2);
+				if (lane == 0) { part[3 * warp] = p0; part[3 * warp + 1] = p1; part[3 * warp + 2] = p2; }
 			}
-#pragma unroll
-			for (int o = 16; o > 0; o >>= 1) {
-				p0 += __shfl_xor_sync(0xffffffffu, p0, o); p1 += __shfl_xor_sync(0xffffffffu, p1, o); p2 += __shfl_xor_sync(0xffffffffu, p2, o);
+			__syncthreads();
+			if (mine) {
+				if (warp % 4 == 0 && lane == 0) {
+					p0 = part[3 * warp]; p1 = part[3 * warp + 1]; p2 = part[3 * warp + 2];
+					for (int g = 1; g < 4; g++) { p0 += part[3 * (warp + g)]; p1 += part[3 * (warp + g) + 1]; p2 += part[3 * (warp + g) + 2]; }
+					finish_row(pre, p0, p1, p2);
+				}
+				prefetch_chain(L - NG);
 			}
-			if (lane == 0) {
-				const Piv3 pv = piv3(d00, d01, d02, d11, d12, d22);
-				if (pv.bad) s.chol_fail = 1;
-				const double *y = T + (size_t)(t1 - 1) * 12;
-				const double y0 = y[0] - p0, y1 = y[1] - p1, y2 = y[2] - p2;
-				x[3 * r + 0] = (pv.c00 * y0 + pv.c01 * y1 + pv.c02 * y2) * pv.idet;
-				x[3 * r + 1] = (pv.c01 * y0 + pv.c11 * y1 + pv.c12 * y2) * pv.idet;
-				x[3 * r + 2] = (pv.c02 * y0 + pv.c12 * y1 + pv.c22 * y2) * pv.idet;
+		} else {
+			const int G = group_of(n_rows);
+			BwdRow q;
+			q.r = -1;
+			if (r0 + warp / G < r1) {
+				fetch_row(r0 + warp / G, G, q);
+				row_partial(q, G, p0, p1, p2);
+			}
+			if (G == 1) {
+				if (q.r >= 0) {
+					if (lane == 0) finish_row(q, p0, p1, p2);
+					for (int r = q.r + NW; r < r1; r += NW) {   // more rows than warps in this level (the wide first levels)
+						fetch_row(r, 1, q);
+						row_partial(q, 1, p0, p1, p2);
+						if (lane == 0) finish_row(q, p0, p1, p2);
+					}
+				}
+			} else {
+				if (q.r >= 0 && lane == 0) { part[3 * warp] = p0; part[3 * warp + 1] = p1; part[3 * warp + 2] = p2; }
+				__syncthreads();
+				if (q.r >= 0 && warp % G == 0 && lane == 0) {
+					p0 = part[3 * warp]; p1 = part[3 * warp + 1]; p2 = part[3 * warp + 2];
+					for (int g = 1; g < G; g++) { p0 += part[3 * (warp + g)]; p1 += part[3 * (warp + g) + 1]; p2 += part[3 * (warp + g) + 2]; }
+					finish_row(q, p0, p1, p2);
+				}
 			}
 		}
 		WT_ADD(5);
-		WAVE_TEAM_SYNC();
+		__syncthreads();
 		WT_ADD(6);
 	}
+	if (staged)
+		for (int i = tid; i < 3 * row0; i += NTH) xg[i] = x[i];
 }
 
 template <int P, int OBSK>
@@ -780,6 +924,7 @@ struct SrbaWaveDims {
 	int n_areas;
 	int max_pairs, max_blocks, max_hess_items, max_obs, max_scalars, max_unk, max_schur2, max_schur3, max_lms, max_edges_S, max_out;
 	int has_lms, n_big, n_solo, max_tail_rows;  // n_big / n_solo: areas with levels below the tail (cluster team / one CTA); largest dense tail (tile rows)
+	int max_bwd_smem;                           // shared memory of the backward kernel (x, row bounds, level bounds), largest area
 };
 
 // Optional CUDA-event timing of the dominant kernel (the cluster-team forward solver) for bench.py's roofline line: a pair of events around
@@ -814,8 +959,12 @@ int wave_run(const WaveArgs &a, const SrbaWaveDims &d, int *h_active_pinned, cud
 	scfg.attrs = sattr;
 	scfg.numAttrs = 1;
 	auto solve_fwd = wave_solve_fwd_kernel<P, OBSK, true>;
+	if (WAVE_SOLVE_CTAS > 8 && cudaFuncSetAttribute(solve_fwd, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return (int)cudaGetLastError();
 	auto solve_tail = wave_solve_tail_kernel<P, OBSK>;
 	const size_t tail_smem = wave_tail_smem_bytes(std::max(1, d.max_tail_rows));
+	auto solve_bwd = wave_solve_bwd_kernel<P, OBSK>;
+	const size_t bwd_smem = (size_t)std::min(std::max(d.max_bwd_smem, 16), 200 * 1024);   // larger areas run the backward levels on the global arrays
+	if (cudaFuncSetAttribute(solve_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem) != cudaSuccess) return (int)cudaGetLastError();
 	if (cudaFuncSetAttribute(solve_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem) != cudaSuccess) return (int)cudaGetLastError();
 	cudaMemsetAsync(a.big + n, 0, sizeof(int), st);
 	cudaMemsetAsync(a.solo + n, 0, sizeof(int), st);
@@ -879,8 +1028,8 @@ int wave_run(const WaveArgs &a, const SrbaWaveDims &d, int *h_active_pinned, cud
 		if (both) { cudaEventRecord(ev_fork, st); cudaStreamWaitEvent(side, ev_fork, 0); }
 		// The back-substitution has at most a handful of rows per level (one warp each): a cluster only adds barrier latency there, so the
 		// wide areas run it with ONE CTA as well (CTA barriers, all of them resident at once) -- on the side stream, next to the solo areas.
-		if (d.n_solo) { wave_solve_bwd_kernel<P, OBSK, false><<<dim3(1, (unsigned)d.n_solo, 1), WAVE_SOLO_NT, 0, st>>>(a, 0); nl++; }
-		if (d.n_big) { wave_solve_bwd_kernel<P, OBSK, false><<<dim3(1, (unsigned)d.n_big, 1), WAVE_SOLO_NT, 0, scfg.stream>>>(a, 1); nl++; }
+		if (d.n_solo) { solve_bwd<<<dim3(1, (unsigned)d.n_solo, 1), WAVE_SOLO_NT, bwd_smem, st>>>(a, 0, (int)bwd_smem); nl++; }
+		if (d.n_big) { solve_bwd<<<dim3(1, (unsigned)d.n_big, 1), WAVE_SOLO_NT, bwd_smem, scfg.stream>>>(a, 1, (int)bwd_smem); nl++; }
 		if (both) { cudaEventRecord(ev_join, side); cudaStreamWaitEvent(st, ev_join, 0); }
 		wave_solve_finish_kernel<P, OBSK><<<n, 256, 0, st>>>(a);
 		nl++;
