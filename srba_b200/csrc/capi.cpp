@@ -665,8 +665,23 @@ void symbolic_levels(const srba_problem_t &p, int P, TileSymbolic &sy, bool debu
 	//   [n_dst + 1 pointers into the further contributions, padded to 4 ints] [{tile(k,a), tile(k,b), diagonal tile of row k, 0} ...]
 	// One pass: the first contribution of a destination writes its record; the rare further ones go to a side list that is bucketed by
 	// destination entry afterwards (stable: ascending source row is kept).
-	std::vector<int32_t> rec, ex, slot(ntiles, -1), touched;
-	rec.reserve(16 * (size_t)ntiles);
+	// (the records are written straight into sy.upd, the pointer and side lists are appended behind them: no second copy of the 16 n_dst bytes)
+	std::vector<int32_t> rec_dbg, ex, slot(ntiles, -1), touched;
+	std::vector<int32_t> &rec = debug_format ? rec_dbg : sy.upd;
+	rec.clear();
+	{  // exact number of destination entries is not known yet: an upper bound on the contributions, capped, avoids most regrowth
+		size_t bound = 0;
+		for (int k = 0; k < ntr; k++) { const size_t m = (size_t)(sy.rs[k + 1] - sy.rs[k]) - 1; bound += m * (m + 1) / 2; }
+		rec.reserve(5 * std::min<size_t>(bound, (size_t)4 << 20) + 64);   // records + pointers + side list
+	}
+	// Destination look-up.  Row i holds every column j >= i of row k (fill).  Small systems: a dense (row, column) -> tile table, one
+	// look-up per contribution; large ones: both lists ascend, so a merge walk along row i finds the tiles.
+	const bool dense_map = (size_t)ntr * ntc <= ((size_t)16 << 20);
+	std::vector<int32_t> tile_of;
+	if (dense_map) {
+		tile_of.resize((size_t)ntr * ntc);   // only entries of stored tiles are ever read
+		for (int t = 0; t < ntiles; t++) tile_of[(size_t)(sy.tile_ij[t] >> 16) * ntc + (sy.tile_ij[t] & 0xffff)] = t;
+	}
 	sy.phase.assign(2 * (size_t)(nlev + 1), 0);
 	int r = 0, ne = 0;
 	for (int L = 0; L < nlev; L++) {
@@ -679,10 +694,14 @@ void symbolic_levels(const srba_problem_t &p, int P, TileSymbolic &sy, bool debu
 			const int32_t td = sy.rs[k], k_end = sy.rs[k + 1];
 			for (int a = td + 1; a < k_end - 1; a++) {  // tile (k,i): off-diagonal, not the right-hand side
 				const int i = sy.tile_ij[a] & 0xffff;
-				int32_t d = sy.rs[i];   // row i holds every column j >= i of row k (fill): both lists ascend, so one merge walk finds the tiles
+				int32_t d = sy.rs[i];
+				const int32_t *row_i = dense_map ? &tile_of[(size_t)i * ntc] : nullptr;
 				for (int b = a; b < k_end; b++) {           // tile (k,j), j >= i, right-hand side included
-					const int32_t key = (i << 16) | (sy.tile_ij[b] & 0xffff);
-					while (sy.tile_ij[d] != key) d++;
+					if (dense_map) d = row_i[sy.tile_ij[b] & 0xffff];
+					else {
+						const int32_t key = (i << 16) | (sy.tile_ij[b] & 0xffff);
+						while (sy.tile_ij[d] != key) d++;
+					}
 					if (slot[d] < 0) {
 						slot[d] = ne++;
 						touched.push_back(d);
@@ -715,8 +734,8 @@ void symbolic_levels(const srba_problem_t &p, int P, TileSymbolic &sy, bool debu
 			extra[4 * w] = ex[4 * q + 1]; extra[4 * w + 1] = ex[4 * q + 2]; extra[4 * w + 2] = ex[4 * q + 3]; extra[4 * w + 3] = 0;
 		}
 	}
-	sy.upd.clear();
 	if (debug_format) {  // srba_b200_debug_level_schedule: [dst | contribution pointer | 1 pad | (tile(k,a), tile(k,b)) x n_contrib]
+		sy.upd.clear();
 		sy.upd.reserve(2 * nd + 2 + 2 * (nd + n_extra));
 		for (size_t e = 0; e < nd; e++) sy.upd.push_back(rec[4 * e]);
 		for (size_t e = 0; e <= nd; e++) sy.upd.push_back((int32_t)(e + (size_t)xptr[e]));   // first + further contributions before entry e
@@ -726,8 +745,7 @@ void symbolic_levels(const srba_problem_t &p, int P, TileSymbolic &sy, bool debu
 			for (int32_t c = xptr[e]; c < xptr[e + 1]; c++) { sy.upd.push_back(extra[4 * (size_t)c]); sy.upd.push_back(extra[4 * (size_t)c + 1]); }
 		}
 	} else {
-		sy.upd.resize(4 * nd + xlen + 4 * n_extra);
-		std::memcpy(sy.upd.data(), rec.data(), 4 * nd * sizeof(int32_t));
+		sy.upd.resize(4 * nd + xlen + 4 * n_extra);   // (the 4 nd record ints are already in place)
 		std::memcpy(sy.upd.data() + 4 * nd, xptr.data(), xlen * sizeof(int32_t));
 		if (n_extra) std::memcpy(sy.upd.data() + 4 * nd + xlen, extra.data(), 4 * n_extra * sizeof(int32_t));
 	}
