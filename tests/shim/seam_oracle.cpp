@@ -134,6 +134,21 @@ static int run(const orc_params_t &prm, std::istream &f, bool run_gpu) {
 	CHECK(same(p.S_term_rowblk, q.S_term_rowblk, p.n_S_terms) && same(p.S_term_colblk, q.S_term_colblk, p.n_S_terms));
 	std::printf("FLATTEN identical: n_p %d n_f %d n_obs %d blkA %d blkF %d pairs %d HAp %d HApf %d S %d S_terms %d\n", p.n_unk_edges, p.n_unk_lms, p.n_obs, p.n_blkA, p.n_blkF,
 	            p.n_pairs, p.n_HAp, p.n_HApf, p.n_S, p.n_S_terms);
+	{  // feedback_user_iteration replay on a synthetic trace (no device): accepted trials only, iter = number of accepted steps before
+		srba_result_t fake;
+		std::memset(&fake, 0, sizeof(fake));
+		double tr[5 * 6] = {1e-3, 1, 0.8, 90.0, 1, 0,   1e-3, 0, 0, 0, 0, 0,   4e-3, 1, -0.1, 95.0, 0, 0,   1.6e-2, 1, 0.5, 40.0, 1, 1,   5e-3, 1, 0.9, 10.0, 1, 0};
+		fake.trace = tr; fake.trace_len = 5; fake.trace_cap = 5;
+		fake.stats.total_sqr_error_init = 100.0;
+		g_feedback.clear();
+		srba_b200_shim::replay_feedback(&record_feedback, *F, fake);
+		CHECK(g_feedback.size() == 4);
+		CHECK(g_feedback[0].iter == 0 && g_feedback[0].err == 100.0 && g_feedback[1].iter == 0 && g_feedback[1].err == 90.0);
+		CHECK(g_feedback[2].iter == 1 && g_feedback[2].err == 40.0 && g_feedback[3].iter == 2 && g_feedback[3].err == 10.0);
+		CHECK(std::fabs(g_feedback[3].rmse - std::sqrt(10.0 / p.n_total_obs_rows)) < 1e-15);
+		srba_b200_shim::replay_feedback((void (*)(unsigned int, const double, const double))NULL, *F, fake);   // no callback installed: nothing happens
+		g_feedback.clear();
+	}
 	if (run_gpu) {
 		srba_result_t res = F->make_result_buffers(S, 256);   // with the per-trial trace: feedback_user_iteration is replayed from it
 		const int rc = srba_b200_optimize(&F->p, &res);
